@@ -1,0 +1,86 @@
+"""Functional fp32 restatement of MetNet3 (/root/reference/src/metnet3.py:86-430).
+
+Test infrastructure only (see oracle/__init__.py).  Also used as the timed CPU
+baseline ("port") by bench.py, because the Python reference itself cannot travel
+to the GPU box.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .maxvit_oracle import maxvit_forward
+from .synth import GridConfig
+
+
+def chan_layer_norm(x, g, b, eps: float = 1e-5):
+    """metnet3.py:94-104: biased variance, clamp(min=eps).rsqrt() (NOT var+eps)."""
+    var = x.var(dim=1, unbiased=False, keepdim=True)
+    mean = x.mean(dim=1, keepdim=True)
+    return (x - mean) * var.clamp(min=eps).rsqrt() * g + b
+
+
+def resnet_block(x, cond, sd, p: str):
+    """metnet3.py:129-162.  FiLM (scale+1, shift) only in block1; cond MLP is ReLU->Linear."""
+    ss = F.linear(F.relu(cond), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])
+    scale, shift = ss.chunk(2, dim=1)
+    h = F.conv2d(x, sd[p + "block1.proj.weight"], sd[p + "block1.proj.bias"], padding=1)
+    h = chan_layer_norm(h, sd[p + "block1.norm.g"], sd[p + "block1.norm.b"])
+    h = F.relu(h * (scale[:, :, None, None] + 1) + shift[:, :, None, None])
+    h = F.conv2d(h, sd[p + "block2.proj.weight"], sd[p + "block2.proj.bias"], padding=1)
+    h = F.relu(chan_layer_norm(h, sd[p + "block2.norm.g"], sd[p + "block2.norm.b"]))
+    if (p + "res_conv.weight") in sd:
+        x = F.conv2d(x, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"])
+    return h + x
+
+
+def prepare_input(x, timestamps, sd, cfg: GridConfig):
+    """metnet3.py:354-416 -> (net_in (N,c_in,HP,WP), cond (N,lead_emb)), N = B*L.
+
+    * PM2.5 channels {4,10,16,22} of every time step standardised (:361-380)
+    * every sample replicated L times, lead-minor: n = b*L + l (:383, :407)
+    * zero pad to multiples of 14 (:384)
+    * time channels: lead embedding (lead_emb) ++ the *scrambled* model-time embedding:
+      the three (N,1) embeddings are concatenated on dim 0 and viewed as (N,3), so row n
+      holds flat[3n:3n+3] of [month_0..month_{N-1}, day_0.., hour_0..] (:395-401, quirk Q1)
+    * timestamps are taken at hard-coded time index 6 (:405, quirk Q2)
+    """
+    B, L = x.shape[0], cfg.L
+    x = x.clone()
+    pm = torch.tensor([4, 10, 16, 22])
+    x[:, :, pm] = (x[:, :, pm] - cfg.pm25_mean) / cfg.pm25_std
+    x = x.repeat_interleave(L, dim=0)
+    x = F.pad(x, cfg.pads, value=0.0)
+    N, HP, WP = B * L, x.shape[-2], x.shape[-1]
+    x = x.reshape(N, -1, HP, WP)
+    ts = timestamps[:, 6, :].repeat_interleave(L, dim=0)
+    lead = torch.arange(1, L + 1).repeat(B)
+    cond = sd["condition_lead_time.weight"][lead]
+    mt = ts[:, 1:4].int().long()                                   # month, day, hour
+    flat = torch.cat([sd[f"condition_model_time.{i}.weight"][mt[:, i]] for i in range(3)], dim=0)
+    t_emb = torch.cat([cond, flat.reshape(N, -1)], dim=1)          # (N, lead_emb + 3*time_emb)
+    x = torch.cat([x, t_emb[:, :, None, None].expand(-1, -1, HP, WP)], dim=1)
+    return x, cond
+
+
+def metnet3_forward(x, timestamps, sd, cfg: GridConfig, *, training: bool = False, return_features: bool = False):
+    """MetNet3.forward (metnet3.py:339-430): (B,T,C,H,W), (B,*,4) -> (B,L,H,W) fp32."""
+    B = x.shape[0]
+    h, cond = prepare_input(x, timestamps, sd, cfg)
+    for bi in range(cfg.resnet_depth):
+        h = resnet_block(h, cond, sd, f"resnet1.blocks.{bi}.")
+    feats = {"resnet1": h}
+    h = F.max_pool2d(h, 2, 2)
+    h = maxvit_forward(h, cond, sd, prefix="vit.", depth=cfg.vit_depth, heads=cfg.heads,
+                       window=cfg.window, num_reg=cfg.num_reg, training=training)
+    feats["vit"] = h
+    h = F.conv_transpose2d(h, sd["up.weight"], sd["up.bias"], stride=2)
+    feats["up"] = h
+    for bi in range(cfg.resnet_depth):
+        h = resnet_block(h, cond, sd, f"resnet2.blocks.{bi}.")
+    feats["resnet2"] = h
+    pl, pr, pt, pb = cfg.pads
+    h = h[..., pt:h.shape[-2] - pb, pl:h.shape[-1] - pr]           # unpad (:335-337), pads > 0 here
+    out = F.conv2d(h, sd["classifier_pm25.weight"], sd["classifier_pm25.bias"])
+    out = out.squeeze(1).reshape(B, cfg.L, cfg.H, cfg.W) * cfg.pm25_std + cfg.pm25_mean
+    return (out, feats) if return_features else out

@@ -1,0 +1,73 @@
+"""The oracle (oracle/) against the golden fixtures generated from the real reference."""
+import pytest
+import torch
+
+from oracle import synth
+from oracle.maxvit_oracle import (attention, block_pixel_index, grid_pixel_index, maxvit_forward,
+                                  rel_pos_indices)
+from oracle.metnet3_oracle import metnet3_forward
+from oracle.focal_r_oracle import focal_r, focal_r_grad
+
+
+def test_rel_pos_indices_bit_exact(golden):
+    g = golden("index_golden.pt")
+    for (w, r) in ((7, 4), (8, 1), (4, 2)):
+        assert torch.equal(rel_pos_indices(w, r), g[f"rel_pos_w{w}_r{r}"])
+
+
+@pytest.mark.parametrize("H,W,w", [(42, 35, 7), (14, 14, 7), (28, 21, 7), (259, 259, 7), (16, 24, 8)])
+def test_partition_indices_bit_exact(golden, H, W, w):
+    g = golden("index_golden.pt")
+    assert torch.equal(block_pixel_index(H, W, w).int(), g[f"block_{H}x{W}_w{w}"])
+    assert torch.equal(grid_pixel_index(H, W, w).int(), g[f"grid_{H}x{W}_w{w}"])
+
+
+def test_attention_matches_reference(golden):
+    f = golden("attention_small.pt")
+    spec = {k[len("layers.0.1."):]: v for k, v in
+            synth.maxvit_spec(f["dim"], 1, 2, f["heads"], f["dim_head"], f["window"], 4, 0.25, f["num_reg"]).items()
+            if k.startswith("layers.0.1.")}
+    sd = synth.make_state_dict(spec, seed=f["seed"])
+    y = attention(f["x"], f["cond"], sd, "", heads=f["heads"], window=f["window"], num_reg=f["num_reg"])
+    torch.testing.assert_close(y, f["y"], rtol=1e-5, atol=1e-5)
+
+
+def test_maxvit_matches_reference(golden):
+    f = golden("maxvit_small.pt")
+    sd = synth.make_state_dict(synth.maxvit_spec(f["dim"], f["depth"], 2, f["heads"], f["dim_head"],
+                                                 f["window"], 4, 0.25, f["num_reg"]), seed=f["seed"])
+    y = maxvit_forward(f["x"], f["cond"], sd, depth=f["depth"], heads=f["heads"], window=f["window"],
+                       num_reg=f["num_reg"])
+    torch.testing.assert_close(y, f["y"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["metnet3_tiny.pt", "metnet3_small128.pt", "metnet3_12hr_b1.pt"])
+def test_metnet3_matches_reference(golden, name):
+    f = golden(name)
+    cfg = synth.GridConfig(**f["cfg"])
+    spec = synth.metnet3_spec(cfg)
+    assert set(spec.keys()) == set(f["keys"])          # state-dict contract
+    sd = synth.make_state_dict(spec, seed=f["weight_seed"])
+    x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
+    y = metnet3_forward(x, ts, sd, cfg)
+    rel = ((y - f["y"]).abs().max() / f["y"].abs().max()).item()
+    assert rel < 1e-4, rel
+
+
+def test_12hr_param_count(golden):
+    f = golden("metnet3_12hr_b1.pt")
+    assert f["n_params"] == 3_346_145
+    assert len(f["keys"]) == 93
+
+
+def test_focal_r_properties():
+    g = torch.Generator().manual_seed(0)
+    p, t = torch.rand(4, 3, 9, 7, generator=g) * 50, torch.rand(4, 3, 9, 7, generator=g) * 50
+    assert focal_r(p, p).item() == 0.0
+    l1 = (p - t).abs().mean()
+    assert 0 < focal_r(p, t) < l1                      # weight (2*sigmoid-1) in (0,1)
+    # analytic gradient of |e|*(2s(b|e|)-1): sign(e)*[(2s-1) + 2 b |e| s (1-s)] / numel
+    e = p - t
+    s = torch.sigmoid(0.2 * e.abs())
+    ga = torch.sign(e) * ((2 * s - 1) + 2 * 0.2 * e.abs() * s * (1 - s)) / e.numel()
+    torch.testing.assert_close(focal_r_grad(p, t), ga, rtol=1e-5, atol=1e-8)
