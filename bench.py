@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark: MaxViT grid fields/sec of the 12hr MetNet3 model (BASELINE.json configs[1]:
+inference, bf16, batch 64 synthetic CMAQ grids = 768 fields per step per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+* a "step" = one forward of `MetNet3` over one batch of B=64 synthetic CMAQ tensors (64*12 = 768 grid fields)
+* `value`  = fields/s with the inputs already resident in HBM (CUDA events, max over ranks)
+* `e2e`    = same metric through the public nn.Module call with HOST (pinned) inputs: H2D of x/timestamps and D2H of
+             the predictions inside the timed region
+* `roofline` = the dominant kernel (3x3-conv implicit GEMM + LN epilogue, tcgen05), from CUDA events recorded
+             around its launches inside the timed region; algorithmic FLOPs = 2*84*70*128*1152 per field per launch
+* `cpu_baseline` = the CPU oracle port of the reference (oracle/, plain PyTorch fp32) on the host cores, B=1
+* `--impl reference` times that same CPU port as the reference arm (the Python reference cannot travel to the box)
+N>1: one process per GPU (torchrun), batch-sharded, no data-path collective (inference) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC, UNIT = "grid_fields_per_sec", "fields/s"
+CONV_FLOPS_PER_FIELD = 2.0 * 84 * 70 * 128 * 1152          # algorithmic: unpadded-frame pixels x Cout x 9*Cin x 2
+FWD_GFLOP_PER_FIELD_REF = 25.864                            # SURVEY F8 (reference graph, no lead-time dedup)
+FWD_GFLOP_PER_FIELD_EXEC = 17.516                           # with the stem computed once per sample (H5)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_forward_time(batch=1, repeats=3, threads=None):
+    """time the CPU oracle port of the reference forward (fp32, eval) -> (best seconds, threads)"""
+    from oracle import synth
+    from oracle.metnet3_oracle import metnet3_forward
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = synth.CFG_12HR
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=0)
+    x, ts, _ = synth.make_inputs(cfg, batch, seed=1234)
+    best = float("inf")
+    with torch.no_grad():
+        metnet3_forward(x, ts, sd, cfg)                      # warm-up
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            metnet3_forward(x, ts, sd, cfg)
+            best = min(best, time.perf_counter() - t0)
+    return best, threads
+
+
+def run_reference(args, rank, world):
+    """reference arm: the reference's CPU implementation of the path (oracle port) on the host cores"""
+    if rank != 0:
+        return
+    from oracle import synth
+    from oracle.metnet3_oracle import metnet3_forward
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = synth.CFG_12HR
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=0)
+    bs = 1                                                   # bounded sample: one CMAQ tensor (12 fields) per step
+    x, ts, _ = synth.make_inputs(cfg, bs, seed=1234)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            metnet3_forward(x, ts, sd, cfg)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            metnet3_forward(x, ts, sd, cfg)
+        dt = time.perf_counter() - t0
+    value = bs * cfg.L * args.steps / dt
+    sample = f"B={bs} synthetic CMAQ tensor (12 fields) per step, fp32, eval, {threads} torch CPU threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "12hr MetNet3/MaxViT forward (BASELINE configs[1] model), bounded CPU sample", "batch": bs,
+                   "fields_per_step": bs * cfg.L},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="CMAQ samples per GPU per step (x12 lead times = fields)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="print a per-entry-point time breakdown (rank 0)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from oracle import synth                                  # synthetic weights / inputs only (no oracle compute here)
+    from vit_grid_model_b200 import MetNet3, _lib
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+
+    cfg = synth.CFG_12HR
+    B, L = args.batch, cfg.L
+    model = MetNet3(**cfg.metnet3_kwargs())
+    model.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), strict=True)
+    model = model.to(dev).eval().set_precision(args.precision)
+    x, ts, _ = synth.make_inputs(cfg, B, seed=1234 + rank)    # every rank has its own shard of CMAQ time steps
+    x_host, ts_host = x.pin_memory(), ts.pin_memory()
+    x_dev, ts_dev = x_host.to(dev), ts_host.to(dev)
+    y_host = torch.empty(B, L, cfg.H, cfg.W, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def step_resident():
+        return model(x_dev, timestamps=ts_dev)
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        td = ts_host.to(dev, non_blocking=True)
+        y = model(xd, timestamps=td)
+        y_host.copy_(y, non_blocking=True)
+        return y
+
+    with torch.no_grad():
+        # ---------------- device-resident throughput
+        for _ in range(W):
+            step_resident()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launch_count()
+        _lib.TRACE = []
+        with ClockSampler(local) as clk:
+            e0.record()
+            for _ in range(args.steps):
+                step_resident()
+            e1.record()
+            barrier()
+        trace, _lib.TRACE = _lib.TRACE, None
+        launches = (_lib.launch_count() - launches0) // args.steps
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # ---------------- end to end (host buffers in, host predictions out)
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    fields = world * B * L * args.steps
+    value = fields / (ms_total * 1e-3)
+    e2e_value = fields / (ms_e2e * 1e-3)
+
+    # ---------------- per-entry-point breakdown + roofline of the dominant kernel (events from the timed region)
+    per = {}
+    for name, tag, a, b in trace:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    conv_ms = per.get("vg_conv3x3_ln_fwd", [])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # sustained: the kernel is timed inside a long step
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("conv3x3_ln_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = None
+    if conv_ms and args.precision == "bf16":
+        avg_ms = sum(conv_ms) / len(conv_ms)
+        achieved = CONV_FLOPS_PER_FIELD * B * L / (avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": "gemm_tc_kernel<EPI_CONV_LN> (3x3 conv 128->128 implicit GEMM + ChanLN/FiLM/ReLU/residual)",
+                    "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": traffic, "launches_per_step": len(conv_ms) // args.steps, "avg_launch_ms": avg_ms,
+                    "peak_source": peak_src,
+                    "share_of_step": sum(conv_ms) / (e0.elapsed_time(e1) if False else ms_total)}
+
+    if rank == 0:
+        if args.trace:
+            tot = sum(sum(v) for v in per.values())
+            for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+                print(f"# {name:24s} calls/step {len(v) // args.steps:3d}  ms/step {sum(v) / args.steps:9.3f}  {100 * sum(v) / tot:5.1f}%", file=sys.stderr)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, threads = cpu_port_forward_time(batch=1, repeats=3)
+            cpu = {"value": L / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"oracle port of the reference forward, B=1 (12 fields), fp32 eval, best of 3 after 1 warm-up, {threads} torch threads, {sec:.3f} s/forward"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: 12hr MetNet3/MaxViT inference, batch 64 synthetic CMAQ grids per GPU (768 fields/step/GPU)",
+                       "batch_per_gpu": B, "fields_per_step": world * B * L, "input_shape": [B, cfg.T, cfg.C, cfg.H, cfg.W],
+                       "l2": "inputs (844 MB) and every activation exceed the 126 MB L2", "parallelism": f"batch-sharded x{world}, no collective",
+                       "gflop_per_field_reference_graph": FWD_GFLOP_PER_FIELD_REF, "gflop_per_field_executed": FWD_GFLOP_PER_FIELD_EXEC,
+                       "lead_time_dedup": True},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + ts_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_tflops_executed": value * FWD_GFLOP_PER_FIELD_EXEC / 1e3,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

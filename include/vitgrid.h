@@ -1,0 +1,153 @@
+/* vitgrid.h -- C ABI of libvitgrid.so: the sm_100a (B200) kernels behind the MaxViT / MetNet3 hot path of
+ * jhsk777/VIT-Grid-Model.
+ *
+ * The reference has no FFI layer (it is pure PyTorch); its boundary is the nn.Module API
+ * (src/maxvit.py:224-341, src/metnet3.py:191-430).  These entry points are what a binding for that path
+ * would call; each one names the reference lines it replaces.  The Python host side
+ * (vit-grid-model_b200/{maxvit,metnet3}.py) binds them with ctypes and keeps the reference's nn.Module API.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; `stream` is a cudaStream_t passed as void*
+ *  - dtype: 0 = bf16 activations/weights (tcgen05 tensor-core path), 1 = fp32 (SIMT FFMA path, "fp32 mode")
+ *  - functions never allocate, never synchronise and never touch the default stream; workspaces are
+ *    caller-provided; return 0 on success, non-zero on error (message via vg_last_error())
+ *  - there is NO CPU fallback: on a device that is not sm_100 every launch fails loudly
+ *
+ * Layouts
+ *  - "PG" (padded grid): a set of N frames of HP x WP pixels, channels-last, with one shared zero column
+ *    between pixel rows and one shared zero row between frames:
+ *        flat pixel q = (n*(HP+1) + h + 1)*(WP+1) + (w+1);   buffer = vg_pg_pixels(N,HP,WP) * C elements
+ *    (a 3x3/pad-1 convolution becomes a GEMM over 9 row-shifted views of the same 2-D [q][C] tensor)
+ *  - "CL" (channels-last): plain (N, H, W, C)
+ */
+#ifndef VITGRID_H_
+#define VITGRID_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VG_API __attribute__((visibility("default")))
+#else
+#define VG_API
+#endif
+
+#define VG_DTYPE_BF16 0
+#define VG_DTYPE_FP32 1
+
+VG_API int vg_version(void);
+VG_API const char* vg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
+VG_API long long vg_launch_count(void);
+/* 0 when the current CUDA device is compute capability 10.x; error otherwise */
+VG_API int vg_device_check(void);
+/* number of flat pixels (rows of the [q][C] matrix) of a PG buffer */
+VG_API long long vg_pg_pixels(int N, int HP, int WP);
+
+/* metnet3.py:356-387 -- PM2.5 standardisation of channels {4,10,16,22}, zero pad to the HPxWP frame, NCHW(T*C)
+ * -> PG with Cpad channels (zeros above T*C).  x is fp32 (B,T,C,H,W) with element strides xstride[5] (HOST
+ * array).  The L-fold lead-time replication (:383) is not materialised. */
+VG_API int vg_prepare_fwd(int dtype, const float* x, const long long* xstride, int B, int T, int C, int H, int W,
+                   int pad_top, int pad_left, int HP, int WP, int Cpad, float pm_mean, float pm_std, void* out,
+                   void* stream);
+
+/* metnet3.py:389-416 -- lead-time / model-time embeddings (with the reference's dim-0 concat quirk and
+ * hard-coded time index 6), and their analytic contribution to the first 3x3 conv (9 border cases) and to
+ * res_conv: temb (N,le+3te), cond (N,le), tt (N,9,Cout), tres (N,Cout); N = B*L, all fp32.
+ * ts: fp32 timestamps with element strides (ts_sB, ts_sT, ts_sF); w3/w1: the ORIGINAL fp32 conv weights
+ * (Cout,c_in,3,3)/(Cout,c_in,1,1); c_data = T*C (index of the first time channel). */
+VG_API int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long long ts_sF, int B, int L, int le,
+                      int te, const float* emb_lead, const float* emb_month, const float* emb_day,
+                      const float* emb_hour, const float* w3, const float* w1, int c_in, int c_data, int Cout,
+                      float* temb, float* cond, float* tt, float* tres, void* stream);
+
+/* metnet3.py:140-143 (pre_relu=1, W1=NULL) and maxvit.py:130-135 (Linear->SiLU->Linear): per-field
+ * conditioning vectors, fp32.  out (N,hid) if W1 is NULL else (N,od). */
+VG_API int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu, const float* W0, const float* b0,
+                    int hid, const float* W1, const float* b1, int od, float* out, void* stream);
+
+/* Shifted-row GEMM with a plain epilogue: out[m][n] = act(acc*scale[n]+shift[n] | acc+bias[n]) (+res[m][n]),
+ * acc = sum_tap sum_c A[m+shift[tap]][c] * Wt[n][tap*Ca+c].   Covers nn.Conv2d 1x1 + BatchNorm(eval) + GELU
+ * (maxvit.py:88-90, 95-96), nn.Linear to_qkv (maxvit.py:139) and the raw 3x3 stem conv (ntaps=9).
+ * A: [rowsA][Ca]; Wt: [Ntot*(batches)][ntaps*Ca]; tap_shift: HOST int[ntaps]; act: 0 none, 1 GELU, 2 ReLU.
+ * rows_per_batch>0 selects per-batch weights (Wt rows advance by b_rows_per_batch every rows_per_batch rows).
+ * out_f32=1 stores fp32 regardless of dtype.  scratch (fp32, M*Ntot) is used by fp32 mode only. */
+VG_API int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* Wt, int Ntot, int ntaps,
+                const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
+                const float* bias, const float* scale, const float* shift, int act, const void* res,
+                long long ldres, void* out, long long ldo, int out_f32, float* scratch, long long scratch_elems,
+                void* stream);
+
+/* metnet3.py:110-126 Block = Conv2d 3x3 (pad 1) -> ChanLayerNorm (var.clamp(eps).rsqrt) -> optional FiLM
+ * x*(scale+1)+shift -> ReLU, plus the ResnetBlock residual add (:162) when res != NULL.  x,out,res: PG
+ * layout (N,HP,WP,C=128); Wt: [128][9*Ca] tap-major (ky,kx) then channel; film: (N,256) fp32 or NULL. */
+VG_API int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
+                      const float* ln_b, float ln_eps, const float* film, const void* res, void* out, int N,
+                      int HP, int WP, float* scratch, long long scratch_elems, void* stream);
+
+/* dedup'd first block (metnet3.py:383-418): raw3/rawres are the per-SAMPLE stem 3x3 / res_conv 1x1 GEMM
+ * outputs (fp32, PG over B frames); per FIELD n=b*L+l adds bias + analytic time term, ChanLayerNorm, FiLM, ReLU
+ * -> h1 (PG over N frames) and res = rawres + bias1 + tres (the ResnetBlock residual). */
+VG_API int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                       const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                       const float* film, int B, int L, int HP, int WP, void* h1, void* res, void* stream);
+
+/* metnet3.py:86,419 -- MaxPool2d(2,2): PG (N,HP,WP,C) -> CL (N,HP/2,WP/2,C) */
+VG_API int vg_pool2_fwd(int dtype, const void* in, void* out, int N, int HP, int WP, int C, void* stream);
+
+/* maxvit.py:91-93 -- depthwise 3x3 + BatchNorm(eval, folded into scale/shift) + GELU on CL (N,H,W,C);
+ * w9: fp32 [9][C]; psum: fp32 (N,H,C) per-row channel sums for the squeeze-excite mean. */
+VG_API int vg_dw3x3_bnact_fwd(int dtype, const void* in, const float* w9, const float* scale, const float* shift,
+                       void* out, float* psum, int N, int H, int W, int C, void* stream);
+
+/* maxvit.py:38-48 -- squeeze-excite gate from the row sums: gate (N,C) fp32 */
+VG_API int vg_se_gate_fwd(const float* psum, int N, int H, int W, const float* W1, const float* W2, int C, int se,
+                   float* gate, void* stream);
+/* x *= gate (in place), CL (N,HW,C) */
+VG_API int vg_se_scale_fwd(int dtype, void* x, const float* gate, int N, long long HW, int C, void* stream);
+
+/* maxvit.py:298-308 / 322-332 + 176-187 -- partition (mode 0 block, 1 grid) folded into addressing, register
+ * tokens prepended (reg: fp32 [R][C] shared or [N][R][C] per field), LayerNorm (no affine), FiLM (film: fp32
+ * (N,2C) = gamma|beta)  ->  tokens [(N*nwin*S)][C]. */
+VG_API int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, int N,
+                       int Hl, int Wl, int C, int win, int R, int grid_mode, float ln_eps, void* tokens,
+                       void* stream);
+
+/* maxvit.py:195-215 -- per (window, head): q,k RMSNorm (F.normalize * sqrt(d) * gamma), QK^T + rel-pos bias
+ * (table (2w-1)^2+1 x heads, fp32), softmax, PV.  qkv [(Nw*S)][3*heads*dh] -> out [(Nw*S)][heads*dh]. */
+VG_API int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma,
+                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out,
+                     void* stream);
+
+/* maxvit.py:218-219 + 310/334 + 312-319/336-340 -- to_out projection, residual add and inverse partition:
+ * window tokens are scattered back to CL x_out (N,Hl,Wl,C) = proj + x_in; register-token rows go to reg_out
+ * (fp32 [Nw][R][C] = proj + reg_in) when reg_out != NULL (block attention) and are dropped otherwise. */
+VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, const void* x_in, const float* reg_in,
+                    int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
+                    int grid_mode, float* scratch, long long scratch_elems, void* stream);
+
+/* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */
+VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);
+
+/* metnet3.py:88-89,421 -- ConvTranspose2d(k=2,s=2) as GEMM + depth-to-space: CL (N,Hl,Wl,C) -> PG (N,2Hl,2Wl,C).
+ * Wt: [4*C][C], row (di*2+dj)*C+co = weight[ci][co][di][dj]. */
+VG_API int vg_convT2_fwd(int dtype, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl,
+                  int C, float* scratch, long long scratch_elems, void* stream);
+
+/* metnet3.py:424-430 -- unpad, Conv2d 1x1 C->1, *std + mean: PG (N,HP,WP,C) -> fp32 (N,H,W) */
+VG_API int vg_head_fwd(int dtype, const void* h, const float* w, float bias, float pm_std, float pm_mean, int N, int HP,
+                int WP, int C, int H, int W, int pad_top, int pad_left, float* out, void* stream);
+
+/* Focal-R loss (README.md:16; no reference implementation): loss = mean(|e|*(2*sigmoid(beta|e|)-1)^gamma),
+ * mse=1 uses e^2.  partial: fp32 workspace of nblocks floats.  bwd: grad[i] = gscale * d(sum_j term_j)/dpred_i
+ * (pass gscale = upstream_grad / n for the mean). */
+VG_API int vg_focal_r_fwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse,
+                   float* partial, int nblocks, float* loss, void* stream);
+VG_API int vg_focal_r_bwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse,
+                   float gscale, float* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITGRID_H_ */

@@ -1,0 +1,311 @@
+"""Per-kernel parity (GPU): every libvitgrid entry point, called through the C ABI, against the CPU oracle /
+a plain fp32 PyTorch statement of the same op on identical seeded inputs.
+
+Tolerances: fp32 mode 1e-4 relative (max-abs error / max-abs reference); bf16 mode 1e-2 (2e-2 where the
+reference output itself is rounded to bf16).  Index work is bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import synth
+from oracle import maxvit_oracle as mo
+from oracle import metnet3_oracle as m3o
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1.5e-2}
+
+
+def ops():
+    from vit_grid_model_b200 import ops as _ops
+    return _ops
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def q(t, dtype):
+    """round a CPU fp32 tensor to what the device path will see"""
+    return t.to(dtype).float()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 128), (4099, 512, 384), (130, 1024, 128), (20000, 128, 3072)])
+def test_gemm_plain(dtype, M, K, N):
+    o = ops()
+    A, W = q(rnd(M, K, seed=1), dtype), q(rnd(N, K, seed=2) / math.sqrt(K), dtype)
+    out = o.gemm(A.cuda().to(dtype), W.cuda().to(dtype))
+    assert rel_err(out, A @ W.t()) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_bn_gelu_residual(dtype):
+    o = ops()
+    M, K, N = 3000, 128, 512
+    A, W = q(rnd(M, K, seed=1), dtype), q(rnd(N, K, seed=2) / math.sqrt(K), dtype)
+    scale, shift, res = 0.5 + torch.rand(N), rnd(N, seed=4), q(rnd(M, N, seed=5), dtype)
+    out = o.gemm(A.cuda().to(dtype), W.cuda().to(dtype), scale=scale.cuda(), shift=shift.cuda(), act=1,
+                 res=res.cuda().to(dtype))
+    ref = F.gelu((A @ W.t()) * scale + shift) + res
+    assert rel_err(out, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_per_batch_weights(dtype):
+    o = ops()
+    nb, rows, K, N = 5, 300, 128, 128
+    A = q(rnd(nb * rows, K, seed=1), dtype)
+    W = q(rnd(nb, N, K, seed=2) / math.sqrt(K), dtype)
+    out = o.gemm(A.cuda().to(dtype), W.reshape(nb * N, K).cuda().to(dtype), rows_per_batch=rows, b_rows_per_batch=N)
+    ref = torch.einsum("brk,bnk->brn", A.view(nb, rows, K), W).reshape(nb * rows, N)
+    assert rel_err(out, ref) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,H,W,Ca", [(2, 12, 10, 128), (3, 28, 28, 64), (1, 84, 70, 192)])
+def test_conv3x3_as_shifted_gemm(dtype, N, H, W, Ca):
+    """raw 3x3/pad-1 convolution over the padded-grid layout == F.conv2d"""
+    o = ops()
+    x = q(rnd(N, Ca, H, W, seed=3), dtype)
+    w = q(rnd(128, Ca, 3, 3, seed=4) / math.sqrt(9 * Ca), dtype)
+    xp = o.pg_from_nchw(x.cuda(), dtype)
+    wt = w.permute(0, 2, 3, 1).reshape(128, 9 * Ca).contiguous().cuda().to(dtype)
+    out = o.gemm(xp, wt, ntaps=9, tap_shift=o.conv_tap_shifts(W), out_f32=True)
+    got = o.pg_to_nchw(out, N, H, W)
+    assert rel_err(got, F.conv2d(x, w, padding=1)) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("with_film,with_res", [(True, False), (False, True)])
+def test_conv3x3_ln_block(dtype, with_film, with_res):
+    """metnet3.py:110-126 Block (+ residual) fused epilogue; pads of the output must be exactly zero"""
+    o = ops()
+    N, H, W, C = 3, 14, 28, 128
+    x = q(rnd(N, C, H, W, seed=3), dtype)
+    w = q(rnd(C, C, 3, 3, seed=4) / math.sqrt(9 * C), dtype)
+    b, g, be = rnd(C, seed=5, scale=0.1), 0.5 + torch.rand(C), rnd(C, seed=7, scale=0.1)
+    film = rnd(N, 2 * C, seed=8, scale=0.3) if with_film else None
+    res = q(rnd(N, C, H, W, seed=9), dtype) if with_res else None
+    out = torch.full((o.pg_pixels(N, H, W), C), 7.0, dtype=dtype, device="cuda")
+    o.conv3x3_ln(o.pg_from_nchw(x.cuda(), dtype), w.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().cuda().to(dtype),
+                 b.cuda(), g.cuda(), be.cuda(), 1e-5, None if film is None else film.cuda(),
+                 None if res is None else o.pg_from_nchw(res.cuda(), dtype), out, N, H, W)
+    h = m3o.chan_layer_norm(F.conv2d(x, w, b, padding=1), g.view(1, C, 1, 1), be.view(1, C, 1, 1))
+    if with_film:
+        h = h * (film[:, :C, None, None] + 1) + film[:, C:, None, None]
+    h = F.relu(h)
+    if with_res:
+        h = h + res
+    assert rel_err(o.pg_to_nchw(out, N, H, W), h) < TOL[dtype]
+    # pad positions are zero
+    full = out.float().view(N * (H + 1) + 1, W + 1, C)
+    assert full[:, 0].abs().max().item() == 0.0
+    assert full[::H + 1].abs().max().item() == 0.0
+
+
+# ------------------------------------------------------------------------------------------ input side
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("layout", ["contiguous", "channels_last_view"])
+def test_prepare(dtype, layout):
+    o = ops()
+    cfg = synth.CFG_SMALL128
+    x, ts, _ = synth.make_inputs(cfg, 2)
+    xd = x.cuda()
+    if layout == "channels_last_view":      # the eval driver's permuted view (evaluation_vit.py:248-249)
+        xd = x.permute(0, 3, 4, 1, 2).contiguous().cuda().permute(0, 3, 4, 1, 2)
+    cpad = (cfg.T * cfg.C + 63) // 64 * 64
+    out = o.prepare(xd, cfg.pads, cfg.HP, cfg.WP, cpad, cfg.pm25_mean, cfg.pm25_std, dtype)
+    ref = x.clone()
+    pm = torch.tensor([4, 10, 16, 22])
+    ref[:, :, pm] = (ref[:, :, pm] - cfg.pm25_mean) / cfg.pm25_std
+    ref = F.pad(ref, cfg.pads).reshape(2, cfg.T * cfg.C, cfg.HP, cfg.WP)
+    got = o.pg_to_nchw(out, 2, cfg.HP, cfg.WP)
+    assert got[:, cfg.T * cfg.C:].abs().max().item() == 0.0
+    if dtype == torch.float32:
+        assert torch.equal(got[:, :cfg.T * cfg.C].cpu(), ref)
+    else:
+        assert torch.equal(got[:, :cfg.T * cfg.C].cpu(), ref.to(dtype))
+
+
+def test_time_terms_match_explicit_conv():
+    """analytic time-channel term == the 3x3 / 1x1 convolution of the constant time channels (Q1, Q2 included)"""
+    o = ops()
+    cfg = synth.CFG_SMALL128
+    B = 3
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg))
+    x, ts, _ = synth.make_inputs(cfg, B)
+    net_in, cond = m3o.prepare_input(x, ts, sd, cfg)
+    w3, w1 = sd["resnet1.blocks.0.block1.proj.weight"], sd["resnet1.blocks.0.res_conv.weight"]
+    cd = cfg.T * cfg.C
+    t_only = net_in[:, cd:]
+    ref3 = F.conv2d(t_only, w3[:, cd:], padding=1)             # (N,128,HP,WP)
+    ref1 = F.conv2d(t_only, w1[:, cd:])
+    temb, cond_d, tt, tres = o.time_terms(ts.cuda(), B, cfg.L, sd["condition_lead_time.weight"].cuda(),
+                                          *[sd[f"condition_model_time.{i}.weight"].cuda() for i in range(3)],
+                                          w3.cuda().contiguous(), w1.cuda().contiguous(), cd, cfg.dim)
+    assert torch.equal(cond_d.cpu(), cond)
+    assert torch.equal(temb.cpu(), net_in[:, cd:, 0, 0])
+    HP, WP = cfg.HP, cfg.WP
+    rows = {0: 0, 1: HP // 2, 2: HP - 1}
+    cols = {0: 0, 1: WP // 2, 2: WP - 1}
+    for ry in range(3):
+        for rx in range(3):
+            assert rel_err(tt[:, ry * 3 + rx], ref3[:, :, rows[ry], cols[rx]]) < 1e-5
+    assert rel_err(tres, ref1[:, :, 3, 3]) < 1e-5
+
+
+def test_cond_mlps():
+    o = ops()
+    g = torch.Generator().manual_seed(3)
+    cond = torch.randn(7, 2, generator=g)
+    W0, b0 = torch.randn(256, 2, generator=g), torch.randn(256, generator=g)
+    W1, b1 = torch.randn(256, 256, generator=g) / 16, torch.randn(256, generator=g)
+    got = o.cond_mlp(cond.cuda(), W0.cuda(), b0.cuda(), pre_relu=True)
+    assert rel_err(got, F.linear(F.relu(cond), W0, b0)) < 1e-5
+    got = o.cond_mlp(cond.cuda(), W0.cuda(), b0.cuda(), W1.cuda(), b1.cuda())
+    assert rel_err(got, F.linear(F.silu(F.linear(cond, W0, b0)), W1, b1)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ MBConv pieces
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pool2(dtype):
+    o = ops()
+    x = q(rnd(3, 128, 14, 28, seed=1), dtype)
+    got = o.pool2(o.pg_from_nchw(x.cuda(), dtype), 3, 14, 28)
+    assert torch.equal(got.float().cpu().permute(0, 3, 1, 2), F.max_pool2d(x, 2, 2))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_bn_gelu_and_se(dtype):
+    o = ops()
+    N, H, W, C, se = 3, 14, 21, 512, 128
+    x = q(rnd(N, C, H, W, seed=1), dtype)
+    w, scale, shift = rnd(C, 1, 3, 3, seed=2) / 3, 0.5 + torch.rand(C), rnd(C, seed=4, scale=0.1)
+    out, psum = o.dw3x3_bnact(x.permute(0, 2, 3, 1).contiguous().cuda().to(dtype),
+                              w.reshape(C, 9).t().contiguous().cuda(), scale.cuda(), shift.cuda())
+    ref = F.gelu(F.conv2d(x, w, padding=1, groups=C) * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1))
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < TOL[dtype]
+    assert rel_err(psum.sum(1) / (H * W), ref.mean(dim=(2, 3))) < 1e-4
+    W1, W2 = rnd(se, C, seed=5) / math.sqrt(C), rnd(C, se, seed=6) / math.sqrt(se)
+    gate = o.se_gate(psum, W, W1.cuda(), W2.cuda())
+    gref = torch.sigmoid(F.linear(F.relu(F.linear(ref.mean(dim=(2, 3)), W1)), W2))
+    assert rel_err(gate, gref) < 1e-4
+    o.se_scale_(out, gate)
+    assert rel_err(out.permute(0, 3, 1, 2), ref * gref[:, :, None, None]) < TOL[dtype]
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_sd(dim, heads, dh, w, r, seed):
+    spec = {k[len("layers.0.1."):]: v for k, v in synth.maxvit_spec(dim, 1, 2, heads, dh, w, 4, 0.25, r).items()
+            if k.startswith("layers.0.1.")}
+    return synth.make_state_dict(spec, seed=seed)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("grid_mode", [False, True])
+def test_attention_layer(dtype, grid_mode):
+    """gather+LN+FiLM -> QKV GEMM -> core -> out-proj(+residual, scatter) == oracle attention + residual"""
+    o = ops()
+    N, H, W, C, heads, dh, w, R = 2, 14, 21, 128, 32, 32, 7, 4
+    sd = _attn_sd(C, heads, dh, w, R, seed=7)
+    x = q(rnd(N, H, W, C, seed=1), dtype)
+    cond = rnd(N, 2, seed=2)
+    reg = rnd(N, R, C, seed=3) if grid_mode else rnd(R, C, seed=3)
+    nwin = (H // w) * (W // w)
+    idx = (mo.grid_pixel_index if grid_mode else mo.block_pixel_index)(H, W, w).reshape(-1)
+    flat = x.reshape(N, H * W, C)
+    tok = flat[:, idx].reshape(N * nwin, w * w, C)
+    regs = reg.repeat_interleave(nwin, 0) if grid_mode else reg[None].expand(N * nwin, R, C)
+    seq = torch.cat([regs, tok], dim=1)
+    # the oracle sees the same rounded weights the device uses
+    sdq = dict(sd)
+    for k in ("to_qkv.weight", "to_out.0.weight"):
+        sdq[k] = q(sd[k], dtype)
+    ref = mo.attention(seq, cond, sdq, "", heads=heads, window=w, num_reg=R) + seq
+    ref_x = torch.empty_like(flat)
+    ref_x[:, idx] = ref[:, R:].reshape(N, nwin * w * w, C)
+
+    gamma, beta = mo.film(cond, sd, "")
+    film = torch.cat([gamma, beta], dim=1).cuda().contiguous()
+    xd = x.cuda().to(dtype)
+    tokens = o.attn_gather(xd, reg.cuda(), film, w, R, grid_mode)
+    qkv = o.gemm(tokens, sd["to_qkv.weight"].cuda().to(dtype))
+    att = o.attn_core(qkv, sd["q_norm.gamma"].reshape(-1).cuda(), sd["k_norm.gamma"].reshape(-1).cuda(),
+                      sd["rel_pos_bias.weight"].cuda(), N, H, W, w, R, heads, dh)
+    x_out, reg_out = o.attn_out(att, sd["to_out.0.weight"].cuda().to(dtype), xd, reg.cuda(), w, R, grid_mode, True)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel_err(x_out.reshape(N, H * W, C), ref_x) < tol
+    assert rel_err(reg_out, ref[:, :R]) < tol
+    mean = o.reg_mean(reg_out, N, nwin)
+    assert rel_err(mean, reg_out.view(N, nwin, R, C).mean(1)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxvit_module(dtype):
+    """MaxViT nn.Module (reference API) vs oracle, depth 2 (second MBConv is residual)"""
+    from vit_grid_model_b200 import MaxViT
+    dim, depth, heads, dh, w, R, N, H, W = 128, 2, 32, 32, 7, 4, 3, 14, 21
+    sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, R), seed=5)
+    m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=R)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision("bf16" if dtype == torch.bfloat16 else "fp32")
+    x, cond = rnd(N, dim, H, W, seed=1), rnd(N, 2, seed=2)
+    with torch.no_grad():
+        y = m(x.cuda(), cond.cuda())
+    ref = mo.maxvit_forward(x, cond, sd, depth=depth, heads=heads, window=w, num_reg=R)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert rel_err(y, ref) < (1e-4 if dtype == torch.float32 else 3e-2)
+
+
+# ------------------------------------------------------------------------------------------ decoder side
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_convT2(dtype):
+    o = ops()
+    N, Hl, Wl, C = 2, 7, 14, 128
+    x = q(rnd(N, C, Hl, Wl, seed=1), dtype)
+    w, b = q(rnd(C, C, 2, 2, seed=2) / math.sqrt(C), dtype), rnd(C, seed=3, scale=0.1)
+    out = torch.zeros(o.pg_pixels(N, 2 * Hl, 2 * Wl), C, dtype=dtype, device="cuda")
+    o.convT2(x.permute(0, 2, 3, 1).contiguous().cuda().to(dtype),
+             w.permute(2, 3, 1, 0).reshape(4 * C, C).contiguous().cuda().to(dtype), b.cuda(), out)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    assert rel_err(o.pg_to_nchw(out, N, 2 * Hl, 2 * Wl), ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_head(dtype):
+    o = ops()
+    cfg = synth.CFG_SMALL128
+    N, C = 3, 128
+    h = q(rnd(N, C, cfg.HP, cfg.WP, seed=1), dtype)
+    w, b = rnd(C, seed=2) / math.sqrt(C), 0.3
+    got = o.head(o.pg_from_nchw(h.cuda(), dtype), w.cuda(), b, cfg.pm25_std, cfg.pm25_mean, N, cfg.HP, cfg.WP, cfg.H,
+                 cfg.W, cfg.pads)
+    pl, pr, pt, pb = cfg.pads
+    ref = (F.conv2d(h[..., pt:cfg.HP - pb, pl:cfg.WP - pr], w.view(1, C, 1, 1)) + b).squeeze(1) * cfg.pm25_std + cfg.pm25_mean
+    assert rel_err(got, ref) < 1e-5
+
+
+def test_focal_r_forward_backward():
+    from oracle.focal_r_oracle import focal_r, focal_r_grad
+    from vit_grid_model_b200 import focal_r_loss
+    g = torch.Generator().manual_seed(0)
+    p = (torch.rand(4, 12, 82, 67, generator=g) * 60)
+    t = (torch.rand(4, 12, 82, 67, generator=g) * 60)
+    for mse in (False, True):
+        pd = p.cuda().requires_grad_(True)
+        loss = focal_r_loss(pd, t.cuda(), mse=mse)
+        loss.backward()
+        assert abs(loss.item() - focal_r(p.double(), t.double(), mse=mse).item()) / focal_r(p, t, mse=mse).item() < 1e-4
+        assert rel_err(pd.grad, focal_r_grad(p, t, mse=mse)) < 1e-4

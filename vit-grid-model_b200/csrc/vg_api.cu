@@ -1,0 +1,206 @@
+// extern "C" entry points of libvitgrid.so (declared in include/vitgrid.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vitgrid.h"
+#include "vg_epilogue.cuh"
+#include "vg_host.h"
+
+namespace vg {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+static unsigned long long g_launches = 0;
+
+int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static EpiParams epi_zero() {
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  return ep;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" {
+
+int vg_version(void) { return 100; }
+
+long long vg_launch_count(void) { return (long long)g_launches; }
+
+const char* vg_last_error(void) { return g_err; }
+
+int vg_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error("no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) return set_error("libvitgrid is built for sm_100a only; device is sm_%d%d", major, minor);
+  return 0;
+}
+
+long long vg_pg_pixels(int N, int HP, int WP) { return make_pgeom(N, HP, WP).pixels(); }
+
+int vg_prepare_fwd(int dtype, const float* x, const long long* xstride, int B, int T, int C, int H, int W, int pad_top,
+                   int pad_left, int HP, int WP, int Cpad, float pm_mean, float pm_std, void* out, void* stream) {
+  return prepare_run(dtype, x, xstride, B, T, C, H, W, pad_top, pad_left, HP, WP, Cpad, pm_mean, pm_std, out,
+                     (cudaStream_t)stream);
+}
+
+int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long long ts_sF, int B, int L, int le, int te,
+                      const float* emb_lead, const float* emb_month, const float* emb_day, const float* emb_hour,
+                      const float* w3, const float* w1, int c_in, int c_data, int Cout, float* temb, float* cond,
+                      float* tt, float* tres, void* stream) {
+  TimeParams p;
+  p.ts = ts; p.ts_sB = ts_sB; p.ts_sT = ts_sT; p.ts_sF = ts_sF;
+  p.B = B; p.L = L; p.le = le; p.te = te;
+  p.emb_lead = emb_lead; p.emb_m = emb_month; p.emb_d = emb_day; p.emb_h = emb_hour;
+  p.w3 = w3; p.w1 = w1; p.c_in = c_in; p.c_data = c_data; p.Cout = Cout;
+  p.temb = temb; p.cond = cond; p.tt = tt; p.tres = tres;
+  return time_terms_run(p, (cudaStream_t)stream);
+}
+
+int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu, const float* W0, const float* b0, int hid,
+                    const float* W1, const float* b1, int od, float* out, void* stream) {
+  return cond_mlp_run(cond, N, cond_dim, pre_relu, W0, b0, hid, W1, b1, od, out, (cudaStream_t)stream);
+}
+
+int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* Wt, int Ntot, int ntaps,
+                const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch, const float* bias,
+                const float* scale, const float* shift, int act, const void* res, long long ldres, void* out,
+                long long ldo, int out_f32, float* scratch, long long scratch_elems, void* stream) {
+  EpiParams ep = epi_zero();
+  ep.out = out; ep.ldo = ldo; ep.out_f32 = out_f32; ep.n_total = Ntot;
+  ep.bias = bias; ep.col_scale = scale; ep.col_shift = shift; ep.act = act; ep.res = res; ep.ldres = ldres;
+  if ((scale == nullptr) != (shift == nullptr)) return set_error("gemm: scale and shift must be given together");
+  return gemm_run(dtype, EPI_STORE, A, rowsA, Ca, Wt, Ntot, ntaps, tap_shift, M, rows_per_batch, b_rows_per_batch, ep,
+                  scratch, scratch_elems, (cudaStream_t)stream);
+}
+
+int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
+                      const float* ln_b, float ln_eps, const float* film, const void* res, void* out, int N, int HP,
+                      int WP, float* scratch, long long scratch_elems, void* stream) {
+  PGeom pg = make_pgeom(N, HP, WP);
+  EpiParams ep = epi_zero();
+  ep.out = out; ep.ldo = 128; ep.n_total = 128; ep.bias = bias; ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_eps = ln_eps;
+  ep.film = film; ep.res = res; ep.ldres = 128; ep.pg = pg;
+  int shifts[9];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) shifts[ky * 3 + kx] = (ky - 1) * pg.P + (kx - 1);
+  return gemm_run(dtype, EPI_CONV_LN, x, pg.pixels(), Ca, Wt, 128, 9, shifts, pg.pixels(), 0, 0, ep, scratch,
+                  scratch_elems, (cudaStream_t)stream);
+}
+
+int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                       const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                       const float* film, int B, int L, int HP, int WP, void* h1, void* res, void* stream) {
+  StemParams p;
+  p.raw3 = raw3; p.rawres = rawres; p.bias3 = bias3; p.bias1 = bias1; p.tt = tt; p.tres = tres;
+  p.ln_g = ln_g; p.ln_b = ln_b; p.eps = ln_eps; p.film = film; p.L = L;
+  p.pgB = make_pgeom(B, HP, WP); p.pgN = make_pgeom(B * L, HP, WP);
+  return stem_finish_run(dtype, p, h1, res, (cudaStream_t)stream);
+}
+
+int vg_pool2_fwd(int dtype, const void* in, void* out, int N, int HP, int WP, int C, void* stream) {
+  return maxpool2_run(dtype, in, out, N, HP, WP, C, (cudaStream_t)stream);
+}
+
+int vg_dw3x3_bnact_fwd(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out,
+                       float* psum, int N, int H, int W, int C, void* stream) {
+  return dwconv_run(dtype, in, w9, scale, shift, out, psum, N, H, W, C, (cudaStream_t)stream);
+}
+
+int vg_se_gate_fwd(const float* psum, int N, int H, int W, const float* W1, const float* W2, int C, int se, float* gate,
+                   void* stream) {
+  return se_gate_run(psum, N, H, H * W, W1, W2, C, se, gate, (cudaStream_t)stream);
+}
+
+int vg_se_scale_fwd(int dtype, void* x, const float* gate, int N, long long HW, int C, void* stream) {
+  return se_scale_run(dtype, x, gate, N, HW, C, (cudaStream_t)stream);
+}
+
+static int make_attn_geom(AttnGeom& g, int N, int Hl, int Wl, int C, int win, int R, int grid_mode) {
+  if (win <= 0 || Hl % win || Wl % win) return set_error("attention: map %dx%d not divisible by window %d", Hl, Wl, win);
+  g.N = N; g.Hl = Hl; g.Wl = Wl; g.C = C; g.win = win; g.R = R; g.X = Hl / win; g.Y = Wl / win; g.grid_mode = grid_mode;
+  return 0;
+}
+
+int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, int N, int Hl,
+                       int Wl, int C, int win, int R, int grid_mode, float ln_eps, void* tokens, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
+  return attn_gather_run(dtype, x, reg, reg_per_field, film, g, ln_eps, tokens, (cudaStream_t)stream);
+}
+
+int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma, const float* bias_table,
+                     int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
+  return attn_core_run(dtype, qkv, q_gamma, k_gamma, bias_table, g, heads, dh, out, (cudaStream_t)stream);
+}
+
+int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, const void* x_in, const float* reg_in,
+                    int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
+                    int grid_mode, float* scratch, long long scratch_elems, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
+  EpiParams ep = epi_zero();
+  ep.out = x_out; ep.n_total = C; ep.S = g.S(); ep.R = R; ep.nwin = g.nwin(); ep.grid_mode = grid_mode; ep.win = win;
+  ep.X = g.X; ep.Y = g.Y; ep.Hl = Hl; ep.Wl = Wl; ep.x_in = x_in; ep.reg_in = reg_in;
+  ep.reg_in_per_field = reg_per_field; ep.reg_out = reg_out;
+  const long long M = (long long)N * g.nwin() * g.S();
+  const int shift0 = 0;
+  return gemm_run(dtype, EPI_ATTN_OUT, attn, M, inner, Wt, C, 1, &shift0, M, 0, 0, ep, scratch, scratch_elems,
+                  (cudaStream_t)stream);
+}
+
+int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream) {
+  return reg_mean_run(in, out, N, nwin, RC, (cudaStream_t)stream);
+}
+
+int vg_convT2_fwd(int dtype, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl, int C,
+                  float* scratch, long long scratch_elems, void* stream) {
+  EpiParams ep = epi_zero();
+  ep.out = out; ep.ldo = C; ep.n_total = 4 * C; ep.bias = bias; ep.Hl = Hl; ep.Wl = Wl;
+  ep.pg = make_pgeom(N, 2 * Hl, 2 * Wl);
+  if (C % 128) return set_error("convT2: C=%d must be a multiple of 128", C);
+  const long long M = (long long)N * Hl * Wl;
+  const int shift0 = 0;
+  return gemm_run(dtype, EPI_CONVT, x, M, C, Wt, 4 * C, 1, &shift0, M, 0, 0, ep, scratch, scratch_elems,
+                  (cudaStream_t)stream);
+}
+
+int vg_head_fwd(int dtype, const void* h, const float* w, float bias, float pm_std, float pm_mean, int N, int HP, int WP,
+                int C, int H, int W, int pad_top, int pad_left, float* out, void* stream) {
+  return head_run(dtype, h, w, bias, pm_std, pm_mean, N, HP, WP, C, H, W, pad_top, pad_left, out, (cudaStream_t)stream);
+}
+
+int vg_focal_r_fwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse, float* partial,
+                   int nblocks, float* loss, void* stream) {
+  return focal_r_fwd_run(pred, target, n, beta, gamma, mse, partial, nblocks, loss, (cudaStream_t)stream);
+}
+
+int vg_focal_r_bwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse, float gscale,
+                   float* grad, void* stream) {
+  return focal_r_bwd_run(pred, target, n, beta, gamma, mse, gscale, grad, (cudaStream_t)stream);
+}
+
+}  // extern "C"

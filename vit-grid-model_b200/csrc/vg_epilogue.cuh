@@ -1,0 +1,210 @@
+// Row-wise GEMM epilogues shared by the tcgen05 kernel (accumulator row read from TMEM, one thread per
+// row) and the fp32-mode SIMT path (accumulator row read from a global scratch).  A "Loader" exposes
+//     void load(int chunk, float v[32])   // columns [n0 + 32*chunk, +32) of this thread's accumulator row
+// and MUST be called uniformly by all threads of a warp (the TMEM load is warp-collective); only the global
+// stores are predicated on row validity.
+#pragma once
+#include "vg_common.cuh"
+
+namespace vg {
+
+enum EpiKind : int {
+  EPI_STORE = 0,      // y = act(acc*scale + shift | acc + bias) (+ res)                 -> [row][ldo]
+  EPI_CONV_LN = 1,    // conv3x3 block: +bias, channel LayerNorm, FiLM, ReLU, (+res), zero pads (PG layout)
+  EPI_ATTN_OUT = 2,   // attention out-projection: + residual, scatter through the inverse window/grid map
+  EPI_CONVT = 3,      // ConvTranspose2d k2 s2 as GEMM: + bias, depth-to-space into the PG layout
+};
+
+struct EpiParams {
+  void* out;
+  long long ldo;
+  int out_f32;               // EPI_STORE: store fp32 regardless of the activation dtype
+  int n_total;               // total number of GEMM columns
+  const float* bias;         // [n_total] (EPI_CONVT: [C])
+  const float* col_scale;    // folded BatchNorm: y = acc*scale + shift (bias already folded into shift)
+  const float* col_shift;
+  int act;                   // 0 none, 1 GELU(erf), 2 ReLU
+  const void* res;           // residual, same row indexing as out
+  long long ldres;
+  // EPI_CONV_LN
+  const float* ln_g;
+  const float* ln_b;
+  float ln_eps;
+  const float* film;         // [fields][2C]  (scale | shift), applied as v*(scale+1)+shift; null = none
+  PGeom pg;                  // output geometry (EPI_CONV_LN, EPI_CONVT)
+  const float* head_w;       // optional fused 1x1 head (C -> 1): out_head[...] = dot(y, head_w) (unused in v1)
+  // EPI_ATTN_OUT
+  int S, R, nwin, grid_mode, win, X, Y, Hl, Wl;
+  const void* x_in;          // (N, Hl*Wl, C) residual stream the window tokens came from
+  const float* reg_in;       // register-token residual: [R][C] (shared) or [N][R][C] (per field)
+  int reg_in_per_field;
+  float* reg_out;            // [Nw][R][C] register-token outputs (block attention) or null
+};
+
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  float v[32];
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+    const int c0 = n0 + ch * 32;
+    if (!ok || c0 >= ep.n_total) continue;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j];
+      if (ep.col_scale) x = x * __ldg(ep.col_scale + c0 + j) + __ldg(ep.col_shift + c0 + j);
+      else if (ep.bias) x += __ldg(ep.bias + c0 + j);
+      if (ep.act == 1) x = gelu_erf(x);
+      else if (ep.act == 2) x = fmaxf(x, 0.f);
+      v[j] = x;
+    }
+    if (ep.res) {
+      const T* r = reinterpret_cast<const T*>(ep.res) + row * ep.ldres + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) { float t[8]; ld8(r + j, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
+    }
+    if (ep.out_f32) {
+      float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st8(o + j, v + j);
+    } else {
+      T* o = reinterpret_cast<T*>(ep.out) + row * ep.ldo + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st8(o + j, v + j);
+    }
+  }
+}
+
+// Requires the whole channel row in one tile: n0 == 0, C == 128.
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  (void)n0;
+  constexpr int C = 128;
+  float v[32];
+  int n, h, w;
+  const bool in_buf = ok && row < ep.pg.pixels();
+  const bool valid = ep.pg.decode(row, n, h, w) && in_buf;
+  // pass 1: mean of (acc + bias)
+  float s = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j] + __ldg(ep.bias + ch * 32 + j);
+  }
+  const float mean = s * (1.0f / C);
+  // pass 2: biased variance (two-pass form, as torch.var does)
+  float ss = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { float d = v[j] + __ldg(ep.bias + ch * 32 + j) - mean; ss += d * d; }
+  }
+  const float rstd = rsqrtf(fmaxf(ss * (1.0f / C), ep.ln_eps));     // var.clamp(min=eps).rsqrt()  (metnet3.py:104)
+  const float* film = (ep.film && valid) ? ep.film + (long long)n * 2 * C : nullptr;
+  T* o = reinterpret_cast<T*>(ep.out) + row * ep.ldo;
+  const T* r = ep.res ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
+  // pass 3: normalise, FiLM, ReLU, residual, store (zeros at pad positions)
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+    if (!in_buf) continue;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = ch * 32 + j;
+        float y = (v[j] + __ldg(ep.bias + c) - mean) * rstd * __ldg(ep.ln_g + c) + __ldg(ep.ln_b + c);
+        if (film) y = y * (film[c] + 1.0f) + film[C + c];
+        v[j] = fmaxf(y, 0.f);
+      }
+      if (r) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) { float t[8]; ld8(r + ch * 32 + j, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+  }
+}
+
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_attn_out(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  const int C = ep.n_total;
+  const long long wdx = row / ep.S;
+  const int tok = (int)(row - wdx * ep.S);
+  const int n = (int)(wdx / ep.nwin);
+  const int wi = (int)(wdx - (long long)n * ep.nwin);
+  const T* rsrc = nullptr; T* dst = nullptr; const float* rreg = nullptr; float* dreg = nullptr;
+  if (ok) {
+    if (tok < ep.R) {
+      if (ep.reg_out) {
+        rreg = ep.reg_in + (ep.reg_in_per_field ? (long long)n * ep.R * C : 0) + (long long)tok * C;
+        dreg = ep.reg_out + (wdx * ep.R + tok) * C;
+      }
+    } else {
+      const int t = tok - ep.R, a = t / ep.win, b = t - a * ep.win;
+      const int x = wi / ep.Y, y = wi - x * ep.Y;
+      const int ph = ep.grid_mode ? a * ep.X + x : x * ep.win + a;      // maxvit.py:322 / :298
+      const int pw = ep.grid_mode ? b * ep.Y + y : y * ep.win + b;
+      const long long pix = (long long)n * ep.Hl * ep.Wl + (long long)ph * ep.Wl + pw;
+      rsrc = reinterpret_cast<const T*>(ep.x_in) + pix * C;
+      dst = reinterpret_cast<T*>(ep.out) + pix * C;
+    }
+  }
+  float v[32];
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+    const int c0 = n0 + ch * 32;
+    if (c0 >= C) continue;
+    if (dst) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) { float t[8]; ld8(rsrc + c0 + j, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] += t[i];
+        st8(dst + c0 + j, v + j); }
+    } else if (dreg) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dreg[c0 + j] = v[j] + __ldg(rreg + c0 + j);
+    }
+  }
+}
+
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  const int C = ep.n_total / 4;
+  const int tap = n0 / C, cbase = n0 - tap * C;
+  const int lo = ep.Hl * ep.Wl;
+  const int n = (int)(row / lo);
+  const int p = (int)(row - (long long)n * lo);
+  const int i = p / ep.Wl, j0 = p - i * ep.Wl;
+  T* o = reinterpret_cast<T*>(ep.out) + ep.pg.q(n, 2 * i + (tap >> 1), 2 * j0 + (tap & 1)) * ep.ldo + cbase;
+  float v[32];
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    ld.load(ch, v);
+    if (!ok || cbase + ch * 32 >= C) continue;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + cbase + ch * 32 + j);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+  }
+}
+
+template <int KIND, typename T, class Loader>
+__device__ __forceinline__ void run_epilogue(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  if constexpr (KIND == EPI_STORE) epi_store<T>(ep, row, ok, n0, ld);
+  else if constexpr (KIND == EPI_CONV_LN) epi_conv_ln<T>(ep, row, ok, n0, ld);
+  else if constexpr (KIND == EPI_ATTN_OUT) epi_attn_out<T>(ep, row, ok, n0, ld);
+  else epi_convt<T>(ep, row, ok, n0, ld);
+}
+
+}  // namespace vg

@@ -1,0 +1,321 @@
+// Shifted-row GEMM for sm_100a: D[m][n] = sum_tap sum_c A[m + shift(tap)][c] * B[n][tap*Ca + c]
+//
+// One kernel serves every tensor-core contraction on the path: 3x3 convolutions over the padded-grid layout
+// (9 taps = 9 row shifts of the same 2-D A tensor, see vg_common.cuh), 1x1 convolutions / linear layers
+// (1 tap) and ConvTranspose2d-as-GEMM.  bf16 mode: persistent warp-specialised tcgen05 kernel, operands
+// streamed by TMA into a 128B-swizzled multi-stage ring, fp32 accumulators double-buffered in TMEM, row-wise
+// fused epilogues (vg_epilogue.cuh).  fp32 mode: SIMT FFMA kernel + the same epilogues run row-wise.
+#include <stdio.h>
+
+#include "vg_epilogue.cuh"
+#include "vg_host.h"
+
+namespace vg {
+
+struct GemmShape {
+  long long M;              // valid output rows (all batches)
+  int num_m_tiles, num_n_tiles;
+  int k_blocks, cblocks;    // 64-wide K blocks: total and per tap
+  int tap_shift[9];
+  int tiles_per_batch;      // m-tiles per batch (== num_m_tiles when not batched)
+  long long rows_per_batch; // A / output rows per batch (== M when not batched)
+  int b_rows_per_batch;     // B row offset per batch (per-field weights)
+};
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
+constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;          // 32 KiB
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 2 * BN;                             // double-buffered accumulator
+
+struct TmemLoader {
+  uint32_t taddr;
+  __device__ __forceinline__ void load(int chunk, float* v) {
+    tmem_ld32(taddr + chunk * 32, v);
+    tmem_wait_ld();
+  }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const GemmShape gs, const EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = gs.num_m_tiles * gs.num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {                                         // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_tile = t / gs.num_n_tiles, n_tile = t - m_tile * gs.num_n_tiles;
+        const int batch = m_tile / gs.tiles_per_batch, mt = m_tile - batch * gs.tiles_per_batch;
+        const long long row0 = (long long)batch * gs.rows_per_batch + (long long)mt * BM;
+        const int brow0 = batch * gs.b_rows_per_batch + n_tile * BN;
+        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          const int tap = kb / gs.cblocks, cb = kb - tap * gs.cblocks;
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d(sa, &mapA, full + stage, cb * BK, (int)(row0 + gs.tap_shift[tap]));
+          tma_load_2d(sa + BM * BK * 2, &mapB, full + stage, kb * BK, brow0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                         // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty + as, aphase ^ 1);                  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < gs.k_blocks; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + BM * BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)                  // +32 B per K=16 step inside the swizzle atom
+            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          tc_commit(empty + stage);                          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull + as);                               // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {                                    // ===== epilogue: 128 threads, one row each =====
+    const int lg = warp & 3;                                 // TMEM lane group this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int m_tile = t / gs.num_n_tiles, n_tile = t - m_tile * gs.num_n_tiles;
+      const int batch = m_tile / gs.tiles_per_batch, mt = m_tile - batch * gs.tiles_per_batch;
+      const long long lrow = (long long)mt * BM + lg * 32 + lane;
+      const long long row = (long long)batch * gs.rows_per_batch + lrow;
+      const bool ok = lrow < gs.rows_per_batch && row < gs.M;
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull + as, aphase);
+      tc_fence_after();
+      TmemLoader ld{tmem_base + as * BN + ((uint32_t)(lg * 32) << 16)};
+      run_epilogue<KIND, bf16>(ep, row, ok, n_tile * BN, ld);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 mode: SIMT GEMM into a scratch accumulator + row-wise epilogue kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, long long rowsA, int Ca, const float* __restrict__ B, int Ktot,
+                 const GemmShape gs, float* __restrict__ scratch, int Ntot) {
+  __shared__ float sA[16][65], sB[16][65];
+  const int batch = blockIdx.z;
+  const long long lrow0 = (long long)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const long long grow0 = (long long)batch * gs.rows_per_batch + lrow0;
+  const float* Bb = B + (long long)batch * gs.b_rows_per_batch * Ktot;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  const int ntaps = gs.k_blocks / gs.cblocks;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    for (int c0 = 0; c0 < Ca; c0 += 16) {
+      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int r = i >> 4, c = i & 15;
+        const long long ar = grow0 + r + gs.tap_shift[tap];
+        sA[c][r] = (ar >= 0 && ar < rowsA && c0 + c < Ca) ? A[ar * Ca + c0 + c] : 0.f;
+        const int bn = n0 + r;
+        sB[c][r] = (bn < Ntot && c0 + c < Ca) ? Bb[(long long)bn * Ktot + tap * Ca + c0 + c] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; b[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long lr = lrow0 + ty * 4 + i;
+    const long long gr = grow0 + ty * 4 + i;
+    if (lr >= gs.rows_per_batch || gr >= gs.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < Ntot) scratch[gr * Ntot + n] = acc[i][j];
+    }
+  }
+}
+
+struct ScratchLoader {
+  const float* p;   // scratch + row*Ntot + n0 (null when the row is out of range)
+  int ncols;        // valid columns from n0
+  __device__ __forceinline__ void load(int chunk, float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const int c = chunk * 32 + j; v[j] = (p && c < ncols) ? p[c] : 0.f; }
+  }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+epilogue_rows_kernel(const float* __restrict__ scratch, int Ntot, const GemmShape gs, const EpiParams ep) {
+  const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const bool ok = row < gs.M;
+  ScratchLoader ld{ok ? scratch + row * Ntot + n0 : nullptr, Ntot - n0};
+  run_epilogue<KIND, float>(ep, row, ok, n0, ld);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] (inner contiguous), box 64 x box_outer, 128B swizzle, zero OOB fill
+static int make_map_bf16_2d(CUtensorMap* m, const void* ptr, long long inner, long long outer, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld", (int)r, ptr, inner, outer);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int KIND>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int total = gs.num_m_tiles * gs.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<KIND><<<grid, 256, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int KIND>
+static int launch_simt_epi(const float* scratch, int Ntot, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
+  dim3 grid((unsigned)((gs.M + 127) / 128), (unsigned)((Ntot + BN - 1) / BN));
+  epilogue_rows_kernel<KIND><<<grid, 128, 0, st>>>(scratch, Ntot, gs, ep);
+  return check_launch("epilogue_rows_kernel");
+}
+
+// The one host entry used by the C ABI (vg_api.cu).  dtype: 0 = bf16 (tcgen05), 1 = fp32 (SIMT).
+int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
+             const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
+             const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st) {
+  if (Ca % BK) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, BK);
+  if (ntaps < 1 || ntaps > 9) return set_error("gemm: bad tap count %d", ntaps);
+  if (M <= 0) return 0;
+  GemmShape gs;
+  gs.M = M;
+  gs.cblocks = Ca / BK;
+  gs.k_blocks = gs.cblocks * ntaps;
+  for (int i = 0; i < 9; ++i) gs.tap_shift[i] = i < ntaps ? tap_shift[i] : 0;
+  const bool batched = rows_per_batch > 0 && rows_per_batch < M;
+  gs.rows_per_batch = batched ? rows_per_batch : M;
+  gs.b_rows_per_batch = batched ? b_rows_per_batch : 0;
+  const long long nbatch = (M + gs.rows_per_batch - 1) / gs.rows_per_batch;
+  gs.tiles_per_batch = (int)((gs.rows_per_batch + BM - 1) / BM);
+  gs.num_m_tiles = (int)(gs.tiles_per_batch * nbatch);
+  gs.num_n_tiles = (Ntot + BN - 1) / BN;
+  const int Ktot = Ca * ntaps;
+  if (kind == EPI_CONV_LN && Ntot != BN) return set_error("gemm: conv+LN epilogue needs exactly %d output channels (got %d)", BN, Ntot);
+
+  if (dtype == 0) {
+    CUtensorMap ma, mb;
+    int rc = make_map_bf16_2d(&ma, A, Ca, rowsA, BM);
+    if (rc) return rc;
+    rc = make_map_bf16_2d(&mb, B, Ktot, (long long)Ntot * (batched ? nbatch : 1), BN);
+    if (rc) return rc;
+    switch (kind) {
+      case EPI_STORE: return launch_tc<EPI_STORE>(ma, mb, gs, ep, st);
+      case EPI_CONV_LN: return launch_tc<EPI_CONV_LN>(ma, mb, gs, ep, st);
+      case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT>(ma, mb, gs, ep, st);
+      case EPI_CONVT: return launch_tc<EPI_CONVT>(ma, mb, gs, ep, st);
+    }
+    return set_error("gemm: bad epilogue kind %d", kind);
+  }
+  if (dtype != 1) return set_error("gemm: bad dtype %d", dtype);
+  if (scratch_elems < M * (long long)Ntot) return set_error("gemm(fp32): scratch too small (%lld < %lld)", scratch_elems, M * (long long)Ntot);
+  dim3 grid((unsigned)((gs.rows_per_batch + 63) / 64), (unsigned)((Ntot + 63) / 64), (unsigned)nbatch);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(A), rowsA, Ca, reinterpret_cast<const float*>(B),
+                                         Ktot, gs, scratch, Ntot);
+  int rc = check_launch("gemm_simt_kernel");
+  if (rc) return rc;
+  switch (kind) {
+    case EPI_STORE: return launch_simt_epi<EPI_STORE>(scratch, Ntot, gs, ep, st);
+    case EPI_CONV_LN: return launch_simt_epi<EPI_CONV_LN>(scratch, Ntot, gs, ep, st);
+    case EPI_ATTN_OUT: return launch_simt_epi<EPI_ATTN_OUT>(scratch, Ntot, gs, ep, st);
+    case EPI_CONVT: return launch_simt_epi<EPI_CONVT>(scratch, Ntot, gs, ep, st);
+  }
+  return set_error("gemm: bad epilogue kind %d", kind);
+}
+
+}  // namespace vg

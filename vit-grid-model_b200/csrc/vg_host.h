@@ -1,0 +1,88 @@
+// Host-side helpers shared by the translation units of libvitgrid (error reporting, launch checks,
+// internal entry points).  Not part of the public C ABI (that is include/vitgrid.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vg_common.cuh"
+
+namespace vg {
+
+struct EpiParams;
+
+// printf-style: records the message for vg_last_error() and returns a non-zero error code
+int set_error(const char* fmt, ...);
+// cudaGetLastError() after a launch; 0 when clean
+int check_launch(const char* what);
+
+int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
+             const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
+             const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st);
+
+struct PrepParams {
+  const float* x;
+  long long sB, sT, sC, sH, sW;   // element strides of x
+  int B, T, C, H, W;
+  int pad_top, pad_left;
+  int Cpad;
+  float mean, inv_std_unused, stdv;
+  PGeom pg;
+  int w_fast;                     // 1: x contiguous along W (tile transposed through smem along w)
+};
+
+struct TimeParams {
+  const float* ts; long long ts_sB, ts_sT, ts_sF;  // timestamps (B, n_ts, 4) strides
+  int B, L, le, te;
+  const float* emb_lead;   // (L+1, le)
+  const float* emb_m; const float* emb_d; const float* emb_h;  // (13|32|25, te)
+  const float* w3;         // (Cout, c_in, 3, 3) original layout
+  const float* w1;         // (Cout, c_in, 1, 1)
+  int c_in, c_data, Cout;
+  float* temb;             // (N, le+3te)
+  float* cond;             // (N, le)
+  float* tt;               // (N, 9, Cout)
+  float* tres;             // (N, Cout)
+};
+
+struct StemParams {
+  const float* raw3; const float* rawres;   // [q_b][C] fp32 over the B-image PG geometry
+  const float* bias3; const float* bias1;
+  const float* tt; const float* tres;       // (N,9,C), (N,C)
+  const float* ln_g; const float* ln_b; float eps;
+  const float* film;                        // (N, 2C)
+  int L;
+  PGeom pgB, pgN;
+};
+
+int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, int C, int H, int W, int pad_top, int pad_left,
+                int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st);
+int time_terms_run(const TimeParams& p, cudaStream_t st);
+int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
+                 const float* W1, const float* b1, int od, float* out, cudaStream_t st);
+int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStream_t st);
+int maxpool2_run(int dtype, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st);
+int dwconv_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out, float* psum,
+               int N, int H, int W, int C, cudaStream_t st);
+int se_gate_run(const float* psum, int N, int H, int HW, const float* W1, const float* W2, int C, int se, float* gate, cudaStream_t st);
+int se_scale_run(int dtype, void* x, const float* gate, int N, long long HW, int C, cudaStream_t st);
+int reg_mean_run(const float* in, float* out, int N, int nwin, int RC, cudaStream_t st);
+int head_run(int dtype, const void* h, const float* w, float bias, float stdv, float mean, int N, int HP, int WP, int C,
+             int H, int W, int pad_top, int pad_left, float* out, cudaStream_t st);
+int focal_r_fwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float* partial,
+                    int nb, float* loss, cudaStream_t st);
+int focal_r_bwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float gscale,
+                    float* grad, cudaStream_t st);
+
+// attention (vg_attn.cu)
+struct AttnGeom {
+  int N, Hl, Wl, C;        // fields, low-res map, channels
+  int win, R, X, Y;        // window size, register tokens, windows per column / row
+  int grid_mode;           // 0 block partition (maxvit.py:298), 1 grid partition (maxvit.py:322)
+  __host__ __device__ int S() const { return R + win * win; }
+  __host__ __device__ int nwin() const { return X * Y; }
+};
+int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
+                    float eps, void* tokens, cudaStream_t st);
+int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
+                  const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st);
+
+}  // namespace vg

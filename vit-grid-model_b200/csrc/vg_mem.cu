@@ -1,0 +1,483 @@
+// Bandwidth-bound kernels of the MetNet3 / MaxViT path (judged by achieved HBM GB/s):
+// input preparation, time-channel terms, stem finish (LN+FiLM+ReLU per lead time), max-pool, depthwise 3x3 +
+// BN + GELU (+ squeeze-excite partial sums), SE gate / scale, conditioning MLPs, register-token mean,
+// 1x1 head + de-normalisation, Focal-R loss.
+// All kernels are templated on the activation dtype T (bf16 mode / fp32 mode) and use channels-last layouts.
+#include "vg_common.cuh"
+#include "vg_host.h"
+
+namespace vg {
+
+// ================================================================================================
+// prepare: x (B,T,C,H,W) fp32, arbitrary strides -> PG layout [q][Cpad] with PM2.5 channels standardised
+// (metnet3.py:361-380), spatially zero-padded into the HPxWP frame (metnet3.py:384), channel padded with zeros.
+// The L-fold replication (metnet3.py:383) is NOT materialised: the stem convolution runs once per sample.
+// The output buffer is zero-filled first (pads, channel padding); this kernel writes frame pixels with a source.
+// ================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int w0 = blockIdx.x * 32;
+  const int h = blockIdx.y;
+  const int cblocks = p.Cpad / 64;
+  const int b = blockIdx.z / cblocks, ch0 = (blockIdx.z - b * cblocks) * 64;
+  const int TC = p.T * p.C;
+  const float* xb = p.x + (long long)b * p.sB + (long long)h * p.sH;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    int cl, wl;
+    if (p.w_fast) { wl = i & 31; cl = i >> 5; } else { cl = i & 63; wl = i >> 6; }
+    const int ch = ch0 + cl, w = w0 + wl;
+    float v = 0.f;
+    if (ch < TC && w < p.W) {
+      const int t = ch / p.C, c = ch - t * p.C;
+      v = xb[(long long)t * p.sT + (long long)c * p.sC + (long long)w * p.sW];
+      if (c == 4 || c == 10 || c == 16 || c == 22) v = (v - p.mean) / p.stdv;     // metnet3.py:362,370
+    }
+    tile[cl][wl] = v;
+  }
+  __syncthreads();
+  const int wl = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
+  const int w = w0 + wl;
+  if (w < p.W) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tile[c8 + j][wl];
+    st8(out + p.pg.q(b, h + p.pad_top, w + p.pad_left) * p.Cpad + ch0 + c8, v);
+  }
+}
+
+// ================================================================================================
+// time terms.  Field n = b*L + l.  temb[n] = [lead_emb(l+1) | scrambled model-time embedding] (metnet3.py:389-402,
+// quirk Q1: the three (N,te) embeddings are concatenated on dim 0 and re-viewed as (N,3te)); cond[n] = lead_emb.
+// The time channels are spatially constant over the whole HPxWP frame, so their contribution to the first 3x3
+// convolution is a per-(field, border case, out-channel) constant tt[n][case][co] (case = 3*ry+rx; r=0 first
+// row/col: tap 0 falls outside, r=2 last row/col: tap 2 outside, r=1 interior) and to the 1x1 res_conv tres[n][co].
+// ================================================================================================
+
+__global__ void time_embed_kernel(const TimeParams p) {
+  const int N = p.B * p.L, ntc = p.le + 3 * p.te;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ntc) return;
+  const int n = i / ntc, c = i - n * ntc;
+  float v;
+  if (c < p.le) {
+    v = p.emb_lead[((n % p.L) + 1) * p.le + c];
+    p.cond[n * p.le + c] = v;
+  } else {
+    const int f = n * 3 * p.te + (c - p.le);          // flat index into the (3N, te) concatenation
+    const int r = f / p.te, col = f - r * p.te;
+    const int which = r / N, idx = r - which * N;     // which embedding, which field's timestamp
+    const int b = idx / p.L;
+    const float tv = p.ts[(long long)b * p.ts_sB + 6 * p.ts_sT + (long long)(1 + which) * p.ts_sF];   // time index 6 (Q2)
+    const int k = (int)tv;                            // .int() truncation (metnet3.py:392)
+    const float* e = which == 0 ? p.emb_m : (which == 1 ? p.emb_d : p.emb_h);
+    v = e[k * p.te + col];
+  }
+  p.temb[i] = v;
+}
+
+__global__ void time_terms_kernel(const TimeParams p) {
+  const int N = p.B * p.L, ntc = p.le + 3 * p.te;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 10 * p.Cout) return;
+  const int co = i % p.Cout, cs = (i / p.Cout) % 10, n = i / (p.Cout * 10);
+  const float* te = p.temb + n * ntc;
+  float acc = 0.f;
+  if (cs == 9) {
+    for (int c = 0; c < ntc; ++c) acc += p.w1[(long long)co * p.c_in + p.c_data + c] * te[c];
+    p.tres[n * p.Cout + co] = acc;
+  } else {
+    const int ry = cs / 3, rx = cs - ry * 3;
+    for (int ky = 0; ky < 3; ++ky) {
+      if ((ry == 0 && ky == 0) || (ry == 2 && ky == 2)) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        if ((rx == 0 && kx == 0) || (rx == 2 && kx == 2)) continue;
+        for (int c = 0; c < ntc; ++c)
+          acc += p.w3[(((long long)co * p.c_in + p.c_data + c) * 3 + ky) * 3 + kx] * te[c];
+      }
+    }
+    p.tt[(n * 9 + cs) * p.Cout + co] = acc;
+  }
+}
+
+// ================================================================================================
+// conditioning MLPs (tiny): out = W1 * mid(W0 * pre(cond) + b0) + b1   or   out = W0 * pre(cond) + b0
+// resnet cond (metnet3.py:140-143): pre = ReLU, single layer.  FiLM (maxvit.py:130-135): Linear -> SiLU -> Linear.
+// ================================================================================================
+__global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_relu, const float* __restrict__ W0,
+                                const float* __restrict__ b0, int hid, const float* __restrict__ W1,
+                                const float* __restrict__ b1, int od, float* __restrict__ out) {
+  extern __shared__ float sh[];      // cd + hid
+  float* sc = sh; float* shid = sh + cd;
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < cd; i += blockDim.x) { float v = cond[n * cd + i]; sc[i] = pre_relu ? fmaxf(v, 0.f) : v; }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    float a = b0 ? b0[j] : 0.f;
+    for (int i = 0; i < cd; ++i) a += W0[j * cd + i] * sc[i];
+    if (W1) { a = a / (1.0f + expf(-a)); shid[j] = a; }          // SiLU
+    else out[(long long)n * hid + j] = a;
+  }
+  if (!W1) return;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < od; o += nw) {
+    float a = 0.f;
+    for (int j = lane; j < hid; j += 32) a += W1[(long long)o * hid + j] * shid[j];
+    a = warp_sum(a);
+    if (lane == 0) out[(long long)n * od + o] = a + (b1 ? b1[o] : 0.f);
+  }
+}
+
+// ================================================================================================
+// stem finish: per field n = b*L + l and frame pixel: v = raw3[b] + bias + tt[n][case]; ChanLayerNorm; FiLM
+// (scale+1, shift); ReLU -> h1[n].  Also the per-field residual  res[n] = rawres[b] + res_bias + tres[n].
+// One warp per output flat pixel q (C = 128: 4 channels per lane).  Pads are written as zeros.
+// ================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, T* __restrict__ res) {
+  constexpr int C = 128;
+  const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= p.pgN.pixels()) return;
+  const int lane = threadIdx.x & 31, c0 = lane * 4;
+  int n, h, w;
+  const bool valid = p.pgN.decode(q, n, h, w);
+  float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const int b = n / p.L;
+    const long long qb = p.pgB.q(b, h, w);
+    const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1), rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
+    const float4 a = *reinterpret_cast<const float4*>(p.raw3 + qb * C + c0);
+    const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0);
+    const float4 t = *reinterpret_cast<const float4*>(p.tt + ((long long)n * 9 + ry * 3 + rx) * C + c0);
+    float v[4] = {a.x + bb.x + t.x, a.y + bb.y + t.y, a.z + bb.z + t.z, a.w + bb.w + t.w};
+    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
+    const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
+    const float* film = p.film + (long long)n * 2 * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float z = v[i] * rstd * p.ln_g[c0 + i] + p.ln_b[c0 + i];
+      z = z * (film[c0 + i] + 1.0f) + film[C + c0 + i];
+      y[i] = fmaxf(z, 0.f);
+    }
+    const float4 ra = *reinterpret_cast<const float4*>(p.rawres + qb * C + c0);
+    const float4 rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
+    const float4 rt = *reinterpret_cast<const float4*>(p.tres + (long long)n * C + c0);
+    r[0] = ra.x + rb.x + rt.x; r[1] = ra.y + rb.y + rt.y; r[2] = ra.z + rb.z + rt.z; r[3] = ra.w + rb.w + rt.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { Act<T>::st(h1 + q * C + c0 + i, y[i]); Act<T>::st(res + q * C + c0 + i, r[i]); }
+}
+
+// ================================================================================================
+// 2x2 max-pool: PG layout (N,HP,WP,C) -> plain channels-last (N,HP/2,WP/2,C)   (metnet3.py:86,419)
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, PGeom pg, int C) {
+  const int Ho = pg.HP / 2, Wo = pg.WP / 2, cv = C / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)pg.N * Ho * Wo * cv;
+  if (i >= total) return;
+  const int c8 = (int)(i % cv) * 8;
+  long long p = i / cv;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho); const int n = (int)(p / Ho);
+  float m[8], v[8];
+  ld8(in + pg.q(n, 2 * ho, 2 * wo) * C + c8, m);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    ld8(in + pg.q(n, 2 * ho + (k >> 1), 2 * wo + (k & 1)) * C + c8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+  }
+  st8(out + (((long long)n * Ho + ho) * Wo + wo) * C + c8, m);
+}
+
+// ================================================================================================
+// depthwise 3x3 (pad 1) + folded BatchNorm + GELU(erf) on plain channels-last (N,H,W,C); also emits per-(n,row)
+// channel sums for the squeeze-excite mean (deterministic two-stage reduction, no atomics).  maxvit.py:91-93,39
+// block = one (n, row): C/8 channel groups x WL w-lanes.
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in, const float* __restrict__ w9,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        T* __restrict__ out, float* __restrict__ psum, int H, int W, int C) {
+  extern __shared__ float red[];               // [WL][C]
+  const int cg = C / 8, WL = blockDim.x / cg;
+  const int g = threadIdx.x % cg, wl = threadIdx.x / cg, c8 = g * 8;
+  const int h = blockIdx.x % H, n = blockIdx.x / H;
+  float wk[9][8], sc[8], sh[8], acc_sum[8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wk[k][j] = w9[k * C + c8 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c8 + j]; sh[j] = shift[c8 + j]; acc_sum[j] = 0.f; }
+  const T* base = in + (long long)n * H * W * C;
+  if (wl < WL) {
+    for (int w = wl; w < W; w += WL) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int hh = h + dy;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int ww = w + dx;
+          if (ww < 0 || ww >= W) continue;
+          ld8(base + ((long long)hh * W + ww) * C + c8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = fmaf(v[j], wk[(dy + 1) * 3 + dx + 1][j], a[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = gelu_erf(a[j] * sc[j] + sh[j]); }
+      st8(out + (((long long)n * H + h) * W + w) * C + c8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_sum[j] += a[j];               // SE mean over the fp32 values
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[wl * C + c8 + j] = acc_sum[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < WL; ++l) s += red[l * C + c];
+    psum[((long long)n * H + h) * C + c] = s;
+  }
+}
+
+// SE gate (maxvit.py:38-44): mean -> Linear(C,se) -> ReLU -> Linear(se,C) -> Sigmoid.  One block per field.
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ psum, int H, float inv_count,
+                                                      const float* __restrict__ W1, const float* __restrict__ W2,
+                                                      int C, int se, float* __restrict__ gate) {
+  extern __shared__ float sh[];            // mean[C] + hid[se]
+  float* mean = sh; float* hid = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int h = 0; h < H; ++h) s += psum[((long long)n * H + h) * C + c];
+    mean[c] = s * inv_count;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < se; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += W1[(long long)j * C + c] * mean[c];
+    a = warp_sum(a);
+    if (lane == 0) hid[j] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nw) {
+    float a = 0.f;
+    for (int j = lane; j < se; j += 32) a += W2[(long long)c * se + j] * hid[j];
+    a = warp_sum(a);
+    if (lane == 0) gate[(long long)n * C + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// x[n][p][c] *= gate[n][c]   (in place)
+template <typename T>
+__global__ void __launch_bounds__(256) se_scale_kernel(T* __restrict__ x, const float* __restrict__ gate, long long HW, int C, long long total_vec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cv = C / 8;
+  const int c8 = (int)(i % cv) * 8;
+  const long long n = (i / cv) / HW;
+  float v[8];
+  ld8(x + i * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= gate[n * C + c8 + j];
+  st8(x + i * 8, v);
+}
+
+// register-token mean over windows (maxvit.py:326): (N, nwin, R*C) -> (N, R*C), fp32
+__global__ void reg_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int nwin, int RC, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / RC; const int k = (int)(i - n * RC);
+  float s = 0.f;
+  for (int w = 0; w < nwin; ++w) s += in[(n * nwin + w) * RC + k];
+  out[i] = s / (float)nwin;
+}
+
+// ================================================================================================
+// head (metnet3.py:424-430): unpad, 1x1 conv C->1, *std + mean.  One warp per output pixel.
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ h, const float* __restrict__ w, float bias, float stdv,
+                                                   float mean, PGeom pg, int C, int H, int W, int pad_top, int pad_left,
+                                                   float* __restrict__ out, long long total) {
+  const long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int x = (int)(i % W); long long t = i / W;
+  const int y = (int)(t % H); const int n = (int)(t / H);
+  const T* p = h + pg.q(n, y + pad_top, x + pad_left) * C;
+  float a = 0.f;
+  for (int c = lane; c < C; c += 32) a += Act<T>::ld(p + c) * w[c];
+  a = warp_sum(a);
+  if (lane == 0) out[i] = (a + bias) * stdv + mean;
+}
+
+// ================================================================================================
+// Focal-R loss (not in the reference; README.md:16): loss = mean(|e| * (2*sigmoid(beta*|e|)-1)^gamma)
+// ================================================================================================
+__device__ __forceinline__ float focal_term(float e, float beta, float gamma, int mse, float* dterm) {
+  const float ae = fabsf(e);
+  const float s = 1.0f / (1.0f + expf(-beta * ae));
+  const float wgt = 2.0f * s - 1.0f;
+  const float wg = gamma == 1.0f ? wgt : powf(wgt, gamma);
+  const float base = mse ? ae * ae : ae;
+  if (dterm) {
+    const float dw = 2.0f * beta * s * (1.0f - s);
+    const float wgm1 = gamma == 1.0f ? 1.0f : (wgt > 0.f ? powf(wgt, gamma - 1.0f) : 0.f);
+    const float dbase = mse ? 2.0f * ae : 1.0f;
+    const float d = dbase * wg + base * gamma * wgm1 * dw;
+    *dterm = e > 0.f ? d : (e < 0.f ? -d : 0.f);
+  }
+  return base * wg;
+}
+
+__global__ void __launch_bounds__(256) focal_r_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                              long long n, float beta, float gamma, int mse, float* __restrict__ partial) {
+  __shared__ float sw[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += focal_term(pred[i] - tgt[i], beta, gamma, mse, nullptr);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < 8; ++i) s += sw[i]; partial[blockIdx.x] = s; }
+}
+__global__ void focal_r_final_kernel(const float* __restrict__ partial, int nb, float inv_n, float* __restrict__ loss) {
+  __shared__ float sw[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partial[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sw[i]; *loss = s * inv_n; }
+}
+__global__ void __launch_bounds__(256) focal_r_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n,
+                                                          float beta, float gamma, int mse, float gscale, float* __restrict__ grad) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d; focal_term(pred[i] - tgt[i], beta, gamma, mse, &d);
+    grad[i] = d * gscale;
+  }
+}
+
+// ================================================================================================
+// host launchers (called from vg_api.cu)
+// ================================================================================================
+static inline unsigned nblk(long long total, int per) { return (unsigned)((total + per - 1) / per); }
+
+int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, int C, int H, int W, int pad_top, int pad_left,
+                int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st) {
+  if (Cpad % 64 || Cpad < T * C) return set_error("prepare: Cpad=%d must be a multiple of 64 and >= T*C=%d", Cpad, T * C);
+  PrepParams p;
+  p.x = x; p.sB = xs[0]; p.sT = xs[1]; p.sC = xs[2]; p.sH = xs[3]; p.sW = xs[4];
+  p.B = B; p.T = T; p.C = C; p.H = H; p.W = W; p.pad_top = pad_top; p.pad_left = pad_left; p.Cpad = Cpad;
+  p.mean = mean; p.stdv = stdv; p.inv_std_unused = 0.f; p.pg = make_pgeom(B, HP, WP); p.w_fast = (xs[4] == 1);
+  const size_t esz = dtype == 0 ? 2 : 4;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)p.pg.pixels() * Cpad * esz, st);
+  if (e != cudaSuccess) return set_error("prepare memset: %s", cudaGetErrorString(e));
+  dim3 grid((W + 31) / 32, H, B * (Cpad / 64));
+  if (dtype == 0) prepare_kernel<bf16><<<grid, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
+  else prepare_kernel<float><<<grid, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
+  return check_launch("prepare_kernel");
+}
+
+int time_terms_run(const TimeParams& p, cudaStream_t st) {
+  const int N = p.B * p.L, ntc = p.le + 3 * p.te;
+  time_embed_kernel<<<nblk((long long)N * ntc, 128), 128, 0, st>>>(p);
+  int rc = check_launch("time_embed_kernel");
+  if (rc) return rc;
+  time_terms_kernel<<<nblk((long long)N * 10 * p.Cout, 256), 256, 0, st>>>(p);
+  return check_launch("time_terms_kernel");
+}
+
+int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
+                 const float* W1, const float* b1, int od, float* out, cudaStream_t st) {
+  cond_mlp_kernel<<<N, 256, (cd + hid) * sizeof(float), st>>>(cond, cd, pre_relu, W0, b0, hid, W1, b1, od, out);
+  return check_launch("cond_mlp_kernel");
+}
+
+int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStream_t st) {
+  const unsigned g = nblk(p.pgN.pixels(), 8);
+  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), reinterpret_cast<bf16*>(res));
+  else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), reinterpret_cast<float*>(res));
+  return check_launch("stem_finish_kernel");
+}
+
+int maxpool2_run(int dtype, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st) {
+  if (C % 8 || HP % 2 || WP % 2) return set_error("maxpool2: bad shape");
+  PGeom pg = make_pgeom(N, HP, WP);
+  const long long total = (long long)N * (HP / 2) * (WP / 2) * (C / 8);
+  if (dtype == 0) maxpool2_kernel<bf16><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), pg, C);
+  else maxpool2_kernel<float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), pg, C);
+  return check_launch("maxpool2_kernel");
+}
+
+int dwconv_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out, float* psum,
+               int N, int H, int W, int C, cudaStream_t st) {
+  if (C % 8) return set_error("dwconv: C %% 8 != 0");
+  const int cg = C / 8;
+  int threads = 256;
+  if (cg > 256) return set_error("dwconv: C=%d too large", C);
+  const int WL = threads / cg;
+  threads = WL * cg;
+  const size_t smem = (size_t)WL * C * sizeof(float);
+  if (dtype == 0) dwconv3x3_kernel<bf16><<<N * H, threads, smem, st>>>(reinterpret_cast<const bf16*>(in), w9, scale, shift, reinterpret_cast<bf16*>(out), psum, H, W, C);
+  else dwconv3x3_kernel<float><<<N * H, threads, smem, st>>>(reinterpret_cast<const float*>(in), w9, scale, shift, reinterpret_cast<float*>(out), psum, H, W, C);
+  return check_launch("dwconv3x3_kernel");
+}
+
+int se_gate_run(const float* psum, int N, int H, int HW, const float* W1, const float* W2, int C, int se, float* gate, cudaStream_t st) {
+  se_gate_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(psum, H, 1.0f / (float)HW, W1, W2, C, se, gate);
+  return check_launch("se_gate_kernel");
+}
+
+int se_scale_run(int dtype, void* x, const float* gate, int N, long long HW, int C, cudaStream_t st) {
+  const long long total = (long long)N * HW * (C / 8);
+  if (dtype == 0) se_scale_kernel<bf16><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<bf16*>(x), gate, HW, C, total);
+  else se_scale_kernel<float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<float*>(x), gate, HW, C, total);
+  return check_launch("se_scale_kernel");
+}
+
+int reg_mean_run(const float* in, float* out, int N, int nwin, int RC, cudaStream_t st) {
+  const long long total = (long long)N * RC;
+  reg_mean_kernel<<<nblk(total, 256), 256, 0, st>>>(in, out, nwin, RC, total);
+  return check_launch("reg_mean_kernel");
+}
+
+int head_run(int dtype, const void* h, const float* w, float bias, float stdv, float mean, int N, int HP, int WP, int C,
+             int H, int W, int pad_top, int pad_left, float* out, cudaStream_t st) {
+  PGeom pg = make_pgeom(N, HP, WP);
+  const long long total = (long long)N * H * W;
+  if (dtype == 0) head_kernel<bf16><<<nblk(total, 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(h), w, bias, stdv, mean, pg, C, H, W, pad_top, pad_left, out, total);
+  else head_kernel<float><<<nblk(total, 8), 256, 0, st>>>(reinterpret_cast<const float*>(h), w, bias, stdv, mean, pg, C, H, W, pad_top, pad_left, out, total);
+  return check_launch("head_kernel");
+}
+
+int focal_r_fwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float* partial,
+                    int nb, float* loss, cudaStream_t st) {
+  focal_r_partial_kernel<<<nb, 256, 0, st>>>(pred, tgt, n, beta, gamma, mse, partial);
+  int rc = check_launch("focal_r_partial_kernel");
+  if (rc) return rc;
+  focal_r_final_kernel<<<1, 256, 0, st>>>(partial, nb, 1.0f / (float)n, loss);
+  return check_launch("focal_r_final_kernel");
+}
+
+int focal_r_bwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float gscale,
+                    float* grad, cudaStream_t st) {
+  focal_r_bwd_kernel<<<nblk(n, 256 * 4) < 4096 ? nblk(n, 256 * 4) : 4096, 256, 0, st>>>(pred, tgt, n, beta, gamma, mse, gscale, grad);
+  return check_launch("focal_r_bwd_kernel");
+}
+
+}  // namespace vg

@@ -1,0 +1,219 @@
+"""MaxViT backbone with the reference's nn.Module API (/root/reference/src/maxvit.py:224-341) on libvitgrid kernels.
+
+Same constructor arguments, parameter names and shapes as the reference ``MaxViT`` so reference state dicts load
+unchanged.  The sub-modules below are *parameter holders* laid out to reproduce the reference's state-dict keys
+(e.g. ``layers.0.0.3.weight`` = depthwise conv, ``layers.0.1.to_qkv.weight``); the computation is the fused
+pipeline in ``MaxViT.forward_cl``:
+
+  MBConv  : 1x1 GEMM + BN + GELU  ->  depthwise 3x3 + BN + GELU (+SE row sums)  ->  SE gate, scale  ->  1x1 GEMM + BN (+x)
+  attention (block, then grid): gather+LN+FiLM -> QKV GEMM -> per-(window,head) core -> out-proj GEMM whose
+            epilogue adds the residual and scatters through the inverse partition map.
+
+Only the eval-mode forward exists so far (BatchNorm uses running statistics, dropout is identity).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class RMSNorm(nn.Module):
+    """holder for q/k norm gamma (maxvit.py:18-30)"""
+
+    def __init__(self, dim, *, heads):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(heads, 1, dim))
+
+
+class SqueezeExcitation(nn.Module):
+    """holder: gate.1 = Linear(dim, hidden), gate.3 = Linear(hidden, dim) (maxvit.py:33-48)"""
+
+    def __init__(self, dim, shrinkage_rate=0.25):
+        super().__init__()
+        hidden = int(dim * shrinkage_rate)
+        self.gate = nn.Sequential(nn.Identity(), nn.Linear(dim, hidden, bias=False), nn.ReLU(),
+                                  nn.Linear(hidden, dim, bias=False), nn.Sigmoid(), nn.Identity())
+
+
+class MBConvResidual(nn.Module):
+    """holder that reproduces the ``.fn.`` key level of residual MBConv blocks (maxvit.py:50-59)"""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+def MBConv(dim_in, dim_out, *, downsample, expansion_rate=4, shrinkage_rate=0.25):
+    hidden = int(expansion_rate * dim_out)
+    net = nn.Sequential(
+        nn.Conv2d(dim_in, hidden, 1), nn.BatchNorm2d(hidden), nn.GELU(),
+        nn.Conv2d(hidden, hidden, 3, padding=1, groups=hidden), nn.BatchNorm2d(hidden), nn.GELU(),
+        SqueezeExcitation(hidden, shrinkage_rate=shrinkage_rate),
+        nn.Conv2d(hidden, dim_out, 1), nn.BatchNorm2d(dim_out))
+    # the first layer of a stage has no residual even though it never downsamples (maxvit.py:85,99-100,270)
+    if dim_in == dim_out and not downsample:
+        net = MBConvResidual(net)
+    return net
+
+
+def rel_pos_indices(window_size: int, num_registers: int) -> torch.Tensor:
+    """closed form of maxvit.py:156-168 (bit-exact, tests/test_indices.py)"""
+    w, r = window_size, num_registers
+    s = r + w * w
+    idx = torch.full((s, s), (2 * w - 1) ** 2, dtype=torch.int64)
+    t = torch.arange(w * w)
+    a, b = t // w, t % w
+    idx[r:, r:] = (a[:, None] - a[None, :] + w - 1) * (2 * w - 1) + (b[:, None] - b[None, :] + w - 1)
+    return idx
+
+
+class Attention(nn.Module):
+    """parameter holder for one window/grid attention (maxvit.py:106-168)"""
+
+    def __init__(self, dim, cond_dim=None, heads=32, dim_head=32, dropout=0., window_size=8, num_registers=1):
+        super().__init__()
+        assert num_registers > 0
+        assert (dim % dim_head) == 0, 'dimension should be divisible by dimension per head'
+        if cond_dim is None:
+            raise NotImplementedError("vit_grid_model_b200.Attention requires cond_dim (FiLM conditioning), as MaxViT always passes it")
+        inner = dim_head * heads
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
+        self.window_size, self.num_registers, self.dropout_p = window_size, num_registers, dropout
+        self.film = nn.Sequential(nn.Linear(cond_dim, dim * 2), nn.SiLU(), nn.Linear(dim * 2, dim * 2), nn.Identity())
+        self.norm = nn.LayerNorm(dim, elementwise_affine=False)
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.q_norm = RMSNorm(dim_head, heads=heads)
+        self.k_norm = RMSNorm(dim_head, heads=heads)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), nn.Dropout(dropout))
+        self.rel_pos_bias = nn.Embedding((2 * window_size - 1) ** 2 + 1, heads)
+        self.register_buffer('rel_pos_indices', rel_pos_indices(window_size, num_registers), persistent=False)
+
+
+def _fold_bn(conv_bias, bn: nn.BatchNorm2d):
+    """eval BatchNorm after a conv with bias -> per-channel (scale, shift) in fp32"""
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.float() - bn.running_mean.float() * scale + conv_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class MaxViT(nn.Module):
+    def __init__(self, dim, depth, cond_dim=32, heads=32, dim_head=32, vit_window_size=8, mbconv_expansion_rate=4,
+                 mbconv_shrinkage_rate=0.25, dropout=0.1, num_register_tokens=4):
+        super().__init__()
+        depth = (depth,) if isinstance(depth, int) else tuple(depth)
+        assert num_register_tokens > 0
+        if len(depth) != 1:
+            # the reference builds len(depth)-1 stages of doubling width for tuples (maxvit.py:246-262); MetNet3
+            # only ever passes an int
+            raise NotImplementedError("vit_grid_model_b200.MaxViT supports a single stage (int depth)")
+        self.cond_dim = cond_dim
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
+        self.vit_window_size = vit_window_size
+        self.num_register_tokens = num_register_tokens
+        self.layers = nn.ModuleList([])
+        self.register_tokens = nn.ParameterList([])
+        for stage_ind in range(depth[0]):
+            conv = MBConv(dim, dim, downsample=(stage_ind == 0), expansion_rate=mbconv_expansion_rate,
+                          shrinkage_rate=mbconv_shrinkage_rate)
+            kw = dict(dim=dim, cond_dim=cond_dim, heads=heads, dim_head=dim_head, dropout=dropout,
+                      window_size=vit_window_size, num_registers=num_register_tokens)
+            self.layers.append(nn.ModuleList([conv, Attention(**kw), Attention(**kw)]))
+            self.register_tokens.append(nn.Parameter(torch.randn(num_register_tokens, dim)))
+        self.compute_dtype = torch.bfloat16
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ weights -> kernel layouts
+    def set_precision(self, precision: str):
+        self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        return self
+
+    def _pack_key(self, dtype):
+        return (dtype, tuple((p.data_ptr(), p._version) for p in self.parameters()),
+                tuple((b.data_ptr(), b._version) for b in self.buffers()))
+
+    @torch.no_grad()
+    def packed(self, dtype):
+        key = self._pack_key(dtype)
+        if self._packed_key == key:
+            return self._packed
+        layers = []
+        for li, (conv, battn, gattn) in enumerate(self.layers):
+            seq = conv.fn if isinstance(conv, MBConvResidual) else conv
+            P = {"residual": isinstance(conv, MBConvResidual)}
+            P["w_exp"] = seq[0].weight.flatten(1).to(dtype).contiguous()                     # (hidden, dim)
+            P["s_exp"], P["t_exp"] = _fold_bn(seq[0].bias, seq[1])
+            P["w_dw"] = seq[3].weight.float().reshape(seq[3].weight.shape[0], 9).t().contiguous()   # [9][hidden]
+            P["s_dw"], P["t_dw"] = _fold_bn(seq[3].bias, seq[4])
+            P["se_w1"] = seq[6].gate[1].weight.float().contiguous()
+            P["se_w2"] = seq[6].gate[3].weight.float().contiguous()
+            P["w_proj"] = seq[7].weight.flatten(1).to(dtype).contiguous()                    # (dim, hidden)
+            P["s_proj"], P["t_proj"] = _fold_bn(seq[7].bias, seq[8])
+            for name, att in (("block", battn), ("grid", gattn)):
+                P[name] = dict(
+                    film_w0=att.film[0].weight.float().contiguous(), film_b0=att.film[0].bias.float().contiguous(),
+                    film_w1=att.film[2].weight.float().contiguous(), film_b1=att.film[2].bias.float().contiguous(),
+                    w_qkv=att.to_qkv.weight.to(dtype).contiguous(),
+                    q_gamma=att.q_norm.gamma.float().reshape(-1).contiguous(),
+                    k_gamma=att.k_norm.gamma.float().reshape(-1).contiguous(),
+                    w_out=att.to_out[0].weight.to(dtype).contiguous(),
+                    bias_table=att.rel_pos_bias.weight.float().contiguous())
+            P["reg"] = self.register_tokens[li].float().contiguous()
+            layers.append(P)
+        self._packed, self._packed_key = layers, key
+        return layers
+
+    # ------------------------------------------------------------------ forward
+    def _attention(self, x, film, P, reg_in, grid_mode, want_reg_out):
+        """x: CL (N,H,W,C).  returns (x + attn(x), reg_out)"""
+        N, H, W, C = x.shape
+        w, R = self.vit_window_size, self.num_register_tokens
+        tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
+        qkv = ops.gemm(tokens, P["w_qkv"])
+        del tokens
+        att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head)
+        del qkv
+        return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out)
+
+    def forward_cl(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        """channels-last entry used by MetNet3: x (N,H,W,dim) in the compute dtype, cond (N,cond_dim) fp32"""
+        _lib.require_device()
+        if self.training:
+            raise NotImplementedError("training-mode forward (batch-stat BatchNorm, dropout, backward) is not built yet")
+        N, H, W, C = x.shape
+        w = self.vit_window_size
+        assert H % w == 0 and W % w == 0, "feature map must be divisible by the window size"
+        assert cond.shape == (N, self.cond_dim)
+        cond = cond.float().contiguous()
+        nwin = (H // w) * (W // w)
+        for P in self.packed(x.dtype):
+            h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1)
+            hidden = h.shape[1]
+            h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
+            del h
+            gate = ops.se_gate(psum, W, P["se_w1"], P["se_w2"])
+            ops.se_scale_(h2, gate)
+            y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
+                         res=x.view(N * H * W, C) if P["residual"] else None)
+            del h2
+            x = y.view(N, H, W, C)
+            fb = P["block"]
+            film = ops.cond_mlp(cond, fb["film_w0"], fb["film_b0"], fb["film_w1"], fb["film_b1"])
+            x, reg_out = self._attention(x, film, fb, P["reg"], False, True)
+            reg = ops.reg_mean(reg_out, N, nwin)
+            fg = P["grid"]
+            film = ops.cond_mlp(cond, fg["film_w0"], fg["film_b0"], fg["film_w1"], fg["film_b1"])
+            x, _ = self._attention(x, film, fg, reg, True, False)
+        return x
+
+    def forward(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        """reference signature (maxvit.py:289): x (N,dim,H,W) -> (N,dim,H,W), same dtype as x"""
+        assert cond.shape == (x.shape[0], self.cond_dim)
+        if not x.is_cuda:
+            raise _lib.VitGridError("vit_grid_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        x_cl = x.permute(0, 2, 3, 1).to(self.compute_dtype).contiguous()
+        y = self.forward_cl(x_cl, cond)
+        return y.permute(0, 3, 1, 2).to(x.dtype).contiguous()

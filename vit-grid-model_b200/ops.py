@@ -1,0 +1,229 @@
+"""Tensor-level wrappers over the C ABI (include/vitgrid.h).  PyTorch is used for device memory and streams
+only; every computation below is a libvitgrid kernel launch on the caller's current stream."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+DT_CODE = {torch.bfloat16: 0, torch.float32: 1}
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _scratch(dtype, elems, device):
+    """fp32-mode GEMMs accumulate into a caller-provided scratch; bf16 mode needs none."""
+    if dtype == torch.float32:
+        t = torch.empty(int(elems), dtype=torch.float32, device=device)
+        return t, t.data_ptr(), t.numel()
+    return None, None, 0
+
+
+def pg_pixels(N, HP, WP):
+    return (N * (HP + 1) + 1) * (WP + 1)
+
+
+def pg_empty(N, HP, WP, C, dtype, device):
+    return torch.empty(pg_pixels(N, HP, WP), C, dtype=dtype, device=device)
+
+
+def pg_from_nchw(x, dtype):
+    """(N,C,H,W) -> PG buffer (test helper / standalone-module boundary; plain torch indexing)."""
+    N, C, H, W = x.shape
+    buf = torch.zeros(N * (H + 1) + 1, W + 1, C, dtype=dtype, device=x.device)
+    buf[:N * (H + 1)].view(N, H + 1, W + 1, C)[:, 1:, 1:] = x.permute(0, 2, 3, 1).to(dtype)
+    return buf.view(-1, C)
+
+
+def pg_to_nchw(buf, N, H, W):
+    C = buf.shape[1]
+    v = buf.view(N * (H + 1) + 1, W + 1, C)[:N * (H + 1)].view(N, H + 1, W + 1, C)[:, 1:, 1:]
+    return v.permute(0, 3, 1, 2).contiguous()
+
+
+def prepare(x, cfg_pads, HP, WP, Cpad, mean, std, dtype):
+    B, T, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_cuda
+    out = torch.empty(pg_pixels(B, HP, WP), Cpad, dtype=dtype, device=x.device)
+    strides = (ctypes.c_longlong * 5)(*x.stride())
+    pl, _, pt, _ = cfg_pads
+    _lib.call("vg_prepare_fwd", DT_CODE[dtype], x.data_ptr(), strides, B, T, C, H, W, pt, pl, HP, WP, Cpad,
+              float(mean), float(std), out.data_ptr(), _st())
+    return out
+
+
+def time_terms(ts, B, L, emb_lead, emb_m, emb_d, emb_h, w3, w1, c_data, Cout):
+    le, te = emb_lead.shape[1], emb_m.shape[1]
+    N = B * L
+    dev = ts.device
+    temb = torch.empty(N, le + 3 * te, dtype=torch.float32, device=dev)
+    cond = torch.empty(N, le, dtype=torch.float32, device=dev)
+    tt = torch.empty(N, 9, Cout, dtype=torch.float32, device=dev)
+    tres = torch.empty(N, Cout, dtype=torch.float32, device=dev)
+    assert ts.dtype == torch.float32 and ts.shape[1] > 6 and ts.shape[2] >= 4, "timestamps must be (B, >=7, 4) fp32"
+    sB, sT, sF = ts.stride()
+    _lib.call("vg_time_terms_fwd", ts.data_ptr(), sB, sT, sF, B, L, le, te, emb_lead.data_ptr(), emb_m.data_ptr(),
+              emb_d.data_ptr(), emb_h.data_ptr(), w3.data_ptr(), _p(w1), w3.shape[1], c_data, Cout,
+              temb.data_ptr(), cond.data_ptr(), tt.data_ptr(), tres.data_ptr(), _st())
+    return temb, cond, tt, tres
+
+
+def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
+    N, cd = cond.shape
+    hid = W0.shape[0]
+    od = W1.shape[0] if W1 is not None else hid
+    out = torch.empty(N, od, dtype=torch.float32, device=cond.device)
+    _lib.call("vg_cond_mlp_fwd", cond.data_ptr(), N, cd, int(pre_relu), W0.data_ptr(), _p(b0), hid, _p(W1), _p(b1), od,
+              out.data_ptr(), _st())
+    return out
+
+
+def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per_batch=0, bias=None, scale=None,
+         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None):
+    dtype = A.dtype
+    rowsA, Ca = A.shape
+    M = rowsA if M is None else M
+    Ntot = n_out if n_out is not None else (b_rows_per_batch if rows_per_batch else Wt.shape[0])
+    if out is None:
+        out = torch.empty(M, Ntot, dtype=torch.float32 if out_f32 else dtype, device=A.device)
+    shifts = (ctypes.c_int * ntaps)(*tap_shift)
+    keep, sp, sn = _scratch(dtype, M * Ntot, A.device)
+    _lib.call("vg_gemm_fwd", DT_CODE[dtype], A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
+              rows_per_batch, b_rows_per_batch, _p(bias), _p(scale), _p(shift), act, _p(res),
+              res.shape[1] if res is not None else 0, out.data_ptr(), out.shape[1], int(out_f32), sp, sn, _st())
+    return out
+
+
+def conv_tap_shifts(WP):
+    P = WP + 1
+    return tuple((ky - 1) * P + (kx - 1) for ky in range(3) for kx in range(3))
+
+
+def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP):
+    dtype = x.dtype
+    keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
+    _lib.call("vg_conv3x3_ln_fwd", DT_CODE[dtype], x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
+              ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), out.data_ptr(), N, HP, WP, sp, sn, _st())
+    return out
+
+
+def stem_finish(raw3, rawres, bias3, bias1, tt, tres, ln_g, ln_b, eps, film, B, L, HP, WP, h1, res):
+    _lib.call("vg_stem_finish_fwd", DT_CODE[h1.dtype], raw3.data_ptr(), rawres.data_ptr(), bias3.data_ptr(),
+              bias1.data_ptr(), tt.data_ptr(), tres.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), float(eps),
+              film.data_ptr(), B, L, HP, WP, h1.data_ptr(), res.data_ptr(), _st())
+
+
+def pool2(x, N, HP, WP, out=None):
+    C = x.shape[1]
+    if out is None:
+        out = torch.empty(N, HP // 2, WP // 2, C, dtype=x.dtype, device=x.device)
+    _lib.call("vg_pool2_fwd", DT_CODE[x.dtype], x.data_ptr(), out.data_ptr(), N, HP, WP, C, _st())
+    return out
+
+
+def dw3x3_bnact(x, w9, scale, shift, out=None):
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    psum = torch.empty(N, H, C, dtype=torch.float32, device=x.device)
+    _lib.call("vg_dw3x3_bnact_fwd", DT_CODE[x.dtype], x.data_ptr(), w9.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+              out.data_ptr(), psum.data_ptr(), N, H, W, C, _st())
+    return out, psum
+
+
+def se_gate(psum, W, W1, W2):
+    N, H, C = psum.shape
+    gate = torch.empty(N, C, dtype=torch.float32, device=psum.device)
+    _lib.call("vg_se_gate_fwd", psum.data_ptr(), N, H, W, W1.data_ptr(), W2.data_ptr(), C, W1.shape[0], gate.data_ptr(), _st())
+    return gate
+
+
+def se_scale_(x, gate):
+    N, H, W, C = x.shape
+    _lib.call("vg_se_scale_fwd", DT_CODE[x.dtype], x.data_ptr(), gate.data_ptr(), N, H * W, C, _st())
+    return x
+
+
+def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None):
+    N, Hl, Wl, C = x.shape
+    S = R + win * win
+    rows = N * (Hl // win) * (Wl // win) * S
+    if out is None:
+        out = torch.empty(rows, C, dtype=x.dtype, device=x.device)
+    _lib.call("vg_attn_gather_fwd", DT_CODE[x.dtype], x.data_ptr(), reg.data_ptr(), int(reg.dim() == 3), film.data_ptr(),
+              N, Hl, Wl, C, win, R, int(grid_mode), float(eps), out.data_ptr(), _st())
+    return out
+
+
+def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None):
+    if out is None:
+        out = torch.empty(qkv.shape[0], heads * dh, dtype=qkv.dtype, device=qkv.device)
+    _lib.call("vg_attn_core_fwd", DT_CODE[qkv.dtype], qkv.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
+              bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, out.data_ptr(), _st())
+    return out
+
+
+def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None):
+    N, Hl, Wl, C = x_in.shape
+    nwin = (Hl // win) * (Wl // win)
+    if x_out is None:
+        x_out = torch.empty_like(x_in)
+    reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x_in.device) if want_reg_out else None
+    keep, sp, sn = _scratch(attn.dtype, attn.shape[0] * C, attn.device)
+    _lib.call("vg_attn_out_fwd", DT_CODE[attn.dtype], attn.data_ptr(), attn.shape[1], Wt.data_ptr(), x_in.data_ptr(),
+              reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out), x_out.data_ptr(), N, Hl, Wl, C, win, R,
+              int(grid_mode), sp, sn, _st())
+    return x_out, reg_out
+
+
+def reg_mean(reg_out, N, nwin):
+    R, C = reg_out.shape[1], reg_out.shape[2]
+    out = torch.empty(N, R, C, dtype=torch.float32, device=reg_out.device)
+    _lib.call("vg_reg_mean_fwd", reg_out.data_ptr(), out.data_ptr(), N, nwin, R * C, _st())
+    return out
+
+
+def convT2(x, Wt, bias, out):
+    """x CL (N,Hl,Wl,C) -> out PG (N,2Hl,2Wl,C); `out` must already hold zeros at its pad positions."""
+    N, Hl, Wl, C = x.shape
+    keep, sp, sn = _scratch(x.dtype, N * Hl * Wl * 4 * C, x.device)
+    _lib.call("vg_convT2_fwd", DT_CODE[x.dtype], x.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), N, Hl, Wl,
+              C, sp, sn, _st())
+    return out
+
+
+def head(h, w, bias, std, mean, N, HP, WP, H, W, pads, out=None):
+    C = h.shape[1]
+    if out is None:
+        out = torch.empty(N, H, W, dtype=torch.float32, device=h.device)
+    pl, _, pt, _ = pads
+    _lib.call("vg_head_fwd", DT_CODE[h.dtype], h.data_ptr(), w.data_ptr(), float(bias), float(std), float(mean), N, HP, WP,
+              C, H, W, pt, pl, out.data_ptr(), _st())
+    return out
+
+
+def focal_r_forward(pred, target, beta=0.2, gamma=1.0, mse=False):
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32 and pred.is_contiguous() and target.is_contiguous()
+    n = pred.numel()
+    nb = max(1, min(1024, (n + 1023) // 1024))
+    partial = torch.empty(nb, dtype=torch.float32, device=pred.device)
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    _lib.call("vg_focal_r_fwd", pred.data_ptr(), target.data_ptr(), n, float(beta), float(gamma), int(mse),
+              partial.data_ptr(), nb, loss.data_ptr(), _st())
+    return loss
+
+
+def focal_r_backward(pred, target, grad_out, beta=0.2, gamma=1.0, mse=False):
+    n = pred.numel()
+    grad = torch.empty_like(pred)
+    _lib.call("vg_focal_r_bwd", pred.data_ptr(), target.data_ptr(), n, float(beta), float(gamma), int(mse),
+              float(grad_out) / n, grad.data_ptr(), _st())
+    return grad
