@@ -233,6 +233,8 @@ def main():
     per = {}
     for name, tag, a, b in trace:
         per.setdefault(name, []).append(a.elapsed_time(b))
+        if name == "vg_gemm_fwd":
+            per.setdefault(f"  gemm[{tag}]", []).append(a.elapsed_time(b))
     conv_ms = per.get("vg_conv3x3_ln_fwd", [])
     peaks = {}
     try:
@@ -258,7 +260,7 @@ def main():
 
     if rank == 0:
         if args.trace:
-            tot = sum(sum(v) for v in per.values())
+            tot = sum(sum(v) for k, v in per.items() if not k.startswith("  "))
             for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
                 print(f"# {name:24s} calls/step {len(v) // args.steps:3d}  ms/step {sum(v) / args.steps:9.3f}  {100 * sum(v) / tot:5.1f}%", file=sys.stderr)
         cpu = None

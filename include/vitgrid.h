@@ -8,7 +8,8 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer unless stated otherwise; `stream` is a cudaStream_t passed as void*
- *  - dtype: 0 = bf16 activations/weights (tcgen05 tensor-core path), 1 = fp32 (SIMT FFMA path, "fp32 mode")
+ *  - dtype: 0 = bf16 activations/weights (tcgen05 kind::f16), 1 = fp32 (SIMT FFMA path, "fp32 mode"),
+ *    2 = fp32 storage with tcgen05 kind::tf32 MMA (GEMM entry points only; elsewhere 2 behaves as 1)
  *  - functions never allocate, never synchronise and never touch the default stream; workspaces are
  *    caller-provided; return 0 on success, non-zero on error (message via vg_last_error())
  *  - there is NO CPU fallback: on a device that is not sm_100 every launch fails loudly
@@ -72,7 +73,7 @@ VG_API int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu,
  * (maxvit.py:88-90, 95-96), nn.Linear to_qkv (maxvit.py:139) and the raw 3x3 stem conv (ntaps=9).
  * A: [rowsA][Ca]; Wt: [Ntot*(batches)][ntaps*Ca]; tap_shift: HOST int[ntaps]; act: 0 none, 1 GELU, 2 ReLU.
  * rows_per_batch>0 selects per-batch weights (Wt rows advance by b_rows_per_batch every rows_per_batch rows).
- * out_f32=1 stores fp32 regardless of dtype.  scratch (fp32, M*Ntot) is used by fp32 mode only. */
+ * out_f32: 0 = output in the activation dtype, 1 = fp32, 2 = bf16.  scratch (fp32, M*Ntot) is used by fp32 mode only. */
 VG_API int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* Wt, int Ntot, int ntaps,
                 const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
                 const float* bias, const float* scale, const float* shift, int act, const void* res,
@@ -93,8 +94,8 @@ VG_API int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres,
                        const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
                        const float* film, int B, int L, int HP, int WP, void* h1, void* res, void* stream);
 
-/* metnet3.py:86,419 -- MaxPool2d(2,2): PG (N,HP,WP,C) -> CL (N,HP/2,WP/2,C) */
-VG_API int vg_pool2_fwd(int dtype, const void* in, void* out, int N, int HP, int WP, int C, void* stream);
+/* metnet3.py:86,419 -- MaxPool2d(2,2): PG (N,HP,WP,C) -> CL (N,HP/2,WP/2,C); out_f32=1: bf16 in, fp32 out */
+VG_API int vg_pool2_fwd(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, void* stream);
 
 /* maxvit.py:91-93 -- depthwise 3x3 + BatchNorm(eval, folded into scale/shift) + GELU on CL (N,H,W,C);
  * w9: fp32 [9][C]; psum: fp32 (N,H,C) per-row channel sums for the squeeze-excite mean. */
@@ -131,9 +132,9 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
 VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);
 
 /* metnet3.py:88-89,421 -- ConvTranspose2d(k=2,s=2) as GEMM + depth-to-space: CL (N,Hl,Wl,C) -> PG (N,2Hl,2Wl,C).
- * Wt: [4*C][C], row (di*2+dj)*C+co = weight[ci][co][di][dj]. */
-VG_API int vg_convT2_fwd(int dtype, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl,
-                  int C, float* scratch, long long scratch_elems, void* stream);
+ * Wt: [4*C][C], row (di*2+dj)*C+co = weight[ci][co][di][dj].  out_bf16=1 writes bf16 whatever dtype is. */
+VG_API int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl,
+                  int Wl, int C, float* scratch, long long scratch_elems, void* stream);
 
 /* metnet3.py:424-430 -- unpad, Conv2d 1x1 C->1, *std + mean: PG (N,HP,WP,C) -> fp32 (N,H,W) */
 VG_API int vg_head_fwd(int dtype, const void* h, const float* w, float bias, float pm_std, float pm_mean, int N, int HP,

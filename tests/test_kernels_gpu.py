@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 
 DTYPES = [torch.float32, torch.bfloat16]
 TOL = {torch.float32: 1e-4, torch.bfloat16: 1.5e-2}
+# GEMM modes: (storage dtype, tf32 tensor cores?) -> tolerance of a single GEMM against fp32
+GEMM_MODES = [(torch.float32, False), (torch.bfloat16, False), (torch.float32, True)]
+GEMM_TOL = {(torch.float32, False): 2e-5, (torch.bfloat16, False): 6e-3, (torch.float32, True): 1.5e-3}
 
 
 def ops():
@@ -41,25 +44,29 @@ def q(t, dtype):
 
 
 # ------------------------------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("M,K,N", [(1000, 128, 128), (4099, 512, 384), (130, 1024, 128), (20000, 128, 3072)])
-def test_gemm_plain(dtype, M, K, N):
+@pytest.mark.parametrize("mode", GEMM_MODES)
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 128), (4099, 512, 384), (130, 1024, 128), (20000, 128, 3072), (300, 96, 256)])
+def test_gemm_plain(mode, M, K, N):
+    dtype, tf32 = mode
+    if not tf32 and K % 64:
+        pytest.skip("bf16 / SIMT K blocks are 64 wide; only the tf32 path takes K % 32 == 0")
     o = ops()
     A, W = q(rnd(M, K, seed=1), dtype), q(rnd(N, K, seed=2) / math.sqrt(K), dtype)
-    out = o.gemm(A.cuda().to(dtype), W.cuda().to(dtype))
-    assert rel_err(out, A @ W.t()) < (2e-5 if dtype == torch.float32 else 6e-3)
+    out = o.gemm(A.cuda().to(dtype), W.cuda().to(dtype), tf32=tf32)
+    assert rel_err(out, A @ W.t()) < GEMM_TOL[mode]
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_gemm_bn_gelu_residual(dtype):
+@pytest.mark.parametrize("mode", GEMM_MODES)
+def test_gemm_bn_gelu_residual(mode):
+    dtype, tf32 = mode
     o = ops()
     M, K, N = 3000, 128, 512
     A, W = q(rnd(M, K, seed=1), dtype), q(rnd(N, K, seed=2) / math.sqrt(K), dtype)
     scale, shift, res = 0.5 + torch.rand(N), rnd(N, seed=4), q(rnd(M, N, seed=5), dtype)
     out = o.gemm(A.cuda().to(dtype), W.cuda().to(dtype), scale=scale.cuda(), shift=shift.cuda(), act=1,
-                 res=res.cuda().to(dtype))
+                 res=res.cuda().to(dtype), tf32=tf32)
     ref = F.gelu((A @ W.t()) * scale + shift) + res
-    assert rel_err(out, ref) < TOL[dtype]
+    assert rel_err(out, ref) < (2e-3 if tf32 else TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -179,11 +186,13 @@ def test_cond_mlps():
 
 
 # ------------------------------------------------------------------------------------------ MBConv pieces
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_pool2(dtype):
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                             (torch.bfloat16, torch.float32)])
+def test_pool2(dtype, out_dtype):
     o = ops()
     x = q(rnd(3, 128, 14, 28, seed=1), dtype)
-    got = o.pool2(o.pg_from_nchw(x.cuda(), dtype), 3, 14, 28)
+    got = o.pool2(o.pg_from_nchw(x.cuda(), dtype), 3, 14, 28, out_dtype=out_dtype)
+    assert got.dtype == out_dtype
     assert torch.equal(got.float().cpu().permute(0, 3, 1, 2), F.max_pool2d(x, 2, 2))
 
 
@@ -213,10 +222,11 @@ def _attn_sd(dim, heads, dh, w, r, seed):
     return synth.make_state_dict(spec, seed=seed)
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", GEMM_MODES)
 @pytest.mark.parametrize("grid_mode", [False, True])
-def test_attention_layer(dtype, grid_mode):
+def test_attention_layer(mode, grid_mode):
     """gather+LN+FiLM -> QKV GEMM -> core -> out-proj(+residual, scatter) == oracle attention + residual"""
+    dtype, tf32 = mode
     o = ops()
     N, H, W, C, heads, dh, w, R = 2, 14, 21, 128, 32, 32, 7, 4
     sd = _attn_sd(C, heads, dh, w, R, seed=7)
@@ -241,46 +251,47 @@ def test_attention_layer(dtype, grid_mode):
     film = torch.cat([gamma, beta], dim=1).cuda().contiguous()
     xd = x.cuda().to(dtype)
     tokens = o.attn_gather(xd, reg.cuda(), film, w, R, grid_mode)
-    qkv = o.gemm(tokens, sd["to_qkv.weight"].cuda().to(dtype))
+    qkv = o.gemm(tokens, sd["to_qkv.weight"].cuda().to(dtype), tf32=tf32)
     att = o.attn_core(qkv, sd["q_norm.gamma"].reshape(-1).cuda(), sd["k_norm.gamma"].reshape(-1).cuda(),
                       sd["rel_pos_bias.weight"].cuda(), N, H, W, w, R, heads, dh)
-    x_out, reg_out = o.attn_out(att, sd["to_out.0.weight"].cuda().to(dtype), xd, reg.cuda(), w, R, grid_mode, True)
-    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    x_out, reg_out = o.attn_out(att, sd["to_out.0.weight"].cuda().to(dtype), xd, reg.cuda(), w, R, grid_mode, True, tf32=tf32)
+    tol = {(torch.float32, False): 1e-4, (torch.bfloat16, False): 2e-2, (torch.float32, True): 3e-3}[mode]
     assert rel_err(x_out.reshape(N, H * W, C), ref_x) < tol
     assert rel_err(reg_out, ref[:, :R]) < tol
     mean = o.reg_mean(reg_out, N, nwin)
     assert rel_err(mean, reg_out.view(N, nwin, R, C).mean(1)) < 1e-5
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_maxvit_module(dtype):
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3), ("bf16_all", 3e-2)])
+def test_maxvit_module(precision, tol):
     """MaxViT nn.Module (reference API) vs oracle, depth 2 (second MBConv is residual)"""
     from vit_grid_model_b200 import MaxViT
     dim, depth, heads, dh, w, R, N, H, W = 128, 2, 32, 32, 7, 4, 3, 14, 21
     sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, R), seed=5)
     m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=R)
     m.load_state_dict(sd, strict=True)
-    m = m.cuda().eval().set_precision("bf16" if dtype == torch.bfloat16 else "fp32")
+    m = m.cuda().eval().set_precision(precision)
     x, cond = rnd(N, dim, H, W, seed=1), rnd(N, 2, seed=2)
     with torch.no_grad():
         y = m(x.cuda(), cond.cuda())
     ref = mo.maxvit_forward(x, cond, sd, depth=depth, heads=heads, window=w, num_reg=R)
     assert y.shape == ref.shape and y.dtype == torch.float32
-    assert rel_err(y, ref) < (1e-4 if dtype == torch.float32 else 3e-2)
+    assert rel_err(y, ref) < tol
 
 
 # ------------------------------------------------------------------------------------------ decoder side
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_convT2(dtype):
+@pytest.mark.parametrize("dtype,tf32,out_dtype", [(torch.float32, False, torch.float32), (torch.bfloat16, False, torch.bfloat16),
+                                                  (torch.float32, True, torch.bfloat16)])
+def test_convT2(dtype, tf32, out_dtype):
     o = ops()
     N, Hl, Wl, C = 2, 7, 14, 128
     x = q(rnd(N, C, Hl, Wl, seed=1), dtype)
     w, b = q(rnd(C, C, 2, 2, seed=2) / math.sqrt(C), dtype), rnd(C, seed=3, scale=0.1)
-    out = torch.zeros(o.pg_pixels(N, 2 * Hl, 2 * Wl), C, dtype=dtype, device="cuda")
+    out = torch.zeros(o.pg_pixels(N, 2 * Hl, 2 * Wl), C, dtype=out_dtype, device="cuda")
     o.convT2(x.permute(0, 2, 3, 1).contiguous().cuda().to(dtype),
-             w.permute(2, 3, 1, 0).reshape(4 * C, C).contiguous().cuda().to(dtype), b.cuda(), out)
+             w.permute(2, 3, 1, 0).reshape(4 * C, C).contiguous().cuda().to(dtype), b.cuda(), out, tf32=tf32)
     ref = F.conv_transpose2d(x, w, b, stride=2)
-    assert rel_err(o.pg_to_nchw(out, N, 2 * Hl, 2 * Wl), ref) < TOL[dtype]
+    assert rel_err(o.pg_to_nchw(out, N, 2 * Hl, 2 * Wl), ref) < TOL[out_dtype]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

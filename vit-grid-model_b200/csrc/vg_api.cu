@@ -119,8 +119,8 @@ int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const 
   return stem_finish_run(dtype, p, h1, res, (cudaStream_t)stream);
 }
 
-int vg_pool2_fwd(int dtype, const void* in, void* out, int N, int HP, int WP, int C, void* stream) {
-  return maxpool2_run(dtype, in, out, N, HP, WP, C, (cudaStream_t)stream);
+int vg_pool2_fwd(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, void* stream) {
+  return maxpool2_run(dtype, out_f32, in, out, N, HP, WP, C, (cudaStream_t)stream);
 }
 
 int vg_dw3x3_bnact_fwd(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out,
@@ -176,10 +176,10 @@ int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* 
   return reg_mean_run(in, out, N, nwin, RC, (cudaStream_t)stream);
 }
 
-int vg_convT2_fwd(int dtype, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl, int C,
-                  float* scratch, long long scratch_elems, void* stream) {
+int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl,
+                  int C, float* scratch, long long scratch_elems, void* stream) {
   EpiParams ep = epi_zero();
-  ep.out = out; ep.ldo = C; ep.n_total = 4 * C; ep.bias = bias; ep.Hl = Hl; ep.Wl = Wl;
+  ep.out = out; ep.ldo = C; ep.out_f32 = out_bf16 ? 2 : 0; ep.n_total = 4 * C; ep.bias = bias; ep.Hl = Hl; ep.Wl = Wl;
   ep.pg = make_pgeom(N, 2 * Hl, 2 * Wl);
   if (C % 128) return set_error("convT2: C=%d must be a multiple of 128", C);
   const long long M = (long long)N * Hl * Wl;

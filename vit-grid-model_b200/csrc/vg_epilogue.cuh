@@ -18,7 +18,7 @@ enum EpiKind : int {
 struct EpiParams {
   void* out;
   long long ldo;
-  int out_f32;               // EPI_STORE: store fp32 regardless of the activation dtype
+  int out_f32;               // output element type: 0 = activation dtype T, 1 = fp32, 2 = bf16
   int n_total;               // total number of GEMM columns
   const float* bias;         // [n_total] (EPI_CONVT: [C])
   const float* col_scale;    // folded BatchNorm: y = acc*scale + shift (bias already folded into shift)
@@ -40,6 +40,14 @@ struct EpiParams {
   int reg_in_per_field;
   float* reg_out;            // [Nw][R][C] register-token outputs (block attention) or null
 };
+
+// store 8 consecutive outputs at element offset `off` of ep.out in the selected output type
+template <typename T>
+__device__ __forceinline__ void st8_out(const EpiParams& ep, long long off, const float* v) {
+  if (ep.out_f32 == 1) st8(reinterpret_cast<float*>(ep.out) + off, v);
+  else if (ep.out_f32 == 2) st8(reinterpret_cast<bf16*>(ep.out) + off, v);
+  else st8(reinterpret_cast<T*>(ep.out) + off, v);
+}
 
 template <typename T, class Loader>
 __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
@@ -65,15 +73,8 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bo
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
     }
-    if (ep.out_f32) {
-      float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st8(o + j, v + j);
-    } else {
-      T* o = reinterpret_cast<T*>(ep.out) + row * ep.ldo + c0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) st8(o + j, v + j);
-    }
+    for (int j = 0; j < 32; j += 8) st8_out<T>(ep, row * ep.ldo + c0 + j, v + j);
   }
 }
 
@@ -186,7 +187,7 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
   const int n = (int)(row / lo);
   const int p = (int)(row - (long long)n * lo);
   const int i = p / ep.Wl, j0 = p - i * ep.Wl;
-  T* o = reinterpret_cast<T*>(ep.out) + ep.pg.q(n, 2 * i + (tap >> 1), 2 * j0 + (tap & 1)) * ep.ldo + cbase;
+  const long long o = ep.pg.q(n, 2 * i + (tap >> 1), 2 * j0 + (tap & 1)) * ep.ldo + cbase;
   float v[32];
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
@@ -195,7 +196,7 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + cbase + ch * 32 + j);
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+    for (int j = 0; j < 32; j += 8) st8_out<T>(ep, o + ch * 32 + j, v + j);
   }
 }
 

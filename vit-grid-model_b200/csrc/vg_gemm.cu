@@ -15,7 +15,7 @@ namespace vg {
 struct GemmShape {
   long long M;              // valid output rows (all batches)
   int num_m_tiles, num_n_tiles;
-  int k_blocks, cblocks;    // 64-wide K blocks: total and per tap
+  int k_blocks, cblocks;    // 128-byte-wide K blocks (64 bf16 / 32 tf32 elements): total and per tap
   int tap_shift[9];
   int tiles_per_batch;      // m-tiles per batch (== num_m_tiles when not batched)
   long long rows_per_batch; // A / output rows per batch (== M when not batched)
@@ -35,7 +35,9 @@ struct TmemLoader {
   }
 };
 
-template <int KIND>
+// TF32 = 0: bf16 operands (64 per 128-byte K block, UMMA K = 16); TF32 = 1: fp32 operands read as tf32 (32 per K
+// block, UMMA K = 8).  The smem tiles are [128 rows][128 bytes] either way, so the pipeline is identical.
+template <int KIND, int TF32>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmShape gs, const EpiParams ep) {
@@ -63,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = gs.num_m_tiles * gs.num_n_tiles;
+  constexpr int BKE = TF32 ? 32 : 64;                        // elements per K block
 
   if (warp == 0) {
     if (lane == 0) {                                         // ===== TMA producer =====
@@ -77,15 +80,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(empty + stage, phase ^ 1);
           mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(sa, &mapA, full + stage, cb * BK, (int)(row0 + gs.tap_shift[tap]));
-          tma_load_2d(sa + BM * BK * 2, &mapB, full + stage, kb * BK, brow0);
+          tma_load_2d(sa, &mapA, full + stage, cb * BKE, (int)(row0 + gs.tap_shift[tap]));
+          tma_load_2d(sa + BM * BK * 2, &mapB, full + stage, kb * BKE, brow0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                         // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -98,8 +101,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + BM * BK * 2);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)                  // +32 B per K=16 step inside the swizzle atom
-            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {                      // 4 x 32 B per K block, +32 B inside the swizzle atom
+            if (TF32) tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
           tc_commit(empty + stage);                          // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -119,7 +124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
       TmemLoader ld{tmem_base + as * BN + ((uint32_t)(lg * 32) << 16)};
-      run_epilogue<KIND, bf16>(ep, row, ok, n_tile * BN, ld);
+      if (TF32) run_epilogue<KIND, float>(ep, row, ok, n_tile * BN, ld);
+      else run_epilogue<KIND, bf16>(ep, row, ok, n_tile * BN, ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
@@ -220,15 +226,15 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [outer][inner] (inner contiguous), box 64 x box_outer, 128B swizzle, zero OOB fill
-static int make_map_bf16_2d(CUtensorMap* m, const void* ptr, long long inner, long long outer, int box_outer) {
+// 2-D tensor [outer][inner] (inner contiguous, bf16 or fp32), box (128 bytes) x box_outer, 128B swizzle, zero OOB fill
+static int make_map_2d(CUtensorMap* m, bool f32, const void* ptr, long long inner, long long outer, int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld", (int)r, ptr, inner, outer);
@@ -245,17 +251,17 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int KIND>
+template <int KIND, int TF32>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int total = gs.num_m_tiles * gs.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<KIND><<<grid, 256, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
+  gemm_tc_kernel<KIND, TF32><<<grid, 256, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -266,16 +272,18 @@ static int launch_simt_epi(const float* scratch, int Ntot, const GemmShape& gs, 
   return check_launch("epilogue_rows_kernel");
 }
 
-// The one host entry used by the C ABI (vg_api.cu).  dtype: 0 = bf16 (tcgen05), 1 = fp32 (SIMT).
+// The one host entry used by the C ABI (vg_api.cu).  dtype: 0 = bf16 (tcgen05), 1 = fp32 (SIMT FFMA),
+// 2 = fp32 storage with TF32 tcgen05 MMA.
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st) {
-  if (Ca % BK) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, BK);
+  const int bke = dtype == 2 ? 32 : 64;
+  if (Ca % bke) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, bke);
   if (ntaps < 1 || ntaps > 9) return set_error("gemm: bad tap count %d", ntaps);
   if (M <= 0) return 0;
   GemmShape gs;
   gs.M = M;
-  gs.cblocks = Ca / BK;
+  gs.cblocks = Ca / bke;
   gs.k_blocks = gs.cblocks * ntaps;
   for (int i = 0; i < 9; ++i) gs.tap_shift[i] = i < ntaps ? tap_shift[i] : 0;
   const bool batched = rows_per_batch > 0 && rows_per_batch < M;
@@ -288,17 +296,26 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
   const int Ktot = Ca * ntaps;
   if (kind == EPI_CONV_LN && Ntot != BN) return set_error("gemm: conv+LN epilogue needs exactly %d output channels (got %d)", BN, Ntot);
 
-  if (dtype == 0) {
+  if (dtype == 0 || dtype == 2) {
     CUtensorMap ma, mb;
-    int rc = make_map_bf16_2d(&ma, A, Ca, rowsA, BM);
+    int rc = make_map_2d(&ma, dtype == 2, A, Ca, rowsA, BM);
     if (rc) return rc;
-    rc = make_map_bf16_2d(&mb, B, Ktot, (long long)Ntot * (batched ? nbatch : 1), BN);
+    rc = make_map_2d(&mb, dtype == 2, B, Ktot, (long long)Ntot * (batched ? nbatch : 1), BN);
     if (rc) return rc;
-    switch (kind) {
-      case EPI_STORE: return launch_tc<EPI_STORE>(ma, mb, gs, ep, st);
-      case EPI_CONV_LN: return launch_tc<EPI_CONV_LN>(ma, mb, gs, ep, st);
-      case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT>(ma, mb, gs, ep, st);
-      case EPI_CONVT: return launch_tc<EPI_CONVT>(ma, mb, gs, ep, st);
+    if (dtype == 0) {
+      switch (kind) {
+        case EPI_STORE: return launch_tc<EPI_STORE, 0>(ma, mb, gs, ep, st);
+        case EPI_CONV_LN: return launch_tc<EPI_CONV_LN, 0>(ma, mb, gs, ep, st);
+        case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT, 0>(ma, mb, gs, ep, st);
+        case EPI_CONVT: return launch_tc<EPI_CONVT, 0>(ma, mb, gs, ep, st);
+      }
+    } else {
+      switch (kind) {
+        case EPI_STORE: return launch_tc<EPI_STORE, 1>(ma, mb, gs, ep, st);
+        case EPI_CONV_LN: return launch_tc<EPI_CONV_LN, 1>(ma, mb, gs, ep, st);
+        case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT, 1>(ma, mb, gs, ep, st);
+        case EPI_CONVT: return launch_tc<EPI_CONVT, 1>(ma, mb, gs, ep, st);
+      }
     }
     return set_error("gemm: bad epilogue kind %d", kind);
   }

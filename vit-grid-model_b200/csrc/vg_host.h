@@ -59,7 +59,7 @@ int time_terms_run(const TimeParams& p, cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
 int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStream_t st);
-int maxpool2_run(int dtype, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st);
+int maxpool2_run(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st);
 int dwconv_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out, float* psum,
                int N, int H, int W, int C, cudaStream_t st);
 int se_gate_run(const float* psum, int N, int H, int HW, const float* W1, const float* W2, int C, int se, float* gate, cudaStream_t st);

@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
 // ================================================================================================
 // 2x2 max-pool: PG layout (N,HP,WP,C) -> plain channels-last (N,HP/2,WP/2,C)   (metnet3.py:86,419)
 // ================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, PGeom pg, int C) {
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, TO* __restrict__ out, PGeom pg, int C) {
   const int Ho = pg.HP / 2, Wo = pg.WP / 2, cv = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)pg.N * Ho * Wo * cv;
@@ -415,12 +415,13 @@ int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStr
   return check_launch("stem_finish_kernel");
 }
 
-int maxpool2_run(int dtype, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st) {
+int maxpool2_run(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st) {
   if (C % 8 || HP % 2 || WP % 2) return set_error("maxpool2: bad shape");
   PGeom pg = make_pgeom(N, HP, WP);
   const long long total = (long long)N * (HP / 2) * (WP / 2) * (C / 8);
-  if (dtype == 0) maxpool2_kernel<bf16><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), pg, C);
-  else maxpool2_kernel<float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), pg, C);
+  if (dtype == 0 && out_f32) maxpool2_kernel<bf16, float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<float*>(out), pg, C);
+  else if (dtype == 0) maxpool2_kernel<bf16, bf16><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), pg, C);
+  else maxpool2_kernel<float, float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), pg, C);
   return check_launch("maxpool2_kernel");
 }
 

@@ -122,13 +122,19 @@ class MaxViT(nn.Module):
                       window_size=vit_window_size, num_registers=num_register_tokens)
             self.layers.append(nn.ModuleList([conv, Attention(**kw), Attention(**kw)]))
             self.register_tokens.append(nn.Parameter(torch.randn(num_register_tokens, dim)))
-        self.compute_dtype = torch.bfloat16
+        self.set_precision("bf16")
         self._packed = None
         self._packed_key = None
+        self._capture = None
 
     # ------------------------------------------------------------------ weights -> kernel layouts
     def set_precision(self, precision: str):
-        self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        """'bf16'     : fp32 storage, projections on tcgen05 kind::tf32 (the MaxViT block dominates the rounding error
+                        of the network, see DESIGN.md, so it keeps 10-bit mantissas; the 3x3 convs around it are bf16)
+           'bf16_all' : bf16 storage and kind::f16 MMA everywhere (faster, ~2x the error)
+           'fp32'     : fp32 storage, exact-fp32 SIMT GEMMs"""
+        self.compute_dtype, self.tf32 = {"bf16": (torch.float32, True), "bf16_all": (torch.bfloat16, False),
+                                         "fp32": (torch.float32, False)}[precision]
         return self
 
     def _pack_key(self, dtype):
@@ -172,11 +178,11 @@ class MaxViT(nn.Module):
         N, H, W, C = x.shape
         w, R = self.vit_window_size, self.num_register_tokens
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
-        qkv = ops.gemm(tokens, P["w_qkv"])
+        qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32)
         del tokens
         att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head)
         del qkv
-        return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out)
+        return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=self.tf32)
 
     def forward_cl(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
         """channels-last entry used by MetNet3: x (N,H,W,dim) in the compute dtype, cond (N,cond_dim) fp32"""
@@ -190,20 +196,25 @@ class MaxViT(nn.Module):
         cond = cond.float().contiguous()
         nwin = (H // w) * (W // w)
         for P in self.packed(x.dtype):
-            h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1)
+            h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1, tf32=self.tf32)
             hidden = h.shape[1]
             h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
             del h
             gate = ops.se_gate(psum, W, P["se_w1"], P["se_w2"])
             ops.se_scale_(h2, gate)
             y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
-                         res=x.view(N * H * W, C) if P["residual"] else None)
+                         res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
             del h2
             x = y.view(N, H, W, C)
+            cap = self._capture
+            if cap is not None:
+                cap["mbconv"] = x.permute(0, 3, 1, 2).float()
             fb = P["block"]
             film = ops.cond_mlp(cond, fb["film_w0"], fb["film_b0"], fb["film_w1"], fb["film_b1"])
             x, reg_out = self._attention(x, film, fb, P["reg"], False, True)
             reg = ops.reg_mean(reg_out, N, nwin)
+            if cap is not None:
+                cap["block_attn"] = x.permute(0, 3, 1, 2).float()
             fg = P["grid"]
             film = ops.cond_mlp(cond, fg["film_w0"], fg["film_b0"], fg["film_w1"], fg["film_b1"])
             x, _ = self._attention(x, film, fg, reg, True, False)

@@ -145,15 +145,18 @@ class MetNet3(nn.Module):
             self._unsupported = f"n_start_channels={n_start_channels}: the sm_100a kernels are built for 128 channels"
         else:
             self._unsupported = None
-        self.compute_dtype = torch.bfloat16
+        self.compute_dtype, self.precision = torch.bfloat16, "bf16"
         self.max_fields = {torch.bfloat16: 768, torch.float32: 48}
         self._packed, self._packed_key = None, None
+        self._capture = None          # debugging: set to a dict to collect stage outputs (NCHW copies)
 
     # ------------------------------------------------------------------ helpers
     def set_precision(self, precision: str):
-        """'bf16' (tensor-core path, default) or 'fp32' (exact-fp32 SIMT path)"""
-        self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        """'bf16' (default): bf16 storage + tcgen05 kind::f16 for the 3x3-conv encoder/decoder, fp32 storage + kind::tf32
+        for the MaxViT block; 'bf16_all': bf16 everywhere; 'fp32': exact-fp32 SIMT path."""
+        self.compute_dtype = {"bf16": torch.bfloat16, "bf16_all": torch.bfloat16, "fp32": torch.float32}[precision]
         self.vit.set_precision(precision)
+        self.precision = precision
         return self
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -170,7 +173,7 @@ class MetNet3(nn.Module):
     @torch.no_grad()
     def packed(self, dtype):
         own = [p for n, p in self.named_parameters() if not n.startswith("vit.")]
-        key = (dtype, tuple((p.data_ptr(), p._version) for p in own))
+        key = (dtype, self.vit.compute_dtype, tuple((p.data_ptr(), p._version) for p in own))
         if self._packed_key == key:
             return self._packed
         c_data = self.n_input_channels
@@ -200,7 +203,7 @@ class MetNet3(nn.Module):
                 blocks.append(d)
             P[name] = blocks
         C = self.n_start_channels
-        P["w_up"] = self.up.weight.permute(2, 3, 1, 0).reshape(4 * C, C).to(dtype).contiguous()
+        P["w_up_vit"] = self.up.weight.permute(2, 3, 1, 0).reshape(4 * C, C).to(self.vit.compute_dtype).contiguous()
         P["b_up"] = self.up.bias.float().contiguous()
         P["w_head"] = self.classifier_pm25.weight.float().reshape(-1).contiguous()
         P["b_head"] = float(self.classifier_pm25.bias.float().item())
@@ -242,18 +245,31 @@ class MetNet3(nn.Module):
         del raw3, rawres
         ops.conv3x3_ln(bufs[0], s0["w2"], s0["b2"], s0["g2"], s0["be2"], s0["eps2"], None, bufs[1], bufs[2], N, HP, WP)
         h = bufs[2]
+        cap = self._capture
+        if cap is not None:
+            cap["stem_h1"], cap["stem_res"] = ops.pg_to_nchw(bufs[0], N, HP, WP), ops.pg_to_nchw(bufs[1], N, HP, WP)
+            cap["resnet1.0"] = ops.pg_to_nchw(h, N, HP, WP)
         for d in P["resnet1"][1:]:
             h = self._resblock(h, cond, d, bufs, N, HP, WP)
         # ---- MaxViT at half resolution
-        low = ops.pool2(h, N, HP, WP)
+        low = ops.pool2(h, N, HP, WP, out_dtype=self.vit.compute_dtype)
+        if cap is not None:
+            cap["resnet1"] = ops.pg_to_nchw(h, N, HP, WP)
+            self.vit._capture = cap
         low = self.vit.forward_cl(low, cond)
+        if cap is not None:
+            cap["vit"] = low.permute(0, 3, 1, 2).float()
         # ---- decoder
         up = [b for b in bufs if b is not h][0]       # pads of every PG buffer are already zero (written by conv/stem)
-        ops.convT2(low, P["w_up"], P["b_up"], up)
+        ops.convT2(low, P["w_up_vit"], P["b_up"], up, tf32=self.vit.tf32)
         del low
         h = up
+        if cap is not None:
+            cap["up"] = ops.pg_to_nchw(h, N, HP, WP)
         for d in P["resnet2"]:
             h = self._resblock(h, cond, d, bufs, N, HP, WP)
+        if cap is not None:
+            cap["resnet2"] = ops.pg_to_nchw(h, N, HP, WP)
         ops.head(h, P["w_head"], P["b_head"], self.pm25_std, self.pm25_mean, N, HP, WP, self.input_height, self.input_width,
                  pads, out=out[b0:b1].view(N, self.input_height, self.input_width))
 

@@ -19,9 +19,16 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _scratch(dtype, elems, device):
-    """fp32-mode GEMMs accumulate into a caller-provided scratch; bf16 mode needs none."""
-    if dtype == torch.float32:
+def _gemm_code(dtype, tf32):
+    """0 = bf16 tcgen05, 1 = fp32 SIMT, 2 = fp32 storage + tf32 tcgen05"""
+    if dtype == torch.bfloat16:
+        return 0
+    return 2 if tf32 else 1
+
+
+def _scratch(dtype, elems, device, tf32=False):
+    """exact-fp32 (SIMT) GEMMs accumulate into a caller-provided scratch; the tcgen05 paths need none."""
+    if dtype == torch.float32 and not tf32:
         t = torch.empty(int(elems), dtype=torch.float32, device=device)
         return t, t.data_ptr(), t.numel()
     return None, None, 0
@@ -87,7 +94,7 @@ def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
 
 
 def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per_batch=0, bias=None, scale=None,
-         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None):
+         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None, tf32=False):
     dtype = A.dtype
     rowsA, Ca = A.shape
     M = rowsA if M is None else M
@@ -95,8 +102,9 @@ def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per
     if out is None:
         out = torch.empty(M, Ntot, dtype=torch.float32 if out_f32 else dtype, device=A.device)
     shifts = (ctypes.c_int * ntaps)(*tap_shift)
-    keep, sp, sn = _scratch(dtype, M * Ntot, A.device)
-    _lib.call("vg_gemm_fwd", DT_CODE[dtype], A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
+    keep, sp, sn = _scratch(dtype, M * Ntot, A.device, tf32)
+    _lib.TRACE_TAG = f"M={M} K={ntaps}x{Ca} N={Ntot} {'tf32' if tf32 else str(dtype)[6:]}"
+    _lib.call("vg_gemm_fwd", _gemm_code(dtype, tf32), A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
               rows_per_batch, b_rows_per_batch, _p(bias), _p(scale), _p(shift), act, _p(res),
               res.shape[1] if res is not None else 0, out.data_ptr(), out.shape[1], int(out_f32), sp, sn, _st())
     return out
@@ -121,11 +129,12 @@ def stem_finish(raw3, rawres, bias3, bias1, tt, tres, ln_g, ln_b, eps, film, B, 
               film.data_ptr(), B, L, HP, WP, h1.data_ptr(), res.data_ptr(), _st())
 
 
-def pool2(x, N, HP, WP, out=None):
+def pool2(x, N, HP, WP, out_dtype=None):
     C = x.shape[1]
-    if out is None:
-        out = torch.empty(N, HP // 2, WP // 2, C, dtype=x.dtype, device=x.device)
-    _lib.call("vg_pool2_fwd", DT_CODE[x.dtype], x.data_ptr(), out.data_ptr(), N, HP, WP, C, _st())
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty(N, HP // 2, WP // 2, C, dtype=out_dtype, device=x.device)
+    assert out_dtype == x.dtype or (x.dtype == torch.bfloat16 and out_dtype == torch.float32)
+    _lib.call("vg_pool2_fwd", DT_CODE[x.dtype], int(out_dtype != x.dtype), x.data_ptr(), out.data_ptr(), N, HP, WP, C, _st())
     return out
 
 
@@ -171,14 +180,14 @@ def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, o
     return out
 
 
-def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None):
+def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False):
     N, Hl, Wl, C = x_in.shape
     nwin = (Hl // win) * (Wl // win)
     if x_out is None:
         x_out = torch.empty_like(x_in)
     reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x_in.device) if want_reg_out else None
-    keep, sp, sn = _scratch(attn.dtype, attn.shape[0] * C, attn.device)
-    _lib.call("vg_attn_out_fwd", DT_CODE[attn.dtype], attn.data_ptr(), attn.shape[1], Wt.data_ptr(), x_in.data_ptr(),
+    keep, sp, sn = _scratch(attn.dtype, attn.shape[0] * C, attn.device, tf32)
+    _lib.call("vg_attn_out_fwd", _gemm_code(attn.dtype, tf32), attn.data_ptr(), attn.shape[1], Wt.data_ptr(), x_in.data_ptr(),
               reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out), x_out.data_ptr(), N, Hl, Wl, C, win, R,
               int(grid_mode), sp, sn, _st())
     return x_out, reg_out
@@ -191,11 +200,12 @@ def reg_mean(reg_out, N, nwin):
     return out
 
 
-def convT2(x, Wt, bias, out):
-    """x CL (N,Hl,Wl,C) -> out PG (N,2Hl,2Wl,C); `out` must already hold zeros at its pad positions."""
+def convT2(x, Wt, bias, out, tf32=False):
+    """x CL (N,Hl,Wl,C) -> out PG (N,2Hl,2Wl,C); `out` must already hold zeros at its pad positions.
+    `out` may be bf16 while x is fp32 (mixed mode: tf32 MaxViT feeding the bf16 decoder convs)."""
     N, Hl, Wl, C = x.shape
-    keep, sp, sn = _scratch(x.dtype, N * Hl * Wl * 4 * C, x.device)
-    _lib.call("vg_convT2_fwd", DT_CODE[x.dtype], x.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), N, Hl, Wl,
+    keep, sp, sn = _scratch(x.dtype, N * Hl * Wl * 4 * C, x.device, tf32)
+    _lib.call("vg_convT2_fwd", _gemm_code(x.dtype, tf32), int(out.dtype == torch.bfloat16 and x.dtype != torch.bfloat16), x.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), N, Hl, Wl,
               C, sp, sn, _st())
     return out
 
