@@ -82,17 +82,23 @@ VG_API int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const 
 
 /* metnet3.py:110-126 Block = Conv2d 3x3 (pad 1) -> ChanLayerNorm (var.clamp(eps).rsqrt) -> optional FiLM
  * x*(scale+1)+shift -> ReLU, plus the ResnetBlock residual add (:162) when res != NULL.  x,out,res: PG
- * layout (N,HP,WP,C=128); Wt: [128][9*Ca] tap-major (ky,kx) then channel; film: (N,256) fp32 or NULL. */
+ * layout (N,HP,WP,C=128); Wt: [128][9*Ca] tap-major (ky,kx) then channel; film: (N,256) fp32 or NULL.
+ * res_f32=1: the residual tensor is fp32 (skip connections are kept in full precision in bf16 mode);
+ * out_f32_copy (or NULL): an additional fp32 copy of the block output for the next block's skip connection.
+ * head_w != NULL fuses metnet3.py:424-430 (unpad, Conv2d 1x1 C->1, *std + mean) into the epilogue:
+ * head_out (N,H,W) fp32 receives the predictions; `out` may then be NULL. */
 VG_API int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
-                      const float* ln_b, float ln_eps, const float* film, const void* res, void* out, int N,
-                      int HP, int WP, float* scratch, long long scratch_elems, void* stream);
+                      const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                      float* out_f32_copy, int N, int HP, int WP, const float* head_w, float head_b, float head_std,
+                      float head_mean, int H, int W, int pad_top, int pad_left, float* head_out, float* scratch,
+                      long long scratch_elems, void* stream);
 
 /* dedup'd first block (metnet3.py:383-418): raw3/rawres are the per-SAMPLE stem 3x3 / res_conv 1x1 GEMM
  * outputs (fp32, PG over B frames); per FIELD n=b*L+l adds bias + analytic time term, ChanLayerNorm, FiLM, ReLU
- * -> h1 (PG over N frames) and res = rawres + bias1 + tres (the ResnetBlock residual). */
+ * -> h1 (PG over N frames) and res = rawres + bias1 + tres (the ResnetBlock residual, always fp32). */
 VG_API int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
                        const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
-                       const float* film, int B, int L, int HP, int WP, void* h1, void* res, void* stream);
+                       const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* stream);
 
 /* metnet3.py:86,419 -- MaxPool2d(2,2): PG (N,HP,WP,C) -> CL (N,HP/2,WP/2,C); out_f32=1: bf16 in, fp32 out */
 VG_API int vg_pool2_fwd(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, void* stream);
@@ -128,13 +134,25 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
                     int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
                     int grid_mode, float* scratch, long long scratch_elems, void* stream);
 
+/* maxvit.py:170-219 + 298-340 in ONE kernel (fp32 residual stream, tcgen05 kind::tf32 projections / QK^T, bf16 PV):
+ * gather + register tokens + LayerNorm + FiLM -> per head {QKV, QK-RMSNorm, QK^T + rel-pos bias, softmax, PV,
+ * out-projection accumulated over heads} -> + residual -> inverse partition.  x/x_out: CL (N,Hl,Wl,128) fp32;
+ * wqkv_h: fp32 [heads][96][128] (per head the 32 q rows, 32 k rows, 32 v rows of to_qkv.weight);
+ * wout_h: fp32 [heads][128][32] (per head the 32 columns of to_out.0.weight); head_tab: fp32 [heads][800] =
+ * per head the relative-position bias as 7 pre-shifted copies [bi][row 0..12][8] (entry k = table[(row*13 + bi+6-k)]),
+ * table[169] (+7 pad), q gamma[32], k gamma[32].  Needs C=128, dim_head=32, win=7, R=4. */
+VG_API int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
+                      const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
+                      int grid_mode, int heads, int dh, float ln_eps, void* stream);
+
 /* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */
 VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);
 
 /* metnet3.py:88-89,421 -- ConvTranspose2d(k=2,s=2) as GEMM + depth-to-space: CL (N,Hl,Wl,C) -> PG (N,2Hl,2Wl,C).
- * Wt: [4*C][C], row (di*2+dj)*C+co = weight[ci][co][di][dj].  out_bf16=1 writes bf16 whatever dtype is. */
-VG_API int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl,
-                  int Wl, int C, float* scratch, long long scratch_elems, void* stream);
+ * Wt: [4*C][C], row (di*2+dj)*C+co = weight[ci][co][di][dj].  out_bf16=1 writes bf16 whatever dtype is;
+ * out_f32_copy (or NULL) receives an fp32 copy (skip connection of the next ResnetBlock). */
+VG_API int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out,
+                  float* out_f32_copy, int N, int Hl, int Wl, int C, float* scratch, long long scratch_elems, void* stream);
 
 /* metnet3.py:424-430 -- unpad, Conv2d 1x1 C->1, *std + mean: PG (N,HP,WP,C) -> fp32 (N,H,W) */
 VG_API int vg_head_fwd(int dtype, const void* h, const float* w, float bias, float pm_std, float pm_mean, int N, int HP,

@@ -262,6 +262,39 @@ def test_attention_layer(mode, grid_mode):
     assert rel_err(mean, reg_out.view(N, nwin, R, C).mean(1)) < 1e-5
 
 
+@pytest.mark.parametrize("grid_mode", [False, True])
+@pytest.mark.parametrize("N,H,W", [(2, 14, 21), (5, 7, 7), (3, 42, 35)])
+def test_attention_fused(grid_mode, N, H, W):
+    """the one-kernel attention layer (tf32 projections, bf16 PV) == oracle attention + residual.
+    (5,7,7): odd number of windows -> a half-empty last tile; (3,42,35): the 12hr model's map."""
+    o = ops()
+    C, heads, dh, w, R = 128, 32, 32, 7, 4
+    sd = _attn_sd(C, heads, dh, w, R, seed=9)
+    x = rnd(N, H, W, C, seed=1)
+    cond = rnd(N, 2, seed=2)
+    reg = rnd(N, R, C, seed=3) if grid_mode else rnd(R, C, seed=3)
+    nwin = (H // w) * (W // w)
+    idx = (mo.grid_pixel_index if grid_mode else mo.block_pixel_index)(H, W, w).reshape(-1)
+    flat = x.reshape(N, H * W, C)
+    tok = flat[:, idx].reshape(N * nwin, w * w, C)
+    regs = reg.repeat_interleave(nwin, 0) if grid_mode else reg[None].expand(N * nwin, R, C)
+    seq = torch.cat([regs, tok], dim=1)
+    ref = mo.attention(seq, cond, sd, "", heads=heads, window=w, num_reg=R) + seq
+    ref_x = torch.empty_like(flat)
+    ref_x[:, idx] = ref[:, R:].reshape(N, nwin * w * w, C)
+    gamma, beta = mo.film(cond, sd, "")
+    film = torch.cat([gamma, beta], dim=1).cuda().contiguous()
+    inner = heads * dh
+    wq = sd["to_qkv.weight"]
+    wqkv_h = torch.stack([wq[i * inner:(i + 1) * inner].reshape(heads, dh, C) for i in range(3)], dim=1).reshape(heads * 96, C)
+    wout_h = sd["to_out.0.weight"].reshape(C, heads, dh).permute(1, 0, 2).contiguous()
+    head_tab = o.pack_head_tables(sd["rel_pos_bias.weight"], sd["q_norm.gamma"], sd["k_norm.gamma"]).cuda()
+    x_out, reg_out = o.attn_fused(x.cuda(), reg.cuda(), film, wqkv_h.contiguous().cuda(), wout_h.cuda(), head_tab,
+                                  w, R, grid_mode, True, heads, dh)
+    assert rel_err(x_out.reshape(N, H * W, C), ref_x) < 4e-3
+    assert rel_err(reg_out, ref[:, :R]) < 4e-3
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3), ("bf16_all", 3e-2)])
 def test_maxvit_module(precision, tol):
     """MaxViT nn.Module (reference API) vs oracle, depth 2 (second MBConv is residual)"""
@@ -292,6 +325,32 @@ def test_convT2(dtype, tf32, out_dtype):
              w.permute(2, 3, 1, 0).reshape(4 * C, C).contiguous().cuda().to(dtype), b.cuda(), out, tf32=tf32)
     ref = F.conv_transpose2d(x, w, b, stride=2)
     assert rel_err(o.pg_to_nchw(out, N, 2 * Hl, 2 * Wl), ref) < TOL[out_dtype]
+
+
+def test_conv3x3_ln_fp32_skip_copy_and_fused_head():
+    """bf16 block with an fp32 residual, an fp32 output copy and the 1x1 head fused into the epilogue"""
+    o = ops()
+    cfg = synth.CFG_SMALL128
+    N, H, W, C, dtype = 3, cfg.HP, cfg.WP, 128, torch.bfloat16
+    x = q(rnd(N, C, H, W, seed=3), dtype)
+    w = q(rnd(C, C, 3, 3, seed=4) / math.sqrt(9 * C), dtype)
+    b, g, be = rnd(C, seed=5, scale=0.1), 0.5 + torch.rand(C), rnd(C, seed=7, scale=0.1)
+    res = rnd(N, C, H, W, seed=9)
+    hw, hb = rnd(C, seed=11) / math.sqrt(C), 0.2
+    h = F.relu(m3o.chan_layer_norm(F.conv2d(x, w, b, padding=1), g.view(1, C, 1, 1), be.view(1, C, 1, 1))) + res
+    pl, pr, pt, pb = cfg.pads
+    ref_head = (F.conv2d(h[..., pt:H - pb, pl:W - pr], hw.view(1, C, 1, 1)) + hb).squeeze(1) * cfg.pm25_std + cfg.pm25_mean
+    wt = w.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().cuda().to(dtype)
+    xp, rp = o.pg_from_nchw(x.cuda(), dtype), o.pg_from_nchw(res.cuda(), torch.float32)
+    out = torch.empty(o.pg_pixels(N, H, W), C, dtype=dtype, device="cuda")
+    copy = torch.empty(o.pg_pixels(N, H, W), C, dtype=torch.float32, device="cuda")
+    o.conv3x3_ln(xp, wt, b.cuda(), g.cuda(), be.cuda(), 1e-5, None, rp, out, N, H, W, out_copy=copy)
+    assert rel_err(o.pg_to_nchw(copy, N, H, W), h) < 2e-3                  # only the conv operands are bf16
+    assert torch.equal(out.float(), copy.to(dtype).float())                # bf16 output == rounded fp32 copy
+    pred = torch.empty(N, cfg.H, cfg.W, dtype=torch.float32, device="cuda")
+    o.conv3x3_ln(xp, wt, b.cuda(), g.cuda(), be.cuda(), 1e-5, None, rp, None, N, H, W,
+                 head=(hw.cuda(), hb, cfg.pm25_std, cfg.pm25_mean, cfg.H, cfg.W, cfg.pads, pred))
+    assert rel_err(pred, ref_head) < 2e-3
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -1,0 +1,25 @@
+"""Run the fused attention kernel alone on the 12hr-model map (for ncu / timing)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vit_grid_model_b200 import ops
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+H, W, C, heads, dh, w, R = 42, 35, 128, 32, 32, 7, 4
+g = torch.Generator().manual_seed(0)
+x = torch.randn(N, H, W, C, generator=g).cuda()
+reg = torch.randn(R, C, generator=g).cuda()
+film = torch.randn(N, 2 * C, generator=g).cuda()
+wqkv = (torch.randn(heads * 96, C, generator=g) / 11.3).cuda()
+wout = (torch.randn(heads, C, dh, generator=g) / 32).cuda()
+qg, kg = torch.ones(heads * dh).cuda(), torch.ones(heads * dh).cuda()
+bias = torch.randn(170, heads, generator=g).cuda()
+tab = ops.pack_head_tables(bias, qg, kg)
+for _ in range(iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    y, r = ops.attn_fused(x, reg, film, wqkv, wout, tab, w, R, False, True, heads, dh)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"N={N} windows={N*30} ms={e0.elapsed_time(e1):.3f}")

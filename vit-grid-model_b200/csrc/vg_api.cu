@@ -96,12 +96,18 @@ int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* W
 }
 
 int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
-                      const float* ln_b, float ln_eps, const float* film, const void* res, void* out, int N, int HP,
-                      int WP, float* scratch, long long scratch_elems, void* stream) {
+                      const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                      float* out_f32_copy, int N, int HP, int WP, const float* head_w, float head_b, float head_std,
+                      float head_mean, int H, int W, int pad_top, int pad_left, float* head_out, float* scratch,
+                      long long scratch_elems, void* stream) {
   PGeom pg = make_pgeom(N, HP, WP);
   EpiParams ep = epi_zero();
   ep.out = out; ep.ldo = 128; ep.n_total = 128; ep.bias = bias; ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_eps = ln_eps;
-  ep.film = film; ep.res = res; ep.ldres = 128; ep.pg = pg;
+  ep.film = film; ep.res = res; ep.ldres = 128; ep.pg = pg; ep.res_f32 = res_f32; ep.out2 = out_f32_copy;
+  ep.head_w = head_w; ep.head_out = head_out; ep.head_b = head_b; ep.head_std = head_std; ep.head_mean = head_mean;
+  ep.head_H = H; ep.head_W = W; ep.head_pt = pad_top; ep.head_pl = pad_left;
+  if (!out && !head_w) return set_error("conv3x3_ln: no output requested");
+  if (head_w && !head_out) return set_error("conv3x3_ln: head_w without head_out");
   int shifts[9];
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) shifts[ky * 3 + kx] = (ky - 1) * pg.P + (kx - 1);
@@ -111,7 +117,7 @@ int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const fl
 
 int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
                        const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
-                       const float* film, int B, int L, int HP, int WP, void* h1, void* res, void* stream) {
+                       const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* stream) {
   StemParams p;
   p.raw3 = raw3; p.rawres = rawres; p.bias3 = bias3; p.bias1 = bias1; p.tt = tt; p.tres = tres;
   p.ln_g = ln_g; p.ln_b = ln_b; p.eps = ln_eps; p.film = film; p.L = L;
@@ -172,14 +178,23 @@ int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, cons
                   (cudaStream_t)stream);
 }
 
+int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
+                      const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
+                      int grid_mode, int heads, int dh, float ln_eps, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
+  return attn_fused_run(x, x_out, reg_in, reg_per_field, reg_out, film, wqkv_h, wout_h, head_tab, g,
+                        heads, dh, ln_eps, (cudaStream_t)stream);
+}
+
 int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream) {
   return reg_mean_run(in, out, N, nwin, RC, (cudaStream_t)stream);
 }
 
-int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out, int N, int Hl, int Wl,
-                  int C, float* scratch, long long scratch_elems, void* stream) {
+int vg_convT2_fwd(int dtype, int out_bf16, const void* x, const void* Wt, const float* bias, void* out, float* out_f32_copy,
+                  int N, int Hl, int Wl, int C, float* scratch, long long scratch_elems, void* stream) {
   EpiParams ep = epi_zero();
-  ep.out = out; ep.ldo = C; ep.out_f32 = out_bf16 ? 2 : 0; ep.n_total = 4 * C; ep.bias = bias; ep.Hl = Hl; ep.Wl = Wl;
+  ep.out = out; ep.ldo = C; ep.out_f32 = out_bf16 ? 2 : 0; ep.out2 = out_f32_copy; ep.n_total = 4 * C; ep.bias = bias; ep.Hl = Hl; ep.Wl = Wl;
   ep.pg = make_pgeom(N, 2 * Hl, 2 * Wl);
   if (C % 128) return set_error("convT2: C=%d must be a multiple of 128", C);
   const long long M = (long long)N * Hl * Wl;

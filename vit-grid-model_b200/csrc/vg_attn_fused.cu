@@ -1,0 +1,518 @@
+// Fused window / grid attention for sm_100a (maxvit.py:170-219 + the partition / residual code around it, :298-340).
+//
+// One persistent CTA processes tiles of TWO windows (2 x 64 token slots = the 128 rows of a tcgen05 M=128 MMA).
+// Nothing between the residual stream in and the residual stream out touches HBM:
+//
+//   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (smem, tf32)
+//   per head h (weights streamed by TMA, double use of TMEM):
+//     QKV_h = X * Wqkv_h^T           tcgen05 kind::tf32  M128 N96  K128      -> TMEM
+//     q,k RMSNorm (* sqrt(d) * gamma) in registers; Q^,K^ (tf32) and V^T (bf16) -> smem
+//     S = Q^ K^^T                    tcgen05 kind::tf32  M128 N128 K32       -> TMEM (both windows; off-diagonal unused)
+//     + relative-position bias (index computed arithmetically), masked softmax in registers; P (bf16) -> smem
+//     O_h = P V                      tcgen05 kind::f16   M128 N32  K128      -> TMEM
+//     O_h / rowsum (tf32) -> smem
+//     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32       -> TMEM, accumulated over heads
+//   epilogue: Out + residual, scattered back through the inverse partition map; register-token rows to reg_out.
+//
+// Warp roles: warp 0 = TMA (weights), warp 1 = MMA issuer, warps 2..5 = 128 compute threads (thread <-> token row
+// <-> TMEM lane).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
+#include "vg_common.cuh"
+#include "vg_host.h"
+
+namespace vg {
+
+namespace fa {
+constexpr int C = 128;         // model channels (K of the QKV projection)
+constexpr int DH = 32;         // head dim
+constexpr int SLOT = 64;       // token slots per window (S <= 64)
+constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specialised for 7x7 windows + 4 register tokens
+// shared memory map (bytes); every operand tile is 1024-B aligned
+constexpr int X_OFF = 0;                         // 4 k-blocks x [128 rows x 128 B]
+constexpr int WQ_OFF = X_OFF + 4 * 16384;        // 4 k-blocks x [96 rows x 128 B]
+constexpr int WO_OFF = WQ_OFF + 4 * 12288;       // [128 rows x 128 B]
+constexpr int R1_OFF = WO_OFF + 16384;           // 2 x 32 KiB: Q^ | K^  ->  P (2 k-blocks)  ->  O
+constexpr int VT_OFF = R1_OFF + 2 * 32768;       // 2 x [2 k-blocks x 32 rows x 128 B]
+constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | q gamma | k gamma
+constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
+constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
+constexpr int BAR_OFF = RED_OFF + 4 * 1024;
+constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
+constexpr int THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 compute (2 threads per token row)
+// TMEM columns
+constexpr int T_QKV0 = 0;      // 96   (QKV accumulators of even heads)
+constexpr int T_O = 96;        // 32
+constexpr int T_QKV1 = 128;    // 96   (odd heads)
+constexpr int T_S = 256;       // 128
+constexpr int T_OUT = 384;     // 128
+constexpr float LOG2E = 1.4426950408889634f;
+}  // namespace fa
+
+struct FusedAttnParams {
+  const float* x; float* x_out;
+  const float* reg_in; int reg_per_field; float* reg_out;
+  const float* film;                   // (N, 2C) gamma | beta
+  const float* head_tab;               // [heads][TAB_FLOATS] (see pack_head_tables in maxvit.py)
+  AttnGeom g;
+  int heads;
+  float ln_eps;
+  long long n_windows;
+};
+
+// byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int r, int c16) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, unsigned short v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+// named barriers: 1 = all 256 compute threads, 2..5 = the two warps that share a TMEM lane group
+__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void pair_sync(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory"); }
+
+__global__ void __launch_bounds__(fa::THREADS, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_constant__ CUtensorMap mapWo,
+                  const FusedAttnParams p) {
+  using namespace fa;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* wq_full = bars + 0;  uint64_t* wq_free = bars + 1;
+  uint64_t* wo_full = bars + 2;  uint64_t* wo_free = bars + 3;
+  uint64_t* x_ready = bars + 4;
+  uint64_t* qkv_done = bars + 5;                 // [2]
+  uint64_t* qk_ready = bars + 7; uint64_t* s_done = bars + 8;
+  uint64_t* p_ready = bars + 9;  uint64_t* o_done = bars + 10;
+  uint64_t* osm_ready = bars + 11;
+  uint64_t* out_done = bars + 12;                // [2]
+  uint64_t* tile_done = bars + 14; uint64_t* out_free = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int heads = p.heads;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(wq_full, 1); mbar_init(wq_free, 1); mbar_init(wo_full, 1); mbar_init(wo_free, 1);
+    mbar_init(x_ready, 8);
+    mbar_init(qkv_done + 0, 1); mbar_init(qkv_done + 1, 1);
+    mbar_init(qk_ready, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8); mbar_init(o_done, 1); mbar_init(osm_ready, 8);
+    mbar_init(out_done + 0, 1); mbar_init(out_done + 1, 1);
+    mbar_init(tile_done, 1); mbar_init(out_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&mapWq); tma_prefetch_desc(&mapWo); }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_tiles = (p.n_windows + 1) / 2;
+
+  if (warp == 0) {
+    // ============================== TMA: stream the per-head weights ==============================
+    if (lane == 0) {
+      uint32_t it = 0;                                       // global head counter
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int h = 0; h < heads; ++h, ++it) {
+          mbar_wait(wq_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(wq_full, 4 * 12288);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + WQ_OFF + kb * 12288, &mapWq, wq_full, kb * 32, h * 96);
+          mbar_wait(wo_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(wo_full, 16384);
+          tma_load_2d(smem + WO_OFF, &mapWo, wo_full, 0, h * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t id_qkv = umma_idesc_tf32(128, 96);
+      constexpr uint32_t id_s = umma_idesc_tf32(128, 128);
+      constexpr uint32_t id_pv = umma_idesc_bf16(128, 32);
+      constexpr uint32_t id_out = umma_idesc_tf32(128, 128);
+      const uint32_t sX = smem_u32(smem + X_OFF), sWQ = smem_u32(smem + WQ_OFF), sWO = smem_u32(smem + WO_OFF);
+      uint32_t it = 0, tl = 0;                               // global head counter, tile counter
+      auto issue_qkv = [&](uint32_t hh) {
+        mbar_wait(wq_full, hh & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + ((hh & 1) ? T_QKV1 : T_QKV0);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t da = umma_desc_k128(sX + kb * 16384), db = umma_desc_k128(sWQ + kb * 12288);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32(d, da + 2 * k, db + 2 * k, id_qkv, (kb | k) ? 1u : 0u);
+        }
+        tc_commit(qkv_done + (hh & 1));
+        tc_commit(wq_free);
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        mbar_wait(x_ready, tl & 1);
+        tc_fence_after();
+        issue_qkv(it);
+        for (int h = 0; h < heads; ++h, ++it) {
+          const uint32_t r = it & 1;
+          const uint32_t sR1 = smem_u32(smem + R1_OFF + r * 32768), sVT = smem_u32(smem + VT_OFF + r * 8192);
+          // ---- S = Q^ K^^T
+          mbar_wait(qk_ready, it & 1);
+          tc_fence_after();
+          {
+            const uint64_t da = umma_desc_k128(sR1), db = umma_desc_k128(sR1 + 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem + T_S, da + 2 * k, db + 2 * k, id_s, k ? 1u : 0u);
+          }
+          tc_commit(s_done);
+          // ---- next head's QKV projection runs under this head's softmax
+          if (h + 1 < heads) issue_qkv(it + 1);
+          // ---- O = P V
+          mbar_wait(p_ready, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t da = umma_desc_k128(sR1 + kb * 16384), db = umma_desc_k128(sVT + kb * 4096);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + T_O, da + 2 * k, db + 2 * k, id_pv, (kb | k) ? 1u : 0u);
+          }
+          tc_commit(o_done);
+          // ---- Out += O_h Wout_h^T
+          mbar_wait(osm_ready, it & 1);
+          mbar_wait(wo_full, it & 1);
+          if (h == 0) mbar_wait(out_free, (tl & 1) ^ 1);     // previous tile's epilogue has drained Out
+          tc_fence_after();
+          {
+            const uint64_t da = umma_desc_k128(sR1), db = umma_desc_k128(sWO);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem + T_OUT, da + 2 * k, db + 2 * k, id_out, (h | k) ? 1u : 0u);
+          }
+          tc_commit(out_done + r);
+          tc_commit(wo_free);
+        }
+        tc_commit(tile_done);
+      }
+    }
+  } else {
+    // ============================== compute warps: two threads per token row ==============================
+    const int cw = warp - 2;                                 // 0..7
+    const int lg = warp & 3;                                 // TMEM lane group this warp may access
+    const int ch = cw >> 2;                                  // column half handled by this thread
+    const int ctid = cw * 32 + lane;                         // 0..255
+    const int t = lg * 32 + lane;                            // tile row == TMEM lane
+    const int half = t >> 6, i = t & 63;                     // window within the pair, token slot
+    const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
+    const AttnGeom g = p.g;
+    const int nwin = g.nwin();
+    const bool tok_valid = i < SEQ;
+    const bool is_reg = i < REG;
+    // window position of this token (clamped for register / pad slots so that table addresses stay valid)
+    const int ti = (i >= REG && i < SEQ) ? i - REG : 0;
+    const int ai = ti / WIN, bi = ti - ai * WIN;
+    const uint32_t s_base = smem_u32(smem);
+    uint32_t swz[8];                                         // swizzled chunk offsets of this thread's tile row
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swz[c] = sw128(t, c);
+    float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [4][128][2]: 0 softmax sum, 1 LN sum, 2 softmax max, 3 LN sq-sum
+    const float rs = sqrtf((float)DH);
+    uint32_t it = 0, tl = 0;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      // ---------------- gather + LayerNorm + FiLM -> X tile (tf32, swizzled K-major) ----------------
+      const long long wdx = tile * 2 + half;
+      const bool win_valid = wdx < p.n_windows;
+      const int n = win_valid ? (int)(wdx / nwin) : 0;
+      const int wi = win_valid ? (int)(wdx - (long long)n * nwin) : 0;
+      const float* src = nullptr;                           // residual-stream row of this token
+      long long pix = -1;
+      if (win_valid && tok_valid) {
+        if (is_reg) src = p.reg_in + (p.reg_per_field ? (long long)n * REG * C : 0) + (long long)i * C;
+        else {
+          const int xw = wi / g.Y, yw = wi - xw * g.Y;
+          const int ph = g.grid_mode ? ai * g.X + xw : xw * WIN + ai;     // maxvit.py:322 / :298
+          const int pw = g.grid_mode ? bi * g.Y + yw : yw * WIN + bi;
+          pix = (long long)n * g.Hl * g.Wl + (long long)ph * g.Wl + pw;
+          src = p.x + pix * C;
+        }
+      }
+      {
+        // this thread owns channels [ch*64, +64) of the row; the row statistics are exchanged within the pair
+        float4 v[16];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          v[c] = src ? *reinterpret_cast<const float4*>(src + ch * 64 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          s += v[c].x + v[c].y + v[c].z + v[c].w;
+        }
+        red[(1 * 128 + t) * 2 + ch] = s;
+        pair_sync(lg);
+        const float mean = (red[(1 * 128 + t) * 2] + red[(1 * 128 + t) * 2 + 1]) * (1.0f / C);
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+          ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
+        }
+        red[(3 * 128 + t) * 2 + ch] = ss;
+        pair_sync(lg);
+        const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
+        const float* film = p.film + (long long)n * 2 * C + ch * 64;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src) {
+            const float4 ga = *reinterpret_cast<const float4*>(film + c * 4), be = *reinterpret_cast<const float4*>(film + C + c * 4);
+            o.x = v[c].x * rstd * ga.x + be.x; o.y = v[c].y * rstd * ga.y + be.y;
+            o.z = v[c].z * rstd * ga.z + be.z; o.w = v[c].w * rstd * ga.w + be.w;
+          }
+          sts128(s_base + X_OFF + (ch * 2 + (c >> 3)) * 16384 + swz[c & 7], o.x, o.y, o.z, o.w);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_ready);
+
+      for (int h = 0; h < heads; ++h, ++it) {
+        const uint32_t r = it & 1;
+        const uint32_t R1 = s_base + R1_OFF + r * 32768;
+        const uint32_t VT = s_base + VT_OFF + r * 8192;
+        const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
+        // per-head tables (shifted relative-position bias rows, q/k gamma): global (L2) -> smem
+        {
+          const float* gt = p.head_tab + (long long)h * TAB_FLOATS;
+          float* st = reinterpret_cast<float*>(smem + TAB_OFF) + r * TAB_FLOATS;
+          for (int k = ctid; k < TAB_FLOATS; k += 256) st[k] = __ldg(gt + k);
+        }
+        compute_bar_sync();
+        // ---------------- QKV_h: TMEM -> registers, RMSNorm, -> smem operands ----------------
+        mbar_wait(qkv_done + r, (it >> 1) & 1);
+        if (it >= 2) mbar_wait(out_done + r, ((it - 2) >> 1) & 1);      // R1[r] / VT[r] no longer read by MMAs
+        tc_fence_after();
+        {
+          const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
+          float v[32], vv[16];
+          tmem_ld32(tq + ch * 32, v);                                    // ch 0: q, ch 1: k
+          tmem_ld16(tq + 64 + ch * 16, vv);                              // half of v
+          tmem_wait_ld();
+          float nrm = 0.f;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) nrm += v[d] * v[d];
+          const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);              // F.normalize(eps=1e-12) * sqrt(d)  (maxvit.py:30)
+          const uint32_t gam = tab + (7 * 13 * 8 + 8 + ch * 32) * 4;
+          const uint32_t dst = R1 + ch * 16384;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 gm = lds128(gam + c * 16);
+            sts128(dst + swz[c], v[4 * c] * inv * gm.x, v[4 * c + 1] * inv * gm.y, v[4 * c + 2] * inv * gm.z, v[4 * c + 3] * inv * gm.w);
+          }
+          // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
+          const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
+          const int kc = (t & 63) >> 3;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            const int dd = ch * 16 + d;
+            sts16(vt + sw128(dd, kc), __bfloat16_as_ushort(__float2bfloat16(vv[d])));
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qk_ready);
+
+        // ---------------- S half-row: + bias, masked softmax -> P (bf16) ----------------
+        mbar_wait(s_done, it & 1);
+        tc_fence_after();
+        {
+          float sc[32];
+          tmem_ld32(lane_addr + T_S + half * 64 + ch * 32, sc);
+          tmem_wait_ld();
+          const float t169 = reinterpret_cast<const float*>(smem + TAB_OFF)[r * TAB_FLOATS + 7 * 13 * 8];
+          const uint32_t brow = tab + (bi * 13 * 8) * 4;
+          float m = -INFINITY;
+          if (ch == 0) {
+            // keys 0..3 are register tokens, keys 4..31 are window rows aj = 0..3
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[j] += t169;
+#pragma unroll
+            for (int aj = 0; aj < 4; ++aj) {
+              const uint32_t a = brow + (ai + 6 - aj) * 32;
+              const float4 b0 = lds128(a), b1 = lds128(a + 16);
+              float* q = sc + 4 + aj * 7;
+              q[0] += is_reg ? t169 : b0.x; q[1] += is_reg ? t169 : b0.y; q[2] += is_reg ? t169 : b0.z; q[3] += is_reg ? t169 : b0.w;
+              q[4] += is_reg ? t169 : b1.x; q[5] += is_reg ? t169 : b1.y; q[6] += is_reg ? t169 : b1.z;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, sc[j]);
+          } else {
+            // keys 32..52 are window rows aj = 4..6; keys 53..63 are padding
+#pragma unroll
+            for (int aj = 4; aj < 7; ++aj) {
+              const uint32_t a = brow + (ai + 6 - aj) * 32;
+              const float4 b0 = lds128(a), b1 = lds128(a + 16);
+              float* q = sc + (aj - 4) * 7;
+              q[0] += is_reg ? t169 : b0.x; q[1] += is_reg ? t169 : b0.y; q[2] += is_reg ? t169 : b0.z; q[3] += is_reg ? t169 : b0.w;
+              q[4] += is_reg ? t169 : b1.x; q[5] += is_reg ? t169 : b1.y; q[6] += is_reg ? t169 : b1.z;
+            }
+#pragma unroll
+            for (int j = 0; j < 21; ++j) m = fmaxf(m, sc[j]);
+          }
+          red[(2 * 128 + t) * 2 + ch] = m;
+          pair_sync(lg);
+          m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]) * LOG2E;
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = (ch == 0 || j < 21) ? ex2(fmaf(sc[j], LOG2E, -m)) : 0.f;
+            sc[j] = e; sum += e;
+          }
+          red[(0 * 128 + t) * 2 + ch] = sum;
+          // own 32 keys = chunks [ch*4, +4) of this row in k-block `half`; same chunks of the other k-block are zero
+          const uint32_t prow = R1 + half * 16384, zrow = R1 + (half ^ 1) * 16384;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
+                    pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
+            sts128u(zrow + swz[ch * 4 + c], 0u, 0u, 0u, 0u);
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        pair_sync(lg);                                                   // partner's partial row sum is visible
+        const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
+
+        // ---------------- O_h / rowsum -> smem (tf32) ----------------
+        mbar_wait(o_done, it & 1);
+        tc_fence_after();
+        {
+          float o[16];
+          tmem_ld16(lane_addr + T_O + ch * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(R1 + swz[ch * 4 + c], o[4 * c] * inv_sum, o[4 * c + 1] * inv_sum, o[4 * c + 2] * inv_sum, o[4 * c + 3] * inv_sum);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(osm_ready);
+      }
+
+      // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------
+      mbar_wait(tile_done, tl & 1);
+      tc_fence_after();
+      {
+        float* dst = nullptr;
+        if (src) {
+          if (is_reg) dst = p.reg_out ? p.reg_out + (wdx * REG + i) * C : nullptr;
+          else dst = p.x_out + pix * C;
+        }
+        float v[32];
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          const int c0 = ch * 64 + q * 32;
+          tmem_ld32(lane_addr + T_OUT + c0, v); tmem_wait_ld();
+          if (dst) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(src + c0 + c);
+              *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(v[c] + rr.x, v[c + 1] + rr.y, v[c + 2] + rr.z, v[c + 3] + rr.w);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_w_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, int box_outer) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || !q)
+      return set_error("cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("attn_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// wqkv_h: fp32 [heads*96][128] (per head: 32 q rows, 32 k rows, 32 v rows); wout_h: fp32 [heads*128][32]
+int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
+                   const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab,
+                   const AttnGeom& g, int heads, int dh, float ln_eps, cudaStream_t st) {
+  if (g.C != fa::C || dh != fa::DH) return set_error("attn_fused: needs C=128, dim_head=32 (got C=%d, dh=%d)", g.C, dh);
+  if (g.win != fa::WIN || g.R != fa::REG) return set_error("attn_fused: specialised for 7x7 windows + 4 register tokens (got %d, %d)", g.win, g.R);
+  CUtensorMap mq, mo;
+  int rc = make_w_map(&mq, wqkv_h, 128, (long long)heads * 96, 96);
+  if (rc) return rc;
+  rc = make_w_map(&mo, wout_h, 32, (long long)heads * 128, 128);
+  if (rc) return rc;
+  FusedAttnParams p;
+  p.x = x; p.x_out = x_out; p.reg_in = reg_in; p.reg_per_field = reg_per_field; p.reg_out = reg_out; p.film = film;
+  p.head_tab = head_tab; p.g = g; p.heads = heads;
+  p.ln_eps = ln_eps; p.n_windows = (long long)g.N * g.nwin();
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("attn_fused smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (p.n_windows + 1) / 2;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  attn_fused_kernel<<<grid, fa::THREADS, fa::SMEM_BYTES, st>>>(mq, mo, p);
+  return check_launch("attn_fused_kernel");
+}
+
+}  // namespace vg

@@ -32,7 +32,13 @@ struct EpiParams {
   float ln_eps;
   const float* film;         // [fields][2C]  (scale | shift), applied as v*(scale+1)+shift; null = none
   PGeom pg;                  // output geometry (EPI_CONV_LN, EPI_CONVT)
-  const float* head_w;       // optional fused 1x1 head (C -> 1): out_head[...] = dot(y, head_w) (unused in v1)
+  int res_f32;               // EPI_CONV_LN: the residual is fp32 (skip connections keep full precision)
+  float* out2;               // optional fp32 copy of the output (EPI_CONV_LN, EPI_CONVT), same indexing as out
+  // optional fused 1x1 head + unpad + de-normalisation (metnet3.py:424-430): head_out[n][h-pt][w-pl]
+  const float* head_w;       // [C]; null = no head
+  float* head_out;           // (N, H, W) fp32
+  float head_b, head_std, head_mean;
+  int head_H, head_W, head_pt, head_pl;
   // EPI_ATTN_OUT
   int S, R, nwin, grid_mode, win, X, Y, Hl, Wl;
   const void* x_in;          // (N, Hl*Wl, C) residual stream the window tokens came from
@@ -106,8 +112,11 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, long long row, 
   }
   const float rstd = rsqrtf(fmaxf(ss * (1.0f / C), ep.ln_eps));     // var.clamp(min=eps).rsqrt()  (metnet3.py:104)
   const float* film = (ep.film && valid) ? ep.film + (long long)n * 2 * C : nullptr;
-  T* o = reinterpret_cast<T*>(ep.out) + row * ep.ldo;
-  const T* r = ep.res ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
+  T* o = ep.out ? reinterpret_cast<T*>(ep.out) + row * ep.ldo : nullptr;
+  float* o2 = ep.out2 ? ep.out2 + row * ep.ldo : nullptr;
+  const T* r = (ep.res && !ep.res_f32) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
+  const float* rf = (ep.res && ep.res_f32) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
+  float head = 0.f;
   // pass 3: normalise, FiLM, ReLU, residual, store (zeros at pad positions)
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
@@ -127,12 +136,33 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, long long row, 
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
       }
+      if (rf) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) { float t[8]; ld8(rf + ch * 32 + j, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
+      }
+      if (ep.head_w) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) head = fmaf(v[j], __ldg(ep.head_w + ch * 32 + j), head);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
+    if (o) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+      for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+    }
+    if (o2) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st8(o2 + ch * 32 + j, v + j);
+    }
+  }
+  if (ep.head_w && valid) {
+    const int hh = h - ep.head_pt, ww = w - ep.head_pl;
+    if (hh >= 0 && hh < ep.head_H && ww >= 0 && ww < ep.head_W)
+      ep.head_out[((long long)n * ep.head_H + hh) * ep.head_W + ww] = (head + ep.head_b) * ep.head_std + ep.head_mean;
   }
 }
 
@@ -197,6 +227,10 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
     for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + cbase + ch * 32 + j);
 #pragma unroll
     for (int j = 0; j < 32; j += 8) st8_out<T>(ep, o + ch * 32 + j, v + j);
+    if (ep.out2) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st8(ep.out2 + o + ch * 32 + j, v + j);
+    }
   }
 }
 

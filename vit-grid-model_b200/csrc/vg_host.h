@@ -58,7 +58,7 @@ int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, in
 int time_terms_run(const TimeParams& p, cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
-int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStream_t st);
+int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st);
 int maxpool2_run(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st);
 int dwconv_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out, float* psum,
                int N, int H, int W, int C, cudaStream_t st);
@@ -84,5 +84,9 @@ int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_fiel
                     float eps, void* tokens, cudaStream_t st);
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
                   const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st);
+
+int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
+                   const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,
+                   cudaStream_t st);
 
 }  // namespace vg

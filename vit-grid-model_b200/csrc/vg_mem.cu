@@ -137,7 +137,7 @@ __global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_
 // ================================================================================================
 
 template <typename T>
-__global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, T* __restrict__ res) {
+__global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
   constexpr int C = 128;
   const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (q >= p.pgN.pixels()) return;
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
     r[0] = ra.x + rb.x + rt.x; r[1] = ra.y + rb.y + rt.y; r[2] = ra.z + rb.z + rt.z; r[3] = ra.w + rb.w + rt.w;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { Act<T>::st(h1 + q * C + c0 + i, y[i]); Act<T>::st(res + q * C + c0 + i, r[i]); }
+  for (int i = 0; i < 4; ++i) Act<T>::st(h1 + q * C + c0 + i, y[i]);
+  *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // ================================================================================================
@@ -408,10 +409,10 @@ int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0
   return check_launch("cond_mlp_kernel");
 }
 
-int stem_finish_run(int dtype, const StemParams& p, void* h1, void* res, cudaStream_t st) {
+int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st) {
   const unsigned g = nblk(p.pgN.pixels(), 8);
-  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), reinterpret_cast<bf16*>(res));
-  else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), reinterpret_cast<float*>(res));
+  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), res);
+  else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), res);
   return check_launch("stem_finish_kernel");
 }
 

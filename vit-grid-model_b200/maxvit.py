@@ -123,6 +123,7 @@ class MaxViT(nn.Module):
             self.layers.append(nn.ModuleList([conv, Attention(**kw), Attention(**kw)]))
             self.register_tokens.append(nn.Parameter(torch.randn(num_register_tokens, dim)))
         self.set_precision("bf16")
+        self.fused_attention = True      # one-kernel attention (tf32 mode, dim 128, dim_head 32, <=64 tokens/window)
         self._packed = None
         self._packed_key = None
         self._capture = None
@@ -167,6 +168,14 @@ class MaxViT(nn.Module):
                     k_gamma=att.k_norm.gamma.float().reshape(-1).contiguous(),
                     w_out=att.to_out[0].weight.to(dtype).contiguous(),
                     bias_table=att.rel_pos_bias.weight.float().contiguous())
+                inner, dh, hd = att.heads * att.dim_head, att.dim_head, att.heads
+                wq = att.to_qkv.weight.float()
+                # per-head operand tiles of the fused kernel: [q_h | k_h | v_h] rows, and the head's to_out columns
+                P[name]["wqkv_h"] = torch.stack([wq[i * inner:(i + 1) * inner].reshape(hd, dh, -1) for i in range(3)],
+                                                dim=1).reshape(hd * 3 * dh, -1).contiguous()
+                P[name]["wout_h"] = att.to_out[0].weight.float().reshape(-1, hd, dh).permute(1, 0, 2).contiguous()
+                if att.window_size == 7 and dh == 32:
+                    P[name]["head_tab"] = ops.pack_head_tables(P[name]["bias_table"], P[name]["q_gamma"], P[name]["k_gamma"])
             P["reg"] = self.register_tokens[li].float().contiguous()
             layers.append(P)
         self._packed, self._packed_key = layers, key
@@ -177,6 +186,9 @@ class MaxViT(nn.Module):
         """x: CL (N,H,W,C).  returns (x + attn(x), reg_out)"""
         N, H, W, C = x.shape
         w, R = self.vit_window_size, self.num_register_tokens
+        if self.fused_attention and self.tf32 and C == 128 and self.dim_head == 32 and w == 7 and R == 4:
+            return ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
+                                  self.heads, self.dim_head)
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
         qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32)
         del tokens

@@ -213,13 +213,16 @@ class MetNet3(nn.Module):
         return P
 
     # ------------------------------------------------------------------ forward
-    def _resblock(self, x, cond, d, bufs, N, HP, WP):
-        """generic 128->128 ResnetBlock on PG buffers: returns the buffer holding h + x (metnet3.py:149-162)"""
+    def _resblock(self, x, skip, cond, d, bufs, N, HP, WP, out_copy=None, head=None):
+        """128->128 ResnetBlock on PG buffers (metnet3.py:149-162).  x: block input (compute dtype); skip: the same
+        tensor as the residual operand (fp32 copy in bf16 mode).  Returns the buffer holding h + x (None when the head
+        is fused into the last epilogue)."""
         film = ops.cond_mlp(cond, d["mlp_w"], d["mlp_b"], pre_relu=True)
         t1, t2 = [b for b in bufs if b is not x][:2]
         ops.conv3x3_ln(x, d["w1"], d["b1"], d["g1"], d["be1"], d["eps1"], film, None, t1, N, HP, WP)
-        ops.conv3x3_ln(t1, d["w2"], d["b2"], d["g2"], d["be2"], d["eps2"], None, x, t2, N, HP, WP)
-        return t2
+        ops.conv3x3_ln(t1, d["w2"], d["b2"], d["g2"], d["be2"], d["eps2"], None, skip, None if head else t2, N, HP, WP,
+                       out_copy=out_copy, head=head)
+        return None if head else t2
 
     def _forward_chunk(self, x, b0, b1, terms, P, dtype, out):
         """fields of samples [b0,b1) of x -> out[b0:b1]"""
@@ -232,6 +235,7 @@ class MetNet3(nn.Module):
         dev = x.device
         cond = cond_all[b0 * L:b1 * L]
         tt, tres = tt_all[b0 * L:b1 * L], tres_all[b0 * L:b1 * L]
+        mixed = dtype != torch.float32            # bf16 activations: skip connections travel as separate fp32 copies
         # ---- stem, once per sample
         s0 = P["resnet1"][0]
         xin = ops.prepare(x[b0:b1], pads, HP, WP, P["c_pad"], self.pm25_mean, self.pm25_std, dtype)
@@ -239,18 +243,26 @@ class MetNet3(nn.Module):
         rawres = ops.gemm(xin, s0["wres"], out_f32=True)
         del xin
         bufs = [ops.pg_empty(N, HP, WP, C, dtype, dev) for _ in range(3)]
+        skips = [ops.pg_empty(N, HP, WP, C, torch.float32, dev) for _ in range(2)]
         film = ops.cond_mlp(cond, s0["mlp_w"], s0["mlp_b"], pre_relu=True)
         ops.stem_finish(raw3, rawres, s0["b1"], s0["bres"], tt, tres, s0["g1"], s0["be1"], s0["eps1"], film, B, L, HP, WP,
-                        bufs[0], bufs[1])
+                        bufs[0], skips[0])
         del raw3, rawres
-        ops.conv3x3_ln(bufs[0], s0["w2"], s0["b2"], s0["g2"], s0["be2"], s0["eps2"], None, bufs[1], bufs[2], N, HP, WP)
-        h = bufs[2]
+        blocks1, blocks2 = P["resnet1"][1:], P["resnet2"]
+        # block output that a later ResnetBlock uses as its skip gets an fp32 copy (bf16 mode only)
+        want_copy = mixed and len(blocks1) > 0
+        ops.conv3x3_ln(bufs[0], s0["w2"], s0["b2"], s0["g2"], s0["be2"], s0["eps2"], None, skips[0], bufs[2], N, HP, WP,
+                       out_copy=skips[1] if want_copy else None)
+        h, hs = bufs[2], (skips[1] if want_copy else bufs[2])
         cap = self._capture
         if cap is not None:
-            cap["stem_h1"], cap["stem_res"] = ops.pg_to_nchw(bufs[0], N, HP, WP), ops.pg_to_nchw(bufs[1], N, HP, WP)
+            cap["stem_h1"], cap["stem_res"] = ops.pg_to_nchw(bufs[0], N, HP, WP), ops.pg_to_nchw(skips[0], N, HP, WP)
             cap["resnet1.0"] = ops.pg_to_nchw(h, N, HP, WP)
-        for d in P["resnet1"][1:]:
-            h = self._resblock(h, cond, d, bufs, N, HP, WP)
+        for k, d in enumerate(blocks1):
+            nxt = [sk for sk in skips if sk is not hs][0]
+            copy = nxt if (mixed and k + 1 < len(blocks1)) else None
+            h = self._resblock(h, hs, cond, d, bufs, N, HP, WP, out_copy=copy)
+            hs = copy if copy is not None else h
         # ---- MaxViT at half resolution
         low = ops.pool2(h, N, HP, WP, out_dtype=self.vit.compute_dtype)
         if cap is not None:
@@ -261,17 +273,23 @@ class MetNet3(nn.Module):
             cap["vit"] = low.permute(0, 3, 1, 2).float()
         # ---- decoder
         up = [b for b in bufs if b is not h][0]       # pads of every PG buffer are already zero (written by conv/stem)
-        ops.convT2(low, P["w_up_vit"], P["b_up"], up, tf32=self.vit.tf32)
+        ops.convT2(low, P["w_up_vit"], P["b_up"], up, tf32=self.vit.tf32, out_copy=skips[0] if mixed else None)
         del low
-        h = up
+        h, hs = up, (skips[0] if mixed else up)
         if cap is not None:
             cap["up"] = ops.pg_to_nchw(h, N, HP, WP)
-        for d in P["resnet2"]:
-            h = self._resblock(h, cond, d, bufs, N, HP, WP)
+        head = (P["w_head"], P["b_head"], self.pm25_std, self.pm25_mean, self.input_height, self.input_width, pads,
+                out[b0:b1].view(N, self.input_height, self.input_width))
+        for k, d in enumerate(blocks2):
+            last = k + 1 == len(blocks2)
+            nxt = [sk for sk in skips if sk is not hs][0]
+            copy = nxt if (mixed and not last) else None
+            h = self._resblock(h, hs, cond, d, bufs, N, HP, WP, out_copy=copy, head=head if (last and cap is None) else None)
+            hs = copy if copy is not None else h
         if cap is not None:
             cap["resnet2"] = ops.pg_to_nchw(h, N, HP, WP)
-        ops.head(h, P["w_head"], P["b_head"], self.pm25_std, self.pm25_mean, N, HP, WP, self.input_height, self.input_width,
-                 pads, out=out[b0:b1].view(N, self.input_height, self.input_width))
+            ops.head(h, P["w_head"], P["b_head"], self.pm25_std, self.pm25_mean, N, HP, WP, self.input_height,
+                     self.input_width, pads, out=out[b0:b1].view(N, self.input_height, self.input_width))
 
     def forward(self, x, labels_pm25=None, region_targets_pm25=None, labels_pm10=None, region_targets_pm10=None,
                 timestamps: torch.Tensor = None, prev_vals: torch.Tensor = None):

@@ -115,11 +115,19 @@ def conv_tap_shifts(WP):
     return tuple((ky - 1) * P + (kx - 1) for ky in range(3) for kx in range(3))
 
 
-def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP):
+def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy=None, head=None):
+    """head = (w[C], b, std, mean, H, W, pads, out (N,H,W) fp32) fuses the 1x1 head / unpad / de-normalisation"""
     dtype = x.dtype
     keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
+    res_f32 = int(res is not None and res.dtype == torch.float32 and dtype != torch.float32)
+    if head is None:
+        hw, hb, hs, hm, H, W, pt, pl, ho = None, 0.0, 1.0, 0.0, 0, 0, 0, 0, None
+    else:
+        hw, hb, hs, hm, H, W, pads, ho = head
+        pl, _, pt, _ = pads
     _lib.call("vg_conv3x3_ln_fwd", DT_CODE[dtype], x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
-              ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), out.data_ptr(), N, HP, WP, sp, sn, _st())
+              ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP,
+              _p(hw), float(hb), float(hs), float(hm), H, W, pt, pl, _p(ho), sp, sn, _st())
     return out
 
 
@@ -193,6 +201,37 @@ def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None
     return x_out, reg_out
 
 
+def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
+    """per-head table of the fused attention kernel: relative-position bias as `win` pre-shifted copies
+    [bi][row 0..2w-2][8] with entry k = table[row*(2w-1) + bi + (w-1) - k] (so that the 7 keys of one window row are one
+    aligned 32-byte read), then table[(2w-1)^2] (+7 pad), q gamma[dh], k gamma[dh].  bias_table: (nb, heads)."""
+    assert win == 7, "the fused kernel is specialised for 7x7 windows"
+    heads, w2 = bias_table.shape[1], 2 * win - 1
+    bi = torch.arange(win).view(win, 1, 1)
+    row = torch.arange(w2).view(1, w2, 1)
+    k = torch.arange(8).view(1, 1, 8)
+    idx = (row * w2 + bi + (win - 1) - k).clamp_(0, w2 * w2 - 1)                      # k = 7 is padding
+    T = bias_table.t().float()                                                       # (heads, nb)
+    shifted = T[:, idx.reshape(-1).to(T.device)].reshape(heads, win, w2, 8)
+    shifted[..., 7] = 0
+    t_last = torch.zeros(heads, 8, device=T.device)
+    t_last[:, 0] = T[:, w2 * w2]
+    return torch.cat([shifted.reshape(heads, -1), t_last, q_gamma.float().reshape(heads, -1),
+                      k_gamma.float().reshape(heads, -1)], dim=1).contiguous()
+
+
+def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5):
+    """whole attention layer (+ residual) in one kernel; x CL (N,Hl,Wl,128) fp32"""
+    N, Hl, Wl, C = x.shape
+    assert x.dtype == torch.float32
+    nwin = (Hl // win) * (Wl // win)
+    x_out = torch.empty_like(x)
+    reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x.device) if want_reg_out else None
+    _lib.call("vg_attn_fused_fwd", x.data_ptr(), x_out.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out),
+              film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps), _st())
+    return x_out, reg_out
+
+
 def reg_mean(reg_out, N, nwin):
     R, C = reg_out.shape[1], reg_out.shape[2]
     out = torch.empty(N, R, C, dtype=torch.float32, device=reg_out.device)
@@ -200,12 +239,12 @@ def reg_mean(reg_out, N, nwin):
     return out
 
 
-def convT2(x, Wt, bias, out, tf32=False):
+def convT2(x, Wt, bias, out, tf32=False, out_copy=None):
     """x CL (N,Hl,Wl,C) -> out PG (N,2Hl,2Wl,C); `out` must already hold zeros at its pad positions.
     `out` may be bf16 while x is fp32 (mixed mode: tf32 MaxViT feeding the bf16 decoder convs)."""
     N, Hl, Wl, C = x.shape
     keep, sp, sn = _scratch(x.dtype, N * Hl * Wl * 4 * C, x.device, tf32)
-    _lib.call("vg_convT2_fwd", _gemm_code(x.dtype, tf32), int(out.dtype == torch.bfloat16 and x.dtype != torch.bfloat16), x.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), N, Hl, Wl,
+    _lib.call("vg_convT2_fwd", _gemm_code(x.dtype, tf32), int(out.dtype == torch.bfloat16 and x.dtype != torch.bfloat16), x.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), _p(out_copy), N, Hl, Wl,
               C, sp, sn, _st())
     return out
 
