@@ -23,3 +23,19 @@ for _ in range(iters):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"N={N} ms={ms:.3f} algorithmic TFLOP/s={flops / ms / 1e9:.1f}")
+# mainloop-only reference point: same shifted GEMM with the plain store epilogue
+o2 = torch.empty_like(x)
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.gemm(x, w, ntaps=9, tap_shift=ops.conv_tap_shifts(WP), out=o2)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"plain-store epilogue: ms={e0.elapsed_time(e1):.3f} TFLOP/s={flops / e0.elapsed_time(e1) / 1e9:.1f}")
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.conv3x3_ln(x, w, b, ga, be, 1e-5, None, None, out, N, HP, WP)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"LN epilogue, no film/res: ms={e0.elapsed_time(e1):.3f} TFLOP/s={flops / e0.elapsed_time(e1) / 1e9:.1f}")

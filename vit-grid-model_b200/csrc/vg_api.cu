@@ -108,6 +108,10 @@ int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const fl
   ep.head_H = H; ep.head_W = W; ep.head_pt = pad_top; ep.head_pl = pad_left;
   if (!out && !head_w) return set_error("conv3x3_ln: no output requested");
   if (head_w && !head_out) return set_error("conv3x3_ln: head_w without head_out");
+  if (dtype == 0 && Ca == 128) {                     // halo-reuse kernel (falls through when the row pitch is too large)
+    const int rc = conv_halo_run(x, Wt, pg, ep, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   int shifts[9];
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) shifts[ky * 3 + kx] = (ky - 1) * pg.P + (kx - 1);

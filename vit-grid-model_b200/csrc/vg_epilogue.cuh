@@ -84,63 +84,108 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bo
   }
 }
 
+// Per-channel parameters of the conv epilogue; the tcgen05 kernel stages them in shared memory once per CTA,
+// the fp32-mode row kernel points them at global memory.
+struct EpiCtx {
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  // FiLM folded into the LayerNorm affine, staged per tile by the epilogue warpgroup (tcgen05 kernel only):
+  // gb[f][0..127] = g*(scale+1), gb[f][128..255] = b*(scale+1)+shift for the fields n_first+f, f in {0,1}
+  const float* gb;
+  int n_first;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// residual row: issued before the accumulator is ready so the DRAM latency hides behind the MMAs
+template <typename T>
+__device__ __forceinline__ void epi_conv_ln_prefetch(const EpiParams& ep, long long row, bool ok) {
+  if (!ep.res || !ok || row >= ep.pg.pixels()) return;
+  const char* r = reinterpret_cast<const char*>(ep.res) + row * ep.ldres * (ep.res_f32 ? 4 : (long long)sizeof(T));
+  const int bytes = 128 * (ep.res_f32 ? 4 : (int)sizeof(T));
+  for (int o = 0; o < bytes; o += 128) prefetch_l2(r + o);
+}
+
 // Requires the whole channel row in one tile: n0 == 0, C == 128.
 template <typename T, class Loader>
-__device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+__device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& cx, long long row, bool ok, int n0, Loader& ld) {
   (void)n0;
   constexpr int C = 128;
   float v[32];
   int n, h, w;
   const bool in_buf = ok && row < ep.pg.pixels();
   const bool valid = ep.pg.decode(row, n, h, w) && in_buf;
-  // pass 1: mean of (acc + bias)
-  float s = 0.f;
+  // pass 1: shifted one-pass statistics of x = acc + bias (shift = first element, so E[d^2]-E[d]^2 does not cancel)
+  float s1 = 0.f, s2 = 0.f, x0 = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     ld.load(ch, v);
+    if (ch == 0) x0 = v[0] + cx.bias[0];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += v[j] + __ldg(ep.bias + ch * 32 + j);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(cx.bias + ch * 32 + j);
+      const float d0 = v[j] + b4.x - x0, d1 = v[j + 1] + b4.y - x0, d2 = v[j + 2] + b4.z - x0, d3 = v[j + 3] + b4.w - x0;
+      s1 += (d0 + d1) + (d2 + d3);
+      s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+    }
   }
-  const float mean = s * (1.0f / C);
-  // pass 2: biased variance (two-pass form, as torch.var does)
-  float ss = 0.f;
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    ld.load(ch, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { float d = v[j] + __ldg(ep.bias + ch * 32 + j) - mean; ss += d * d; }
-  }
-  const float rstd = rsqrtf(fmaxf(ss * (1.0f / C), ep.ln_eps));     // var.clamp(min=eps).rsqrt()  (metnet3.py:104)
-  const float* film = (ep.film && valid) ? ep.film + (long long)n * 2 * C : nullptr;
+  const float md = s1 * (1.0f / C);
+  const float mean = x0 + md;
+  const float var = fmaxf(s2 * (1.0f / C) - md * md, 0.f);             // biased variance
+  const float rstd = rsqrtf(fmaxf(var, ep.ln_eps));                    // var.clamp(min=eps).rsqrt()  (metnet3.py:104)
+  // affine = LayerNorm (g, b) with the per-field FiLM (scale+1, shift) folded in when staged; else applied explicitly
+  const float* film = (ep.film && valid && !cx.gb) ? ep.film + (long long)n * 2 * C : nullptr;
+  const float* pg_ = cx.ln_g;
+  const float* pb_ = cx.ln_b;
+  if (cx.gb) { const int f = (valid && n > cx.n_first) ? 1 : 0; pg_ = cx.gb + f * 256; pb_ = pg_ + 128; }
   T* o = ep.out ? reinterpret_cast<T*>(ep.out) + row * ep.ldo : nullptr;
   float* o2 = ep.out2 ? ep.out2 + row * ep.ldo : nullptr;
-  const T* r = (ep.res && !ep.res_f32) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
-  const float* rf = (ep.res && ep.res_f32) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
+  const T* r = (ep.res && !ep.res_f32 && valid) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
+  const float* rf = (ep.res && ep.res_f32 && valid) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
   float head = 0.f;
-  // pass 3: normalise, FiLM, ReLU, residual, store (zeros at pad positions)
+  // pass 2: normalise, FiLM, ReLU, residual, store (zeros at pad positions); the residual of chunk ch+1 is in
+  // flight while chunk ch is processed
+  float rr[32];
+  if (rf) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) ld8(rf + j, rr + j);
+  } else if (r) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) ld8(r + j, rr + j);
+  }
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     ld.load(ch, v);
     if (!in_buf) continue;
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < 32; j += 4) {
         const int c = ch * 32 + j;
-        float y = (v[j] + __ldg(ep.bias + c) - mean) * rstd * __ldg(ep.ln_g + c) + __ldg(ep.ln_b + c);
-        if (film) y = y * (film[c] + 1.0f) + film[C + c];
-        v[j] = fmaxf(y, 0.f);
+        const float4 b4 = *reinterpret_cast<const float4*>(cx.bias + c);
+        const float4 g4 = *reinterpret_cast<const float4*>(pg_ + c);
+        const float4 e4 = *reinterpret_cast<const float4*>(pb_ + c);
+        float y0 = fmaf((v[j] + b4.x - mean) * rstd, g4.x, e4.x), y1 = fmaf((v[j + 1] + b4.y - mean) * rstd, g4.y, e4.y);
+        float y2 = fmaf((v[j + 2] + b4.z - mean) * rstd, g4.z, e4.z), y3 = fmaf((v[j + 3] + b4.w - mean) * rstd, g4.w, e4.w);
+        if (film) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(film + c)), sh = __ldg(reinterpret_cast<const float4*>(film + C + c));
+          y0 = fmaf(y0, sc.x + 1.0f, sh.x); y1 = fmaf(y1, sc.y + 1.0f, sh.y);
+          y2 = fmaf(y2, sc.z + 1.0f, sh.z); y3 = fmaf(y3, sc.w + 1.0f, sh.w);
+        }
+        v[j] = fmaxf(y0, 0.f); v[j + 1] = fmaxf(y1, 0.f); v[j + 2] = fmaxf(y2, 0.f); v[j + 3] = fmaxf(y3, 0.f);
       }
-      if (r) {
+      if (rf || r) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) { float t[8]; ld8(r + ch * 32 + j, t);
+        for (int j = 0; j < 32; ++j) v[j] += rr[j];
+        if (ch < 3) {
+          if (rf) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
-      }
-      if (rf) {
+            for (int j = 0; j < 32; j += 8) ld8(rf + (ch + 1) * 32 + j, rr + j);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) { float t[8]; ld8(rf + ch * 32 + j, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
+            for (int j = 0; j < 32; j += 8) ld8(r + (ch + 1) * 32 + j, rr + j);
+          }
+        }
       }
       if (ep.head_w) {
 #pragma unroll
@@ -235,9 +280,9 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
 }
 
 template <int KIND, typename T, class Loader>
-__device__ __forceinline__ void run_epilogue(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+__device__ __forceinline__ void run_epilogue(const EpiParams& ep, const EpiCtx& cx, long long row, bool ok, int n0, Loader& ld) {
   if constexpr (KIND == EPI_STORE) epi_store<T>(ep, row, ok, n0, ld);
-  else if constexpr (KIND == EPI_CONV_LN) epi_conv_ln<T>(ep, row, ok, n0, ld);
+  else if constexpr (KIND == EPI_CONV_LN) epi_conv_ln<T>(ep, cx, row, ok, n0, ld);
   else if constexpr (KIND == EPI_ATTN_OUT) epi_attn_out<T>(ep, row, ok, n0, ld);
   else epi_convt<T>(ep, row, ok, n0, ld);
 }

@@ -6,6 +6,7 @@
 // streamed by TMA into a 128B-swizzled multi-stage ring, fp32 accumulators double-buffered in TMEM, row-wise
 // fused epilogues (vg_epilogue.cuh).  fp32 mode: SIMT FFMA kernel + the same epilogues run row-wise.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vg_epilogue.cuh"
 #include "vg_host.h"
@@ -22,10 +23,14 @@ struct GemmShape {
   int b_rows_per_batch;     // B row offset per batch (per-field weights)
 };
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
-constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;          // 32 KiB
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 2 * BN;                             // double-buffered accumulator
+constexpr int BM = 256, BN = 128, BK = 64, STAGES = 4;        // tile = 256 rows (two M=128 MMAs sharing one B stage) x 128 cols
+constexpr int A_BYTES = BM * BK * 2;                          // 32 KiB: rows 0..127 then rows 128..255, 128 B per row
+constexpr int B_BYTES = BN * BK * 2;                          // 16 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                // 48 KiB
+constexpr int PARAM_FLOATS = 3 * 128 + 2 * 2 * 256;           // conv epilogue: bias | ln_g | ln_b | per-WG folded FiLM affine [2 fields][256]
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_FLOATS * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;                                // 2 tiles in flight x 2 row halves x 128 fp32 columns
+constexpr int TC_THREADS = 384;                               // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue WGs
 
 struct TmemLoader {
   uint32_t taddr;
@@ -36,14 +41,16 @@ struct TmemLoader {
 };
 
 // TF32 = 0: bf16 operands (64 per 128-byte K block, UMMA K = 16); TF32 = 1: fp32 operands read as tf32 (32 per K
-// block, UMMA K = 8).  The smem tiles are [128 rows][128 bytes] either way, so the pipeline is identical.
+// block, UMMA K = 8).  The smem tiles are [rows][128 bytes] either way, so the pipeline is identical.
+// Epilogue warpgroup e (warps 4+4e .. 7+4e) owns rows [128e, 128e+128) of every tile.
 template <int KIND, int TF32>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmShape gs, const EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* sparam = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PARAM_FLOATS * 4);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -55,10 +62,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (KIND == EPI_CONV_LN) {
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
+      sparam[i] = ep.bias[i]; sparam[128 + i] = ep.ln_g[i]; sparam[256 + i] = ep.ln_b[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -80,52 +92,223 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(empty + stage, phase ^ 1);
           mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(sa, &mapA, full + stage, cb * BKE, (int)(row0 + gs.tap_shift[tap]));
-          tma_load_2d(sa + BM * BK * 2, &mapB, full + stage, kb * BKE, brow0);
+          tma_load_2d(sa, &mapA, full + stage, cb * BKE, (int)(row0 + gs.tap_shift[tap]));      // 256-row box
+          tma_load_2d(sa + A_BYTES, &mapB, full + stage, kb * BKE, brow0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                         // ===== MMA issuer =====
-      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(tempty + as, aphase ^ 1);                  // epilogue has drained this accumulator
+        mbar_wait(tempty + as, aphase ^ 1);                  // both epilogue warpgroups have drained this buffer
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d0 = tmem_base + as * 256, d1 = d0 + 128;
         for (int kb = 0; kb < gs.k_blocks; ++kb) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + BM * BK * 2);
+          const uint64_t da0 = umma_desc_k128(sa), da1 = umma_desc_k128(sa + A_BYTES / 2), db = umma_desc_k128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                      // 4 x 32 B per K block, +32 B inside the swizzle atom
-            if (TF32) tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            const uint32_t acc = (kb | k) ? 1u : 0u;
+            if (TF32) { tc_mma_tf32(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_tf32(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
+            else { tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
           }
           tc_commit(empty + stage);                          // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull + as);                               // accumulator complete -> epilogue
+        tc_commit(tfull + as);                               // accumulators complete -> epilogue
       }
     }
-  } else if (warp >= 4) {                                    // ===== epilogue: 128 threads, one row each =====
+  } else if (warp >= 4) {                                    // ===== epilogue: 2 x 128 threads, one row each =====
     const int lg = warp & 3;                                 // TMEM lane group this warp may access
+    const int e = (warp - 4) >> 2;                           // row half of the tile
+    EpiCtx cx;
+    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    float* sgb = sparam + 384 + e * 512;                     // this warpgroup's staging buffer
+    const int wt = (warp & 3) * 32 + lane;                   // thread index inside the warpgroup
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m_tile = t / gs.num_n_tiles, n_tile = t - m_tile * gs.num_n_tiles;
       const int batch = m_tile / gs.tiles_per_batch, mt = m_tile - batch * gs.tiles_per_batch;
-      const long long lrow = (long long)mt * BM + lg * 32 + lane;
+      const long long lrow = (long long)mt * BM + e * 128 + lg * 32 + lane;
       const long long row = (long long)batch * gs.rows_per_batch + lrow;
       const bool ok = lrow < gs.rows_per_batch && row < gs.M;
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      if (KIND == EPI_CONV_LN) {
+        if (TF32) epi_conv_ln_prefetch<float>(ep, row, ok); else epi_conv_ln_prefetch<bf16>(ep, row, ok);
+        if (ep.film) {
+          // fold FiLM of the (at most two) fields this warpgroup's 128 rows touch into the LayerNorm affine
+          const long long r0 = (long long)batch * gs.rows_per_batch + (long long)mt * BM + e * 128;
+          int nf = (int)((r0 / ep.pg.P) / ep.pg.R);
+          if (nf > ep.pg.N - 1) nf = ep.pg.N - 1;
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + e) : "memory");          // previous tile's readers are done
+          for (int i = wt; i < 256; i += 128) {
+            const int f = i >> 7, c = i & 127;
+            const int n2 = (nf + f < ep.pg.N) ? nf + f : nf;
+            const float sc = ep.film[(long long)n2 * 256 + c] + 1.0f, sh = ep.film[(long long)n2 * 256 + 128 + c];
+            sgb[f * 256 + c] = sparam[128 + c] * sc;
+            sgb[f * 256 + 128 + c] = fmaf(sparam[256 + c], sc, sh);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + e) : "memory");
+          cx.gb = sgb; cx.n_first = nf;
+        }
+      }
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
-      TmemLoader ld{tmem_base + as * BN + ((uint32_t)(lg * 32) << 16)};
-      if (TF32) run_epilogue<KIND, float>(ep, row, ok, n_tile * BN, ld);
-      else run_epilogue<KIND, bf16>(ep, row, ok, n_tile * BN, ld);
+      TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
+      if (TF32) run_epilogue<KIND, float>(ep, cx, row, ok, n_tile * BN, ld);
+      else run_epilogue<KIND, bf16>(ep, cx, row, ok, n_tile * BN, ld);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolution with halo reuse (bf16, Cin = Cout = 128, PG layout).
+//
+// The generic kernel above re-reads the A operand from L2 once per tap (9x).  Here a tile of 256 output pixels loads
+// its input rows ONCE, with the halo of P+1 rows on each side, as two [HR rows x 128 B] channel-block tiles
+// (SWIZZLE_128B, written by TMA); tap (dy,dx) is then the same smem tile addressed through a UMMA descriptor whose
+// start address is shifted by (P+1 + dy*P + dx) rows (128 B each; the descriptor's base-offset field carries the
+// swizzle phase of the shifted start).  Only the weights (16 KiB per tap and channel block) stream through a ring.
+// K order: channel block 0 taps 0..8, then channel block 1 taps 0..8, so each A half-buffer is reloaded for the next
+// tile while the other half is being consumed.  L2->SM traffic per 256-pixel tile: 100 KiB (A) + 288 KiB (B)
+// instead of 576 + 288 KiB.
+// ------------------------------------------------------------------------------------------------
+constexpr int HALO_MAX_ROWS = 416;                            // HR <= 416 (two TMA boxes of <= 208 rows)
+constexpr int HB_STAGES = 5;                                  // weight ring
+constexpr int HALO_A_BYTES = HALO_MAX_ROWS * 128;             // per channel block
+constexpr int HALO_SMEM_BYTES = 2 * HALO_A_BYTES + HB_STAGES * B_BYTES + PARAM_FLOATS * 4 + 1024 + 256;
+static int g_halo_base_offset = 0;   // measured on B200: the 128B swizzle is applied to absolute smem address bits, so a
+                                     // row-shifted start into a 1024-B-aligned tile needs base_offset = 0 (1 gives wrong results)
+
+struct HaloShape {
+  long long M;          // flat pixels (rows of the [q][128] matrices)
+  int num_tiles;        // 256-pixel tiles
+  int P;                // row pitch (pixels)
+  int HR;               // halo rows loaded per tile (multiple of 16)
+  int use_base_offset;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int row) {
+  const uint32_t a = tile_addr + (uint32_t)row * 128u;
+  return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const HaloShape hs, const EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem + 2 * HALO_A_BYTES;
+  float* sparam = reinterpret_cast<float*>(sB + HB_STAGES * B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + HB_STAGES * B_BYTES + PARAM_FLOATS * 4);
+  uint64_t* empty = full + HB_STAGES;
+  uint64_t* a_full = empty + HB_STAGES;    // [2]
+  uint64_t* a_free = a_full + 2;           // [2]
+  uint64_t* tfull = a_free + 2;            // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < HB_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_free + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
+    sparam[i] = ep.bias[i]; sparam[128 + i] = ep.ln_g[i]; sparam[256 + i] = ep.ln_b[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int halo = hs.P + 1;                                 // rows in front of the tile's first output pixel
+
+  if (warp == 0) {
+    if (lane == 0) {                                         // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      const int half_rows = hs.HR / 2;
+      for (int t = blockIdx.x; t < hs.num_tiles; t += gridDim.x, ++it) {
+        const long long q0 = (long long)t * BM;
+        for (int cb = 0; cb < 2; ++cb) {
+          mbar_wait(a_free + cb, (it & 1) ^ 1);              // previous tile's taps on this half have retired
+          mbar_arrive_expect_tx(a_full + cb, hs.HR * 128);
+          uint8_t* sa = smem + cb * HALO_A_BYTES;
+          tma_load_2d(sa, &mapA, a_full + cb, cb * 64, (int)(q0 - halo));
+          tma_load_2d(sa + half_rows * 128, &mapA, a_full + cb, cb * 64, (int)(q0 - halo + half_rows));
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty + stage, phase ^ 1);
+            mbar_arrive_expect_tx(full + stage, B_BYTES);
+            tma_load_2d(sB + stage * B_BYTES, &mapB, full + stage, tap * 128 + cb * 64, 0);
+            if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                         // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      for (int t = blockIdx.x; t < hs.num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty + as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + as * 256, d1 = d0 + 128;
+        for (int cb = 0; cb < 2; ++cb) {
+          mbar_wait(a_full + cb, it & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + cb * HALO_A_BYTES);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r0 = halo + (tap / 3 - 1) * hs.P + (tap % 3 - 1);       // first input row of this tap
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            uint64_t da0 = umma_desc_k128_shift(sa, r0), da1 = umma_desc_k128_shift(sa, r0 + 128);
+            if (hs.use_base_offset) { da0 |= (uint64_t)(r0 & 7) << 49; da1 |= (uint64_t)((r0 + 128) & 7) << 49; }
+            const uint64_t db = umma_desc_k128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (cb | tap | k) ? 1u : 0u;
+              tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc);
+              tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc);
+            }
+            tc_commit(empty + stage);
+            if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(a_free + cb);
+        }
+        tc_commit(tfull + as);
+      }
+    }
+  } else if (warp >= 4) {                                    // ===== epilogue: 2 x 128 threads, one pixel row each =====
+    const int lg = warp & 3;
+    const int e = (warp - 4) >> 2;
+    EpiCtx cx;
+    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < hs.num_tiles; t += gridDim.x, ++it) {
+      const long long row = (long long)t * BM + e * 128 + lg * 32 + lane;
+      const bool ok = row < hs.M;
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      epi_conv_ln_prefetch<bf16>(ep, row, ok);
+      mbar_wait(tfull + as, aphase);
+      tc_fence_after();
+      TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
+      run_epilogue<EPI_CONV_LN, bf16>(ep, cx, row, ok, 0, ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
@@ -203,7 +386,9 @@ epilogue_rows_kernel(const float* __restrict__ scratch, int Ntot, const GemmShap
   const int n0 = blockIdx.y * BN;
   const bool ok = row < gs.M;
   ScratchLoader ld{ok ? scratch + row * Ntot + n0 : nullptr, Ntot - n0};
-  run_epilogue<KIND, float>(ep, row, ok, n0, ld);
+  EpiCtx cx;
+  cx.bias = ep.bias; cx.ln_g = ep.ln_g; cx.ln_b = ep.ln_b; cx.gb = nullptr; cx.n_first = 0;
+  run_epilogue<KIND, float>(ep, cx, row, ok, n0, ld);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +446,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmSha
   }
   const int total = gs.num_m_tiles * gs.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<KIND, TF32><<<grid, 256, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
+  gemm_tc_kernel<KIND, TF32><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -270,6 +455,43 @@ static int launch_simt_epi(const float* scratch, int Ntot, const GemmShape& gs, 
   dim3 grid((unsigned)((gs.M + 127) / 128), (unsigned)((Ntot + BN - 1) / BN));
   epilogue_rows_kernel<KIND><<<grid, 128, 0, st>>>(scratch, Ntot, gs, ep);
   return check_launch("epilogue_rows_kernel");
+}
+
+// bf16 3x3 conv (Cin = Cout = 128) over a PG buffer with halo reuse; returns -1 when the shape does not fit
+int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, cudaStream_t st) {
+  const int P = pg.P;
+  const int HR = ((BM + 2 * (P + 1)) + 15) / 16 * 16;
+  if (HR > HALO_MAX_ROWS) return -1;
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("VG_CONV_HALO"); mode = (e && e[0] == '0') ? 0 : 1;
+                  const char* b = getenv("VG_HALO_BASEOFF"); if (b) g_halo_base_offset = (b[0] != '0'); }
+  if (!mode) return -1;
+  CUtensorMap ma, mb;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  {
+    cuuint64_t dims[2] = {128, (cuuint64_t)pg.pixels()};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64u, (cuuint32_t)(HR / 2)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("conv_halo: A tensor map failed (%d)", (int)r);
+  }
+  int rc = make_map_2d(&mb, false, Wt, 9 * 128, 128, BN);
+  if (rc) return rc;
+  HaloShape hs;
+  hs.M = pg.pixels(); hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = hs.num_tiles < num_sms() ? hs.num_tiles : num_sms();
+  conv_halo_kernel<<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
+  return check_launch("conv_halo_kernel");
 }
 
 // The one host entry used by the C ABI (vg_api.cu).  dtype: 0 = bf16 (tcgen05), 1 = fp32 (SIMT FFMA),
@@ -298,7 +520,7 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
 
   if (dtype == 0 || dtype == 2) {
     CUtensorMap ma, mb;
-    int rc = make_map_2d(&ma, dtype == 2, A, Ca, rowsA, BM);
+    int rc = make_map_2d(&ma, dtype == 2, A, Ca, rowsA, BM);       // one 256-row box per K block
     if (rc) return rc;
     rc = make_map_2d(&mb, dtype == 2, B, Ktot, (long long)Ntot * (batched ? nbatch : 1), BN);
     if (rc) return rc;

@@ -14,6 +14,7 @@ int set_error(const char* fmt, ...);
 // cudaGetLastError() after a launch; 0 when clean
 int check_launch(const char* what);
 
+int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, cudaStream_t st);
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st);
