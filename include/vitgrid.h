@@ -73,12 +73,14 @@ VG_API int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu,
  * (maxvit.py:88-90, 95-96), nn.Linear to_qkv (maxvit.py:139) and the raw 3x3 stem conv (ntaps=9).
  * A: [rowsA][Ca]; Wt: [Ntot*(batches)][ntaps*Ca]; tap_shift: HOST int[ntaps]; act: 0 none, 1 GELU, 2 ReLU.
  * rows_per_batch>0 selects per-batch weights (Wt rows advance by b_rows_per_batch every rows_per_batch rows).
- * out_f32: 0 = output in the activation dtype, 1 = fp32, 2 = bf16.  scratch (fp32, M*Ntot) is used by fp32 mode only. */
+ * out_f32: 0 = output in the activation dtype, 1 = fp32, 2 = bf16.  res_f32 = 1: the residual is fp32 whatever dtype is.
+ * scratch (fp32, M*Ntot) is used by fp32 mode only.  The backward pass uses the same entry point for every dgrad
+ * (3x3: negated tap shifts and [Cin][tap][Cout] weights). */
 VG_API int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* Wt, int Ntot, int ntaps,
                 const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
                 const float* bias, const float* scale, const float* shift, int act, const void* res,
-                long long ldres, void* out, long long ldo, int out_f32, float* scratch, long long scratch_elems,
-                void* stream);
+                long long ldres, int res_f32, void* out, long long ldo, int out_f32, float* scratch,
+                long long scratch_elems, void* stream);
 
 /* metnet3.py:110-126 Block = Conv2d 3x3 (pad 1) -> ChanLayerNorm (var.clamp(eps).rsqrt) -> optional FiLM
  * x*(scale+1)+shift -> ReLU, plus the ResnetBlock residual add (:162) when res != NULL.  x,out,res: PG
@@ -165,6 +167,121 @@ VG_API int vg_focal_r_fwd(const float* pred, const float* target, long long n, f
                    float* partial, int nblocks, float* loss, void* stream);
 VG_API int vg_focal_r_bwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse,
                    float gscale, float* grad, void* stream);
+
+/* ================================================================================================================
+ * Training step.  The reference has no hand-written backward: it is autograd over metnet3.py:86-430 and
+ * maxvit.py:33-341 in train() mode (batch-statistic BatchNorm).  Gradients travel as fp32 tensors; dgrad GEMMs go
+ * through vg_gemm_fwd; every dW below is ACCUMULATED (the caller zeroes the gradient buffer once per step).
+ * ================================================================================================================ */
+
+/* vg_conv3x3_ln_fwd that also saves what backward needs: xhat = normalised conv output (activation dtype, PG, zeros
+ * at pads), rstd (fp32 [q]), relu_mask (4 x 32 bits per pixel: bit c%32 of word c/32 set where the ReLU input > 0). */
+VG_API int vg_conv3x3_ln_train_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
+                            const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                            float* out_f32_copy, void* xhat, float* rstd, void* relu_mask, int N, int HP, int WP,
+                            float* scratch, long long scratch_elems, void* stream);
+/* vg_stem_finish_fwd with the same three saved tensors (per field) */
+VG_API int vg_stem_finish_train_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                             const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                             const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* xhat, float* rstd,
+                             void* relu_mask, void* stream);
+
+/* Block backward (metnet3.py:110-126): dY fp32 PG -> dconv (odtype: 0 bf16, 1 fp32; zeros at pads) and per-field sums
+ * sumA += dZ*xhat, sumB += dZ, sumD += dconv ((N,128) fp32, zeroed by the caller); border (or NULL): (N,8,128) sums of
+ * dconv over first/last row, first/last column and the four corners (time-channel gradients of the stem). */
+VG_API int vg_conv_ln_bwd(int xdtype, int odtype, const float* dY, const void* xhat, const float* rstd, const void* relu_mask,
+                   const float* ln_g, const float* film, float ln_eps, void* dconv, float* sumA, float* sumB, float* sumD,
+                   float* border, int N, int HP, int WP, void* stream);
+/* dg, db (ChanLayerNorm), dbias (conv) accumulated from the per-field sums; dfilm (N,256) written (or NULL) */
+VG_API int vg_conv_ln_param_grads(const float* sumA, const float* sumB, const float* sumD, int N, const float* ln_g,
+                           const float* ln_b, const float* film, float* dg, float* db, float* dbias, float* dfilm,
+                           void* stream);
+
+/* Weight gradient of a shifted-row GEMM / 3x3 conv / linear layer:
+ *   dW[n][tap*Ca + c] = beta*dW + sum_m dY[m][n] * A[m + tap_shift[tap]][c],   dW fp32 [Ntot][ntaps*Ca]
+ * dtype 0: bf16 operands (tcgen05, MN-major operands straight from the row-major activations), 1: fp32 SIMT,
+ * 2: fp32 operands as tf32 (tcgen05).  work: fp32 workspace of vg_wgrad_workspace() floats (split-K partials). */
+VG_API long long vg_wgrad_workspace(int dtype, long long M, int Ntot, int Ca, int ntaps);
+VG_API int vg_wgrad(int dtype, const void* dY, const void* A, long long rowsA, long long M, int Ntot, int Ca, int ntaps,
+             const int* tap_shift, float* dW, float beta, float* work, long long work_elems, void* stream);
+
+/* metnet3.py:424-430 backward: dH fp32 PG (every position written), dw[C] and db[1] accumulated */
+VG_API int vg_head_bwd(int dtype, const float* dpred, const void* h, const float* w, float pm_std, int N, int HP, int WP, int H,
+                int W, int pad_top, int pad_left, float* dH, float* dw, float* db, void* stream);
+/* MaxPool2d(2,2) backward: gradient to the first maximum of each window; dx fp32 PG, every position written */
+VG_API int vg_pool2_bwd(int dtype, const void* x, const float* dlow, float* dx, int N, int HP, int WP, int C, void* stream);
+/* ConvTranspose2d(k2,s2) backward gather: dUp fp32 PG (N,2Hl,2Wl,C) -> G [N*Hl*Wl][4C] (odtype 0 bf16 / 1 fp32),
+ * dbias[C] accumulated; dgrad / wgrad are then plain GEMMs on G */
+VG_API int vg_convT2_bwd_gather(int odtype, const float* dUp, void* G, float* dbias, int N, int Hl, int Wl, int C, void* stream);
+/* transpose of the lead-time replication (metnet3.py:383): out[b] = sum_l in[b*L+l], PG over B frames */
+VG_API int vg_lead_sum(int idtype, int odtype, const void* in, void* out, int B, int L, int HP, int WP, void* stream);
+/* out[n][c] += sum over the frame pixels of an fp32 PG tensor (C = 128) */
+VG_API int vg_pg_field_sum(const float* in, float* out, int N, int HP, int WP, void* stream);
+/* transpose of vg_time_terms_fwd: time-channel slices of the stem conv / res_conv weight gradients (accumulated into
+ * the ORIGINAL-layout gradients dw3 (Cout,c_in,3,3), dw1 (Cout,c_in,1,1)), db1 (Cout) and dtemb (N, le+3te) written */
+VG_API int vg_time_terms_bwd(const float* border, const float* sumD, const float* tres_sum, const float* temb, const float* w3,
+                      const float* w1, int N, int ntc, int c_in, int c_data, int Cout, float* dw3, float* dw1, float* db1,
+                      float* dtemb, void* stream);
+/* embedding gradients (accumulated): lead-time rows get dtemb[:, :le] + dcond, model-time rows follow the dim-0
+ * concat quirk of metnet3.py:395-401 */
+VG_API int vg_time_embed_bwd(const float* dtemb, const float* dcond, const float* ts, long long ts_sB, long long ts_sT,
+                      long long ts_sF, int B, int L, int le, int te, float* d_lead, float* d_month, float* d_day,
+                      float* d_hour, void* stream);
+/* backward of vg_cond_mlp_fwd; dW*, db*, dcond (N,cond_dim) accumulated; work: N*(cond_dim + 2*hid) floats */
+VG_API int vg_cond_mlp_bwd(const float* cond, int N, int cond_dim, int pre_relu, const float* W0, const float* b0, int hid,
+                    const float* W1, int od, const float* dout, float* dW0, float* db0, float* dW1, float* db1,
+                    float* dcond, float* work, long long work_elems, void* stream);
+/* fused AdamW over a flat fp32 parameter buffer; gscale multiplies the gradient (1/world_size after a sum all-reduce) */
+VG_API int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float gscale, void* stream);
+
+/* BatchNorm2d in train() mode (maxvit.py:89,92,96) on a channels-last fp32 matrix [M][C]:
+ * batch mean / rstd, folded affine (scale, shift), momentum update of the running buffers (NULL = no update).
+ * work: vg_bn_workspace() floats. */
+VG_API long long vg_bn_workspace(long long M, int C);
+VG_API int vg_bn_stats(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift,
+                float* work, long long work_elems, void* stream);
+/* out = act(raw*scale + shift) (+ res); act 0 none, 1 GELU(erf) */
+VG_API int vg_bn_act(const float* raw, const float* scale, const float* shift, int act, const float* res, float* out,
+              long long M, int C, void* stream);
+/* BatchNorm (+ activation) backward; the upstream gradient is dOut*fgate[n] + fadd[n] (per-field vectors (N,C) or NULL,
+ * n = row / rows_per_field: the squeeze-excite scale and mean paths).  dgamma, dbeta accumulated, draw [M][C] written.
+ * work: vg_bn_workspace() + 2*C floats */
+VG_API int vg_bn_bwd(const float* dOut, const float* raw, const float* scale, const float* shift, const float* mean,
+              const float* rstd, const float* gamma, int act, const float* fgate, const float* fadd,
+              long long rows_per_field, long long M, int C, float* dgamma, float* dbeta, float* draw, float* work,
+              long long work_elems, void* stream);
+/* out[c] += sum_m x[m][c] (bias gradients) */
+VG_API int vg_colsum(const float* x, long long M, int C, float* out, void* stream);
+/* depthwise 3x3 (marching stencil): out = act(conv(in, w9)*scale + shift); psum (or NULL): (N, vg_dw_strips(W), C)
+ * partial channel sums of the outputs.  Training forward: scale = 1, shift = bias, act = 0; dgrad: flipped taps. */
+VG_API int vg_dw_strips(int W);
+VG_API int vg_dw3x3_fwd(int dtype, const void* in, const float* w9, const float* scale, const float* shift, int act, void* out,
+                 float* psum, int N, int H, int W, int C, void* stream);
+/* depthwise weight / bias gradient (accumulated): dw9 [9][C], dbias [C]; work: (N*strips + 1)*10*C floats */
+VG_API int vg_dw3x3_wgrad(const float* x, const float* dY, int N, int H, int W, int C, float* dw9, float* dbias, float* work,
+                   long long work_elems, void* stream);
+/* squeeze-excite (maxvit.py:33-48) with saved intermediates, out-of-place scale, and backward (dW1, dW2 accumulated,
+ * dmean (N,C) already divided by HW); work: N*(2C+se) floats */
+VG_API int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C,
+                         int se, float* gate, float* mean, float* hid, void* stream);
+VG_API int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream);
+VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
+              const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
+              long long work_elems, void* stream);
+/* attention backward (fp32): gradient at the out-projection output (inverse of the scatter + register rows) */
+VG_API int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
+                           int R, int grid_mode, float* dproj, void* stream);
+/* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated */
+VG_API int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
+                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, void* stream);
+/* LayerNorm + FiLM backward with the inverse partition; dx_in written (= dx + dx_out), dreg_in and dfilm accumulated */
+VG_API int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
+                       const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in,
+                       float* dfilm, int N, int Hl, int Wl, int C, int win, int R, int grid_mode, float ln_eps,
+                       void* stream);
 
 #ifdef __cplusplus
 }

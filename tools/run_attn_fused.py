@@ -23,3 +23,16 @@ for _ in range(iters):
     e1.record()
     torch.cuda.synchronize()
     print(f"N={N} windows={N*30} ms={e0.elapsed_time(e1):.3f}")
+
+# per-phase clock stamps of one compute thread (CTA 0, first tile)
+dbg = torch.zeros(heads * 8, dtype=torch.int64, device="cuda")
+os.environ["VG_ATTN_DBG"] = hex(dbg.data_ptr())
+ops.attn_fused(x, reg, film, wqkv, wout, tab, w, R, False, True, heads, dh)
+torch.cuda.synchronize()
+d = dbg.cpu().view(heads, 8)
+names = ["table+bar", "wait qkv_done", "step2 (norm, stores)", "wait s_done", "step4 (softmax)", "wait o_done(+pair)", "step6"]
+delta = (d[:, 1:] - d[:, :-1]).float()
+print("head period (cycles):", (d[1:, 0] - d[:-1, 0]).float()[2:].mean().item())
+for i, nm in enumerate(names):
+    print(f"  {nm:24s} {delta[2:, i].mean().item():8.0f}")
+print("  next-head gap           ", (d[1:, 0] - d[:-1, 7]).float()[2:].mean().item())

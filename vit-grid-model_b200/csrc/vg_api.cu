@@ -85,11 +85,12 @@ int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu, const 
 
 int vg_gemm_fwd(int dtype, const void* A, long long rowsA, int Ca, const void* Wt, int Ntot, int ntaps,
                 const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch, const float* bias,
-                const float* scale, const float* shift, int act, const void* res, long long ldres, void* out,
-                long long ldo, int out_f32, float* scratch, long long scratch_elems, void* stream) {
+                const float* scale, const float* shift, int act, const void* res, long long ldres, int res_f32,
+                void* out, long long ldo, int out_f32, float* scratch, long long scratch_elems, void* stream) {
   EpiParams ep = epi_zero();
   ep.out = out; ep.ldo = ldo; ep.out_f32 = out_f32; ep.n_total = Ntot;
   ep.bias = bias; ep.col_scale = scale; ep.col_shift = shift; ep.act = act; ep.res = res; ep.ldres = ldres;
+  ep.res_f32 = res_f32;
   if ((scale == nullptr) != (shift == nullptr)) return set_error("gemm: scale and shift must be given together");
   return gemm_run(dtype, EPI_STORE, A, rowsA, Ca, Wt, Ntot, ntaps, tap_shift, M, rows_per_batch, b_rows_per_batch, ep,
                   scratch, scratch_elems, (cudaStream_t)stream);
@@ -109,7 +110,7 @@ int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const fl
   if (!out && !head_w) return set_error("conv3x3_ln: no output requested");
   if (head_w && !head_out) return set_error("conv3x3_ln: head_w without head_out");
   if (dtype == 0 && Ca == 128) {                     // halo-reuse kernel (falls through when the row pitch is too large)
-    const int rc = conv_halo_run(x, Wt, pg, ep, (cudaStream_t)stream);
+    const int rc = conv_halo_run(x, Wt, pg, ep, 0, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
   int shifts[9];
@@ -119,12 +120,47 @@ int vg_conv3x3_ln_fwd(int dtype, const void* x, int Ca, const void* Wt, const fl
                   scratch_elems, (cudaStream_t)stream);
 }
 
+int vg_conv3x3_ln_train_fwd(int dtype, const void* x, int Ca, const void* Wt, const float* bias, const float* ln_g,
+                            const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                            float* out_f32_copy, void* xhat, float* rstd, void* relu_mask, int N, int HP, int WP,
+                            float* scratch, long long scratch_elems, void* stream) {
+  PGeom pg = make_pgeom(N, HP, WP);
+  EpiParams ep = epi_zero();
+  ep.out = out; ep.ldo = 128; ep.n_total = 128; ep.bias = bias; ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_eps = ln_eps;
+  ep.film = film; ep.res = res; ep.ldres = 128; ep.pg = pg; ep.res_f32 = res_f32; ep.out2 = out_f32_copy;
+  ep.xhat = xhat; ep.rstd_out = rstd; ep.relu_mask = reinterpret_cast<unsigned*>(relu_mask);
+  if (!out || !xhat || !rstd || !relu_mask) return set_error("conv3x3_ln_train: out, xhat, rstd and relu_mask are required");
+  if (dtype == 0 && Ca == 128) {
+    const int rc = conv_halo_run(x, Wt, pg, ep, 1, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
+  int shifts[9];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) shifts[ky * 3 + kx] = (ky - 1) * pg.P + (kx - 1);
+  return gemm_run(dtype, EPI_CONV_LN_TRAIN, x, pg.pixels(), Ca, Wt, 128, 9, shifts, pg.pixels(), 0, 0, ep, scratch,
+                  scratch_elems, (cudaStream_t)stream);
+}
+
 int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
                        const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
                        const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* stream) {
   StemParams p;
   p.raw3 = raw3; p.rawres = rawres; p.bias3 = bias3; p.bias1 = bias1; p.tt = tt; p.tres = tres;
   p.ln_g = ln_g; p.ln_b = ln_b; p.eps = ln_eps; p.film = film; p.L = L;
+  p.xhat = nullptr; p.rstd = nullptr; p.mask = nullptr;
+  p.pgB = make_pgeom(B, HP, WP); p.pgN = make_pgeom(B * L, HP, WP);
+  return stem_finish_run(dtype, p, h1, res, (cudaStream_t)stream);
+}
+
+int vg_stem_finish_train_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                             const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                             const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* xhat, float* rstd,
+                             void* relu_mask, void* stream) {
+  StemParams p;
+  p.raw3 = raw3; p.rawres = rawres; p.bias3 = bias3; p.bias1 = bias1; p.tt = tt; p.tres = tres;
+  p.ln_g = ln_g; p.ln_b = ln_b; p.eps = ln_eps; p.film = film; p.L = L;
+  p.xhat = xhat; p.rstd = rstd; p.mask = reinterpret_cast<unsigned*>(relu_mask);
+  if (!xhat || !rstd || !relu_mask) return set_error("stem_finish_train: xhat, rstd and relu_mask are required");
   p.pgB = make_pgeom(B, HP, WP); p.pgN = make_pgeom(B * L, HP, WP);
   return stem_finish_run(dtype, p, h1, res, (cudaStream_t)stream);
 }
@@ -220,6 +256,153 @@ int vg_focal_r_fwd(const float* pred, const float* target, long long n, float be
 int vg_focal_r_bwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse, float gscale,
                    float* grad, void* stream) {
   return focal_r_bwd_run(pred, target, n, beta, gamma, mse, gscale, grad, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ training
+int vg_conv_ln_bwd(int xdtype, int odtype, const float* dY, const void* xhat, const float* rstd, const void* relu_mask,
+                   const float* ln_g, const float* film, float ln_eps, void* dconv, float* sumA, float* sumB, float* sumD,
+                   float* border, int N, int HP, int WP, void* stream) {
+  return conv_ln_bwd_run(xdtype, odtype, dY, xhat, rstd, reinterpret_cast<const unsigned*>(relu_mask), ln_g, film, ln_eps,
+                         dconv, sumA, sumB, sumD, border, N, HP, WP, (cudaStream_t)stream);
+}
+
+int vg_conv_ln_param_grads(const float* sumA, const float* sumB, const float* sumD, int N, const float* ln_g,
+                           const float* ln_b, const float* film, float* dg, float* db, float* dbias, float* dfilm,
+                           void* stream) {
+  return conv_ln_param_grads_run(sumA, sumB, sumD, N, ln_g, ln_b, film, dg, db, dbias, dfilm, (cudaStream_t)stream);
+}
+
+long long vg_wgrad_workspace(int dtype, long long M, int Ntot, int Ca, int ntaps) {
+  return wgrad_workspace_elems(dtype, M, Ntot, Ca, ntaps);
+}
+
+int vg_wgrad(int dtype, const void* dY, const void* A, long long rowsA, long long M, int Ntot, int Ca, int ntaps,
+             const int* tap_shift, float* dW, float beta, float* work, long long work_elems, void* stream) {
+  return wgrad_run(dtype, dY, A, rowsA, M, Ntot, Ca, ntaps, tap_shift, dW, beta, work, work_elems, (cudaStream_t)stream);
+}
+
+int vg_head_bwd(int dtype, const float* dpred, const void* h, const float* w, float pm_std, int N, int HP, int WP, int H,
+                int W, int pad_top, int pad_left, float* dH, float* dw, float* db, void* stream) {
+  return head_bwd_run(dtype, dpred, h, w, pm_std, N, HP, WP, H, W, pad_top, pad_left, dH, dw, db, (cudaStream_t)stream);
+}
+
+int vg_pool2_bwd(int dtype, const void* x, const float* dlow, float* dx, int N, int HP, int WP, int C, void* stream) {
+  return maxpool2_bwd_run(dtype, x, dlow, dx, N, HP, WP, C, (cudaStream_t)stream);
+}
+
+int vg_convT2_bwd_gather(int odtype, const float* dUp, void* G, float* dbias, int N, int Hl, int Wl, int C, void* stream) {
+  return convT_bwd_gather_run(odtype, dUp, G, dbias, N, Hl, Wl, C, (cudaStream_t)stream);
+}
+
+int vg_lead_sum(int idtype, int odtype, const void* in, void* out, int B, int L, int HP, int WP, void* stream) {
+  return lead_sum_run(idtype, odtype, in, out, B, L, HP, WP, (cudaStream_t)stream);
+}
+
+int vg_pg_field_sum(const float* in, float* out, int N, int HP, int WP, void* stream) {
+  return pg_field_sum_run(in, out, N, HP, WP, (cudaStream_t)stream);
+}
+
+int vg_time_terms_bwd(const float* border, const float* sumD, const float* tres_sum, const float* temb, const float* w3,
+                      const float* w1, int N, int ntc, int c_in, int c_data, int Cout, float* dw3, float* dw1, float* db1,
+                      float* dtemb, void* stream) {
+  return time_terms_bwd_run(border, sumD, tres_sum, temb, w3, w1, N, ntc, c_in, c_data, Cout, dw3, dw1, db1, dtemb,
+                            (cudaStream_t)stream);
+}
+
+int vg_time_embed_bwd(const float* dtemb, const float* dcond, const float* ts, long long ts_sB, long long ts_sT,
+                      long long ts_sF, int B, int L, int le, int te, float* d_lead, float* d_month, float* d_day,
+                      float* d_hour, void* stream) {
+  return time_embed_bwd_run(dtemb, dcond, ts, ts_sB, ts_sT, ts_sF, B, L, le, te, d_lead, d_month, d_day, d_hour,
+                            (cudaStream_t)stream);
+}
+
+int vg_cond_mlp_bwd(const float* cond, int N, int cond_dim, int pre_relu, const float* W0, const float* b0, int hid,
+                    const float* W1, int od, const float* dout, float* dW0, float* db0, float* dW1, float* db1,
+                    float* dcond, float* work, long long work_elems, void* stream) {
+  return cond_mlp_bwd_run(cond, N, cond_dim, pre_relu, W0, b0, hid, W1, od, dout, dW0, db0, dW1, db1, dcond, work,
+                          work_elems, (cudaStream_t)stream);
+}
+
+int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float gscale, void* stream) {
+  return adamw_run(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, gscale, (cudaStream_t)stream);
+}
+
+long long vg_bn_workspace(long long M, int C) { return bn_workspace_elems(M, C); }
+
+int vg_bn_stats(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift,
+                float* work, long long work_elems, void* stream) {
+  return bn_stats_run(x, M, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, work,
+                      work_elems, (cudaStream_t)stream);
+}
+
+int vg_bn_act(const float* raw, const float* scale, const float* shift, int act, const float* res, float* out,
+              long long M, int C, void* stream) {
+  return bn_act_run(raw, scale, shift, act, res, out, M, C, (cudaStream_t)stream);
+}
+
+int vg_bn_bwd(const float* dOut, const float* raw, const float* scale, const float* shift, const float* mean,
+              const float* rstd, const float* gamma, int act, const float* fgate, const float* fadd,
+              long long rows_per_field, long long M, int C, float* dgamma, float* dbeta, float* draw, float* work,
+              long long work_elems, void* stream) {
+  return bn_bwd_run(dOut, raw, scale, shift, mean, rstd, gamma, act, fgate, fadd, rows_per_field, M, C, dgamma, dbeta, draw,
+                    work, work_elems, (cudaStream_t)stream);
+}
+
+int vg_colsum(const float* x, long long M, int C, float* out, void* stream) { return colsum_run(x, M, C, out, (cudaStream_t)stream); }
+
+int vg_dw_strips(int W) { return dwconv_strips(W); }
+
+int vg_dw3x3_fwd(int dtype, const void* in, const float* w9, const float* scale, const float* shift, int act, void* out,
+                 float* psum, int N, int H, int W, int C, void* stream) {
+  return dwconv_march_run(dtype, in, w9, scale, shift, act, out, psum, N, H, W, C, (cudaStream_t)stream);
+}
+
+int vg_dw3x3_wgrad(const float* x, const float* dY, int N, int H, int W, int C, float* dw9, float* dbias, float* work,
+                   long long work_elems, void* stream) {
+  return dw_wgrad_run(x, dY, N, H, W, C, dw9, dbias, work, work_elems, (cudaStream_t)stream);
+}
+
+int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C,
+                         int se, float* gate, float* mean, float* hid, void* stream) {
+  return se_gate_train_run(psum, N, nparts, HW, W1, W2, C, se, gate, mean, hid, (cudaStream_t)stream);
+}
+
+int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream) {
+  return se_scale_oop_run(x, gate, out, N, HW, C, (cudaStream_t)stream);
+}
+
+int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
+              const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
+              long long work_elems, void* stream) {
+  return se_bwd_run(dh4, h3, gate, mean, hid, W1, W2, N, HW, C, se, dW1, dW2, dmean, work, work_elems, (cudaStream_t)stream);
+}
+
+int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
+                           int R, int grid_mode, float* dproj, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
+  return attn_out_bwd_gather_run(dx_out, dreg, reg_scale, g, dproj, (cudaStream_t)stream);
+}
+
+int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
+                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
+  return attn_core_bwd_run(qkv, datt, q_gamma, k_gamma, bias_table, g, heads, dh, dqkv, dq_gamma, dk_gamma, dbias_table,
+                           (cudaStream_t)stream);
+}
+
+int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
+                       const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in,
+                       float* dfilm, int N, int Hl, int Wl, int C, int win, int R, int grid_mode, float ln_eps,
+                       void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
+  return attn_gather_bwd_run(x, reg, reg_per_field, film, dtok, dx_out, dreg_res, reg_scale, dx_in, dreg_in, dfilm, g, ln_eps,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

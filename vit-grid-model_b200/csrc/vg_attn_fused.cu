@@ -16,6 +16,8 @@
 //
 // Warp roles: warp 0 = TMA (weights), warp 1 = MMA issuer, warps 2..5 = 128 compute threads (thread <-> token row
 // <-> TMEM lane).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
+#include <stdlib.h>
+
 #include "vg_common.cuh"
 #include "vg_host.h"
 
@@ -56,6 +58,7 @@ struct FusedAttnParams {
   int heads;
   float ln_eps;
   long long n_windows;
+  long long* dbg;                      // optional [heads][8] clock64 stamps of CTA 0 / compute thread 0 / first tile
 };
 
 // byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
@@ -301,6 +304,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       if (lane == 0) mbar_arrive(x_ready);
 
       for (int h = 0; h < heads; ++h, ++it) {
+        const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
+        if (dbg) p.dbg[h * 8 + 0] = clock64();
         const uint32_t r = it & 1;
         const uint32_t R1 = s_base + R1_OFF + r * 32768;
         const uint32_t VT = s_base + VT_OFF + r * 8192;
@@ -312,10 +317,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           for (int k = ctid; k < TAB_FLOATS; k += 256) st[k] = __ldg(gt + k);
         }
         compute_bar_sync();
+        if (dbg) p.dbg[h * 8 + 1] = clock64();
         // ---------------- QKV_h: TMEM -> registers, RMSNorm, -> smem operands ----------------
         mbar_wait(qkv_done + r, (it >> 1) & 1);
         if (it >= 2) mbar_wait(out_done + r, ((it - 2) >> 1) & 1);      // R1[r] / VT[r] no longer read by MMAs
         tc_fence_after();
+        if (dbg) p.dbg[h * 8 + 2] = clock64();
         {
           const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
           float v[32], vv[16];
@@ -346,10 +353,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(qk_ready);
+        if (dbg) p.dbg[h * 8 + 3] = clock64();
 
         // ---------------- S half-row: + bias, masked softmax -> P (bf16) ----------------
         mbar_wait(s_done, it & 1);
         tc_fence_after();
+        if (dbg) p.dbg[h * 8 + 4] = clock64();
         {
           float sc[32];
           tmem_ld32(lane_addr + T_S + half * 64 + ch * 32, sc);
@@ -407,12 +416,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
+        if (dbg) p.dbg[h * 8 + 5] = clock64();
         pair_sync(lg);                                                   // partner's partial row sum is visible
         const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
 
         // ---------------- O_h / rowsum -> smem (tf32) ----------------
         mbar_wait(o_done, it & 1);
         tc_fence_after();
+        if (dbg) p.dbg[h * 8 + 6] = clock64();
         {
           float o[16];
           tmem_ld16(lane_addr + T_O + ch * 16, o);
@@ -425,6 +436,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(osm_ready);
+        if (dbg) p.dbg[h * 8 + 7] = clock64();
       }
 
       // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------
@@ -500,6 +512,8 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   p.x = x; p.x_out = x_out; p.reg_in = reg_in; p.reg_per_field = reg_per_field; p.reg_out = reg_out; p.film = film;
   p.head_tab = head_tab; p.g = g; p.heads = heads;
   p.ln_eps = ln_eps; p.n_windows = (long long)g.N * g.nwin();
+  p.dbg = nullptr;
+  if (const char* e = getenv("VG_ATTN_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);

@@ -1,0 +1,783 @@
+// Training kernels of the MaxViT block (maxvit.py:33-102 MBConv with batch-statistic BatchNorm, :170-219 attention):
+// column statistics, BatchNorm apply / backward, depthwise 3x3 (marching stencil, also the inference kernel),
+// squeeze-excite backward, and the attention backward (out-projection gather, per-(field, head) core backward with the
+// relative-position-bias gradient accumulated in shared memory, LayerNorm + FiLM backward with the inverse partition).
+// The dense projections' dgrad / wgrad run on the tcgen05 GEMMs (vg_gemm.cu, vg_wgrad.cu).
+#include "vg_common.cuh"
+#include "vg_host.h"
+
+namespace vg {
+
+static inline unsigned nblk(long long total, int per) { return (unsigned)((total + per - 1) / per); }
+
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752440f));
+  return cdf + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+
+// ================================================================================================
+// column statistics of X fp32 [M][C]: partial (sum, sum of squares) per 256-row block, combined in double.
+// ================================================================================================
+constexpr int STAT_ROWS = 256;
+
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ X, long long M, int C, float* __restrict__ part) {
+  const long long r0 = (long long)blockIdx.x * STAT_ROWS;
+  long long r1 = r0 + STAT_ROWS;
+  if (r1 > M) r1 = M;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f, s2 = 0.f;
+    for (long long r = r0; r < r1; ++r) { const float v = X[r * C + c]; s += v; s2 = fmaf(v, v, s2); }
+    part[((long long)blockIdx.x * 2) * C + c] = s;
+    part[((long long)blockIdx.x * 2 + 1) * C + c] = s2;
+  }
+}
+
+// BatchNorm2d training statistics (maxvit.py:89,92,96): biased variance for normalisation, unbiased for the running
+// estimate, momentum update of the running buffers, and the folded per-channel affine  y = raw*scale + shift.
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, s2 = 0.0;
+  for (int p = 0; p < nparts; ++p) { s += part[((long long)p * 2) * C + c]; s2 += part[((long long)p * 2 + 1) * C + c]; }
+  const double m = s / (double)M;
+  double var = s2 / (double)M - m * m;
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)m; rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc; shift[c] = beta[c] - (float)m * sc;
+  if (run_mean) {
+    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * (float)m;
+    run_var[c] = (1.0f - momentum) * run_var[c] + momentum * (float)unb;
+  }
+}
+
+// out = act(raw*scale + shift) (+ res)     act: 0 none, 1 GELU(erf)
+__global__ void __launch_bounds__(256) bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, int act, const float* __restrict__ res,
+                                                     float* __restrict__ out, long long total4, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c = (int)((i * 4) % C);
+  const float4 v = *reinterpret_cast<const float4*>(raw + i * 4);
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+  float o[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
+  }
+  if (res) { const float4 r = *reinterpret_cast<const float4*>(res + i * 4); o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w; }
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ---- BatchNorm (+activation) backward.  Upstream gradient wrt the activation output:
+//        g = dOut * fgate[n][c] + fadd[n][c]        (squeeze-excite scale / mean paths; both optional, n = row / rows_per_field)
+//      dpre = g * act'(raw*scale+shift);  xhat = (raw-mean)*rstd;  S1 = sum dpre, S2 = sum dpre*xhat
+//      draw = gamma*rstd*(dpre - S1/M - xhat*S2/M);  dgamma += S2;  dbeta += S1
+struct BnBwdParams {
+  const float* dOut; const float* raw;
+  const float* scale; const float* shift; const float* mean; const float* rstd; const float* gamma;
+  const float* fgate; const float* fadd; long long rows_per_field;
+  int act, C;
+  long long M;
+};
+
+__device__ __forceinline__ float bn_dpre(const BnBwdParams& p, long long r, int c, float rawv) {
+  float g = p.dOut[r * p.C + c];
+  if (p.fgate) { const long long n = r / p.rows_per_field; g = g * p.fgate[n * p.C + c] + (p.fadd ? p.fadd[n * p.C + c] : 0.f); }
+  if (p.act == 1) g *= gelu_grad(fmaf(rawv, p.scale[c], p.shift[c]));
+  return g;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p, float* __restrict__ part) {
+  const long long r0 = (long long)blockIdx.x * STAT_ROWS;
+  long long r1 = r0 + STAT_ROWS;
+  if (r1 > p.M) r1 = p.M;
+  for (int c = threadIdx.x; c < p.C; c += 256) {
+    float s1 = 0.f, s2 = 0.f;
+    const float m = p.mean[c], rs = p.rstd[c];
+    for (long long r = r0; r < r1; ++r) {
+      const float rawv = p.raw[r * p.C + c];
+      const float d = bn_dpre(p, r, c, rawv);
+      s1 += d; s2 = fmaf(d, (rawv - m) * rs, s2);
+    }
+    part[((long long)blockIdx.x * 2) * p.C + c] = s1;
+    part[((long long)blockIdx.x * 2 + 1) * p.C + c] = s2;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int p = 0; p < nparts; ++p) { s1 += part[((long long)p * 2) * C + c]; s2 += part[((long long)p * 2 + 1) * C + c]; }
+  dbeta[c] += (float)s1; dgamma[c] += (float)s2;
+  k1[c] = (float)(s1 / (double)M); k2[c] = (float)(s2 / (double)M);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p, const float* __restrict__ k1, const float* __restrict__ k2,
+                                                           float* __restrict__ draw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M * p.C) return;
+  const long long r = i / p.C;
+  const int c = (int)(i - r * p.C);
+  const float rawv = p.raw[i];
+  const float d = bn_dpre(p, r, c, rawv);
+  const float xh = (rawv - p.mean[c]) * p.rstd[c];
+  draw[i] = p.gamma[c] * p.rstd[c] * (d - k1[c] - xh * k2[c]);
+}
+
+// out[j] (+)= sum_p part[p][j]
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int nparts, long long n, float beta, float* __restrict__ out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + j];
+  out[j] = (beta != 0.f ? beta * out[j] : 0.f) + s;
+}
+
+// column sums of X fp32 [M][C] accumulated into out[C] (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, long long M, int C, float* __restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * STAT_ROWS;
+  long long r1 = r0 + STAT_ROWS;
+  if (r1 > M) r1 = M;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += X[r * C + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ================================================================================================
+// depthwise 3x3 (pad 1) on channels-last (N,H,W,C): marching stencil.  One thread owns 4 channels x a strip of SW
+// columns and walks down the rows keeping a 3-row register window, so every input element is loaded once per strip
+// (plus the one-column halo) instead of nine times.   out = act(conv*scale + shift)   (act: 0 none, 1 GELU)
+// psum (optional): (N, strips, C) per-strip channel sums of the outputs (squeeze-excite mean).
+// Used for: inference (folded BN + GELU), training forward (scale = 1, shift = bias), dgrad (flipped taps).
+// ================================================================================================
+constexpr int DW_SW = 5;
+
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Ld4<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128, 4) dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w9,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                           T* __restrict__ out, float* __restrict__ psum, int H, int W, int C, int strips) {
+  const int quads = C / 4;
+  const int spb = 128 / quads > 0 ? 128 / quads : 1;             // strips per block
+  const int quad = threadIdx.x % quads, sub = threadIdx.x / quads;
+  const int sblocks = (strips + spb - 1) / spb;
+  const int n = blockIdx.x / sblocks, strip = (blockIdx.x - n * sblocks) * spb + sub;
+  if (sub >= spb || strip >= strips) return;
+  const int c0 = quad * 4, w0 = strip * DW_SW;
+  float4 wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float4*>(w9 + k * C + c0);
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c0), sh = *reinterpret_cast<const float4*>(shift + c0);
+  const T* base = in + (long long)n * H * W * C + c0;
+  T* obase = out + (long long)n * H * W * C + c0;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r0[DW_SW + 2], r1[DW_SW + 2], r2[DW_SW + 2];
+#pragma unroll
+  for (int j = 0; j < DW_SW + 2; ++j) {
+    const int w = w0 - 1 + j;
+    r0[j] = z;
+    r1[j] = (w >= 0 && w < W) ? Ld4<T>::ld(base + (long long)w * C) : z;
+  }
+  float4 acc_sum = z;
+  for (int h = 0; h < H; ++h) {
+#pragma unroll
+    for (int j = 0; j < DW_SW + 2; ++j) {
+      const int w = w0 - 1 + j;
+      r2[j] = (h + 1 < H && w >= 0 && w < W) ? Ld4<T>::ld(base + ((long long)(h + 1) * W + w) * C) : z;
+    }
+#pragma unroll
+    for (int j = 0; j < DW_SW; ++j) {
+      if (w0 + j < W) {
+        float4 a = z;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 t0 = r0[j + dx], t1 = r1[j + dx], t2 = r2[j + dx];
+          const float4 k0 = wk[dx], k1 = wk[3 + dx], k2 = wk[6 + dx];
+          a.x = fmaf(t0.x, k0.x, a.x); a.y = fmaf(t0.y, k0.y, a.y); a.z = fmaf(t0.z, k0.z, a.z); a.w = fmaf(t0.w, k0.w, a.w);
+          a.x = fmaf(t1.x, k1.x, a.x); a.y = fmaf(t1.y, k1.y, a.y); a.z = fmaf(t1.z, k1.z, a.z); a.w = fmaf(t1.w, k1.w, a.w);
+          a.x = fmaf(t2.x, k2.x, a.x); a.y = fmaf(t2.y, k2.y, a.y); a.z = fmaf(t2.z, k2.z, a.z); a.w = fmaf(t2.w, k2.w, a.w);
+        }
+        a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
+        if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+        Ld4<T>::st(obase + ((long long)h * W + w0 + j) * C, a);
+        acc_sum.x += a.x; acc_sum.y += a.y; acc_sum.z += a.z; acc_sum.w += a.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DW_SW + 2; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+  }
+  if (psum) *reinterpret_cast<float4*>(psum + ((long long)n * strips + strip) * C + c0) = acc_sum;
+}
+
+// depthwise weight gradient: part[(n,strip)][k][c] = sum_{h, w in strip} dY[n,h,w,c] * X[n,h+dy,w+dx,c]  (k = 3*(dy+1)+dx+1),
+// k = 9: sum dY (bias gradient).  fp32 only.
+__global__ void __launch_bounds__(128) dw_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
+                                                       int H, int W, int C, int strips) {
+  const int quads = C / 4;
+  const int spb = 128 / quads > 0 ? 128 / quads : 1;
+  const int quad = threadIdx.x % quads, sub = threadIdx.x / quads;
+  const int sblocks = (strips + spb - 1) / spb;
+  const int n = blockIdx.x / sblocks, strip = (blockIdx.x - n * sblocks) * spb + sub;
+  if (sub >= spb || strip >= strips) return;
+  const int c0 = quad * 4, w0 = strip * DW_SW;
+  const float* xb = X + (long long)n * H * W * C + c0;
+  const float* gb = dY + (long long)n * H * W * C + c0;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = z;
+  for (int h = 0; h < H; ++h) {
+    float4 g[DW_SW];
+#pragma unroll
+    for (int j = 0; j < DW_SW; ++j) {
+      g[j] = (w0 + j < W) ? *reinterpret_cast<const float4*>(gb + ((long long)h * W + w0 + j) * C) : z;
+      acc[9].x += g[j].x; acc[9].y += g[j].y; acc[9].z += g[j].z; acc[9].w += g[j].w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hh = h + dy - 1;
+      if (hh < 0 || hh >= H) continue;
+      float4 x[DW_SW + 2];
+#pragma unroll
+      for (int j = 0; j < DW_SW + 2; ++j) {
+        const int w = w0 - 1 + j;
+        x[j] = (w >= 0 && w < W) ? *reinterpret_cast<const float4*>(xb + ((long long)hh * W + w) * C) : z;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int j = 0; j < DW_SW; ++j) {
+          float4& a = acc[dy * 3 + dx];
+          a.x = fmaf(g[j].x, x[j + dx].x, a.x); a.y = fmaf(g[j].y, x[j + dx].y, a.y);
+          a.z = fmaf(g[j].z, x[j + dx].z, a.z); a.w = fmaf(g[j].w, x[j + dx].w, a.w);
+        }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) *reinterpret_cast<float4*>(part + (((long long)n * strips + strip) * 10 + k) * C + c0) = acc[k];
+}
+
+// ================================================================================================
+// squeeze-excite (maxvit.py:33-48)
+// ================================================================================================
+// gate with the intermediates the backward pass needs (mean (N,C), hid (N,se)); psum: (N, nparts, C) partial sums
+__global__ void __launch_bounds__(256) se_gate_train_kernel(const float* __restrict__ psum, int nparts, float inv_count,
+                                                            const float* __restrict__ W1, const float* __restrict__ W2, int C, int se,
+                                                            float* __restrict__ gate, float* __restrict__ mean_out, float* __restrict__ hid_out) {
+  extern __shared__ float sh[];
+  float* mean = sh; float* hid = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int h = 0; h < nparts; ++h) s += psum[((long long)n * nparts + h) * C + c];
+    mean[c] = s * inv_count;
+    if (mean_out) mean_out[(long long)n * C + c] = mean[c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < se; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += W1[(long long)j * C + c] * mean[c];
+    a = warp_sum(a);
+    if (lane == 0) { hid[j] = fmaxf(a, 0.f); if (hid_out) hid_out[(long long)n * se + j] = hid[j]; }
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nw) {
+    float a = 0.f;
+    for (int j = lane; j < se; j += 32) a += W2[(long long)c * se + j] * hid[j];
+    a = warp_sum(a);
+    if (lane == 0) gate[(long long)n * C + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// out[n][p][c] = x[n][p][c] * gate[n][c]   (out of place: training keeps the pre-gate activations)
+__global__ void __launch_bounds__(256) se_scale_oop_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ out,
+                                                           long long HW, int C, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const long long e = i * 4;
+  const int c = (int)(e % C);
+  const long long n = (e / C) / HW;
+  const float4 v = *reinterpret_cast<const float4*>(x + e), g = *reinterpret_cast<const float4*>(gate + n * C + c);
+  *reinterpret_cast<float4*>(out + e) = make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w);
+}
+
+// dgate[n][c] = sum_p a[n][p][c] * b[n][p][c]        grid (chunks, N)
+__global__ void __launch_bounds__(256) field_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                        long long HW, int C) {
+  const int n = blockIdx.y;
+  const long long rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * rows_per;
+  long long p1 = p0 + rows_per;
+  if (p1 > HW) p1 = HW;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (long long p = p0; p < p1; ++p) { const long long i = ((long long)n * HW + p) * C + c; s = fmaf(a[i], b[i], s); }
+    atomicAdd(out + (long long)n * C + c, s);
+  }
+}
+
+// per field: dpre2 = dgate*gate*(1-gate); dhid = relu'(hid) * W2^T dpre2; dmean = W1^T dhid  (scaled by 1/HW for the apply)
+__global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate, const float* __restrict__ hid,
+                                                     const float* __restrict__ W1, const float* __restrict__ W2, int C, int se, float inv_count,
+                                                     float* __restrict__ dpre2, float* __restrict__ dhid, float* __restrict__ dmean) {
+  extern __shared__ float sh[];
+  float* sp = sh; float* sd = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gate[(long long)n * C + c];
+    const float v = dgate[(long long)n * C + c] * g * (1.0f - g);
+    sp[c] = v; dpre2[(long long)n * C + c] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < se; j += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a += W2[(long long)c * se + j] * sp[c];
+    if (hid[(long long)n * se + j] <= 0.f) a = 0.f;
+    sd[j] = a; dhid[(long long)n * se + j] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < se; ++j) a += W1[(long long)j * C + c] * sd[j];
+    dmean[(long long)n * C + c] = a * inv_count;
+  }
+}
+
+// ================================================================================================
+// attention backward
+// ================================================================================================
+__device__ __forceinline__ long long tok_pixel(const AttnGeom& g, int wi, int t) {
+  const int a = t / g.win, b = t - a * g.win;
+  const int x = wi / g.Y, y = wi - x * g.Y;
+  const int ph = g.grid_mode ? a * g.X + x : x * g.win + a;
+  const int pw = g.grid_mode ? b * g.Y + y : y * g.win + b;
+  return (long long)ph * g.Wl + pw;
+}
+
+// gradient wrt the out-projection output (maxvit.py:218-219, 310-319): window rows gather dX_out through the partition
+// map, register rows take dreg (N,R,C) * reg_scale (the mean over windows, maxvit.py:326) or zero.
+__global__ void __launch_bounds__(256) attn_out_bwd_gather_kernel(const float* __restrict__ dx_out, const float* __restrict__ dreg, float reg_scale,
+                                                                  const AttnGeom g, float* __restrict__ dproj, long long rows) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31, C = g.C, S = g.S(), nwin = g.nwin();
+  const long long wdx = r / S;
+  const int tok = (int)(r - wdx * S);
+  const int n = (int)(wdx / nwin), wi = (int)(wdx - (long long)n * nwin);
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tok < g.R) {
+      if (dreg) { v = *reinterpret_cast<const float4*>(dreg + ((long long)n * g.R + tok) * C + c); v.x *= reg_scale; v.y *= reg_scale; v.z *= reg_scale; v.w *= reg_scale; }
+    } else {
+      v = *reinterpret_cast<const float4*>(dx_out + ((long long)n * g.Hl * g.Wl + tok_pixel(g, wi, tok - g.R)) * C + c);
+    }
+    *reinterpret_cast<float4*>(dproj + r * C + c) = v;
+  }
+}
+
+// Core backward (maxvit.py:195-215), one block per (field, head), looping over the field's windows so that the
+// relative-position-bias and q/k-gamma gradients accumulate in shared memory / registers and reach global memory
+// once per block.  fp32, DH = 32, S <= 64.
+struct AttnCoreBwdParams {
+  const float* qkv;        // [rows][3*inner]
+  const float* datt;       // [rows][inner]
+  const float* qgamma; const float* kgamma;   // [heads*DH]
+  const float* bias_table; // [nb][heads]
+  float* dqkv;             // [rows][3*inner]
+  float* dqgamma; float* dkgamma; float* dbias_table;
+  AttnGeom g;
+  int heads;
+};
+
+__global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdParams p) {
+  constexpr int DH = 32, LD = DH + 1, SM = 64;
+  extern __shared__ float sm[];
+  const AttnGeom g = p.g;
+  const int S = g.S(), nwin = g.nwin(), W2 = 2 * g.win - 1, nb = W2 * W2 + 1;
+  float* qh = sm;                 // [SM][LD] normalised * gamma
+  float* kh = qh + SM * LD;
+  float* vv = kh + SM * LD;
+  float* dO = vv + SM * LD;
+  float* qu = dO + SM * LD;       // unit vectors
+  float* ku = qu + SM * LD;
+  float* dqh = ku + SM * LD;
+  float* dkh = dqh + SM * LD;
+  float* P = dkh + SM * LD;       // [SM][SM+1]
+  float* sbias = P + SM * (SM + 1);   // [nb]
+  float* dbias = sbias + nb;          // [nb]
+  float* inq = dbias + nb;            // [SM] 1/|q|
+  float* ink = inq + SM;
+  float* gred = ink + SM;             // [8][2][DH]
+  const int n = blockIdx.x / p.heads, hd = blockIdx.x - n * p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = p.heads * DH;
+  const float rs = sqrtf((float)DH);
+  for (int i = threadIdx.x; i < nb; i += 256) { sbias[i] = p.bias_table[i * p.heads + hd]; dbias[i] = 0.f; }
+  const float gq = p.qgamma[hd * DH + lane], gk = p.kgamma[hd * DH + lane];
+  float dgq = 0.f, dgk = 0.f;
+  __syncthreads();
+
+  for (int wi = 0; wi < nwin; ++wi) {
+    const long long row0 = ((long long)n * nwin + wi) * S;
+    // ---- load + normalise: warp per row, lane = d
+    for (int i = warp; i < S; i += 8) {
+      const float* src = p.qkv + (row0 + i) * 3 * inner + hd * DH + lane;
+      const float q = src[0], k = src[inner], v = src[2 * inner];
+      const float nq = fmaxf(sqrtf(warp_sum(q * q)), 1e-12f), nk = fmaxf(sqrtf(warp_sum(k * k)), 1e-12f);
+      const float uq = q / nq, uk = k / nk;
+      qu[i * LD + lane] = uq; ku[i * LD + lane] = uk;
+      qh[i * LD + lane] = uq * rs * gq; kh[i * LD + lane] = uk * rs * gk;
+      vv[i * LD + lane] = v;
+      dO[i * LD + lane] = p.datt[(row0 + i) * inner + hd * DH + lane];
+      if (lane == 0) { inq[i] = 1.0f / nq; ink[i] = 1.0f / nk; }
+    }
+    __syncthreads();
+    // ---- P = softmax(qh kh^T + bias): warp per row, lanes over keys j, j+32
+    for (int i = warp; i < S; i += 8) {
+      float s[2];
+      const int ti = i - g.R, ai = ti / g.win, bi = ti - ai * g.win;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        float a = -INFINITY;
+        if (j < S) {
+          a = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) a = fmaf(qh[i * LD + d], kh[j * LD + d], a);
+          int bidx = nb - 1;
+          if (i >= g.R && j >= g.R) { const int tj = j - g.R, aj = tj / g.win, bj = tj - aj * g.win; bidx = (ai - aj + g.win - 1) * W2 + (bi - bj + g.win - 1); }
+          a += sbias[bidx];
+        }
+        s[t] = a;
+      }
+      const float m = warp_max(fmaxf(s[0], s[1]));
+      const float e0 = lane < S ? __expf(s[0] - m) : 0.f, e1 = lane + 32 < S ? __expf(s[1] - m) : 0.f;
+      const float inv = 1.0f / warp_sum(e0 + e1);
+      P[i * (SM + 1) + lane] = e0 * inv;
+      P[i * (SM + 1) + lane + 32] = e1 * inv;
+    }
+    __syncthreads();
+    // ---- dV[j][d] = sum_i P[i][j] dO[i][d]: warp per j, lane = d
+    for (int j = warp; j < S; j += 8) {
+      float a = 0.f;
+      for (int i = 0; i < S; ++i) a = fmaf(P[i * (SM + 1) + j], dO[i * LD + lane], a);
+      p.dqkv[(row0 + j) * 3 * inner + 2 * inner + hd * DH + lane] = a;
+    }
+    __syncthreads();
+    // ---- dS = P * (dP - sum_j P dP), dP[i][j] = dO[i] . v[j]; overwrite P with dS; bias-table gradient
+    for (int i = warp; i < S; i += 8) {
+      float dp[2], pr[2];
+      const int ti = i - g.R, ai = ti / g.win, bi = ti - ai * g.win;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        float a = 0.f;
+        if (j < S) {
+#pragma unroll
+          for (int d = 0; d < DH; ++d) a = fmaf(dO[i * LD + d], vv[j * LD + d], a);
+        }
+        dp[t] = a; pr[t] = j < S ? P[i * (SM + 1) + j] : 0.f;
+      }
+      const float dot = warp_sum(pr[0] * dp[0] + pr[1] * dp[1]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        if (j < S) {
+          const float ds = pr[t] * (dp[t] - dot);
+          P[i * (SM + 1) + j] = ds;
+          int bidx = nb - 1;
+          if (i >= g.R && j >= g.R) { const int tj = j - g.R, aj = tj / g.win, bj = tj - aj * g.win; bidx = (ai - aj + g.win - 1) * W2 + (bi - bj + g.win - 1); }
+          atomicAdd(&dbias[bidx], ds);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- dqh[i][d] = sum_j dS[i][j] kh[j][d];  dkh[j][d] = sum_i dS[i][j] qh[i][d]
+    for (int i = warp; i < S; i += 8) {
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < S; ++j) {
+        a = fmaf(P[i * (SM + 1) + j], kh[j * LD + lane], a);
+        b = fmaf(P[j * (SM + 1) + i], qh[j * LD + lane], b);
+      }
+      dqh[i * LD + lane] = a; dkh[i * LD + lane] = b;
+    }
+    __syncthreads();
+    // ---- RMSNorm backward (maxvit.py:30): xh = u * rs * gamma, u = x/|x|
+    for (int i = warp; i < S; i += 8) {
+      const float aq = dqh[i * LD + lane], ak = dkh[i * LD + lane];
+      const float uq = qu[i * LD + lane], uk = ku[i * LD + lane];
+      dgq = fmaf(aq, uq * rs, dgq); dgk = fmaf(ak, uk * rs, dgk);
+      const float g1 = aq * rs * gq, g2 = ak * rs * gk;
+      const float d1 = warp_sum(g1 * uq), d2 = warp_sum(g2 * uk);
+      float* dst = p.dqkv + (row0 + i) * 3 * inner + hd * DH + lane;
+      dst[0] = inq[i] * (g1 - uq * d1);
+      dst[inner] = ink[i] * (g2 - uk * d2);
+    }
+    __syncthreads();
+  }
+  gred[(warp * 2) * DH + lane] = dgq; gred[(warp * 2 + 1) * DH + lane] = dgk;
+  __syncthreads();
+  if (threadIdx.x < 2 * DH) {
+    const int which = threadIdx.x / DH, d = threadIdx.x % DH;
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += gred[(w * 2 + which) * DH + d];
+    atomicAdd((which ? p.dkgamma : p.dqgamma) + hd * DH + d, s);
+  }
+  for (int i = threadIdx.x; i < nb; i += 256) atomicAdd(p.dbias_table + i * p.heads + hd, dbias[i]);
+}
+
+// LayerNorm (no affine) + FiLM backward with the inverse partition (maxvit.py:176-187, 298-308, 322-332), C = 128.
+//   tok = xhat*gamma[n] + beta[n];  dgamma[n][c] += dtok*xhat;  dbeta[n][c] += dtok;  dxhat = dtok*gamma
+//   dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) + dres   (dres = gradient of the residual path)
+// window rows write dx_in[pix] = dx + dx_out[pix]; register rows accumulate into dreg_in ([R][C] or [N][R][C]) with
+// the residual gradient dreg_res (N,R,C)*reg_scale (or none).
+struct AttnGatherBwdParams {
+  const float* x; const float* reg; int reg_per_field; const float* film;
+  const float* dtok; const float* dx_out; const float* dreg_res; float reg_scale;
+  float* dx_in; float* dreg_in; float* dfilm;     // dfilm (N, 2C) accumulated
+  AttnGeom g; float eps;
+};
+
+__global__ void __launch_bounds__(256) attn_gather_bwd_kernel(const AttnGatherBwdParams p, long long rows) {
+  constexpr int C = 128, RPW = 16;
+  const AttnGeom g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 4;
+  const int S = g.S(), nwin = g.nwin();
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  int n_cur = -1;
+  auto flush = [&]() {
+    if (n_cur < 0) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { atomicAdd(p.dfilm + (long long)n_cur * 2 * C + c0 + i, ag[i]); atomicAdd(p.dfilm + (long long)n_cur * 2 * C + C + c0 + i, ab[i]); ag[i] = ab[i] = 0.f; }
+  };
+  const long long r0 = ((long long)blockIdx.x * 8 + warp) * RPW;
+  for (int k = 0; k < RPW; ++k) {
+    const long long r = r0 + k;
+    if (r >= rows) break;
+    const long long wdx = r / S;
+    const int tok = (int)(r - wdx * S);
+    const int n = (int)(wdx / nwin), wi = (int)(wdx - (long long)n * nwin);
+    if (n != n_cur) { flush(); n_cur = n; }
+    const float* src; long long pix = -1;
+    if (tok < g.R) src = p.reg + (p.reg_per_field ? (long long)n * g.R * C : 0) + (long long)tok * C;
+    else { pix = (long long)n * g.Hl * g.Wl + tok_pixel(g, wi, tok - g.R); src = p.x + pix * C; }
+    const float4 xv = *reinterpret_cast<const float4*>(src + c0);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + p.eps);
+    const float4 gm = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c0);
+    const float4 dt = *reinterpret_cast<const float4*>(p.dtok + r * C + c0);
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, dtv[4] = {dt.x, dt.y, dt.z, dt.w};
+    float dx[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] *= rstd;                                            // xhat
+      ag[i] = fmaf(dtv[i], v[i], ag[i]); ab[i] += dtv[i];
+      dx[i] = dtv[i] * gmv[i]; s1 += dx[i]; s2 = fmaf(dx[i], v[i], s2);
+    }
+    s1 = warp_sum(s1) * (1.0f / C); s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dx[i] = rstd * (dx[i] - s1 - v[i] * s2);
+    if (tok < g.R) {
+      float* d = p.dreg_in + (p.reg_per_field ? (long long)n * g.R * C : 0) + (long long)tok * C + c0;
+      const float* rr = p.dreg_res ? p.dreg_res + ((long long)n * g.R + tok) * C + c0 : nullptr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(d + i, dx[i] + (rr ? rr[i] * p.reg_scale : 0.f));
+    } else {
+      const float4 ro = *reinterpret_cast<const float4*>(p.dx_out + pix * C + c0);
+      *reinterpret_cast<float4*>(p.dx_in + pix * C + c0) = make_float4(dx[0] + ro.x, dx[1] + ro.y, dx[2] + ro.z, dx[3] + ro.w);
+    }
+  }
+  flush();
+}
+
+// ================================================================================================
+// host launchers
+// ================================================================================================
+long long bn_workspace_elems(long long M, int C) { return ((M + STAT_ROWS - 1) / STAT_ROWS) * 2 * C; }
+
+int bn_stats_run(const float* X, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* run_mean, float* run_var, float* mean, float* rstd, float* scale, float* shift, float* work,
+                 long long work_elems, cudaStream_t st) {
+  const int nparts = (int)((M + STAT_ROWS - 1) / STAT_ROWS);
+  if (work_elems < (long long)nparts * 2 * C) return set_error("bn_stats: workspace too small");
+  colstats_kernel<<<nparts, 256, 0, st>>>(X, M, C, work);
+  int rc = check_launch("colstats_kernel");
+  if (rc) return rc;
+  bn_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(work, nparts, M, C, gamma, beta, eps, momentum, run_mean, run_var, mean, rstd, scale, shift);
+  return check_launch("bn_finalize_kernel");
+}
+
+int bn_act_run(const float* raw, const float* scale, const float* shift, int act, const float* res, float* out, long long M, int C,
+               cudaStream_t st) {
+  if (C % 4) return set_error("bn_act: C %% 4 != 0");
+  const long long total4 = M * C / 4;
+  bn_act_kernel<<<nblk(total4, 256), 256, 0, st>>>(raw, scale, shift, act, res, out, total4, C);
+  return check_launch("bn_act_kernel");
+}
+
+int bn_bwd_run(const float* dOut, const float* raw, const float* scale, const float* shift, const float* mean, const float* rstd,
+               const float* gamma, int act, const float* fgate, const float* fadd, long long rows_per_field, long long M, int C,
+               float* dgamma, float* dbeta, float* draw, float* work, long long work_elems, cudaStream_t st) {
+  const int nparts = (int)((M + STAT_ROWS - 1) / STAT_ROWS);
+  if (work_elems < (long long)nparts * 2 * C + 2 * C) return set_error("bn_bwd: workspace too small");
+  BnBwdParams p;
+  p.dOut = dOut; p.raw = raw; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.gamma = gamma;
+  p.fgate = fgate; p.fadd = fadd; p.rows_per_field = rows_per_field > 0 ? rows_per_field : 1; p.act = act; p.C = C; p.M = M;
+  float* k1 = work + (long long)nparts * 2 * C; float* k2 = k1 + C;
+  bn_bwd_reduce_kernel<<<nparts, 256, 0, st>>>(p, work);
+  int rc = check_launch("bn_bwd_reduce_kernel");
+  if (rc) return rc;
+  bn_bwd_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(work, nparts, M, C, dgamma, dbeta, k1, k2);
+  rc = check_launch("bn_bwd_finalize_kernel");
+  if (rc) return rc;
+  bn_bwd_apply_kernel<<<nblk(M * C, 256), 256, 0, st>>>(p, k1, k2, draw);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+int colsum_run(const float* X, long long M, int C, float* out, cudaStream_t st) {
+  colsum_kernel<<<nblk(M, STAT_ROWS), 256, 0, st>>>(X, M, C, out);
+  return check_launch("colsum_kernel");
+}
+
+int dwconv_march_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, int act, void* out,
+                     float* psum, int N, int H, int W, int C, cudaStream_t st) {
+  if (C % 4 || C / 4 > 128 || (128 % (C / 4))) return set_error("dwconv: C=%d must be 4*k with k | 128", C);
+  const int strips = (W + DW_SW - 1) / DW_SW;
+  const int spb = 128 / (C / 4);
+  const int sblocks = (strips + spb - 1) / spb;
+  if (dtype == 0) dwconv_march_kernel<bf16><<<N * sblocks, 128, 0, st>>>(reinterpret_cast<const bf16*>(in), w9, scale, shift, act, reinterpret_cast<bf16*>(out), psum, H, W, C, strips);
+  else dwconv_march_kernel<float><<<N * sblocks, 128, 0, st>>>(reinterpret_cast<const float*>(in), w9, scale, shift, act, reinterpret_cast<float*>(out), psum, H, W, C, strips);
+  return check_launch("dwconv_march_kernel");
+}
+int dwconv_strips(int W) { return (W + DW_SW - 1) / DW_SW; }
+
+int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, float* dw9, float* dbias, float* work,
+                 long long work_elems, cudaStream_t st) {
+  if (C % 4 || C / 4 > 128 || (128 % (C / 4))) return set_error("dw_wgrad: C=%d must be 4*k with k | 128", C);
+  const int strips = (W + DW_SW - 1) / DW_SW;
+  const long long nparts = (long long)N * strips;
+  if (work_elems < nparts * 10 * C + 10 * C) return set_error("dw_wgrad: workspace too small");
+  const int spb = 128 / (C / 4);
+  const int sblocks = (strips + spb - 1) / spb;
+  dw_wgrad_kernel<<<N * sblocks, 128, 0, st>>>(X, dY, work, H, W, C, strips);
+  int rc = check_launch("dw_wgrad_kernel");
+  if (rc) return rc;
+  float* tot = work + nparts * 10 * C;
+  partial_sum_kernel<<<nblk(10LL * C, 256), 256, 0, st>>>(work, (int)nparts, 10LL * C, 0.f, tot);
+  rc = check_launch("partial_sum_kernel");
+  if (rc) return rc;
+  // dw9 [9][C] += tot[0..9), dbias[C] += tot[9]
+  partial_sum_kernel<<<nblk(9LL * C, 256), 256, 0, st>>>(tot, 1, 9LL * C, 1.f, dw9);
+  rc = check_launch("partial_sum_kernel");
+  if (rc) return rc;
+  partial_sum_kernel<<<nblk(C, 256), 256, 0, st>>>(tot + 9LL * C, 1, C, 1.f, dbias);
+  return check_launch("partial_sum_kernel");
+}
+
+int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C, int se,
+                      float* gate, float* mean, float* hid, cudaStream_t st) {
+  se_gate_train_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(psum, nparts, 1.0f / (float)HW, W1, W2, C, se, gate, mean, hid);
+  return check_launch("se_gate_train_kernel");
+}
+
+int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st) {
+  const long long total4 = (long long)N * HW * C / 4;
+  se_scale_oop_kernel<<<nblk(total4, 256), 256, 0, st>>>(x, gate, out, HW, C, total4);
+  return check_launch("se_scale_oop_kernel");
+}
+
+int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
+               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
+               long long work_elems, cudaStream_t st) {
+  const long long need = (long long)N * (2 * C + se);
+  if (work_elems < need) return set_error("se_bwd: workspace too small");
+  float* dgate = work; float* dpre2 = dgate + (long long)N * C; float* dhid = dpre2 + (long long)N * C;
+  cudaError_t e = cudaMemsetAsync(dgate, 0, (size_t)N * C * sizeof(float), st);
+  if (e != cudaSuccess) return set_error("se_bwd memset: %s", cudaGetErrorString(e));
+  int chunks = (int)((HW + 127) / 128);
+  if (chunks > 16) chunks = 16;
+  field_dot_kernel<<<dim3(chunks, N), 256, 0, st>>>(dh4, h3, dgate, HW, C);
+  int rc = check_launch("field_dot_kernel");
+  if (rc) return rc;
+  se_bwd_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(dgate, gate, hid, W1, W2, C, se, 1.0f / (float)HW, dpre2, dhid, dmean);
+  rc = check_launch("se_bwd_kernel");
+  if (rc) return rc;
+  rc = outer_sum_run(dpre2, hid, N, C, se, dW2, nullptr, st);       // dW2[c][j] += sum_n dpre2[n][c] hid[n][j]
+  if (rc) return rc;
+  return outer_sum_run(dhid, mean, N, se, C, dW1, nullptr, st);     // dW1[j][c] += sum_n dhid[n][j] mean[n][c]
+}
+
+int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, cudaStream_t st) {
+  if (g.C % 128) return set_error("attn_out_bwd_gather: C %% 128 != 0");
+  const long long rows = (long long)g.N * g.nwin() * g.S();
+  attn_out_bwd_gather_kernel<<<nblk(rows, 8), 256, 0, st>>>(dx_out, dreg, reg_scale, g, dproj, rows);
+  return check_launch("attn_out_bwd_gather_kernel");
+}
+
+int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
+                      const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
+                      cudaStream_t st) {
+  if (dh != 32) return set_error("attn_core_bwd: dim_head must be 32 (got %d)", dh);
+  if (g.S() > 64) return set_error("attn_core_bwd: sequence %d > 64", g.S());
+  const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
+  const size_t smem = (size_t)(8 * 64 * 33 + 64 * 65 + 2 * nb + 128 + 8 * 2 * 32) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("attn_core_bwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  AttnCoreBwdParams p;
+  p.qkv = qkv; p.datt = datt; p.qgamma = qgamma; p.kgamma = kgamma; p.bias_table = bias_table; p.dqkv = dqkv;
+  p.dqgamma = dqgamma; p.dkgamma = dkgamma; p.dbias_table = dbias_table; p.g = g; p.heads = heads;
+  attn_core_bwd_kernel<<<g.N * heads, 256, smem, st>>>(p);
+  return check_launch("attn_core_bwd_kernel");
+}
+
+int attn_gather_bwd_run(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
+                        const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in, float* dfilm,
+                        const AttnGeom& g, float eps, cudaStream_t st) {
+  if (g.C != 128) return set_error("attn_gather_bwd: C must be 128");
+  AttnGatherBwdParams p;
+  p.x = x; p.reg = reg; p.reg_per_field = reg_per_field; p.film = film; p.dtok = dtok; p.dx_out = dx_out; p.dreg_res = dreg_res;
+  p.reg_scale = reg_scale; p.dx_in = dx_in; p.dreg_in = dreg_in; p.dfilm = dfilm; p.g = g; p.eps = eps;
+  const long long rows = (long long)g.N * g.nwin() * g.S();
+  attn_gather_bwd_kernel<<<nblk(rows, 8 * 16), 256, 0, st>>>(p, rows);
+  return check_launch("attn_gather_bwd_kernel");
+}
+
+}  // namespace vg

@@ -13,6 +13,7 @@ enum EpiKind : int {
   EPI_CONV_LN = 1,    // conv3x3 block: +bias, channel LayerNorm, FiLM, ReLU, (+res), zero pads (PG layout)
   EPI_ATTN_OUT = 2,   // attention out-projection: + residual, scatter through the inverse window/grid map
   EPI_CONVT = 3,      // ConvTranspose2d k2 s2 as GEMM: + bias, depth-to-space into the PG layout
+  EPI_CONV_LN_TRAIN = 4,  // EPI_CONV_LN that also saves what the backward pass needs (normalised activations, rstd, ReLU mask)
 };
 
 struct EpiParams {
@@ -34,6 +35,11 @@ struct EpiParams {
   PGeom pg;                  // output geometry (EPI_CONV_LN, EPI_CONVT)
   int res_f32;               // EPI_CONV_LN: the residual is fp32 (skip connections keep full precision)
   float* out2;               // optional fp32 copy of the output (EPI_CONV_LN, EPI_CONVT), same indexing as out
+  // EPI_CONV_LN_TRAIN: saved for backward -- xhat (activation dtype, [q][C], zeros at pads), rstd (fp32 [q]),
+  // relu_mask (4 x 32 bits per pixel: bit c%32 of word c/32 = ReLU input > 0)
+  void* xhat;
+  float* rstd_out;
+  unsigned* relu_mask;
   // optional fused 1x1 head + unpad + de-normalisation (metnet3.py:424-430): head_out[n][h-pt][w-pl]
   const float* head_w;       // [C]; null = no head
   float* head_out;           // (N, H, W) fp32
@@ -72,7 +78,13 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bo
       else if (ep.act == 2) x = fmaxf(x, 0.f);
       v[j] = x;
     }
-    if (ep.res) {
+    if (ep.res && ep.res_f32) {
+      const float* r = reinterpret_cast<const float*>(ep.res) + row * ep.ldres + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) { float t[8]; ld8(r + j, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] += t[i]; }
+    } else if (ep.res) {
       const T* r = reinterpret_cast<const T*>(ep.res) + row * ep.ldres + c0;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) { float t[8]; ld8(r + j, t);
@@ -108,7 +120,7 @@ __device__ __forceinline__ void epi_conv_ln_prefetch(const EpiParams& ep, long l
 }
 
 // Requires the whole channel row in one tile: n0 == 0, C == 128.
-template <typename T, class Loader>
+template <typename T, bool TRAIN, class Loader>
 __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& cx, long long row, bool ok, int n0, Loader& ld) {
   (void)n0;
   constexpr int C = 128;
@@ -144,6 +156,10 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
   const T* r = (ep.res && !ep.res_f32 && valid) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
   const float* rf = (ep.res && ep.res_f32 && valid) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
   float head = 0.f;
+  T* xo = (TRAIN && ep.xhat) ? reinterpret_cast<T*>(ep.xhat) + row * ep.ldo : nullptr;
+  if (TRAIN && in_buf) {
+    if (ep.rstd_out) ep.rstd_out[row] = valid ? rstd : 0.f;
+  }
   // pass 2: normalise, FiLM, ReLU, residual, store (zeros at pad positions); the residual of chunk ch+1 is in
   // flight while chunk ch is processed
   float rr[32];
@@ -158,6 +174,8 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
   for (int ch = 0; ch < 4; ++ch) {
     ld.load(ch, v);
     if (!in_buf) continue;
+    unsigned mbits = 0u;
+    float xh[TRAIN ? 32 : 1];
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -172,7 +190,17 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
           y0 = fmaf(y0, sc.x + 1.0f, sh.x); y1 = fmaf(y1, sc.y + 1.0f, sh.y);
           y2 = fmaf(y2, sc.z + 1.0f, sh.z); y3 = fmaf(y3, sc.w + 1.0f, sh.w);
         }
+        if (TRAIN) {
+          mbits |= (y0 > 0.f ? 1u : 0u) << j; mbits |= (y1 > 0.f ? 1u : 0u) << (j + 1);
+          mbits |= (y2 > 0.f ? 1u : 0u) << (j + 2); mbits |= (y3 > 0.f ? 1u : 0u) << (j + 3);
+          xh[j] = (v[j] + b4.x - mean) * rstd; xh[j + 1] = (v[j + 1] + b4.y - mean) * rstd;
+          xh[j + 2] = (v[j + 2] + b4.z - mean) * rstd; xh[j + 3] = (v[j + 3] + b4.w - mean) * rstd;
+        }
         v[j] = fmaxf(y0, 0.f); v[j + 1] = fmaxf(y1, 0.f); v[j + 2] = fmaxf(y2, 0.f); v[j + 3] = fmaxf(y3, 0.f);
+      }
+      if (TRAIN && xo) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st8(xo + ch * 32 + j, xh + j);
       }
       if (rf || r) {
 #pragma unroll
@@ -194,7 +222,12 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      if (TRAIN && xo) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st8(xo + ch * 32 + j, v + j);
+      }
     }
+    if (TRAIN && ep.relu_mask) ep.relu_mask[row * 4 + ch] = mbits;
     if (o) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
@@ -282,7 +315,8 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
 template <int KIND, typename T, class Loader>
 __device__ __forceinline__ void run_epilogue(const EpiParams& ep, const EpiCtx& cx, long long row, bool ok, int n0, Loader& ld) {
   if constexpr (KIND == EPI_STORE) epi_store<T>(ep, row, ok, n0, ld);
-  else if constexpr (KIND == EPI_CONV_LN) epi_conv_ln<T>(ep, cx, row, ok, n0, ld);
+  else if constexpr (KIND == EPI_CONV_LN) epi_conv_ln<T, false>(ep, cx, row, ok, n0, ld);
+  else if constexpr (KIND == EPI_CONV_LN_TRAIN) epi_conv_ln<T, true>(ep, cx, row, ok, n0, ld);
   else if constexpr (KIND == EPI_ATTN_OUT) epi_attn_out<T>(ep, row, ok, n0, ld);
   else epi_convt<T>(ep, row, ok, n0, ld);
 }

@@ -66,7 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (KIND == EPI_CONV_LN) {
+  if (KIND == EPI_CONV_LN || KIND == EPI_CONV_LN_TRAIN) {
     for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
       sparam[i] = ep.bias[i]; sparam[128 + i] = ep.ln_g[i]; sparam[256 + i] = ep.ln_b[i];
     }
@@ -139,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const long long row = (long long)batch * gs.rows_per_batch + lrow;
       const bool ok = lrow < gs.rows_per_batch && row < gs.M;
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
-      if (KIND == EPI_CONV_LN) {
+      if (KIND == EPI_CONV_LN || KIND == EPI_CONV_LN_TRAIN) {
         if (TF32) epi_conv_ln_prefetch<float>(ep, row, ok); else epi_conv_ln_prefetch<bf16>(ep, row, ok);
         if (ep.film) {
           // fold FiLM of the (at most two) fields this warpgroup's 128 rows touch into the LayerNorm affine
@@ -205,6 +205,7 @@ __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int
   return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const HaloShape hs, const EpiParams ep) {
@@ -308,7 +309,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
       TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
-      run_epilogue<EPI_CONV_LN, bf16>(ep, cx, row, ok, 0, ld);
+      run_epilogue<TRAIN ? EPI_CONV_LN_TRAIN : EPI_CONV_LN, bf16>(ep, cx, row, ok, 0, ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
@@ -458,7 +459,7 @@ static int launch_simt_epi(const float* scratch, int Ntot, const GemmShape& gs, 
 }
 
 // bf16 3x3 conv (Cin = Cout = 128) over a PG buffer with halo reuse; returns -1 when the shape does not fit
-int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, cudaStream_t st) {
+int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, int train, cudaStream_t st) {
   const int P = pg.P;
   const int HR = ((BM + 2 * (P + 1)) + 15) / 16 * 16;
   if (HR > HALO_MAX_ROWS) return -1;
@@ -485,12 +486,14 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   hs.M = pg.pixels(); hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = hs.num_tiles < num_sms() ? hs.num_tiles : num_sms();
-  conv_halo_kernel<<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
+  if (train) conv_halo_kernel<true><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
+  else conv_halo_kernel<false><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
   return check_launch("conv_halo_kernel");
 }
 
@@ -516,7 +519,7 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
   gs.num_m_tiles = (int)(gs.tiles_per_batch * nbatch);
   gs.num_n_tiles = (Ntot + BN - 1) / BN;
   const int Ktot = Ca * ntaps;
-  if (kind == EPI_CONV_LN && Ntot != BN) return set_error("gemm: conv+LN epilogue needs exactly %d output channels (got %d)", BN, Ntot);
+  if ((kind == EPI_CONV_LN || kind == EPI_CONV_LN_TRAIN) && Ntot != BN) return set_error("gemm: conv+LN epilogue needs exactly %d output channels (got %d)", BN, Ntot);
 
   if (dtype == 0 || dtype == 2) {
     CUtensorMap ma, mb;
@@ -530,6 +533,7 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
         case EPI_CONV_LN: return launch_tc<EPI_CONV_LN, 0>(ma, mb, gs, ep, st);
         case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT, 0>(ma, mb, gs, ep, st);
         case EPI_CONVT: return launch_tc<EPI_CONVT, 0>(ma, mb, gs, ep, st);
+        case EPI_CONV_LN_TRAIN: return launch_tc<EPI_CONV_LN_TRAIN, 0>(ma, mb, gs, ep, st);
       }
     } else {
       switch (kind) {
@@ -537,6 +541,7 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
         case EPI_CONV_LN: return launch_tc<EPI_CONV_LN, 1>(ma, mb, gs, ep, st);
         case EPI_ATTN_OUT: return launch_tc<EPI_ATTN_OUT, 1>(ma, mb, gs, ep, st);
         case EPI_CONVT: return launch_tc<EPI_CONVT, 1>(ma, mb, gs, ep, st);
+        case EPI_CONV_LN_TRAIN: return launch_tc<EPI_CONV_LN_TRAIN, 1>(ma, mb, gs, ep, st);
       }
     }
     return set_error("gemm: bad epilogue kind %d", kind);
@@ -553,6 +558,7 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
     case EPI_CONV_LN: return launch_simt_epi<EPI_CONV_LN>(scratch, Ntot, gs, ep, st);
     case EPI_ATTN_OUT: return launch_simt_epi<EPI_ATTN_OUT>(scratch, Ntot, gs, ep, st);
     case EPI_CONVT: return launch_simt_epi<EPI_CONVT>(scratch, Ntot, gs, ep, st);
+    case EPI_CONV_LN_TRAIN: return launch_simt_epi<EPI_CONV_LN_TRAIN>(scratch, Ntot, gs, ep, st);
   }
   return set_error("gemm: bad epilogue kind %d", kind);
 }

@@ -14,7 +14,7 @@ int set_error(const char* fmt, ...);
 // cudaGetLastError() after a launch; 0 when clean
 int check_launch(const char* what);
 
-int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, cudaStream_t st);
+int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, int train, cudaStream_t st);
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st);
@@ -45,6 +45,8 @@ struct TimeParams {
 };
 
 struct StemParams {
+  // training only (null in inference): saved for backward, same meaning as the EPI_CONV_LN_TRAIN outputs
+  void* xhat; float* rstd; unsigned* mask;
   const float* raw3; const float* rawres;   // [q_b][C] fp32 over the B-image PG geometry
   const float* bias3; const float* bias1;
   const float* tt; const float* tres;       // (N,9,C), (N,C)
@@ -89,5 +91,61 @@ int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* 
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                    const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,
                    cudaStream_t st);
+
+// ---- training (vg_wgrad.cu, vg_bwd.cu, vg_bwd_vit.cu)
+long long wgrad_workspace_elems(int dtype, long long M, int Ntot, int Ca, int ntaps);
+int wgrad_run(int dtype, const void* dY, const void* A, long long rowsA, long long M, int Ntot, int Ca, int ntaps,
+              const int* tap_shift, float* dW, float beta, float* work, long long work_elems, cudaStream_t st);
+int conv_ln_bwd_run(int xdtype, int odtype, const float* dY, const void* xhat, const float* rstd, const unsigned* mask,
+                    const float* ln_g, const float* film, float eps, void* dconv, float* sumA, float* sumB, float* sumD,
+                    float* border, int N, int HP, int WP, cudaStream_t st);
+int conv_ln_param_grads_run(const float* sumA, const float* sumB, const float* sumD, int N, const float* g, const float* b,
+                            const float* film, float* dg, float* db, float* dbias, float* dfilm, cudaStream_t st);
+int head_bwd_run(int dtype, const float* dpred, const void* h, const float* w, float stdv, int N, int HP, int WP, int H, int W,
+                 int pt, int pl, float* dH, float* dw, float* db, cudaStream_t st);
+int maxpool2_bwd_run(int dtype, const void* x, const float* dlow, float* dx, int N, int HP, int WP, int C, cudaStream_t st);
+int convT_bwd_gather_run(int odtype, const float* dUp, void* G, float* dbias, int N, int Hl, int Wl, int C, cudaStream_t st);
+int lead_sum_run(int idtype, int odtype, const void* in, void* out, int B, int L, int HP, int WP, cudaStream_t st);
+int pg_field_sum_run(const float* in, float* out, int N, int HP, int WP, cudaStream_t st);
+int time_terms_bwd_run(const float* border, const float* sumD, const float* tres_sum, const float* temb, const float* w3,
+                       const float* w1, int N, int ntc, int c_in, int c_data, int Cout, float* dw3, float* dw1, float* db1,
+                       float* dtemb, cudaStream_t st);
+int time_embed_bwd_run(const float* dtemb, const float* dcond, const float* ts, long long sB, long long sT, long long sF, int B,
+                       int L, int le, int te, float* d_lead, float* d_m, float* d_d, float* d_h, cudaStream_t st);
+int cond_mlp_bwd_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid, const float* W1,
+                     int od, const float* dout, float* dW0, float* db0, float* dW1, float* db1, float* dcond, float* work,
+                     long long work_elems, cudaStream_t st);
+int outer_sum_run(const float* G, const float* X, int N, int O, int I, float* dW, float* db, cudaStream_t st);
+int adamw_run(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              int step, float gscale, cudaStream_t st);
+
+long long bn_workspace_elems(long long M, int C);
+int bn_stats_run(const float* X, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* run_mean, float* run_var, float* mean, float* rstd, float* scale, float* shift, float* work,
+                 long long work_elems, cudaStream_t st);
+int bn_act_run(const float* raw, const float* scale, const float* shift, int act, const float* res, float* out, long long M, int C,
+               cudaStream_t st);
+int bn_bwd_run(const float* dOut, const float* raw, const float* scale, const float* shift, const float* mean, const float* rstd,
+               const float* gamma, int act, const float* fgate, const float* fadd, long long rows_per_field, long long M, int C,
+               float* dgamma, float* dbeta, float* draw, float* work, long long work_elems, cudaStream_t st);
+int colsum_run(const float* X, long long M, int C, float* out, cudaStream_t st);
+int dwconv_march_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, int act, void* out,
+                     float* psum, int N, int H, int W, int C, cudaStream_t st);
+int dwconv_strips(int W);
+int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, float* dw9, float* dbias, float* work,
+                 long long work_elems, cudaStream_t st);
+int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C, int se,
+                      float* gate, float* mean, float* hid, cudaStream_t st);
+int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st);
+int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
+               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
+               long long work_elems, cudaStream_t st);
+int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, cudaStream_t st);
+int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
+                      const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
+                      cudaStream_t st);
+int attn_gather_bwd_run(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
+                        const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in, float* dfilm,
+                        const AttnGeom& g, float eps, cudaStream_t st);
 
 }  // namespace vg

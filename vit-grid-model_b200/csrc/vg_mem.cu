@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
   const int lane = threadIdx.x & 31, c0 = lane * 4;
   int n, h, w;
   const bool valid = p.pgN.decode(q, n, h, w);
-  float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+  float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned nib = 0u;
+  float rstd_save = 0.f;
   if (valid) {
     const int b = n / p.L;
     const long long qb = p.pgB.q(b, h, w);
@@ -158,11 +160,14 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
     const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
+    rstd_save = rstd;
     const float* film = p.film + (long long)n * 2 * C;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float z = v[i] * rstd * p.ln_g[c0 + i] + p.ln_b[c0 + i];
+      xh[i] = v[i] * rstd;
+      float z = xh[i] * p.ln_g[c0 + i] + p.ln_b[c0 + i];
       z = z * (film[c0 + i] + 1.0f) + film[C + c0 + i];
+      if (z > 0.f) nib |= 1u << i;
       y[i] = fmaxf(z, 0.f);
     }
     const float4 ra = *reinterpret_cast<const float4*>(p.rawres + qb * C + c0);
@@ -173,6 +178,17 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
 #pragma unroll
   for (int i = 0; i < 4; ++i) Act<T>::st(h1 + q * C + c0 + i, y[i]);
   *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
+  if (p.xhat) {                                   // training: what the backward pass needs
+    T* xo = reinterpret_cast<T*>(p.xhat);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Act<T>::st(xo + q * C + c0 + i, xh[i]);
+    unsigned wbits = nib << ((lane & 7) * 4);
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+    if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
+    if (lane == 0) p.rstd[q] = rstd_save;
+  }
 }
 
 // ================================================================================================
