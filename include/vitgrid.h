@@ -266,6 +266,9 @@ VG_API int vg_dw3x3_wgrad(const float* x, const float* dY, int N, int H, int W, 
  * dmean (N,C) already divided by HW); work: N*(2C+se) floats */
 VG_API int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C,
                          int se, float* gate, float* mean, float* hid, void* stream);
+/* out[n][c] += sum_p a[n][p][c] * b[n][p][c] over the HW positions of each field (b = NULL: plain sums, the
+ * squeeze-excite mean) */
+VG_API int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW, int C, void* stream);
 VG_API int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream);
 VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,

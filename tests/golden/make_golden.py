@@ -101,6 +101,33 @@ def metnet3_fixture(name, cfg, B, wseed, iseed):
                     n_params=n_params, keys=list(m.state_dict().keys())))
 
 
+def sample_index(numel, k=48, seed=0):
+    g = torch.Generator().manual_seed(seed + numel)
+    return torch.randperm(numel, generator=g)[:min(k, numel)].clone()
+
+
+def metnet3_train_fixture(name, cfg, B, wseed, iseed):
+    """train() mode forward + Focal-R + backward through the REAL reference (dropout 0: its RNG stream cannot be matched).
+    Stores the loss, the prediction, and per parameter the gradient norm plus 48 sampled entries; BatchNorm running
+    statistics after the step."""
+    from oracle.focal_r_oracle import focal_r
+    m = ref_metnet3.MetNet3(**cfg.metnet3_kwargs(), dropout=0.0).train()
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=wseed)
+    m.load_state_dict(sd, strict=True)
+    x, ts, target = synth.make_inputs(cfg, B, seed=iseed)
+    pred = m(x, timestamps=ts)
+    loss = focal_r(pred, target)
+    loss.backward()
+    grads = {}
+    for k, p in m.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        idx = sample_index(g.numel())
+        grads[k] = dict(norm=g.norm().item(), absmax=g.abs().max().item(), idx=idx, val=g[idx].clone())
+    bn = {k: v.clone() for k, v in m.state_dict().items() if "running_" in k or "num_batches" in k}
+    save(name, dict(cfg=cfg.to_dict(), B=B, weight_seed=wseed, input_seed=iseed, loss=loss.item(), pred=pred.detach().contiguous(),
+                    grads=grads, bn=bn))
+
+
 if __name__ == "__main__":
     index_fixtures()
     attention_fixture()
@@ -108,3 +135,4 @@ if __name__ == "__main__":
     metnet3_fixture("metnet3_tiny.pt", synth.CFG_TINY, 2, 0, 1234)
     metnet3_fixture("metnet3_small128.pt", synth.CFG_SMALL128, 2, 0, 1234)
     metnet3_fixture("metnet3_12hr_b1.pt", synth.CFG_12HR, 1, 0, 1234)
+    metnet3_train_fixture("metnet3_small128_train.pt", synth.CFG_SMALL128, 3, 0, 4321)

@@ -208,7 +208,7 @@ def test_dwconv_bn_gelu_and_se(dtype):
     assert rel_err(out.permute(0, 3, 1, 2), ref) < TOL[dtype]
     assert rel_err(psum.sum(1) / (H * W), ref.mean(dim=(2, 3))) < 1e-4
     W1, W2 = rnd(se, C, seed=5) / math.sqrt(C), rnd(C, se, seed=6) / math.sqrt(se)
-    gate = o.se_gate(psum, W, W1.cuda(), W2.cuda())
+    gate = o.se_gate(psum, H * W, W1.cuda(), W2.cuda())
     gref = torch.sigmoid(F.linear(F.relu(F.linear(ref.mean(dim=(2, 3)), W1)), W2))
     assert rel_err(gate, gref) < 1e-4
     o.se_scale_(out, gate)

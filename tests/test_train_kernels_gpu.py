@@ -1,0 +1,112 @@
+"""Per-kernel parity of the training kernels (GPU), through the C ABI, against PyTorch autograd of the same op.
+
+Gradient tolerances: fp32 mode 1e-4 (relative to the largest reference entry), tf32 2e-3, bf16 1.5e-2.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import metnet3_oracle as m3o
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(torch.float32, False), (torch.bfloat16, False), (torch.float32, True)]
+WTOL = {(torch.float32, False): 2e-5, (torch.bfloat16, False): 1e-2, (torch.float32, True): 2e-3}
+
+
+def O():
+    from vit_grid_model_b200 import ops
+    return ops
+
+
+def OT():
+    from vit_grid_model_b200 import ops_train
+    return ops_train
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("M,N,Ca", [(5000, 128, 128), (3001, 512, 128), (4099, 128, 512), (2500, 3072, 128), (70000, 128, 1024)])
+def test_wgrad_plain(mode, M, N, Ca):
+    dtype, tf32 = mode
+    dY, A = rnd(M, N, seed=1).to(dtype), rnd(M, Ca, seed=2).to(dtype)
+    ref = dY.float().t() @ A.float()
+    dW = torch.zeros(N, Ca, device="cuda")
+    OT().wgrad(dY.cuda(), A.cuda(), dW, tf32=tf32, beta=0.0)
+    assert rel_err(dW, ref) < WTOL[mode]
+    OT().wgrad(dY.cuda(), A.cuda(), dW, tf32=tf32, beta=1.0)          # accumulate
+    assert rel_err(dW, 2 * ref) < WTOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("Nf,H,W", [(2, 12, 10), (3, 28, 28)])
+def test_wgrad_conv3x3(mode, Nf, H, W):
+    """3x3 weight gradient over the padded-grid layout vs autograd of F.conv2d"""
+    dtype, tf32 = mode
+    o = O()
+    x = rnd(Nf, 128, H, W, seed=3).to(dtype).float()
+    dy = rnd(Nf, 128, H, W, seed=4).to(dtype).float()
+    w = torch.zeros(128, 128, 3, 3, requires_grad=True)
+    F.conv2d(x, w, padding=1).backward(dy)
+    xp, dyp = o.pg_from_nchw(x.cuda(), dtype), o.pg_from_nchw(dy.cuda(), dtype)
+    dW = torch.zeros(128, 9 * 128, device="cuda")
+    OT().wgrad(dyp, xp, dW, ntaps=9, tap_shift=o.conv_tap_shifts(W), tf32=tf32, beta=0.0)
+    got = dW.view(128, 9, 128).permute(0, 2, 1).reshape(128, 128, 3, 3)
+    assert rel_err(got, w.grad) < WTOL[mode]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_film,with_res", [(True, False), (False, True)])
+def test_conv_block_backward(dtype, with_film, with_res):
+    """Block (conv3x3 -> ChanLayerNorm -> FiLM -> ReLU (+res)) forward with saves + full backward vs autograd"""
+    o, ot = O(), OT()
+    N, H, W, C = 3, 12, 10, 128
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    x = rnd(N, C, H, W, seed=1).to(dtype).float().requires_grad_(True)
+    w = (rnd(C, C, 3, 3, seed=2) / math.sqrt(9 * C)).to(dtype).float().requires_grad_(True)
+    b = rnd(C, seed=3, scale=0.1).requires_grad_(True)
+    g = (0.5 + torch.rand(C, generator=torch.Generator().manual_seed(4))).requires_grad_(True)
+    be = rnd(C, seed=5, scale=0.1).requires_grad_(True)
+    film = rnd(N, 2 * C, seed=6, scale=0.3).requires_grad_(True) if with_film else None
+    res = rnd(N, C, H, W, seed=7).requires_grad_(True) if with_res else None
+    dy = rnd(N, C, H, W, seed=8)
+    h = m3o.chan_layer_norm(F.conv2d(x, w, b, padding=1), g.view(1, C, 1, 1), be.view(1, C, 1, 1))
+    if with_film:
+        h = h * (film[:, :C, None, None] + 1) + film[:, C:, None, None]
+    y = F.relu(h)
+    if with_res:
+        y = y + res
+    y.backward(dy)
+    # device path
+    xp = o.pg_from_nchw(x.detach().cuda(), dtype)
+    Wt = w.detach().permute(0, 2, 3, 1).reshape(C, 9 * C).to(dtype).cuda().contiguous()
+    out = o.pg_empty(N, H, W, C, dtype, "cuda")
+    resp = o.pg_from_nchw(res.detach().cuda(), torch.float32) if with_res else None
+    filmd = film.detach().cuda() if with_film else None
+    gd, bed, bd = g.detach().cuda(), be.detach().cuda(), b.detach().cuda()
+    _, saved = ot.conv3x3_ln_train(xp, Wt, bd, gd, bed, 1e-5, filmd, resp, out, N, H, W)
+    assert rel_err(o.pg_to_nchw(out, N, H, W), y) < (1e-4 if dtype == torch.float32 else 1.5e-2)
+    dyp = o.pg_from_nchw(dy.cuda(), torch.float32)
+    dconv, sums, _ = ot.conv_ln_bwd(dyp, saved, gd, filmd, 1e-5, N, H, W, dtype)
+    dg, db, dbias = (torch.zeros(C, device="cuda") for _ in range(3))
+    dfilm = ot.conv_ln_param_grads(sums, N, gd, bed, filmd, dg, db, dbias, with_film)
+    assert rel_err(dg, g.grad) < tol and rel_err(db, be.grad) < tol and rel_err(dbias, b.grad) < tol
+    if with_film:
+        assert rel_err(dfilm, film.grad) < tol
+    dW = torch.zeros(C, 9 * C, device="cuda")
+    ot.wgrad(dconv, xp, dW, ntaps=9, tap_shift=o.conv_tap_shifts(W), beta=0.0)
+    assert rel_err(dW.view(C, 9, C).permute(0, 2, 1).reshape(C, C, 3, 3), w.grad) < tol
+    Wd = w.detach().permute(1, 2, 3, 0).reshape(C, 9 * C).to(dtype).cuda().contiguous()          # [ci][tap][co]
+    dx = o.gemm(dconv, Wd, ntaps=9, tap_shift=tuple(-s for s in o.conv_tap_shifts(W)), out_f32=True)
+    assert rel_err(o.pg_to_nchw(dx, N, H, W), x.grad) < tol

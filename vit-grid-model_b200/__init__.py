@@ -9,5 +9,7 @@ from .maxvit import MaxViT, Attention, MBConv          # noqa: F401
 from .metnet3 import MetNet3                            # noqa: F401
 from .focal_r import FocalRLoss, focal_r_loss           # noqa: F401
 from ._lib import VitGridError                          # noqa: F401
+from .parallel import DataParallel                      # noqa: F401
+from .optim import FlatAdamW                            # noqa: F401
 
 __version__ = "0.1.0"

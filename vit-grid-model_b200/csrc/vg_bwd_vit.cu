@@ -183,7 +183,7 @@ template <> struct Ld4<bf16> {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128, 4) dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w9,
+__global__ void __launch_bounds__(128, 3) dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w9,
                                                            const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                                            T* __restrict__ out, float* __restrict__ psum, int H, int W, int C, int strips) {
   const int quads = C / 4;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) field_dot_kernel(const float* __restrict_
   if (p1 > HW) p1 = HW;
   for (int c = threadIdx.x; c < C; c += 256) {
     float s = 0.f;
-    for (long long p = p0; p < p1; ++p) { const long long i = ((long long)n * HW + p) * C + c; s = fmaf(a[i], b[i], s); }
+    for (long long p = p0; p < p1; ++p) { const long long i = ((long long)n * HW + p) * C + c; s = b ? fmaf(a[i], b[i], s) : s + a[i]; }
     atomicAdd(out + (long long)n * C + c, s);
   }
 }
@@ -712,6 +712,13 @@ int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const 
                       float* gate, float* mean, float* hid, cudaStream_t st) {
   se_gate_train_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(psum, nparts, 1.0f / (float)HW, W1, W2, C, se, gate, mean, hid);
   return check_launch("se_gate_train_kernel");
+}
+
+int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st) {
+  int chunks = (int)((HW + 127) / 128);
+  if (chunks > 16) chunks = 16;
+  field_dot_kernel<<<dim3(chunks, N), 256, 0, st>>>(a, b, out, HW, C);
+  return check_launch("field_dot_kernel");
 }
 
 int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st) {

@@ -38,10 +38,13 @@ struct WgradShape {
   int swap_lbo_sbo;            // debugging switch for the descriptor convention
 };
 
-// MN-major SWIZZLE_128B operand: 128-byte column groups `lbo` bytes apart, 8-row K groups `sbo` bytes apart
-__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+// MN-major 128-byte-swizzled operand: 128-byte column groups `lbo` bytes apart, K row groups `sbo` bytes apart.
+// 16-bit types: SWIZZLE_128B (layout type 2, 16-byte chunks XOR row%8, K groups of 8 rows).
+// 32-bit types (tf32): the only MN-major layout is SWIZZLE_128B_BASE32B (layout type 1: 32-byte chunks XOR row%4,
+// K groups of 4 rows), written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-         (1ull << 46) | (2ull << 61);
+         (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
 template <int TF32>
@@ -114,8 +117,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       // both operands MN-major (transpose bits 15 / 16)
       constexpr uint32_t idesc = (TF32 ? umma_idesc_tf32(128, 128) : umma_idesc_bf16(128, 128)) | (1u << 15) | (1u << 16);
       constexpr int KSTEP_ROWS = TF32 ? 8 : 16;                // rows consumed per MMA
-      const uint32_t lbo = ws.swap_lbo_sbo ? 1024u : (uint32_t)BOX_BYTES;
-      const uint32_t sbo = ws.swap_lbo_sbo ? (uint32_t)BOX_BYTES : 1024u;
+      constexpr uint32_t KGROUP_BYTES = TF32 ? 512u : 1024u;   // 4 rows (tf32) / 8 rows (bf16) of 128 bytes
+      constexpr uint32_t LAYOUT = TF32 ? 1u : 2u;
+      const uint32_t lbo = ws.swap_lbo_sbo ? KGROUP_BYTES : (uint32_t)BOX_BYTES;
+      const uint32_t sbo = ws.swap_lbo_sbo ? (uint32_t)BOX_BYTES : KGROUP_BYTES;
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < k_steps; ++kb) {
         mbar_wait(full + stage, phase);
@@ -126,8 +131,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           const uint32_t sa = sy + (1 + a) * TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < KT / KSTEP_ROWS; ++k) {
-            const uint64_t dy = umma_desc_mn128(sy + k * KSTEP_ROWS * 128, lbo, sbo);
-            const uint64_t da = umma_desc_mn128(sa + k * KSTEP_ROWS * 128, lbo, sbo);
+            const uint64_t dy = umma_desc_mn128(sy + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
+            const uint64_t da = umma_desc_mn128(sa + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
             if (TF32) tc_mma_tf32(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
             else tc_mma_bf16(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
           }
@@ -256,7 +261,7 @@ static int make_rows_map(CUtensorMap* m, bool f32, const void* ptr, long long in
   cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld", (int)r, inner, outer);
   return 0;

@@ -9,7 +9,8 @@ pipeline in ``MaxViT.forward_cl``:
   attention (block, then grid): gather+LN+FiLM -> QKV GEMM -> per-(window,head) core -> out-proj GEMM whose
             epilogue adds the residual and scatters through the inverse partition map.
 
-Only the eval-mode forward exists so far (BatchNorm uses running statistics, dropout is identity).
+This file holds the eval-mode forward (BatchNorm uses running statistics, dropout is identity); the train-mode
+forward / backward (batch statistics, saved activations) is in train.py.
 """
 from __future__ import annotations
 
@@ -159,6 +160,10 @@ class MaxViT(nn.Module):
             P["se_w2"] = seq[6].gate[3].weight.float().contiguous()
             P["w_proj"] = seq[7].weight.flatten(1).to(dtype).contiguous()                    # (dim, hidden)
             P["s_proj"], P["t_proj"] = _fold_bn(seq[7].bias, seq[8])
+            # training (batch-statistic BatchNorm: nothing is folded)
+            P["b_exp"], P["b_dw"], P["b_proj"] = (seq[i].bias.float().contiguous() for i in (0, 3, 7))
+            P["w_dw_flip"] = P["w_dw"].flip(0).contiguous()                                  # dgrad = correlation with flipped taps
+            P["ones_hid"], P["zeros_hid"] = torch.ones_like(P["b_dw"]), torch.zeros_like(P["b_dw"])
             for name, att in (("block", battn), ("grid", gattn)):
                 P[name] = dict(
                     film_w0=att.film[0].weight.float().contiguous(), film_b0=att.film[0].bias.float().contiguous(),
@@ -200,7 +205,8 @@ class MaxViT(nn.Module):
         """channels-last entry used by MetNet3: x (N,H,W,dim) in the compute dtype, cond (N,cond_dim) fp32"""
         _lib.require_device()
         if self.training:
-            raise NotImplementedError("training-mode forward (batch-stat BatchNorm, dropout, backward) is not built yet")
+            raise NotImplementedError("MaxViT.forward_cl is the inference path; training goes through MetNet3 in train() mode "
+                                      "(vit_grid_model_b200.train)")
         N, H, W, C = x.shape
         w = self.vit_window_size
         assert H % w == 0 and W % w == 0, "feature map must be divisible by the window size"
@@ -212,7 +218,7 @@ class MaxViT(nn.Module):
             hidden = h.shape[1]
             h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
             del h
-            gate = ops.se_gate(psum, W, P["se_w1"], P["se_w2"])
+            gate = ops.se_gate(psum, H * W, P["se_w1"], P["se_w2"])
             ops.se_scale_(h2, gate)
             y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
                          res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)

@@ -149,6 +149,9 @@ class MetNet3(nn.Module):
         self.max_fields = {torch.bfloat16: 768, torch.float32: 48}
         self._packed, self._packed_key = None, None
         self._capture = None          # debugging: set to a dict to collect stage outputs (NCHW copies)
+        self._grad_buffer = None      # training: flat fp32 gradient buffer (train.GradBuffer)
+        self._grad_sync = None        # training: data-parallel gradient all-reduce (set by parallel.DataParallel)
+        self.dropout = dropout
 
     # ------------------------------------------------------------------ helpers
     def set_precision(self, precision: str):
@@ -291,14 +294,30 @@ class MetNet3(nn.Module):
             ops.head(h, P["w_head"], P["b_head"], self.pm25_std, self.pm25_mean, N, HP, WP, self.input_height,
                      self.input_width, pads, out=out[b0:b1].view(N, self.input_height, self.input_width))
 
+    # ------------------------------------------------------------------ training
+    def grad_buffer(self):
+        """flat fp32 gradient buffer the backward kernels accumulate into (one view per parameter)"""
+        from .train import GradBuffer
+        dev = next(self.parameters()).device
+        if self._grad_buffer is None or self._grad_buffer.flat.device != dev:
+            self._grad_buffer = GradBuffer(self)
+        return self._grad_buffer
+
+    def _forward_train(self, x, ts):
+        """train() mode: batch-statistic BatchNorm, activations saved, hand-written backward (train.py)"""
+        from .train import MetNet3TrainFn
+        if self.precision == "bf16_all":
+            raise NotImplementedError("training supports set_precision('bf16') (mixed) and 'fp32'")
+        if self.dropout > 0:
+            raise NotImplementedError("attention dropout (maxvit.py:146,151) is not built yet: construct with dropout=0.0 to train")
+        return MetNet3TrainFn.apply(self, x, ts, *self.parameters())
+
     def forward(self, x, labels_pm25=None, region_targets_pm25=None, labels_pm10=None, region_targets_pm10=None,
                 timestamps: torch.Tensor = None, prev_vals: torch.Tensor = None):
         """x: (B,T,C,H,W) fp32; timestamps: (B, >=7, 4) [year, month, day, hour] -> (B, L, H, W) fp32 PM2.5"""
         _lib.require_device()
         if self._unsupported:
             raise NotImplementedError(self._unsupported)
-        if self.training:
-            raise NotImplementedError("training-mode forward/backward is not built yet; call .eval()")
         if timestamps is None:
             raise ValueError("timestamps is required (metnet3.py:405)")
         if not x.is_cuda:
@@ -311,6 +330,8 @@ class MetNet3(nn.Module):
         dtype = self.compute_dtype
         x = x.float()
         ts = timestamps.to(device=x.device, dtype=torch.float32)
+        if self.training:
+            return self._forward_train(x, ts)
         P = self.packed(dtype)
         L = self.end_lead_time
         s0 = P["resnet1"][0]

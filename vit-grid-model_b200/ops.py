@@ -104,9 +104,10 @@ def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per
     shifts = (ctypes.c_int * ntaps)(*tap_shift)
     keep, sp, sn = _scratch(dtype, M * Ntot, A.device, tf32)
     _lib.TRACE_TAG = f"M={M} K={ntaps}x{Ca} N={Ntot} {'tf32' if tf32 else str(dtype)[6:]}"
+    res_f32 = int(res is not None and res.dtype == torch.float32)
     _lib.call("vg_gemm_fwd", _gemm_code(dtype, tf32), A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
               rows_per_batch, b_rows_per_batch, _p(bias), _p(scale), _p(shift), act, _p(res),
-              res.shape[1] if res is not None else 0, out.data_ptr(), out.shape[1], int(out_f32), sp, sn, _st())
+              res.shape[1] if res is not None else 0, res_f32, out.data_ptr(), out.shape[1], int(out_f32), sp, sn, _st())
     return out
 
 
@@ -147,19 +148,28 @@ def pool2(x, N, HP, WP, out_dtype=None):
 
 
 def dw3x3_bnact(x, w9, scale, shift, out=None):
+    """depthwise 3x3 + folded BN + GELU (marching-stencil kernel); psum (N, strips, C) feeds the squeeze-excite mean"""
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if C % 4 == 0 and 128 % (C // 4) == 0:
+        strips = _lib.load().vg_dw_strips(W)
+        psum = torch.empty(N, strips, C, dtype=torch.float32, device=x.device)
+        _lib.call("vg_dw3x3_fwd", DT_CODE[x.dtype], x.data_ptr(), w9.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1,
+                  out.data_ptr(), psum.data_ptr(), N, H, W, C, _st())
+        return out, psum
     psum = torch.empty(N, H, C, dtype=torch.float32, device=x.device)
     _lib.call("vg_dw3x3_bnact_fwd", DT_CODE[x.dtype], x.data_ptr(), w9.data_ptr(), scale.data_ptr(), shift.data_ptr(),
               out.data_ptr(), psum.data_ptr(), N, H, W, C, _st())
     return out, psum
 
 
-def se_gate(psum, W, W1, W2):
-    N, H, C = psum.shape
+def se_gate(psum, HW, W1, W2):
+    """psum: (N, nparts, C) partial channel sums over the HW pixels of each field"""
+    N, nparts, C = psum.shape
     gate = torch.empty(N, C, dtype=torch.float32, device=psum.device)
-    _lib.call("vg_se_gate_fwd", psum.data_ptr(), N, H, W, W1.data_ptr(), W2.data_ptr(), C, W1.shape[0], gate.data_ptr(), _st())
+    _lib.call("vg_se_gate_train_fwd", psum.data_ptr(), N, nparts, HW, W1.data_ptr(), W2.data_ptr(), C, W1.shape[0],
+              gate.data_ptr(), None, None, _st())
     return gate
 
 
