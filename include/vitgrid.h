@@ -276,10 +276,12 @@ VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const
 /* attention backward (fp32): gradient at the out-projection output (inverse of the scatter + register rows) */
 VG_API int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
                            int R, int grid_mode, float* dproj, void* stream);
-/* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated */
+/* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated.  use_tf32 = 1 / 2: tensor-core
+ * kernel (1: tf32 mma; 2: bf16 mma + ldmatrix; fp32 accumulate), which can also re-materialise the forward output att = softmax(.) V [rows][inner]
+ * (att_out, or NULL) for the to_out weight gradient when the forward pass was the fused kernel; 0: exact-fp32 SIMT kernel. */
 VG_API int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, void* stream);
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, void* stream);
 /* LayerNorm + FiLM backward with the inverse partition; dx_in written (= dx + dx_out), dreg_in and dfilm accumulated */
 VG_API int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
                        const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in,

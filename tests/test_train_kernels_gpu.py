@@ -3,6 +3,7 @@
 Gradient tolerances: fp32 mode 1e-4 (relative to the largest reference entry), tf32 2e-3, bf16 1.5e-2.
 """
 import math
+import re
 
 import pytest
 import torch
@@ -110,3 +111,50 @@ def test_conv_block_backward(dtype, with_film, with_res):
     Wd = w.detach().permute(1, 2, 3, 0).reshape(C, 9 * C).to(dtype).cuda().contiguous()          # [ci][tap][co]
     dx = o.gemm(dconv, Wd, ntaps=9, tap_shift=tuple(-s for s in o.conv_tap_shifts(W)), out_f32=True)
     assert rel_err(o.pg_to_nchw(dx, N, H, W), x.grad) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_maxvit_block_backward(precision):
+    """MaxViT (depth 2: MBConv without and with residual, block + grid attention, register tokens) in train() mode:
+    forward and every gradient vs autograd through the CPU oracle (batch-statistic BatchNorm)."""
+    from oracle import synth
+    from oracle import maxvit_oracle as mo
+    from vit_grid_model_b200 import MaxViT
+    from vit_grid_model_b200 import train as tr
+    dim, depth, heads, dh, w, r, N, H, W = 128, 2, 32, 32, 7, 4, 3, 14, 21
+    sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, r), seed=5)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    x = rnd(N, dim, H, W, seed=12).requires_grad_(True)
+    cond = rnd(N, 2, seed=13).requires_grad_(True)
+    dy = rnd(N, dim, H, W, seed=14)
+    y = mo.maxvit_forward(x, cond, sd, depth=depth, heads=heads, window=w, num_reg=r, training=True)
+    y.backward(dy)
+    m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=r, dropout=0.0)
+    m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    m = m.cuda().train().set_precision(precision)
+    xc = x.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    condc = cond.detach().cuda()
+    with torch.no_grad():
+        yc, saved = tr.maxvit_train_forward(m, xc, condc)
+        G = {k: torch.zeros_like(p) for k, p in m.named_parameters()}
+        dcond = torch.zeros_like(condc)
+        dxc = tr.maxvit_train_backward(m, saved, condc, dcond, dy.permute(0, 2, 3, 1).contiguous().cuda(), G, "")
+    fp32 = precision == "fp32"
+    assert rel_err(yc.permute(0, 3, 1, 2), y) < (1e-4 if fp32 else 2e-2)
+    tol = 2e-3 if fp32 else 6e-2
+    bad = []
+    for name, got, ref in [("dx", dxc.permute(0, 3, 1, 2), x.grad), ("dcond", dcond, cond.grad)] + [(k, G[k], sd[k].grad) for k in G]:
+        g, rf = got.detach().float().cpu(), ref
+        if re.fullmatch(r"layers\.\d+\.0\.(fn\.)?[037]\.bias", name):
+            # conv bias in front of a batch-statistic BatchNorm: the gradient is analytically zero; both sides hold
+            # rounding noise only, which must stay far below the BatchNorm beta gradient next to it
+            beta = G[name[:-len("0.bias")] + str(int(name[-len("0.bias")]) + 1) + ".bias"].norm().item()
+            if g.norm().item() > 1e-3 * beta:
+                bad.append((name, g.norm().item(), beta))
+            continue
+        e = ((g - rf).norm() / max(rf.norm().item(), 1e-2)).item()
+        if e > tol:
+            bad.append((name, round(e, 5)))
+    assert not bad, bad

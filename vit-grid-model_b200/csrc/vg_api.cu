@@ -392,11 +392,11 @@ int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_sca
 
 int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, void* stream) {
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
   return attn_core_bwd_run(qkv, datt, q_gamma, k_gamma, bias_table, g, heads, dh, dqkv, dq_gamma, dk_gamma, dbias_table,
-                           (cudaStream_t)stream);
+                           use_tf32, att_out, (cudaStream_t)stream);
 }
 
 int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,

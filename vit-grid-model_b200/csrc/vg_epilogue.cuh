@@ -96,6 +96,67 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bo
   }
 }
 
+// EPI_STORE for the tcgen05 kernel: same math as epi_store, but the 32x32 block a warp reads from TMEM (one row per
+// thread) is transposed through a padded shared-memory tile so that every global access is a run of four full
+// 128-byte row segments per warp instruction instead of 32 scattered 16-byte pieces (the row-per-thread stores made
+// the wide 1x1 / projection GEMMs LSU-transaction-bound).  `row0` = global row of lane 0, `nvalid` = valid rows of
+// this warp's 32 (rows are consecutive), stg = this warp's [32][36] float tile.
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_store_coalesced(const EpiParams& ep, long long row0, int nvalid, int n0, Loader& ld,
+                                                    float* stg, int lane) {
+  constexpr int LDS_ = 36;                                 // row stride of the tile: 16-byte aligned, conflict-free for 128-bit access
+  float v[32];
+  const int rr = lane >> 3, cq = (lane & 7) * 4;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    const int c0 = n0 + ch * 32;
+    // this lane's four output columns are the same for every row of the transposed phase: fetch their parameters once
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 < ep.n_total) {
+      if (ep.col_scale) { sc = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + cq)); sh = __ldg(reinterpret_cast<const float4*>(ep.col_shift + c0 + cq)); }
+      else if (ep.bias) sh = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + cq));
+    }
+    ld.load(ch, v);
+    if (c0 >= ep.n_total) continue;                       // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * LDS_ + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rr;
+      if (r < nvalid) {
+        const long long row = row0 + r;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS_ + cq);
+        float o[4] = {fmaf(a4.x, sc.x, sh.x), fmaf(a4.y, sc.y, sh.y), fmaf(a4.z, sc.z, sh.z), fmaf(a4.w, sc.w, sh.w)};
+        if (ep.act == 1) { o[0] = gelu_erf(o[0]); o[1] = gelu_erf(o[1]); o[2] = gelu_erf(o[2]); o[3] = gelu_erf(o[3]); }
+        else if (ep.act == 2) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        if (ep.res) {
+          if (ep.res_f32 || sizeof(T) == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res) + row * ep.ldres + c0 + cq);
+            o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
+          } else {
+            const bf16* q = reinterpret_cast<const bf16*>(ep.res) + row * ep.ldres + c0 + cq;
+            const uint2 u = *reinterpret_cast<const uint2*>(q);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+          }
+        }
+        const long long off = row * ep.ldo + c0 + cq;
+        const bool f32out = ep.out_f32 == 1 || (ep.out_f32 == 0 && sizeof(T) == 4);
+        if (f32out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+          uint2 u;
+          *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(o[0], o[1]);
+          *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(o[2], o[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + off) = u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Per-channel parameters of the conv epilogue; the tcgen05 kernel stages them in shared memory once per CTA,
 // the fp32-mode row kernel points them at global memory.
 struct EpiCtx {

@@ -29,6 +29,11 @@ constexpr int B_BYTES = BN * BK * 2;                          // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                // 48 KiB
 constexpr int PARAM_FLOATS = 3 * 128 + 2 * 2 * 256;           // conv epilogue: bias | ln_g | ln_b | per-WG folded FiLM affine [2 fields][256]
 constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_FLOATS * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+// EPI_STORE kernels are epilogue / HBM-bound: 3 stages, and the freed space holds the 8 per-warp [32][33] fp32 tiles the
+// coalesced store epilogue transposes through ([32][36] each)
+constexpr int STORE_STAGES = 3;
+constexpr int STORE_STG_FLOATS = 8 * 32 * 36;
+constexpr int TC_SMEM_BYTES_STORE = STORE_STAGES * STAGE_BYTES + STORE_STG_FLOATS * 4 + 1024 + 256;
 constexpr int TMEM_COLS = 512;                                // 2 tiles in flight x 2 row halves x 128 fp32 columns
 constexpr int TC_THREADS = 384;                               // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue WGs
 
@@ -47,10 +52,12 @@ template <int KIND, int TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmShape gs, const EpiParams ep) {
+  constexpr int STAGES = KIND == EPI_STORE ? STORE_STAGES : vg::STAGES;
+  constexpr int PARAM_BYTES = KIND == EPI_STORE ? STORE_STG_FLOATS * 4 : PARAM_FLOATS * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sparam = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PARAM_FLOATS * 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PARAM_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -161,8 +168,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
       TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
-      if (TF32) run_epilogue<KIND, float>(ep, cx, row, ok, n_tile * BN, ld);
-      else run_epilogue<KIND, bf16>(ep, cx, row, ok, n_tile * BN, ld);
+      if constexpr (KIND == EPI_STORE) {
+        // rows of this warp are consecutive: lane 0 holds lrow - lane
+        const long long lrow0 = lrow - lane;
+        long long nv = gs.rows_per_batch - lrow0;
+        const long long nv2 = gs.M - ((long long)batch * gs.rows_per_batch + lrow0);
+        if (nv2 < nv) nv = nv2;
+        const int nvalid = nv < 0 ? 0 : (nv > 32 ? 32 : (int)nv);
+        float* stg = sparam + (warp - 4) * (32 * 36);
+        if (TF32) epi_store_coalesced<float>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+        else epi_store_coalesced<bf16>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+      } else {
+        if (TF32) run_epilogue<KIND, float>(ep, cx, row, ok, n_tile * BN, ld);
+        else run_epilogue<KIND, bf16>(ep, cx, row, ok, n_tile * BN, ld);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
@@ -440,14 +459,15 @@ static int num_sms() {
 template <int KIND, int TF32>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
   static bool attr_set = false;
+  constexpr int SMEM = KIND == EPI_STORE ? TC_SMEM_BYTES_STORE : TC_SMEM_BYTES;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int total = gs.num_m_tiles * gs.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<KIND, TF32><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma, mb, gs, ep);
+  gemm_tc_kernel<KIND, TF32><<<grid, TC_THREADS, SMEM, st>>>(ma, mb, gs, ep);
   return check_launch("gemm_tc_kernel");
 }
 

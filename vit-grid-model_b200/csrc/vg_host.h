@@ -144,7 +144,7 @@ int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float
 int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, cudaStream_t st);
 int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
                       const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
-                      cudaStream_t st);
+                      int use_tf32, float* att_out, cudaStream_t st);
 int attn_gather_bwd_run(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
                         const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in, float* dfilm,
                         const AttnGeom& g, float eps, cudaStream_t st);

@@ -3,6 +3,7 @@ PyTorch supplies device memory and streams; every computation is a libvitgrid ke
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -243,12 +244,17 @@ def attn_out_bwd_gather(dx_out, dreg, reg_scale, win, R, grid_mode):
     return dproj
 
 
-def attn_core_bwd(qkv, datt, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, dq_gamma, dk_gamma, dbias_table):
+def attn_core_bwd(qkv, datt, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, dq_gamma, dk_gamma, dbias_table,
+                  tf32=False, want_att=False):
+    """-> dqkv (, att = softmax(.) V re-materialised by the tensor-core kernel when want_att)"""
     dqkv = torch.empty_like(qkv)
+    att = torch.empty(qkv.shape[0], heads * dh, dtype=torch.float32, device=qkv.device) if want_att else None
+    # tensor-core variants: 2 = bf16 mma + ldmatrix (default), 1 = tf32 mma (VG_ATTN_BWD=tf32); 0 = exact-fp32 SIMT
+    mode = 0 if not tf32 else (1 if os.environ.get("VG_ATTN_BWD", "bf16") == "tf32" else 2)
     _lib.call("vg_attn_core_bwd", qkv.data_ptr(), datt.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
               bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, dqkv.data_ptr(), dq_gamma.data_ptr(), dk_gamma.data_ptr(),
-              dbias_table.data_ptr(), _st())
-    return dqkv
+              dbias_table.data_ptr(), mode, _p(att), _st())
+    return (dqkv, att) if want_att else dqkv
 
 
 def attn_gather_bwd(x, reg, film, dtok, dx_out, dreg_res, reg_scale, dreg_in, dfilm, win, R, grid_mode, eps=1e-5):

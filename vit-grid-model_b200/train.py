@@ -110,9 +110,20 @@ def _unpack_wgrad3x3(dWt, co, ci_pad, ci):
 
 
 # ------------------------------------------------------------------------------------------------ MaxViT block
+def _fused_ok(vit, C):
+    return (vit.fused_attention and vit.tf32 and C == 128 and vit.dim_head == 32 and vit.vit_window_size == 7
+            and vit.num_register_tokens == 4)
+
+
 def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out):
+    """mixed precision: the fused one-kernel attention, nothing but its inputs is kept (backward re-materialises
+    tokens / qkv / att on the tensor cores); fp32 mode: unfused path, intermediates saved."""
     N, H, W, C = x.shape
     w, R = vit.vit_window_size, vit.num_register_tokens
+    if _fused_ok(vit, C):
+        x_out, reg_out = ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
+                                        vit.heads, vit.dim_head)
+        return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, grid_mode=grid_mode)
     tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
     qkv = ops.gemm(tokens, P["w_qkv"], tf32=vit.tf32)
     att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head)
@@ -127,16 +138,24 @@ def _attention_train_bwd(vit, sv, P, att_mod, pre, G, cond, dcond, dx_out, dreg_
     w, R = vit.vit_window_size, vit.num_register_tokens
     tf32 = vit.tf32
     gm = sv["grid_mode"]
+    recompute = "qkv" not in sv
+    if recompute:
+        tokens = ops.attn_gather(x, sv["reg_in"], sv["film"], w, R, gm)
+        qkv = ops.gemm(tokens, P["w_qkv"], tf32=tf32)
+    else:
+        tokens, qkv = sv["tokens"], sv["qkv"]
     dproj = ot.attn_out_bwd_gather(dx_out, dreg_res, reg_scale, w, R, gm)
-    ot.wgrad(dproj, sv["att"], G[pre + "to_out.0.weight"], tf32=tf32)
     datt = ops.gemm(dproj, att_mod.to_out[0].weight.detach().t().contiguous(), tf32=tf32)
-    del dproj
-    dqkv = ot.attn_core_bwd(sv["qkv"], datt, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads,
-                            vit.dim_head, G[pre + "q_norm.gamma"], G[pre + "k_norm.gamma"], G[pre + "rel_pos_bias.weight"])
-    del datt
-    ot.wgrad(dqkv, sv["tokens"], G[pre + "to_qkv.weight"], tf32=tf32)
+    res = ot.attn_core_bwd(qkv, datt, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head,
+                           G[pre + "q_norm.gamma"], G[pre + "k_norm.gamma"], G[pre + "rel_pos_bias.weight"], tf32=tf32,
+                           want_att=recompute)
+    dqkv, att = res if recompute else (res, sv["att"])
+    del datt, qkv
+    ot.wgrad(dproj, att, G[pre + "to_out.0.weight"], tf32=tf32)
+    del dproj, att
+    ot.wgrad(dqkv, tokens, G[pre + "to_qkv.weight"], tf32=tf32)
     dtok = ops.gemm(dqkv, att_mod.to_qkv.weight.detach().t().contiguous(), tf32=tf32)
-    del dqkv
+    del dqkv, tokens
     dfilm = torch.zeros(N, 2 * C, dtype=torch.float32, device=x.device)
     dx_in = ot.attn_gather_bwd(x, sv["reg_in"], sv["film"], dtok, dx_out, dreg_res, reg_scale, dreg_in, dfilm, w, R, gm)
     ot.cond_mlp_bwd(cond, P["film_w0"], P["film_b0"], P["film_w1"], dfilm, G[pre + "film.0.weight"], G[pre + "film.0.bias"],
