@@ -30,7 +30,7 @@ os.environ["VG_ATTN_DBG"] = hex(dbg.data_ptr())
 ops.attn_fused(x, reg, film, wqkv, wout, tab, w, R, False, True, heads, dh)
 torch.cuda.synchronize()
 d = dbg.cpu().view(heads, 8)
-names = ["table+bar", "wait qkv_done", "step2 (norm, stores)", "wait s_done", "step4 (softmax)", "wait o_done(+pair)", "step6"]
+names = ["wait tables", "wait qkv_done", "step2 (norms, K, V stores)", "wait s_done", "softmax + P", "-", "-"]
 delta = (d[:, 1:] - d[:, :-1]).float()
 print("head period (cycles):", (d[1:, 0] - d[:-1, 0]).float()[2:].mean().item())
 for i, nm in enumerate(names):

@@ -4,18 +4,19 @@
 // Nothing between the residual stream in and the residual stream out touches HBM:
 //
 //   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (smem, tf32)
-//   per head h (weights streamed by TMA, double use of TMEM):
+//   per head h (weights and the per-head tables streamed by TMA, accumulators re-used as operands in TMEM):
 //     QKV_h = X * Wqkv_h^T           tcgen05 kind::tf32  M128 N96  K128      -> TMEM
-//     q,k RMSNorm (* sqrt(d) * gamma) in registers; Q^,K^ (tf32) and V^T (bf16) -> smem
-//     S = Q^ K^^T                    tcgen05 kind::tf32  M128 N128 K32       -> TMEM (both windows; off-diagonal unused)
-//     + relative-position bias (index computed arithmetically), masked softmax in registers; P (bf16) -> smem
+//     k RMSNorm in registers: K" = k * (32 gq gk) / |k| (tf32) and V^T (bf16) -> smem; q stays in TMEM, 1/|q| per row
+//     S = q K"^T                     tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the q accumulator)
+//     S/|q| + relative-position bias (index computed arithmetically), masked softmax in registers;
+//     P / rowsum (bf16) -> smem
 //     O_h = P V                      tcgen05 kind::f16   M128 N32  K128      -> TMEM
-//     O_h / rowsum (tf32) -> smem
-//     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32       -> TMEM, accumulated over heads
+//     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the O accumulator),
+//                                    accumulated over heads
 //   epilogue: Out + residual, scattered back through the inverse partition map; register-token rows to reg_out.
 //
-// Warp roles: warp 0 = TMA (weights), warp 1 = MMA issuer, warps 2..5 = 128 compute threads (thread <-> token row
-// <-> TMEM lane).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
+// Warp roles: warp 0 = TMA (weights, tables), warp 1 = MMA issuer, warps 2..9 = 256 compute threads (two per token row
+// = TMEM lane).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
 #include <stdlib.h>
 
 #include "vg_common.cuh"
@@ -32,9 +33,9 @@ constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specia
 constexpr int X_OFF = 0;                         // 4 k-blocks x [128 rows x 128 B]
 constexpr int WQ_OFF = X_OFF + 4 * 16384;        // 4 k-blocks x [96 rows x 128 B]
 constexpr int WO_OFF = WQ_OFF + 4 * 12288;       // [128 rows x 128 B]
-constexpr int R1_OFF = WO_OFF + 16384;           // 2 x 32 KiB: Q^ | K^  ->  P (2 k-blocks)  ->  O
+constexpr int R1_OFF = WO_OFF + 16384;           // 2 x 32 KiB: K" (first 16 KiB)  ->  P (2 k-blocks of 16 KiB)
 constexpr int VT_OFF = R1_OFF + 2 * 32768;       // 2 x [2 k-blocks x 32 rows x 128 B]
-constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | q gamma | k gamma
+constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
 constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
 constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
 constexpr int BAR_OFF = RED_OFF + 4 * 1024;
@@ -95,6 +96,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is an fp32 accumulator read in place as tf32 (lanes = rows, one column per k)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// plain (non-tensor) TMA copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // named barriers: 1 = all 256 compute threads, 2..5 = the two warps that share a TMEM lane group
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void pair_sync(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory"); }
@@ -111,11 +125,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   uint64_t* x_ready = bars + 4;
   uint64_t* qkv_done = bars + 5;                 // [2]
   uint64_t* qk_ready = bars + 7; uint64_t* s_done = bars + 8;
-  uint64_t* p_ready = bars + 9;  uint64_t* o_done = bars + 10;
-  uint64_t* osm_ready = bars + 11;
-  uint64_t* out_done = bars + 12;                // [2]
-  uint64_t* tile_done = bars + 14; uint64_t* out_free = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* p_ready = bars + 9;
+  uint64_t* pv_done = bars + 10;                 // [2]  R1[r] / VT[r] no longer read by MMAs
+  uint64_t* tile_done = bars + 12; uint64_t* out_free = bars + 13;
+  uint64_t* tab_full = bars + 14;                // [2]
+  uint64_t* tab_free = bars + 16;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -125,9 +140,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     mbar_init(wq_full, 1); mbar_init(wq_free, 1); mbar_init(wo_full, 1); mbar_init(wo_free, 1);
     mbar_init(x_ready, 8);
     mbar_init(qkv_done + 0, 1); mbar_init(qkv_done + 1, 1);
-    mbar_init(qk_ready, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8); mbar_init(o_done, 1); mbar_init(osm_ready, 8);
-    mbar_init(out_done + 0, 1); mbar_init(out_done + 1, 1);
+    mbar_init(qk_ready, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8);
+    mbar_init(pv_done + 0, 1); mbar_init(pv_done + 1, 1);
     mbar_init(tile_done, 1); mbar_init(out_free, 8);
+    mbar_init(tab_full + 0, 1); mbar_init(tab_full + 1, 1); mbar_init(tab_free + 0, 8); mbar_init(tab_free + 1, 8);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -148,6 +164,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       uint32_t it = 0;                                       // global head counter
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int h = 0; h < heads; ++h, ++it) {
+          const uint32_t r = it & 1;
+          mbar_wait(tab_free + r, ((it >> 1) & 1) ^ 1);       // the compute warps are done with the tables of head it-2
+          mbar_arrive_expect_tx(tab_full + r, TAB_FLOATS * 4);
+          bulk_load(smem + TAB_OFF + r * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + r);
           mbar_wait(wq_free, (it & 1) ^ 1);
           mbar_arrive_expect_tx(wq_full, 4 * 12288);
 #pragma unroll
@@ -187,13 +207,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         for (int h = 0; h < heads; ++h, ++it) {
           const uint32_t r = it & 1;
           const uint32_t sR1 = smem_u32(smem + R1_OFF + r * 32768), sVT = smem_u32(smem + VT_OFF + r * 8192);
-          // ---- S = Q^ K^^T
+          // ---- S = q K"^T  (A = the q accumulator of this head, read from TMEM)
           mbar_wait(qk_ready, it & 1);
           tc_fence_after();
           {
-            const uint64_t da = umma_desc_k128(sR1), db = umma_desc_k128(sR1 + 16384);
+            const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
+            const uint64_t db = umma_desc_k128(sR1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem + T_S, da + 2 * k, db + 2 * k, id_s, k ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
           }
           tc_commit(s_done);
           // ---- next head's QKV projection runs under this head's softmax
@@ -207,18 +228,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + T_O, da + 2 * k, db + 2 * k, id_pv, (kb | k) ? 1u : 0u);
           }
-          tc_commit(o_done);
-          // ---- Out += O_h Wout_h^T
-          mbar_wait(osm_ready, it & 1);
+          tc_commit(pv_done + r);
+          // ---- Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM; P was normalised before the PV product)
           mbar_wait(wo_full, it & 1);
           if (h == 0) mbar_wait(out_free, (tl & 1) ^ 1);     // previous tile's epilogue has drained Out
           tc_fence_after();
           {
-            const uint64_t da = umma_desc_k128(sR1), db = umma_desc_k128(sWO);
+            const uint64_t db = umma_desc_k128(sWO);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem + T_OUT, da + 2 * k, db + 2 * k, id_out, (h | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * k, db + 2 * k, id_out, (h | k) ? 1u : 0u);
           }
-          tc_commit(out_done + r);
           tc_commit(wo_free);
         }
         tc_commit(tile_done);
@@ -310,43 +329,41 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const uint32_t R1 = s_base + R1_OFF + r * 32768;
         const uint32_t VT = s_base + VT_OFF + r * 8192;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
-        // per-head tables (shifted relative-position bias rows, q/k gamma): global (L2) -> smem
-        {
-          const float* gt = p.head_tab + (long long)h * TAB_FLOATS;
-          float* st = reinterpret_cast<float*>(smem + TAB_OFF) + r * TAB_FLOATS;
-          for (int k = ctid; k < TAB_FLOATS; k += 256) st[k] = __ldg(gt + k);
-        }
-        compute_bar_sync();
+        mbar_wait(tab_full + r, (it >> 1) & 1);                          // per-head tables (TMA)
         if (dbg) p.dbg[h * 8 + 1] = clock64();
-        // ---------------- QKV_h: TMEM -> registers, RMSNorm, -> smem operands ----------------
+        // ---------------- QKV_h: 1/|q| (q itself stays in TMEM), K" and V^T -> smem operands ----------------
         mbar_wait(qkv_done + r, (it >> 1) & 1);
-        if (it >= 2) mbar_wait(out_done + r, ((it - 2) >> 1) & 1);      // R1[r] / VT[r] no longer read by MMAs
+        if (it >= 2) mbar_wait(pv_done + r, ((it - 2) >> 1) & 1);        // R1[r] / VT[r] no longer read by MMAs
         tc_fence_after();
         if (dbg) p.dbg[h * 8 + 2] = clock64();
+        float inv_q;
         {
           const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
-          float v[32], vv[16];
-          tmem_ld32(tq + ch * 32, v);                                    // ch 0: q, ch 1: k
-          tmem_ld16(tq + 64 + ch * 16, vv);                              // half of v
+          float v[32], w[32];
+          tmem_ld32(tq, v);                                              // q: both threads of the row need its norm
+          tmem_ld32(tq + 32 + ch * 32, w);                               // ch 0: k, ch 1: v
           tmem_wait_ld();
-          float nrm = 0.f;
+          float nq = 0.f;
 #pragma unroll
-          for (int d = 0; d < 32; ++d) nrm += v[d] * v[d];
-          const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);              // F.normalize(eps=1e-12) * sqrt(d)  (maxvit.py:30)
-          const uint32_t gam = tab + (7 * 13 * 8 + 8 + ch * 32) * 4;
-          const uint32_t dst = R1 + ch * 16384;
+          for (int d = 0; d < 32; ++d) nq = fmaf(v[d], v[d], nq);
+          inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);                       // F.normalize(eps=1e-12)  (maxvit.py:30)
+          if (ch == 0) {
+            float nk = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 gm = lds128(gam + c * 16);
-            sts128(dst + swz[c], v[4 * c] * inv * gm.x, v[4 * c + 1] * inv * gm.y, v[4 * c + 2] * inv * gm.z, v[4 * c + 3] * inv * gm.w);
-          }
-          // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
-          const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
-          const int kc = (t & 63) >> 3;
+            for (int d = 0; d < 32; ++d) nk = fmaf(w[d], w[d], nk);
+            const float inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
+            const uint32_t ksc = tab + (7 * 13 * 8 + 8) * 4;             // 32 * gamma_q * gamma_k
 #pragma unroll
-          for (int d = 0; d < 16; ++d) {
-            const int dd = ch * 16 + d;
-            sts16(vt + sw128(dd, kc), __bfloat16_as_ushort(__float2bfloat16(vv[d])));
+            for (int c = 0; c < 8; ++c) {
+              const float4 gm = lds128(ksc + c * 16);
+              sts128(R1 + swz[c], w[4 * c] * inv_k * gm.x, w[4 * c + 1] * inv_k * gm.y, w[4 * c + 2] * inv_k * gm.z, w[4 * c + 3] * inv_k * gm.w);
+            }
+          } else {
+            // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
+            const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
+            const int kc = (t & 63) >> 3;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) sts16(vt + sw128(d, kc), __bfloat16_as_ushort(__float2bfloat16(w[d])));
           }
         }
         tc_fence_before();
@@ -355,7 +372,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         if (lane == 0) mbar_arrive(qk_ready);
         if (dbg) p.dbg[h * 8 + 3] = clock64();
 
-        // ---------------- S half-row: + bias, masked softmax -> P (bf16) ----------------
+        // ---------------- S half-row: / |q|, + bias, masked softmax -> normalised P (bf16) ----------------
         mbar_wait(s_done, it & 1);
         tc_fence_after();
         if (dbg) p.dbg[h * 8 + 4] = clock64();
@@ -369,14 +386,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (ch == 0) {
             // keys 0..3 are register tokens, keys 4..31 are window rows aj = 0..3
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sc[j] += t169;
+            for (int j = 0; j < 4; ++j) sc[j] = fmaf(sc[j], inv_q, t169);
 #pragma unroll
             for (int aj = 0; aj < 4; ++aj) {
               const uint32_t a = brow + (ai + 6 - aj) * 32;
               const float4 b0 = lds128(a), b1 = lds128(a + 16);
               float* q = sc + 4 + aj * 7;
-              q[0] += is_reg ? t169 : b0.x; q[1] += is_reg ? t169 : b0.y; q[2] += is_reg ? t169 : b0.z; q[3] += is_reg ? t169 : b0.w;
-              q[4] += is_reg ? t169 : b1.x; q[5] += is_reg ? t169 : b1.y; q[6] += is_reg ? t169 : b1.z;
+              q[0] = fmaf(q[0], inv_q, is_reg ? t169 : b0.x); q[1] = fmaf(q[1], inv_q, is_reg ? t169 : b0.y);
+              q[2] = fmaf(q[2], inv_q, is_reg ? t169 : b0.z); q[3] = fmaf(q[3], inv_q, is_reg ? t169 : b0.w);
+              q[4] = fmaf(q[4], inv_q, is_reg ? t169 : b1.x); q[5] = fmaf(q[5], inv_q, is_reg ? t169 : b1.y);
+              q[6] = fmaf(q[6], inv_q, is_reg ? t169 : b1.z);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) m = fmaxf(m, sc[j]);
@@ -387,12 +406,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
               const uint32_t a = brow + (ai + 6 - aj) * 32;
               const float4 b0 = lds128(a), b1 = lds128(a + 16);
               float* q = sc + (aj - 4) * 7;
-              q[0] += is_reg ? t169 : b0.x; q[1] += is_reg ? t169 : b0.y; q[2] += is_reg ? t169 : b0.z; q[3] += is_reg ? t169 : b0.w;
-              q[4] += is_reg ? t169 : b1.x; q[5] += is_reg ? t169 : b1.y; q[6] += is_reg ? t169 : b1.z;
+              q[0] = fmaf(q[0], inv_q, is_reg ? t169 : b0.x); q[1] = fmaf(q[1], inv_q, is_reg ? t169 : b0.y);
+              q[2] = fmaf(q[2], inv_q, is_reg ? t169 : b0.z); q[3] = fmaf(q[3], inv_q, is_reg ? t169 : b0.w);
+              q[4] = fmaf(q[4], inv_q, is_reg ? t169 : b1.x); q[5] = fmaf(q[5], inv_q, is_reg ? t169 : b1.y);
+              q[6] = fmaf(q[6], inv_q, is_reg ? t169 : b1.z);
             }
 #pragma unroll
             for (int j = 0; j < 21; ++j) m = fmaxf(m, sc[j]);
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tab_free + r);                      // last read of this head's tables
           red[(2 * 128 + t) * 2 + ch] = m;
           pair_sync(lg);
           m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]) * LOG2E;
@@ -403,12 +426,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             sc[j] = e; sum += e;
           }
           red[(0 * 128 + t) * 2 + ch] = sum;
+          pair_sync(lg);                                                 // partner's partial row sum is visible
+          const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
           // own 32 keys = chunks [ch*4, +4) of this row in k-block `half`; same chunks of the other k-block are zero
           const uint32_t prow = R1 + half * 16384, zrow = R1 + (half ^ 1) * 16384;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
-                    pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
+            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c] * inv_sum, sc[8 * c + 1] * inv_sum),
+                    pack_bf16(sc[8 * c + 2] * inv_sum, sc[8 * c + 3] * inv_sum),
+                    pack_bf16(sc[8 * c + 4] * inv_sum, sc[8 * c + 5] * inv_sum),
+                    pack_bf16(sc[8 * c + 6] * inv_sum, sc[8 * c + 7] * inv_sum));
             sts128u(zrow + swz[ch * 4 + c], 0u, 0u, 0u, 0u);
           }
         }
@@ -416,27 +443,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        if (dbg) p.dbg[h * 8 + 5] = clock64();
-        pair_sync(lg);                                                   // partner's partial row sum is visible
-        const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
-
-        // ---------------- O_h / rowsum -> smem (tf32) ----------------
-        mbar_wait(o_done, it & 1);
-        tc_fence_after();
-        if (dbg) p.dbg[h * 8 + 6] = clock64();
-        {
-          float o[16];
-          tmem_ld16(lane_addr + T_O + ch * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            sts128(R1 + swz[ch * 4 + c], o[4 * c] * inv_sum, o[4 * c + 1] * inv_sum, o[4 * c + 2] * inv_sum, o[4 * c + 3] * inv_sum);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(osm_ready);
-        if (dbg) p.dbg[h * 8 + 7] = clock64();
+        if (dbg) { const long long c5 = clock64(); p.dbg[h * 8 + 5] = c5; p.dbg[h * 8 + 6] = c5; p.dbg[h * 8 + 7] = c5; }
       }
 
       // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------

@@ -214,7 +214,8 @@ def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None
 def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     """per-head table of the fused attention kernel: relative-position bias as `win` pre-shifted copies
     [bi][row 0..2w-2][8] with entry k = table[row*(2w-1) + bi + (w-1) - k] (so that the 7 keys of one window row are one
-    aligned 32-byte read), then table[(2w-1)^2] (+7 pad), q gamma[dh], k gamma[dh].  bias_table: (nb, heads)."""
+    aligned 32-byte read), then table[(2w-1)^2] (+7 pad), dh * gamma_q * gamma_k [dh] (the two RMSNorm gains and the two
+    sqrt(dh) factors of maxvit.py:26-30 folded into the key operand), dh unused.  bias_table: (nb, heads)."""
     assert win == 7, "the fused kernel is specialised for 7x7 windows"
     heads, w2 = bias_table.shape[1], 2 * win - 1
     bi = torch.arange(win).view(win, 1, 1)
@@ -226,8 +227,8 @@ def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     shifted[..., 7] = 0
     t_last = torch.zeros(heads, 8, device=T.device)
     t_last[:, 0] = T[:, w2 * w2]
-    return torch.cat([shifted.reshape(heads, -1), t_last, q_gamma.float().reshape(heads, -1),
-                      k_gamma.float().reshape(heads, -1)], dim=1).contiguous()
+    qg, kg = q_gamma.float().reshape(heads, -1), k_gamma.float().reshape(heads, -1)
+    return torch.cat([shifted.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
 
 
 def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5):
