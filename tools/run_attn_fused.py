@@ -25,14 +25,22 @@ for _ in range(iters):
     print(f"N={N} windows={N*30} ms={e0.elapsed_time(e1):.3f}")
 
 # per-phase clock stamps of one compute thread (CTA 0, first tile)
-dbg = torch.zeros(heads * 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2 * heads * 8, dtype=torch.int64, device="cuda")
 os.environ["VG_ATTN_DBG"] = hex(dbg.data_ptr())
 ops.attn_fused(x, reg, film, wqkv, wout, tab, w, R, False, True, heads, dh)
 torch.cuda.synchronize()
-d = dbg.cpu().view(heads, 8)
-names = ["wait tables", "wait qkv_done", "step2 (norms, K, V stores)", "wait s_done", "softmax + P", "-", "-"]
+dall = dbg.cpu().view(2, heads, 8)
+d = dall[0]
+names = ["step2(h+1) (norms, K, V stores)", "wait tables", "-", "wait s_done", "softmax + P", "-", "-"]
 delta = (d[:, 1:] - d[:, :-1]).float()
 print("head period (cycles):", (d[1:, 0] - d[:-1, 0]).float()[2:].mean().item())
 for i, nm in enumerate(names):
     print(f"  {nm:24s} {delta[2:, i].mean().item():8.0f}")
 print("  next-head gap           ", (d[1:, 0] - d[:-1, 7]).float()[2:].mean().item())
+
+m = dall[1]
+mn = ["wait p_ready", "issue S(h+1)", "issue PV", "wait WO", "issue out", "issue QKV(h+3) (incl. wait WQ)", "-"]
+md = (m[:, 1:] - m[:, :-1]).float()
+print("MMA warp, head period:", (m[1:, 0] - m[:-1, 0]).float()[2:-2].mean().item())
+for i, nm in enumerate(mn):
+    print(f"  {nm:32s} {md[2:-2, i].mean().item():8.0f}")

@@ -124,7 +124,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   uint64_t* wo_full = bars + 2;  uint64_t* wo_free = bars + 3;
   uint64_t* x_ready = bars + 4;
   uint64_t* qkv_done = bars + 5;                 // [2]
-  uint64_t* qk_ready = bars + 7; uint64_t* s_done = bars + 8;
+  uint64_t* qk_ready = bars + 20;                // [2]: one per operand buffer (the compute warps run one head ahead of the MMA warp)
+  uint64_t* s_done = bars + 8;
   uint64_t* p_ready = bars + 9;
   uint64_t* pv_done = bars + 10;                 // [2]  R1[r] / VT[r] no longer read by MMAs
   uint64_t* tile_done = bars + 12; uint64_t* out_free = bars + 13;
@@ -140,7 +141,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     mbar_init(wq_full, 1); mbar_init(wq_free, 1); mbar_init(wo_full, 1); mbar_init(wo_free, 1);
     mbar_init(x_ready, 8);
     mbar_init(qkv_done + 0, 1); mbar_init(qkv_done + 1, 1);
-    mbar_init(qk_ready, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8);
+    mbar_init(qk_ready + 0, 8); mbar_init(qk_ready + 1, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8);
     mbar_init(pv_done + 0, 1); mbar_init(pv_done + 1, 1);
     mbar_init(tile_done, 1); mbar_init(out_free, 8);
     mbar_init(tab_full + 0, 1); mbar_init(tab_full + 1, 1); mbar_init(tab_free + 0, 8); mbar_init(tab_free + 1, 8);
@@ -154,28 +155,45 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);        // warp-uniform: lets the MMA issue use uniform registers (no per-MMA elect/broadcast loop)
 
   const long long n_tiles = (p.n_windows + 1) / 2;
 
   if (warp == 0) {
-    // ============================== TMA: stream the per-head weights ==============================
+    // ============================== TMA: stream the per-head weights and bias tables ==============================
+    // Program order follows the order in which the MMA warp needs the data: the QKV weights run two heads ahead of the
+    // out-projection weights (a load that waited for out(j-1) in front of WQ(j+2) would dead-lock the MMA warp, which issues
+    // QKV(j+2) before out(j)).
     if (lane == 0) {
-      uint32_t it = 0;                                       // global head counter
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int h = 0; h < heads; ++h, ++it) {
-          const uint32_t r = it & 1;
-          mbar_wait(tab_free + r, ((it >> 1) & 1) ^ 1);       // the compute warps are done with the tables of head it-2
-          mbar_arrive_expect_tx(tab_full + r, TAB_FLOATS * 4);
-          bulk_load(smem + TAB_OFF + r * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + r);
-          mbar_wait(wq_free, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(wq_full, 4 * 12288);
+      long long my_tiles = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++my_tiles;
+      const long long total = my_tiles * heads;
+      auto load_wq = [&](long long j) {
+        const int h = (int)(j % heads);
+        mbar_wait_tag(wq_free, (uint32_t)((j & 1) ^ 1), 172);
+        mbar_arrive_expect_tx(wq_full, 4 * 12288);
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + WQ_OFF + kb * 12288, &mapWq, wq_full, kb * 32, h * 96);
-          mbar_wait(wo_free, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(wo_full, 16384);
-          tma_load_2d(smem + WO_OFF, &mapWo, wo_full, 0, h * 128);
-        }
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + WQ_OFF + kb * 12288, &mapWq, wq_full, kb * 32, h * 96);
+      };
+      auto load_tab = [&](long long j) {
+        const int h = (int)(j % heads);
+        const uint32_t r = (uint32_t)(j & 1);
+        mbar_wait_tag(tab_free + r, (uint32_t)(((j >> 1) & 1) ^ 1), 180);   // the compute warps are done with the tables of head j-2
+        mbar_arrive_expect_tx(tab_full + r, TAB_FLOATS * 4);
+        bulk_load(smem + TAB_OFF + r * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + r);
+      };
+      // need-order of the MMA warp: QKV(0..2) at the start, then per head j: out(j) [WO(j)] followed by QKV(j+3) [WQ(j+3)]
+      for (long long j = 0; j < 3 && j < total; ++j) { load_wq(j); if (j < 2) load_tab(j); }
+      for (long long j = 0; j < total; ++j) {
+        mbar_wait_tag(wo_free, (uint32_t)((j & 1) ^ 1), 187);
+        mbar_arrive_expect_tx(wo_full, 16384);
+        tma_load_2d(smem + WO_OFF, &mapWo, wo_full, 0, (int)(j % heads) * 128);
+        // WQ(j+3) waits for QKV(j+2); for the last two heads of a tile that projection belongs to the NEXT tile and is only
+        // issued after this tile's last out-projection, so those two loads are deferred behind WO(last head of the tile)
+        const int hj = (int)(j % heads);
+        if (hj < heads - 2) { if (j + 3 < total) load_wq(j + 3); }
+        else if (hj == heads - 1) { if (j + 2 < total) load_wq(j + 2); if (j + 3 < total) load_wq(j + 3); }
+        if (j + 2 < total) load_tab(j + 2);
       }
     }
   } else if (warp == 1) {
@@ -188,7 +206,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       const uint32_t sX = smem_u32(smem + X_OFF), sWQ = smem_u32(smem + WQ_OFF), sWO = smem_u32(smem + WO_OFF);
       uint32_t it = 0, tl = 0;                               // global head counter, tile counter
       auto issue_qkv = [&](uint32_t hh) {
-        mbar_wait(wq_full, hh & 1);
+        mbar_wait_tag(wq_full, hh & 1, 203);
         tc_fence_after();
         const uint32_t d = tmem + ((hh & 1) ? T_QKV1 : T_QKV0);
 #pragma unroll
@@ -200,28 +218,37 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         tc_commit(qkv_done + (hh & 1));
         tc_commit(wq_free);
       };
+      auto issue_s = [&](uint32_t hh) {                      // S = q K"^T, A = the q accumulator of head hh read from TMEM
+        const uint32_t r = hh & 1;
+        mbar_wait_tag(qk_ready + r, (hh >> 1) & 1, 224);
+        tc_fence_after();
+        const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
+        const uint64_t db = umma_desc_k128(smem_u32(smem + R1_OFF + r * 32768));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
+        tc_commit(s_done);
+      };
+      // Issue order per head h:  [wait p_ready(h)]  S(h+1)  PV(h)  out(h)  QKV(h+3)
+      // S(h+1) goes first so that the next softmax can start while PV / out-projection / QKV of other heads execute; the
+      // QKV projection runs three heads ahead (its TMEM buffer was last read by the S product issued just before it).
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-        mbar_wait(x_ready, tl & 1);
+        mbar_wait_tag(x_ready, tl & 1, 216);
         tc_fence_after();
         issue_qkv(it);
+        if (heads > 1) issue_qkv(it + 1);
+        issue_s(it);
+        if (heads > 2) issue_qkv(it + 2);
         for (int h = 0; h < heads; ++h, ++it) {
           const uint32_t r = it & 1;
           const uint32_t sR1 = smem_u32(smem + R1_OFF + r * 32768), sVT = smem_u32(smem + VT_OFF + r * 8192);
-          // ---- S = q K"^T  (A = the q accumulator of this head, read from TMEM)
-          mbar_wait(qk_ready, it & 1);
+          long long* md = (p.dbg && blockIdx.x == 0 && tl == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
+          if (md) md[0] = clock64();
+          mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: S accumulator free, P(h) in smem
           tc_fence_after();
-          {
-            const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
-            const uint64_t db = umma_desc_k128(sR1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
-          }
-          tc_commit(s_done);
-          // ---- next head's QKV projection runs under this head's softmax
-          if (h + 1 < heads) issue_qkv(it + 1);
+          if (md) md[1] = clock64();
+          if (h + 1 < heads) issue_s(it + 1);
+          if (md) md[2] = clock64();
           // ---- O = P V
-          mbar_wait(p_ready, it & 1);
-          tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
             const uint64_t da = umma_desc_k128(sR1 + kb * 16384), db = umma_desc_k128(sVT + kb * 4096);
@@ -229,16 +256,21 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + T_O, da + 2 * k, db + 2 * k, id_pv, (kb | k) ? 1u : 0u);
           }
           tc_commit(pv_done + r);
+          if (md) md[3] = clock64();
           // ---- Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM; P was normalised before the PV product)
-          mbar_wait(wo_full, it & 1);
-          if (h == 0) mbar_wait(out_free, (tl & 1) ^ 1);     // previous tile's epilogue has drained Out
+          mbar_wait_tag(wo_full, it & 1, 246);
+          if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
           tc_fence_after();
+          if (md) md[4] = clock64();
           {
             const uint64_t db = umma_desc_k128(sWO);
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * k, db + 2 * k, id_out, (h | k) ? 1u : 0u);
           }
           tc_commit(wo_free);
+          if (md) md[5] = clock64();
+          if (h + 3 < heads) issue_qkv(it + 3);
+          if (md) { md[6] = clock64(); md[7] = md[6]; }
         }
         tc_commit(tile_done);
       }
@@ -322,58 +354,70 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(x_ready);
 
+      // 1/|q| of the head whose softmax comes next; step2 runs one head ahead of the softmax (software pipeline):
+      //   step2(h+1) | softmax(h) | step2(h+2) | softmax(h+1) ...   so the S product of head h+1 and the PV / out-projection
+      //   of head h execute on the tensor pipe while the compute warps are busy with the other stage.
+      float inv_q_next = 0.f;
+      auto step2 = [&](uint32_t itx, int hx) {
+        const uint32_t r = itx & 1;
+        const uint32_t R1 = s_base + R1_OFF + r * 32768;
+        const uint32_t VT = s_base + VT_OFF + r * 8192;
+        const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);   // 32 * gamma_q * gamma_k
+        float4 gm[8];
+        if (ch == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) gm[c] = __ldg(ksc + c);
+        }
+        mbar_wait_tag(qkv_done + r, (itx >> 1) & 1, 352);
+        tc_fence_after();
+        const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
+        float v[32], w[32];
+        tmem_ld32(tq, v);                                                // q: both threads of the row need its norm
+        tmem_ld32(tq + 32 + ch * 32, w);                                 // ch 0: k, ch 1: v
+        tmem_wait_ld();
+        float nq = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) nq = fmaf(v[d], v[d], nq);
+        inv_q_next = 1.0f / fmaxf(sqrtf(nq), 1e-12f);                    // F.normalize(eps=1e-12)  (maxvit.py:30)
+        float inv_k = 0.f;
+        if (ch == 0) {
+          float nk = 0.f;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) nk = fmaf(w[d], w[d], nk);
+          inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
+        }
+        if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 353);      // R1[r] / VT[r] no longer read by MMAs
+        if (ch == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts128(R1 + swz[c], w[4 * c] * inv_k * gm[c].x, w[4 * c + 1] * inv_k * gm[c].y, w[4 * c + 2] * inv_k * gm[c].z, w[4 * c + 3] * inv_k * gm[c].w);
+        } else {
+          // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
+          const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
+          const int kc = (t & 63) >> 3;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) sts16(vt + sw128(d, kc), __bfloat16_as_ushort(__float2bfloat16(w[d])));
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qk_ready + r);
+      };
+      step2(it, 0);
       for (int h = 0; h < heads; ++h, ++it) {
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
         if (dbg) p.dbg[h * 8 + 0] = clock64();
         const uint32_t r = it & 1;
         const uint32_t R1 = s_base + R1_OFF + r * 32768;
-        const uint32_t VT = s_base + VT_OFF + r * 8192;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
-        mbar_wait(tab_full + r, (it >> 1) & 1);                          // per-head tables (TMA)
+        const float inv_q = inv_q_next;
+        if (h + 1 < heads) step2(it + 1, h + 1);
         if (dbg) p.dbg[h * 8 + 1] = clock64();
-        // ---------------- QKV_h: 1/|q| (q itself stays in TMEM), K" and V^T -> smem operands ----------------
-        mbar_wait(qkv_done + r, (it >> 1) & 1);
-        if (it >= 2) mbar_wait(pv_done + r, ((it - 2) >> 1) & 1);        // R1[r] / VT[r] no longer read by MMAs
-        tc_fence_after();
-        if (dbg) p.dbg[h * 8 + 2] = clock64();
-        float inv_q;
-        {
-          const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
-          float v[32], w[32];
-          tmem_ld32(tq, v);                                              // q: both threads of the row need its norm
-          tmem_ld32(tq + 32 + ch * 32, w);                               // ch 0: k, ch 1: v
-          tmem_wait_ld();
-          float nq = 0.f;
-#pragma unroll
-          for (int d = 0; d < 32; ++d) nq = fmaf(v[d], v[d], nq);
-          inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);                       // F.normalize(eps=1e-12)  (maxvit.py:30)
-          if (ch == 0) {
-            float nk = 0.f;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) nk = fmaf(w[d], w[d], nk);
-            const float inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
-            const uint32_t ksc = tab + (7 * 13 * 8 + 8) * 4;             // 32 * gamma_q * gamma_k
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 gm = lds128(ksc + c * 16);
-              sts128(R1 + swz[c], w[4 * c] * inv_k * gm.x, w[4 * c + 1] * inv_k * gm.y, w[4 * c + 2] * inv_k * gm.z, w[4 * c + 3] * inv_k * gm.w);
-            }
-          } else {
-            // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
-            const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
-            const int kc = (t & 63) >> 3;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) sts16(vt + sw128(d, kc), __bfloat16_as_ushort(__float2bfloat16(w[d])));
-          }
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qk_ready);
-        if (dbg) p.dbg[h * 8 + 3] = clock64();
+        mbar_wait_tag(tab_full + r, (it >> 1) & 1, 394);                          // per-head bias table (TMA)
+        if (dbg) { const long long c2 = clock64(); p.dbg[h * 8 + 2] = c2; p.dbg[h * 8 + 3] = c2; }
 
         // ---------------- S half-row: / |q|, + bias, masked softmax -> normalised P (bf16) ----------------
-        mbar_wait(s_done, it & 1);
+        mbar_wait_tag(s_done, it & 1, 398);
         tc_fence_after();
         if (dbg) p.dbg[h * 8 + 4] = clock64();
         {
@@ -421,9 +465,13 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]) * LOG2E;
           float sum = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = (ch == 0 || j < 21) ? ex2(fmaf(sc[j], LOG2E, -m)) : 0.f;
-            sc[j] = e; sum += e;
+          for (int j = 0; j < 21; ++j) { sc[j] = ex2(fmaf(sc[j], LOG2E, -m)); sum += sc[j]; }
+          if (ch == 0) {
+#pragma unroll
+            for (int j = 21; j < 32; ++j) { sc[j] = ex2(fmaf(sc[j], LOG2E, -m)); sum += sc[j]; }
+          } else {
+#pragma unroll
+            for (int j = 21; j < 32; ++j) sc[j] = 0.f;
           }
           red[(0 * 128 + t) * 2 + ch] = sum;
           pair_sync(lg);                                                 // partner's partial row sum is visible
@@ -447,7 +495,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       }
 
       // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------
-      mbar_wait(tile_done, tl & 1);
+      mbar_wait_tag(tile_done, tl & 1, 472);
       tc_fence_after();
       {
         float* dst = nullptr;
@@ -509,6 +557,7 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
                    const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab,
                    const AttnGeom& g, int heads, int dh, float ln_eps, cudaStream_t st) {
   if (g.C != fa::C || dh != fa::DH) return set_error("attn_fused: needs C=128, dim_head=32 (got C=%d, dh=%d)", g.C, dh);
+  if (heads < 4) return set_error("attn_fused: the head pipeline needs at least 4 heads (got %d)", heads);
   if (g.win != fa::WIN || g.R != fa::REG) return set_error("attn_fused: specialised for 7x7 windows + 4 register tokens (got %d, %d)", g.win, g.R);
   CUtensorMap mq, mo;
   int rc = make_w_map(&mq, wqkv_h, 128, (long long)heads * 96, 96);

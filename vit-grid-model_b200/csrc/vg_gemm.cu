@@ -81,7 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform: lets the MMA issue use uniform registers (no per-MMA elect/broadcast loop)
 
   const int total_tiles = gs.num_m_tiles * gs.num_n_tiles;
   constexpr int BKE = TF32 ? 32 : 64;                        // elements per K block
@@ -256,7 +256,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform: lets the MMA issue use uniform registers (no per-MMA elect/broadcast loop)
   const int halo = hs.P + 1;                                 // rows in front of the tile's first output pixel
 
   if (warp == 0) {

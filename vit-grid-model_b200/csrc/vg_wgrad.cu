@@ -90,7 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);        // warp-uniform: lets the MMA issue use uniform registers (no per-MMA elect/broadcast loop)
 
   if (warp == 0) {
     if (lane == 0) {                                           // ===== TMA producer =====

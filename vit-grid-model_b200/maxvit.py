@@ -191,7 +191,7 @@ class MaxViT(nn.Module):
         """x: CL (N,H,W,C).  returns (x + attn(x), reg_out)"""
         N, H, W, C = x.shape
         w, R = self.vit_window_size, self.num_register_tokens
-        if self.fused_attention and self.tf32 and C == 128 and self.dim_head == 32 and w == 7 and R == 4:
+        if self.fused_attention and self.tf32 and C == 128 and self.dim_head == 32 and w == 7 and R == 4 and self.heads >= 4:
             return ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
                                   self.heads, self.dim_head)
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)

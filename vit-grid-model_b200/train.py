@@ -112,7 +112,7 @@ def _unpack_wgrad3x3(dWt, co, ci_pad, ci):
 # ------------------------------------------------------------------------------------------------ MaxViT block
 def _fused_ok(vit, C):
     return (vit.fused_attention and vit.tf32 and C == 128 and vit.dim_head == 32 and vit.vit_window_size == 7
-            and vit.num_register_tokens == 4)
+            and vit.num_register_tokens == 4 and vit.heads >= 4)
 
 
 def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out):
