@@ -30,6 +30,7 @@ import torch  # noqa: E402
 
 METRIC, UNIT = "grid_fields_per_sec", "fields/s"
 CONV_FLOPS_PER_FIELD = 2.0 * 84 * 70 * 128 * 1152          # algorithmic: unpadded-frame pixels x Cout x 9*Cin x 2
+ATTN_FLOPS_PER_FIELD = 2.0125e9                             # qkv 1.2505 + QK^T 0.1726 + PV 0.1726 + out 0.4168 GF, 53-token count
 FWD_GFLOP_PER_FIELD_REF = 25.864                            # SURVEY F8 (reference graph, no lead-time dedup)
 FWD_GFLOP_PER_FIELD_EXEC = 17.516                           # with the stem computed once per sample (H5)
 
@@ -310,15 +311,34 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("conv3x3_ln_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = None
+    roofline, kernels = None, []
     if conv_ms and args.precision == "bf16":
         avg_ms = sum(conv_ms) / len(conv_ms)
         achieved = CONV_FLOPS_PER_FIELD * B * L / (avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": "gemm_tc_kernel<EPI_CONV_LN> (3x3 conv 128->128 implicit GEMM + ChanLN/FiLM/ReLU/residual)",
-                    "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": traffic, "launches_per_step": len(conv_ms) // args.steps, "avg_launch_ms": avg_ms,
-                    "peak_source": peak_src,
-                    "share_of_step": sum(conv_ms) / (e0.elapsed_time(e1) if False else ms_total)}
+        kernels.append({"kernel": "conv_halo_kernel (3x3 conv 128->128 implicit GEMM, tcgen05 kind::f16, + ChanLN/FiLM/ReLU/residual epilogue)",
+                        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                        "traffic": traffic, "launches_per_step": len(conv_ms) // args.steps, "avg_launch_ms": avg_ms,
+                        "peak_source": peak_src, "share_of_step": sum(conv_ms) / ms_total,
+                        "algorithmic_gflop_per_field_per_launch": CONV_FLOPS_PER_FIELD / 1e9})
+    attn_ms = per.get("vg_attn_fused_fwd", [])
+    if attn_ms and args.precision == "bf16":
+        avg_ms = sum(attn_ms) / len(attn_ms)
+        achieved = ATTN_FLOPS_PER_FIELD * B * L / (avg_ms * 1e-3) / 1e12
+        attn_traffic = None
+        try:
+            attn_traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("attn_fused_dram_bytes_per_launch")
+        except Exception:
+            pass
+        kernels.append({"kernel": "attn_fused_kernel (window / grid attention in one kernel: tcgen05 kind::tf32 QKV, QK^T, out-projection, kind::f16 PV)",
+                        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                        "traffic": attn_traffic, "launches_per_step": len(attn_ms) // args.steps, "avg_launch_ms": avg_ms,
+                        "peak_source": peak_src + "; 88 % of this kernel's FLOPs run as kind::tf32 (half the bf16 rate)",
+                        "share_of_step": sum(attn_ms) / ms_total,
+                        "algorithmic_gflop_per_field_per_launch": ATTN_FLOPS_PER_FIELD / 1e9})
+    kernels.sort(key=lambda k: -k["share_of_step"])
+    if kernels:
+        roofline = dict(kernels[0])                           # the dominant kernel of the step
+        roofline["other_kernels"] = kernels[1:]
 
     if rank == 0:
         if args.trace:
