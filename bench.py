@@ -143,7 +143,7 @@ def run_train(args, cfg, dev, rank, world, barrier, max_over_ranks):
     from oracle import synth
     from vit_grid_model_b200 import MetNet3, DataParallel, FlatAdamW, focal_r_loss, _lib
     Bt, L = args.train_batch, cfg.L
-    model = MetNet3(**cfg.metnet3_kwargs(), dropout=0.0)        # attention dropout is not built yet (reference default 0.1)
+    model = MetNet3(**cfg.metnet3_kwargs())                     # reference defaults, incl. attention dropout 0.1
     model.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), strict=True)
     model = model.to(dev).train().set_precision("bf16")
     net = DataParallel(model) if world > 1 else model
@@ -188,7 +188,7 @@ def run_train(args, cfg, dev, rank, world, barrier, max_over_ranks):
             "loss": float(loss.item()), "gpu_launches": int((_lib.launch_count() - l0) // steps),
             "parallelism": f"data parallel x{world}: per-rank batch shards, gradient all-reduce ({n_params * 4 / 1e6:.1f} MB fp32, "
                            f"6 sections, NCCL on a side stream overlapped with backward)" if world > 1 else "single GPU",
-            "optimizer": "fused AdamW (one kernel over the flat parameter buffer)", "dropout": 0.0,
+            "optimizer": "fused AdamW (one kernel over the flat parameter buffer)", "dropout": model.dropout,
             "gflop_per_field_fwd_bwd": 3 * FWD_GFLOP_PER_FIELD_EXEC}
 
 

@@ -142,10 +142,13 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
  * wqkv_h: fp32 [heads][96][128] (per head the 32 q rows, 32 k rows, 32 v rows of to_qkv.weight);
  * wout_h: fp32 [heads][128][32] (per head the 32 columns of to_out.0.weight); head_tab: fp32 [heads][800] =
  * per head the relative-position bias as 7 pre-shifted copies [bi][row 0..12][8] (entry k = table[(row*13 + bi+6-k)]),
- * table[169] (+7 pad), q gamma[32], k gamma[32].  Needs C=128, dim_head=32, win=7, R=4. */
+ * table[169] (+7 pad), 32*gamma_q*gamma_k [32], 32 unused.  Needs C=128, dim_head=32, win=7, R=4, heads >= 4.
+ * Training: drop_thresh T in [1,255] enables nn.Dropout (maxvit.py:146,151) on the attention probabilities and on the
+ * to_out output with drop probability T/256 (kept values scaled by 256/(256-T)); the masks are a counter-based hash of
+ * (drop_seed, drop_salt = layer id, row, group) that the backward kernels regenerate.  T = 0: no dropout (eval). */
 VG_API int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                       const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
-                      int grid_mode, int heads, int dh, float ln_eps, void* stream);
+                      int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt, int drop_thresh, void* stream);
 
 /* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */
 VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);
@@ -275,13 +278,19 @@ VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const
               long long work_elems, void* stream);
 /* attention backward (fp32): gradient at the out-projection output (inverse of the scatter + register rows) */
 VG_API int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
-                           int R, int grid_mode, float* dproj, void* stream);
+                           int R, int grid_mode, float* dproj, long long drop_seed, int drop_salt, int drop_thresh, void* stream);
+/* test hook: the dropout masks the kernels use, as bytes (1 = kept): prob_mask [n_windows][heads][64][64] (query slot,
+ * key slot), out_mask [n_windows][64][C] */
+VG_API int vg_dropout_mask_debug(long long drop_seed, int drop_salt, int drop_thresh, long long n_windows, int heads, int C,
+                          void* prob_mask, void* out_mask, void* stream);
 /* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated.  use_tf32 = 1 / 2: tensor-core
  * kernel (1: tf32 mma; 2: bf16 mma + ldmatrix; fp32 accumulate), which can also re-materialise the forward output att = softmax(.) V [rows][inner]
- * (att_out, or NULL) for the to_out weight gradient when the forward pass was the fused kernel; 0: exact-fp32 SIMT kernel. */
+ * (att_out, or NULL) for the to_out weight gradient when the forward pass was the fused kernel; 0: exact-fp32 SIMT kernel.
+ * drop_thresh > 0 (bf16 kernel only): the forward pass applied dropout to the probabilities with these parameters. */
 VG_API int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, void* stream);
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, long long drop_seed,
+                     int drop_salt, int drop_thresh, void* stream);
 /* LayerNorm + FiLM backward with the inverse partition; dx_in written (= dx + dx_out), dreg_in and dfilm accumulated */
 VG_API int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
                        const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in,

@@ -65,9 +65,12 @@ def film(cond: torch.Tensor, sd, p: str):
     return gb[:, :d], gb[:, d:]
 
 
-def attention(x: torch.Tensor, cond: torch.Tensor, sd, p: str, *, heads: int, window: int, num_reg: int):
+def attention(x: torch.Tensor, cond: torch.Tensor, sd, p: str, *, heads: int, window: int, num_reg: int,
+              prob_mask: torch.Tensor | None = None, out_mask: torch.Tensor | None = None):
     """maxvit.py:170-219.  x (Nw, S, D) with Nw = N*windows (field-major), cond (N, cond_dim).
-    Returns to_out(attn) WITHOUT the residual.  Dropout is identity (eval / p=0)."""
+    Returns to_out(attn) WITHOUT the residual.  Dropout is identity (eval / p=0) unless explicit masks are given:
+    prob_mask (Nw, heads, S, S) multiplies the softmax output (nn.Dropout of self.attend, :146), out_mask (Nw, S, D) the
+    to_out output (:151); both already contain the 1/(1-p) scale."""
     Nw, S, D = x.shape
     N = cond.shape[0]
     x = F.layer_norm(x, (D,))                                         # no affine when cond_dim is set (:137)
@@ -83,9 +86,13 @@ def attention(x: torch.Tensor, cond: torch.Tensor, sd, p: str, *, heads: int, wi
     sim = q @ k.transpose(-1, -2)                                              # no extra scale (:203)
     bias = sd[p + "rel_pos_bias.weight"][rel_pos_indices(window, num_reg)]     # (S,S,heads)
     sim = sim + bias.permute(2, 0, 1)
-    out = sim.softmax(dim=-1) @ v
+    attn = sim.softmax(dim=-1)
+    if prob_mask is not None:
+        attn = attn * prob_mask
+    out = attn @ v
     out = out.permute(0, 2, 1, 3).reshape(Nw, S, inner)
-    return F.linear(out, sd[p + "to_out.0.weight"])
+    out = F.linear(out, sd[p + "to_out.0.weight"])
+    return out if out_mask is None else out * out_mask
 
 
 def mbconv(x: torch.Tensor, sd, p: str, *, residual: bool, training: bool = False, eps: float = 1e-5):
@@ -105,8 +112,10 @@ def mbconv(x: torch.Tensor, sd, p: str, *, residual: bool, training: bool = Fals
 
 
 def maxvit_forward(x: torch.Tensor, cond: torch.Tensor, sd, *, prefix: str = "", depth: int, heads: int,
-                   window: int, num_reg: int, training: bool = False, return_registers: bool = False):
-    """maxvit.py:289-341 for a single-stage MaxViT.  x (N,D,H,W), cond (N,cond_dim)."""
+                   window: int, num_reg: int, training: bool = False, return_registers: bool = False, drop_masks=None):
+    """maxvit.py:289-341 for a single-stage MaxViT.  x (N,D,H,W), cond (N,cond_dim).
+    drop_masks: optional {(layer, 1|2): (prob_mask, out_mask)} explicit dropout masks for block (1) / grid (2) attention."""
+    drop_masks = drop_masks or {}
     N, D, H, W = x.shape
     assert H % window == 0 and W % window == 0
     nwin = (H // window) * (W // window)
@@ -121,14 +130,18 @@ def maxvit_forward(x: torch.Tensor, cond: torch.Tensor, sd, *, prefix: str = "",
         tok = flat[:, bidx].reshape(N * nwin, window * window, D)
         reg = sd[f"{prefix}register_tokens.{li}"][None].expand(N * nwin, num_reg, D)
         seq = torch.cat([reg, tok], dim=1)
-        seq = attention(seq, cond, sd, f"{prefix}layers.{li}.1.", heads=heads, window=window, num_reg=num_reg) + seq
+        pm, om = drop_masks.get((li, 1), (None, None))
+        seq = attention(seq, cond, sd, f"{prefix}layers.{li}.1.", heads=heads, window=window, num_reg=num_reg,
+                        prob_mask=pm, out_mask=om) + seq
         flat = torch.empty_like(flat)
         flat[:, bidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D)
         # grid attention: registers = mean over windows of block-attention register outputs (:326-327)
         reg = seq[:, :num_reg].reshape(N, nwin, num_reg, D).mean(dim=1)
         tok = flat[:, gidx].reshape(N * nwin, window * window, D)
         seq = torch.cat([reg.repeat_interleave(nwin, 0), tok], dim=1)
-        seq = attention(seq, cond, sd, f"{prefix}layers.{li}.2.", heads=heads, window=window, num_reg=num_reg) + seq
+        pm, om = drop_masks.get((li, 2), (None, None))
+        seq = attention(seq, cond, sd, f"{prefix}layers.{li}.2.", heads=heads, window=window, num_reg=num_reg,
+                        prob_mask=pm, out_mask=om) + seq
         regs_out = seq[:, :num_reg]
         flat = torch.empty_like(flat)
         flat[:, gidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D)

@@ -108,10 +108,20 @@ def test_flat_adamw_matches_torch_and_loss_decreases():
     assert losses[-1] < losses[0], losses
 
 
-def test_train_mode_rejects_unsupported():
-    from vit_grid_model_b200 import MetNet3
+def test_train_with_default_dropout_and_unsupported_modes():
+    from vit_grid_model_b200 import MetNet3, focal_r_loss
     cfg = synth.CFG_SMALL128
     m = MetNet3(**cfg.metnet3_kwargs()).cuda().train()          # reference default dropout = 0.1
-    x, ts, _ = synth.make_inputs(cfg, 1)
-    with pytest.raises(NotImplementedError):
+    m.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), strict=True)
+    x, ts, target = synth.make_inputs(cfg, 2)
+    torch.manual_seed(5)
+    loss = focal_r_loss(m(x.cuda(), timestamps=ts.cuda()), target.cuda())
+    loss.backward()
+    assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x.cuda(), timestamps=ts.cuda())               # eval mode: no dropout, running statistics
+    assert torch.isfinite(y_eval).all()
+    m.train().set_precision("fp32")
+    with pytest.raises(NotImplementedError):                     # dropout is built into the mixed-precision path only
         m(x.cuda(), timestamps=ts.cuda())

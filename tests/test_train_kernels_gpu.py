@@ -158,3 +158,56 @@ def test_maxvit_block_backward(precision):
         if e > tol:
             bad.append((name, round(e, 5)))
     assert not bad, bad
+
+
+def test_attention_dropout_forward_backward():
+    """nn.Dropout on the attention probabilities and after to_out (maxvit.py:146,151), train() mode: the kernels' counter-based
+    masks are exported through the test hook and fed to the oracle, so forward and every gradient must agree as without dropout;
+    the keep rate must match the quantised probability."""
+    from oracle import synth
+    from oracle import maxvit_oracle as mo
+    from vit_grid_model_b200 import MaxViT
+    from vit_grid_model_b200 import train as tr
+    dim, depth, heads, dh, w, r, N, H, W, p = 128, 1, 32, 32, 7, 4, 2, 14, 21, 0.25
+    S, nwin = r + w * w, (H // w) * (W // w)
+    sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, r), seed=7)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    x = rnd(N, dim, H, W, seed=21).requires_grad_(True)
+    cond = rnd(N, 2, seed=22).requires_grad_(True)
+    dy = rnd(N, dim, H, W, seed=23)
+    seed, T = 123456789, tr.dropout_threshold(p)
+    scale = 256.0 / (256 - T)
+    masks = {}
+    for ai, salt in ((1, 0), (2, 1)):
+        pm, om = OT().dropout_masks((seed, salt, T), N * nwin, heads, dim)
+        keep = pm[:, :, :S, :S].float().mean().item()
+        assert abs(keep - (1 - T / 256)) < 5e-3, keep
+        masks[(0, ai)] = (pm[:, :, :S, :S].float().cpu() * scale, om[:, :S].float().cpu() * scale)
+    y = mo.maxvit_forward(x, cond, sd, depth=depth, heads=heads, window=w, num_reg=r, training=True, drop_masks=masks)
+    y.backward(dy)
+    m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=r, dropout=p)
+    m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    m = m.cuda().train().set_precision("bf16")
+    xc, condc = x.detach().permute(0, 2, 3, 1).contiguous().cuda(), cond.detach().cuda()
+    with torch.no_grad():
+        yc, saved = tr.maxvit_train_forward(m, xc, condc, seed=seed)
+        G = {k: torch.zeros_like(q) for k, q in m.named_parameters()}
+        dcond = torch.zeros_like(condc)
+        dxc = tr.maxvit_train_backward(m, saved, condc, dcond, dy.permute(0, 2, 3, 1).contiguous().cuda(), G, "")
+    assert rel_err(yc.permute(0, 3, 1, 2), y) < 2e-2
+    bad = []
+    for name, got, ref in [("dx", dxc.permute(0, 3, 1, 2), x.grad), ("dcond", dcond, cond.grad)] + [(k, G[k], sd[k].grad) for k in G]:
+        if re.fullmatch(r"layers\.\d+\.0\.(fn\.)?[037]\.bias", name):
+            continue
+        g, rf = got.detach().float().cpu(), ref
+        e = ((g - rf).norm() / max(rf.norm().item(), 1e-2)).item()
+        if e > 6e-2:
+            bad.append((name, round(e, 5)))
+    assert not bad, bad
+    # a different seed gives a different mask, the same seed the same output
+    with torch.no_grad():
+        y2, _ = tr.maxvit_train_forward(m, xc, condc, seed=seed)
+        y3, _ = tr.maxvit_train_forward(m, xc, condc, seed=seed + 1)
+    assert torch.equal(yc, y2) and not torch.equal(yc, y3)

@@ -220,11 +220,11 @@ int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, cons
 
 int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                       const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
-                      int grid_mode, int heads, int dh, float ln_eps, void* stream) {
+                      int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt, int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
   return attn_fused_run(x, x_out, reg_in, reg_per_field, reg_out, film, wqkv_h, wout_h, head_tab, g,
-                        heads, dh, ln_eps, (cudaStream_t)stream);
+                        heads, dh, ln_eps, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh, (cudaStream_t)stream);
 }
 
 int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream) {
@@ -384,19 +384,28 @@ int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float*
 }
 
 int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
-                           int R, int grid_mode, float* dproj, void* stream) {
+                           int R, int grid_mode, float* dproj, long long drop_seed, int drop_salt, int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
-  return attn_out_bwd_gather_run(dx_out, dreg, reg_scale, g, dproj, (cudaStream_t)stream);
+  return attn_out_bwd_gather_run(dx_out, dreg, reg_scale, g, dproj, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh,
+                                 (cudaStream_t)stream);
+}
+
+int vg_dropout_mask_debug(long long drop_seed, int drop_salt, int drop_thresh, long long n_windows, int heads, int C,
+                          void* prob_mask, void* out_mask, void* stream) {
+  return dropout_mask_debug_run((unsigned)drop_seed, (unsigned)drop_salt, drop_thresh, n_windows, heads, C,
+                                reinterpret_cast<unsigned char*>(prob_mask), reinterpret_cast<unsigned char*>(out_mask),
+                                (cudaStream_t)stream);
 }
 
 int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, void* stream) {
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, long long drop_seed,
+                     int drop_salt, int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
   return attn_core_bwd_run(qkv, datt, q_gamma, k_gamma, bias_table, g, heads, dh, dqkv, dq_gamma, dk_gamma, dbias_table,
-                           use_tf32, att_out, (cudaStream_t)stream);
+                           use_tf32, att_out, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh, (cudaStream_t)stream);
 }
 
 int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,

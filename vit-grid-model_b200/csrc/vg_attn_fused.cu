@@ -21,6 +21,7 @@
 
 #include "vg_common.cuh"
 #include "vg_host.h"
+#include "vg_rng.cuh"
 
 namespace vg {
 
@@ -60,6 +61,7 @@ struct FusedAttnParams {
   float ln_eps;
   long long n_windows;
   long long* dbg;                      // optional [heads][8] clock64 stamps of CTA 0 / compute thread 0 / first tile
+  DropCfg drop;                        // training: dropout on the probabilities and on the to_out output
 };
 
 // byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
@@ -476,14 +478,25 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           red[(0 * 128 + t) * 2 + ch] = sum;
           pair_sync(lg);                                                 // partner's partial row sum is visible
           const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
+          if (p.drop.thresh) {                                           // nn.Dropout on the probabilities (maxvit.py:146, 209)
+            const float ks = inv_sum * p.drop.scale;
+            const uint32_t rid = drop_row(wdx, i);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t hsh = drop_hash(p.drop.seed, rid, drop_group_prob(p.drop.salt, h, ch * 8 + c));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sc[4 * c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? ks : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j] *= inv_sum;
+          }
           // own 32 keys = chunks [ch*4, +4) of this row in k-block `half`; same chunks of the other k-block are zero
           const uint32_t prow = R1 + half * 16384, zrow = R1 + (half ^ 1) * 16384;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c] * inv_sum, sc[8 * c + 1] * inv_sum),
-                    pack_bf16(sc[8 * c + 2] * inv_sum, sc[8 * c + 3] * inv_sum),
-                    pack_bf16(sc[8 * c + 4] * inv_sum, sc[8 * c + 5] * inv_sum),
-                    pack_bf16(sc[8 * c + 6] * inv_sum, sc[8 * c + 7] * inv_sum));
+            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
+                    pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
             sts128u(zrow + swz[ch * 4 + c], 0u, 0u, 0u, 0u);
           }
         }
@@ -508,6 +521,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         for (int q = 0; q < 2; ++q) {
           const int c0 = ch * 64 + q * 32;
           tmem_ld32(lane_addr + T_OUT + c0, v); tmem_wait_ld();
+          if (p.drop.thresh) {                                           // nn.Dropout after to_out (maxvit.py:151)
+            const uint32_t rid = drop_row(wdx, i);
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const uint32_t hsh = drop_hash(p.drop.seed, rid, drop_group_out(p.drop.salt, (c0 + c) >> 2));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? p.drop.scale : 0.f;
+            }
+          }
           if (dst) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
@@ -555,7 +577,9 @@ static int make_w_map(CUtensorMap* m, const void* ptr, long long inner, long lon
 // wqkv_h: fp32 [heads*96][128] (per head: 32 q rows, 32 k rows, 32 v rows); wout_h: fp32 [heads*128][32]
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                    const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab,
-                   const AttnGeom& g, int heads, int dh, float ln_eps, cudaStream_t st) {
+                   const AttnGeom& g, int heads, int dh, float ln_eps, unsigned seed, unsigned salt, int drop_thresh,
+                   cudaStream_t st) {
+  if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_fused: dropout threshold %d outside [0, 255]", drop_thresh);
   if (g.C != fa::C || dh != fa::DH) return set_error("attn_fused: needs C=128, dim_head=32 (got C=%d, dh=%d)", g.C, dh);
   if (heads < 4) return set_error("attn_fused: the head pipeline needs at least 4 heads (got %d)", heads);
   if (g.win != fa::WIN || g.R != fa::REG) return set_error("attn_fused: specialised for 7x7 windows + 4 register tokens (got %d, %d)", g.win, g.R);
@@ -568,6 +592,7 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   p.x = x; p.x_out = x_out; p.reg_in = reg_in; p.reg_per_field = reg_per_field; p.reg_out = reg_out; p.film = film;
   p.head_tab = head_tab; p.g = g; p.heads = heads;
   p.ln_eps = ln_eps; p.n_windows = (long long)g.N * g.nwin();
+  p.drop.seed = seed; p.drop.salt = salt; p.drop.thresh = drop_thresh; p.drop.scale = 256.0f / (256.0f - (float)drop_thresh);
   p.dbg = nullptr;
   if (const char* e = getenv("VG_ATTN_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   static bool attr = false;

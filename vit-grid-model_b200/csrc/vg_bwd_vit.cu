@@ -5,6 +5,7 @@
 // The dense projections' dgrad / wgrad run on the tcgen05 GEMMs (vg_gemm.cu, vg_wgrad.cu).
 #include "vg_common.cuh"
 #include "vg_host.h"
+#include "vg_rng.cuh"
 
 namespace vg {
 
@@ -387,7 +388,7 @@ __device__ __forceinline__ long long tok_pixel(const AttnGeom& g, int wi, int t)
 // gradient wrt the out-projection output (maxvit.py:218-219, 310-319): window rows gather dX_out through the partition
 // map, register rows take dreg (N,R,C) * reg_scale (the mean over windows, maxvit.py:326) or zero.
 __global__ void __launch_bounds__(256) attn_out_bwd_gather_kernel(const float* __restrict__ dx_out, const float* __restrict__ dreg, float reg_scale,
-                                                                  const AttnGeom g, float* __restrict__ dproj, long long rows) {
+                                                                  const AttnGeom g, float* __restrict__ dproj, long long rows, const DropCfg drop) {
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31, C = g.C, S = g.S(), nwin = g.nwin();
@@ -400,6 +401,13 @@ __global__ void __launch_bounds__(256) attn_out_bwd_gather_kernel(const float* _
       if (dreg) { v = *reinterpret_cast<const float4*>(dreg + ((long long)n * g.R + tok) * C + c); v.x *= reg_scale; v.y *= reg_scale; v.z *= reg_scale; v.w *= reg_scale; }
     } else {
       v = *reinterpret_cast<const float4*>(dx_out + ((long long)n * g.Hl * g.Wl + tok_pixel(g, wi, tok - g.R)) * C + c);
+    }
+    if (drop.thresh) {                                       // the to_out dropout mask of the forward pass (maxvit.py:151)
+      const uint32_t hsh = drop_hash(drop.seed, drop_row(wdx, tok), drop_group_out(drop.salt, c >> 2));
+      v.x *= (int)(hsh & 255u) >= drop.thresh ? drop.scale : 0.f;
+      v.y *= (int)((hsh >> 8) & 255u) >= drop.thresh ? drop.scale : 0.f;
+      v.z *= (int)((hsh >> 16) & 255u) >= drop.thresh ? drop.scale : 0.f;
+      v.w *= (int)((hsh >> 24) & 255u) >= drop.thresh ? drop.scale : 0.f;
     }
     *reinterpret_cast<float4*>(dproj + r * C + c) = v;
   }
@@ -873,7 +881,7 @@ __device__ __forceinline__ uint32_t pack2bf(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCoreBwdParams p, float* __restrict__ att_out) {
+__global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCoreBwdParams p, float* __restrict__ att_out, const DropCfg drop) {
   using namespace cbh;
   extern __shared__ __align__(16) uint8_t smraw[];
   const AttnGeom g_ = p.g;
@@ -966,11 +974,23 @@ __global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCo
       sa += __shfl_xor_sync(0xffffffffu, sa, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 2);
       sb += __shfl_xor_sync(0xffffffffu, sb, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
       const float ia_ = ia < S ? 1.0f / sa : 0.f, ib_ = ib < S ? 1.0f / sb : 0.f;      // padded query rows: P = 0
+      // dropout on the probabilities (maxvit.py:146): mk = mask * scale per element; smem holds P' = P*mk (used by att and dV),
+      // the registers keep P (the softmax Jacobian needs the undropped probabilities)
+      float mk[8][4];
+      const long long wdx = (long long)n * nwin + wi;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         pr[nt][0] *= ia_; pr[nt][1] *= ia_; pr[nt][2] *= ib_; pr[nt][3] *= ib_;
-        *reinterpret_cast<uint32_t*>(sP + ia * LDP + nt * 8 + 2 * t) = pack2bf(pr[nt][0], pr[nt][1]);
-        *reinterpret_cast<uint32_t*>(sP + ib * LDP + nt * 8 + 2 * t) = pack2bf(pr[nt][2], pr[nt][3]);
+        mk[nt][0] = mk[nt][1] = mk[nt][2] = mk[nt][3] = 1.0f;
+        if (drop.thresh) {
+          const int grp = nt * 2 + (t >> 1), sh = 16 * (t & 1);          // keys 4*grp .. 4*grp+3; this thread: bytes 2(t&1), 2(t&1)+1
+          const uint32_t ha = drop_hash(drop.seed, drop_row(wdx, ia), drop_group_prob(drop.salt, hd, grp)) >> sh;
+          const uint32_t hb = drop_hash(drop.seed, drop_row(wdx, ib), drop_group_prob(drop.salt, hd, grp)) >> sh;
+          mk[nt][0] = (int)(ha & 255u) >= drop.thresh ? drop.scale : 0.f; mk[nt][1] = (int)((ha >> 8) & 255u) >= drop.thresh ? drop.scale : 0.f;
+          mk[nt][2] = (int)(hb & 255u) >= drop.thresh ? drop.scale : 0.f; mk[nt][3] = (int)((hb >> 8) & 255u) >= drop.thresh ? drop.scale : 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(sP + ia * LDP + nt * 8 + 2 * t) = pack2bf(pr[nt][0] * mk[nt][0], pr[nt][1] * mk[nt][1]);
+        *reinterpret_cast<uint32_t*>(sP + ib * LDP + nt * 8 + 2 * t) = pack2bf(pr[nt][2] * mk[nt][2], pr[nt][3] * mk[nt][3]);
       }
       __syncwarp();
       if (att_out) {                                                // att = P V (re-materialised forward output)
@@ -988,6 +1008,10 @@ __global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCo
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
       warp_mma_bf16<8, DH, false, false>(dp, adO, LDQ, r0, aV, LDQ, lane);
+      if (drop.thresh) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { dp[nt][0] *= mk[nt][0]; dp[nt][1] *= mk[nt][1]; dp[nt][2] *= mk[nt][2]; dp[nt][3] *= mk[nt][3]; }
+      }
       float da = 0.f, db = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) { da += pr[nt][0] * dp[nt][0] + pr[nt][1] * dp[nt][1]; db += pr[nt][2] * dp[nt][2] + pr[nt][3] * dp[nt][3]; }
@@ -1278,17 +1302,54 @@ int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float
   return outer_sum_run(dhid, mean, N, se, C, dW1, nullptr, st);     // dW1[j][c] += sum_n dhid[n][j] mean[n][c]
 }
 
-int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, cudaStream_t st) {
+static DropCfg make_drop(unsigned seed, unsigned salt, int thresh) {
+  DropCfg d;
+  d.seed = seed; d.salt = salt; d.thresh = thresh; d.scale = 256.0f / (256.0f - (float)thresh);
+  return d;
+}
+
+int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, unsigned seed,
+                            unsigned salt, int drop_thresh, cudaStream_t st) {
   if (g.C % 128) return set_error("attn_out_bwd_gather: C %% 128 != 0");
+  if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_out_bwd_gather: dropout threshold %d outside [0, 255]", drop_thresh);
   const long long rows = (long long)g.N * g.nwin() * g.S();
-  attn_out_bwd_gather_kernel<<<nblk(rows, 8), 256, 0, st>>>(dx_out, dreg, reg_scale, g, dproj, rows);
+  attn_out_bwd_gather_kernel<<<nblk(rows, 8), 256, 0, st>>>(dx_out, dreg, reg_scale, g, dproj, rows, make_drop(seed, salt, drop_thresh));
   return check_launch("attn_out_bwd_gather_kernel");
+}
+
+// test hook: the masks as bytes
+__global__ void dropout_mask_debug_kernel(DropCfg drop, long long n_windows, int heads, int C, unsigned char* __restrict__ prob_mask,
+                                          unsigned char* __restrict__ out_mask) {
+  const long long total_p = n_windows * heads * 64 * 16, total_o = n_windows * 64 * (C / 4);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_p + total_o; idx += (long long)gridDim.x * blockDim.x) {
+    if (idx < total_p) {
+      const int g = (int)(idx % 16); long long r = idx / 16;
+      const int i = (int)(r % 64); r /= 64;
+      const int h = (int)(r % heads); const long long wdx = r / heads;
+      const uint32_t hsh = drop_hash(drop.seed, drop_row(wdx, i), drop_group_prob(drop.salt, h, g));
+      for (int k = 0; k < 4; ++k) prob_mask[((wdx * heads + h) * 64 + i) * 64 + g * 4 + k] = (int)((hsh >> (8 * k)) & 255u) >= drop.thresh;
+    } else {
+      const long long j = idx - total_p;
+      const int g = (int)(j % (C / 4)); long long r = j / (C / 4);
+      const int i = (int)(r % 64); const long long wdx = r / 64;
+      const uint32_t hsh = drop_hash(drop.seed, drop_row(wdx, i), drop_group_out(drop.salt, g));
+      for (int k = 0; k < 4; ++k) out_mask[(wdx * 64 + i) * C + g * 4 + k] = (int)((hsh >> (8 * k)) & 255u) >= drop.thresh;
+    }
+  }
+}
+
+int dropout_mask_debug_run(unsigned seed, unsigned salt, int drop_thresh, long long n_windows, int heads, int C, unsigned char* prob_mask,
+                           unsigned char* out_mask, cudaStream_t st) {
+  dropout_mask_debug_kernel<<<1024, 256, 0, st>>>(make_drop(seed, salt, drop_thresh), n_windows, heads, C, prob_mask, out_mask);
+  return check_launch("dropout_mask_debug_kernel");
 }
 
 int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
                       const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
-                      int use_tf32, float* att_out, cudaStream_t st) {
+                      int use_tf32, float* att_out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
   if (dh != 32) return set_error("attn_core_bwd: dim_head must be 32 (got %d)", dh);
+  if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_core_bwd: dropout threshold %d outside [0, 255]", drop_thresh);
+  if (drop_thresh && use_tf32 != 2) return set_error("attn_core_bwd: dropout is only built into the bf16 tensor-core kernel (mode 2)");
   if (g.S() > 64) return set_error("attn_core_bwd: sequence %d > 64", g.S());
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   if (use_tf32 == 2) {
@@ -1302,7 +1363,7 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
     AttnCoreBwdParams q;
     q.qkv = qkv; q.datt = datt; q.qgamma = qgamma; q.kgamma = kgamma; q.bias_table = bias_table; q.dqkv = dqkv;
     q.dqgamma = dqgamma; q.dkgamma = dkgamma; q.dbias_table = dbias_table; q.g = g; q.heads = heads;
-    attn_core_bwd_bf16_kernel<<<g.N * heads, 128, smem3, st>>>(q, att_out);
+    attn_core_bwd_bf16_kernel<<<g.N * heads, 128, smem3, st>>>(q, att_out, make_drop(seed, salt, drop_thresh));
     return check_launch("attn_core_bwd_bf16_kernel");
   }
   if (use_tf32) {

@@ -90,7 +90,7 @@ int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* 
 
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                    const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,
-                   cudaStream_t st);
+                   unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
 
 // ---- training (vg_wgrad.cu, vg_bwd.cu, vg_bwd_vit.cu)
 long long wgrad_workspace_elems(int dtype, long long M, int Ntot, int Ca, int ntaps);
@@ -141,10 +141,13 @@ int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long 
 int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
                const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
                long long work_elems, cudaStream_t st);
-int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, cudaStream_t st);
+int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, unsigned seed,
+                            unsigned salt, int drop_thresh, cudaStream_t st);
+int dropout_mask_debug_run(unsigned seed, unsigned salt, int drop_thresh, long long n_windows, int heads, int C, unsigned char* prob_mask,
+                           unsigned char* out_mask, cudaStream_t st);
 int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
                       const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
-                      int use_tf32, float* att_out, cudaStream_t st);
+                      int use_tf32, float* att_out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
 int attn_gather_bwd_run(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,
                         const float* dx_out, const float* dreg_res, float reg_scale, float* dx_in, float* dreg_in, float* dfilm,
                         const AttnGeom& g, float eps, cudaStream_t st);

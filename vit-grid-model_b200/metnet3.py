@@ -151,6 +151,7 @@ class MetNet3(nn.Module):
         self._capture = None          # debugging: set to a dict to collect stage outputs (NCHW copies)
         self._grad_buffer = None      # training: flat fp32 gradient buffer (train.GradBuffer)
         self._grad_sync = None        # training: data-parallel gradient all-reduce (set by parallel.DataParallel)
+        self._dropout_state = None
         self.dropout = dropout
 
     # ------------------------------------------------------------------ helpers
@@ -308,9 +309,19 @@ class MetNet3(nn.Module):
         from .train import MetNet3TrainFn
         if self.precision == "bf16_all":
             raise NotImplementedError("training supports set_precision('bf16') (mixed) and 'fp32'")
-        if self.dropout > 0:
-            raise NotImplementedError("attention dropout (maxvit.py:146,151) is not built yet: construct with dropout=0.0 to train")
+        if self.dropout > 0 and self.precision != "bf16":
+            raise NotImplementedError("attention dropout (maxvit.py:146,151) is built into the mixed-precision ('bf16') path only; "
+                                      "construct with dropout=0.0 to train in fp32")
         return MetNet3TrainFn.apply(self, x, ts, *self.parameters())
+
+    def next_dropout_seed(self) -> int:
+        """32-bit seed of this step's dropout masks: derived from torch's seed at the first training step (so that
+        torch.manual_seed reproduces a run) and advanced by one per step; the masks themselves are a counter-based hash
+        inside the kernels (vg_rng.cuh)"""
+        if self._dropout_state is None:
+            self._dropout_state = torch.initial_seed() & 0x7FFFFFFF
+        self._dropout_state = (self._dropout_state * 1103515245 + 12345) & 0x7FFFFFFF
+        return self._dropout_state
 
     def forward(self, x, labels_pm25=None, region_targets_pm25=None, labels_pm10=None, region_targets_pm10=None,
                 timestamps: torch.Tensor = None, prev_vals: torch.Tensor = None):

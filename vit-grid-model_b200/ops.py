@@ -231,15 +231,17 @@ def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     return torch.cat([shifted.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
 
 
-def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5):
-    """whole attention layer (+ residual) in one kernel; x CL (N,Hl,Wl,128) fp32"""
+def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5, drop=(0, 0, 0)):
+    """whole attention layer (+ residual) in one kernel; x CL (N,Hl,Wl,128) fp32.
+    drop = (seed, salt, T): training dropout with probability T/256 on the probabilities and the to_out output"""
     N, Hl, Wl, C = x.shape
     assert x.dtype == torch.float32
     nwin = (Hl // win) * (Wl // win)
     x_out = torch.empty_like(x)
     reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x.device) if want_reg_out else None
     _lib.call("vg_attn_fused_fwd", x.data_ptr(), x_out.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out),
-              film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps), _st())
+              film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
+              int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return x_out, reg_out
 
 

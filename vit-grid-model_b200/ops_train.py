@@ -235,17 +235,26 @@ def se_bwd(dh4, h3, gate, mean, hid, W1, W2, dW1, dW2):
     return dmean
 
 
-def attn_out_bwd_gather(dx_out, dreg, reg_scale, win, R, grid_mode):
+def dropout_masks(drop, n_windows, heads, C):
+    """test hook: the (prob_mask [Nw][heads][64][64], out_mask [Nw][64][C]) uint8 masks the kernels derive from drop = (seed, salt, T)"""
+    dev = torch.device("cuda")
+    pm = torch.empty(n_windows, heads, 64, 64, dtype=torch.uint8, device=dev)
+    om = torch.empty(n_windows, 64, C, dtype=torch.uint8, device=dev)
+    _lib.call("vg_dropout_mask_debug", int(drop[0]), int(drop[1]), int(drop[2]), n_windows, heads, C, pm.data_ptr(), om.data_ptr(), _st())
+    return pm, om
+
+
+def attn_out_bwd_gather(dx_out, dreg, reg_scale, win, R, grid_mode, drop=(0, 0, 0)):
     N, Hl, Wl, C = dx_out.shape
     rows = N * (Hl // win) * (Wl // win) * (R + win * win)
     dproj = torch.empty(rows, C, dtype=torch.float32, device=dx_out.device)
     _lib.call("vg_attn_out_bwd_gather", dx_out.data_ptr(), _p(dreg), float(reg_scale), N, Hl, Wl, C, win, R, int(grid_mode),
-              dproj.data_ptr(), _st())
+              dproj.data_ptr(), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return dproj
 
 
 def attn_core_bwd(qkv, datt, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, dq_gamma, dk_gamma, dbias_table,
-                  tf32=False, want_att=False):
+                  tf32=False, want_att=False, drop=(0, 0, 0)):
     """-> dqkv (, att = softmax(.) V re-materialised by the tensor-core kernel when want_att)"""
     dqkv = torch.empty_like(qkv)
     att = torch.empty(qkv.shape[0], heads * dh, dtype=torch.float32, device=qkv.device) if want_att else None
@@ -253,7 +262,7 @@ def attn_core_bwd(qkv, datt, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, he
     mode = 0 if not tf32 else (1 if os.environ.get("VG_ATTN_BWD", "bf16") == "tf32" else 2)
     _lib.call("vg_attn_core_bwd", qkv.data_ptr(), datt.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
               bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, dqkv.data_ptr(), dq_gamma.data_ptr(), dk_gamma.data_ptr(),
-              dbias_table.data_ptr(), mode, _p(att), _st())
+              dbias_table.data_ptr(), mode, _p(att), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return (dqkv, att) if want_att else dqkv
 
 

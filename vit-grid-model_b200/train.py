@@ -115,20 +115,22 @@ def _fused_ok(vit, C):
             and vit.num_register_tokens == 4 and vit.heads >= 4)
 
 
-def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out):
+def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out, drop=(0, 0, 0)):
     """mixed precision: the fused one-kernel attention, nothing but its inputs is kept (backward re-materialises
     tokens / qkv / att on the tensor cores); fp32 mode: unfused path, intermediates saved."""
     N, H, W, C = x.shape
     w, R = vit.vit_window_size, vit.num_register_tokens
     if _fused_ok(vit, C):
         x_out, reg_out = ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
-                                        vit.heads, vit.dim_head)
-        return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, grid_mode=grid_mode)
+                                        vit.heads, vit.dim_head, drop=drop)
+        return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, grid_mode=grid_mode, drop=drop)
+    if drop[2]:
+        raise NotImplementedError("attention dropout is built into the fused (mixed-precision) attention path only")
     tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
     qkv = ops.gemm(tokens, P["w_qkv"], tf32=vit.tf32)
     att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head)
     x_out, reg_out = ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=vit.tf32)
-    return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, tokens=tokens, qkv=qkv, att=att, grid_mode=grid_mode)
+    return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, tokens=tokens, qkv=qkv, att=att, grid_mode=grid_mode, drop=drop)
 
 
 def _attention_train_bwd(vit, sv, P, att_mod, pre, G, cond, dcond, dx_out, dreg_res, reg_scale, dreg_in):
@@ -144,11 +146,12 @@ def _attention_train_bwd(vit, sv, P, att_mod, pre, G, cond, dcond, dx_out, dreg_
         qkv = ops.gemm(tokens, P["w_qkv"], tf32=tf32)
     else:
         tokens, qkv = sv["tokens"], sv["qkv"]
-    dproj = ot.attn_out_bwd_gather(dx_out, dreg_res, reg_scale, w, R, gm)
+    drop = sv["drop"]
+    dproj = ot.attn_out_bwd_gather(dx_out, dreg_res, reg_scale, w, R, gm, drop=drop)
     datt = ops.gemm(dproj, att_mod.to_out[0].weight.detach().t().contiguous(), tf32=tf32)
     res = ot.attn_core_bwd(qkv, datt, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head,
                            G[pre + "q_norm.gamma"], G[pre + "k_norm.gamma"], G[pre + "rel_pos_bias.weight"], tf32=tf32,
-                           want_att=recompute)
+                           want_att=recompute, drop=drop)
     dqkv, att = res if recompute else (res, sv["att"])
     del datt, qkv
     ot.wgrad(dproj, att, G[pre + "to_out.0.weight"], tf32=tf32)
@@ -163,8 +166,13 @@ def _attention_train_bwd(vit, sv, P, att_mod, pre, G, cond, dcond, dx_out, dreg_
     return dx_in
 
 
-def maxvit_train_forward(vit, x, cond):
-    """x CL (N,H,W,C) fp32, cond (N,cd) -> (y, saved)"""
+def dropout_threshold(p: float) -> int:
+    """drop probability -> mask-byte threshold T (p_eff = T/256)"""
+    return max(0, min(255, int(round(p * 256))))
+
+
+def maxvit_train_forward(vit, x, cond, seed=0):
+    """x CL (N,H,W,C) fp32, cond (N,cd) -> (y, saved).  seed: dropout seed of this step (ignored when dropout is 0)"""
     N, H, W, C = x.shape
     w = vit.vit_window_size
     nwin = (H // w) * (W // w)
@@ -192,11 +200,12 @@ def maxvit_train_forward(vit, x, cond):
         sv = dict(x=x, h0=h0, st1=st1, h1=h1, h2=h2, st2=st2, h3=h3, gate=gate, mean=mean, hidv=hidv, h4=h4, y0=y0, st3=st3)
         fb = P["block"]
         film_b = ops.cond_mlp(cond, fb["film_w0"], fb["film_b0"], fb["film_w1"], fb["film_b1"])
-        xb, reg_out, sv["battn"] = _attention_train_fwd(vit, y, film_b, fb, P["reg"], False, True)
+        T = dropout_threshold(battn.dropout_p)
+        xb, reg_out, sv["battn"] = _attention_train_fwd(vit, y, film_b, fb, P["reg"], False, True, drop=(seed, 2 * li, T))
         reg = ops.reg_mean(reg_out, N, nwin)
         fg = P["grid"]
         film_g = ops.cond_mlp(cond, fg["film_w0"], fg["film_b0"], fg["film_w1"], fg["film_b1"])
-        x, _, sv["gattn"] = _attention_train_fwd(vit, xb, film_g, fg, reg, True, False)
+        x, _, sv["gattn"] = _attention_train_fwd(vit, xb, film_g, fg, reg, True, False, drop=(seed, 2 * li + 1, T))
         saved.append(sv)
     return x, saved
 
@@ -326,7 +335,7 @@ def metnet3_train_forward(model, x, ts):
     S["enc"], S["h_enc"] = enc, h
     # ---- MaxViT at half resolution
     low = ops.pool2(h, N, HP, WP, out_dtype=model.vit.compute_dtype)
-    low, S["vit"] = maxvit_train_forward(model.vit, low, cond)
+    low, S["vit"] = maxvit_train_forward(model.vit, low, cond, seed=model.next_dropout_seed())
     S["low_out"] = low
     # ---- decoder
     up = torch.zeros(ops.pg_pixels(N, HP, WP), C, dtype=dtype, device=dev)
