@@ -272,6 +272,9 @@ VG_API int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long 
 /* out[n][c] += sum_p a[n][p][c] * b[n][p][c] over the HW positions of each field (b = NULL: plain sums, the
  * squeeze-excite mean) */
 VG_API int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW, int C, void* stream);
+/* squeeze-excite scale folded into per-field weights of the following 1x1 projection: out[n][co][c] = W[co][c]*gate[n][c]
+ * (fp32; consumed by vg_gemm_fwd with rows_per_batch = H*W, b_rows_per_batch = Cout) */
+VG_API int vg_se_fold_weights(const float* W, const float* gate, float* out, int N, int Cout, int C, void* stream);
 VG_API int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream);
 VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,

@@ -295,7 +295,7 @@ def test_attention_fused(grid_mode, N, H, W):
     assert rel_err(reg_out, ref[:, :R]) < 4e-3
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3), ("bf16_all", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 6e-3), ("bf16_all", 3e-2)])
 def test_maxvit_module(precision, tol):
     """MaxViT nn.Module (reference API) vs oracle, depth 2 (second MBConv is residual)"""
     from vit_grid_model_b200 import MaxViT

@@ -96,3 +96,15 @@ def test_errors_like_reference():
         m(x.cuda())                              # timestamps missing
     with pytest.raises(AssertionError):
         m(x[:, :, :, :-1].cuda(), timestamps=ts.cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_depth2_backbone_vs_oracle(precision):
+    """vit_block_depth=2 (BASELINE configs[3]: 2x depth MaxViT; the second MBConv is residual) on a small domain vs the oracle"""
+    cfg = synth.GridConfig(T=3, C=24, H=26, W=25, dim=128, L=2, vit_depth=2)
+    m, sd = build(cfg, 3, precision)
+    x, ts, _ = synth.make_inputs(cfg, 2, seed=31)
+    ref = metnet3_forward(x, ts, sd, cfg)
+    with torch.no_grad():
+        y = m(x.cuda(), timestamps=ts.cuda())
+    assert rel_err(y, ref) < TOL[precision]

@@ -320,6 +320,21 @@ __global__ void __launch_bounds__(256) se_gate_train_kernel(const float* __restr
   }
 }
 
+// squeeze-excite scale folded into the per-field weights of the 1x1 projection that follows (maxvit.py:47 + :95):
+//   Wn[n][co][c] = W[co][c] * gate[n][c]    -- 256 KB per field instead of a read-modify-write pass over the activations
+__global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ W, const float* __restrict__ gate, float* __restrict__ out,
+                                                      int Cout, int C, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const long long e = i * 4;
+  const int c = (int)(e % C);
+  const long long r = e / C;
+  const int co = (int)(r % Cout);
+  const long long n = r / Cout;
+  const float4 w = *reinterpret_cast<const float4*>(W + (long long)co * C + c), g = *reinterpret_cast<const float4*>(gate + n * C + c);
+  *reinterpret_cast<float4*>(out + e) = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+}
+
 // out[n][p][c] = x[n][p][c] * gate[n][c]   (out of place: training keeps the pre-gate activations)
 __global__ void __launch_bounds__(256) se_scale_oop_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ out,
                                                            long long HW, int C, long long total4) {
@@ -1273,6 +1288,13 @@ int field_dot_run(const float* a, const float* b, float* out, int N, long long H
   if (chunks > 16) chunks = 16;
   field_dot_kernel<<<dim3(chunks, N), 256, 0, st>>>(a, b, out, HW, C);
   return check_launch("field_dot_kernel");
+}
+
+int se_fold_run(const float* W, const float* gate, float* out, int N, int Cout, int C, cudaStream_t st) {
+  if (C % 4) return set_error("se_fold: C %% 4 != 0");
+  const long long total4 = (long long)N * Cout * C / 4;
+  se_fold_kernel<<<nblk(total4, 256), 256, 0, st>>>(W, gate, out, Cout, C, total4);
+  return check_launch("se_fold_kernel");
 }
 
 int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st) {

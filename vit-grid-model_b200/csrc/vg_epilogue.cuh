@@ -373,6 +373,56 @@ __device__ __forceinline__ void epi_convt(const EpiParams& ep, long long row, bo
   }
 }
 
+// EPI_CONVT for the tcgen05 kernel with the same shared-memory transposition as epi_store_coalesced: every output pixel's
+// 128 channels of one tap are contiguous in the PG buffer, so a warp instruction writes four full row segments.
+template <typename T, class Loader>
+__device__ __forceinline__ void epi_convt_coalesced(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld, float* stg, int lane) {
+  constexpr int LDS_ = 36;
+  const int C = ep.n_total / 4;
+  const int tap = n0 / C, cbase = n0 - tap * C;
+  const int lo = ep.Hl * ep.Wl;
+  long long o = -1;                                        // element offset of this lane's row in the output (or -1)
+  if (ok) {
+    const int n = (int)(row / lo);
+    const int p = (int)(row - (long long)n * lo);
+    const int i = p / ep.Wl, j0 = p - i * ep.Wl;
+    o = ep.pg.q(n, 2 * i + (tap >> 1), 2 * j0 + (tap & 1)) * ep.ldo + cbase;
+  }
+  const int rr = lane >> 3, cq = (lane & 7) * 4;
+  float v[32];
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    const bool live = cbase + ch * 32 < C;                 // warp-uniform
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase + ch * 32 + cq));
+    ld.load(ch, v);
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * LDS_ + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rr;
+      const long long orow = __shfl_sync(0xffffffffu, o, r);
+      if (orow >= 0) {
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS_ + cq);
+        const float4 y = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
+        const long long off = orow + ch * 32 + cq;
+        const bool f32out = ep.out_f32 == 1 || (ep.out_f32 == 0 && sizeof(T) == 4);
+        if (f32out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = y;
+        else {
+          uint2 u;
+          *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(y.x, y.y);
+          *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(y.z, y.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + off) = u;
+        }
+        if (ep.out2) *reinterpret_cast<float4*>(ep.out2 + off) = y;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int KIND, typename T, class Loader>
 __device__ __forceinline__ void run_epilogue(const EpiParams& ep, const EpiCtx& cx, long long row, bool ok, int n0, Loader& ld) {
   if constexpr (KIND == EPI_STORE) epi_store<T>(ep, row, ok, n0, ld);

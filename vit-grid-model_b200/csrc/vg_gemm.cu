@@ -52,8 +52,9 @@ template <int KIND, int TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmShape gs, const EpiParams ep) {
-  constexpr int STAGES = KIND == EPI_STORE ? STORE_STAGES : vg::STAGES;
-  constexpr int PARAM_BYTES = KIND == EPI_STORE ? STORE_STG_FLOATS * 4 : PARAM_FLOATS * 4;
+  constexpr bool STAGED = KIND == EPI_STORE || KIND == EPI_CONVT;      // epilogues that transpose through shared memory
+  constexpr int STAGES = STAGED ? STORE_STAGES : vg::STAGES;
+  constexpr int PARAM_BYTES = STAGED ? STORE_STG_FLOATS * 4 : PARAM_FLOATS * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sparam = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -178,6 +179,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float* stg = sparam + (warp - 4) * (32 * 36);
         if (TF32) epi_store_coalesced<float>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
         else epi_store_coalesced<bf16>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+      } else if constexpr (KIND == EPI_CONVT) {
+        float* stg = sparam + (warp - 4) * (32 * 36);
+        if (TF32) epi_convt_coalesced<float>(ep, row, ok, n_tile * BN, ld, stg, lane);
+        else epi_convt_coalesced<bf16>(ep, row, ok, n_tile * BN, ld, stg, lane);
       } else {
         if (TF32) run_epilogue<KIND, float>(ep, cx, row, ok, n_tile * BN, ld);
         else run_epilogue<KIND, bf16>(ep, cx, row, ok, n_tile * BN, ld);
@@ -459,7 +464,7 @@ static int num_sms() {
 template <int KIND, int TF32>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int SMEM = KIND == EPI_STORE ? TC_SMEM_BYTES_STORE : TC_SMEM_BYTES;
+  constexpr int SMEM = (KIND == EPI_STORE || KIND == EPI_CONVT) ? TC_SMEM_BYTES_STORE : TC_SMEM_BYTES;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));

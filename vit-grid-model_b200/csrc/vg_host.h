@@ -137,6 +137,7 @@ int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, fl
 int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C, int se,
                       float* gate, float* mean, float* hid, cudaStream_t st);
 int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st);
+int se_fold_run(const float* W, const float* gate, float* out, int N, int Cout, int C, cudaStream_t st);
 int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st);
 int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
                const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,

@@ -8,6 +8,27 @@
 
 namespace vg {
 
+// 4 consecutive activations <-> float4 (8-byte vector for bf16)
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Ld4<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
 // ================================================================================================
 // prepare: x (B,T,C,H,W) fp32, arbitrary strides -> PG layout [q][Cpad] with PM2.5 channels standardised
 // (metnet3.py:361-380), spatially zero-padded into the HPxWP frame (metnet3.py:384), channel padded with zeros.
@@ -137,57 +158,72 @@ __global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_
 // ================================================================================================
 
 template <typename T>
-__global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
-  constexpr int C = 128;
-  const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (q >= p.pgN.pixels()) return;
+__global__ void __launch_bounds__(256, 4) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
+  constexpr int C = 128, PX = 2;                   // pixels per warp: the loads of both pixels are in flight together
+  const long long q0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PX;
+  if (q0 >= p.pgN.pixels()) return;
   const int lane = threadIdx.x & 31, c0 = lane * 4;
-  int n, h, w;
-  const bool valid = p.pgN.decode(q, n, h, w);
-  float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
-  unsigned nib = 0u;
-  float rstd_save = 0.f;
-  if (valid) {
-    const int b = n / p.L;
-    const long long qb = p.pgB.q(b, h, w);
-    const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1), rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
-    const float4 a = *reinterpret_cast<const float4*>(p.raw3 + qb * C + c0);
-    const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0);
-    const float4 t = *reinterpret_cast<const float4*>(p.tt + ((long long)n * 9 + ry * 3 + rx) * C + c0);
-    float v[4] = {a.x + bb.x + t.x, a.y + bb.y + t.y, a.z + bb.z + t.z, a.w + bb.w + t.w};
-    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
-    float ss = 0.f;
+  const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0), rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
+  const float4 g4 = *reinterpret_cast<const float4*>(p.ln_g + c0), b4 = *reinterpret_cast<const float4*>(p.ln_b + c0);
+  bool valid[PX];
+  int nn[PX];
+  float4 a[PX], tt[PX], ra[PX], rt[PX], f0[PX], f1[PX];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
-    const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
-    rstd_save = rstd;
-    const float* film = p.film + (long long)n * 2 * C;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      xh[i] = v[i] * rstd;
-      float z = xh[i] * p.ln_g[c0 + i] + p.ln_b[c0 + i];
-      z = z * (film[c0 + i] + 1.0f) + film[C + c0 + i];
-      if (z > 0.f) nib |= 1u << i;
-      y[i] = fmaxf(z, 0.f);
+  for (int k = 0; k < PX; ++k) {
+    const long long q = q0 + k;
+    int n = 0, h = 0, w = 0;
+    valid[k] = q < p.pgN.pixels() && p.pgN.decode(q, n, h, w);
+    nn[k] = n;
+    if (valid[k]) {
+      const int b = n / p.L;
+      const long long qb = p.pgB.q(b, h, w);
+      const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1), rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
+      a[k] = *reinterpret_cast<const float4*>(p.raw3 + qb * C + c0);
+      tt[k] = *reinterpret_cast<const float4*>(p.tt + ((long long)n * 9 + ry * 3 + rx) * C + c0);
+      ra[k] = *reinterpret_cast<const float4*>(p.rawres + qb * C + c0);
+      rt[k] = *reinterpret_cast<const float4*>(p.tres + (long long)n * C + c0);
+      f0[k] = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c0);
+      f1[k] = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + C + c0);
     }
-    const float4 ra = *reinterpret_cast<const float4*>(p.rawres + qb * C + c0);
-    const float4 rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
-    const float4 rt = *reinterpret_cast<const float4*>(p.tres + (long long)n * C + c0);
-    r[0] = ra.x + rb.x + rt.x; r[1] = ra.y + rb.y + rt.y; r[2] = ra.z + rb.z + rt.z; r[3] = ra.w + rb.w + rt.w;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) Act<T>::st(h1 + q * C + c0 + i, y[i]);
-  *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
-  if (p.xhat) {                                   // training: what the backward pass needs
-    T* xo = reinterpret_cast<T*>(p.xhat);
+  for (int k = 0; k < PX; ++k) {
+    const long long q = q0 + k;
+    if (q >= p.pgN.pixels()) break;
+    float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned nib = 0u;
+    float rstd_save = 0.f;
+    if (valid[k]) {
+      float v[4] = {a[k].x + bb.x + tt[k].x, a[k].y + bb.y + tt[k].y, a[k].z + bb.z + tt[k].z, a[k].w + bb.w + tt[k].w};
+      const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
+      float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) Act<T>::st(xo + q * C + c0 + i, xh[i]);
-    unsigned wbits = nib << ((lane & 7) * 4);
-    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
-    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
-    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
-    if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
-    if (lane == 0) p.rstd[q] = rstd_save;
+      for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
+      const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
+      rstd_save = rstd;
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float s[4] = {f0[k].x, f0[k].y, f0[k].z, f0[k].w}, t[4] = {f1[k].x, f1[k].y, f1[k].z, f1[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xh[i] = v[i] * rstd;
+        float z = xh[i] * g[i] + be[i];
+        z = z * (s[i] + 1.0f) + t[i];
+        if (z > 0.f) nib |= 1u << i;
+        y[i] = fmaxf(z, 0.f);
+      }
+      r[0] = ra[k].x + rb.x + rt[k].x; r[1] = ra[k].y + rb.y + rt[k].y; r[2] = ra[k].z + rb.z + rt[k].z; r[3] = ra[k].w + rb.w + rt[k].w;
+    }
+    Ld4<T>::st(h1 + q * C + c0, make_float4(y[0], y[1], y[2], y[3]));
+    *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
+    if (p.xhat) {                                   // training: what the backward pass needs
+      Ld4<T>::st(reinterpret_cast<T*>(p.xhat) + q * C + c0, make_float4(xh[0], xh[1], xh[2], xh[3]));
+      unsigned wbits = nib << ((lane & 7) * 4);
+      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+      if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
+      if (lane == 0) p.rstd[q] = rstd_save;
+    }
   }
 }
 
@@ -426,7 +462,7 @@ int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0
 }
 
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st) {
-  const unsigned g = nblk(p.pgN.pixels(), 8);
+  const unsigned g = nblk(p.pgN.pixels(), 8 * 2);
   if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), res);
   else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), res);
   return check_launch("stem_finish_kernel");

@@ -219,9 +219,16 @@ class MaxViT(nn.Module):
             h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
             del h
             gate = ops.se_gate(psum, H * W, P["se_w1"], P["se_w2"])
-            ops.se_scale_(h2, gate)
-            y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
-                         res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
+            if x.dtype == torch.float32:
+                # the squeeze-excite scale rides on per-field projection weights (256 KB per field) instead of a
+                # read-modify-write pass over the hidden activations
+                wn = ops.se_fold_weights(P["w_proj"], gate)
+                y = ops.gemm(h2.view(N * H * W, hidden), wn, rows_per_batch=H * W, b_rows_per_batch=C, scale=P["s_proj"],
+                             shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
+            else:
+                ops.se_scale_(h2, gate)
+                y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
+                             res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
             del h2
             x = y.view(N, H, W, C)
             cap = self._capture

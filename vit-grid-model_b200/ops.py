@@ -173,6 +173,15 @@ def se_gate(psum, HW, W1, W2):
     return gate
 
 
+def se_fold_weights(W, gate):
+    """(Cout, C) fp32 projection weights x (N, C) gates -> per-field weights (N*Cout, C)"""
+    Cout, C = W.shape
+    N = gate.shape[0]
+    out = torch.empty(N * Cout, C, dtype=torch.float32, device=W.device)
+    _lib.call("vg_se_fold_weights", W.data_ptr(), gate.data_ptr(), out.data_ptr(), N, Cout, C, _st())
+    return out
+
+
 def se_scale_(x, gate):
     N, H, W, C = x.shape
     _lib.call("vg_se_scale_fwd", DT_CODE[x.dtype], x.data_ptr(), gate.data_ptr(), N, H * W, C, _st())
