@@ -266,11 +266,12 @@ VG_API int vg_dw3x3_fwd(int dtype, const void* in, const float* w9, const float*
 VG_API int vg_dw3x3_wgrad(const float* x, const float* dY, int N, int H, int W, int C, float* dw9, float* dbias, float* work,
                    long long work_elems, void* stream);
 /* squeeze-excite (maxvit.py:33-48) with saved intermediates, out-of-place scale, and backward (dW1, dW2 accumulated,
- * dmean (N,C) already divided by HW); work: N*(2C+se) floats */
+ * dmean (N,C) already divided by HW); work: N*((vg_field_parts(HW)+1)*C+se) floats */
 VG_API int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C,
                          int se, float* gate, float* mean, float* hid, void* stream);
-/* out[n][c] += sum_p a[n][p][c] * b[n][p][c] over the HW positions of each field (b = NULL: plain sums, the
- * squeeze-excite mean) */
+/* out[n][k][c] = sum over chunk k of the HW positions of a[n][p][c] * b[n][p][c] (b = NULL: plain sums, the squeeze-excite
+ * mean); k < vg_field_parts(HW); deterministic partial sums, no atomics */
+VG_API int vg_field_parts(long long HW);
 VG_API int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW, int C, void* stream);
 /* squeeze-excite scale folded into per-field weights of the following 1x1 projection: out[n][co][c] = W[co][c]*gate[n][c]
  * (fp32; consumed by vg_gemm_fwd with rows_per_batch = H*W, b_rows_per_batch = Cout) */

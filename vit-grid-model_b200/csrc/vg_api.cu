@@ -369,6 +369,8 @@ int vg_se_gate_train_fwd(const float* psum, int N, int nparts, long long HW, con
   return se_gate_train_run(psum, N, nparts, HW, W1, W2, C, se, gate, mean, hid, (cudaStream_t)stream);
 }
 
+int vg_field_parts(long long HW) { return field_parts(HW); }
+
 int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW, int C, void* stream) {
   return field_dot_run(a, b, out, N, HW, C, (cudaStream_t)stream);
 }

@@ -15,8 +15,9 @@
 //                                    accumulated over heads
 //   epilogue: Out + residual, scattered back through the inverse partition map; register-token rows to reg_out.
 //
-// Warp roles: warp 0 = TMA (weights, tables), warp 1 = MMA issuer, warps 2..9 = 256 compute threads (two per token row
-// = TMEM lane).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
+// Warp roles: warp 0 = TMA (weights, tables), warp 1 = MMA issuer, warps 2..9 = softmax warps (two threads per token row =
+// TMEM lane; they also gather / LayerNorm the tile and write it back), warps 10..17 = staging warps (K" / V^T operands and
+// 1/|q| of the next head, concurrently with the softmax of the current one).  All operand tiles written by threads use the same K-major SWIZZLE_128B layout TMA produces.
 #include <stdlib.h>
 
 #include "vg_common.cuh"
@@ -39,9 +40,10 @@ constexpr int VT_OFF = R1_OFF + 2 * 32768;       // 2 x [2 k-blocks x 32 rows x 
 constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
 constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
 constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
-constexpr int BAR_OFF = RED_OFF + 4 * 1024;
+constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // 2 x float[128]: 1/|q| per row (staging warps -> softmax warps), double-buffered over heads
+constexpr int BAR_OFF = QINV_OFF + 2 * 512;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
-constexpr int THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 compute (2 threads per token row)
+constexpr int THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / tile prologue + epilogue, warps 10..17 operand staging (2 threads per token row each)
 // TMEM columns
 constexpr int T_QKV0 = 0;      // 96   (QKV accumulators of even heads)
 constexpr int T_O = 96;        // 32
@@ -211,11 +213,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         mbar_wait_tag(wq_full, hh & 1, 203);
         tc_fence_after();
         const uint32_t d = tmem + ((hh & 1) ? T_QKV1 : T_QKV0);
-#pragma unroll
+        // running descriptors (not 32 pre-computed ones): they stay in uniform registers, so every tcgen05.mma issues
+        // without a vector->uniform register round trip
+        uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ);
+#pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = umma_desc_k128(sX + kb * 16384), db = umma_desc_k128(sWQ + kb * 12288);
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_tf32(d, da + 2 * k, db + 2 * k, id_qkv, (kb | k) ? 1u : 0u);
+          da += 16384 >> 4; db += 12288 >> 4;
         }
         tc_commit(qkv_done + (hh & 1));
         tc_commit(wq_free);
@@ -250,35 +255,101 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (md) md[1] = clock64();
           if (h + 1 < heads) issue_s(it + 1);
           if (md) md[2] = clock64();
-          // ---- O = P V
+          // ---- PV(h) first (it releases the operand buffers the staging warps wait for), then out(h) interleaved with the QKV
+          // projection of head h+3: the two accumulate into different TMEM columns.  (QKV(h+3) may not be mixed with S(h+1): it
+          // overwrites the q columns that product reads.)
+          const bool do_qkv = h + 3 < heads;
+          const uint32_t hq = it + 3;
+          {
+            const uint64_t dpa = umma_desc_k128(sR1), dvt = umma_desc_k128(sVT);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t da = umma_desc_k128(sR1 + kb * 16384), db = umma_desc_k128(sVT + kb * 4096);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + T_O, da + 2 * k, db + 2 * k, id_pv, (kb | k) ? 1u : 0u);
+            for (int st = 0; st < 8; ++st) {                       // O = P V
+              const int kb = st >> 2, k = st & 3;
+              tc_mma_bf16(tmem + T_O, dpa + kb * (16384 >> 4) + 2 * k, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
+            }
+            tc_commit(pv_done + r);
           }
-          tc_commit(pv_done + r);
           if (md) md[3] = clock64();
-          // ---- Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM; P was normalised before the PV product)
           mbar_wait_tag(wo_full, it & 1, 246);
           if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
+          if (do_qkv) mbar_wait_tag(wq_full, hq & 1, 203);
           tc_fence_after();
           if (md) md[4] = clock64();
           {
-            const uint64_t db = umma_desc_k128(sWO);
+            const uint32_t dq = tmem + ((hq & 1) ? T_QKV1 : T_QKV0);
+            const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ), dwo = umma_desc_k128(sWO);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * k, db + 2 * k, id_out, (h | k) ? 1u : 0u);
+            for (int st = 0; st < 16; ++st) {
+              if (do_qkv) {
+                const int kb = st >> 2, k = st & 3;
+                tc_mma_tf32(dq, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
+              }
+              if (st < 4) {                                        // Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM)
+                tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);
+                if (st == 3) tc_commit(wo_free);
+              }
+            }
+            if (do_qkv) { tc_commit(qkv_done + (hq & 1)); tc_commit(wq_free); }
           }
-          tc_commit(wo_free);
-          if (md) md[5] = clock64();
-          if (h + 3 < heads) issue_qkv(it + 3);
-          if (md) { md[6] = clock64(); md[7] = md[6]; }
+          if (md) { md[5] = clock64(); md[6] = md[5]; md[7] = md[5]; }
         }
         tc_commit(tile_done);
       }
     }
+  } else if (warp >= 10) {
+    // ============================== staging warps: QKV accumulator -> MMA operands, one head ahead of the softmax ==============================
+    const int lg = warp & 3;                                 // TMEM lane group this warp may access
+    const int ch = (warp - 10) >> 2;                         // 0: q norm + K" operand, 1: V^T operand
+    const int t = lg * 32 + lane;                            // tile row == TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
+    const uint32_t s_base = smem_u32(smem);
+    float* qinv = reinterpret_cast<float*>(smem + QINV_OFF);
+    uint32_t itx = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int hx = 0; hx < heads; ++hx, ++itx) {
+        const uint32_t r = itx & 1;
+        const uint32_t R1 = s_base + R1_OFF + r * 32768;
+        const uint32_t VT = s_base + VT_OFF + r * 8192;
+        mbar_wait_tag(qkv_done + r, (itx >> 1) & 1, 352);
+        tc_fence_after();
+        const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
+        if (ch == 0) {
+          const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);   // 32 * gamma_q * gamma_k
+          float v[32], w[32];
+          tmem_ld32(tq, v);                                              // q
+          tmem_ld32(tq + 32, w);                                         // k
+          tmem_wait_ld();
+          float nq = 0.f, nk = 0.f;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) { nq = fmaf(v[d], v[d], nq); nk = fmaf(w[d], w[d], nk); }
+          const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);           // F.normalize(eps=1e-12)  (maxvit.py:30)
+          const float inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
+          if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 353);    // R1[r], qinv[r] of head itx-2 are no longer in use
+          qinv[r * 128 + t] = inv_q;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 gm = __ldg(ksc + c);
+            sts128(R1 + sw128(t, c), w[4 * c] * inv_k * gm.x, w[4 * c + 1] * inv_k * gm.y, w[4 * c + 2] * inv_k * gm.z, w[4 * c + 3] * inv_k * gm.w);
+          }
+        } else {
+          float w[32];
+          tmem_ld32(tq + 64, w);                                         // v
+          tmem_wait_ld();
+          if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 354);    // VT[r] no longer read by MMAs
+          // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
+          const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
+          const int kc = (t & 63) >> 3;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) sts16(vt + sw128(d, kc), __bfloat16_as_ushort(__float2bfloat16(w[d])));
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qk_ready + r);
+      }
+    }
   } else {
-    // ============================== compute warps: two threads per token row ==============================
+    // ============================== softmax warps: two threads per token row ==============================
     const int cw = warp - 2;                                 // 0..7
     const int lg = warp & 3;                                 // TMEM lane group this warp may access
     const int ch = cw >> 2;                                  // column half handled by this thread
@@ -298,6 +369,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
     for (int c = 0; c < 8; ++c) swz[c] = sw128(t, c);
     float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [4][128][2]: 0 softmax sum, 1 LN sum, 2 softmax max, 3 LN sq-sum
+    const float* qinv = reinterpret_cast<const float*>(smem + QINV_OFF);
     const float rs = sqrtf((float)DH);
     uint32_t it = 0, tl = 0;
 
@@ -356,64 +428,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(x_ready);
 
-      // 1/|q| of the head whose softmax comes next; step2 runs one head ahead of the softmax (software pipeline):
-      //   step2(h+1) | softmax(h) | step2(h+2) | softmax(h+1) ...   so the S product of head h+1 and the PV / out-projection
-      //   of head h execute on the tensor pipe while the compute warps are busy with the other stage.
-      float inv_q_next = 0.f;
-      auto step2 = [&](uint32_t itx, int hx) {
-        const uint32_t r = itx & 1;
-        const uint32_t R1 = s_base + R1_OFF + r * 32768;
-        const uint32_t VT = s_base + VT_OFF + r * 8192;
-        const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);   // 32 * gamma_q * gamma_k
-        float4 gm[8];
-        if (ch == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) gm[c] = __ldg(ksc + c);
-        }
-        mbar_wait_tag(qkv_done + r, (itx >> 1) & 1, 352);
-        tc_fence_after();
-        const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
-        float v[32], w[32];
-        tmem_ld32(tq, v);                                                // q: both threads of the row need its norm
-        tmem_ld32(tq + 32 + ch * 32, w);                                 // ch 0: k, ch 1: v
-        tmem_wait_ld();
-        float nq = 0.f;
-#pragma unroll
-        for (int d = 0; d < 32; ++d) nq = fmaf(v[d], v[d], nq);
-        inv_q_next = 1.0f / fmaxf(sqrtf(nq), 1e-12f);                    // F.normalize(eps=1e-12)  (maxvit.py:30)
-        float inv_k = 0.f;
-        if (ch == 0) {
-          float nk = 0.f;
-#pragma unroll
-          for (int d = 0; d < 32; ++d) nk = fmaf(w[d], w[d], nk);
-          inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
-        }
-        if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 353);      // R1[r] / VT[r] no longer read by MMAs
-        if (ch == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts128(R1 + swz[c], w[4 * c] * inv_k * gm[c].x, w[4 * c + 1] * inv_k * gm[c].y, w[4 * c + 2] * inv_k * gm[c].z, w[4 * c + 3] * inv_k * gm[c].w);
-        } else {
-          // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
-          const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
-          const int kc = (t & 63) >> 3;
-#pragma unroll
-          for (int d = 0; d < 32; ++d) sts16(vt + sw128(d, kc), __bfloat16_as_ushort(__float2bfloat16(w[d])));
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qk_ready + r);
-      };
-      step2(it, 0);
       for (int h = 0; h < heads; ++h, ++it) {
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
         if (dbg) p.dbg[h * 8 + 0] = clock64();
         const uint32_t r = it & 1;
         const uint32_t R1 = s_base + R1_OFF + r * 32768;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
-        const float inv_q = inv_q_next;
-        if (h + 1 < heads) step2(it + 1, h + 1);
         if (dbg) p.dbg[h * 8 + 1] = clock64();
         mbar_wait_tag(tab_full + r, (it >> 1) & 1, 394);                          // per-head bias table (TMA)
         if (dbg) { const long long c2 = clock64(); p.dbg[h * 8 + 2] = c2; p.dbg[h * 8 + 3] = c2; }
@@ -426,6 +446,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           float sc[32];
           tmem_ld32(lane_addr + T_S + half * 64 + ch * 32, sc);
           tmem_wait_ld();
+          const float inv_q = qinv[r * 128 + t];             // written by the staging warps before qk_ready -> S -> s_done
           const float t169 = reinterpret_cast<const float*>(smem + TAB_OFF)[r * TAB_FLOATS + 7 * 13 * 8];
           const uint32_t brow = tab + (bi * 13 * 8) * 4;
           float m = -INFINITY;

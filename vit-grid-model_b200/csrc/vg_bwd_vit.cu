@@ -347,7 +347,9 @@ __global__ void __launch_bounds__(256) se_scale_oop_kernel(const float* __restri
   *reinterpret_cast<float4*>(out + e) = make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w);
 }
 
-// dgate[n][c] = sum_p a[n][p][c] * b[n][p][c]        grid (chunks, N)
+// out[n][chunk][c] = sum over the chunk's positions p of a[n][p][c] * b[n][p][c]  (b = NULL: plain sums)   grid (chunks, N)
+// Deterministic: per-chunk partial sums, no atomics (the squeeze-excite mean feeds the forward pass; run-to-run bit
+// differences there are amplified to tf32-rounding level by the layers that follow).
 __global__ void __launch_bounds__(256) field_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                                         long long HW, int C) {
   const int n = blockIdx.y;
@@ -358,20 +360,23 @@ __global__ void __launch_bounds__(256) field_dot_kernel(const float* __restrict_
   for (int c = threadIdx.x; c < C; c += 256) {
     float s = 0.f;
     for (long long p = p0; p < p1; ++p) { const long long i = ((long long)n * HW + p) * C + c; s = b ? fmaf(a[i], b[i], s) : s + a[i]; }
-    atomicAdd(out + (long long)n * C + c, s);
+    out[((long long)n * gridDim.x + blockIdx.x) * C + c] = s;
   }
 }
 
 // per field: dpre2 = dgate*gate*(1-gate); dhid = relu'(hid) * W2^T dpre2; dmean = W1^T dhid  (scaled by 1/HW for the apply)
-__global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate, const float* __restrict__ hid,
-                                                     const float* __restrict__ W1, const float* __restrict__ W2, int C, int se, float inv_count,
-                                                     float* __restrict__ dpre2, float* __restrict__ dhid, float* __restrict__ dmean) {
+__global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ dgate_parts, int nparts, const float* __restrict__ gate,
+                                                     const float* __restrict__ hid, const float* __restrict__ W1, const float* __restrict__ W2,
+                                                     int C, int se, float inv_count, float* __restrict__ dpre2, float* __restrict__ dhid,
+                                                     float* __restrict__ dmean) {
   extern __shared__ float sh[];
   float* sp = sh; float* sd = sh + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gate[(long long)n * C + c];
-    const float v = dgate[(long long)n * C + c] * g * (1.0f - g);
+    float dg = 0.f;
+    for (int k = 0; k < nparts; ++k) dg += dgate_parts[((long long)n * nparts + k) * C + c];
+    const float v = dg * g * (1.0f - g);
     sp[c] = v; dpre2[(long long)n * C + c] = v;
   }
   __syncthreads();
@@ -1283,10 +1288,13 @@ int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const 
   return check_launch("se_gate_train_kernel");
 }
 
-int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st) {
+int field_parts(long long HW) {
   int chunks = (int)((HW + 127) / 128);
-  if (chunks > 16) chunks = 16;
-  field_dot_kernel<<<dim3(chunks, N), 256, 0, st>>>(a, b, out, HW, C);
+  return chunks > 16 ? 16 : (chunks < 1 ? 1 : chunks);
+}
+
+int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st) {
+  field_dot_kernel<<<dim3(field_parts(HW), N), 256, 0, st>>>(a, b, out, HW, C);
   return check_launch("field_dot_kernel");
 }
 
@@ -1306,17 +1314,14 @@ int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long 
 int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
                const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
                long long work_elems, cudaStream_t st) {
-  const long long need = (long long)N * (2 * C + se);
+  const int nparts = field_parts(HW);
+  const long long need = (long long)N * ((nparts + 1) * C + se);
   if (work_elems < need) return set_error("se_bwd: workspace too small");
-  float* dgate = work; float* dpre2 = dgate + (long long)N * C; float* dhid = dpre2 + (long long)N * C;
-  cudaError_t e = cudaMemsetAsync(dgate, 0, (size_t)N * C * sizeof(float), st);
-  if (e != cudaSuccess) return set_error("se_bwd memset: %s", cudaGetErrorString(e));
-  int chunks = (int)((HW + 127) / 128);
-  if (chunks > 16) chunks = 16;
-  field_dot_kernel<<<dim3(chunks, N), 256, 0, st>>>(dh4, h3, dgate, HW, C);
+  float* dgate = work; float* dpre2 = dgate + (long long)N * nparts * C; float* dhid = dpre2 + (long long)N * C;
+  field_dot_kernel<<<dim3(nparts, N), 256, 0, st>>>(dh4, h3, dgate, HW, C);
   int rc = check_launch("field_dot_kernel");
   if (rc) return rc;
-  se_bwd_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(dgate, gate, hid, W1, W2, C, se, 1.0f / (float)HW, dpre2, dhid, dmean);
+  se_bwd_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(dgate, nparts, gate, hid, W1, W2, C, se, 1.0f / (float)HW, dpre2, dhid, dmean);
   rc = check_launch("se_bwd_kernel");
   if (rc) return rc;
   rc = outer_sum_run(dpre2, hid, N, C, se, dW2, nullptr, st);       // dW2[c][j] += sum_n dpre2[n][c] hid[n][j]

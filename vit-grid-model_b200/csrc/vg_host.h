@@ -136,6 +136,7 @@ int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, fl
                  long long work_elems, cudaStream_t st);
 int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C, int se,
                       float* gate, float* mean, float* hid, cudaStream_t st);
+int field_parts(long long HW);
 int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st);
 int se_fold_run(const float* W, const float* gate, float* out, int N, int Cout, int C, cudaStream_t st);
 int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st);

@@ -199,9 +199,9 @@ def dw3x3_wgrad(x, dY, dw9, dbias):
 
 
 def field_sum(x):
-    """(N,H,W,C) fp32 -> (N,1,C) per-field channel sums"""
+    """(N,H,W,C) fp32 -> (N, parts, C) deterministic partial per-field channel sums"""
     N, H, W, C = x.shape
-    out = torch.zeros(N, 1, C, dtype=torch.float32, device=x.device)
+    out = torch.empty(N, _lib.load().vg_field_parts(H * W), C, dtype=torch.float32, device=x.device)
     _lib.call("vg_field_dot", x.data_ptr(), None, out.data_ptr(), N, H * W, C, _st())
     return out
 
@@ -229,7 +229,7 @@ def se_bwd(dh4, h3, gate, mean, hid, W1, W2, dW1, dW2):
     N, H, W, C = h3.shape
     se = W1.shape[0]
     dmean = torch.empty(N, C, dtype=torch.float32, device=h3.device)
-    work = _f32(N * (2 * C + se), h3.device)
+    work = _f32(N * ((_lib.load().vg_field_parts(H * W) + 1) * C + se), h3.device)
     _lib.call("vg_se_bwd", dh4.data_ptr(), h3.data_ptr(), gate.data_ptr(), mean.data_ptr(), hid.data_ptr(), W1.data_ptr(),
               W2.data_ptr(), N, H * W, C, se, dW1.data_ptr(), dW2.data_ptr(), dmean.data_ptr(), work.data_ptr(), work.numel(), _st())
     return dmean
