@@ -912,13 +912,20 @@ __global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCo
   bf16* sP = sdO + SM * LDQ; bf16* sDS = sP + SM * LDP;
   float* inq = reinterpret_cast<float*>(sDS + SM * LDP); float* ink = inq + SM;
   float* sbias = ink + SM; float* dbias = sbias + nb; float* gred = dbias + nb;
+  float* sgam = gred + 2 * DH;             // [4][DH]: rs*gq, 1/(rs*gq), rs*gk, 1/(rs*gk)   (1/. = 0 where gamma = 0)
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO), aP = smem_u32(sP), aDS = smem_u32(sDS);
   const int n = blockIdx.x / p.heads, hd = blockIdx.x - n * p.heads;
   const int inner = p.heads * DH;
   const float rs = sqrtf((float)DH);
   for (int i = threadIdx.x; i < nb; i += 128) { sbias[i] = p.bias_table[i * p.heads + hd]; dbias[i] = 0.f; }
   if (threadIdx.x < 2 * DH) gred[threadIdx.x] = 0.f;
-  const float gq_l = p.qgamma[hd * DH + lane], gk_l = p.kgamma[hd * DH + lane];
+  if (threadIdx.x < DH) {
+    const float a = rs * p.qgamma[hd * DH + threadIdx.x], b = rs * p.kgamma[hd * DH + threadIdx.x];
+    sgam[threadIdx.x] = a; sgam[DH + threadIdx.x] = a != 0.f ? 1.0f / a : 0.f;
+    sgam[2 * DH + threadIdx.x] = b; sgam[3 * DH + threadIdx.x] = b != 0.f ? 1.0f / b : 0.f;
+  }
+  // phase-1 mapping: 4 lanes per row (8 rows per pass), each lane 8 consecutive head dims
+  const int prow = lane >> 2, pd0 = (lane & 3) * 8;
   float dgq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dgk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int r0 = warp * 16;
   const int ia = r0 + g, ib = r0 + g + 8;
@@ -941,26 +948,56 @@ __global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCo
 
   for (int wi = 0; wi < nwin; ++wi) {
     const long long row0 = ((long long)n * nwin + wi) * S;
-    // ---------------- phase 1: rows r0..r0+15, lane = d
+    // ---------------- phase 1: rows r0..r0+15; 4 lanes per row, 16-byte loads, all issued before the first use
     {
-      float qv[16], kv[16], vv[16], dov[16];
+      float4 ld[2][4][2];                                   // [pass][q,k,v,dO][half]
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int i = r0 + r;
-        qv[r] = kv[r] = vv[r] = dov[r] = 0.f;
+      for (int ps = 0; ps < 2; ++ps) {
+        const int i = r0 + ps * 8 + prow;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { ld[ps][m][0] = make_float4(0.f, 0.f, 0.f, 0.f); ld[ps][m][1] = ld[ps][m][0]; }
         if (i < S) {
-          const float* src = p.qkv + (row0 + i) * 3 * inner + hd * DH + lane;
-          qv[r] = __ldg(src); kv[r] = __ldg(src + inner); vv[r] = __ldg(src + 2 * inner);
-          dov[r] = __ldg(p.datt + (row0 + i) * inner + hd * DH + lane);
+          const float* src = p.qkv + (row0 + i) * 3 * inner + hd * DH + pd0;
+          const float* sdo = p.datt + (row0 + i) * inner + hd * DH + pd0;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            ld[ps][m][0] = __ldg(reinterpret_cast<const float4*>(src + m * inner));
+            ld[ps][m][1] = __ldg(reinterpret_cast<const float4*>(src + m * inner + 4));
+          }
+          ld[ps][3][0] = __ldg(reinterpret_cast<const float4*>(sdo));
+          ld[ps][3][1] = __ldg(reinterpret_cast<const float4*>(sdo + 4));
         }
       }
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int i = r0 + r;
-        const float nq = fmaxf(sqrtf(warp_sum(qv[r] * qv[r])), 1e-12f), nk = fmaxf(sqrtf(warp_sum(kv[r] * kv[r])), 1e-12f);
-        sQ[i * LDQ + lane] = __float2bfloat16(qv[r] / nq * rs * gq_l); sK[i * LDQ + lane] = __float2bfloat16(kv[r] / nk * rs * gk_l);
-        sV[i * LDQ + lane] = __float2bfloat16(vv[r]); sdO[i * LDQ + lane] = __float2bfloat16(dov[r]);
-        if (lane == 0) { inq[i] = 1.0f / nq; ink[i] = 1.0f / nk; }
+      for (int ps = 0; ps < 2; ++ps) {
+        const int i = r0 + ps * 8 + prow;
+        float x[4][8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          x[m][0] = ld[ps][m][0].x; x[m][1] = ld[ps][m][0].y; x[m][2] = ld[ps][m][0].z; x[m][3] = ld[ps][m][0].w;
+          x[m][4] = ld[ps][m][1].x; x[m][5] = ld[ps][m][1].y; x[m][6] = ld[ps][m][1].z; x[m][7] = ld[ps][m][1].w;
+        }
+        float nq = 0.f, nk = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { nq = fmaf(x[0][d], x[0][d], nq); nk = fmaf(x[1][d], x[1][d], nk); }
+        nq += __shfl_xor_sync(0xffffffffu, nq, 1); nq += __shfl_xor_sync(0xffffffffu, nq, 2);
+        nk += __shfl_xor_sync(0xffffffffu, nk, 1); nk += __shfl_xor_sync(0xffffffffu, nk, 2);
+        const float iq = 1.0f / fmaxf(sqrtf(nq), 1e-12f), ik = 1.0f / fmaxf(sqrtf(nk), 1e-12f);    // F.normalize eps (maxvit.py:30)
+        float gq8[8], gk8[8];
+        *reinterpret_cast<float4*>(gq8) = *reinterpret_cast<const float4*>(sgam + pd0);
+        *reinterpret_cast<float4*>(gq8 + 4) = *reinterpret_cast<const float4*>(sgam + pd0 + 4);
+        *reinterpret_cast<float4*>(gk8) = *reinterpret_cast<const float4*>(sgam + 2 * DH + pd0);
+        *reinterpret_cast<float4*>(gk8 + 4) = *reinterpret_cast<const float4*>(sgam + 2 * DH + pd0 + 4);
+        uint4 uq, uk, uv, ud;
+        uq.x = pack2bf(x[0][0] * iq * gq8[0], x[0][1] * iq * gq8[1]); uq.y = pack2bf(x[0][2] * iq * gq8[2], x[0][3] * iq * gq8[3]);
+        uq.z = pack2bf(x[0][4] * iq * gq8[4], x[0][5] * iq * gq8[5]); uq.w = pack2bf(x[0][6] * iq * gq8[6], x[0][7] * iq * gq8[7]);
+        uk.x = pack2bf(x[1][0] * ik * gk8[0], x[1][1] * ik * gk8[1]); uk.y = pack2bf(x[1][2] * ik * gk8[2], x[1][3] * ik * gk8[3]);
+        uk.z = pack2bf(x[1][4] * ik * gk8[4], x[1][5] * ik * gk8[5]); uk.w = pack2bf(x[1][6] * ik * gk8[6], x[1][7] * ik * gk8[7]);
+        uv.x = pack2bf(x[2][0], x[2][1]); uv.y = pack2bf(x[2][2], x[2][3]); uv.z = pack2bf(x[2][4], x[2][5]); uv.w = pack2bf(x[2][6], x[2][7]);
+        ud.x = pack2bf(x[3][0], x[3][1]); ud.y = pack2bf(x[3][2], x[3][3]); ud.z = pack2bf(x[3][4], x[3][5]); ud.w = pack2bf(x[3][6], x[3][7]);
+        *reinterpret_cast<uint4*>(sQ + i * LDQ + pd0) = uq; *reinterpret_cast<uint4*>(sK + i * LDQ + pd0) = uk;
+        *reinterpret_cast<uint4*>(sV + i * LDQ + pd0) = uv; *reinterpret_cast<uint4*>(sdO + i * LDQ + pd0) = ud;
+        if ((lane & 3) == 0) { inq[i] = iq; ink[i] = ik; }
       }
     }
     __syncthreads();
@@ -1067,23 +1104,23 @@ __global__ void __launch_bounds__(128, 3) attn_core_bwd_bf16_kernel(const AttnCo
         for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
         if (which == 0) warp_mma_bf16<4, SM, false, true>(acc, aDS, LDP, r0, aK, LDQ, lane);   // dQh = dS Kh
         else warp_mma_bf16<4, SM, true, true>(acc, aDS, LDP, r0, aQ, LDQ, lane);               // dKh = dS^T Qh
-        const float* gam = which == 0 ? p.qgamma : p.kgamma;
         const float* inv = which == 0 ? inq : ink;
+        const bf16* sX = which == 0 ? sQ : sK;               // xh = u * rs * gamma (bf16): u = xh / (rs * gamma)
+        const float* gtab = sgam + which * 2 * DH;
         float* dg = which == 0 ? dgq : dgk;
         float ua[8], ub[8], ga[8], gb[8], dota = 0.f, dotb = 0.f;
         const float inva = inv[ia], invb = inv[ib];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int d = nt * 8 + 2 * t;
-          float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-          if (ia < S) xa = __ldg(reinterpret_cast<const float2*>(p.qkv + (row0 + ia) * 3 * inner + which * inner + hd * DH + d));
-          if (ib < S) xb = __ldg(reinterpret_cast<const float2*>(p.qkv + (row0 + ib) * 3 * inner + which * inner + hd * DH + d));
-          const float g0 = gam[hd * DH + d], g1 = gam[hd * DH + d + 1];
-          ua[2 * nt] = xa.x * inva; ua[2 * nt + 1] = xa.y * inva; ub[2 * nt] = xb.x * invb; ub[2 * nt + 1] = xb.y * invb;
+          const float2 xa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sX + ia * LDQ + d));
+          const float2 xb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sX + ib * LDQ + d));
+          const float2 gg = *reinterpret_cast<const float2*>(gtab + d), ig = *reinterpret_cast<const float2*>(gtab + DH + d);
+          ua[2 * nt] = xa.x * ig.x; ua[2 * nt + 1] = xa.y * ig.y; ub[2 * nt] = xb.x * ig.x; ub[2 * nt + 1] = xb.y * ig.y;
           dg[2 * nt] += (acc[nt][0] * ua[2 * nt] + acc[nt][2] * ub[2 * nt]) * rs;
           dg[2 * nt + 1] += (acc[nt][1] * ua[2 * nt + 1] + acc[nt][3] * ub[2 * nt + 1]) * rs;
-          ga[2 * nt] = acc[nt][0] * rs * g0; ga[2 * nt + 1] = acc[nt][1] * rs * g1;
-          gb[2 * nt] = acc[nt][2] * rs * g0; gb[2 * nt + 1] = acc[nt][3] * rs * g1;
+          ga[2 * nt] = acc[nt][0] * gg.x; ga[2 * nt + 1] = acc[nt][1] * gg.y;
+          gb[2 * nt] = acc[nt][2] * gg.x; gb[2 * nt + 1] = acc[nt][3] * gg.y;
           dota += ga[2 * nt] * ua[2 * nt] + ga[2 * nt + 1] * ua[2 * nt + 1];
           dotb += gb[2 * nt] * ub[2 * nt] + gb[2 * nt + 1] * ub[2 * nt + 1];
         }
@@ -1380,7 +1417,7 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   if (g.S() > 64) return set_error("attn_core_bwd: sequence %d > 64", g.S());
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   if (use_tf32 == 2) {
-    const size_t smem3 = (size_t)cbh::BYTES + (size_t)(2 * nb + 2 * cbh::DH) * sizeof(float);
+    const size_t smem3 = (size_t)cbh::BYTES + (size_t)(2 * nb + 6 * cbh::DH) * sizeof(float);
     static bool attr3 = false;
     if (!attr3) {
       cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
