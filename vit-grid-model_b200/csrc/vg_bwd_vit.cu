@@ -87,27 +87,52 @@ struct BnBwdParams {
   long long M;
 };
 
-__device__ __forceinline__ float bn_dpre(const BnBwdParams& p, long long r, int c, float rawv) {
-  float g = p.dOut[r * p.C + c];
-  if (p.fgate) { const long long n = r / p.rows_per_field; g = g * p.fgate[n * p.C + c] + (p.fadd ? p.fadd[n * p.C + c] : 0.f); }
-  if (p.act == 1) g *= gelu_grad(fmaf(rawv, p.scale[c], p.shift[c]));
+// 4 consecutive channels of one row
+__device__ __forceinline__ float4 bn_dpre4(const BnBwdParams& p, long long r, int c, const float4 rawv) {
+  float4 g = *reinterpret_cast<const float4*>(p.dOut + r * p.C + c);
+  if (p.fgate) {
+    const long long n = r / p.rows_per_field;
+    const float4 fg = *reinterpret_cast<const float4*>(p.fgate + n * p.C + c);
+    g.x *= fg.x; g.y *= fg.y; g.z *= fg.z; g.w *= fg.w;
+    if (p.fadd) { const float4 fa = *reinterpret_cast<const float4*>(p.fadd + n * p.C + c); g.x += fa.x; g.y += fa.y; g.z += fa.z; g.w += fa.w; }
+  }
+  if (p.act == 1) {
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c), sh = *reinterpret_cast<const float4*>(p.shift + c);
+    g.x *= gelu_grad(fmaf(rawv.x, sc.x, sh.x)); g.y *= gelu_grad(fmaf(rawv.y, sc.y, sh.y));
+    g.z *= gelu_grad(fmaf(rawv.z, sc.z, sh.z)); g.w *= gelu_grad(fmaf(rawv.w, sc.w, sh.w));
+  }
   return g;
 }
 
+// block = 256 threads = (C/4 channel quads) x (256 / (C/4) row lanes) over STAT_ROWS rows; partial (S1, S2) per block
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p, float* __restrict__ part) {
+  __shared__ float4 red[2][256];
+  const int quads = p.C / 4, nrl = 256 / quads;
+  const int q = threadIdx.x % quads, rl = threadIdx.x / quads, c = q * 4;
   const long long r0 = (long long)blockIdx.x * STAT_ROWS;
   long long r1 = r0 + STAT_ROWS;
   if (r1 > p.M) r1 = p.M;
-  for (int c = threadIdx.x; c < p.C; c += 256) {
-    float s1 = 0.f, s2 = 0.f;
-    const float m = p.mean[c], rs = p.rstd[c];
-    for (long long r = r0; r < r1; ++r) {
-      const float rawv = p.raw[r * p.C + c];
-      const float d = bn_dpre(p, r, c, rawv);
-      s1 += d; s2 = fmaf(d, (rawv - m) * rs, s2);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (rl < nrl) {
+    const float4 m = *reinterpret_cast<const float4*>(p.mean + c), rs = *reinterpret_cast<const float4*>(p.rstd + c);
+#pragma unroll 2
+    for (long long r = r0 + rl; r < r1; r += nrl) {
+      const float4 rawv = *reinterpret_cast<const float4*>(p.raw + r * p.C + c);
+      const float4 d = bn_dpre4(p, r, c, rawv);
+      s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+      s2.x = fmaf(d.x, (rawv.x - m.x) * rs.x, s2.x); s2.y = fmaf(d.y, (rawv.y - m.y) * rs.y, s2.y);
+      s2.z = fmaf(d.z, (rawv.z - m.z) * rs.z, s2.z); s2.w = fmaf(d.w, (rawv.w - m.w) * rs.w, s2.w);
     }
-    part[((long long)blockIdx.x * 2) * p.C + c] = s1;
-    part[((long long)blockIdx.x * 2 + 1) * p.C + c] = s2;
+  }
+  red[0][threadIdx.x] = s1; red[1][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.x < quads) {
+    for (int k = 1; k < nrl; ++k) {
+      const float4 a = red[0][k * quads + q], b = red[1][k * quads + q];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w; s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.x * 2) * p.C + c) = s1;
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.x * 2 + 1) * p.C + c) = s2;
   }
 }
 
@@ -123,14 +148,20 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p, const float* __restrict__ k1, const float* __restrict__ k2,
                                                            float* __restrict__ draw) {
+  const int quads = p.C / 4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.M * p.C) return;
-  const long long r = i / p.C;
-  const int c = (int)(i - r * p.C);
-  const float rawv = p.raw[i];
-  const float d = bn_dpre(p, r, c, rawv);
-  const float xh = (rawv - p.mean[c]) * p.rstd[c];
-  draw[i] = p.gamma[c] * p.rstd[c] * (d - k1[c] - xh * k2[c]);
+  if (i >= p.M * quads) return;
+  const long long r = i / quads;
+  const int c = (int)(i - r * quads) * 4;
+  const float4 rawv = *reinterpret_cast<const float4*>(p.raw + r * p.C + c);
+  const float4 d = bn_dpre4(p, r, c, rawv);
+  const float4 m = *reinterpret_cast<const float4*>(p.mean + c), rs = *reinterpret_cast<const float4*>(p.rstd + c);
+  const float4 g = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 a1 = *reinterpret_cast<const float4*>(k1 + c), a2 = *reinterpret_cast<const float4*>(k2 + c);
+  float4 o;
+  o.x = g.x * rs.x * (d.x - a1.x - (rawv.x - m.x) * rs.x * a2.x); o.y = g.y * rs.y * (d.y - a1.y - (rawv.y - m.y) * rs.y * a2.y);
+  o.z = g.z * rs.z * (d.z - a1.z - (rawv.z - m.z) * rs.z * a2.z); o.w = g.w * rs.w * (d.w - a1.w - (rawv.w - m.w) * rs.w * a2.w);
+  *reinterpret_cast<float4*>(draw + r * p.C + c) = o;
 }
 
 // out[j] (+)= sum_p part[p][j]
@@ -1264,6 +1295,7 @@ int bn_bwd_run(const float* dOut, const float* raw, const float* scale, const fl
                const float* gamma, int act, const float* fgate, const float* fadd, long long rows_per_field, long long M, int C,
                float* dgamma, float* dbeta, float* draw, float* work, long long work_elems, cudaStream_t st) {
   const int nparts = (int)((M + STAT_ROWS - 1) / STAT_ROWS);
+  if (C % 4 || C / 4 > 256 || 256 % (C / 4)) return set_error("bn_bwd: C=%d must be 4*k with k | 256", C);
   if (work_elems < (long long)nparts * 2 * C + 2 * C) return set_error("bn_bwd: workspace too small");
   BnBwdParams p;
   p.dOut = dOut; p.raw = raw; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.gamma = gamma;
@@ -1275,7 +1307,7 @@ int bn_bwd_run(const float* dOut, const float* raw, const float* scale, const fl
   bn_bwd_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(work, nparts, M, C, dgamma, dbeta, k1, k2);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
-  bn_bwd_apply_kernel<<<nblk(M * C, 256), 256, 0, st>>>(p, k1, k2, draw);
+  bn_bwd_apply_kernel<<<nblk(M * (C / 4), 256), 256, 0, st>>>(p, k1, k2, draw);
   return check_launch("bn_bwd_apply_kernel");
 }
 
