@@ -108,3 +108,21 @@ def test_depth2_backbone_vs_oracle(precision):
     with torch.no_grad():
         y = m(x.cuda(), timestamps=ts.cuda())
     assert rel_err(y, ref) < TOL[precision]
+
+
+def test_host_pipeline_matches_direct_calls():
+    """HostPipeline (pinned host batches in, pinned host predictions out, copies overlapped on a side stream) returns the
+    same predictions, in order, as calling the module on device tensors"""
+    from vit_grid_model_b200 import HostPipeline
+    cfg = synth.CFG_SMALL128
+    m, _ = build(cfg, 2, "bf16")
+    batches = []
+    for k in range(5):
+        x, ts, _ = synth.make_inputs(cfg, 2 + (k % 2), seed=100 + k)            # ragged batch sizes
+        batches.append((x.pin_memory(), ts.pin_memory()))
+    with torch.no_grad():
+        direct = [m(x.cuda(), timestamps=ts.cuda()).cpu() for x, ts in batches]
+    got = [y.clone() for y in HostPipeline(m).run(batches)]
+    assert len(got) == len(direct)
+    for a, b in zip(got, direct):
+        assert a.shape == b.shape and torch.equal(a, b)
