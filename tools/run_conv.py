@@ -39,3 +39,14 @@ for _ in range(3):
     e1.record()
     torch.cuda.synchronize()
     print(f"LN epilogue, no film/res: ms={e0.elapsed_time(e1):.3f} TFLOP/s={flops / e0.elapsed_time(e1) / 1e9:.1f}")
+# fp32 residual (skip connection) variants, as the network runs them
+resf = torch.randn(x.shape[0], C, generator=torch.Generator(device="cuda").manual_seed(1), dtype=torch.float32, device="cuda")
+copy = torch.empty(x.shape[0], C, dtype=torch.float32, device="cuda")
+for label, oc in (("fp32 residual", None), ("fp32 residual + fp32 copy", copy)):
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv3x3_ln(x, w, b, ga, be, 1e-5, film, resf, out, N, HP, WP, out_copy=oc)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{label}: ms={e0.elapsed_time(e1):.3f} TFLOP/s={flops / e0.elapsed_time(e1) / 1e9:.1f}")

@@ -167,6 +167,16 @@ struct EpiCtx {
   // gb[f][0..127] = g*(scale+1), gb[f][128..255] = b*(scale+1)+shift for the fields n_first+f, f in {0,1}
   const float* gb;
   int n_first;
+  // fp32 residual rows delivered by TMA (conv_halo_kernel): the warp owns two [32 rows][128 B] SWIZZLE_128B buffers and
+  // a pair of mbarriers; chunk g of the warp's running sequence (4 per tile) lands in buffer g & 1, parity (g >> 1) & 1.
+  // A row-per-thread LDG.128 of a 512-byte-stride residual costs ~36 L1 wavefronts per warp instruction (ncu), which made
+  // the residual variants LSU-bound; the TMA path leaves only conflict-free 128-bit shared loads on the LSU.
+  const CUtensorMap* res_map = nullptr;
+  uint8_t* res_buf = nullptr;
+  uint64_t* res_bar = nullptr;
+  uint32_t res_g0 = 0;             // running chunk index of this tile's chunk 0
+  long long res_row0 = 0;          // row of lane 0 in this tile
+  long long res_next_row0 = -1;    // row of lane 0 in the CTA's next tile, -1 = none
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -215,7 +225,9 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
   T* o = ep.out ? reinterpret_cast<T*>(ep.out) + row * ep.ldo : nullptr;
   float* o2 = ep.out2 ? ep.out2 + row * ep.ldo : nullptr;
   const T* r = (ep.res && !ep.res_f32 && valid) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
-  const float* rf = (ep.res && ep.res_f32 && valid) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
+  const bool rtma = cx.res_map != nullptr;
+  const int lane_ = threadIdx.x & 31;
+  const float* rf = (ep.res && ep.res_f32 && valid && !rtma) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
   float head = 0.f;
   T* xo = (TRAIN && ep.xhat) ? reinterpret_cast<T*>(ep.xhat) + row * ep.ldo : nullptr;
   if (TRAIN && in_buf) {
@@ -234,6 +246,27 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     ld.load(ch, v);
+    if (rtma) {                                              // warp-uniform
+      const uint32_t g = cx.res_g0 + ch;
+      uint8_t* buf = cx.res_buf + (g & 1) * 4096;
+      uint64_t* bar = cx.res_bar + (g & 1);
+      mbar_wait(bar, (g >> 1) & 1);
+      const uint8_t* p = buf + lane_ * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q4 = *reinterpret_cast<const float4*>(p + ((j ^ (lane_ & 7)) << 4));
+        rr[4 * j] = q4.x; rr[4 * j + 1] = q4.y; rr[4 * j + 2] = q4.z; rr[4 * j + 3] = q4.w;
+      }
+      __syncwarp();
+      if (lane_ == 0) {                                      // refill the buffer with chunk g + 2
+        const long long r0 = ch < 2 ? cx.res_row0 : cx.res_next_row0;
+        if (r0 >= 0) {
+          fence_proxy_async_smem();
+          mbar_arrive_expect_tx(bar, 4096);
+          tma_load_2d(buf, cx.res_map, bar, ((ch + 2) & 3) * 32, (int)r0);
+        }
+      }
+    }
     if (!in_buf) continue;
     unsigned mbits = 0u;
     float xh[TRAIN ? 32 : 1];
@@ -263,14 +296,14 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
 #pragma unroll
         for (int j = 0; j < 32; j += 8) st8(xo + ch * 32 + j, xh + j);
       }
-      if (rf || r) {
+      if (rf || r || rtma) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += rr[j];
         if (ch < 3) {
           if (rf) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) ld8(rf + (ch + 1) * 32 + j, rr + j);
-          } else {
+          } else if (r) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) ld8(r + (ch + 1) * 32 + j, rr + j);
           }

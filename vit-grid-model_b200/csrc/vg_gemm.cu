@@ -210,9 +210,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // instead of 576 + 288 KiB.
 // ------------------------------------------------------------------------------------------------
 constexpr int HALO_MAX_ROWS = 416;                            // HR <= 416 (two TMA boxes of <= 208 rows)
-constexpr int HB_STAGES = 5;                                  // weight ring
+constexpr int HB_STAGES = 3;                                  // weight ring
+constexpr int HALO_RES_BYTES = 8 * 2 * 4096;                  // per epilogue warp: two [32 rows][128 B] fp32 residual chunks (TMA)
 constexpr int HALO_A_BYTES = HALO_MAX_ROWS * 128;             // per channel block
-constexpr int HALO_SMEM_BYTES = 2 * HALO_A_BYTES + HB_STAGES * B_BYTES + PARAM_FLOATS * 4 + 1024 + 256;
+constexpr int HALO_SMEM_BYTES = 2 * HALO_A_BYTES + HB_STAGES * B_BYTES + HALO_RES_BYTES + PARAM_FLOATS * 4 + 1024 + 256;
 static int g_halo_base_offset = 0;   // measured on B200: the 128B swizzle is applied to absolute smem address bits, so a
                                      // row-shifted start into a 1024-B-aligned tile needs base_offset = 0 (1 gives wrong results)
 
@@ -222,6 +223,7 @@ struct HaloShape {
   int P;                // row pitch (pixels)
   int HR;               // halo rows loaded per tile (multiple of 16)
   int use_base_offset;
+  int res_tma;          // the fp32 residual arrives through mapR (else: per-thread global loads)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int row) {
@@ -232,26 +234,29 @@ __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int
 template <bool TRAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const HaloShape hs, const EpiParams ep) {
+                 const __grid_constant__ CUtensorMap mapR, const HaloShape hs, const EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + 2 * HALO_A_BYTES;
-  float* sparam = reinterpret_cast<float*>(sB + HB_STAGES * B_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + HB_STAGES * B_BYTES + PARAM_FLOATS * 4);
+  uint8_t* sres = sB + HB_STAGES * B_BYTES;
+  float* sparam = reinterpret_cast<float*>(sres + HALO_RES_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sres + HALO_RES_BYTES + PARAM_FLOATS * 4);
   uint64_t* empty = full + HB_STAGES;
   uint64_t* a_full = empty + HB_STAGES;    // [2]
   uint64_t* a_free = a_full + 2;           // [2]
   uint64_t* tfull = a_free + 2;            // [2]
   uint64_t* tempty = tfull + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_full = tempty + 2;         // [8 epilogue warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); if (hs.res_tma) tma_prefetch_desc(&mapR); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < HB_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_free + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    for (int s = 0; s < 16; ++s) mbar_init(res_full + s, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -263,7 +268,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform: lets the MMA issue use uniform registers (no per-MMA elect/broadcast loop)
   const int halo = hs.P + 1;                                 // rows in front of the tile's first output pixel
-
   if (warp == 0) {
     if (lane == 0) {                                         // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
@@ -324,12 +328,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int e = (warp - 4) >> 2;
     EpiCtx cx;
     cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    if (hs.res_tma) {
+      cx.res_map = &mapR; cx.res_buf = sres + (warp - 4) * 8192; cx.res_bar = res_full + (warp - 4) * 2;
+      if (lane == 0 && (int)blockIdx.x < hs.num_tiles) {     // chunks 0 and 1 of the first tile
+        const int r0 = (int)((long long)blockIdx.x * BM + e * 128 + lg * 32);
+        for (int c = 0; c < 2; ++c) {
+          mbar_arrive_expect_tx(cx.res_bar + c, 4096);
+          tma_load_2d(cx.res_buf + c * 4096, &mapR, cx.res_bar + c, c * 32, r0);
+        }
+      }
+    }
     uint32_t it = 0;
     for (int t = blockIdx.x; t < hs.num_tiles; t += gridDim.x, ++it) {
       const long long row = (long long)t * BM + e * 128 + lg * 32 + lane;
       const bool ok = row < hs.M;
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
-      epi_conv_ln_prefetch<bf16>(ep, row, ok);
+      if (hs.res_tma) {
+        cx.res_g0 = it * 4; cx.res_row0 = row - lane;
+        cx.res_next_row0 = (t + (int)gridDim.x < hs.num_tiles) ? cx.res_row0 + (long long)gridDim.x * BM : -1;
+      } else {
+        epi_conv_ln_prefetch<bf16>(ep, row, ok);
+      }
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
       TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
@@ -492,9 +511,16 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   if (mode < 0) { const char* e = getenv("VG_CONV_HALO"); mode = (e && e[0] == '0') ? 0 : 1;
                   const char* b = getenv("VG_HALO_BASEOFF"); if (b) g_halo_base_offset = (b[0] != '0'); }
   if (!mode) return -1;
-  CUtensorMap ma, mb;
+  static int res_tma_mode = -1;
+  if (res_tma_mode < 0) { const char* e = getenv("VG_CONV_RES_TMA"); res_tma_mode = (e && e[0] == '0') ? 0 : 1; }
+  CUtensorMap ma, mb, mr;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  const bool res_tma = res_tma_mode && ep.res && ep.res_f32 && ep.ldres == 128 && (reinterpret_cast<uintptr_t>(ep.res) & 15) == 0;
+  if (res_tma) {
+    int rc = make_map_2d(&mr, true, ep.res, 128, pg.pixels(), 32);
+    if (rc) return rc;
+  }
   {
     cuuint64_t dims[2] = {128, (cuuint64_t)pg.pixels()};
     cuuint64_t strides[1] = {256};
@@ -508,7 +534,7 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   int rc = make_map_2d(&mb, false, Wt, 9 * 128, 128, BN);
   if (rc) return rc;
   HaloShape hs;
-  hs.M = pg.pixels(); hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset;
+  hs.M = pg.pixels(); hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset; hs.res_tma = res_tma ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
@@ -517,8 +543,9 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
     attr_set = true;
   }
   const int grid = hs.num_tiles < num_sms() ? hs.num_tiles : num_sms();
-  if (train) conv_halo_kernel<true><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
-  else conv_halo_kernel<false><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, hs, ep);
+  if (!res_tma) mr = ma;                                     // unused by the kernel
+  if (train) conv_halo_kernel<true><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
+  else conv_halo_kernel<false><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
   return check_launch("conv_halo_kernel");
 }
 
