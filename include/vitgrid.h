@@ -171,6 +171,25 @@ VG_API int vg_focal_r_fwd(const float* pred, const float* target, long long n, f
 VG_API int vg_focal_r_bwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse,
                    float gscale, float* grad, void* stream);
 
+/* Fused evaluation statistics (replaces the ~200 host-synchronising reductions per batch of the reference's test loop,
+ * /root/reference/src/evaluation_vit.py:239-455).  Four methods m are scored against the truth: 0 = the model's predictions,
+ * 1 = persistence (last observation, (B,P), repeated over the leads), 2 = the 21 h CMAQ run, 3 = the mean of the four runs.
+ * Class of a value: 0..3 by the boundaries b1 < b2 < b3 (assign_class, :31-32 with range_4class :194, default 0);
+ * truth_class comes from the loader ((B,L,P), int32 or int64, -1 = no label).  One call ACCUMULATES a batch into
+ *   counts  uint64 [4][L][4][5]   #{class(v_m) = a, truth class = t}, t index 0 <-> class -1
+ *   sums    double [4][L][5][2]   sum |v_m - y| and (v_m - y)^2 per truth class
+ *   glob    double [22]           over everything: [m][2] sum (v_m - y)/y, |(v_m - y)/y| over y > 0 (:311-326) | [m][3] sum v_m,
+ *                                 v_m^2, v_m*y | sum y, y^2   (NMB / NME / Pearson r, :507-523, :572-576)
+ *   nonzero uint64 [1]            #{y > 0};    loss_sum double [1] += MSE of this batch (criterion, :140 / :291)
+ * from which every quantity of the reference's list is a linear combination (host side: eval_metrics.py).
+ * clamp_preds != 0 also applies `preds[preds < 0] = 0` in place (:254).  work: vg_eval_metrics_workspace() doubles.
+ * The floating-point sums are reduced in a fixed order (bit-reproducible); the integer tables are exact. */
+VG_API long long vg_eval_metrics_workspace(int B, int L, int P);
+VG_API int vg_eval_metrics(float* preds, const float* truth, const void* truth_class, int class_is_i64, const float* persist,
+                    const float* sim_21h, const float* sim_avg, int B, int L, int P, float b1, float b2, float b3,
+                    int clamp_preds, void* counts, double* sums, double* glob, void* nonzero, double* loss_sum,
+                    double* work, long long work_elems, void* stream);
+
 /* ================================================================================================================
  * Training step.  The reference has no hand-written backward: it is autograd over metnet3.py:86-430 and
  * maxvit.py:33-341 in train() mode (batch-statistic BatchNorm).  Gradients travel as fp32 tensors; dgrad GEMMs go

@@ -34,7 +34,7 @@ def resnet_block(x, cond, sd, p: str):
     return h + x
 
 
-def prepare_input(x, timestamps, sd, cfg: GridConfig):
+def prepare_input(x, timestamps, sd, cfg: GridConfig, stn_imgs: bool = False):
     """metnet3.py:354-416 -> (net_in (N,c_in,HP,WP), cond (N,lead_emb)), N = B*L.
 
     * PM2.5 channels {4,10,16,22} of every time step standardised (:361-380)
@@ -47,8 +47,8 @@ def prepare_input(x, timestamps, sd, cfg: GridConfig):
     """
     B, L = x.shape[0], cfg.L
     x = x.clone()
-    pm = torch.tensor([4, 10, 16, 22])
-    x[:, :, pm] = (x[:, :, pm] - cfg.pm25_mean) / cfg.pm25_std
+    pm = torch.tensor([4, 10, 16, 22] + ([24] if stn_imgs else []))   # MetNet3_with_stn_imgs also standardises the
+    x[:, :, pm] = (x[:, :, pm] - cfg.pm25_mean) / cfg.pm25_std          # station image, channel 24 (metnet3.py:701)
     x = x.repeat_interleave(L, dim=0)
     x = F.pad(x, cfg.pads, value=0.0)
     N, HP, WP = B * L, x.shape[-2], x.shape[-1]
@@ -63,10 +63,13 @@ def prepare_input(x, timestamps, sd, cfg: GridConfig):
     return x, cond
 
 
-def metnet3_forward(x, timestamps, sd, cfg: GridConfig, *, training: bool = False, return_features: bool = False):
-    """MetNet3.forward (metnet3.py:339-430): (B,T,C,H,W), (B,*,4) -> (B,L,H,W) fp32."""
+def metnet3_forward(x, timestamps, sd, cfg: GridConfig, *, training: bool = False, return_features: bool = False,
+                    stn_imgs: bool = False):
+    """MetNet3.forward (metnet3.py:339-430): (B,T,C,H,W), (B,*,4) -> (B,L,H,W) fp32.
+    stn_imgs=True: MetNet3_with_stn_imgs.forward (metnet3.py:666-759), identical but for the extra normalised channel
+    (the reference ALSO writes that normalisation back into the caller's tensor, :701; the oracle is functional)."""
     B = x.shape[0]
-    h, cond = prepare_input(x, timestamps, sd, cfg)
+    h, cond = prepare_input(x, timestamps, sd, cfg, stn_imgs)
     for bi in range(cfg.resnet_depth):
         h = resnet_block(h, cond, sd, f"resnet1.blocks.{bi}.")
     feats = {"resnet1": h}

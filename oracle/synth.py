@@ -88,6 +88,8 @@ CFG_12HR = GridConfig()
 CFG_TINY = GridConfig(T=2, C=24, H=26, W=25, dim=16, L=3, vit_depth=2, heads=2, dim_head=8)
 # GPU-kernel-shaped but small: full channel/head geometry on a 26x25 domain
 CFG_SMALL128 = GridConfig(T=3, C=24, H=26, W=25, dim=128, L=2)
+# MetNet3_with_stn_imgs (metnet3.py:518-759): 25 variables, the last one a station image
+CFG_STN_SMALL128 = GridConfig(T=3, C=25, H=26, W=25, dim=128, L=2)
 
 
 def maxvit_spec(dim: int, depth: int, cond_dim: int, heads: int, dim_head: int, window: int,
@@ -203,4 +205,8 @@ def make_inputs(cfg: GridConfig, B: int, seed: int = 1234, n_ts: int | None = No
     h0 = torch.randint(0, 24 * 360, (B, 1), generator=g) + torch.arange(n_ts)[None, :]
     ts = torch.stack([torch.full_like(h0, 2023), 1 + (h0 // 720) % 12, 1 + (h0 // 24) % 30, h0 % 24], dim=-1)
     target = torch.exp(math.log(18.0) + 0.6 * torch.randn(B, cfg.L, cfg.H, cfg.W, generator=g)).clamp_(0.0, 300.0)
+    if cfg.C >= 25:
+        # MetNet3_with_stn_imgs: channel 24 is the station-observation image in raw ug/m3 (metnet3.py:701); drawn last
+        # so the streams of the 24-channel cases are unchanged
+        x[:, :, 24] = torch.exp(math.log(18.0) + 0.6 * torch.randn(B, cfg.T, cfg.H, cfg.W, generator=g)).clamp_(0.0, 300.0)
     return x, ts.float(), target

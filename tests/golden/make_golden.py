@@ -101,6 +101,22 @@ def metnet3_fixture(name, cfg, B, wseed, iseed):
                     n_params=n_params, keys=list(m.state_dict().keys())))
 
 
+def metnet3_stn_fixture(name, cfg, B, wseed, iseed):
+    """MetNet3_with_stn_imgs (metnet3.py:518-759).  Also records that the reference normalises channel 24 of the CALLER's
+    tensor in place (:701 runs before the clone at :702)."""
+    m = ref_metnet3.MetNet3_with_stn_imgs(**cfg.metnet3_kwargs()).eval()
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=wseed)
+    m.load_state_dict(sd, strict=True)
+    x, ts, _ = synth.make_inputs(cfg, B, seed=iseed)
+    x0 = x.clone()
+    with torch.no_grad():
+        y = m(x, timestamps=ts)
+    mutated = torch.allclose(x[:, :, 24], (x0[:, :, 24] - cfg.pm25_mean) / cfg.pm25_std) and torch.equal(x[:, :, :24], x0[:, :, :24])
+    assert mutated
+    save(name, dict(cfg=cfg.to_dict(), B=B, weight_seed=wseed, input_seed=iseed, y=y.contiguous(), input_mutated=mutated,
+                    keys=list(m.state_dict().keys())))
+
+
 def sample_index(numel, k=48, seed=0):
     g = torch.Generator().manual_seed(seed + numel)
     return torch.randperm(numel, generator=g)[:min(k, numel)].clone()
@@ -136,3 +152,4 @@ if __name__ == "__main__":
     metnet3_fixture("metnet3_small128.pt", synth.CFG_SMALL128, 2, 0, 1234)
     metnet3_fixture("metnet3_12hr_b1.pt", synth.CFG_12HR, 1, 0, 1234)
     metnet3_train_fixture("metnet3_small128_train.pt", synth.CFG_SMALL128, 3, 0, 4321)
+    metnet3_stn_fixture("metnet3_stn_small128.pt", synth.CFG_STN_SMALL128, 2, 0, 1234)

@@ -43,6 +43,27 @@ def test_golden_from_reference(golden, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stn_imgs_variant_golden_from_reference(golden, precision):
+    """MetNet3_with_stn_imgs (metnet3.py:518-759, 25 variables): output vs the real reference class, and the reference's
+    in-place normalisation of the caller's station-image channel (:701)"""
+    from vit_grid_model_b200 import MetNet3_with_stn_imgs
+    f = golden("metnet3_stn_small128.pt")
+    cfg = synth.GridConfig(**f["cfg"])
+    m = MetNet3_with_stn_imgs(**cfg.metnet3_kwargs())
+    m.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=f["weight_seed"]), strict=True)
+    m = m.cuda().eval().set_precision(precision)
+    x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
+    xd = x.cuda()
+    with torch.no_grad():
+        y = m(xd, timestamps=ts.cuda())
+    assert rel_err(y, f["y"]) < TOL[precision]
+    torch.testing.assert_close(xd[:, :, 24].cpu(), (x[:, :, 24] - cfg.pm25_mean) / cfg.pm25_std)
+    assert torch.equal(xd[:, :, :24].cpu(), x[:, :, :24])
+    with pytest.raises(ValueError):
+        MetNet3_with_stn_imgs(**synth.CFG_SMALL128.metnet3_kwargs())       # 24 variables: no station image
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_oracle_batch_chunked(precision):
     """B=5 (ragged chunks of 2 samples) and a channels-last input view, vs the oracle"""
     cfg = synth.CFG_SMALL128

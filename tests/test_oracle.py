@@ -54,6 +54,21 @@ def test_metnet3_matches_reference(golden, name):
     assert rel < 1e-4, rel
 
 
+def test_metnet3_stn_imgs_matches_reference(golden):
+    """MetNet3_with_stn_imgs (metnet3.py:518-759): golden from the real reference class"""
+    f = golden("metnet3_stn_small128.pt")
+    cfg = synth.GridConfig(**f["cfg"])
+    spec = synth.metnet3_spec(cfg)
+    assert set(spec.keys()) == set(f["keys"]) and f["input_mutated"]
+    sd = synth.make_state_dict(spec, seed=f["weight_seed"])
+    x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
+    y = metnet3_forward(x, ts, sd, cfg, stn_imgs=True)
+    rel = ((y - f["y"]).abs().max() / f["y"].abs().max()).item()
+    assert rel < 1e-4, rel
+    y_plain = metnet3_forward(x, ts, sd, cfg)                  # without the station-image normalisation: different
+    assert ((y_plain - f["y"]).abs().max() / f["y"].abs().max()).item() > 1e-3
+
+
 def test_12hr_param_count(golden):
     f = golden("metnet3_12hr_b1.pt")
     assert f["n_params"] == 3_346_145                  # SURVEY F4 / appendix A

@@ -248,6 +248,19 @@ int vg_head_fwd(int dtype, const void* h, const float* w, float bias, float pm_s
   return head_run(dtype, h, w, bias, pm_std, pm_mean, N, HP, WP, C, H, W, pad_top, pad_left, out, (cudaStream_t)stream);
 }
 
+long long vg_eval_metrics_workspace(int B, int L, int P) { return eval_metrics_workspace_run(B, L, P); }
+
+int vg_eval_metrics(float* preds, const float* truth, const void* truth_class, int class_is_i64, const float* persist,
+                    const float* sim_21h, const float* sim_avg, int B, int L, int P, float b1, float b2, float b3,
+                    int clamp_preds, void* counts, double* sums, double* glob, void* nonzero, double* loss_sum, double* work,
+                    long long work_elems, void* stream) {
+  if (!preds || !truth || !truth_class || !persist || !sim_21h || !sim_avg) return set_error("eval_metrics: null input");
+  if (!counts || !sums || !glob || !nonzero || !loss_sum || !work) return set_error("eval_metrics: null accumulator");
+  return eval_metrics_run(preds, truth, truth_class, class_is_i64, persist, sim_21h, sim_avg, B, L, P, b1, b2, b3, clamp_preds,
+                          reinterpret_cast<unsigned long long*>(counts), sums, glob, reinterpret_cast<unsigned long long*>(nonzero),
+                          loss_sum, work, work_elems, (cudaStream_t)stream);
+}
+
 int vg_focal_r_fwd(const float* pred, const float* target, long long n, float beta, float gamma, int mse, float* partial,
                    int nblocks, float* loss, void* stream) {
   return focal_r_fwd_run(pred, target, n, beta, gamma, mse, partial, nblocks, loss, (cudaStream_t)stream);

@@ -70,6 +70,11 @@ int se_scale_run(int dtype, void* x, const float* gate, int N, long long HW, int
 int reg_mean_run(const float* in, float* out, int N, int nwin, int RC, cudaStream_t st);
 int head_run(int dtype, const void* h, const float* w, float bias, float stdv, float mean, int N, int HP, int WP, int C,
              int H, int W, int pad_top, int pad_left, float* out, cudaStream_t st);
+long long eval_metrics_workspace_run(int B, int L, int P);
+int eval_metrics_run(float* preds, const float* truth, const void* tcls, int cls_i64, const float* persist, const float* sim21,
+                     const float* simavg, int B, int L, int P, float b1, float b2, float b3, int clamp_preds,
+                     unsigned long long* counts, double* sums, double* glob, unsigned long long* nonzero, double* loss_sum,
+                     double* work, long long work_elems, cudaStream_t st);
 int focal_r_fwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float* partial,
                     int nb, float* loss, cudaStream_t st);
 int focal_r_bwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float gscale,

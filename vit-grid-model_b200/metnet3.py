@@ -354,3 +354,28 @@ class MetNet3(nn.Module):
         for b0 in range(0, B, step):
             self._forward_chunk(x, b0, min(B, b0 + step), terms, P, dtype, out)
         return out
+
+
+class MetNet3_with_stn_imgs(MetNet3):
+    """/root/reference/src/metnet3.py:518-759.  Same network and state dict as ``MetNet3`` with 25 input variables: variable
+    24 is a station-observation image in raw ug/m3 that ``forward`` standardises with the PM2.5 statistics
+    (metnet3.py:701) next to the four simulated-PM2.5 channels.
+
+    Reference behaviour kept on purpose: the standardisation of variable 24 is written back into the CALLER's tensor
+    (line 701 runs before the ``x.clone()`` of line 702), so calling ``forward`` twice on the same tensor normalises it
+    twice.  ``tests/golden/metnet3_stn_small128.pt`` records that side effect."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.n_variables < 25:
+            raise ValueError("MetNet3_with_stn_imgs reads the station image from variable 24 (metnet3.py:701): n_variables >= 25")
+
+    def forward(self, x, labels_pm25=None, region_targets_pm25=None, labels_pm10=None, region_targets_pm10=None,
+                timestamps: torch.Tensor = None, prev_vals: torch.Tensor = None):
+        _lib.require_device()
+        if not x.is_cuda:
+            raise _lib.VitGridError("vit_grid_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if self.normalization_method == "Standard":
+            stn = x[:, :, 24]                                   # a view: the caller's tensor is updated, as in the reference
+            stn.sub_(self.pm25_mean).div_(self.pm25_std)
+        return super().forward(x, labels_pm25, region_targets_pm25, labels_pm10, region_targets_pm10, timestamps, prev_vals)
