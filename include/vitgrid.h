@@ -102,6 +102,18 @@ VG_API int vg_stem_finish_fwd(int dtype, const float* raw3, const float* rawres,
                        const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
                        const float* film, int B, int L, int HP, int WP, void* h1, float* res, void* stream);
 
+/* Channel widths other than 128 (n_start_channels = 256 / 384 / 512; BASELINE configs[4]).  Same operators as
+ * vg_conv3x3_ln_fwd (C -> C) and vg_stem_finish_fwd, built from a plain tcgen05 shifted-row GEMM into the fp32 scratch plus a
+ * row-wise LayerNorm / FiLM / ReLU / residual kernel (inference only).  scratch: q*C floats (2*q*C in fp32 mode). */
+VG_API int vg_conv3x3_ln_wide_fwd(int dtype, const void* x, int C, const void* Wt, const float* bias, const float* ln_g,
+                           const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                           float* out_f32_copy, int N, int HP, int WP, const float* head_w, float head_b, float head_std,
+                           float head_mean, int H, int W, int pad_top, int pad_left, float* head_out, float* scratch,
+                           long long scratch_elems, void* stream);
+VG_API int vg_stem_finish_wide_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                            const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                            const float* film, int B, int L, int HP, int WP, int C, void* h1, float* res, void* stream);
+
 /* metnet3.py:86,419 -- MaxPool2d(2,2): PG (N,HP,WP,C) -> CL (N,HP/2,WP/2,C); out_f32=1: bf16 in, fp32 out */
 VG_API int vg_pool2_fwd(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, void* stream);
 

@@ -88,6 +88,10 @@ CFG_12HR = GridConfig()
 CFG_TINY = GridConfig(T=2, C=24, H=26, W=25, dim=16, L=3, vit_depth=2, heads=2, dim_head=8)
 # GPU-kernel-shaped but small: full channel/head geometry on a 26x25 domain
 CFG_SMALL128 = GridConfig(T=3, C=24, H=26, W=25, dim=128, L=2)
+# BASELINE configs[4] "MetNet-3-style at larger dim/heads" (n_start_channels 512, dim_head 64) on a small domain,
+# and an intermediate width with depth 2
+CFG_WIDE512 = GridConfig(T=2, C=24, H=26, W=25, dim=512, L=2, heads=32, dim_head=64)
+CFG_WIDE256 = GridConfig(T=3, C=24, H=26, W=25, dim=256, L=2, vit_depth=2, heads=4, dim_head=64)
 # MetNet3_with_stn_imgs (metnet3.py:518-759): 25 variables, the last one a station image
 CFG_STN_SMALL128 = GridConfig(T=3, C=25, H=26, W=25, dim=128, L=2)
 

@@ -153,3 +153,5 @@ if __name__ == "__main__":
     metnet3_fixture("metnet3_12hr_b1.pt", synth.CFG_12HR, 1, 0, 1234)
     metnet3_train_fixture("metnet3_small128_train.pt", synth.CFG_SMALL128, 3, 0, 4321)
     metnet3_stn_fixture("metnet3_stn_small128.pt", synth.CFG_STN_SMALL128, 2, 0, 1234)
+    metnet3_fixture("metnet3_wide256.pt", synth.CFG_WIDE256, 2, 0, 1234)
+    metnet3_fixture("metnet3_wide512.pt", synth.CFG_WIDE512, 2, 0, 1234)

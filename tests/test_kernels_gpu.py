@@ -312,6 +312,25 @@ def test_maxvit_module(precision, tol):
     assert rel_err(y, ref) < tol
 
 
+@pytest.mark.parametrize("dim,heads,dh,w,R,H,W", [(256, 4, 64, 7, 4, 14, 21), (512, 32, 64, 7, 4, 14, 14), (128, 3, 32, 8, 1, 16, 24),
+                                                   (384, 6, 64, 7, 2, 7, 14)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1.5e-2)])   # tf32 logits: the q.k scale grows with dim_head
+def test_maxvit_module_other_widths(dim, heads, dh, w, R, H, W, precision, tol):
+    """MaxViT at the widths / head sizes of BASELINE configs[4] (dim 512, dim_head 64) and other constructor arguments the
+    reference accepts (window 8, one register token, heads * dim_head != dim): the general (un-fused) attention path"""
+    from vit_grid_model_b200 import MaxViT
+    depth, N = 2, 2
+    sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, R), seed=7)
+    m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=R)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision(precision)
+    x, cond = rnd(N, dim, H, W, seed=1), rnd(N, 2, seed=2)
+    with torch.no_grad():
+        y = m(x.cuda(), cond.cuda())
+    ref = mo.maxvit_forward(x, cond, sd, depth=depth, heads=heads, window=w, num_reg=R)
+    assert rel_err(y, ref) < tol
+
+
 # ------------------------------------------------------------------------------------------ decoder side
 @pytest.mark.parametrize("dtype,tf32,out_dtype", [(torch.float32, False, torch.float32), (torch.bfloat16, False, torch.bfloat16),
                                                   (torch.float32, True, torch.bfloat16)])

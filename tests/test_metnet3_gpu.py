@@ -43,6 +43,24 @@ def test_golden_from_reference(golden, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["metnet3_wide256.pt", "metnet3_wide512.pt"])
+def test_wide_channels_golden_from_reference(golden, name, precision):
+    """BASELINE configs[4] shape (n_start_channels 512, dim_head 64) and a 256-channel depth-2 network on a small domain:
+    GEMM + row-kernel conv path and the general attention path, vs the real reference"""
+    f = golden(name)
+    cfg = synth.GridConfig(**f["cfg"])
+    m, _ = build(cfg, f["weight_seed"], precision)
+    x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
+    with torch.no_grad():
+        y = m(x.cuda(), timestamps=ts.cuda())
+    assert y.shape == f["y"].shape and torch.isfinite(y).all()
+    assert rel_err(y, f["y"]) < TOL[precision]
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x.cuda(), timestamps=ts.cuda())                    # training kernels exist for 128 channels only
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_stn_imgs_variant_golden_from_reference(golden, precision):
     """MetNet3_with_stn_imgs (metnet3.py:518-759, 25 variables): output vs the real reference class, and the reference's
     in-place normalisation of the caller's station-image channel (:701)"""

@@ -41,7 +41,8 @@ def test_maxvit_matches_reference(golden):
     torch.testing.assert_close(y, f["y"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", ["metnet3_tiny.pt", "metnet3_small128.pt", "metnet3_12hr_b1.pt"])
+@pytest.mark.parametrize("name", ["metnet3_tiny.pt", "metnet3_small128.pt", "metnet3_12hr_b1.pt", "metnet3_wide256.pt",
+                                  "metnet3_wide512.pt"])
 def test_metnet3_matches_reference(golden, name):
     f = golden(name)
     cfg = synth.GridConfig(**f["cfg"])

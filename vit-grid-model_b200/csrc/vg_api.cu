@@ -165,6 +165,42 @@ int vg_stem_finish_train_fwd(int dtype, const float* raw3, const float* rawres, 
   return stem_finish_run(dtype, p, h1, res, (cudaStream_t)stream);
 }
 
+int vg_conv3x3_ln_wide_fwd(int dtype, const void* x, int C, const void* Wt, const float* bias, const float* ln_g,
+                           const float* ln_b, float ln_eps, const float* film, const void* res, int res_f32, void* out,
+                           float* out_f32_copy, int N, int HP, int WP, const float* head_w, float head_b, float head_std,
+                           float head_mean, int H, int W, int pad_top, int pad_left, float* head_out, float* scratch,
+                           long long scratch_elems, void* stream) {
+  PGeom pg = make_pgeom(N, HP, WP);
+  if (!out && !head_w) return set_error("conv3x3_ln_wide: no output requested");
+  if (head_w && !head_out) return set_error("conv3x3_ln_wide: head_w without head_out");
+  if (C % 128 || C < 128 || C > 512) return set_error("conv3x3_ln_wide: C=%d must be 128, 256, 384 or 512", C);
+  const long long need = pg.pixels() * (long long)C * (dtype == 1 ? 2 : 1);
+  if (scratch_elems < need) return set_error("conv3x3_ln_wide: scratch too small (%lld < %lld floats)", scratch_elems, need);
+  int shifts[9];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) shifts[ky * 3 + kx] = (ky - 1) * pg.P + (kx - 1);
+  // 1. shifted-row GEMM, fp32 result [q][C]   (fp32 mode: the SIMT kernel accumulates in the second half of the scratch)
+  EpiParams ep = epi_zero();
+  ep.out = scratch; ep.ldo = C; ep.out_f32 = 1; ep.n_total = C;
+  int rc = gemm_run(dtype, EPI_STORE, x, pg.pixels(), C, Wt, C, 9, shifts, pg.pixels(), 0, 0, ep, scratch + pg.pixels() * (long long)C,
+                    scratch_elems - pg.pixels() * (long long)C, (cudaStream_t)stream);
+  if (rc) return rc;
+  // 2. bias, channel LayerNorm, FiLM, ReLU, residual, pads, optional head
+  return conv_ln_rows_run(dtype, scratch, C, bias, ln_g, ln_b, ln_eps, film, res, res_f32, out, out_f32_copy, pg, head_w, head_b,
+                          head_std, head_mean, H, W, pad_top, pad_left, head_out, (cudaStream_t)stream);
+}
+
+int vg_stem_finish_wide_fwd(int dtype, const float* raw3, const float* rawres, const float* bias3, const float* bias1,
+                            const float* tt, const float* tres, const float* ln_g, const float* ln_b, float ln_eps,
+                            const float* film, int B, int L, int HP, int WP, int C, void* h1, float* res, void* stream) {
+  StemParams p;
+  p.raw3 = raw3; p.rawres = rawres; p.bias3 = bias3; p.bias1 = bias1; p.tt = tt; p.tres = tres;
+  p.ln_g = ln_g; p.ln_b = ln_b; p.eps = ln_eps; p.film = film; p.L = L;
+  p.xhat = nullptr; p.rstd = nullptr; p.mask = nullptr;
+  p.pgB = make_pgeom(B, HP, WP); p.pgN = make_pgeom(B * L, HP, WP);
+  return stem_finish_wide_run(dtype, p, C, h1, res, (cudaStream_t)stream);
+}
+
 int vg_pool2_fwd(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, void* stream) {
   return maxpool2_run(dtype, out_f32, in, out, N, HP, WP, C, (cudaStream_t)stream);
 }

@@ -555,12 +555,12 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st) {
   const int bke = dtype == 2 ? 32 : 64;
-  if (Ca % bke) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, bke);
+  if (dtype != 1 && Ca % bke) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, bke);   // SIMT path: any Ca
   if (ntaps < 1 || ntaps > 9) return set_error("gemm: bad tap count %d", ntaps);
   if (M <= 0) return 0;
   GemmShape gs;
   gs.M = M;
-  gs.cblocks = Ca / bke;
+  gs.cblocks = dtype == 1 ? 1 : Ca / bke;                    // the SIMT kernel only uses k_blocks / cblocks = ntaps
   gs.k_blocks = gs.cblocks * ntaps;
   for (int i = 0; i < 9; ++i) gs.tap_shift[i] = i < ntaps ? tap_shift[i] : 0;
   const bool batched = rows_per_batch > 0 && rows_per_batch < M;

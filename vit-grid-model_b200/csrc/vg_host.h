@@ -62,6 +62,11 @@ int time_terms_run(const TimeParams& p, cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st);
+int stem_finish_wide_run(int dtype, const StemParams& p, int C, void* h1, float* res, cudaStream_t st);
+int conv_ln_rows_run(int dtype, const float* acc, int C, const float* bias, const float* ln_g, const float* ln_b, float eps,
+                     const float* film, const void* res, int res_f32, void* out, float* out2, const PGeom& pg,
+                     const float* head_w, float head_b, float head_std, float head_mean, int H, int W, int pad_top,
+                     int pad_left, float* head_out, cudaStream_t st);
 int maxpool2_run(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st);
 int dwconv_run(int dtype, const void* in, const float* w9, const float* scale, const float* shift, void* out, float* psum,
                int N, int H, int W, int C, cudaStream_t st);

@@ -379,6 +379,153 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ h, cons
 }
 
 // ================================================================================================
+// Channel widths other than 128 (n_start_channels = 256 / 384 / 512, BASELINE configs[4]).  The fused conv kernels keep
+// one 128-channel row per TMEM lane; wider networks run the 3x3 convolution as a plain tcgen05 shifted-row GEMM into an
+// fp32 scratch [q][C] and finish with the row kernels below (HBM-bound: one warp per pixel, lane owns channels
+// i*128 + lane*4 .. +3, statistics by warp shuffles).  Same math as epi_conv_ln / stem_finish_kernel.
+// ================================================================================================
+struct WideRowParams {
+  const float* acc;                          // [q][C] GEMM result (no bias)
+  const float* bias; const float* ln_g; const float* ln_b; float eps;
+  const float* film;                         // (N, 2C) or null
+  const void* res; int res_f32;              // residual [q][C] (fp32 or T) or null
+  void* out; float* out2;                    // [q][C] in T (or null) / fp32 copy (or null)
+  const float* head_w; float* head_out; float head_b, head_std, head_mean; int head_H, head_W, head_pt, head_pl;
+  int C;
+  PGeom pg;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_ln_rows_kernel(const WideRowParams p) {
+  const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= p.pg.pixels()) return;
+  const int lane = threadIdx.x & 31, C = p.C, nv = C >> 7;
+  int n = 0, h = 0, w = 0;
+  const bool valid = p.pg.decode(q, n, h, w);
+  float4 y[4];
+  float head = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        const float4 a = *reinterpret_cast<const float4*>(p.acc + q * C + c), b = *reinterpret_cast<const float4*>(p.bias + c);
+        y[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+      }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        y[i].x -= mean; y[i].y -= mean; y[i].z -= mean; y[i].w -= mean;
+        ss += y[i].x * y[i].x + y[i].y * y[i].y + y[i].z * y[i].z + y[i].w * y[i].w;
+      }
+    const float rstd = rsqrtf(fmaxf(warp_sum(ss) / (float)C, p.eps));       // var.clamp(min=eps).rsqrt()  (metnet3.py:104)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        const float4 g = *reinterpret_cast<const float4*>(p.ln_g + c), b = *reinterpret_cast<const float4*>(p.ln_b + c);
+        float z[4] = {y[i].x * rstd * g.x + b.x, y[i].y * rstd * g.y + b.y, y[i].z * rstd * g.z + b.z, y[i].w * rstd * g.w + b.w};
+        if (p.film) {
+          const float4 sc = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c);
+          const float4 sh = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + C + c);
+          z[0] = z[0] * (sc.x + 1.0f) + sh.x; z[1] = z[1] * (sc.y + 1.0f) + sh.y;
+          z[2] = z[2] * (sc.z + 1.0f) + sh.z; z[3] = z[3] * (sc.w + 1.0f) + sh.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = fmaxf(z[k], 0.f);
+        if (p.res) {
+          const float4 r = p.res_f32 ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + q * C + c)
+                                     : Ld4<T>::ld(reinterpret_cast<const T*>(p.res) + q * C + c);
+          z[0] += r.x; z[1] += r.y; z[2] += r.z; z[3] += r.w;
+        }
+        y[i] = make_float4(z[0], z[1], z[2], z[3]);
+        if (p.head_w) {
+          const float4 hw = *reinterpret_cast<const float4*>(p.head_w + c);
+          head += z[0] * hw.x + z[1] * hw.y + z[2] * hw.z + z[3] * hw.w;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      if (p.out) Ld4<T>::st(reinterpret_cast<T*>(p.out) + q * C + c, y[i]);
+      if (p.out2) *reinterpret_cast<float4*>(p.out2 + q * C + c) = y[i];
+    }
+  if (p.head_w && valid) {
+    head = warp_sum(head);
+    const int hh = h - p.head_pt, ww = w - p.head_pl;
+    if (lane == 0 && hh >= 0 && hh < p.head_H && ww >= 0 && ww < p.head_W)
+      p.head_out[((long long)n * p.head_H + hh) * p.head_W + ww] = (head + p.head_b) * p.head_std + p.head_mean;
+  }
+}
+
+// stem_finish_kernel for C = 128 * nv (inference only)
+template <typename T>
+__global__ void __launch_bounds__(256) stem_finish_wide_kernel(const StemParams p, int C, T* __restrict__ h1, float* __restrict__ res) {
+  const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= p.pgN.pixels()) return;
+  const int lane = threadIdx.x & 31, nv = C >> 7;
+  int n = 0, h = 0, w = 0;
+  const bool valid = p.pgN.decode(q, n, h, w);
+  float4 y[4], r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    const int b = n / p.L;
+    const long long qb = p.pgB.q(b, h, w);
+    const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1), rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        const float4 a = *reinterpret_cast<const float4*>(p.raw3 + qb * C + c), bb = *reinterpret_cast<const float4*>(p.bias3 + c);
+        const float4 tt = *reinterpret_cast<const float4*>(p.tt + ((long long)n * 9 + ry * 3 + rx) * C + c);
+        y[i] = make_float4(a.x + bb.x + tt.x, a.y + bb.y + tt.y, a.z + bb.z + tt.z, a.w + bb.w + tt.w);
+        s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+        const float4 ra = *reinterpret_cast<const float4*>(p.rawres + qb * C + c), rb = *reinterpret_cast<const float4*>(p.bias1 + c);
+        const float4 rt = *reinterpret_cast<const float4*>(p.tres + (long long)n * C + c);
+        r[i] = make_float4(ra.x + rb.x + rt.x, ra.y + rb.y + rt.y, ra.z + rb.z + rt.z, ra.w + rb.w + rt.w);
+      }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        y[i].x -= mean; y[i].y -= mean; y[i].z -= mean; y[i].w -= mean;
+        ss += y[i].x * y[i].x + y[i].y * y[i].y + y[i].z * y[i].z + y[i].w * y[i].w;
+      }
+    const float rstd = rsqrtf(fmaxf(warp_sum(ss) / (float)C, p.eps));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        const float4 g = *reinterpret_cast<const float4*>(p.ln_g + c), be = *reinterpret_cast<const float4*>(p.ln_b + c);
+        const float4 sc = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c);
+        const float4 sh = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + C + c);
+        y[i].x = fmaxf((y[i].x * rstd * g.x + be.x) * (sc.x + 1.0f) + sh.x, 0.f);
+        y[i].y = fmaxf((y[i].y * rstd * g.y + be.y) * (sc.y + 1.0f) + sh.y, 0.f);
+        y[i].z = fmaxf((y[i].z * rstd * g.z + be.z) * (sc.z + 1.0f) + sh.z, 0.f);
+        y[i].w = fmaxf((y[i].w * rstd * g.w + be.w) * (sc.w + 1.0f) + sh.w, 0.f);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      Ld4<T>::st(h1 + q * C + c, y[i]);
+      *reinterpret_cast<float4*>(res + q * C + c) = r[i];
+    }
+}
+
+// ================================================================================================
 // Focal-R loss (not in the reference; README.md:16): loss = mean(|e| * (2*sigmoid(beta*|e|)-1)^gamma)
 // ================================================================================================
 __device__ __forceinline__ float focal_term(float e, float beta, float gamma, int mse, float* dterm) {
@@ -466,6 +613,29 @@ int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaSt
   if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), res);
   else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), res);
   return check_launch("stem_finish_kernel");
+}
+
+int stem_finish_wide_run(int dtype, const StemParams& p, int C, void* h1, float* res, cudaStream_t st) {
+  if (C % 128 || C < 128 || C > 512) return set_error("stem_finish_wide: C=%d must be 128, 256, 384 or 512", C);
+  const unsigned g = nblk(p.pgN.pixels(), 8);
+  if (dtype == 0) stem_finish_wide_kernel<bf16><<<g, 256, 0, st>>>(p, C, reinterpret_cast<bf16*>(h1), res);
+  else stem_finish_wide_kernel<float><<<g, 256, 0, st>>>(p, C, reinterpret_cast<float*>(h1), res);
+  return check_launch("stem_finish_wide_kernel");
+}
+
+int conv_ln_rows_run(int dtype, const float* acc, int C, const float* bias, const float* ln_g, const float* ln_b, float eps,
+                     const float* film, const void* res, int res_f32, void* out, float* out2, const PGeom& pg,
+                     const float* head_w, float head_b, float head_std, float head_mean, int H, int W, int pad_top,
+                     int pad_left, float* head_out, cudaStream_t st) {
+  if (C % 128 || C < 128 || C > 512) return set_error("conv_ln_rows: C=%d must be 128, 256, 384 or 512", C);
+  WideRowParams p;
+  p.acc = acc; p.bias = bias; p.ln_g = ln_g; p.ln_b = ln_b; p.eps = eps; p.film = film; p.res = res; p.res_f32 = res_f32;
+  p.out = out; p.out2 = out2; p.head_w = head_w; p.head_out = head_out; p.head_b = head_b; p.head_std = head_std;
+  p.head_mean = head_mean; p.head_H = H; p.head_W = W; p.head_pt = pad_top; p.head_pl = pad_left; p.C = C; p.pg = pg;
+  const unsigned g = nblk(pg.pixels(), 8);
+  if (dtype == 0) conv_ln_rows_kernel<bf16><<<g, 256, 0, st>>>(p);
+  else conv_ln_rows_kernel<float><<<g, 256, 0, st>>>(p);
+  return check_launch("conv_ln_rows_kernel");
 }
 
 int maxpool2_run(int dtype, int out_f32, const void* in, void* out, int N, int HP, int WP, int C, cudaStream_t st) {

@@ -140,9 +140,10 @@ class MetNet3(nn.Module):
                                     depth=resnet_block_depth)
         self.classifier_pm25 = nn.Conv2d(n_start_channels, 1, kernel_size=1)
 
-        if n_start_channels != 128:
-            # the conv+ChanLayerNorm epilogue keeps one full channel row per TMEM lane (128 fp32 columns)
-            self._unsupported = f"n_start_channels={n_start_channels}: the sm_100a kernels are built for 128 channels"
+        if n_start_channels not in (128, 256, 384, 512):
+            # the fused conv+ChanLayerNorm epilogue keeps a 128-channel row per TMEM lane; 256 / 384 / 512 run the
+            # GEMM + row-kernel path (inference); other widths have no kernels
+            self._unsupported = f"n_start_channels={n_start_channels}: built for 128 (fused path), 256, 384 and 512 channels"
         else:
             self._unsupported = None
         self.compute_dtype, self.precision = torch.bfloat16, "bf16"
@@ -307,6 +308,8 @@ class MetNet3(nn.Module):
     def _forward_train(self, x, ts):
         """train() mode: batch-statistic BatchNorm, activations saved, hand-written backward (train.py)"""
         from .train import MetNet3TrainFn
+        if self.n_start_channels != 128:
+            raise NotImplementedError("the training kernels are built for n_start_channels=128; wider networks run inference only")
         if self.precision == "bf16_all":
             raise NotImplementedError("training supports set_precision('bf16') (mixed) and 'fp32'")
         if self.dropout > 0 and self.precision != "bf16":

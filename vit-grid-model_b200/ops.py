@@ -119,13 +119,21 @@ def conv_tap_shifts(WP):
 def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy=None, head=None):
     """head = (w[C], b, std, mean, H, W, pads, out (N,H,W) fp32) fuses the 1x1 head / unpad / de-normalisation"""
     dtype = x.dtype
-    keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
+    C = x.shape[1]
     res_f32 = int(res is not None and res.dtype == torch.float32 and dtype != torch.float32)
     if head is None:
         hw, hb, hs, hm, H, W, pt, pl, ho = None, 0.0, 1.0, 0.0, 0, 0, 0, 0, None
     else:
         hw, hb, hs, hm, H, W, pads, ho = head
         pl, _, pt, _ = pads
+    if C != 128:
+        # other widths (256 / 384 / 512): plain shifted-row GEMM into an fp32 scratch + row-wise LN / FiLM / ReLU / residual
+        scratch = torch.empty(x.shape[0] * C * (2 if dtype == torch.float32 else 1), dtype=torch.float32, device=x.device)
+        _lib.call("vg_conv3x3_ln_wide_fwd", DT_CODE[dtype], x.data_ptr(), C, Wt.data_ptr(), bias.data_ptr(), ln_g.data_ptr(),
+                  ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP, _p(hw), float(hb),
+                  float(hs), float(hm), H, W, pt, pl, _p(ho), scratch.data_ptr(), scratch.numel(), _st())
+        return out
+    keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
     _lib.call("vg_conv3x3_ln_fwd", DT_CODE[dtype], x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
               ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP,
               _p(hw), float(hb), float(hs), float(hm), H, W, pt, pl, _p(ho), sp, sn, _st())
@@ -133,6 +141,12 @@ def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy
 
 
 def stem_finish(raw3, rawres, bias3, bias1, tt, tres, ln_g, ln_b, eps, film, B, L, HP, WP, h1, res):
+    C = h1.shape[1]
+    if C != 128:
+        _lib.call("vg_stem_finish_wide_fwd", DT_CODE[h1.dtype], raw3.data_ptr(), rawres.data_ptr(), bias3.data_ptr(),
+                  bias1.data_ptr(), tt.data_ptr(), tres.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), float(eps),
+                  film.data_ptr(), B, L, HP, WP, C, h1.data_ptr(), res.data_ptr(), _st())
+        return
     _lib.call("vg_stem_finish_fwd", DT_CODE[h1.dtype], raw3.data_ptr(), rawres.data_ptr(), bias3.data_ptr(),
               bias1.data_ptr(), tt.data_ptr(), tres.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), float(eps),
               film.data_ptr(), B, L, HP, WP, h1.data_ptr(), res.data_ptr(), _st())
