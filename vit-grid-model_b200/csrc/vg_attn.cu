@@ -156,11 +156,11 @@ template <typename T, int DH>
 static int core_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, cudaStream_t st) {
   const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   const size_t smem = 4 * (size_t)(2 * S * (DH + 1) + nb) * sizeof(float);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  static size_t attr_bytes = 48 * 1024;                     // the size depends on the window geometry: raise the limit when it grows
+  if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("attn_core smem attr: %s", cudaGetErrorString(e));
-    attr = true;
+    attr_bytes = smem;
   }
   const long long pairs = (long long)g.N * g.nwin() * heads;
   attn_core_kernel<T, DH><<<(unsigned)((pairs + 3) / 4), 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), pairs);

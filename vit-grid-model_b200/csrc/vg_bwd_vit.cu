@@ -1450,11 +1450,11 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   if (use_tf32 == 2) {
     const size_t smem3 = (size_t)cbh::BYTES + (size_t)(2 * nb + 6 * cbh::DH) * sizeof(float);
-    static bool attr3 = false;
-    if (!attr3) {
+    static size_t attr3 = 0;                        // depends on the window size: raise the limit when it grows
+    if (smem3 > attr3) {
       cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
       if (e != cudaSuccess) return set_error("attn_core_bwd_bf16 smem attr: %s", cudaGetErrorString(e));
-      attr3 = true;
+      attr3 = smem3;
     }
     AttnCoreBwdParams q;
     q.qkv = qkv; q.datt = datt; q.qgamma = qgamma; q.kgamma = kgamma; q.bias_table = bias_table; q.dqkv = dqkv;
@@ -1464,11 +1464,11 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   }
   if (use_tf32) {
     const size_t smem2 = (size_t)(cb::SLOT_FLOATS + 2 * nb + 2 * cb::DH) * sizeof(float);
-    static bool attr2 = false;
-    if (!attr2) {
+    static size_t attr2 = 0;                        // depends on the window size: raise the limit when it grows
+    if (smem2 > attr2) {
       cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
       if (e != cudaSuccess) return set_error("attn_core_bwd_mma smem attr: %s", cudaGetErrorString(e));
-      attr2 = true;
+      attr2 = smem2;
     }
     AttnCoreBwdParams q;
     q.qkv = qkv; q.datt = datt; q.qgamma = qgamma; q.kgamma = kgamma; q.bias_table = bias_table; q.dqkv = dqkv;
@@ -1478,11 +1478,11 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   }
   if (att_out) return set_error("attn_core_bwd: att_out is only produced by the tf32 kernel");
   const size_t smem = (size_t)(8 * 64 * 33 + 64 * 65 + 2 * nb + 128 + 8 * 2 * 32) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr = 0;                        // depends on the window size: raise the limit when it grows
+  if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("attn_core_bwd smem attr: %s", cudaGetErrorString(e));
-    attr = true;
+    attr = smem;
   }
   AttnCoreBwdParams p;
   p.qkv = qkv; p.datt = datt; p.qgamma = qgamma; p.kgamma = kgamma; p.bias_table = bias_table; p.dqkv = dqkv;
