@@ -12,7 +12,7 @@ namespace vg {
 static inline unsigned nblk(long long total, int per) { return (unsigned)((total + per - 1) / per); }
 
 __device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752440f));
+  const float cdf = 0.5f * (1.0f + erf_as(u * 0.70710678118654752440f));
   return cdf + u * 0.3989422804014327f * __expf(-0.5f * u * u);
 }
 
