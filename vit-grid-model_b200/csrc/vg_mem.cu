@@ -68,6 +68,44 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
   }
 }
 
+// prepare for inputs whose (H, W) planes are contiguous (the layout the reference's loader produces after its permute,
+// evaluation_vit.py:248-249): tiles run over the FLAT pixel index h*W + w, so a 67-wide row does not waste a third of
+// every 32-column tile, and each thread has its eight loads in flight before the transposing store.
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int HW = p.H * p.W;
+  const int px0 = blockIdx.x * 32;
+  const int cblocks = p.Cpad / 64;
+  const int b = blockIdx.y / cblocks, ch0 = (blockIdx.y - b * cblocks) * 64;
+  const int TC = p.T * p.C;
+  const float* xb = p.x + (long long)b * p.sB;
+  const int pl = threadIdx.x & 31, cl0 = threadIdx.x >> 5;         // lane = pixel (coalesced 128-byte rows), warp = channel
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = ch0 + cl0 + 8 * k, px = px0 + pl;
+    v[k] = 0.f;
+    if (ch < TC && px < HW) {
+      const int t = ch / p.C, c = ch - t * p.C;
+      v[k] = xb[(long long)t * p.sT + (long long)c * p.sC + px];
+      if (c == 4 || c == 10 || c == 16 || c == 22) v[k] = (v[k] - p.mean) / p.stdv;     // metnet3.py:362,370
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tile[cl0 + 8 * k][pl] = v[k];
+  __syncthreads();
+  const int wl = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
+  const int px = px0 + wl;
+  if (px < HW) {
+    const int h = px / p.W, w = px - h * p.W;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = tile[c8 + j][wl];
+    st8(out + p.pg.q(b, h + p.pad_top, w + p.pad_left) * p.Cpad + ch0 + c8, o);
+  }
+}
+
 // ================================================================================================
 // time terms.  Field n = b*L + l.  temb[n] = [lead_emb(l+1) | scrambled model-time embedding] (metnet3.py:389-402,
 // quirk Q1: the three (N,te) embeddings are concatenated on dim 0 and re-viewed as (N,3te)); cond[n] = lead_emb.
@@ -158,71 +196,99 @@ __global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_
 // ================================================================================================
 
 template <typename T>
-__global__ void __launch_bounds__(256, 4) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
-  constexpr int C = 128, PX = 2;                   // pixels per warp: the loads of both pixels are in flight together
-  const long long q0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PX;
-  if (q0 >= p.pgN.pixels()) return;
-  const int lane = threadIdx.x & 31, c0 = lane * 4;
-  const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0), rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
-  const float4 g4 = *reinterpret_cast<const float4*>(p.ln_g + c0), b4 = *reinterpret_cast<const float4*>(p.ln_b + c0);
-  bool valid[PX];
-  int nn[PX];
-  float4 a[PX], tt[PX], ra[PX], rt[PX], f0[PX], f1[PX];
-#pragma unroll
-  for (int k = 0; k < PX; ++k) {
-    const long long q = q0 + k;
-    int n = 0, h = 0, w = 0;
-    valid[k] = q < p.pgN.pixels() && p.pgN.decode(q, n, h, w);
-    nn[k] = n;
-    if (valid[k]) {
-      const int b = n / p.L;
-      const long long qb = p.pgB.q(b, h, w);
-      const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1), rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
-      a[k] = *reinterpret_cast<const float4*>(p.raw3 + qb * C + c0);
-      tt[k] = *reinterpret_cast<const float4*>(p.tt + ((long long)n * 9 + ry * 3 + rx) * C + c0);
-      ra[k] = *reinterpret_cast<const float4*>(p.rawres + qb * C + c0);
-      rt[k] = *reinterpret_cast<const float4*>(p.tres + (long long)n * C + c0);
-      f0[k] = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c0);
-      f1[k] = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + C + c0);
+__global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
+  // One block per (sample b, PG row r): the L fields of a sample share raw3 / rawres, so each pixel's two rows are loaded
+  // ONCE and finished for all L lead times (L2 reads / L); the per-lead constants of the row (FiLM scale / shift, the
+  // residual's time term, the three border cases of the conv's time term) sit in shared memory.  Each warp walks the
+  // row's pixels.  (History: pixel-per-warp with per-pixel index divisions and six table loads, 1.81 ms at 768 fields;
+  // row-per-field blocks, 1.45 ms, bound by re-reading raw3 / rawres from L2 for each of the 12 leads.)
+  constexpr int C = 128, LS = 6 * C;                         // per lead: film scale | film shift | tres | tt[rx = 0, 1, 2]
+  extern __shared__ float s_lead[];
+  const int R = p.pgN.R, P = p.pgN.P, L = p.L;
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  T* xhat = reinterpret_cast<T*>(p.xhat);
+  const int h = r - 1;
+  const bool pad_row = r < 1;
+  if (!pad_row) {
+    const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1);
+    for (int i = threadIdx.x; i < L * LS / 4; i += 256) {
+      const int l = i / (LS / 4), k = (i - l * (LS / 4)) * 4, n = b * L + l;
+      const float* src = k < 2 * C ? p.film + (long long)n * 2 * C + k
+                       : (k < 3 * C ? p.tres + (long long)n * C + (k - 2 * C) : p.tt + ((long long)n * 9 + ry * 3) * C + (k - 3 * C));
+      *reinterpret_cast<float4*>(s_lead + l * LS + k) = *reinterpret_cast<const float4*>(src);
     }
   }
-#pragma unroll
-  for (int k = 0; k < PX; ++k) {
-    const long long q = q0 + k;
-    if (q >= p.pgN.pixels()) break;
-    float y[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
-    unsigned nib = 0u;
-    float rstd_save = 0.f;
-    if (valid[k]) {
-      float v[4] = {a[k].x + bb.x + tt[k].x, a[k].y + bb.y + tt[k].y, a[k].z + bb.z + tt[k].z, a[k].w + bb.w + tt[k].w};
-      const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
-      const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
-      rstd_save = rstd;
-      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float s[4] = {f0[k].x, f0[k].y, f0[k].z, f0[k].w}, t[4] = {f1[k].x, f1[k].y, f1[k].z, f1[k].w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xh[i] = v[i] * rstd;
-        float z = xh[i] * g[i] + be[i];
-        z = z * (s[i] + 1.0f) + t[i];
-        if (z > 0.f) nib |= 1u << i;
-        y[i] = fmaxf(z, 0.f);
-      }
-      r[0] = ra[k].x + rb.x + rt[k].x; r[1] = ra[k].y + rb.y + rt[k].y; r[2] = ra[k].z + rb.z + rt[k].z; r[3] = ra[k].w + rb.w + rt[k].w;
+  __syncthreads();
+  const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0), rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
+  const float4 g4 = *reinterpret_cast<const float4*>(p.ln_g + c0), b4 = *reinterpret_cast<const float4*>(p.ln_b + c0);
+  const long long qb_row = ((long long)b * R + r) * P;       // this row in the B-image geometry (same R, P)
+  for (int col = warp; col < P; col += 8) {
+    const bool pad = pad_row || col < 1;
+    float4 a = z, ra = z;
+    if (!pad) {
+      a = *reinterpret_cast<const float4*>(p.raw3 + (qb_row + col) * C + c0);
+      ra = *reinterpret_cast<const float4*>(p.rawres + (qb_row + col) * C + c0);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      ra.x += rb.x; ra.y += rb.y; ra.z += rb.z; ra.w += rb.w;
     }
-    Ld4<T>::st(h1 + q * C + c0, make_float4(y[0], y[1], y[2], y[3]));
-    *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
-    if (p.xhat) {                                   // training: what the backward pass needs
-      Ld4<T>::st(reinterpret_cast<T*>(p.xhat) + q * C + c0, make_float4(xh[0], xh[1], xh[2], xh[3]));
-      unsigned wbits = nib << ((lane & 7) * 4);
-      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
-      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
-      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
-      if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
-      if (lane == 0) p.rstd[q] = rstd_save;
+    const int w = col - 1;
+    const int rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
+#pragma unroll 2
+    for (int l = 0; l < L; ++l) {
+      const long long q = (((long long)(b * L + l)) * R + r) * P + col;
+      float y[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned nib = 0u;
+      float rstd_save = 0.f;
+      if (!pad) {
+        const float* sl = s_lead + l * LS + c0;
+        const float4 f0 = *reinterpret_cast<const float4*>(sl), f1 = *reinterpret_cast<const float4*>(sl + C);
+        const float4 rt = *reinterpret_cast<const float4*>(sl + 2 * C), tt = *reinterpret_cast<const float4*>(sl + (3 + rx) * C);
+        float v[4] = {a.x + tt.x, a.y + tt.y, a.z + tt.z, a.w + tt.w};
+        const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
+        const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
+        rstd_save = rstd;
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float sc[4] = {f0.x, f0.y, f0.z, f0.w}, t[4] = {f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[i] = v[i] * rstd;
+          float zz = xh[i] * g[i] + be[i];
+          zz = zz * (sc[i] + 1.0f) + t[i];
+          if (zz > 0.f) nib |= 1u << i;
+          y[i] = fmaxf(zz, 0.f);
+        }
+        rr[0] = ra.x + rt.x; rr[1] = ra.y + rt.y; rr[2] = ra.z + rt.z; rr[3] = ra.w + rt.w;
+      }
+      Ld4<T>::st(h1 + q * C + c0, make_float4(y[0], y[1], y[2], y[3]));
+      *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+      if (xhat) {                                     // training: what the backward pass needs
+        Ld4<T>::st(xhat + q * C + c0, make_float4(xh[0], xh[1], xh[2], xh[3]));
+        unsigned wbits = nib << ((lane & 7) * 4);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+        if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
+        if (lane == 0) p.rstd[q] = rstd_save;
+      }
+    }
+  }
+  // the single extra pad row that closes the PG buffer (row index N*R)
+  if (blockIdx.x == gridDim.x - 1) {
+    const long long rowl = (long long)p.pgN.N * R;
+    for (int col = warp; col < P; col += 8) {
+      const long long q = rowl * P + col;
+      Ld4<T>::st(h1 + q * C + c0, z);
+      *reinterpret_cast<float4*>(res + q * C + c0) = z;
+      if (xhat) {
+        Ld4<T>::st(xhat + q * C + c0, z);
+        if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = 0u;
+        if (lane == 0) p.rstd[q] = 0.f;
+      }
     }
   }
 }
@@ -587,6 +653,12 @@ int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, in
   const size_t esz = dtype == 0 ? 2 : 4;
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)p.pg.pixels() * Cpad * esz, st);
   if (e != cudaSuccess) return set_error("prepare memset: %s", cudaGetErrorString(e));
+  if (xs[4] == 1 && xs[3] == W) {                              // contiguous (H, W) planes
+    dim3 gridf((unsigned)((H * W + 31) / 32), (unsigned)(B * (Cpad / 64)));
+    if (dtype == 0) prepare_flat_kernel<bf16><<<gridf, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
+    else prepare_flat_kernel<float><<<gridf, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
+    return check_launch("prepare_flat_kernel");
+  }
   dim3 grid((W + 31) / 32, H, B * (Cpad / 64));
   if (dtype == 0) prepare_kernel<bf16><<<grid, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
   else prepare_kernel<float><<<grid, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
@@ -609,9 +681,18 @@ int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0
 }
 
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st) {
-  const unsigned g = nblk(p.pgN.pixels(), 8 * 2);
-  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, 0, st>>>(p, reinterpret_cast<bf16*>(h1), res);
-  else stem_finish_kernel<float><<<g, 256, 0, st>>>(p, reinterpret_cast<float*>(h1), res);
+  const unsigned g = (unsigned)(p.pgB.N * p.pgB.R);          // one block per (sample, PG row)
+  const size_t smem = (size_t)p.L * 6 * 128 * sizeof(float);
+  if (smem > 200 * 1024) return set_error("stem_finish: %d lead times need %zu bytes of shared memory", p.L, smem);
+  static size_t attr[2] = {48 * 1024, 48 * 1024};
+  if (smem > attr[dtype == 0 ? 0 : 1]) {
+    cudaError_t e = dtype == 0 ? cudaFuncSetAttribute(stem_finish_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(stem_finish_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("stem_finish smem attr: %s", cudaGetErrorString(e));
+    attr[dtype == 0 ? 0 : 1] = smem;
+  }
+  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res);
+  else stem_finish_kernel<float><<<g, 256, smem, st>>>(p, reinterpret_cast<float*>(h1), res);
   return check_launch("stem_finish_kernel");
 }
 
