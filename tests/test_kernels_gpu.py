@@ -346,6 +346,30 @@ def test_convT2(dtype, tf32, out_dtype):
     assert rel_err(o.pg_to_nchw(out, N, 2 * Hl, 2 * Wl), ref) < TOL[out_dtype]
 
 
+def test_conv3x3_cta_pair_kernel_matches_single_cta(monkeypatch):
+    """conv_halo2_kernel (tcgen05 cta_group::2, two CTAs per M256 instruction, VG_CONV_PAIR=1) == conv_halo_kernel, bit for bit,
+    with residual / FiLM / fp32 copy and an odd number of tiles"""
+    o = ops()
+    N, HP, WP, C = 5, 28, 28, 128
+    x = o.pg_from_nchw(rnd(N, C, HP, WP, seed=1).cuda(), torch.bfloat16)
+    w = (rnd(C, 9 * C, seed=2) / 34).cuda().bfloat16()
+    b, g, be = rnd(C, seed=3, scale=0.1).cuda(), (1 + rnd(C, seed=4, scale=0.1)).cuda(), rnd(C, seed=5, scale=0.1).cuda()
+    film = rnd(N, 2 * C, seed=6, scale=0.1).cuda()
+    res = rnd(x.shape[0], C, seed=7).cuda()
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("VG_CONV_PAIR", pair)
+        out, copy = torch.zeros_like(x), torch.zeros(x.shape[0], C, device="cuda")
+        o.conv3x3_ln(x, w, b, g, be, 1e-5, film, res, out, N, HP, WP, out_copy=copy)
+        out2 = torch.zeros_like(x)
+        o.conv3x3_ln(x, w, b, g, be, 1e-5, None, None, out2, N, HP, WP)
+        torch.cuda.synchronize()
+        outs.append((out, copy, out2))
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
+    assert outs[0][0].float().abs().max() > 0
+
+
 def test_conv3x3_ln_fp32_skip_copy_and_fused_head():
     """bf16 block with an fp32 residual, an fp32 output copy and the 1x1 head fused into the epilogue"""
     o = ops()
