@@ -148,10 +148,11 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
                     int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
                     int grid_mode, float* scratch, long long scratch_elems, void* stream);
 
-/* maxvit.py:170-219 + 298-340 in ONE kernel (fp32 residual stream, tcgen05 kind::tf32 projections / QK^T, bf16 PV):
+/* maxvit.py:170-219 + 298-340 in ONE kernel (fp32 residual stream, tcgen05 kind::f16 QKV projection on fp16 operands, kind::tf32 QK^T / out-projection, bf16 PV):
  * gather + register tokens + LayerNorm + FiLM -> per head {QKV, QK-RMSNorm, QK^T + rel-pos bias, softmax, PV,
  * out-projection accumulated over heads} -> + residual -> inverse partition.  x/x_out: CL (N,Hl,Wl,128) fp32;
- * wqkv_h: fp32 [heads][96][128] (per head the 32 q rows, 32 k rows, 32 v rows of to_qkv.weight);
+ * wqkv_h: fp16 [heads][96][128] (per head the 32 q rows, 32 k rows, 32 v rows of to_qkv.weight, rounded to fp16:
+ * the QKV projection runs as kind::f16 on fp16 operands -- tf32's 10-bit mantissa at twice the rate);
  * wout_h: fp32 [heads][128][32] (per head the 32 columns of to_out.0.weight); head_tab: fp32 [heads][800] =
  * per head the relative-position bias as 7 pre-shifted copies [bi][row 0..12][8] (entry k = table[(row*13 + bi+6-k)]),
  * table[169] (+7 pad), 32*gamma_q*gamma_k [32], 32 unused.  Needs C=128, dim_head=32, win=7, R=4, heads >= 4.
@@ -159,7 +160,7 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
  * to_out output with drop probability T/256 (kept values scaled by 256/(256-T)); the masks are a counter-based hash of
  * (drop_seed, drop_salt = layer id, row, group) that the backward kernels regenerate.  T = 0: no dropout (eval). */
 VG_API int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
-                      const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
+                      const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
                       int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt, int drop_thresh, void* stream);
 
 /* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */

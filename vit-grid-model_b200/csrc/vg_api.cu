@@ -255,7 +255,7 @@ int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, cons
 }
 
 int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
-                      const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
+                      const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
                       int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt, int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;

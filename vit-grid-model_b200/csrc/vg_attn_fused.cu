@@ -3,9 +3,11 @@
 // One persistent CTA processes tiles of TWO windows (2 x 64 token slots = the 128 rows of a tcgen05 M=128 MMA).
 // Nothing between the residual stream in and the residual stream out touches HBM:
 //
-//   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (smem, tf32)
+//   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (smem, fp16)
 //   per head h (weights and the per-head tables streamed by TMA, accumulators re-used as operands in TMEM):
-//     QKV_h = X * Wqkv_h^T           tcgen05 kind::tf32  M128 N96  K128      -> TMEM
+//     QKV_h = X * Wqkv_h^T           tcgen05 kind::f16 (fp16 operands: the 10-bit mantissa of tf32 at twice the rate and
+//                                    half the shared-memory bytes; X is LayerNorm output, far inside the fp16 range)
+//                                    M128 N96  K128                          -> TMEM
 //     k RMSNorm in registers: K" = k * (32 gq gk) / |k| (tf32) and V^T (bf16) -> smem; q stays in TMEM, 1/|q| per row
 //     S = q K"^T                     tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the q accumulator)
 //     S/|q| + relative-position bias (index computed arithmetically), masked softmax in registers;
@@ -32,9 +34,10 @@ constexpr int DH = 32;         // head dim
 constexpr int SLOT = 64;       // token slots per window (S <= 64)
 constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specialised for 7x7 windows + 4 register tokens
 // shared memory map (bytes); every operand tile is 1024-B aligned
-constexpr int X_OFF = 0;                         // 4 k-blocks x [128 rows x 128 B]
-constexpr int WQ_OFF = X_OFF + 4 * 16384;        // 4 k-blocks x [96 rows x 128 B]
-constexpr int WO_OFF = WQ_OFF + 4 * 12288;       // [128 rows x 128 B]
+constexpr int X_OFF = 0;                         // fp16: 2 k-blocks x [128 rows x 128 B]
+constexpr int WQ_BYTES = 2 * 12288;              // fp16: 2 k-blocks x [96 rows x 128 B]
+constexpr int WQ_OFF = X_OFF + 2 * 16384;        // 2 buffers (heads alternate)
+constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B]
 constexpr int R1_OFF = WO_OFF + 16384;           // 2 x 32 KiB: K" (first 16 KiB)  ->  P (2 k-blocks of 16 KiB)
 constexpr int VT_OFF = R1_OFF + 2 * 32768;       // 2 x [2 k-blocks x 32 rows x 128 B]
 constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
@@ -86,6 +89,10 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -124,7 +131,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* wq_full = bars + 0;  uint64_t* wq_free = bars + 1;
+  uint64_t* wq_full = bars + 0;  uint64_t* wq_free = bars + 22;   // [2] each: one per QKV weight buffer
   uint64_t* wo_full = bars + 2;  uint64_t* wo_free = bars + 3;
   uint64_t* x_ready = bars + 4;
   uint64_t* qkv_done = bars + 5;                 // [2]
@@ -142,7 +149,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   const int heads = p.heads;
 
   if (warp == 1 && lane == 0) {
-    mbar_init(wq_full, 1); mbar_init(wq_free, 1); mbar_init(wo_full, 1); mbar_init(wo_free, 1);
+    mbar_init(wq_full + 0, 1); mbar_init(wq_full + 1, 1); mbar_init(wq_free + 0, 1); mbar_init(wq_free + 1, 1);
+    mbar_init(wo_full, 1); mbar_init(wo_free, 1);
     mbar_init(x_ready, 8);
     mbar_init(qkv_done + 0, 1); mbar_init(qkv_done + 1, 1);
     mbar_init(qk_ready + 0, 8); mbar_init(qk_ready + 1, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8);
@@ -174,10 +182,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       const long long total = my_tiles * heads;
       auto load_wq = [&](long long j) {
         const int h = (int)(j % heads);
-        mbar_wait_tag(wq_free, (uint32_t)((j & 1) ^ 1), 172);
-        mbar_arrive_expect_tx(wq_full, 4 * 12288);
+        const uint32_t b = (uint32_t)(j & 1);
+        mbar_wait_tag(wq_free + b, (uint32_t)(((j >> 1) & 1) ^ 1), 172);    // QKV(j-2) has read this buffer
+        mbar_arrive_expect_tx(wq_full + b, WQ_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + WQ_OFF + kb * 12288, &mapWq, wq_full, kb * 32, h * 96);
+        for (int kb = 0; kb < 2; ++kb) tma_load_2d(smem + WQ_OFF + b * WQ_BYTES + kb * 12288, &mapWq, wq_full + b, kb * 64, h * 96);
       };
       auto load_tab = [&](long long j) {
         const int h = (int)(j % heads);
@@ -187,43 +196,42 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         bulk_load(smem + TAB_OFF + r * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + r);
       };
       // need-order of the MMA warp: QKV(0..2) at the start, then per head j: out(j) [WO(j)] followed by QKV(j+3) [WQ(j+3)]
+      // (WQ(2) waits for QKV(0), which needs nothing but WQ(0) and the X tile)
       for (long long j = 0; j < 3 && j < total; ++j) { load_wq(j); if (j < 2) load_tab(j); }
       for (long long j = 0; j < total; ++j) {
         mbar_wait_tag(wo_free, (uint32_t)((j & 1) ^ 1), 187);
         mbar_arrive_expect_tx(wo_full, 16384);
         tma_load_2d(smem + WO_OFF, &mapWo, wo_full, 0, (int)(j % heads) * 128);
-        // WQ(j+3) waits for QKV(j+2); for the last two heads of a tile that projection belongs to the NEXT tile and is only
-        // issued after this tile's last out-projection, so those two loads are deferred behind WO(last head of the tile)
-        const int hj = (int)(j % heads);
-        if (hj < heads - 2) { if (j + 3 < total) load_wq(j + 3); }
-        else if (hj == heads - 1) { if (j + 2 < total) load_wq(j + 2); if (j + 3 < total) load_wq(j + 3); }
+        // WQ(j+3) re-uses the buffer of WQ(j+1): it waits for QKV(j+1), which the MMA warp issued before out(j-1)
+        if (j + 3 < total) load_wq(j + 3);
         if (j + 2 < total) load_tab(j + 2);
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      constexpr uint32_t id_qkv = umma_idesc_tf32(128, 96);
+      constexpr uint32_t id_qkv = umma_idesc_f16(128, 96);
       constexpr uint32_t id_s = umma_idesc_tf32(128, 128);
       constexpr uint32_t id_pv = umma_idesc_bf16(128, 32);
       constexpr uint32_t id_out = umma_idesc_tf32(128, 128);
       const uint32_t sX = smem_u32(smem + X_OFF), sWQ = smem_u32(smem + WQ_OFF), sWO = smem_u32(smem + WO_OFF);
       uint32_t it = 0, tl = 0;                               // global head counter, tile counter
       auto issue_qkv = [&](uint32_t hh) {
-        mbar_wait_tag(wq_full, hh & 1, 203);
+        const uint32_t b = hh & 1;
+        mbar_wait_tag(wq_full + b, (hh >> 1) & 1, 203);
         tc_fence_after();
-        const uint32_t d = tmem + ((hh & 1) ? T_QKV1 : T_QKV0);
-        // running descriptors (not 32 pre-computed ones): they stay in uniform registers, so every tcgen05.mma issues
+        const uint32_t d = tmem + (b ? T_QKV1 : T_QKV0);
+        // running descriptors (not pre-computed ones): they stay in uniform registers, so every tcgen05.mma issues
         // without a vector->uniform register round trip
-        uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ);
+        uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ + b * WQ_BYTES);
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32(d, da + 2 * k, db + 2 * k, id_qkv, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d, da + 2 * k, db + 2 * k, id_qkv, (kb | k) ? 1u : 0u);
           da += 16384 >> 4; db += 12288 >> 4;
         }
-        tc_commit(qkv_done + (hh & 1));
-        tc_commit(wq_free);
+        tc_commit(qkv_done + b);
+        tc_commit(wq_free + b);
       };
       auto issue_s = [&](uint32_t hh) {                      // S = q K"^T, A = the q accumulator of head hh read from TMEM
         const uint32_t r = hh & 1;
@@ -272,24 +280,24 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (md) md[3] = clock64();
           mbar_wait_tag(wo_full, it & 1, 246);
           if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
-          if (do_qkv) mbar_wait_tag(wq_full, hq & 1, 203);
+          if (do_qkv) mbar_wait_tag(wq_full + (hq & 1), (hq >> 1) & 1, 203);
           tc_fence_after();
           if (md) md[4] = clock64();
           {
             const uint32_t dq = tmem + ((hq & 1) ? T_QKV1 : T_QKV0);
-            const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ), dwo = umma_desc_k128(sWO);
+            const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ + (hq & 1) * WQ_BYTES), dwo = umma_desc_k128(sWO);
 #pragma unroll
-            for (int st = 0; st < 16; ++st) {
+            for (int st = 0; st < 8; ++st) {
               if (do_qkv) {
                 const int kb = st >> 2, k = st & 3;
-                tc_mma_tf32(dq, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
+                tc_mma_bf16(dq, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
               }
               if (st < 4) {                                        // Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM)
                 tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);
                 if (st == 3) tc_commit(wo_free);
               }
             }
-            if (do_qkv) { tc_commit(qkv_done + (hq & 1)); tc_commit(wq_free); }
+            if (do_qkv) { tc_commit(qkv_done + (hq & 1)); tc_commit(wq_free + (hq & 1)); }
           }
           if (md) { md[5] = clock64(); md[6] = md[5]; md[7] = md[5]; }
         }
@@ -374,7 +382,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     uint32_t it = 0, tl = 0;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      // ---------------- gather + LayerNorm + FiLM -> X tile (tf32, swizzled K-major) ----------------
+      // ---------------- gather + LayerNorm + FiLM -> X tile (fp16, swizzled K-major) ----------------
       const long long wdx = tile * 2 + half;
       const bool win_valid = wdx < p.n_windows;
       const int n = win_valid ? (int)(wdx / nwin) : 0;
@@ -413,15 +421,20 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         pair_sync(lg);
         const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
         const float* film = p.film + (long long)n * 2 * C + ch * 64;
+        // fp16 operand tile: this thread's 64 channels are the 128-byte row of k-block `ch`
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) {
+          uint32_t pk[4] = {0u, 0u, 0u, 0u};
           if (src) {
-            const float4 ga = *reinterpret_cast<const float4*>(film + c * 4), be = *reinterpret_cast<const float4*>(film + C + c * 4);
-            o.x = v[c].x * rstd * ga.x + be.x; o.y = v[c].y * rstd * ga.y + be.y;
-            o.z = v[c].z * rstd * ga.z + be.z; o.w = v[c].w * rstd * ga.w + be.w;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 xv = v[2 * c + e];
+              const float4 ga = *reinterpret_cast<const float4*>(film + (2 * c + e) * 4), be = *reinterpret_cast<const float4*>(film + C + (2 * c + e) * 4);
+              pk[2 * e] = pack_f16(xv.x * rstd * ga.x + be.x, xv.y * rstd * ga.y + be.y);
+              pk[2 * e + 1] = pack_f16(xv.z * rstd * ga.z + be.z, xv.w * rstd * ga.w + be.w);
+            }
           }
-          sts128(s_base + X_OFF + (ch * 2 + (c >> 3)) * 16384 + swz[c & 7], o.x, o.y, o.z, o.w);
+          sts128u(s_base + X_OFF + ch * 16384 + swz[c], pk[0], pk[1], pk[2], pk[3]);
         }
       }
       fence_async_smem();
@@ -575,7 +588,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_w_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, int box_outer) {
+static int make_w_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, int box_outer, bool f16) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* q = nullptr;
@@ -584,20 +597,21 @@ static int make_w_map(CUtensorMap* m, const void* ptr, long long inner, long lon
       return set_error("cuTensorMapEncodeTiled entry point unavailable");
     fn = reinterpret_cast<EncodeTiledFn>(q);
   }
+  const int esz = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_outer};      // 128-byte rows (one swizzle atom)
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("attn_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
 
-// wqkv_h: fp32 [heads*96][128] (per head: 32 q rows, 32 k rows, 32 v rows); wout_h: fp32 [heads*128][32]
+// wqkv_h: fp16 [heads*96][128] (per head: 32 q rows, 32 k rows, 32 v rows); wout_h: fp32 [heads*128][32]
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
-                   const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab,
+                   const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab,
                    const AttnGeom& g, int heads, int dh, float ln_eps, unsigned seed, unsigned salt, int drop_thresh,
                    cudaStream_t st) {
   if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_fused: dropout threshold %d outside [0, 255]", drop_thresh);
@@ -605,9 +619,9 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   if (heads < 4) return set_error("attn_fused: the head pipeline needs at least 4 heads (got %d)", heads);
   if (g.win != fa::WIN || g.R != fa::REG) return set_error("attn_fused: specialised for 7x7 windows + 4 register tokens (got %d, %d)", g.win, g.R);
   CUtensorMap mq, mo;
-  int rc = make_w_map(&mq, wqkv_h, 128, (long long)heads * 96, 96);
+  int rc = make_w_map(&mq, wqkv_h, 128, (long long)heads * 96, 96, true);
   if (rc) return rc;
-  rc = make_w_map(&mo, wout_h, 32, (long long)heads * 128, 128);
+  rc = make_w_map(&mo, wout_h, 32, (long long)heads * 128, 128, false);
   if (rc) return rc;
   FusedAttnParams p;
   p.x = x; p.x_out = x_out; p.reg_in = reg_in; p.reg_per_field = reg_per_field; p.reg_out = reg_out; p.film = film;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -222,6 +223,11 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D=f32, A=B=fp16 (kind::f16 with the fp16 operand format), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D=f32, A=B=tf32 (fp32 storage), both K-major

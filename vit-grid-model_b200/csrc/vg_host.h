@@ -99,7 +99,7 @@ int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* 
                   const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st);
 
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
-                   const float* film, const float* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,
+                   const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,
                    unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
 
 // ---- training (vg_wgrad.cu, vg_bwd.cu, vg_bwd_vit.cu)

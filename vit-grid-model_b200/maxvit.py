@@ -177,7 +177,7 @@ class MaxViT(nn.Module):
                 wq = att.to_qkv.weight.float()
                 # per-head operand tiles of the fused kernel: [q_h | k_h | v_h] rows, and the head's to_out columns
                 P[name]["wqkv_h"] = torch.stack([wq[i * inner:(i + 1) * inner].reshape(hd, dh, -1) for i in range(3)],
-                                                dim=1).reshape(hd * 3 * dh, -1).contiguous()
+                                                dim=1).reshape(hd * 3 * dh, -1).half().contiguous()   # fp16 operand of the fused kernel
                 P[name]["wout_h"] = att.to_out[0].weight.float().reshape(-1, hd, dh).permute(1, 0, 2).contiguous()
                 if att.window_size == 7 and dh == 32:
                     P[name]["head_tab"] = ops.pack_head_tables(P[name]["bias_table"], P[name]["q_gamma"], P[name]["k_gamma"])

@@ -262,6 +262,8 @@ def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, wan
     nwin = (Hl // win) * (Wl // win)
     x_out = torch.empty_like(x)
     reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x.device) if want_reg_out else None
+    if wqkv_h.dtype != torch.float16:                       # the kernel's QKV operand format (the modules pack it once)
+        wqkv_h = wqkv_h.half()
     _lib.call("vg_attn_fused_fwd", x.data_ptr(), x_out.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out),
               film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
               int(drop[0]), int(drop[1]), int(drop[2]), _st())
