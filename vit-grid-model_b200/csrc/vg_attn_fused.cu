@@ -11,8 +11,8 @@
 //     k RMSNorm in registers: K" = k * (32 gq gk) / |k| (tf32) and V^T (bf16) -> smem; q stays in TMEM, 1/|q| per row
 //     S = q K"^T                     tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the q accumulator)
 //     S/|q| + relative-position bias (index computed arithmetically), masked softmax in registers;
-//     P / rowsum (bf16) -> smem
-//     O_h = P V                      tcgen05 kind::f16   M128 N32  K128      -> TMEM
+//     P / rowsum (bf16) -> TMEM (tcgen05.st over the first 64 columns of the S accumulator)
+//     O_h = P V                      tcgen05 kind::f16   M128 N32  K128, A operand = P read from TMEM -> TMEM
 //     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the O accumulator),
 //                                    accumulated over heads
 //   epilogue: Out + residual, scattered back through the inverse partition map; register-token rows to reg_out.
@@ -38,8 +38,9 @@ constexpr int X_OFF = 0;                         // fp16: 2 k-blocks x [128 rows
 constexpr int WQ_BYTES = 2 * 12288;              // fp16: 2 k-blocks x [96 rows x 128 B]
 constexpr int WQ_OFF = X_OFF + 2 * 16384;        // 2 buffers (heads alternate)
 constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B]
-constexpr int R1_OFF = WO_OFF + 16384;           // 2 x 32 KiB: K" (first 16 KiB)  ->  P (2 k-blocks of 16 KiB)
-constexpr int VT_OFF = R1_OFF + 2 * 32768;       // 2 x [2 k-blocks x 32 rows x 128 B]
+constexpr int R1_BYTES = 16384;                  // K" operand: tf32 [128 keys x 128 B]
+constexpr int R1_OFF = WO_OFF + 16384;           // 2 buffers (heads alternate)
+constexpr int VT_OFF = R1_OFF + 2 * R1_BYTES;    // 2 x [2 k-blocks x 32 rows x 128 B]
 constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
 constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
 constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
@@ -51,7 +52,7 @@ constexpr int THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / t
 constexpr int T_QKV0 = 0;      // 96   (QKV accumulators of even heads)
 constexpr int T_O = 96;        // 32
 constexpr int T_QKV1 = 128;    // 96   (odd heads)
-constexpr int T_S = 256;       // 128
+constexpr int T_S = 256;       // 128  (S; its first 64 columns are then overwritten by P as packed bf16 pairs, the A operand of PV)
 constexpr int T_OUT = 384;     // 128
 constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace fa
@@ -115,6 +116,23 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T with 16-bit operands: A = packed bf16 pairs written with tcgen05.st (one 32-bit column per two k)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 registers -> 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // plain (non-tensor) TMA copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -209,7 +227,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // The whole warp runs this role converged (all lanes poll the barriers); the tcgen05 instructions of a batch are issued
+    // by one elected lane.  Written this way nvcc emits the UTCHMMAs of a batch back to back; a `lane == 0` branch makes it
+    // wrap each one in an ELECT / BRA.U.ANY loop.
+    {
       constexpr uint32_t id_qkv = umma_idesc_f16(128, 96);
       constexpr uint32_t id_s = umma_idesc_tf32(128, 128);
       constexpr uint32_t id_pv = umma_idesc_bf16(128, 32);
@@ -220,32 +241,34 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const uint32_t b = hh & 1;
         mbar_wait_tag(wq_full + b, (hh >> 1) & 1, 203);
         tc_fence_after();
-        const uint32_t d = tmem + (b ? T_QKV1 : T_QKV0);
-        // running descriptors (not pre-computed ones): they stay in uniform registers, so every tcgen05.mma issues
-        // without a vector->uniform register round trip
-        uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ + b * WQ_BYTES);
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
+        if (elect_one()) {
+          const uint32_t d = tmem + (b ? T_QKV1 : T_QKV0);
+          const uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ + b * WQ_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_bf16(d, da + 2 * k, db + 2 * k, id_qkv, (kb | k) ? 1u : 0u);
-          da += 16384 >> 4; db += 12288 >> 4;
+          for (int st = 0; st < 8; ++st) {
+            const int kb = st >> 2, k = st & 3;
+            tc_mma_bf16(d, da + kb * (16384 >> 4) + 2 * k, db + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
+          }
+          tc_commit(qkv_done + b);
+          tc_commit(wq_free + b);
         }
-        tc_commit(qkv_done + b);
-        tc_commit(wq_free + b);
+        __syncwarp();
       };
       auto issue_s = [&](uint32_t hh) {                      // S = q K"^T, A = the q accumulator of head hh read from TMEM
         const uint32_t r = hh & 1;
         mbar_wait_tag(qk_ready + r, (hh >> 1) & 1, 224);
         tc_fence_after();
-        const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
-        const uint64_t db = umma_desc_k128(smem_u32(smem + R1_OFF + r * 32768));
+        if (elect_one()) {
+          const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
+          const uint64_t db = umma_desc_k128(smem_u32(smem + R1_OFF + r * R1_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
-        tc_commit(s_done);
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
+          tc_commit(s_done);
+        }
+        __syncwarp();
       };
-      // Issue order per head h:  [wait p_ready(h)]  S(h+1)  PV(h)  out(h)  QKV(h+3)
-      // S(h+1) goes first so that the next softmax can start while PV / out-projection / QKV of other heads execute; the
-      // QKV projection runs three heads ahead (its TMEM buffer was last read by the S product issued just before it).
+      // Issue order per head h:  [wait p_ready(h)]  PV(h)  S(h+1)  out(h) + QKV(h+3)
+      // The QKV projection runs three heads ahead (its TMEM buffer was last read by the S product issued just before it).
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         mbar_wait_tag(x_ready, tl & 1, 216);
         tc_fence_after();
@@ -255,53 +278,60 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         if (heads > 2) issue_qkv(it + 2);
         for (int h = 0; h < heads; ++h, ++it) {
           const uint32_t r = it & 1;
-          const uint32_t sR1 = smem_u32(smem + R1_OFF + r * 32768), sVT = smem_u32(smem + VT_OFF + r * 8192);
-          long long* md = (p.dbg && blockIdx.x == 0 && tl == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
+          const uint32_t sVT = smem_u32(smem + VT_OFF + r * 8192);
+          long long* md = (p.dbg && blockIdx.x == 0 && tl == 0 && lane == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
           if (md) md[0] = clock64();
-          mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: S accumulator free, P(h) in smem
+          mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: P(h) sits in the first 64 columns of the S accumulator
           tc_fence_after();
           if (md) md[1] = clock64();
-          if (h + 1 < heads) issue_s(it + 1);
-          if (md) md[2] = clock64();
-          // ---- PV(h) first (it releases the operand buffers the staging warps wait for), then out(h) interleaved with the QKV
-          // projection of head h+3: the two accumulate into different TMEM columns.  (QKV(h+3) may not be mixed with S(h+1): it
-          // overwrites the q columns that product reads.)
+          // ---- PV(h) first (A = P from TMEM; it also releases the operand buffers the staging warps wait for), then S(h+1),
+          // which overwrites P: the tensor pipe executes in issue order.  Then out(h) and the QKV projection of head h+3,
+          // interleaved: the two accumulate into different TMEM columns.  (QKV(h+3) may not be mixed with S(h+1): it overwrites
+          // the q columns that product reads.)
           const bool do_qkv = h + 3 < heads;
           const uint32_t hq = it + 3;
-          {
-            const uint64_t dpa = umma_desc_k128(sR1), dvt = umma_desc_k128(sVT);
+          if (elect_one()) {
+            const uint64_t dvt = umma_desc_k128(sVT);
 #pragma unroll
             for (int st = 0; st < 8; ++st) {                       // O = P V
               const int kb = st >> 2, k = st & 3;
-              tc_mma_bf16(tmem + T_O, dpa + kb * (16384 >> 4) + 2 * k, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
+              tc_mma_bf16_ts(tmem + T_O, tmem + T_S + 8 * st, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
             }
             tc_commit(pv_done + r);
           }
+          __syncwarp();
+          if (md) md[2] = clock64();
+          if (h + 1 < heads) issue_s(it + 1);
           if (md) md[3] = clock64();
           mbar_wait_tag(wo_full, it & 1, 246);
           if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
           if (do_qkv) mbar_wait_tag(wq_full + (hq & 1), (hq >> 1) & 1, 203);
           tc_fence_after();
           if (md) md[4] = clock64();
-          {
+          if (elect_one()) {
             const uint32_t dq = tmem + ((hq & 1) ? T_QKV1 : T_QKV0);
             const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ + (hq & 1) * WQ_BYTES), dwo = umma_desc_k128(sWO);
+            if (do_qkv) {
 #pragma unroll
-            for (int st = 0; st < 8; ++st) {
-              if (do_qkv) {
+              for (int st = 0; st < 8; ++st) {
                 const int kb = st >> 2, k = st & 3;
                 tc_mma_bf16(dq, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
-              }
-              if (st < 4) {                                        // Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM)
-                tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);
+                if (st < 4) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);   // Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM)
                 if (st == 3) tc_commit(wo_free);
               }
+              tc_commit(qkv_done + (hq & 1));
+              tc_commit(wq_free + (hq & 1));
+            } else {
+#pragma unroll
+              for (int st = 0; st < 4; ++st) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);
+              tc_commit(wo_free);
             }
-            if (do_qkv) { tc_commit(qkv_done + (hq & 1)); tc_commit(wq_free + (hq & 1)); }
           }
+          __syncwarp();
           if (md) { md[5] = clock64(); md[6] = md[5]; md[7] = md[5]; }
         }
-        tc_commit(tile_done);
+        if (elect_one()) tc_commit(tile_done);
+        __syncwarp();
       }
     }
   } else if (warp >= 10) {
@@ -316,7 +346,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int hx = 0; hx < heads; ++hx, ++itx) {
         const uint32_t r = itx & 1;
-        const uint32_t R1 = s_base + R1_OFF + r * 32768;
+        const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
         const uint32_t VT = s_base + VT_OFF + r * 8192;
         mbar_wait_tag(qkv_done + r, (itx >> 1) & 1, 352);
         tc_fence_after();
@@ -445,7 +475,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
         if (dbg) p.dbg[h * 8 + 0] = clock64();
         const uint32_t r = it & 1;
-        const uint32_t R1 = s_base + R1_OFF + r * 32768;
+        const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
         if (dbg) p.dbg[h * 8 + 1] = clock64();
         mbar_wait_tag(tab_full + r, (it >> 1) & 1, 394);                          // per-head bias table (TMA)
@@ -525,17 +555,21 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) sc[j] *= inv_sum;
           }
-          // own 32 keys = chunks [ch*4, +4) of this row in k-block `half`; same chunks of the other k-block are zero
-          const uint32_t prow = R1 + half * 16384, zrow = R1 + (half ^ 1) * 16384;
+          // P row (bf16 pairs, one 32-bit TMEM column per two keys) over the first 64 columns of this lane's S accumulator:
+          // own 32 keys -> columns [half*32 + ch*16, +16); the same keys of the other window are zero.  Both threads of the pair
+          // hold their S half-row in registers since the first pair_sync above.
+          {
+            uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            sts128u(prow + swz[ch * 4 + c], pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
-                    pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
-            sts128u(zrow + swz[ch * 4 + c], 0u, 0u, 0u, 0u);
+            for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(sc[2 * c], sc[2 * c + 1]);
+            tmem_st16(lane_addr + T_S + half * 32 + ch * 16, pk);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[c] = 0u;
+            tmem_st16(lane_addr + T_S + (half ^ 1) * 32 + ch * 16, pk);
+            tmem_wait_st();
           }
         }
         tc_fence_before();
-        fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
         if (dbg) { const long long c5 = clock64(); p.dbg[h * 8 + 5] = c5; p.dbg[h * 8 + 6] = c5; p.dbg[h * 8 + 7] = c5; }
