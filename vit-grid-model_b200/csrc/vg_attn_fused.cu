@@ -11,7 +11,8 @@
 //     k RMSNorm in registers: K" = k * (32 gq gk) / |k| (tf32) and V^T (bf16) -> smem; q stays in TMEM, 1/|q| per row
 //     S = q K"^T                     tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the q accumulator)
 //     S/|q| + relative-position bias (index computed arithmetically), masked softmax in registers;
-//     P / rowsum (bf16) -> TMEM (tcgen05.st over the first 64 columns of the S accumulator)
+//     P / rowsum (bf16) -> TMEM (tcgen05.st, 64 columns of bf16 pairs; the S accumulator is free for the next head as soon
+//                                    as the softmax warps hold S in registers)
 //     O_h = P V                      tcgen05 kind::f16   M128 N32  K128, A operand = P read from TMEM -> TMEM
 //     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the O accumulator),
 //                                    accumulated over heads
@@ -37,9 +38,9 @@ constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specia
 constexpr int X_OFF = 0;                         // fp16: 2 k-blocks x [128 rows x 128 B]
 constexpr int WQ_BYTES = 2 * 12288;              // fp16: 2 k-blocks x [96 rows x 128 B]
 constexpr int WQ_OFF = X_OFF + 2 * 16384;        // 2 buffers (heads alternate)
-constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B]
+constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B], 2 buffers
 constexpr int R1_BYTES = 16384;                  // K" operand: tf32 [128 keys x 128 B]
-constexpr int R1_OFF = WO_OFF + 16384;           // 2 buffers (heads alternate)
+constexpr int R1_OFF = WO_OFF + 2 * 16384;       // 2 buffers (heads alternate)
 constexpr int VT_OFF = R1_OFF + 2 * R1_BYTES;    // 2 x [2 k-blocks x 32 rows x 128 B]
 constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
 constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
@@ -48,11 +49,13 @@ constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // 2 x float[128]: 1/|q
 constexpr int BAR_OFF = QINV_OFF + 2 * 512;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
 constexpr int THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / tile prologue + epilogue, warps 10..17 operand staging (2 threads per token row each)
-// TMEM columns
-constexpr int T_QKV0 = 0;      // 96   (QKV accumulators of even heads)
-constexpr int T_O = 96;        // 32
-constexpr int T_QKV1 = 128;    // 96   (odd heads)
-constexpr int T_S = 256;       // 128  (S; its first 64 columns are then overwritten by P as packed bf16 pairs, the A operand of PV)
+// TMEM columns (all 512 in use)
+constexpr int T_QKV0 = 0;      // 96   q | k | v accumulators of even heads
+constexpr int T_QKV1 = 96;     // 96   odd heads
+constexpr int T_OV = 64;       // O_h (32 columns) is written over the v columns of the OTHER head parity's buffer: that buffer is
+                               // dead between the S product of head h+1 and the QKV projection of head h+3
+constexpr int T_P = 192;       // 64   P as bf16 pairs (A operand of PV)
+constexpr int T_S = 256;       // 128
 constexpr int T_OUT = 384;     // 128
 constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace fa
@@ -149,18 +152,19 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* wq_full = bars + 0;  uint64_t* wq_free = bars + 22;   // [2] each: one per QKV weight buffer
-  uint64_t* wo_full = bars + 2;  uint64_t* wo_free = bars + 3;
-  uint64_t* x_ready = bars + 4;
-  uint64_t* qkv_done = bars + 5;                 // [2]
-  uint64_t* qk_ready = bars + 20;                // [2]: one per operand buffer (the compute warps run one head ahead of the MMA warp)
-  uint64_t* s_done = bars + 8;
-  uint64_t* p_ready = bars + 9;
-  uint64_t* pv_done = bars + 10;                 // [2]  R1[r] / VT[r] no longer read by MMAs
-  uint64_t* tile_done = bars + 12; uint64_t* out_free = bars + 13;
-  uint64_t* tab_full = bars + 14;                // [2]
-  uint64_t* tab_free = bars + 16;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* wq_full = bars + 0;  uint64_t* wq_free = bars + 2;    // [2] each: one per QKV weight buffer
+  uint64_t* wo_full = bars + 4;  uint64_t* wo_free = bars + 6;    // [2] each
+  uint64_t* x_ready = bars + 8;
+  uint64_t* qkv_done = bars + 9;                 // [2]
+  uint64_t* qk_ready = bars + 11;                // [2]: one per operand buffer
+  uint64_t* s_done = bars + 13;
+  uint64_t* p_ready = bars + 14;
+  uint64_t* pv_done = bars + 15;                 // [2]  R1[r] / VT[r] no longer read by MMAs
+  uint64_t* tile_done = bars + 17; uint64_t* out_free = bars + 18;
+  uint64_t* tab_full = bars + 19;                // [2]
+  uint64_t* tab_free = bars + 21;                // [2]
+  uint64_t* s_free = bars + 23;                  // the softmax warps hold S in registers: the next S product may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -168,7 +172,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 
   if (warp == 1 && lane == 0) {
     mbar_init(wq_full + 0, 1); mbar_init(wq_full + 1, 1); mbar_init(wq_free + 0, 1); mbar_init(wq_free + 1, 1);
-    mbar_init(wo_full, 1); mbar_init(wo_free, 1);
+    mbar_init(wo_full + 0, 1); mbar_init(wo_full + 1, 1); mbar_init(wo_free + 0, 1); mbar_init(wo_free + 1, 1);
+    mbar_init(s_free, 8);
     mbar_init(x_ready, 8);
     mbar_init(qkv_done + 0, 1); mbar_init(qkv_done + 1, 1);
     mbar_init(qk_ready + 0, 8); mbar_init(qk_ready + 1, 8); mbar_init(s_done, 1); mbar_init(p_ready, 8);
@@ -213,14 +218,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         mbar_arrive_expect_tx(tab_full + r, TAB_FLOATS * 4);
         bulk_load(smem + TAB_OFF + r * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + r);
       };
-      // need-order of the MMA warp: QKV(0..2) at the start, then per head j: out(j) [WO(j)] followed by QKV(j+3) [WQ(j+3)]
-      // (WQ(2) waits for QKV(0), which needs nothing but WQ(0) and the X tile)
+      // need-order of the MMA warp: QKV(0..2) at the start, then per head j: out(j) [WO(j)] followed by QKV(j+3) [WQ(j+3)].
+      // Every load only waits for MMAs that were issued before the ones that need it (WO(j): out(j-2); WQ(j+3): QKV(j+1);
+      // WQ(2): QKV(0), which needs nothing but WQ(0) and the X tile).
       for (long long j = 0; j < 3 && j < total; ++j) { load_wq(j); if (j < 2) load_tab(j); }
       for (long long j = 0; j < total; ++j) {
-        mbar_wait_tag(wo_free, (uint32_t)((j & 1) ^ 1), 187);
-        mbar_arrive_expect_tx(wo_full, 16384);
-        tma_load_2d(smem + WO_OFF, &mapWo, wo_full, 0, (int)(j % heads) * 128);
-        // WQ(j+3) re-uses the buffer of WQ(j+1): it waits for QKV(j+1), which the MMA warp issued before out(j-1)
+        const uint32_t b = (uint32_t)(j & 1);
+        mbar_wait_tag(wo_free + b, (uint32_t)(((j >> 1) & 1) ^ 1), 187);
+        mbar_arrive_expect_tx(wo_full + b, 16384);
+        tma_load_2d(smem + WO_OFF + b * 16384, &mapWo, wo_full + b, 0, (int)(j % heads) * 128);
         if (j + 3 < total) load_wq(j + 3);
         if (j + 2 < total) load_tab(j + 2);
       }
@@ -254,8 +260,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         }
         __syncwarp();
       };
-      auto issue_s = [&](uint32_t hh) {                      // S = q K"^T, A = the q accumulator of head hh read from TMEM
+      auto issue_s = [&](uint32_t hh, bool first) {          // S = q K"^T, A = the q accumulator of head hh read from TMEM
         const uint32_t r = hh & 1;
+        if (!first) mbar_wait_tag(s_free, (hh - 1) & 1, 225);   // the softmax warps hold S(hh-1) in registers
         mbar_wait_tag(qk_ready + r, (hh >> 1) & 1, 224);
         tc_fence_after();
         if (elect_one()) {
@@ -267,67 +274,64 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         }
         __syncwarp();
       };
-      // Issue order per head h:  [wait p_ready(h)]  PV(h)  S(h+1)  out(h) + QKV(h+3)
-      // The QKV projection runs three heads ahead (its TMEM buffer was last read by the S product issued just before it).
+      // Issue order per head h:  [p_ready(h)] PV(h), out(h), QKV(h+3)   [s_free(h+1), qk_ready(h+2)] S(h+2)
+      // The S product runs one head ahead of the softmax (S(h+1) is complete before the softmax of head h ends), the QKV
+      // projection three heads ahead: QKV(h+3) re-uses the TMEM buffer of head h+1, whose q columns were read by S(h+1) and
+      // whose v columns hold O_h between PV(h) and out(h) (the tensor pipe executes in issue order).
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         mbar_wait_tag(x_ready, tl & 1, 216);
         tc_fence_after();
         issue_qkv(it);
-        if (heads > 1) issue_qkv(it + 1);
-        issue_s(it);
-        if (heads > 2) issue_qkv(it + 2);
+        issue_qkv(it + 1);
+        issue_s(it, true);                                   // (the previous tile's last p_ready implied its s_free)
+        issue_qkv(it + 2);
+        issue_s(it + 1, false);
         for (int h = 0; h < heads; ++h, ++it) {
           const uint32_t r = it & 1;
           const uint32_t sVT = smem_u32(smem + VT_OFF + r * 8192);
           long long* md = (p.dbg && blockIdx.x == 0 && tl == 0 && lane == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
           if (md) md[0] = clock64();
-          mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: P(h) sits in the first 64 columns of the S accumulator
+          mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: P(h) is in TMEM
           tc_fence_after();
           if (md) md[1] = clock64();
-          // ---- PV(h) first (A = P from TMEM; it also releases the operand buffers the staging warps wait for), then S(h+1),
-          // which overwrites P: the tensor pipe executes in issue order.  Then out(h) and the QKV projection of head h+3,
-          // interleaved: the two accumulate into different TMEM columns.  (QKV(h+3) may not be mixed with S(h+1): it overwrites
-          // the q columns that product reads.)
           const bool do_qkv = h + 3 < heads;
-          const uint32_t hq = it + 3;
+          const uint32_t tqn = tmem + (r ? T_QKV0 : T_QKV1);       // buffer of heads h+1 / h+3
+          const uint32_t tO = tqn + T_OV;
           if (elect_one()) {
             const uint64_t dvt = umma_desc_k128(sVT);
 #pragma unroll
-            for (int st = 0; st < 8; ++st) {                       // O = P V
+            for (int st = 0; st < 8; ++st) {                       // O = P V  (A = P from TMEM)
               const int kb = st >> 2, k = st & 3;
-              tc_mma_bf16_ts(tmem + T_O, tmem + T_S + 8 * st, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
+              tc_mma_bf16_ts(tO, tmem + T_P + 8 * st, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
             }
             tc_commit(pv_done + r);
           }
           __syncwarp();
           if (md) md[2] = clock64();
-          if (h + 1 < heads) issue_s(it + 1);
-          if (md) md[3] = clock64();
-          mbar_wait_tag(wo_full, it & 1, 246);
+          mbar_wait_tag(wo_full + r, (it >> 1) & 1, 246);
           if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
-          if (do_qkv) mbar_wait_tag(wq_full + (hq & 1), (hq >> 1) & 1, 203);
+          if (do_qkv) mbar_wait_tag(wq_full + (r ^ 1), ((it + 3) >> 1) & 1, 203);
           tc_fence_after();
-          if (md) md[4] = clock64();
+          if (md) md[3] = clock64();
           if (elect_one()) {
-            const uint32_t dq = tmem + ((hq & 1) ? T_QKV1 : T_QKV0);
-            const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ + (hq & 1) * WQ_BYTES), dwo = umma_desc_k128(sWO);
-            if (do_qkv) {
+            const uint64_t dwo = umma_desc_k128(sWO + r * 16384);
+#pragma unroll
+            for (int st = 0; st < 4; ++st) tc_mma_tf32_ts(tmem + T_OUT, tO + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);   // Out += O_h Wout_h^T  (A = O_h read from TMEM)
+            tc_commit(wo_free + r);
+            if (do_qkv) {                                          // QKV(h+3) (overwrites O_h: issued after out(h))
+              const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ + (r ^ 1) * WQ_BYTES);
 #pragma unroll
               for (int st = 0; st < 8; ++st) {
                 const int kb = st >> 2, k = st & 3;
-                tc_mma_bf16(dq, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
-                if (st < 4) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);   // Out += O_h Wout_h^T  (A = the O accumulator, read from TMEM)
-                if (st == 3) tc_commit(wo_free);
+                tc_mma_bf16(tqn, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
               }
-              tc_commit(qkv_done + (hq & 1));
-              tc_commit(wq_free + (hq & 1));
-            } else {
-#pragma unroll
-              for (int st = 0; st < 4; ++st) tc_mma_tf32_ts(tmem + T_OUT, tmem + T_O + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);
-              tc_commit(wo_free);
+              tc_commit(qkv_done + (r ^ 1));
+              tc_commit(wq_free + (r ^ 1));
             }
           }
           __syncwarp();
+          if (md) md[4] = clock64();
+          if (h + 2 < heads) issue_s(it + 2, false);
           if (md) { md[5] = clock64(); md[6] = md[5]; md[7] = md[5]; }
         }
         if (elect_one()) tc_commit(tile_done);
@@ -348,26 +352,31 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const uint32_t r = itx & 1;
         const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
         const uint32_t VT = s_base + VT_OFF + r * 8192;
+        float4 gm[8];                                            // 32 * gamma_q * gamma_k of this head: in flight during the wait
+        if (ch == 0) {
+          const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) gm[c] = __ldg(ksc + c);
+        }
         mbar_wait_tag(qkv_done + r, (itx >> 1) & 1, 352);
         tc_fence_after();
         const uint32_t tq = lane_addr + (r ? T_QKV1 : T_QKV0);
         if (ch == 0) {
-          const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);   // 32 * gamma_q * gamma_k
           float v[32], w[32];
           tmem_ld32(tq, v);                                              // q
           tmem_ld32(tq + 32, w);                                         // k
           tmem_wait_ld();
-          float nq = 0.f, nk = 0.f;
+          float nq4[4] = {0.f, 0.f, 0.f, 0.f}, nk4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int d = 0; d < 32; ++d) { nq = fmaf(v[d], v[d], nq); nk = fmaf(w[d], w[d], nk); }
+          for (int d = 0; d < 32; ++d) { nq4[d & 3] = fmaf(v[d], v[d], nq4[d & 3]); nk4[d & 3] = fmaf(w[d], w[d], nk4[d & 3]); }
+          const float nq = (nq4[0] + nq4[1]) + (nq4[2] + nq4[3]), nk = (nk4[0] + nk4[1]) + (nk4[2] + nk4[3]);
           const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);           // F.normalize(eps=1e-12)  (maxvit.py:30)
           const float inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
           if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 353);    // R1[r], qinv[r] of head itx-2 are no longer in use
           qinv[r * 128 + t] = inv_q;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 gm = __ldg(ksc + c);
-            sts128(R1 + sw128(t, c), w[4 * c] * inv_k * gm.x, w[4 * c + 1] * inv_k * gm.y, w[4 * c + 2] * inv_k * gm.z, w[4 * c + 3] * inv_k * gm.w);
+            sts128(R1 + sw128(t, c), w[4 * c] * inv_k * gm[c].x, w[4 * c + 1] * inv_k * gm[c].y, w[4 * c + 2] * inv_k * gm[c].z, w[4 * c + 3] * inv_k * gm[c].w);
           }
         } else {
           float w[32];
@@ -489,6 +498,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           float sc[32];
           tmem_ld32(lane_addr + T_S + half * 64 + ch * 32, sc);
           tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);                            // S(h+1) may now overwrite the accumulator
           const float inv_q = qinv[r * 128 + t];             // written by the staging warps before qk_ready -> S -> s_done
           const float t169 = reinterpret_cast<const float*>(smem + TAB_OFF)[r * TAB_FLOATS + 7 * 13 * 8];
           const uint32_t brow = tab + (bi * 13 * 8) * 4;
@@ -555,17 +567,18 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) sc[j] *= inv_sum;
           }
-          // P row (bf16 pairs, one 32-bit TMEM column per two keys) over the first 64 columns of this lane's S accumulator:
-          // own 32 keys -> columns [half*32 + ch*16, +16); the same keys of the other window are zero.  Both threads of the pair
-          // hold their S half-row in registers since the first pair_sync above.
+          // P row (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same
+          // keys of the other window are zero.  PV(h-1) has read the previous P (it was issued a whole softmax ago).
           {
+            if (it >= 1) mbar_wait_tag(pv_done + (r ^ 1), ((it - 1) >> 1) & 1, 399);
+            const uint32_t tp = lane_addr + T_P;
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(sc[2 * c], sc[2 * c + 1]);
-            tmem_st16(lane_addr + T_S + half * 32 + ch * 16, pk);
+            tmem_st16(tp + half * 32 + ch * 16, pk);
 #pragma unroll
             for (int c = 0; c < 16; ++c) pk[c] = 0u;
-            tmem_st16(lane_addr + T_S + (half ^ 1) * 32 + ch * 16, pk);
+            tmem_st16(tp + (half ^ 1) * 32 + ch * 16, pk);
             tmem_wait_st();
           }
         }
