@@ -107,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                         // ===== MMA issuer =====
+    {                                                        // ===== MMA issuer: the warp runs converged, an elected lane issues (see elect_one) =====
       constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -119,17 +119,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da0 = umma_desc_k128(sa), da1 = umma_desc_k128(sa + A_BYTES / 2), db = umma_desc_k128(sa + A_BYTES);
+          if (elect_one()) {
+            const uint64_t da0 = umma_desc_k128(sa), da1 = umma_desc_k128(sa + A_BYTES / 2), db = umma_desc_k128(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                      // 4 x 32 B per K block, +32 B inside the swizzle atom
-            const uint32_t acc = (kb | k) ? 1u : 0u;
-            if (TF32) { tc_mma_tf32(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_tf32(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
-            else { tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
+            for (int k = 0; k < 4; ++k) {                    // 4 x 32 B per K block, +32 B inside the swizzle atom
+              const uint32_t acc = (kb | k) ? 1u : 0u;
+              if (TF32) { tc_mma_tf32(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_tf32(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
+              else { tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc); tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc); }
+            }
+            tc_commit(empty + stage);                        // frees the smem slot when these MMAs retire
+            if (kb == gs.k_blocks - 1) tc_commit(tfull + as);   // accumulators complete -> epilogue
           }
-          tc_commit(empty + stage);                          // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull + as);                               // accumulators complete -> epilogue
       }
     }
   } else if (warp >= 4) {                                    // ===== epilogue: 2 x 128 threads, one row each =====
@@ -290,7 +293,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                         // ===== MMA issuer =====
+    {                                                        // ===== MMA issuer: the warp runs converged, an elected lane issues (see elect_one) =====
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (int t = blockIdx.x; t < hs.num_tiles; t += gridDim.x, ++it) {
@@ -306,21 +309,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int r0 = halo + (tap / 3 - 1) * hs.P + (tap % 3 - 1);       // first input row of this tap
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            uint64_t da0 = umma_desc_k128_shift(sa, r0), da1 = umma_desc_k128_shift(sa, r0 + 128);
-            if (hs.use_base_offset) { da0 |= (uint64_t)(r0 & 7) << 49; da1 |= (uint64_t)((r0 + 128) & 7) << 49; }
-            const uint64_t db = umma_desc_k128(smem_u32(sB + stage * B_BYTES));
+            if (elect_one()) {
+              uint64_t da0 = umma_desc_k128_shift(sa, r0), da1 = umma_desc_k128_shift(sa, r0 + 128);
+              if (hs.use_base_offset) { da0 |= (uint64_t)(r0 & 7) << 49; da1 |= (uint64_t)((r0 + 128) & 7) << 49; }
+              const uint64_t db = umma_desc_k128(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t acc = (cb | tap | k) ? 1u : 0u;
-              tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc);
-              tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (cb | tap | k) ? 1u : 0u;
+                tc_mma_bf16(d0, da0 + 2 * k, db + 2 * k, idesc, acc);
+                tc_mma_bf16(d1, da1 + 2 * k, db + 2 * k, idesc, acc);
+              }
+              tc_commit(empty + stage);
+              if (tap == 8) {
+                tc_commit(a_free + cb);
+                if (cb == 1) tc_commit(tfull + as);
+              }
             }
-            tc_commit(empty + stage);
+            __syncwarp();
             if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(a_free + cb);
         }
-        tc_commit(tfull + as);
       }
     }
   } else if (warp >= 4) {                                    // ===== epilogue: 2 x 128 threads, one pixel row each =====
@@ -481,7 +489,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {                            // ===== MMA issuer (leader CTA, for the pair) =====
+    if (rank == 0) {                                         // ===== MMA issuer (leader CTA, for the pair): converged warp, elected lane issues =====
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (int pt = pair; pt < n_pair_tiles; pt += npairs_grid, ++it) {
@@ -497,21 +505,26 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const int r0 = halo + (tap / 3 - 1) * hs.P + (tap % 3 - 1);
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            uint64_t da0 = umma_desc_k128_shift(sa, r0), da1 = umma_desc_k128_shift(sa, r0 + 128);
-            if (hs.use_base_offset) { da0 |= (uint64_t)(r0 & 7) << 49; da1 |= (uint64_t)((r0 + 128) & 7) << 49; }
-            const uint64_t db = umma_desc_k128(smem_u32(sB + stage * B2_BYTES));
+            if (elect_one()) {
+              uint64_t da0 = umma_desc_k128_shift(sa, r0), da1 = umma_desc_k128_shift(sa, r0 + 128);
+              if (hs.use_base_offset) { da0 |= (uint64_t)(r0 & 7) << 49; da1 |= (uint64_t)((r0 + 128) & 7) << 49; }
+              const uint64_t db = umma_desc_k128(smem_u32(sB + stage * B2_BYTES));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t acc = (cb | tap | k) ? 1u : 0u;
-              tc_mma_bf16_pair(d0, da0 + 2 * k, db + 2 * k, idesc, acc);
-              tc_mma_bf16_pair(d1, da1 + 2 * k, db + 2 * k, idesc, acc);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (cb | tap | k) ? 1u : 0u;
+                tc_mma_bf16_pair(d0, da0 + 2 * k, db + 2 * k, idesc, acc);
+                tc_mma_bf16_pair(d1, da1 + 2 * k, db + 2 * k, idesc, acc);
+              }
+              tc_commit_pair(empty + stage);
+              if (tap == 8) {
+                tc_commit_pair(a_free + cb);
+                if (cb == 1) tc_commit_pair(tfull + as);
+              }
             }
-            tc_commit_pair(empty + stage);
+            __syncwarp();
             if (++stage == HB2_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit_pair(a_free + cb);
         }
-        tc_commit_pair(tfull + as);
       }
     }
   } else if (warp >= 4) {                                    // ===== epilogue (both CTAs, own tile) =====

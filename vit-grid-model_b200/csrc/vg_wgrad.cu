@@ -113,7 +113,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                           // ===== MMA issuer =====
+    {                                                          // ===== MMA issuer: converged warp, an elected lane issues (see elect_one) =====
       // both operands MN-major (transpose bits 15 / 16)
       constexpr uint32_t idesc = (TF32 ? umma_idesc_tf32(128, 128) : umma_idesc_bf16(128, 128)) | (1u << 15) | (1u << 16);
       constexpr int KSTEP_ROWS = TF32 ? 8 : 16;                // rows consumed per MMA
@@ -128,19 +128,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
         const uint32_t sy = smem_u32(smem + stage * stage_bytes);
 #pragma unroll 1
         for (int a = 0; a < nacc; ++a) {
-          const uint32_t sa = sy + (1 + a) * TILE_BYTES;
+          if (elect_one()) {
+            const uint32_t sa = sy + (1 + a) * TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < KT / KSTEP_ROWS; ++k) {
-            const uint64_t dy = umma_desc_mn128(sy + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
-            const uint64_t da = umma_desc_mn128(sa + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
-            if (TF32) tc_mma_tf32(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
-            else tc_mma_bf16(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < KT / KSTEP_ROWS; ++k) {
+              const uint64_t dy = umma_desc_mn128(sy + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
+              const uint64_t da = umma_desc_mn128(sa + k * KSTEP_ROWS * 128, lbo, sbo, LAYOUT);
+              if (TF32) tc_mma_tf32(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
+              else tc_mma_bf16(tmem + a * 128, dy, da, idesc, (kb | k) ? 1u : 0u);
+            }
+            if (a == nacc - 1) tc_commit(empty + stage);
           }
+          __syncwarp();
         }
-        tc_commit(empty + stage);
         if (++stage == ws.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done);
+      if (elect_one()) tc_commit(done);
+      __syncwarp();
     }
   } else {                                                     // ===== epilogue: lane = dW row n =====
     const int lg = warp & 3;
