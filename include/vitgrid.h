@@ -153,9 +153,10 @@ VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* W
  * out-projection accumulated over heads} -> + residual -> inverse partition.  x/x_out: CL (N,Hl,Wl,128) fp32;
  * wqkv_h: fp16 [heads][96][128] (per head the 32 q rows, 32 k rows, 32 v rows of to_qkv.weight, rounded to fp16:
  * the QKV projection runs as kind::f16 on fp16 operands -- tf32's 10-bit mantissa at twice the rate);
- * wout_h: fp32 [heads][128][32] (per head the 32 columns of to_out.0.weight); head_tab: fp32 [heads][800] =
- * per head the relative-position bias as 7 pre-shifted copies [bi][row 0..12][8] (entry k = table[(row*13 + bi+6-k)]),
- * table[169] (+7 pad), 32*gamma_q*gamma_k [32], 32 unused.  Needs C=128, dim_head=32, win=7, R=4, heads >= 4.
+ * wout_h: fp32 [heads][128][32] (per head the 32 columns of to_out.0.weight); head_tab: fp32 [heads][1332] =
+ * per head the relative-position bias times log2(e) as 7 pre-shifted copies [bi][row 0..12] (bi stride 180 floats, row stride
+ * 12 floats, entry k = 0..6 of a row = table[(row*13 + bi+6-k)]; the strides make the kernel's reads bank-conflict-free),
+ * table[169]*log2(e) x 8, 32*gamma_q*gamma_k [32], 32 unused.  Needs C=128, dim_head=32, win=7, R=4, heads >= 4.
  * Training: drop_thresh T in [1,255] enables nn.Dropout (maxvit.py:146,151) on the attention probabilities and on the
  * to_out output with drop probability T/256 (kept values scaled by 256/(256-T)); the masks are a counter-based hash of
  * (drop_seed, drop_salt = layer id, row, group) that the backward kernels regenerate.  T = 0: no dropout (eval). */

@@ -42,7 +42,11 @@ constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B], 2 b
 constexpr int R1_BYTES = 16384;                  // K" operand: tf32 [128 keys x 128 B]
 constexpr int R1_OFF = WO_OFF + 2 * 16384;       // 2 buffers (heads alternate)
 constexpr int VT_OFF = R1_OFF + 2 * R1_BYTES;    // 2 x [2 k-blocks x 32 rows x 128 B]
-constexpr int TAB_FLOATS = 7 * 13 * 8 + 8 + 64;  // shifted bias rows [bi][row][8] | t169 (+pad) | 32*gq*gk [32] | unused [32]
+// per-head table: shifted bias rows [bi][row 0..12] (row stride TAB_SR, bi stride TAB_SB floats: with these strides the
+// 16-byte reads of the eight tokens of a quarter-warp fall into different banks, 268 wavefronts per head instead of 588 for
+// the dense [7][13][8] layout) | table[169] x 8 | 32*gq*gk [32] | unused [32]
+constexpr int TAB_SR = 12, TAB_SB = 180, TAB_T169 = 7 * TAB_SB;
+constexpr int TAB_FLOATS = TAB_T169 + 8 + 64;
 constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
 constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
 constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // 2 x float[128]: 1/|q| per row (staging warps -> softmax warps), double-buffered over heads
@@ -91,6 +95,17 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
+}
+// packed fp32 pairs (FADD2 / FMUL2 on sm_100): half the issue slots of the softmax's elementwise passes
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
 }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
@@ -354,7 +369,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const uint32_t VT = s_base + VT_OFF + r * 8192;
         float4 gm[8];                                            // 32 * gamma_q * gamma_k of this head: in flight during the wait
         if (ch == 0) {
-          const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + 7 * 13 * 8 + 8);
+          const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + TAB_T169 + 8);
 #pragma unroll
           for (int c = 0; c < 8; ++c) gm[c] = __ldg(ksc + c);
         }
@@ -417,7 +432,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     for (int c = 0; c < 8; ++c) swz[c] = sw128(t, c);
     float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [4][128][2]: 0 softmax sum, 1 LN sum, 2 softmax max, 3 LN sq-sum
     const float* qinv = reinterpret_cast<const float*>(smem + QINV_OFF);
-    const float rs = sqrtf((float)DH);
+    // bias rows of this token: window tokens step one 32-byte row back per key row aj; register-token rows (maxvit.py:167:
+    // one shared bias for every key) read the constant row, with step 0 -- no per-element select
+    const uint32_t b_off = is_reg ? (uint32_t)TAB_T169 * 4u : (uint32_t)(bi * TAB_SB + (ai + 6) * TAB_SR) * 4u;
+    const uint32_t b_step = is_reg ? 0u : (uint32_t)TAB_SR * 4u;
     uint32_t it = 0, tl = 0;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
@@ -495,29 +513,29 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         tc_fence_after();
         if (dbg) p.dbg[h * 8 + 4] = clock64();
         {
-          float sc[32];
+          float2 sc2[16];
+          float* sc = reinterpret_cast<float*>(sc2);
           tmem_ld32(lane_addr + T_S + half * 64 + ch * 32, sc);
           tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free);                            // S(h+1) may now overwrite the accumulator
-          const float inv_q = qinv[r * 128 + t];             // written by the staging warps before qk_ready -> S -> s_done
-          const float t169 = reinterpret_cast<const float*>(smem + TAB_OFF)[r * TAB_FLOATS + 7 * 13 * 8];
-          const uint32_t brow = tab + (bi * 13 * 8) * 4;
+          // logits in the exp2 domain: S * (log2e / |q|) + bias * log2e (the table is stored pre-multiplied)
+          const float cq = qinv[r * 128 + t] * LOG2E;                    // written by the staging warps before qk_ready -> S -> s_done
+          const uint32_t brow = tab + b_off;                             // register-token rows read the constant row (b_step = 0)
           float m = -INFINITY;
           if (ch == 0) {
             // keys 0..3 are register tokens, keys 4..31 are window rows aj = 0..3
+            const float t169 = reinterpret_cast<const float*>(smem + TAB_OFF)[r * TAB_FLOATS + TAB_T169];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sc[j] = fmaf(sc[j], inv_q, t169);
+            for (int j = 0; j < 4; ++j) sc[j] = fmaf(sc[j], cq, t169);
 #pragma unroll
             for (int aj = 0; aj < 4; ++aj) {
-              const uint32_t a = brow + (ai + 6 - aj) * 32;
+              const uint32_t a = brow - aj * b_step;
               const float4 b0 = lds128(a), b1 = lds128(a + 16);
               float* q = sc + 4 + aj * 7;
-              q[0] = fmaf(q[0], inv_q, is_reg ? t169 : b0.x); q[1] = fmaf(q[1], inv_q, is_reg ? t169 : b0.y);
-              q[2] = fmaf(q[2], inv_q, is_reg ? t169 : b0.z); q[3] = fmaf(q[3], inv_q, is_reg ? t169 : b0.w);
-              q[4] = fmaf(q[4], inv_q, is_reg ? t169 : b1.x); q[5] = fmaf(q[5], inv_q, is_reg ? t169 : b1.y);
-              q[6] = fmaf(q[6], inv_q, is_reg ? t169 : b1.z);
+              q[0] = fmaf(q[0], cq, b0.x); q[1] = fmaf(q[1], cq, b0.y); q[2] = fmaf(q[2], cq, b0.z); q[3] = fmaf(q[3], cq, b0.w);
+              q[4] = fmaf(q[4], cq, b1.x); q[5] = fmaf(q[5], cq, b1.y); q[6] = fmaf(q[6], cq, b1.z);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) m = fmaxf(m, sc[j]);
@@ -525,13 +543,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             // keys 32..52 are window rows aj = 4..6; keys 53..63 are padding
 #pragma unroll
             for (int aj = 4; aj < 7; ++aj) {
-              const uint32_t a = brow + (ai + 6 - aj) * 32;
+              const uint32_t a = brow - aj * b_step;
               const float4 b0 = lds128(a), b1 = lds128(a + 16);
               float* q = sc + (aj - 4) * 7;
-              q[0] = fmaf(q[0], inv_q, is_reg ? t169 : b0.x); q[1] = fmaf(q[1], inv_q, is_reg ? t169 : b0.y);
-              q[2] = fmaf(q[2], inv_q, is_reg ? t169 : b0.z); q[3] = fmaf(q[3], inv_q, is_reg ? t169 : b0.w);
-              q[4] = fmaf(q[4], inv_q, is_reg ? t169 : b1.x); q[5] = fmaf(q[5], inv_q, is_reg ? t169 : b1.y);
-              q[6] = fmaf(q[6], inv_q, is_reg ? t169 : b1.z);
+              q[0] = fmaf(q[0], cq, b0.x); q[1] = fmaf(q[1], cq, b0.y); q[2] = fmaf(q[2], cq, b0.z); q[3] = fmaf(q[3], cq, b0.w);
+              q[4] = fmaf(q[4], cq, b1.x); q[5] = fmaf(q[5], cq, b1.y); q[6] = fmaf(q[6], cq, b1.z);
             }
 #pragma unroll
             for (int j = 0; j < 21; ++j) m = fmaxf(m, sc[j]);
@@ -540,18 +556,30 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (lane == 0) mbar_arrive(tab_free + r);                      // last read of this head's tables
           red[(2 * 128 + t) * 2 + ch] = m;
           pair_sync(lg);
-          m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]) * LOG2E;
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 21; ++j) { sc[j] = ex2(fmaf(sc[j], LOG2E, -m)); sum += sc[j]; }
+          m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]);
+          const float2 nm = make_float2(-m, -m);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
           if (ch == 0) {
 #pragma unroll
-            for (int j = 21; j < 32; ++j) { sc[j] = ex2(fmaf(sc[j], LOG2E, -m)); sum += sc[j]; }
+            for (int k = 0; k < 16; ++k) {
+              sc2[k] = fadd2(sc2[k], nm);
+              sc2[k].x = ex2(sc2[k].x); sc2[k].y = ex2(sc2[k].y);
+              if (k & 1) acc1 = fadd2(acc1, sc2[k]); else acc0 = fadd2(acc0, sc2[k]);
+            }
           } else {
 #pragma unroll
-            for (int j = 21; j < 32; ++j) sc[j] = 0.f;
+            for (int k = 0; k < 10; ++k) {
+              sc2[k] = fadd2(sc2[k], nm);
+              sc2[k].x = ex2(sc2[k].x); sc2[k].y = ex2(sc2[k].y);
+              if (k & 1) acc1 = fadd2(acc1, sc2[k]); else acc0 = fadd2(acc0, sc2[k]);
+            }
+            sc[20] = ex2(sc[20] - m); sc[21] = 0.f;
+            acc0 = fadd2(acc0, sc2[10]);
+#pragma unroll
+            for (int k = 11; k < 16; ++k) sc2[k] = make_float2(0.f, 0.f);
           }
-          red[(0 * 128 + t) * 2 + ch] = sum;
+          acc0 = fadd2(acc0, acc1);
+          red[(0 * 128 + t) * 2 + ch] = acc0.x + acc0.y;
           pair_sync(lg);                                                 // partner's partial row sum is visible
           const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
           if (p.drop.thresh) {                                           // nn.Dropout on the probabilities (maxvit.py:146, 209)
@@ -564,8 +592,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
               for (int k = 0; k < 4; ++k) sc[4 * c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? ks : 0.f;
             }
           } else {
+            const float2 is2 = make_float2(inv_sum, inv_sum);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sc[j] *= inv_sum;
+            for (int k = 0; k < 16; ++k) sc2[k] = fmul2(sc2[k], is2);
           }
           // P row (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same
           // keys of the other window are zero.  PV(h-1) has read the previous P (it was issued a whole softmax ago).

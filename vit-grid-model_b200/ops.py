@@ -234,24 +234,30 @@ def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None
     return x_out, reg_out
 
 
+TAB_SR, TAB_SB = 12, 180      # row / column-offset strides (floats) of the fused kernel's bias table: bank-conflict-free reads
+
+
 def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     """per-head table of the fused attention kernel: relative-position bias as `win` pre-shifted copies
-    [bi][row 0..2w-2][8] with entry k = table[row*(2w-1) + bi + (w-1) - k] (so that the 7 keys of one window row are one
-    aligned 32-byte read), then table[(2w-1)^2] (+7 pad), dh * gamma_q * gamma_k [dh] (the two RMSNorm gains and the two
-    sqrt(dh) factors of maxvit.py:26-30 folded into the key operand), dh unused.  bias_table: (nb, heads)."""
+    [bi][row 0..2w-2] with entry k (0..6) = table[row*(2w-1) + bi + (w-1) - k] (so that the 7 keys of one window row are two
+    aligned 16-byte reads; row stride TAB_SR, bi stride TAB_SB floats, chosen so that a quarter-warp's reads hit different
+    banks), then table[(2w-1)^2] x 8 (the register-token bias, maxvit.py:167, as a row of its own), dh * gamma_q * gamma_k [dh]
+    (the two RMSNorm gains and the two sqrt(dh) factors of maxvit.py:26-30 folded into the key operand), dh unused.
+    The bias entries are stored times log2(e): the kernel's softmax works in the exp2 domain.  bias_table: (nb, heads)."""
     assert win == 7, "the fused kernel is specialised for 7x7 windows"
     heads, w2 = bias_table.shape[1], 2 * win - 1
     bi = torch.arange(win).view(win, 1, 1)
     row = torch.arange(w2).view(1, w2, 1)
     k = torch.arange(8).view(1, 1, 8)
     idx = (row * w2 + bi + (win - 1) - k).clamp_(0, w2 * w2 - 1)                      # k = 7 is padding
-    T = bias_table.t().float()                                                       # (heads, nb)
+    T = bias_table.t().float() * 1.4426950408889634                                  # (heads, nb), exp2 domain
     shifted = T[:, idx.reshape(-1).to(T.device)].reshape(heads, win, w2, 8)
     shifted[..., 7] = 0
-    t_last = torch.zeros(heads, 8, device=T.device)
-    t_last[:, 0] = T[:, w2 * w2]
+    tab = torch.zeros(heads, win, TAB_SB, device=T.device)
+    tab[:, :, :w2 * TAB_SR].view(heads, win, w2, TAB_SR)[..., :8] = shifted
+    t_last = T[:, w2 * w2].reshape(heads, 1).expand(heads, 8)
     qg, kg = q_gamma.float().reshape(heads, -1), k_gamma.float().reshape(heads, -1)
-    return torch.cat([shifted.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
+    return torch.cat([tab.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
 
 
 def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5, drop=(0, 0, 0)):
