@@ -39,7 +39,7 @@ for i, nm in enumerate(names):
 print("  next-head gap           ", (d[1:, 0] - d[:-1, 7]).float()[2:].mean().item())
 
 m = dall[1]
-mn = ["wait p_ready", "issue PV", "wait WO / WQ", "issue out + QKV(h+3)", "wait s_free, qk_ready + issue S(h+2)", "-", "-"]
+mn = ["wait WO / WQ (hoisted)", "wait p_ready", "-", "issue PV + out + QKV(h+3)", "wait s_free, qk_ready + issue S(h+2)", "-", "-"]
 md = (m[:, 1:] - m[:, :-1]).float()
 print("MMA warp, head period:", (m[1:, 0] - m[:-1, 0]).float()[2:-2].mean().item())
 for i, nm in enumerate(mn):

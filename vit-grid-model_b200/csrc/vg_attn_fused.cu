@@ -306,10 +306,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           const uint32_t sVT = smem_u32(smem + VT_OFF + r * 8192);
           long long* md = (p.dbg && blockIdx.x == 0 && tl == 0 && lane == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
           if (md) md[0] = clock64();
+          const bool do_qkv = h + 3 < heads;
+          // the weights arrive a head early: poll their barriers while this warp would idle on p_ready anyway
+          mbar_wait_tag(wo_full + r, (it >> 1) & 1, 246);
+          if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
+          if (do_qkv) mbar_wait_tag(wq_full + (r ^ 1), ((it + 3) >> 1) & 1, 203);
+          if (md) md[1] = clock64();
           mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: P(h) is in TMEM
           tc_fence_after();
-          if (md) md[1] = clock64();
-          const bool do_qkv = h + 3 < heads;
+          if (md) { md[2] = clock64(); md[3] = md[2]; }
           const uint32_t tqn = tmem + (r ? T_QKV0 : T_QKV1);       // buffer of heads h+1 / h+3
           const uint32_t tO = tqn + T_OV;
           if (elect_one()) {
@@ -322,12 +327,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             tc_commit(pv_done + r);
           }
           __syncwarp();
-          if (md) md[2] = clock64();
-          mbar_wait_tag(wo_full + r, (it >> 1) & 1, 246);
-          if (h == 0) mbar_wait_tag(out_free, (tl & 1) ^ 1, 247);     // previous tile's epilogue has drained Out
-          if (do_qkv) mbar_wait_tag(wq_full + (r ^ 1), ((it + 3) >> 1) & 1, 203);
+          // out(h) reads O_h as its A operand from TMEM: the tensor pipe orders accumulation into the same columns, NOT a TMEM
+          // operand read behind the write of the previous instruction -- wait for PV(h) to retire (back to back, the
+          // out-projection read a partly written O_h: non-deterministic results)
+          mbar_wait_tag(pv_done + r, (it >> 1) & 1, 248);
           tc_fence_after();
-          if (md) md[3] = clock64();
           if (elect_one()) {
             const uint64_t dwo = umma_desc_k128(sWO + r * 16384);
 #pragma unroll
@@ -437,6 +441,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     const uint32_t b_off = is_reg ? (uint32_t)TAB_T169 * 4u : (uint32_t)(bi * TAB_SB + (ai + 6) * TAB_SR) * 4u;
     const uint32_t b_step = is_reg ? 0u : (uint32_t)TAB_SR * 4u;
     uint32_t it = 0, tl = 0;
+    uint32_t my_heads = 0;                                   // heads this CTA processes over all its tiles
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) my_heads += (uint32_t)heads;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       // ---------------- gather + LayerNorm + FiLM -> X tile (fp16, swizzled K-major) ----------------
@@ -505,7 +511,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
         if (dbg) p.dbg[h * 8 + 1] = clock64();
-        mbar_wait_tag(tab_full + r, (it >> 1) & 1, 394);                          // per-head bias table (TMA)
+        if (it == 0) mbar_wait_tag(tab_full + 0, 0, 394);                         // per-head bias table (TMA); later heads: waited for below
         if (dbg) { const long long c2 = clock64(); p.dbg[h * 8 + 2] = c2; p.dbg[h * 8 + 3] = c2; }
 
         // ---------------- S half-row: / |q|, + bias, masked softmax -> normalised P (bf16) ----------------
@@ -554,6 +560,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(tab_free + r);                      // last read of this head's tables
+          // Barriers that completed long ago are polled here, where the thread has independent work in flight, instead of at
+          // the hand-over between heads: the next head's table (loaded two heads ahead) and PV(h-1) (P is single-buffered).
+          if (it + 1 < my_heads) mbar_wait_tag(tab_full + (r ^ 1), ((it + 1) >> 1) & 1, 394);
+          if (it >= 1) mbar_wait_tag(pv_done + (r ^ 1), ((it - 1) >> 1) & 1, 399);
           red[(2 * 128 + t) * 2 + ch] = m;
           pair_sync(lg);
           m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]);
@@ -599,7 +609,6 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           // P row (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same
           // keys of the other window are zero.  PV(h-1) has read the previous P (it was issued a whole softmax ago).
           {
-            if (it >= 1) mbar_wait_tag(pv_done + (r ^ 1), ((it - 1) >> 1) & 1, 399);
             const uint32_t tp = lane_addr + T_P;
             uint32_t pk[16];
 #pragma unroll
