@@ -31,7 +31,7 @@ ops.attn_fused(x, reg, film, wqkv, wout, tab, w, R, False, True, heads, dh)
 torch.cuda.synchronize()
 dall = dbg.cpu().view(2, heads, 8)
 d = dall[0]
-names = ["step2(h+1) (norms, K, V stores)", "wait tables", "-", "wait s_done", "softmax + P", "-", "-"]
+names = ["wait s_done", "S load + s_free", "bias + max (+ hoisted waits)", "pair_sync (max)", "exp2 + sum", "pair_sync (sum) + normalise + pack + P store issue", "wait P store + p_ready"]
 delta = (d[:, 1:] - d[:, :-1]).float()
 print("head period (cycles):", (d[1:, 0] - d[:-1, 0]).float()[2:].mean().item())
 for i, nm in enumerate(names):
@@ -39,7 +39,7 @@ for i, nm in enumerate(names):
 print("  next-head gap           ", (d[1:, 0] - d[:-1, 7]).float()[2:].mean().item())
 
 m = dall[1]
-mn = ["wait WO / WQ (hoisted)", "wait p_ready", "-", "issue PV + out + QKV(h+3)", "wait s_free, qk_ready + issue S(h+2)", "-", "-"]
+mn = ["wait WO / WQ (hoisted)", "wait p_ready", "issue PV", "wait pv_done + issue out", "wait s_free, qk_ready + issue S(h+2)", "issue QKV(h+3)", "-"]
 md = (m[:, 1:] - m[:, :-1]).float()
 print("MMA warp, head period:", (m[1:, 0] - m[:-1, 0]).float()[2:-2].mean().item())
 for i, nm in enumerate(mn):

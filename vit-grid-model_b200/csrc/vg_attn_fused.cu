@@ -3,7 +3,8 @@
 // One persistent CTA processes tiles of TWO windows (2 x 64 token slots = the 128 rows of a tcgen05 M=128 MMA).
 // Nothing between the residual stream in and the residual stream out touches HBM:
 //
-//   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (smem, fp16)
+//   gather (block/grid partition folded into addressing) + register tokens + LayerNorm + FiLM  -> X tile (fp16, in TMEM:
+//                                    the A operand of all 32 QKV projections never touches shared memory)
 //   per head h (weights and the per-head tables streamed by TMA, accumulators re-used as operands in TMEM):
 //     QKV_h = X * Wqkv_h^T           tcgen05 kind::f16 (fp16 operands: the 10-bit mantissa of tf32 at twice the rate and
 //                                    half the shared-memory bytes; X is LayerNorm output, far inside the fp16 range)
@@ -11,8 +12,9 @@
 //     k RMSNorm in registers: K" = k * (32 gq gk) / |k| (tf32) and V^T (bf16) -> smem; q stays in TMEM, 1/|q| per row
 //     S = q K"^T                     tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the q accumulator)
 //     S/|q| + relative-position bias (index computed arithmetically), masked softmax in registers;
-//     P / rowsum (bf16) -> TMEM (tcgen05.st, 64 columns of bf16 pairs; the S accumulator is free for the next head as soon
-//                                    as the softmax warps hold S in registers)
+//     P / rowsum (bf16) -> TMEM (tcgen05.st, 64 columns of bf16 pairs over the q | k columns of the NEXT head's QKV buffer,
+//                                    dead by then; the S accumulator is free for the next head as soon as the softmax warps
+//                                    hold S in registers)
 //     O_h = P V                      tcgen05 kind::f16   M128 N32  K128, A operand = P read from TMEM -> TMEM
 //     Out += O_h * Wout_h^T          tcgen05 kind::tf32  M128 N128 K32, A operand read from TMEM (the O accumulator),
 //                                    accumulated over heads
@@ -35,30 +37,35 @@ constexpr int DH = 32;         // head dim
 constexpr int SLOT = 64;       // token slots per window (S <= 64)
 constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specialised for 7x7 windows + 4 register tokens
 // shared memory map (bytes); every operand tile is 1024-B aligned
-constexpr int X_OFF = 0;                         // fp16: 2 k-blocks x [128 rows x 128 B]
 constexpr int WQ_BYTES = 2 * 12288;              // fp16: 2 k-blocks x [96 rows x 128 B]
-constexpr int WQ_OFF = X_OFF + 2 * 16384;        // 2 buffers (heads alternate)
+constexpr int WQ_OFF = 0;                        // 2 buffers (heads alternate)
 constexpr int WO_OFF = WQ_OFF + 2 * WQ_BYTES;    // tf32 [128 rows x 128 B], 2 buffers
 constexpr int R1_BYTES = 16384;                  // K" operand: tf32 [128 keys x 128 B]
-constexpr int R1_OFF = WO_OFF + 2 * 16384;       // 2 buffers (heads alternate)
-constexpr int VT_OFF = R1_OFF + 2 * R1_BYTES;    // 2 x [2 k-blocks x 32 rows x 128 B]
+// K" / V^T / 1/|q| are written by the staging warps two heads ahead of PV: three buffers (head % 3), so that staging head h+2
+// does not wait for PV(h) to release the buffers of head h
+constexpr int NOPB = 3;
+constexpr int R1_OFF = WO_OFF + 2 * 16384;
+constexpr int VT_OFF = R1_OFF + NOPB * R1_BYTES; // NOPB x [2 k-blocks x 32 rows x 128 B]
 // per-head table: shifted bias rows [bi][row 0..12] (row stride TAB_SR, bi stride TAB_SB floats: with these strides the
 // 16-byte reads of the eight tokens of a quarter-warp fall into different banks, 268 wavefronts per head instead of 588 for
 // the dense [7][13][8] layout) | table[169] x 8 | 32*gq*gk [32] | unused [32]
 constexpr int TAB_SR = 12, TAB_SB = 180, TAB_T169 = 7 * TAB_SB;
 constexpr int TAB_FLOATS = TAB_T169 + 8 + 64;
-constexpr int TAB_OFF = VT_OFF + 2 * 8192;       // 2 x TAB_FLOATS floats
+constexpr int TAB_OFF = VT_OFF + NOPB * 8192;    // 2 x TAB_FLOATS floats
 constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
-constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // 2 x float[128]: 1/|q| per row (staging warps -> softmax warps), double-buffered over heads
-constexpr int BAR_OFF = QINV_OFF + 2 * 512;
+constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // NOPB x float[128]: 1/|q| per row (staging warps -> softmax warps)
+constexpr int BAR_OFF = QINV_OFF + NOPB * 512;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
 constexpr int THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / tile prologue + epilogue, warps 10..17 operand staging (2 threads per token row each)
 // TMEM columns (all 512 in use)
 constexpr int T_QKV0 = 0;      // 96   q | k | v accumulators of even heads
 constexpr int T_QKV1 = 96;     // 96   odd heads
-constexpr int T_OV = 64;       // O_h (32 columns) is written over the v columns of the OTHER head parity's buffer: that buffer is
-                               // dead between the S product of head h+1 and the QKV projection of head h+3
-constexpr int T_P = 192;       // 64   P as bf16 pairs (A operand of PV)
+// The buffer of head h+1 is dead between the S product of head h+1 (issued a head ahead of its softmax) and the QKV projection
+// of head h+3: in that window its q | k columns hold P(h) (64 columns of bf16 pairs, the A operand of PV(h)) and its v columns
+// O_h (the D of PV(h), the A operand of out(h)).
+constexpr int T_PQ = 0;        // P inside the other-parity buffer
+constexpr int T_OV = 64;       // O_h inside the other-parity buffer
+constexpr int T_X = 192;       // 64   X tile: 128 channels as fp16 pairs (A operand of every QKV projection of the tile)
 constexpr int T_S = 256;       // 128
 constexpr int T_OUT = 384;     // 128
 constexpr float LOG2E = 1.4426950408889634f;
@@ -256,7 +263,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       constexpr uint32_t id_s = umma_idesc_tf32(128, 128);
       constexpr uint32_t id_pv = umma_idesc_bf16(128, 32);
       constexpr uint32_t id_out = umma_idesc_tf32(128, 128);
-      const uint32_t sX = smem_u32(smem + X_OFF), sWQ = smem_u32(smem + WQ_OFF), sWO = smem_u32(smem + WO_OFF);
+      const uint32_t sWQ = smem_u32(smem + WQ_OFF), sWO = smem_u32(smem + WO_OFF);
       uint32_t it = 0, tl = 0;                               // global head counter, tile counter
       auto issue_qkv = [&](uint32_t hh) {
         const uint32_t b = hh & 1;
@@ -264,11 +271,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = tmem + (b ? T_QKV1 : T_QKV0);
-          const uint64_t da = umma_desc_k128(sX), db = umma_desc_k128(sWQ + b * WQ_BYTES);
+          const uint64_t db = umma_desc_k128(sWQ + b * WQ_BYTES);
 #pragma unroll
-          for (int st = 0; st < 8; ++st) {
+          for (int st = 0; st < 8; ++st) {                         // A = X from TMEM: 8 columns (16 fp16) per K step
             const int kb = st >> 2, k = st & 3;
-            tc_mma_bf16(d, da + kb * (16384 >> 4) + 2 * k, db + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
+            tc_mma_bf16_ts(d, tmem + T_X + 8 * st, db + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
           }
           tc_commit(qkv_done + b);
           tc_commit(wq_free + b);
@@ -282,14 +289,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           const uint32_t ta = tmem + (r ? T_QKV1 : T_QKV0);
-          const uint64_t db = umma_desc_k128(smem_u32(smem + R1_OFF + r * R1_BYTES));
+          const uint64_t db = umma_desc_k128(smem_u32(smem + R1_OFF + (hh % NOPB) * R1_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tmem + T_S, ta + 8 * k, db + 2 * k, id_s, k ? 1u : 0u);
           tc_commit(s_done);
         }
         __syncwarp();
       };
-      // Issue order per head h:  [p_ready(h)] PV(h), out(h), QKV(h+3)   [s_free(h+1), qk_ready(h+2)] S(h+2)
+      // Issue order per head h:  [p_ready(h)] PV(h)   [pv_done(h)] out(h)   [s_free(h+1), qk_ready(h+2)] S(h+2)   QKV(h+3)
       // The S product runs one head ahead of the softmax (S(h+1) is complete before the softmax of head h ends), the QKV
       // projection three heads ahead: QKV(h+3) re-uses the TMEM buffer of head h+1, whose q columns were read by S(h+1) and
       // whose v columns hold O_h between PV(h) and out(h) (the tensor pipe executes in issue order).
@@ -303,7 +310,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         issue_s(it + 1, false);
         for (int h = 0; h < heads; ++h, ++it) {
           const uint32_t r = it & 1;
-          const uint32_t sVT = smem_u32(smem + VT_OFF + r * 8192);
+          const uint32_t sVT = smem_u32(smem + VT_OFF + (it % NOPB) * 8192);
           long long* md = (p.dbg && blockIdx.x == 0 && tl == 0 && lane == 0) ? p.dbg + (heads + h) * 8 : nullptr;   // MMA-warp time stamps
           if (md) md[0] = clock64();
           const bool do_qkv = h + 3 < heads;
@@ -314,7 +321,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (md) md[1] = clock64();
           mbar_wait_tag(p_ready, it & 1, 236);               // softmax(h) done: P(h) is in TMEM
           tc_fence_after();
-          if (md) { md[2] = clock64(); md[3] = md[2]; }
+          if (md) md[2] = clock64();
           const uint32_t tqn = tmem + (r ? T_QKV0 : T_QKV1);       // buffer of heads h+1 / h+3
           const uint32_t tO = tqn + T_OV;
           if (elect_one()) {
@@ -322,11 +329,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int st = 0; st < 8; ++st) {                       // O = P V  (A = P from TMEM)
               const int kb = st >> 2, k = st & 3;
-              tc_mma_bf16_ts(tO, tmem + T_P + 8 * st, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
+              tc_mma_bf16_ts(tO, tqn + T_PQ + 8 * st, dvt + kb * (4096 >> 4) + 2 * k, id_pv, st ? 1u : 0u);
             }
             tc_commit(pv_done + r);
           }
           __syncwarp();
+          if (md) md[3] = clock64();
           // out(h) reads O_h as its A operand from TMEM: the tensor pipe orders accumulation into the same columns, NOT a TMEM
           // operand read behind the write of the previous instruction -- wait for PV(h) to retire (back to back, the
           // out-projection read a partly written O_h: non-deterministic results)
@@ -337,21 +345,27 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int st = 0; st < 4; ++st) tc_mma_tf32_ts(tmem + T_OUT, tO + 8 * st, dwo + 2 * st, id_out, (h | st) ? 1u : 0u);   // Out += O_h Wout_h^T  (A = O_h read from TMEM)
             tc_commit(wo_free + r);
-            if (do_qkv) {                                          // QKV(h+3) (overwrites O_h: issued after out(h))
-              const uint64_t dxa = umma_desc_k128(sX), dwq = umma_desc_k128(sWQ + (r ^ 1) * WQ_BYTES);
+          }
+          __syncwarp();
+          if (md) md[4] = clock64();
+          // S(h+2) before the long QKV projection: the softmax warps wait for it twice (before P(h+1) is written over the q
+          // columns it reads, and at the start of head h+2)
+          if (h + 2 < heads) issue_s(it + 2, false);
+          if (md) md[5] = clock64();
+          if (elect_one()) {
+            if (do_qkv) {                                          // QKV(h+3) (overwrites P(h), O_h: issued after PV(h), out(h))
+              const uint64_t dwq = umma_desc_k128(sWQ + (r ^ 1) * WQ_BYTES);
 #pragma unroll
               for (int st = 0; st < 8; ++st) {
                 const int kb = st >> 2, k = st & 3;
-                tc_mma_bf16(tqn, dxa + kb * (16384 >> 4) + 2 * k, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
+                tc_mma_bf16_ts(tqn, tmem + T_X + 8 * st, dwq + kb * (12288 >> 4) + 2 * k, id_qkv, st ? 1u : 0u);
               }
               tc_commit(qkv_done + (r ^ 1));
               tc_commit(wq_free + (r ^ 1));
             }
           }
           __syncwarp();
-          if (md) md[4] = clock64();
-          if (h + 2 < heads) issue_s(it + 2, false);
-          if (md) { md[5] = clock64(); md[6] = md[5]; md[7] = md[5]; }
+          if (md) { md[6] = clock64(); md[7] = md[6]; }
         }
         if (elect_one()) tc_commit(tile_done);
         __syncwarp();
@@ -369,8 +383,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int hx = 0; hx < heads; ++hx, ++itx) {
         const uint32_t r = itx & 1;
-        const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
-        const uint32_t VT = s_base + VT_OFF + r * 8192;
+        const uint32_t ob = itx % NOPB;                        // operand buffer of this head
+        const uint32_t R1 = s_base + R1_OFF + ob * R1_BYTES;
+        const uint32_t VT = s_base + VT_OFF + ob * 8192;
         float4 gm[8];                                            // 32 * gamma_q * gamma_k of this head: in flight during the wait
         if (ch == 0) {
           const float4* ksc = reinterpret_cast<const float4*>(p.head_tab + (long long)hx * TAB_FLOATS + TAB_T169 + 8);
@@ -391,8 +406,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           const float nq = (nq4[0] + nq4[1]) + (nq4[2] + nq4[3]), nk = (nk4[0] + nk4[1]) + (nk4[2] + nk4[3]);
           const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);           // F.normalize(eps=1e-12)  (maxvit.py:30)
           const float inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
-          if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 353);    // R1[r], qinv[r] of head itx-2 are no longer in use
-          qinv[r * 128 + t] = inv_q;
+          // K" / 1/|q| of head itx-3 (same buffer) are no longer in use: QKV(itx) was issued behind S(itx-3) and PV(itx-3), so
+          // qkv_done(itx) implies both retired, and the softmax of head itx-3 ended before PV(itx-3) was issued
+          qinv[ob * 128 + t] = inv_q;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             sts128(R1 + sw128(t, c), w[4 * c] * inv_k * gm[c].x, w[4 * c + 1] * inv_k * gm[c].y, w[4 * c + 2] * inv_k * gm[c].z, w[4 * c + 3] * inv_k * gm[c].w);
@@ -401,7 +417,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           float w[32];
           tmem_ld32(tq + 64, w);                                         // v
           tmem_wait_ld();
-          if (itx >= 2) mbar_wait_tag(pv_done + r, ((itx - 2) >> 1) & 1, 354);    // VT[r] no longer read by MMAs
+          // V^T of head itx-3 (same buffer): PV(itx-3) was issued before QKV(itx), so qkv_done(itx) implies it retired
           // V^T (bf16): element (d, key t) of a [32 x 128] K-major tile, 2 k-blocks of 64 keys
           const uint32_t vt = VT + (t >> 6) * 4096 + (t & 7) * 2;
           const int kc = (t & 63) >> 3;
@@ -484,23 +500,23 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         pair_sync(lg);
         const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
         const float* film = p.film + (long long)n * 2 * C + ch * 64;
-        // fp16 operand tile: this thread's 64 channels are the 128-byte row of k-block `ch`
+        // fp16 operand tile in TMEM: this thread's 64 channels are columns [ch*32, +32) of its lane (two channels per column)
+        uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t pk[4] = {0u, 0u, 0u, 0u};
+        for (int c = 0; c < 16; ++c) {
+          pk[2 * c] = 0u; pk[2 * c + 1] = 0u;
           if (src) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float4 xv = v[2 * c + e];
-              const float4 ga = *reinterpret_cast<const float4*>(film + (2 * c + e) * 4), be = *reinterpret_cast<const float4*>(film + C + (2 * c + e) * 4);
-              pk[2 * e] = pack_f16(xv.x * rstd * ga.x + be.x, xv.y * rstd * ga.y + be.y);
-              pk[2 * e + 1] = pack_f16(xv.z * rstd * ga.z + be.z, xv.w * rstd * ga.w + be.w);
-            }
+            const float4 xv = v[c];
+            const float4 ga = *reinterpret_cast<const float4*>(film + c * 4), be = *reinterpret_cast<const float4*>(film + C + c * 4);
+            pk[2 * c] = pack_f16(xv.x * rstd * ga.x + be.x, xv.y * rstd * ga.y + be.y);
+            pk[2 * c + 1] = pack_f16(xv.z * rstd * ga.z + be.z, xv.w * rstd * ga.w + be.w);
           }
-          sts128u(s_base + X_OFF + ch * 16384 + swz[c], pk[0], pk[1], pk[2], pk[3]);
         }
+        tmem_st16(lane_addr + T_X + ch * 32, pk);
+        tmem_st16(lane_addr + T_X + ch * 32 + 16, pk + 16);
+        tmem_wait_st();
       }
-      fence_async_smem();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(x_ready);
 
@@ -508,16 +524,13 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
         if (dbg) p.dbg[h * 8 + 0] = clock64();
         const uint32_t r = it & 1;
-        const uint32_t R1 = s_base + R1_OFF + r * R1_BYTES;
         const uint32_t tab = s_base + TAB_OFF + r * TAB_FLOATS * 4;
-        if (dbg) p.dbg[h * 8 + 1] = clock64();
         if (it == 0) mbar_wait_tag(tab_full + 0, 0, 394);                         // per-head bias table (TMA); later heads: waited for below
-        if (dbg) { const long long c2 = clock64(); p.dbg[h * 8 + 2] = c2; p.dbg[h * 8 + 3] = c2; }
 
         // ---------------- S half-row: / |q|, + bias, masked softmax -> normalised P (bf16) ----------------
         mbar_wait_tag(s_done, it & 1, 398);
         tc_fence_after();
-        if (dbg) p.dbg[h * 8 + 4] = clock64();
+        if (dbg) p.dbg[h * 8 + 1] = clock64();
         {
           float2 sc2[16];
           float* sc = reinterpret_cast<float*>(sc2);
@@ -526,8 +539,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free);                            // S(h+1) may now overwrite the accumulator
+          if (dbg) p.dbg[h * 8 + 2] = clock64();
           // logits in the exp2 domain: S * (log2e / |q|) + bias * log2e (the table is stored pre-multiplied)
-          const float cq = qinv[r * 128 + t] * LOG2E;                    // written by the staging warps before qk_ready -> S -> s_done
+          const float cq = qinv[(it % NOPB) * 128 + t] * LOG2E;                    // written by the staging warps before qk_ready -> S -> s_done
           const uint32_t brow = tab + b_off;                             // register-token rows read the constant row (b_step = 0)
           float m = -INFINITY;
           if (ch == 0) {
@@ -561,11 +575,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(tab_free + r);                      // last read of this head's tables
           // Barriers that completed long ago are polled here, where the thread has independent work in flight, instead of at
-          // the hand-over between heads: the next head's table (loaded two heads ahead) and PV(h-1) (P is single-buffered).
+          // the hand-over between heads: the next head's table (loaded two heads ahead).
           if (it + 1 < my_heads) mbar_wait_tag(tab_full + (r ^ 1), ((it + 1) >> 1) & 1, 394);
-          if (it >= 1) mbar_wait_tag(pv_done + (r ^ 1), ((it - 1) >> 1) & 1, 399);
           red[(2 * 128 + t) * 2 + ch] = m;
+          if (dbg) p.dbg[h * 8 + 3] = clock64();
           pair_sync(lg);
+          if (dbg) p.dbg[h * 8 + 4] = clock64();
           m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]);
           const float2 nm = make_float2(-m, -m);
           float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
@@ -590,6 +605,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           }
           acc0 = fadd2(acc0, acc1);
           red[(0 * 128 + t) * 2 + ch] = acc0.x + acc0.y;
+          // P(h) goes over the q | k columns of head h+1's buffer: S(h+1), which reads that q, was issued when this softmax
+          // released the S accumulator (s_free) and has long retired
+          if (h + 1 < heads) mbar_wait_tag(s_done, (it + 1) & 1, 399);
+          if (dbg) p.dbg[h * 8 + 5] = clock64();
           pair_sync(lg);                                                 // partner's partial row sum is visible
           const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
           if (p.drop.thresh) {                                           // nn.Dropout on the probabilities (maxvit.py:146, 209)
@@ -607,9 +626,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             for (int k = 0; k < 16; ++k) sc2[k] = fmul2(sc2[k], is2);
           }
           // P row (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same
-          // keys of the other window are zero.  PV(h-1) has read the previous P (it was issued a whole softmax ago).
+          // keys of the other window are zero.
           {
-            const uint32_t tp = lane_addr + T_P;
+            const uint32_t tp = lane_addr + (r ? T_QKV0 : T_QKV1) + T_PQ;
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(sc[2 * c], sc[2 * c + 1]);
@@ -617,13 +636,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 #pragma unroll
             for (int c = 0; c < 16; ++c) pk[c] = 0u;
             tmem_st16(tp + (half ^ 1) * 32 + ch * 16, pk);
+            if (dbg) p.dbg[h * 8 + 6] = clock64();
             tmem_wait_st();
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        if (dbg) { const long long c5 = clock64(); p.dbg[h * 8 + 5] = c5; p.dbg[h * 8 + 6] = c5; p.dbg[h * 8 + 7] = c5; }
+        if (dbg) p.dbg[h * 8 + 7] = clock64();
       }
 
       // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------
