@@ -56,7 +56,10 @@ constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pa
 constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // NOPB x float[128]: 1/|q| per row (staging warps -> softmax warps)
 constexpr int BAR_OFF = QINV_OFF + NOPB * 512;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
-constexpr int THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / tile prologue + epilogue, warps 10..17 operand staging (2 threads per token row each)
+// warp 0 TMA, warp 1 MMA, warps 2..9 softmax, warps 10..17 operand staging + tile prologue / epilogue (2 threads per token row
+// each).  (A warpgroup-aligned 640-thread layout with setmaxnreg was tried: ptxas kept every role within the launch-time 96
+// registers, so it only added spills.)
+constexpr int THREADS = 576;
 // TMEM columns (all 512 in use)
 constexpr int T_QKV0 = 0;      // 96   q | k | v accumulators of even heads
 constexpr int T_QKV1 = 96;     // 96   odd heads
@@ -166,6 +169,35 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 // named barriers: 1 = all 256 compute threads, 2..5 = the two warps that share a TMEM lane group
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void pair_sync(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory"); }
+
+// residual-stream row of tile row t (= token slot i of window `half` of the tile): block / grid partition and the register
+// tokens folded into the address (maxvit.py:298 / :322 / :305)
+struct TokRow { const float* src; long long pix; long long wdx; int n; };
+__device__ __forceinline__ TokRow tok_row(const FusedAttnParams& p, long long tile, int t) {
+  using namespace fa;
+  const int half = t >> 6, i = t & 63;
+  const AttnGeom& g = p.g;
+  const int nwin = g.nwin();
+  TokRow r;
+  r.wdx = tile * 2 + half;
+  const bool win_valid = r.wdx < p.n_windows;
+  r.n = win_valid ? (int)(r.wdx / nwin) : 0;
+  const int wi = win_valid ? (int)(r.wdx - (long long)r.n * nwin) : 0;
+  r.src = nullptr; r.pix = -1;
+  if (win_valid && i < SEQ) {
+    if (i < REG) r.src = p.reg_in + (p.reg_per_field ? (long long)r.n * REG * C : 0) + (long long)i * C;
+    else {
+      const int ti = i - REG, ai = ti / WIN, bi = ti - ai * WIN;
+      const int xw = wi / g.Y, yw = wi - xw * g.Y;
+      const int ph = g.grid_mode ? ai * g.X + xw : xw * WIN + ai;     // maxvit.py:322 / :298
+      const int pw = g.grid_mode ? bi * g.Y + yw : yw * WIN + bi;
+      r.pix = (long long)r.n * g.Hl * g.Wl + (long long)ph * g.Wl + pw;
+      r.src = p.x + r.pix * C;
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ void pair_sync2(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(6 + lg) : "memory"); }   // staging-warp pairs
 
 __global__ void __launch_bounds__(fa::THREADS, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_constant__ CUtensorMap mapWo,
@@ -379,9 +411,101 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
     const uint32_t s_base = smem_u32(smem);
     float* qinv = reinterpret_cast<float*>(smem + QINV_OFF);
-    uint32_t itx = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    float* red = reinterpret_cast<float*>(smem + RED_OFF);   // arrays 1 (LN sum) and 3 (LN sq-sum) belong to these warps
+    // ---------------- tile prologue: gather + LayerNorm + FiLM -> X tile (fp16, TMEM).  Run here, by the warps that have slack:
+    // the X tile of the NEXT tile is built while the softmax warps are still on the last heads of this one (every QKV
+    // projection of this tile has retired once its last head is staged). ----------------
+    auto build_x = [&](long long tile) {
+      const TokRow tr = tok_row(p, tile, t);
+      const float* src = tr.src;
+      // this thread owns channels [ch*64, +64) of the row; the row statistics are exchanged within the pair
+      float4 v[16];
+      float sm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        v[c] = src ? *reinterpret_cast<const float4*>(src + ch * 64 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sm += v[c].x + v[c].y + v[c].z + v[c].w;
+      }
+      red[(1 * 128 + t) * 2 + ch] = sm;
+      pair_sync2(lg);
+      const float mean = (red[(1 * 128 + t) * 2] + red[(1 * 128 + t) * 2 + 1]) * (1.0f / C);
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+        ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
+      }
+      red[(3 * 128 + t) * 2 + ch] = ss;
+      pair_sync2(lg);
+      const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
+      const float* film = p.film + (long long)tr.n * 2 * C + ch * 64;
+      // fp16 operand tile in TMEM: this thread's 64 channels are columns [ch*32, +32) of its lane (two channels per column)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          pk[2 * c] = 0u; pk[2 * c + 1] = 0u;
+          if (src) {
+            const float4 xv = v[hf * 8 + c];
+            const float4 ga = *reinterpret_cast<const float4*>(film + (hf * 8 + c) * 4), be = *reinterpret_cast<const float4*>(film + C + (hf * 8 + c) * 4);
+            pk[2 * c] = pack_f16(xv.x * rstd * ga.x + be.x, xv.y * rstd * ga.y + be.y);
+            pk[2 * c + 1] = pack_f16(xv.z * rstd * ga.z + be.z, xv.w * rstd * ga.w + be.w);
+          }
+        }
+        tmem_st16(lane_addr + T_X + ch * 32 + hf * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_ready);
+    };
+    // ---------------- tile epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)).  Also run here: the
+    // softmax warps go straight on to the next tile's heads. ----------------
+    auto epilogue = [&](long long tile, uint32_t tl) {
+      const TokRow tr = tok_row(p, tile, t);
+      const int i = t & 63;
+      mbar_wait_tag(tile_done, tl & 1, 472);
+      tc_fence_after();
+      float* dst = nullptr;
+      if (tr.src) {
+        if (i < REG) dst = p.reg_out ? p.reg_out + (tr.wdx * REG + i) * C : nullptr;
+        else dst = p.x_out + tr.pix * C;
+      }
+      float v[32];
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const int c0 = ch * 64 + q * 32;
+        tmem_ld32(lane_addr + T_OUT + c0, v); tmem_wait_ld();
+        if (p.drop.thresh) {                                           // nn.Dropout after to_out (maxvit.py:151)
+          const uint32_t rid = drop_row(tr.wdx, i);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const uint32_t hsh = drop_hash(p.drop.seed, rid, drop_group_out(p.drop.salt, (c0 + c) >> 2));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? p.drop.scale : 0.f;
+          }
+        }
+        if (dst) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(tr.src + c0 + c));
+            *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(v[c] + rr.x, v[c + 1] + rr.y, v[c + 2] + rr.z, v[c + 3] + rr.w);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_free);
+    };
+    uint32_t itx = 0, tl = 0;
+    long long ep_tile = -1;                                  // tile whose epilogue is pending
+    if ((long long)blockIdx.x < n_tiles) build_x(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       for (int hx = 0; hx < heads; ++hx, ++itx) {
+        // the previous tile's epilogue runs once the first three heads of this tile are staged (the MMA warp issued their QKV
+        // projections together; the fourth follows a softmax later): the pipeline refill never waits for it
+        if (hx == 3 && ep_tile >= 0) { epilogue(ep_tile, tl - 1); ep_tile = -1; }
         const uint32_t r = itx & 1;
         const uint32_t ob = itx % NOPB;                        // operand buffer of this head
         const uint32_t R1 = s_base + R1_OFF + ob * R1_BYTES;
@@ -429,7 +553,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(qk_ready + r);
       }
+      // the last head of this tile is staged: every QKV projection that reads the X tile has retired
+      if (tile + gridDim.x < n_tiles) { tc_fence_after(); build_x(tile + gridDim.x); }
+      ep_tile = tile;
     }
+    if (ep_tile >= 0) epilogue(ep_tile, tl - 1);
   } else {
     // ============================== softmax warps: two threads per token row ==============================
     const int cw = warp - 2;                                 // 0..7
@@ -461,64 +589,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) my_heads += (uint32_t)heads;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      // ---------------- gather + LayerNorm + FiLM -> X tile (fp16, swizzled K-major) ----------------
-      const long long wdx = tile * 2 + half;
-      const bool win_valid = wdx < p.n_windows;
-      const int n = win_valid ? (int)(wdx / nwin) : 0;
-      const int wi = win_valid ? (int)(wdx - (long long)n * nwin) : 0;
-      const float* src = nullptr;                           // residual-stream row of this token
-      long long pix = -1;
-      if (win_valid && tok_valid) {
-        if (is_reg) src = p.reg_in + (p.reg_per_field ? (long long)n * REG * C : 0) + (long long)i * C;
-        else {
-          const int xw = wi / g.Y, yw = wi - xw * g.Y;
-          const int ph = g.grid_mode ? ai * g.X + xw : xw * WIN + ai;     // maxvit.py:322 / :298
-          const int pw = g.grid_mode ? bi * g.Y + yw : yw * WIN + bi;
-          pix = (long long)n * g.Hl * g.Wl + (long long)ph * g.Wl + pw;
-          src = p.x + pix * C;
-        }
-      }
-      {
-        // this thread owns channels [ch*64, +64) of the row; the row statistics are exchanged within the pair
-        float4 v[16];
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          v[c] = src ? *reinterpret_cast<const float4*>(src + ch * 64 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          s += v[c].x + v[c].y + v[c].z + v[c].w;
-        }
-        red[(1 * 128 + t) * 2 + ch] = s;
-        pair_sync(lg);
-        const float mean = (red[(1 * 128 + t) * 2] + red[(1 * 128 + t) * 2 + 1]) * (1.0f / C);
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
-          ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
-        }
-        red[(3 * 128 + t) * 2 + ch] = ss;
-        pair_sync(lg);
-        const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
-        const float* film = p.film + (long long)n * 2 * C + ch * 64;
-        // fp16 operand tile in TMEM: this thread's 64 channels are columns [ch*32, +32) of its lane (two channels per column)
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          pk[2 * c] = 0u; pk[2 * c + 1] = 0u;
-          if (src) {
-            const float4 xv = v[c];
-            const float4 ga = *reinterpret_cast<const float4*>(film + c * 4), be = *reinterpret_cast<const float4*>(film + C + c * 4);
-            pk[2 * c] = pack_f16(xv.x * rstd * ga.x + be.x, xv.y * rstd * ga.y + be.y);
-            pk[2 * c + 1] = pack_f16(xv.z * rstd * ga.z + be.z, xv.w * rstd * ga.w + be.w);
-          }
-        }
-        tmem_st16(lane_addr + T_X + ch * 32, pk);
-        tmem_st16(lane_addr + T_X + ch * 32 + 16, pk + 16);
-        tmem_wait_st();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_ready);
+      // (the X tile of this tile is built by the staging warps)
+      const TokRow tr = tok_row(p, tile, t);
+      const float* src = tr.src;                             // residual-stream row of this token
+      const long long pix = tr.pix, wdx = tr.wdx;
 
       for (int h = 0; h < heads; ++h, ++it) {
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
@@ -646,41 +720,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         if (dbg) p.dbg[h * 8 + 7] = clock64();
       }
 
-      // ---------------- epilogue: Out + residual, inverse partition (this thread: channels [ch*64, +64)) ----------------
-      mbar_wait_tag(tile_done, tl & 1, 472);
-      tc_fence_after();
-      {
-        float* dst = nullptr;
-        if (src) {
-          if (is_reg) dst = p.reg_out ? p.reg_out + (wdx * REG + i) * C : nullptr;
-          else dst = p.x_out + pix * C;
-        }
-        float v[32];
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          const int c0 = ch * 64 + q * 32;
-          tmem_ld32(lane_addr + T_OUT + c0, v); tmem_wait_ld();
-          if (p.drop.thresh) {                                           // nn.Dropout after to_out (maxvit.py:151)
-            const uint32_t rid = drop_row(wdx, i);
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const uint32_t hsh = drop_hash(p.drop.seed, rid, drop_group_out(p.drop.salt, (c0 + c) >> 2));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) v[c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? p.drop.scale : 0.f;
-            }
-          }
-          if (dst) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 rr = *reinterpret_cast<const float4*>(src + c0 + c);
-              *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(v[c] + rr.x, v[c + 1] + rr.y, v[c + 2] + rr.z, v[c + 3] + rr.w);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(out_free);
+      // (the epilogue of this tile is run by the staging warps)
     }
   }
   tc_fence_before();
