@@ -52,8 +52,8 @@ constexpr int VT_OFF = R1_OFF + NOPB * R1_BYTES; // NOPB x [2 k-blocks x 32 rows
 constexpr int TAB_SR = 12, TAB_SB = 180, TAB_T169 = 7 * TAB_SB;
 constexpr int TAB_FLOATS = TAB_T169 + 8 + 64;
 constexpr int TAB_OFF = VT_OFF + NOPB * 8192;    // 2 x TAB_FLOATS floats
-constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // 4 x float[128][2] pair-exchange buffers
-constexpr int QINV_OFF = RED_OFF + 4 * 1024;             // NOPB x float[128]: 1/|q| per row (staging warps -> softmax warps)
+constexpr int RED_OFF = TAB_OFF + 2 * TAB_FLOATS * 4;    // softmax pair exchange: 2 (head parity) x float[128][2][2] (max, sum); then LN sum / sq-sum float[128][2] each
+constexpr int QINV_OFF = RED_OFF + 6 * 1024;             // NOPB x float[128]: 1/|q| per row (staging warps -> softmax warps)
 constexpr int BAR_OFF = QINV_OFF + NOPB * 512;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;          // + barriers + alignment slack
 // warp 0 TMA, warp 1 MMA, warps 2..9 softmax, warps 10..17 operand staging + tile prologue / epilogue (2 threads per token row
@@ -411,7 +411,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
     const uint32_t s_base = smem_u32(smem);
     float* qinv = reinterpret_cast<float*>(smem + QINV_OFF);
-    float* red = reinterpret_cast<float*>(smem + RED_OFF);   // arrays 1 (LN sum) and 3 (LN sq-sum) belong to these warps
+    float* lnred = reinterpret_cast<float*>(smem + RED_OFF) + 1024;   // LN sum [128][2] | LN sq-sum [128][2], behind the softmax exchange buffers
     // ---------------- tile prologue: gather + LayerNorm + FiLM -> X tile (fp16, TMEM).  Run here, by the warps that have slack:
     // the X tile of the NEXT tile is built while the softmax warps are still on the last heads of this one (every QKV
     // projection of this tile has retired once its last head is staged). ----------------
@@ -426,18 +426,18 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         v[c] = src ? *reinterpret_cast<const float4*>(src + ch * 64 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         sm += v[c].x + v[c].y + v[c].z + v[c].w;
       }
-      red[(1 * 128 + t) * 2 + ch] = sm;
+      lnred[t * 2 + ch] = sm;
       pair_sync2(lg);
-      const float mean = (red[(1 * 128 + t) * 2] + red[(1 * 128 + t) * 2 + 1]) * (1.0f / C);
+      const float mean = (lnred[t * 2] + lnred[t * 2 + 1]) * (1.0f / C);
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
         ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
       }
-      red[(3 * 128 + t) * 2 + ch] = ss;
+      lnred[256 + t * 2 + ch] = ss;
       pair_sync2(lg);
-      const float rstd = rsqrtf((red[(3 * 128 + t) * 2] + red[(3 * 128 + t) * 2 + 1]) * (1.0f / C) + p.ln_eps);
+      const float rstd = rsqrtf((lnred[256 + t * 2] + lnred[256 + t * 2 + 1]) * (1.0f / C) + p.ln_eps);
       const float* film = p.film + (long long)tr.n * 2 * C + ch * 64;
       // fp16 operand tile in TMEM: this thread's 64 channels are columns [ch*32, +32) of its lane (two channels per column)
 #pragma unroll
@@ -578,7 +578,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     uint32_t swz[8];                                         // swizzled chunk offsets of this thread's tile row
 #pragma unroll
     for (int c = 0; c < 8; ++c) swz[c] = sw128(t, c);
-    float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [4][128][2]: 0 softmax sum, 1 LN sum, 2 softmax max, 3 LN sq-sum
+    float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [2 head parities][128 rows][2 threads] x (max, sum)
     const float* qinv = reinterpret_cast<const float*>(smem + QINV_OFF);
     // bias rows of this token: window tokens step one 32-byte row back per key row aj; register-token rows (maxvit.py:167:
     // one shared bias for every key) read the constant row, with step 0 -- no per-element select
@@ -651,11 +651,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           // Barriers that completed long ago are polled here, where the thread has independent work in flight, instead of at
           // the hand-over between heads: the next head's table (loaded two heads ahead).
           if (it + 1 < my_heads) mbar_wait_tag(tab_full + (r ^ 1), ((it + 1) >> 1) & 1, 394);
-          red[(2 * 128 + t) * 2 + ch] = m;
-          if (dbg) p.dbg[h * 8 + 3] = clock64();
-          pair_sync(lg);
-          if (dbg) p.dbg[h * 8 + 4] = clock64();
-          m = fmaxf(red[(2 * 128 + t) * 2], red[(2 * 128 + t) * 2 + 1]);
+          // ONE exchange per head: every thread exponentiates against the maximum of its OWN half row; the pair then swaps
+          // (max, sum) and rescales by 2^(own max - row max) together with the normalisation (the same softmax, exactly)
+          if (dbg) { p.dbg[h * 8 + 3] = clock64(); p.dbg[h * 8 + 4] = p.dbg[h * 8 + 3]; }
           const float2 nm = make_float2(-m, -m);
           float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
           if (ch == 0) {
@@ -678,13 +676,17 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
             for (int k = 11; k < 16; ++k) sc2[k] = make_float2(0.f, 0.f);
           }
           acc0 = fadd2(acc0, acc1);
-          red[(0 * 128 + t) * 2 + ch] = acc0.x + acc0.y;
+          const float s_own = acc0.x + acc0.y;
+          *reinterpret_cast<float2*>(red + (r * 128 + t) * 4 + ch * 2) = make_float2(m, s_own);
           // P(h) goes over the q | k columns of head h+1's buffer: S(h+1), which reads that q, was issued when this softmax
           // released the S accumulator (s_free) and has long retired
           if (h + 1 < heads) mbar_wait_tag(s_done, (it + 1) & 1, 399);
           if (dbg) p.dbg[h * 8 + 5] = clock64();
-          pair_sync(lg);                                                 // partner's partial row sum is visible
-          const float inv_sum = 1.0f / (red[(0 * 128 + t) * 2] + red[(0 * 128 + t) * 2 + 1]);
+          pair_sync(lg);                                                 // partner's (max, sum) is visible
+          const float2 oth = *reinterpret_cast<const float2*>(red + (r * 128 + t) * 4 + (ch ^ 1) * 2);
+          const float mrow = fmaxf(m, oth.x);
+          const float f_own = ex2(m - mrow), f_oth = ex2(oth.x - mrow);
+          const float inv_sum = f_own / fmaf(s_own, f_own, oth.y * f_oth);
           if (p.drop.thresh) {                                           // nn.Dropout on the probabilities (maxvit.py:146, 209)
             const float ks = inv_sum * p.drop.scale;
             const uint32_t rid = drop_row(wdx, i);
