@@ -295,6 +295,32 @@ def test_attention_fused(grid_mode, N, H, W):
     assert rel_err(reg_out, ref[:, :R]) < 4e-3
 
 
+@pytest.mark.parametrize("grid_mode", [False, True])
+@pytest.mark.parametrize("drop", [(0, 0, 0), (1234, 3, 26)])
+def test_attention_fused_is_deterministic(grid_mode, drop):
+    """race detector: the fused kernel hands operands between four warp roles through TMEM / shared memory (P, X and O_h are
+    TMEM operands, S runs a head ahead); every repeat on the same input must be bit-identical -- a missing wait (e.g. the
+    out-projection reading O_h before PV retired) shows up as differing repeats.  24 fields: several tiles per CTA."""
+    o = ops()
+    N, H, W, C, heads, dh, w, R = 24, 42, 35, 128, 32, 32, 7, 4
+    x = rnd(N, H, W, C, seed=11).cuda()
+    reg = (rnd(N, R, C, seed=12) if grid_mode else rnd(R, C, seed=12)).cuda()
+    film = rnd(N, 2 * C, seed=13).cuda()
+    wqkv = (rnd(heads * 96, C, seed=14) / 11.3).cuda()
+    wout = (rnd(heads, C, dh, seed=15) / 32).cuda()
+    qg, kg = (0.5 + torch.rand(heads * dh)).cuda(), (0.5 + torch.rand(heads * dh)).cuda()
+    tab = o.pack_head_tables(rnd(170, heads, seed=16).cuda(), qg, kg)
+    ref = None
+    for _ in range(6):
+        y, r = o.attn_fused(x, reg, film, wqkv, wout, tab, w, R, grid_mode, True, heads, dh, drop=drop)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (y.clone(), r.clone())
+        else:
+            assert torch.equal(y, ref[0]) and torch.equal(r, ref[1])
+    assert torch.isfinite(ref[0]).all()
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 6e-3), ("bf16_all", 3e-2)])
 def test_maxvit_module(precision, tol):
     """MaxViT nn.Module (reference API) vs oracle, depth 2 (second MBConv is residual)"""
