@@ -199,6 +199,9 @@ __device__ __forceinline__ TokRow tok_row(const FusedAttnParams& p, long long ti
 }
 __device__ __forceinline__ void pair_sync2(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(6 + lg) : "memory"); }   // staging-warp pairs
 
+// DROP: training instantiation with the dropout code; the inference instantiation is a quarter smaller (the kernel's cold paths
+// -- tile prologue / epilogue -- run from an instruction cache shared with four hot role loops)
+template <bool DROP>
 __global__ void __launch_bounds__(fa::THREADS, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_constant__ CUtensorMap mapWo,
                   const FusedAttnParams p) {
@@ -477,7 +480,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
       for (int q = 0; q < 2; ++q) {
         const int c0 = ch * 64 + q * 32;
         tmem_ld32(lane_addr + T_OUT + c0, v); tmem_wait_ld();
-        if (p.drop.thresh) {                                           // nn.Dropout after to_out (maxvit.py:151)
+        if (DROP && p.drop.thresh) {                                   // nn.Dropout after to_out (maxvit.py:151)
           const uint32_t rid = drop_row(tr.wdx, i);
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
@@ -687,7 +690,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           const float mrow = fmaxf(m, oth.x);
           const float f_own = ex2(m - mrow), f_oth = ex2(oth.x - mrow);
           const float inv_sum = f_own / fmaf(s_own, f_own, oth.y * f_oth);
-          if (p.drop.thresh) {                                           // nn.Dropout on the probabilities (maxvit.py:146, 209)
+          if (DROP && p.drop.thresh) {                                   // nn.Dropout on the probabilities (maxvit.py:146, 209)
             const float ks = inv_sum * p.drop.scale;
             const uint32_t rid = drop_row(wdx, i);
 #pragma unroll
@@ -779,7 +782,8 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   if (const char* e = getenv("VG_ATTN_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("attn_fused smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -788,7 +792,8 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (p.n_windows + 1) / 2;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  attn_fused_kernel<<<grid, fa::THREADS, fa::SMEM_BYTES, st>>>(mq, mo, p);
+  if (drop_thresh) attn_fused_kernel<true><<<grid, fa::THREADS, fa::SMEM_BYTES, st>>>(mq, mo, p);
+  else attn_fused_kernel<false><<<grid, fa::THREADS, fa::SMEM_BYTES, st>>>(mq, mo, p);
   return check_launch("attn_fused_kernel");
 }
 
