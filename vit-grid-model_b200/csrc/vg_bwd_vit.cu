@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(128, 3) dwconv_march_kernel(const T* __restric
           a.x = fmaf(t2.x, k2.x, a.x); a.y = fmaf(t2.y, k2.y, a.y); a.z = fmaf(t2.z, k2.z, a.z); a.w = fmaf(t2.w, k2.w, a.w);
         }
         a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
-        if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+        if (act == 1) {
+          const float2 g0 = gelu_erf2(make_float2(a.x, a.y)), g1 = gelu_erf2(make_float2(a.z, a.w));
+          a.x = g0.x; a.y = g0.y; a.z = g1.x; a.w = g1.y;
+        }
         Ld4<T>::st(obase + ((long long)h * W + w0 + j) * C, a);
         acc_sum.x += a.x; acc_sum.y += a.y; acc_sum.z += a.z; acc_sum.w += a.w;
       }

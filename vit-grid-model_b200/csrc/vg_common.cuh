@@ -93,6 +93,41 @@ __device__ __forceinline__ float erf_as(float x) {
   p *= t;
   return copysignf(fmaf(-p, __expf(-ax * ax), 1.0f), x);
 }
+// Two GELUs at once with packed fp32 pairs (FMUL2 / FFMA2 / FADD2 on sm_100: half the issue slots of the polynomial; the two MUFU
+// ops per element stay).  Same A&S 7.1.26 arithmetic as erf_as, evaluated as 0.5 x (1 + sign(x) (1 - p(t) e^{-x^2/2})).
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+#ifdef VG_EXACT_ERFF
+  return make_float2(0.5f * x.x * (1.0f + erff(x.x * 0.70710678118654752440f)), 0.5f * x.y * (1.0f + erff(x.y * 0.70710678118654752440f)));
+#else
+  const float2 z = f2_mul(x, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = f2_fma(make_float2(0.3275911f, 0.3275911f), az, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 pp = f2_fma(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  pp = f2_fma(pp, t, make_float2(1.421413741f, 1.421413741f));
+  pp = f2_fma(pp, t, make_float2(-0.284496736f, -0.284496736f));
+  pp = f2_fma(pp, t, make_float2(0.254829592f, 0.254829592f));
+  pp = f2_mul(pp, t);
+  const float2 nz2 = f2_mul(az, make_float2(-az.x, -az.y));                 // -z^2
+  const float2 e = make_float2(__expf(nz2.x), __expf(nz2.y));
+  const float2 one_m = f2_fma(make_float2(-pp.x, -pp.y), e, make_float2(1.0f, 1.0f));     // erf(|z|)
+  const float2 er = make_float2(copysignf(one_m.x, z.x), copysignf(one_m.y, z.y));
+  const float2 hx = f2_mul(x, make_float2(0.5f, 0.5f));
+  return f2_fma(hx, er, hx);                                                // 0.5 x (1 + erf)
+#endif
+}
 #ifdef VG_EXACT_ERFF
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 #else

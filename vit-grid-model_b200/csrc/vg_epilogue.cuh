@@ -128,7 +128,10 @@ __device__ __forceinline__ void epi_store_coalesced(const EpiParams& ep, long lo
         const long long row = row0 + r;
         const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS_ + cq);
         float o[4] = {fmaf(a4.x, sc.x, sh.x), fmaf(a4.y, sc.y, sh.y), fmaf(a4.z, sc.z, sh.z), fmaf(a4.w, sc.w, sh.w)};
-        if (ep.act == 1) { o[0] = gelu_erf(o[0]); o[1] = gelu_erf(o[1]); o[2] = gelu_erf(o[2]); o[3] = gelu_erf(o[3]); }
+        if (ep.act == 1) {
+          const float2 g0 = gelu_erf2(make_float2(o[0], o[1])), g1 = gelu_erf2(make_float2(o[2], o[3]));
+          o[0] = g0.x; o[1] = g0.y; o[2] = g1.x; o[3] = g1.y;
+        }
         else if (ep.act == 2) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
         if (ep.res) {
           if (ep.res_f32 || sizeof(T) == 4) {

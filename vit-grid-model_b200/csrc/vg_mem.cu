@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] = gelu_erf(a[j] * sc[j] + sh[j]); }
+      for (int j = 0; j < 8; j += 2) {
+        const float2 g = gelu_erf2(f2_fma(make_float2(a[j], a[j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1])));
+        a[j] = g.x; a[j + 1] = g.y;
+      }
       st8(out + (((long long)n * H + h) * W + w) * C + c8, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc_sum[j] += a[j];               // SE mean over the fp32 values
