@@ -121,18 +121,31 @@ __device__ __forceinline__ void epi_store_coalesced(const EpiParams& ep, long lo
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * LDS_ + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     __syncwarp();
+    // activation first, for all eight row groups at once and without branches: the GELU is a chain of ~20 dependent operations
+    // and two MUFU round trips per element, and only two epilogue warps share a scheduler -- eight independent chains per
+    // thread hide it (with the row-validity branch around each group the compiler kept the groups serial)
+    float o8[8][4];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float4 a4 = *reinterpret_cast<const float4*>(stg + (it * 4 + rr) * LDS_ + cq);
+      o8[it][0] = fmaf(a4.x, sc.x, sh.x); o8[it][1] = fmaf(a4.y, sc.y, sh.y); o8[it][2] = fmaf(a4.z, sc.z, sh.z); o8[it][3] = fmaf(a4.w, sc.w, sh.w);
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float2 g0 = gelu_erf2(make_float2(o8[it][0], o8[it][1])), g1 = gelu_erf2(make_float2(o8[it][2], o8[it][3]));
+        o8[it][0] = g0.x; o8[it][1] = g0.y; o8[it][2] = g1.x; o8[it][3] = g1.y;
+      }
+    } else if (ep.act == 2) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { o8[it][0] = fmaxf(o8[it][0], 0.f); o8[it][1] = fmaxf(o8[it][1], 0.f); o8[it][2] = fmaxf(o8[it][2], 0.f); o8[it][3] = fmaxf(o8[it][3], 0.f); }
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + rr;
       if (r < nvalid) {
         const long long row = row0 + r;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS_ + cq);
-        float o[4] = {fmaf(a4.x, sc.x, sh.x), fmaf(a4.y, sc.y, sh.y), fmaf(a4.z, sc.z, sh.z), fmaf(a4.w, sc.w, sh.w)};
-        if (ep.act == 1) {
-          const float2 g0 = gelu_erf2(make_float2(o[0], o[1])), g1 = gelu_erf2(make_float2(o[2], o[3]));
-          o[0] = g0.x; o[1] = g0.y; o[2] = g1.x; o[3] = g1.y;
-        }
-        else if (ep.act == 2) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        float* o = o8[it];
         if (ep.res) {
           if (ep.res_f32 || sizeof(T) == 4) {
             const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res) + row * ep.ldres + c0 + cq);
