@@ -73,36 +73,48 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
 // every 32-column tile, and each thread has its eight loads in flight before the transposing store.
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T* __restrict__ out) {
-  __shared__ float tile[64][33];
+  constexpr int PT = 2;                                            // 32-pixel tiles per block: 16 loads in flight per thread
+  __shared__ float tile[PT][64][33];
   const int HW = p.H * p.W;
-  const int px0 = blockIdx.x * 32;
+  const int px0 = blockIdx.x * 32 * PT;
   const int cblocks = p.Cpad / 64;
   const int b = blockIdx.y / cblocks, ch0 = (blockIdx.y - b * cblocks) * 64;
   const int TC = p.T * p.C;
   const float* xb = p.x + (long long)b * p.sB;
   const int pl = threadIdx.x & 31, cl0 = threadIdx.x >> 5;         // lane = pixel (coalesced 128-byte rows), warp = channel
-  float v[8];
+  float v[PT][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int ch = ch0 + cl0 + 8 * k, px = px0 + pl;
-    v[k] = 0.f;
-    if (ch < TC && px < HW) {
-      const int t = ch / p.C, c = ch - t * p.C;
-      v[k] = xb[(long long)t * p.sT + (long long)c * p.sC + px];
-      if (c == 4 || c == 10 || c == 16 || c == 22) v[k] = (v[k] - p.mean) / p.stdv;     // metnet3.py:362,370
+    const int ch = ch0 + cl0 + 8 * k;
+    const int t = ch / p.C, c = ch - t * p.C;
+    const float* xc = xb + (long long)t * p.sT + (long long)c * p.sC;
+    const bool pm = c == 4 || c == 10 || c == 16 || c == 22;       // metnet3.py:362,370
+#pragma unroll
+    for (int u = 0; u < PT; ++u) {
+      const int px = px0 + u * 32 + pl;
+      v[u][k] = (ch < TC && px < HW) ? __ldg(xc + px) : 0.f;
+    }
+    if (pm && ch < TC) {
+#pragma unroll
+      for (int u = 0; u < PT; ++u) if (px0 + u * 32 + pl < HW) v[u][k] = (v[u][k] - p.mean) / p.stdv;
     }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) tile[cl0 + 8 * k][pl] = v[k];
+  for (int u = 0; u < PT; ++u)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[u][cl0 + 8 * k][pl] = v[u][k];
   __syncthreads();
   const int wl = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
-  const int px = px0 + wl;
-  if (px < HW) {
-    const int h = px / p.W, w = px - h * p.W;
-    float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = tile[c8 + j][wl];
-    st8(out + p.pg.q(b, h + p.pad_top, w + p.pad_left) * p.Cpad + ch0 + c8, o);
+  for (int u = 0; u < PT; ++u) {
+    const int px = px0 + u * 32 + wl;
+    if (px < HW) {
+      const int h = px / p.W, w = px - h * p.W;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = tile[u][c8 + j][wl];
+      st8(out + p.pg.q(b, h + p.pad_top, w + p.pad_left) * p.Cpad + ch0 + c8, o);
+    }
   }
 }
 
@@ -657,7 +669,7 @@ int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, in
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)p.pg.pixels() * Cpad * esz, st);
   if (e != cudaSuccess) return set_error("prepare memset: %s", cudaGetErrorString(e));
   if (xs[4] == 1 && xs[3] == W) {                              // contiguous (H, W) planes
-    dim3 gridf((unsigned)((H * W + 31) / 32), (unsigned)(B * (Cpad / 64)));
+    dim3 gridf((unsigned)((H * W + 63) / 64), (unsigned)(B * (Cpad / 64)));
     if (dtype == 0) prepare_flat_kernel<bf16><<<gridf, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
     else prepare_flat_kernel<float><<<gridf, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
     return check_launch("prepare_flat_kernel");
