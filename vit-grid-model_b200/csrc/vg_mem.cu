@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
 // every 32-column tile, and each thread has its eight loads in flight before the transposing store.
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T* __restrict__ out) {
-  constexpr int PT = 2;                                            // 32-pixel tiles per block: 16 loads in flight per thread
+  constexpr int PT = 4;                                            // 32-pixel tiles per block: 32 loads in flight per thread
   __shared__ float tile[PT][64][33];
   const int HW = p.H * p.W;
   const int px0 = blockIdx.x * 32 * PT;
@@ -669,7 +669,7 @@ int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, in
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)p.pg.pixels() * Cpad * esz, st);
   if (e != cudaSuccess) return set_error("prepare memset: %s", cudaGetErrorString(e));
   if (xs[4] == 1 && xs[3] == W) {                              // contiguous (H, W) planes
-    dim3 gridf((unsigned)((H * W + 63) / 64), (unsigned)(B * (Cpad / 64)));
+    dim3 gridf((unsigned)((H * W + 127) / 128), (unsigned)(B * (Cpad / 64)));
     if (dtype == 0) prepare_flat_kernel<bf16><<<gridf, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
     else prepare_flat_kernel<float><<<gridf, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
     return check_launch("prepare_flat_kernel");
