@@ -247,35 +247,45 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
     }
     const int w = col - 1;
     const int rx = w == 0 ? 0 : (w == p.pgN.WP - 1 ? 2 : 1);
-#pragma unroll 2
+    if (pad) {                                                // pad pixels: zeros for every lead (no branch in the main loop below)
+      for (int l = 0; l < L; ++l) {
+        const long long q = (((long long)(b * L + l)) * R + r) * P + col;
+        Ld4<T>::st(h1 + q * C + c0, z);
+        *reinterpret_cast<float4*>(res + q * C + c0) = z;
+        if (xhat) {
+          Ld4<T>::st(xhat + q * C + c0, z);
+          if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = 0u;
+          if (lane == 0) p.rstd[q] = 0.f;
+        }
+      }
+      continue;
+    }
+    // four leads in flight: the two warp reductions per (pixel, lead) are chains of five dependent shuffles
+#pragma unroll 4
     for (int l = 0; l < L; ++l) {
       const long long q = (((long long)(b * L + l)) * R + r) * P + col;
-      float y[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
+      float y[4], rr[4], xh[4];
       unsigned nib = 0u;
-      float rstd_save = 0.f;
-      if (!pad) {
-        const float* sl = s_lead + l * LS + c0;
-        const float4 f0 = *reinterpret_cast<const float4*>(sl), f1 = *reinterpret_cast<const float4*>(sl + C);
-        const float4 rt = *reinterpret_cast<const float4*>(sl + 2 * C), tt = *reinterpret_cast<const float4*>(sl + (3 + rx) * C);
-        float v[4] = {a.x + tt.x, a.y + tt.y, a.z + tt.z, a.w + tt.w};
-        const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
-        float ss = 0.f;
+      const float* sl = s_lead + l * LS + c0;
+      const float4 f0 = *reinterpret_cast<const float4*>(sl), f1 = *reinterpret_cast<const float4*>(sl + C);
+      const float4 rt = *reinterpret_cast<const float4*>(sl + 2 * C), tt = *reinterpret_cast<const float4*>(sl + (3 + rx) * C);
+      float v[4] = {a.x + tt.x, a.y + tt.y, a.z + tt.z, a.w + tt.w};
+      const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
+      float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
-        const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
-        rstd_save = rstd;
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-        const float sc[4] = {f0.x, f0.y, f0.z, f0.w}, t[4] = {f1.x, f1.y, f1.z, f1.w};
+      for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
+      const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float sc[4] = {f0.x, f0.y, f0.z, f0.w}, t[4] = {f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xh[i] = v[i] * rstd;
-          float zz = xh[i] * g[i] + be[i];
-          zz = zz * (sc[i] + 1.0f) + t[i];
-          if (zz > 0.f) nib |= 1u << i;
-          y[i] = fmaxf(zz, 0.f);
-        }
-        rr[0] = ra.x + rt.x; rr[1] = ra.y + rt.y; rr[2] = ra.z + rt.z; rr[3] = ra.w + rt.w;
+      for (int i = 0; i < 4; ++i) {
+        xh[i] = v[i] * rstd;
+        float zz = xh[i] * g[i] + be[i];
+        zz = zz * (sc[i] + 1.0f) + t[i];
+        if (zz > 0.f) nib |= 1u << i;
+        y[i] = fmaxf(zz, 0.f);
       }
+      rr[0] = ra.x + rt.x; rr[1] = ra.y + rt.y; rr[2] = ra.z + rt.z; rr[3] = ra.w + rt.w;
       Ld4<T>::st(h1 + q * C + c0, make_float4(y[0], y[1], y[2], y[3]));
       *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
       if (xhat) {                                     // training: what the backward pass needs
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
         wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
         wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
         if ((lane & 7) == 0) p.mask[q * 4 + (lane >> 3)] = wbits;
-        if (lane == 0) p.rstd[q] = rstd_save;
+        if (lane == 0) p.rstd[q] = rstd;
       }
     }
   }
