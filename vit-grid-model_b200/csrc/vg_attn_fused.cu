@@ -605,7 +605,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
         if (it == 0) mbar_wait_tag(tab_full + 0, 0, 394);                         // per-head bias table (TMA); later heads: waited for below
 
         // ---------------- S half-row: / |q|, + bias, masked softmax -> normalised P (bf16) ----------------
-        mbar_wait_tag(s_done, it & 1, 398);
+        if (h == 0) mbar_wait_tag(s_done, it & 1, 398);       // later heads: observed during the previous head (before its P store)
         tc_fence_after();
         if (dbg) p.dbg[h * 8 + 1] = clock64();
         {
@@ -653,7 +653,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           if (lane == 0) mbar_arrive(tab_free + r);                      // last read of this head's tables
           // Barriers that completed long ago are polled here, where the thread has independent work in flight, instead of at
           // the hand-over between heads: the next head's table (loaded two heads ahead).
-          if (it + 1 < my_heads) mbar_wait_tag(tab_full + (r ^ 1), ((it + 1) >> 1) & 1, 394);
+          const bool tab_next = it + 1 < my_heads;
+          const bool tab_ok = tab_next ? mbar_try_wait(tab_full + (r ^ 1), ((it + 1) >> 1) & 1) : true;   // result used at the end of the head
           // ONE exchange per head: every thread exponentiates against the maximum of its OWN half row; the pair then swaps
           // (max, sum) and rescales by 2^(own max - row max) together with the normalisation (the same softmax, exactly)
           if (dbg) { p.dbg[h * 8 + 3] = clock64(); p.dbg[h * 8 + 4] = p.dbg[h * 8 + 3]; }
@@ -683,7 +684,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           *reinterpret_cast<float2*>(red + (r * 128 + t) * 4 + ch * 2) = make_float2(m, s_own);
           // P(h) goes over the q | k columns of head h+1's buffer: S(h+1), which reads that q, was issued when this softmax
           // released the S accumulator (s_free) and has long retired
-          if (h + 1 < heads) mbar_wait_tag(s_done, (it + 1) & 1, 399);
+          const bool sd_next = h + 1 < heads;
+          const bool sd_ok = sd_next ? mbar_try_wait(s_done, (it + 1) & 1) : true;   // polled here, needed before the P store
           if (dbg) p.dbg[h * 8 + 5] = clock64();
           pair_sync(lg);                                                 // partner's (max, sum) is visible
           const float2 oth = *reinterpret_cast<const float2*>(red + (r * 128 + t) * 4 + (ch ^ 1) * 2);
@@ -707,6 +709,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
           // P row (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same
           // keys of the other window are zero.
           {
+            if (!sd_ok) mbar_wait_tag(s_done, (it + 1) & 1, 399);
+            if (!tab_ok) mbar_wait_tag(tab_full + (r ^ 1), ((it + 1) >> 1) & 1, 394);
             const uint32_t tp = lane_addr + (r ? T_QKV0 : T_QKV1) + T_PQ;
             uint32_t pk[16];
 #pragma unroll
