@@ -34,7 +34,6 @@ namespace vg {
 namespace fa {
 constexpr int C = 128;         // model channels (K of the QKV projection)
 constexpr int DH = 32;         // head dim
-constexpr int SLOT = 64;       // token slots per window (S <= 64)
 constexpr int WIN = 7, REG = 4, SEQ = REG + WIN * WIN;   // the kernel is specialised for 7x7 windows + 4 register tokens
 // shared memory map (bytes); every operand tile is 1024-B aligned
 constexpr int WQ_BYTES = 2 * 12288;              // fp16: 2 k-blocks x [96 rows x 128 B]
@@ -570,17 +569,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
     const int t = lg * 32 + lane;                            // tile row == TMEM lane
     const int half = t >> 6, i = t & 63;                     // window within the pair, token slot
     const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
-    const AttnGeom g = p.g;
-    const int nwin = g.nwin();
-    const bool tok_valid = i < SEQ;
     const bool is_reg = i < REG;
     // window position of this token (clamped for register / pad slots so that table addresses stay valid)
     const int ti = (i >= REG && i < SEQ) ? i - REG : 0;
     const int ai = ti / WIN, bi = ti - ai * WIN;
     const uint32_t s_base = smem_u32(smem);
-    uint32_t swz[8];                                         // swizzled chunk offsets of this thread's tile row
-#pragma unroll
-    for (int c = 0; c < 8; ++c) swz[c] = sw128(t, c);
     float* red = reinterpret_cast<float*>(smem + RED_OFF);   // [2 head parities][128 rows][2 threads] x (max, sum)
     const float* qinv = reinterpret_cast<const float*>(smem + QINV_OFF);
     // bias rows of this token: window tokens step one 32-byte row back per key row aj; register-token rows (maxvit.py:167:
@@ -593,9 +586,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_consta
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       // (the X tile of this tile is built by the staging warps)
-      const TokRow tr = tok_row(p, tile, t);
-      const float* src = tr.src;                             // residual-stream row of this token
-      const long long pix = tr.pix, wdx = tr.wdx;
+      const long long wdx = tile * 2 + half;                 // window of this row (dropout row id)
 
       for (int h = 0; h < heads; ++h, ++it) {
         const bool dbg = p.dbg && blockIdx.x == 0 && ctid == 0 && tl == 0;
