@@ -13,6 +13,11 @@ inference, bf16, batch 64 synthetic CMAQ grids = 768 fields per step per GPU).
              around its launches inside the timed region; algorithmic FLOPs = 2*84*70*128*1152 per field per launch
 * `cpu_baseline` = the CPU oracle port of the reference (oracle/, plain PyTorch fp32) on the host cores, B=1
 * `--impl reference` times that same CPU port as the reference arm (the Python reference cannot travel to the box)
+* `gpu_eager_baseline` = the same oracle port run as plain PyTorch eager (cuDNN / cuBLAS / ATen) on cuda:0 -- SURVEY 2.1's
+             "bar on the box" -- in fp32 with TF32 off and under bf16 autocast, at the largest batch it is run at (stated)
+* `train`  = BASELINE configs[2]: the training step (train-mode forward, Focal-R, backward, NCCL gradient all-reduce, fused
+             AdamW), with its own roofline block for the kernel with the largest share of the step
+* `--config 3|4` = BASELINE configs[3] (512x512 domain, MaxViT depth 2) / configs[4] (512 channels, 32 x 64 heads, depth 4)
 N>1: one process per GPU (torchrun), batch-sharded, no data-path collective (inference) -> weak scaling.
 """
 import argparse
@@ -104,6 +109,43 @@ def cpu_port_forward_time(batch=1, repeats=3, threads=None):
     return best, threads
 
 
+def gpu_eager_forward_time(dev, batch=16, repeats=3):
+    """SURVEY 2.1 / BASELINE.md 4: "PyTorch eager (cuDNN / cuBLAS / ATen) running the reference module" on the same GPU.  The
+    reference itself cannot travel to the box, so this runs the oracle port (pinned to the reference by tests/golden) with
+    its tensors on the device -- the same ATen call sequence as the reference module.  Three settings: fp32 with TF32 disabled
+    (the strict-parity setting), fp32 with TF32 allowed, and bf16 autocast."""
+    from oracle import synth
+    from oracle.metnet3_oracle import metnet3_forward
+    cfg = synth.CFG_12HR
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(synth.metnet3_spec(cfg), seed=0).items()}
+    out = {"batch": batch, "fields_per_step": batch * cfg.L, "unit": UNIT, "kind": "oracle port on cuda (PyTorch eager)"}
+    x, ts, _ = synth.make_inputs(cfg, batch, seed=1234)
+    x, ts = x.to(dev), ts.to(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for name in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = name == "fp32_tf32_on"
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=name == "bf16_autocast"):
+                metnet3_forward(x, ts, sd, cfg)
+                torch.cuda.synchronize()
+                best = float("inf")
+                for _ in range(repeats):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    metnet3_forward(x, ts, sd, cfg)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+            out[name] = {"value": batch * cfg.L / (best * 1e-3), "ms_per_step": best}
+        except Exception as e:                              # OOM or an op the port cannot run on the device: report, do not fail
+            out[name] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:120]}"}
+            torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     """reference arm: the reference's CPU implementation of the path (oracle port) on the host cores"""
     if rank != 0:
@@ -137,6 +179,9 @@ def run_reference(args, rank, world):
     }))
 
 
+ATTN_BWD_FLOPS_PER_FIELD = 2.0 * 2.0125e9                  # backward of one attention = 2x its forward FLOPs (dX and dW of every contraction)
+
+
 def run_train(args, cfg, dev, rank, world, barrier, max_over_ranks):
     """BASELINE configs[2]: training step (train-mode forward, Focal-R, hand-written backward, gradient all-reduce over
     NCCL overlapped with backward when world > 1, fused AdamW), batch-sharded data parallel, weak scaling."""
@@ -159,38 +204,174 @@ def run_train(args, cfg, dev, rank, world, barrier, max_over_ranks):
         opt.step()
         return loss
 
-    for _ in range(3):
+    for _ in range(max(5, args.warmup)):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
-    if args.trace:
-        _lib.TRACE = []
-    steps = max(3, args.steps // 2)
+    steps = max(20, args.steps)
     e0.record()
     for _ in range(steps):
         loss = step()
     e1.record()
     barrier()
-    trace, _lib.TRACE = _lib.TRACE, None
+    launches = int((_lib.launch_count() - l0) // steps)
     ms = max_over_ranks(e0.elapsed_time(e1))
-    if args.trace and rank == 0 and trace:
-        per = {}
-        for name, tag, a, b in trace:
-            key = name if name not in ("vg_gemm_fwd", "vg_wgrad") else f"{name}[{tag}]"
-            per.setdefault(key, []).append(a.elapsed_time(b))
-        tot = sum(sum(v) for v in per.values())
-        print(f"# ---- training step, {Bt * L} fields: {ms / steps:.2f} ms/step, kernels {tot / steps:.2f} ms", file=sys.stderr)
+    # per-entry-point CUDA events on a few extra steps OUTSIDE the timed region (the host enqueues a step in about half its
+    # device time; two event records per launch would eat into that margin)
+    _lib.TRACE = []
+    tsteps = 3
+    for _ in range(tsteps):
+        step()
+    torch.cuda.synchronize()
+    trace, _lib.TRACE = _lib.TRACE, None
+    per = {}
+    for name, tag, a, b in trace:
+        key = name if name not in ("vg_gemm_fwd", "vg_wgrad") else f"{name}[{tag}]"
+        per.setdefault(key, []).append(a.elapsed_time(b))
+    tot = sum(sum(v) for v in per.values())
+    if args.trace and rank == 0:
+        print(f"# ---- training step, {Bt * L} fields: {ms / steps:.2f} ms/step, kernels {tot / tsteps:.2f} ms", file=sys.stderr)
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1]))[:40]:
-            print(f"# {name:60s} calls/step {len(v) // steps:3d}  ms/step {sum(v) / steps:9.3f}  {100 * sum(v) / tot:5.1f}%", file=sys.stderr)
+            print(f"# {name:60s} calls/step {len(v) // tsteps:3d}  ms/step {sum(v) / tsteps:9.3f}  {100 * sum(v) / tot:5.1f}%", file=sys.stderr)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    top = sorted(per.items(), key=lambda kv: -sum(kv[1]))[:6]
+    breakdown = [{"entry": k, "ms_per_step": sum(v) / tsteps, "share": sum(v) / tot} for k, v in top]
+    roof = None
+    bwd = per.get("vg_attn_bwd_fused") or per.get("vg_attn_core_bwd")
+    if bwd:
+        name = "vg_attn_bwd_fused" if "vg_attn_bwd_fused" in per else "vg_attn_core_bwd"
+        avg = sum(bwd) / len(bwd)
+        # the fused backward covers the whole attention (projections included); the un-fused core only QK^T / PV and their gradients
+        flops = ATTN_BWD_FLOPS_PER_FIELD if name == "vg_attn_bwd_fused" else 4.0 * 2 * 0.1726e9
+        ach = flops * Bt * L / (avg * 1e-3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "avg_launch_ms": avg, "launches_per_step": len(bwd) // tsteps, "share_of_step": sum(bwd) / tot, "traffic": None}
     n_params = sum(p.numel() for p in model.parameters())
-    return {"metric": "train_grid_fields_per_sec", "value": world * Bt * L * steps / (ms * 1e-3), "unit": UNIT,
-            "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": Bt, "fields_per_step": world * Bt * L,
-            "loss": float(loss.item()), "gpu_launches": int((_lib.launch_count() - l0) // steps),
+    value = world * Bt * L * steps / (ms * 1e-3)
+    return {"metric": "train_grid_fields_per_sec", "value": value, "unit": UNIT,
+            "ms_per_step": ms / steps, "steps": steps, "warmup": max(5, args.warmup), "batch_per_gpu": Bt, "fields_per_step": world * Bt * L,
+            "loss": float(loss.item()), "gpu_launches": launches,
             "parallelism": f"data parallel x{world}: per-rank batch shards, gradient all-reduce ({n_params * 4 / 1e6:.1f} MB fp32, "
                            f"6 sections, NCCL on a side stream overlapped with backward)" if world > 1 else "single GPU",
             "optimizer": "fused AdamW (one kernel over the flat parameter buffer)", "dropout": model.dropout,
-            "gflop_per_field_fwd_bwd": 3 * FWD_GFLOP_PER_FIELD_EXEC}
+            "gflop_per_field_fwd_bwd": 3 * FWD_GFLOP_PER_FIELD_EXEC,
+            "model_tflops": value / world * 3 * FWD_GFLOP_PER_FIELD_EXEC / 1e3, "frac_of_bf16_peak": value / world * 3 * FWD_GFLOP_PER_FIELD_EXEC / 1e3 / peak_tf,
+            "roofline": roof, "breakdown": breakdown}
+
+
+def run_other_config(args, dev, rank, world):
+    """BASELINE configs[3] / configs[4] as bench lines (same JSON contract; `config.workload` names the configuration)."""
+    import torch.distributed as dist
+    from oracle import synth
+    from vit_grid_model_b200 import MetNet3, DataParallel, FlatAdamW, focal_r_loss, _lib
+    if args.config == 3:
+        cfg = synth.GridConfig(H=512, W=512, vit_depth=2)
+        B = 1 if args.batch == 64 else args.batch
+        workload = ("BASELINE configs[3]: enlarged 512x512 domain (518x518 padded, 1,369 windows per field, grid-partition stride 37), "
+                    "MaxViT depth 2, bf16")
+        gf_ref = 25.864 * (518 * 518) / (84 * 70) + 4.424 * (259 * 259) / (42 * 35)      # conv part scales with pixels, + one more MaxViT layer
+    else:
+        cfg = synth.GridConfig(dim=512, heads=32, dim_head=64, vit_depth=4)
+        B = 8 if args.batch == 64 else args.batch
+        workload = "BASELINE configs[4]: MetNet-3-style backbone, 512 channels, 32 heads x dim_head 64, MaxViT depth 4, 82x67 domain"
+        gf_ref = 370.9
+    L = cfg.L
+    W = max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    model = MetNet3(**cfg.metnet3_kwargs())
+    model.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), strict=True)
+    model = model.to(dev).eval().set_precision("bf16")
+    x, ts, target = synth.make_inputs(cfg, B, seed=1234 + rank)
+    x_host, ts_host = x.pin_memory(), ts.pin_memory()
+    x, ts, target = x.to(dev), ts.to(dev), target.to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(W):
+            model(x, timestamps=ts)
+        barrier()
+        l0 = _lib.launch_count()
+        with ClockSampler(dev.index or 0) as clk:
+            e0.record()
+            for _ in range(args.steps):
+                model(x, timestamps=ts)
+            e1.record()
+            barrier()
+        launches = (_lib.launch_count() - l0) // args.steps
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        # end to end: pinned host tensor in, pinned host predictions out, synchronously per step (tiny batches: no pipelining)
+        y_host = torch.empty(B, L, cfg.H, cfg.W, dtype=torch.float32).pin_memory()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            y_host.copy_(model(x_host.to(dev, non_blocking=True), timestamps=ts_host.to(dev, non_blocking=True)), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    fields = world * B * L * args.steps
+    value = fields / (ms * 1e-3)
+    train = None
+    if not args.no_train:
+        try:
+            model.train()
+            net = DataParallel(model) if world > 1 else model
+            opt = FlatAdamW(model, lr=1e-5)
+
+            def step():
+                opt.zero_grad()
+                loss = focal_r_loss(net(x, timestamps=ts), target)
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(3):
+                step()
+            barrier()
+            steps = max(5, args.steps)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            barrier()
+            tms = max_over_ranks(e0.elapsed_time(e1))
+            train = {"metric": "train_grid_fields_per_sec", "value": world * B * L * steps / (tms * 1e-3), "unit": UNIT,
+                     "ms_per_step": tms / steps, "steps": steps, "fields_per_step": world * B * L, "loss": float(loss.item()),
+                     "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except NotImplementedError as e:
+            train = {"unavailable": str(e)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload, "batch_per_gpu": B, "fields_per_step": world * B * L,
+                       "input_shape": [B, cfg.T, cfg.C, cfg.H, cfg.W], "gflop_per_field_reference_graph": gf_ref,
+                       "l2": "activations of one step exceed the 126 MB L2", "parallelism": f"batch-sharded x{world}"},
+            "clocks": clk.summary(),
+            "e2e": {"value": fields / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + ts_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+            "gpu_launches": int(launches),
+            "model_tflops_reference_graph": value / world * gf_ref / 1e3,
+            "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "train": train,
+        }))
 
 
 def main():
@@ -205,6 +386,13 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (BASELINE configs[2])")
     ap.add_argument("--train-batch", type=int, default=16, help="CMAQ samples per GPU per training step")
     ap.add_argument("--trace", action="store_true", help="print a per-entry-point time breakdown (rank 0)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs index: 1 = the headline (12hr model, B=64 inference + the configs[2] training step); "
+                         "3 = 512x512 domain, MaxViT depth 2 (inference + training step); 4 = 512 channels, 32 x 64 heads, depth 4")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU comparator")
+    ap.add_argument("--e2e-input", default="bf16", choices=["bf16", "fp32"],
+                    help="host format of the e2e leg's inputs: bf16 = batches packed by pipeline.pack_host (bit-identical "
+                         "predictions, half the H2D bytes); fp32 = the reference's tensor; the other one is reported beside it")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +412,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
+
+    if args.config != 1:
+        run_other_config(args, dev, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cfg = synth.CFG_12HR
     B, L = args.batch, cfg.L
@@ -270,20 +464,29 @@ def main():
         # ---------------- end to end (host buffers in, host predictions out) through the package's streaming API:
         # every step's inputs come from pinned host memory and its predictions land in pinned host memory inside the timed
         # region; HostPipeline overlaps those copies with the kernels of the neighbouring steps (side stream + events)
-        from vit_grid_model_b200 import HostPipeline
+        from vit_grid_model_b200 import HostPipeline, pack_host
         pipe = HostPipeline(model)
         y_hosts = [torch.empty(B, L, cfg.H, cfg.W, dtype=torch.float32).pin_memory() for _ in range(2)]
-        for _ in pipe.run((x_host, ts_host, y_hosts[i % 2]) for i in range(2)):
-            pass
-        barrier()
-        e0.record()
-        n_out = 0
-        for _ in pipe.run((x_host, ts_host, y_hosts[i % 2]) for i in range(args.steps)):
-            n_out += 1
-        e1.record()
-        barrier()
-        assert n_out == args.steps
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        x_packed = pack_host(x, cfg.pm25_mean, cfg.pm25_std)          # data-loader side, outside the timed region (stated in config)
+
+        def e2e_run(x_in):
+            for _ in pipe.run((x_in, ts_host, y_hosts[i % 2]) for i in range(2)):
+                pass
+            barrier()
+            e0.record()
+            n_out = 0
+            for _ in pipe.run((x_in, ts_host, y_hosts[i % 2]) for i in range(args.steps)):
+                n_out += 1
+            e1.record()
+            barrier()
+            assert n_out == args.steps
+            return max_over_ranks(e0.elapsed_time(e1))
+
+        ms_e2e_fp32 = e2e_run(x_host)
+        y_ref = y_hosts[(args.steps - 1) % 2].clone()
+        ms_e2e_bf16 = e2e_run(x_packed)
+        packed_identical = bool(torch.equal(y_ref, y_hosts[(args.steps - 1) % 2]))
+        ms_e2e = ms_e2e_bf16 if args.e2e_input == "bf16" else ms_e2e_fp32
 
     train = None
     if not args.no_train and args.precision == "bf16":
@@ -297,6 +500,8 @@ def main():
     per = {}
     for name, tag, a, b in trace:
         per.setdefault(name, []).append(a.elapsed_time(b))
+        if name == "vg_conv3x3_ln_fwd":
+            per.setdefault(f"  conv[{tag}]", []).append(a.elapsed_time(b))
         if name == "vg_gemm_fwd":
             per.setdefault(f"  gemm[{tag}]", []).append(a.elapsed_time(b))
     conv_ms = per.get("vg_conv3x3_ln_fwd", [])
@@ -307,9 +512,10 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # sustained: the kernel is timed inside a long step
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    traffic = None
+    traffic, traffic_all = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("conv3x3_ln_dram_bytes_per_launch")
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = traffic_all.get("conv3x3_ln_dram_bytes_per_launch")
     except Exception:
         pass
     roofline, kernels = None, []
@@ -320,7 +526,11 @@ def main():
                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         "traffic": traffic, "launches_per_step": len(conv_ms) // args.steps, "avg_launch_ms": avg_ms,
                         "peak_source": peak_src, "share_of_step": sum(conv_ms) / ms_total,
-                        "algorithmic_gflop_per_field_per_launch": CONV_FLOPS_PER_FIELD / 1e9})
+                        "algorithmic_gflop_per_field_per_launch": CONV_FLOPS_PER_FIELD / 1e9,
+                        "variants": {k.strip()[5:-1]: {"launches_per_step": len(v) // args.steps, "avg_launch_ms": sum(v) / len(v),
+                                                       "frac": CONV_FLOPS_PER_FIELD * B * L / (sum(v) / len(v) * 1e-3) / 1e12 / peak_tf,
+                                                       "traffic": (traffic_all.get("conv_variants") or {}).get(k.strip()[5:-1])}
+                                     for k, v in per.items() if k.startswith("  conv[")}})
     attn_ms = per.get("vg_attn_fused_fwd", [])
     if attn_ms and args.precision == "bf16":
         avg_ms = sum(attn_ms) / len(attn_ms)
@@ -346,11 +556,22 @@ def main():
             tot = sum(sum(v) for k, v in per.items() if not k.startswith("  "))
             for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
                 print(f"# {name:24s} calls/step {len(v) // args.steps:3d}  ms/step {sum(v) / args.steps:9.3f}  {100 * sum(v) / tot:5.1f}%", file=sys.stderr)
-        cpu = None
+        cpu = eager = None
         if world == 1 and not args.no_cpu_baseline:
-            sec, threads = cpu_port_forward_time(batch=1, repeats=3)
+            # all host cores, and the reference's own setting of 4 threads (evaluation_vit.py:3-5)
+            allc = os.cpu_count() or 1
+            sec, threads = cpu_port_forward_time(batch=1, repeats=3, threads=allc)
+            sec4, _ = cpu_port_forward_time(batch=1, repeats=2, threads=min(4, allc))
             cpu = {"value": L / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"oracle port of the reference forward, B=1 (12 fields), fp32 eval, best of 3 after 1 warm-up, {threads} torch threads, {sec:.3f} s/forward"}
+                   "sample": f"oracle port of the reference forward, B=1 (12 fields), fp32 eval, best of 3 after 1 warm-up, {threads} torch threads, {sec:.3f} s/forward",
+                   "threads_4": {"value": L / sec4, "cores": min(4, allc), "seconds_per_forward": sec4,
+                                 "note": "the reference pins OMP/MKL/OPENBLAS threads to 4 (evaluation_vit.py:3-5)"}}
+        if world == 1 and not args.no_eager_baseline:
+            eager = gpu_eager_forward_time(dev, batch=16)
+            for k in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast"):
+                if eager.get(k, {}).get("value"):
+                    eager[k]["speedup_of_this_repo"] = value / eager[k]["value"]
+        h2d = {"bf16": x_packed.numel() * 2 + ts_host.numel() * 4, "fp32": x_host.numel() * 4 + ts_host.numel() * 4}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,14 +579,22 @@ def main():
             "config": {"workload": "BASELINE configs[1]: 12hr MetNet3/MaxViT inference, batch 64 synthetic CMAQ grids per GPU (768 fields/step/GPU)",
                        "batch_per_gpu": B, "fields_per_step": world * B * L, "input_shape": [B, cfg.T, cfg.C, cfg.H, cfg.W],
                        "l2": "inputs (844 MB) and every activation exceed the 126 MB L2", "parallelism": f"batch-sharded x{world}, no collective",
+                       "e2e_input": f"{args.e2e_input}: " + ("pinned bf16 batches packed once by pipeline.pack_host outside the timed region (the data-loader "
+                                    "side; PM2.5 channels standardised in fp32 before the rounding, predictions bit-identical to the fp32 tensor: "
+                                    f"checked in this run = {packed_identical})" if args.e2e_input == "bf16" else "the reference's pinned fp32 tensor"),
                        "gflop_per_field_reference_graph": FWD_GFLOP_PER_FIELD_REF, "gflop_per_field_executed": FWD_GFLOP_PER_FIELD_EXEC,
                        "lead_time_dedup": True},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": x_host.numel() * 4 + ts_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+                    "h2d_bytes_per_step": h2d[args.e2e_input], "d2h_bytes_per_step": y_host.numel() * 4,
+                    "frac_of_device_resident": e2e_value / value,
+                    "fp32_host_input": {"value": fields / (ms_e2e_fp32 * 1e-3), "ms_per_step": ms_e2e_fp32 / args.steps, "h2d_bytes_per_step": h2d["fp32"]},
+                    "bf16_host_input": {"value": fields / (ms_e2e_bf16 * 1e-3), "ms_per_step": ms_e2e_bf16 / args.steps, "h2d_bytes_per_step": h2d["bf16"],
+                                        "bit_identical_to_fp32_input": packed_identical}},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "model_tflops_executed": value * FWD_GFLOP_PER_FIELD_EXEC / 1e3,
             "train": train,
         }

@@ -43,6 +43,11 @@ VG_API const char* vg_last_error(void);
 VG_API long long vg_launch_count(void);
 /* 0 when the current CUDA device is compute capability 10.x; error otherwise */
 VG_API int vg_device_check(void);
+/* Sticky device-side error word: kernels that meet input the reference's PyTorch op would have raised on (today: a
+ * timestamp whose month / day / hour falls outside nn.Embedding(13 | 32 | 25), metnet3.py:262-266,392 -> IndexError in
+ * the reference) skip the access, poison the affected field's predictions with NaN and set bit 0 here.  Meaningful after
+ * the stream has been synchronised; clear != 0 resets it.  Bit 0 (value 1) = timestamp out of range. */
+VG_API int vg_device_error(int clear);
 /* number of flat pixels (rows of the [q][C] matrix) of a PG buffer */
 VG_API long long vg_pg_pixels(int N, int HP, int WP);
 
@@ -52,6 +57,13 @@ VG_API long long vg_pg_pixels(int N, int HP, int WP);
 VG_API int vg_prepare_fwd(int dtype, const float* x, const long long* xstride, int B, int T, int C, int H, int W,
                    int pad_top, int pad_left, int HP, int WP, int Cpad, float pm_mean, float pm_std, void* out,
                    void* stream);
+
+/* Same as vg_prepare_fwd for a batch PACKED on the host (HostPipeline.pack_host: the data-loader side of
+ * evaluation_vit.py:236-249): x is bf16 (B,T,C,H,W) whose PM2.5 channels were standardised in fp32 BEFORE the rounding
+ * to bf16 -- exactly the values vg_prepare_fwd(VG_DTYPE_BF16) produces from the fp32 tensor, so the predictions are
+ * bit-identical while the host->device copy moves half the bytes. */
+VG_API int vg_prepare_packed_fwd(int dtype, const void* x_bf16, const long long* xstride, int B, int T, int C, int H, int W,
+                          int pad_top, int pad_left, int HP, int WP, int Cpad, void* out, void* stream);
 
 /* metnet3.py:389-416 -- lead-time / model-time embeddings (with the reference's dim-0 concat quirk and
  * hard-coded time index 6), and their analytic contribution to the first 3x3 conv (9 border cases) and to
@@ -127,6 +139,11 @@ VG_API int vg_se_gate_fwd(const float* psum, int N, int H, int W, const float* W
                    float* gate, void* stream);
 /* x *= gate (in place), CL (N,HW,C) */
 VG_API int vg_se_scale_fwd(int dtype, void* x, const float* gate, int N, long long HW, int C, void* stream);
+
+/* Test hook (bit-exact index parity): the partition map every attention kernel of this library addresses
+ * tokens through (attn_token_pixel), evaluated ON THE DEVICE for every token row: pixel_index[(n*nwin + wi)*S + tok] =
+ * n*Hl*Wl + pixel of window token tok-R (maxvit.py:298 block / :322 grid), -1 for the R register-token rows. */
+VG_API int vg_attn_partition_debug(int N, int Hl, int Wl, int win, int R, int grid_mode, long long* pixel_index, void* stream);
 
 /* maxvit.py:298-308 / 322-332 + 176-187 -- partition (mode 0 block, 1 grid) folded into addressing, register
  * tokens prepended (reg: fp32 [R][C] shared or [N][R][C] per field), LayerNorm (no affine), FiLM (film: fp32

@@ -34,7 +34,21 @@ def resnet_block(x, cond, sd, p: str):
     return h + x
 
 
-def prepare_input(x, timestamps, sd, cfg: GridConfig, stn_imgs: bool = False):
+def time_embedding(timestamps, sd, cfg: GridConfig):
+    """metnet3.py:389-408 for the WHOLE batch -> (t_emb (N, lead_emb + 3*time_emb), cond (N, lead_emb)), N = B*L.
+    The scramble of quirk Q1 couples every field to the timestamps of other samples, so it is always computed on the
+    full batch, even when the rest of the network is evaluated in sample chunks."""
+    B, L = timestamps.shape[0], cfg.L
+    N = B * L
+    ts = timestamps[:, 6, :].repeat_interleave(L, dim=0)
+    lead = torch.arange(1, L + 1).repeat(B)
+    cond = sd["condition_lead_time.weight"][lead]
+    mt = ts[:, 1:4].int().long()                                   # month, day, hour
+    flat = torch.cat([sd[f"condition_model_time.{i}.weight"][mt[:, i]] for i in range(3)], dim=0)
+    return torch.cat([cond, flat.reshape(N, -1)], dim=1), cond
+
+
+def prepare_input(x, timestamps, sd, cfg: GridConfig, stn_imgs: bool = False, samples=None):
     """metnet3.py:354-416 -> (net_in (N,c_in,HP,WP), cond (N,lead_emb)), N = B*L.
 
     * PM2.5 channels {4,10,16,22} of every time step standardised (:361-380)
@@ -44,8 +58,14 @@ def prepare_input(x, timestamps, sd, cfg: GridConfig, stn_imgs: bool = False):
       the three (N,1) embeddings are concatenated on dim 0 and viewed as (N,3), so row n
       holds flat[3n:3n+3] of [month_0..month_{N-1}, day_0.., hour_0..] (:395-401, quirk Q1)
     * timestamps are taken at hard-coded time index 6 (:405, quirk Q2)
+    samples = (b0, b1): only the fields of samples [b0, b1) (time embedding still from the whole batch).
     """
-    B, L = x.shape[0], cfg.L
+    L = cfg.L
+    t_emb, cond = time_embedding(timestamps, sd, cfg)
+    if samples is not None:
+        b0, b1 = samples
+        x, t_emb, cond = x[b0:b1], t_emb[b0 * L:b1 * L], cond[b0 * L:b1 * L]
+    B = x.shape[0]
     x = x.clone()
     pm = torch.tensor([4, 10, 16, 22] + ([24] if stn_imgs else []))   # MetNet3_with_stn_imgs also standardises the
     x[:, :, pm] = (x[:, :, pm] - cfg.pm25_mean) / cfg.pm25_std          # station image, channel 24 (metnet3.py:701)
@@ -53,23 +73,28 @@ def prepare_input(x, timestamps, sd, cfg: GridConfig, stn_imgs: bool = False):
     x = F.pad(x, cfg.pads, value=0.0)
     N, HP, WP = B * L, x.shape[-2], x.shape[-1]
     x = x.reshape(N, -1, HP, WP)
-    ts = timestamps[:, 6, :].repeat_interleave(L, dim=0)
-    lead = torch.arange(1, L + 1).repeat(B)
-    cond = sd["condition_lead_time.weight"][lead]
-    mt = ts[:, 1:4].int().long()                                   # month, day, hour
-    flat = torch.cat([sd[f"condition_model_time.{i}.weight"][mt[:, i]] for i in range(3)], dim=0)
-    t_emb = torch.cat([cond, flat.reshape(N, -1)], dim=1)          # (N, lead_emb + 3*time_emb)
     x = torch.cat([x, t_emb[:, :, None, None].expand(-1, -1, HP, WP)], dim=1)
     return x, cond
 
 
 def metnet3_forward(x, timestamps, sd, cfg: GridConfig, *, training: bool = False, return_features: bool = False,
-                    stn_imgs: bool = False):
+                    stn_imgs: bool = False, sample_chunk: int | None = None):
     """MetNet3.forward (metnet3.py:339-430): (B,T,C,H,W), (B,*,4) -> (B,L,H,W) fp32.
     stn_imgs=True: MetNet3_with_stn_imgs.forward (metnet3.py:666-759), identical but for the extra normalised channel
-    (the reference ALSO writes that normalisation back into the caller's tensor, :701; the oracle is functional)."""
+    (the reference ALSO writes that normalisation back into the caller's tensor, :701; the oracle is functional).
+    sample_chunk (eval mode only): evaluate the network `sample_chunk` samples at a time to bound host memory at large B --
+    nothing after the time embedding couples the fields of a batch in eval mode, so the result is the same
+    (tests/test_oracle.py::test_sample_chunking_is_exact)."""
     B = x.shape[0]
-    h, cond = prepare_input(x, timestamps, sd, cfg, stn_imgs)
+    if sample_chunk is not None and not training and not return_features and sample_chunk < B:
+        return torch.cat([_forward_samples(x, timestamps, sd, cfg, (b0, min(B, b0 + sample_chunk)), False, False, stn_imgs)
+                          for b0 in range(0, B, sample_chunk)], dim=0)
+    return _forward_samples(x, timestamps, sd, cfg, None, training, return_features, stn_imgs)
+
+
+def _forward_samples(x, timestamps, sd, cfg, samples, training, return_features, stn_imgs):
+    h, cond = prepare_input(x, timestamps, sd, cfg, stn_imgs, samples)
+    B = h.shape[0] // cfg.L
     for bi in range(cfg.resnet_depth):
         h = resnet_block(h, cond, sd, f"resnet1.blocks.{bi}.")
     feats = {"resnet1": h}

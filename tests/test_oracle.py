@@ -87,3 +87,16 @@ def test_focal_r_properties():
     s = torch.sigmoid(0.2 * e.abs())
     ga = torch.sign(e) * ((2 * s - 1) + 2 * 0.2 * e.abs() * s * (1 - s)) / e.numel()
     torch.testing.assert_close(focal_r_grad(p, t), ga, rtol=1e-5, atol=1e-8)
+
+
+def test_sample_chunking_is_exact():
+    """the oracle evaluated in sample chunks (full-batch time embedding, quirk Q1) == the oracle on the whole batch"""
+    cfg = synth.CFG_TINY
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=1)
+    x, ts, _ = synth.make_inputs(cfg, 5, seed=8)
+    y = metnet3_forward(x, ts, sd, cfg)
+    y2 = metnet3_forward(x, ts, sd, cfg, sample_chunk=2)
+    torch.testing.assert_close(y2, y, rtol=1e-6, atol=1e-6)
+    # and the scramble really couples samples: chunking the INPUT (timestamps included) changes the answer
+    y3 = torch.cat([metnet3_forward(x[b:b + 1], ts[b:b + 1], sd, cfg) for b in range(5)])
+    assert (y3 - y).abs().max() > 1e-4

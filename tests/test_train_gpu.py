@@ -125,3 +125,97 @@ def test_train_with_default_dropout_and_unsupported_modes():
     m.train().set_precision("fp32")
     with pytest.raises(NotImplementedError):                     # dropout is built into the mixed-precision path only
         m(x.cuda(), timestamps=ts.cuda())
+
+
+def test_two_forwards_one_backward_accumulate_like_autograd():
+    """the model applied twice inside one autograd graph (two micro-batches summed into one loss).  The
+    gradients must be the SUM of the two applications' gradients (reference: autograd through the oracle on the same two
+    batches; BatchNorm statistics are per application, exactly as in the reference module), and gradient accumulation over
+    two backward passes must give the same."""
+    from vit_grid_model_b200 import focal_r_loss
+    from oracle.focal_r_oracle import focal_r
+    from oracle.metnet3_oracle import metnet3_forward
+    cfg = synth.CFG_SMALL128
+    m = build(cfg, 0, "fp32")
+    xa, tsa, ta = synth.make_inputs(cfg, 2, seed=21)
+    xb, tsb, tb = synth.make_inputs(cfg, 2, seed=22)
+    # reference gradients
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=0)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k and k != "pm25_boundaries":
+            v.requires_grad_(True)
+    (focal_r(metnet3_forward(xa, tsa, sd, cfg, training=True), ta)
+     + focal_r(metnet3_forward(xb, tsb, sd, cfg, training=True), tb)).backward()
+    # (1) one graph, one backward
+    loss = focal_r_loss(m(xa.cuda(), timestamps=tsa.cuda()), ta.cuda()) + focal_r_loss(m(xb.cuda(), timestamps=tsb.cuda()), tb.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    g1 = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    # (2) two backward passes accumulating into p.grad
+    for p in m.parameters():
+        p.grad = None
+    m2 = build(cfg, 0, "fp32")                           # fresh BatchNorm running buffers
+    focal_r_loss(m2(xa.cuda(), timestamps=tsa.cuda()), ta.cuda()).backward()
+    focal_r_loss(m2(xb.cuda(), timestamps=tsb.cuda()), tb.cuda()).backward()
+    torch.cuda.synchronize()
+    num = den = 0.0
+    for k, p in m2.named_parameters():
+        ref = sd[k].grad
+        for g in (g1[k].cpu(), p.grad.detach().cpu()):
+            assert ((g - ref).abs().max() / max(ref.abs().max().item(), 1e-2)).item() < 2e-2, k
+            num += (g - ref).pow(2).sum().item()
+            den += ref.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 1e-3
+    # a second backward through the same forward is refused loudly (saved activations are released)
+    pred = m(xa.cuda(), timestamps=tsa.cuda())
+    l2 = focal_r_loss(pred, ta.cuda())
+    l2.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="retain_graph"):
+        l2.backward()
+
+
+def test_flat_adamw_honours_p_grad_clipping_and_checkpoints():
+    """FlatAdamW consumes p.grad (accumulated, clipped or edited in place), not the last backward's raw buffer; its state
+    round-trips through state_dict / load_state_dict"""
+    from vit_grid_model_b200 import FlatAdamW, focal_r_loss
+    cfg = synth.CFG_SMALL128
+    x, ts, target = synth.make_inputs(cfg, 2, seed=9)
+    x, ts, target = x.cuda(), ts.cuda(), target.cuda()
+
+    def run(mode):
+        m = build(cfg, 0, "fp32")
+        opt = FlatAdamW(m, lr=1e-3)
+        ref_p = {k: p.detach().clone().requires_grad_(True) for k, p in m.named_parameters()}
+        ref_opt = torch.optim.AdamW(list(ref_p.values()), lr=1e-3, weight_decay=0.0)
+        opt.zero_grad()
+        focal_r_loss(m(x, timestamps=ts), target).backward()
+        if mode == "accumulate":
+            focal_r_loss(m(x, timestamps=ts), target).backward()
+        if mode == "clip_torch":
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 0.05)
+        if mode == "clip_flat":
+            total = opt.clip_grad_norm_(0.05)
+            assert total.item() > 0.05
+        if mode == "replaced":                                   # slow path: p.grad replaced by fresh tensors
+            for p in m.parameters():
+                p.grad = p.grad * 0.5
+        for k, p in m.named_parameters():
+            ref_p[k].grad = p.grad.detach().clone()
+        if mode == "clip_flat":
+            assert torch.linalg.vector_norm(torch.cat([g.grad.reshape(-1) for g in ref_p.values()])).item() < 0.0501
+        ref_opt.step()
+        opt.step()
+        for k, p in m.named_parameters():
+            assert torch.allclose(p.detach(), ref_p[k].detach(), rtol=1e-5, atol=1e-6), (mode, k)
+        return m, opt
+
+    for mode in ("plain", "accumulate", "clip_torch", "clip_flat", "replaced"):
+        m, opt = run(mode)
+    sd = opt.state_dict()
+    m2 = build(cfg, 0, "fp32")
+    opt2 = FlatAdamW(m2, lr=5.0)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 1 and opt2.lr == 1e-3
+    assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v)
+    with pytest.raises(RuntimeError):
+        opt2.step()                                              # no gradients yet

@@ -11,7 +11,7 @@ from .focal_r import FocalRLoss, focal_r_loss           # noqa: F401
 from ._lib import VitGridError                          # noqa: F401
 from .parallel import DataParallel                      # noqa: F401
 from .optim import FlatAdamW                            # noqa: F401
-from .pipeline import HostPipeline                      # noqa: F401
+from .pipeline import HostPipeline, pack_host           # noqa: F401
 from .eval_metrics import EvalMetrics                   # noqa: F401
 
 __version__ = "0.1.0"

@@ -54,11 +54,16 @@ def load(build_if_missing: bool = True):
         return _lib
     path = _build.LIB_PATH
     if build_if_missing and _build.is_stale():
-        try:
-            _build.build_library()
-        except Exception as e:  # pragma: no cover - depends on toolchain
-            if not os.path.exists(path):
-                raise VitGridError(f"libvitgrid.so is missing and could not be built: {e}") from e
+        # a stale binary is never loaded against the freshly parsed header: rebuild (under a file lock: the ranks of a
+        # multi-process job all arrive here) or fail.  A box without nvcc runs the prebuilt .so that travelled with the tree.
+        if _build.have_nvcc():
+            try:
+                _build.build_library()
+            except Exception as e:
+                raise VitGridError(f"libvitgrid.so is missing or older than its sources and the rebuild failed: {e}") from e
+        elif os.path.exists(path):
+            import warnings
+            warnings.warn("libvitgrid.so is older than its sources and nvcc is not available to rebuild it")
     if not os.path.exists(path):
         raise VitGridError(f"{path} not found: run `python __graft_entry__.py build` (no CPU fallback exists)")
     lib = ctypes.CDLL(path)
@@ -97,6 +102,19 @@ def call(name: str, *args):
         rc = getattr(lib, name)(*args)
     if rc != 0:
         raise VitGridError(f"{name} failed: {lib.vg_last_error().decode(errors='replace')}")
+
+
+def raise_device_errors():
+    """raise what kernels of EARLIER calls flagged (vg_device_error; meaningful for work that has completed)"""
+    if _lib is None:
+        return
+    code = _lib.vg_device_error(0)
+    if code:
+        _lib.vg_device_error(1)
+        if code & 1:
+            raise IndexError("a timestamp's month / day / hour was outside the embedding tables 13 / 32 / 25 "
+                             "(metnet3.py:392); the affected predictions are NaN")
+        raise VitGridError(f"device-side error word {code:#x}")
 
 
 def launch_count() -> int:

@@ -25,6 +25,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libvitgrid.so cannot be built (there is no CPU fallback)")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def _newest_source_mtime() -> float:
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vitgrid.h")]
     return max(os.path.getmtime(f) for f in files if os.path.isfile(f))
@@ -38,7 +46,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)                # one builder at a time (torchrun ranks share the tree)
+        if not force and not is_stale():                # another process built it while this one waited
+            return LIB_PATH
+        return _build_locked(nvcc, verbose)
+
+
+def _build_locked(nvcc: str, verbose: bool) -> str:
+    objdir = os.path.join(HERE, "build", f"obj.{os.getpid()}")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src: str) -> str:
@@ -55,11 +73,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
     r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIB_PATH
 
 

@@ -28,6 +28,21 @@ int check_launch(const char* what) {
   return 0;
 }
 
+static int* g_deverr_host = nullptr;
+static int* g_deverr_dev = nullptr;
+
+int* device_error_ptr() {
+  if (!g_deverr_host) {
+    int* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *h = 0;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return nullptr; }
+    g_deverr_host = h; g_deverr_dev = d;
+  }
+  return g_deverr_dev;
+}
+
 static EpiParams epi_zero() {
   EpiParams ep;
   memset(&ep, 0, sizeof(ep));
@@ -46,6 +61,13 @@ long long vg_launch_count(void) { return (long long)g_launches; }
 
 const char* vg_last_error(void) { return g_err; }
 
+int vg_device_error(int clear) {
+  if (!g_deverr_host) return 0;
+  const int v = *reinterpret_cast<volatile int*>(g_deverr_host);
+  if (clear) *reinterpret_cast<volatile int*>(g_deverr_host) = 0;
+  return v;
+}
+
 int vg_device_check(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -61,7 +83,13 @@ long long vg_pg_pixels(int N, int HP, int WP) { return make_pgeom(N, HP, WP).pix
 
 int vg_prepare_fwd(int dtype, const float* x, const long long* xstride, int B, int T, int C, int H, int W, int pad_top,
                    int pad_left, int HP, int WP, int Cpad, float pm_mean, float pm_std, void* out, void* stream) {
-  return prepare_run(dtype, x, xstride, B, T, C, H, W, pad_top, pad_left, HP, WP, Cpad, pm_mean, pm_std, out,
+  return prepare_run(dtype, x, 0, 0, xstride, B, T, C, H, W, pad_top, pad_left, HP, WP, Cpad, pm_mean, pm_std, out,
+                     (cudaStream_t)stream);
+}
+
+int vg_prepare_packed_fwd(int dtype, const void* x_bf16, const long long* xstride, int B, int T, int C, int H, int W, int pad_top,
+                          int pad_left, int HP, int WP, int Cpad, void* out, void* stream) {
+  return prepare_run(dtype, x_bf16, 1, 1, xstride, B, T, C, H, W, pad_top, pad_left, HP, WP, Cpad, 0.f, 1.f, out,
                      (cudaStream_t)stream);
 }
 
@@ -75,6 +103,7 @@ int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long lo
   p.emb_lead = emb_lead; p.emb_m = emb_month; p.emb_d = emb_day; p.emb_h = emb_hour;
   p.w3 = w3; p.w1 = w1; p.c_in = c_in; p.c_data = c_data; p.Cout = Cout;
   p.temb = temb; p.cond = cond; p.tt = tt; p.tres = tres;
+  p.err = device_error_ptr();
   return time_terms_run(p, (cudaStream_t)stream);
 }
 
@@ -223,6 +252,12 @@ static int make_attn_geom(AttnGeom& g, int N, int Hl, int Wl, int C, int win, in
   if (win <= 0 || Hl % win || Wl % win) return set_error("attention: map %dx%d not divisible by window %d", Hl, Wl, win);
   g.N = N; g.Hl = Hl; g.Wl = Wl; g.C = C; g.win = win; g.R = R; g.X = Hl / win; g.Y = Wl / win; g.grid_mode = grid_mode;
   return 0;
+}
+
+int vg_attn_partition_debug(int N, int Hl, int Wl, int win, int R, int grid_mode, long long* pixel_index, void* stream) {
+  AttnGeom g;
+  if (make_attn_geom(g, N, Hl, Wl, 128, win, R, grid_mode)) return 1;
+  return attn_partition_debug_run(g, pixel_index, (cudaStream_t)stream);
 }
 
 int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, int N, int Hl,

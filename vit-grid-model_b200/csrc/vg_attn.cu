@@ -12,13 +12,18 @@
 
 namespace vg {
 
-// token row r = wdx*S + tok,  wdx = n*nwin + x*Y + y  (windows field-major, x-major: maxvit.py:306-307)
-__device__ __forceinline__ long long token_pixel(const AttnGeom& g, int wi, int t) {
-  const int a = t / g.win, b = t - a * g.win;
-  const int x = wi / g.Y, y = wi - x * g.Y;
-  const int ph = g.grid_mode ? a * g.X + x : x * g.win + a;
-  const int pw = g.grid_mode ? b * g.Y + y : y * g.win + b;
-  return (long long)ph * g.Wl + pw;
+// token row r = wdx*S + tok,  wdx = n*nwin + x*Y + y  (windows field-major, x-major: maxvit.py:306-307); the pixel of a
+// window token is attn_token_pixel (vg_host.h)
+
+// test hook: the global pixel index every token row gathers from / scatters to (-1 for register-token rows)
+__global__ void attn_partition_debug_kernel(const AttnGeom g, long long* __restrict__ out, long long rows) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int S = g.S(), nwin = g.nwin();
+  const long long wdx = r / S;
+  const int tok = (int)(r - wdx * S);
+  const int n = (int)(wdx / nwin), wi = (int)(wdx - (long long)n * nwin);
+  out[r] = tok < g.R ? -1 : (long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R);
 }
 
 template <typename T>
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
       v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
     }
   } else {
-    const T* src = x + ((long long)n * g.Hl * g.Wl + token_pixel(g, wi, tok - g.R)) * C;
+    const T* src = x + ((long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R)) * C;
     for (int i = 0; i < nv; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[4 * i + j] = Act<T>::ld(src + i * 128 + lane * 4 + j);
@@ -150,6 +155,12 @@ int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_fiel
   if (dtype == 0) attn_gather_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<bf16*>(tokens), rows);
   else attn_gather_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<float*>(tokens), rows);
   return check_launch("attn_gather_kernel");
+}
+
+int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st) {
+  const long long rows = (long long)g.N * g.nwin() * g.S();
+  attn_partition_debug_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(g, out, rows);
+  return check_launch("attn_partition_debug_kernel");
 }
 
 template <typename T, int DH>

@@ -186,11 +186,7 @@ __device__ __forceinline__ TokRow tok_row(const FusedAttnParams& p, long long ti
   if (win_valid && i < SEQ) {
     if (i < REG) r.src = p.reg_in + (p.reg_per_field ? (long long)r.n * REG * C : 0) + (long long)i * C;
     else {
-      const int ti = i - REG, ai = ti / WIN, bi = ti - ai * WIN;
-      const int xw = wi / g.Y, yw = wi - xw * g.Y;
-      const int ph = g.grid_mode ? ai * g.X + xw : xw * WIN + ai;     // maxvit.py:322 / :298
-      const int pw = g.grid_mode ? bi * g.Y + yw : yw * WIN + bi;
-      r.pix = (long long)r.n * g.Hl * g.Wl + (long long)ph * g.Wl + pw;
+      r.pix = (long long)r.n * g.Hl * g.Wl + attn_token_pixel(g, wi, i - REG);     // maxvit.py:298 / :322
       r.src = p.x + r.pix * C;
     }
   }

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) time_emb_bwd_kernel(const TimeBwdParams p
 // embedding gradients (transpose of time_embed_kernel, metnet3.py:389-416): dtemb (N, le+3te) and dcond (N, le)
 __global__ void time_embed_bwd_kernel(const float* __restrict__ dtemb, const float* __restrict__ dcond, const float* __restrict__ ts,
                                       long long ts_sB, long long ts_sT, long long ts_sF, int B, int L, int le, int te,
-                                      float* __restrict__ d_lead, float* __restrict__ d_m, float* __restrict__ d_d, float* __restrict__ d_h) {
+                                      float* __restrict__ d_lead, float* __restrict__ d_m, float* __restrict__ d_d, float* __restrict__ d_h, int* err) {
   const int N = B * L, ntc = le + 3 * te;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * ntc) return;
@@ -369,6 +369,8 @@ __global__ void time_embed_bwd_kernel(const float* __restrict__ dtemb, const flo
     const int b = idx / L;
     const int k = (int)ts[(long long)b * ts_sB + 6 * ts_sT + (long long)(1 + which) * ts_sF];
     float* e = which == 0 ? d_m : (which == 1 ? d_d : d_h);
+    const int rows = which == 0 ? 13 : (which == 1 ? 32 : 25);
+    if (k < 0 || k >= rows) { if (err) atomicOr(err, VG_DEVERR_TIMESTAMP); return; }   // forward already poisoned this field
     atomicAdd(e + k * te + col, g);
   }
 }
@@ -538,7 +540,7 @@ int time_terms_bwd_run(const float* border, const float* sumD, const float* tres
 int time_embed_bwd_run(const float* dtemb, const float* dcond, const float* ts, long long sB, long long sT, long long sF, int B,
                        int L, int le, int te, float* d_lead, float* d_m, float* d_d, float* d_h, cudaStream_t st) {
   const int N = B * L, ntc = le + 3 * te;
-  time_embed_bwd_kernel<<<nblk((long long)N * ntc, 128), 128, 0, st>>>(dtemb, dcond, ts, sB, sT, sF, B, L, le, te, d_lead, d_m, d_d, d_h);
+  time_embed_bwd_kernel<<<nblk((long long)N * ntc, 128), 128, 0, st>>>(dtemb, dcond, ts, sB, sT, sF, B, L, le, te, d_lead, d_m, d_d, d_h, device_error_ptr());
   return check_launch("time_embed_bwd_kernel");
 }
 

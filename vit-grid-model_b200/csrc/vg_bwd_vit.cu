@@ -431,14 +431,6 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ d
 // ================================================================================================
 // attention backward
 // ================================================================================================
-__device__ __forceinline__ long long tok_pixel(const AttnGeom& g, int wi, int t) {
-  const int a = t / g.win, b = t - a * g.win;
-  const int x = wi / g.Y, y = wi - x * g.Y;
-  const int ph = g.grid_mode ? a * g.X + x : x * g.win + a;
-  const int pw = g.grid_mode ? b * g.Y + y : y * g.win + b;
-  return (long long)ph * g.Wl + pw;
-}
-
 // gradient wrt the out-projection output (maxvit.py:218-219, 310-319): window rows gather dX_out through the partition
 // map, register rows take dreg (N,R,C) * reg_scale (the mean over windows, maxvit.py:326) or zero.
 __global__ void __launch_bounds__(256) attn_out_bwd_gather_kernel(const float* __restrict__ dx_out, const float* __restrict__ dreg, float reg_scale,
@@ -454,7 +446,7 @@ __global__ void __launch_bounds__(256) attn_out_bwd_gather_kernel(const float* _
     if (tok < g.R) {
       if (dreg) { v = *reinterpret_cast<const float4*>(dreg + ((long long)n * g.R + tok) * C + c); v.x *= reg_scale; v.y *= reg_scale; v.z *= reg_scale; v.w *= reg_scale; }
     } else {
-      v = *reinterpret_cast<const float4*>(dx_out + ((long long)n * g.Hl * g.Wl + tok_pixel(g, wi, tok - g.R)) * C + c);
+      v = *reinterpret_cast<const float4*>(dx_out + ((long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R)) * C + c);
     }
     if (drop.thresh) {                                       // the to_out dropout mask of the forward pass (maxvit.py:151)
       const uint32_t hsh = drop_hash(drop.seed, drop_row(wdx, tok), drop_group_out(drop.salt, c >> 2));
@@ -1235,7 +1227,7 @@ __global__ void __launch_bounds__(256) attn_gather_bwd_kernel(const AttnGatherBw
     if (n != n_cur) { flush(); n_cur = n; }
     const float* src; long long pix = -1;
     if (tok < g.R) src = p.reg + (p.reg_per_field ? (long long)n * g.R * C : 0) + (long long)tok * C;
-    else { pix = (long long)n * g.Hl * g.Wl + tok_pixel(g, wi, tok - g.R); src = p.x + pix * C; }
+    else { pix = (long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R); src = p.x + pix * C; }
     const float4 xv = *reinterpret_cast<const float4*>(src + c0);
     float v[4] = {xv.x, xv.y, xv.z, xv.w};
     const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);

@@ -44,6 +44,29 @@ struct PGeom {
 inline PGeom make_pgeom(int N, int HP, int WP) { PGeom g; g.HP = HP; g.WP = WP; g.P = WP + 1; g.R = HP + 1; g.N = N; return g; }
 
 // ----------------------------------------------------------------------------------------------
+// attention geometry and the window / grid partition map
+// ----------------------------------------------------------------------------------------------
+struct AttnGeom {
+  int N, Hl, Wl, C;        // fields, low-res map, channels
+  int win, R, X, Y;        // window size, register tokens, windows per column / row
+  int grid_mode;           // 0 block partition (maxvit.py:298), 1 grid partition (maxvit.py:322)
+  __host__ __device__ int S() const { return R + win * win; }
+  __host__ __device__ int nwin() const { return X * Y; }
+};
+// THE partition map of the package (every kernel that gathers or scatters tokens calls this one function; the device
+// test vg_attn_partition_debug dumps it against the einops-generated golden tables): pixel offset, inside its field, of
+// window token t (0 .. win*win-1, row-major inside the window) of window wi = x*Y + y.
+//   block partition  'b d (x w1) (y w2) -> b x y w1 w2 d'  (maxvit.py:298):  pixel (x*win + w1, y*win + w2)
+//   grid partition   'b d (w1 x) (w2 y) -> b x y w1 w2 d'  (maxvit.py:322):  pixel (w1*X + x,  w2*Y + y)
+__host__ __device__ __forceinline__ long long attn_token_pixel(const AttnGeom& g, int wi, int t) {
+  const int a = t / g.win, b = t - a * g.win;
+  const int x = wi / g.Y, y = wi - x * g.Y;
+  const int ph = g.grid_mode ? a * g.X + x : x * g.win + a;
+  const int pw = g.grid_mode ? b * g.Y + y : y * g.win + b;
+  return (long long)ph * g.Wl + pw;
+}
+
+// ----------------------------------------------------------------------------------------------
 // dtype traits: activations are bf16 ("bf16 mode") or float ("fp32 mode")
 // ----------------------------------------------------------------------------------------------
 template <typename T> struct Act;

@@ -369,11 +369,9 @@ __device__ __forceinline__ void epi_attn_out(const EpiParams& ep, long long row,
         dreg = ep.reg_out + (wdx * ep.R + tok) * C;
       }
     } else {
-      const int t = tok - ep.R, a = t / ep.win, b = t - a * ep.win;
-      const int x = wi / ep.Y, y = wi - x * ep.Y;
-      const int ph = ep.grid_mode ? a * ep.X + x : x * ep.win + a;      // maxvit.py:322 / :298
-      const int pw = ep.grid_mode ? b * ep.Y + y : y * ep.win + b;
-      const long long pix = (long long)n * ep.Hl * ep.Wl + (long long)ph * ep.Wl + pw;
+      AttnGeom g;
+      g.Hl = ep.Hl; g.Wl = ep.Wl; g.win = ep.win; g.X = ep.X; g.Y = ep.Y; g.grid_mode = ep.grid_mode;
+      const long long pix = (long long)n * ep.Hl * ep.Wl + attn_token_pixel(g, wi, tok - ep.R);     // maxvit.py:298 / :322
       rsrc = reinterpret_cast<const T*>(ep.x_in) + pix * C;
       dst = reinterpret_cast<T*>(ep.out) + pix * C;
     }

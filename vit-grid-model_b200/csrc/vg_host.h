@@ -13,6 +13,11 @@ struct EpiParams;
 int set_error(const char* fmt, ...);
 // cudaGetLastError() after a launch; 0 when clean
 int check_launch(const char* what);
+// Sticky device-side error word (one mapped, pinned int shared by every device of the process): kernels that meet input a
+// PyTorch op would have raised on (e.g. an embedding row out of range) OR a bit into it instead of touching memory; the host reads
+// it with vg_device_error() after a synchronisation.  Returns the device-visible pointer (nullptr if the allocation failed).
+int* device_error_ptr();
+enum { VG_DEVERR_TIMESTAMP = 1 };
 
 int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, int train, cudaStream_t st);
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
@@ -20,12 +25,13 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st);
 
 struct PrepParams {
-  const float* x;
+  const void* x;                  // fp32, or bf16 (packed host batches)
   long long sB, sT, sC, sH, sW;   // element strides of x
   int B, T, C, H, W;
   int pad_top, pad_left;
   int Cpad;
-  float mean, inv_std_unused, stdv;
+  float mean, stdv;
+  int prestd;                     // 1: the PM2.5 channels of x are already standardised
   PGeom pg;
   int w_fast;                     // 1: x contiguous along W (tile transposed through smem along w)
 };
@@ -42,6 +48,7 @@ struct TimeParams {
   float* cond;             // (N, le)
   float* tt;               // (N, 9, Cout)
   float* tres;             // (N, Cout)
+  int* err;                // device error word (device_error_ptr())
 };
 
 struct StemParams {
@@ -56,8 +63,8 @@ struct StemParams {
   PGeom pgB, pgN;
 };
 
-int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, int C, int H, int W, int pad_top, int pad_left,
-                int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st);
+int prepare_run(int dtype, const void* x, int x_bf16, int prestd, const long long* xs, int B, int T, int C, int H, int W, int pad_top,
+                int pad_left, int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st);
 int time_terms_run(const TimeParams& p, cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
@@ -85,14 +92,8 @@ int focal_r_fwd_run(const float* pred, const float* tgt, long long n, float beta
 int focal_r_bwd_run(const float* pred, const float* tgt, long long n, float beta, float gamma, int mse, float gscale,
                     float* grad, cudaStream_t st);
 
-// attention (vg_attn.cu)
-struct AttnGeom {
-  int N, Hl, Wl, C;        // fields, low-res map, channels
-  int win, R, X, Y;        // window size, register tokens, windows per column / row
-  int grid_mode;           // 0 block partition (maxvit.py:298), 1 grid partition (maxvit.py:322)
-  __host__ __device__ int S() const { return R + win * win; }
-  __host__ __device__ int nwin() const { return X * Y; }
-};
+// attention (vg_attn.cu); AttnGeom / attn_token_pixel live in vg_common.cuh
+int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st);
 int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
                     float eps, void* tokens, cudaStream_t st);
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,

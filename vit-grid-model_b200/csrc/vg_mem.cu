@@ -36,7 +36,12 @@ template <> struct Ld4<bf16> {
 // The output buffer is zero-filled first (pads, channel padding); this kernel writes frame pixels with a source.
 // ================================================================================================
 
-template <typename T>
+__device__ __forceinline__ float ld_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_in(const bf16* p) { return __bfloat162float(*p); }
+
+// TIn = float: the reference's input tensor; TIn = bf16: a batch packed on the host by HostPipeline.pack_host (PM2.5 channels
+// already standardised in fp32, then everything rounded to bf16 -- p.prestd = 1)
+template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __restrict__ out) {
   __shared__ float tile[64][33];
   const int w0 = blockIdx.x * 32;
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
   const int cblocks = p.Cpad / 64;
   const int b = blockIdx.z / cblocks, ch0 = (blockIdx.z - b * cblocks) * 64;
   const int TC = p.T * p.C;
-  const float* xb = p.x + (long long)b * p.sB + (long long)h * p.sH;
+  const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (long long)b * p.sB + (long long)h * p.sH;
   for (int i = threadIdx.x; i < 64 * 32; i += 256) {
     int cl, wl;
     if (p.w_fast) { wl = i & 31; cl = i >> 5; } else { cl = i & 63; wl = i >> 6; }
@@ -52,8 +57,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
     float v = 0.f;
     if (ch < TC && w < p.W) {
       const int t = ch / p.C, c = ch - t * p.C;
-      v = xb[(long long)t * p.sT + (long long)c * p.sC + (long long)w * p.sW];
-      if (c == 4 || c == 10 || c == 16 || c == 22) v = (v - p.mean) / p.stdv;     // metnet3.py:362,370
+      v = ld_in(xb + (long long)t * p.sT + (long long)c * p.sC + (long long)w * p.sW);
+      if (!p.prestd && (c == 4 || c == 10 || c == 16 || c == 22)) v = (v - p.mean) / p.stdv;     // metnet3.py:362,370
     }
     tile[cl][wl] = v;
   }
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
 // prepare for inputs whose (H, W) planes are contiguous (the layout the reference's loader produces after its permute,
 // evaluation_vit.py:248-249): tiles run over the FLAT pixel index h*W + w, so a 67-wide row does not waste a third of
 // every 32-column tile, and each thread has its eight loads in flight before the transposing store.
-template <typename T>
+template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T* __restrict__ out) {
   constexpr int PT = 4;                                            // 32-pixel tiles per block: 32 loads in flight per thread
   __shared__ float tile[PT][64][33];
@@ -80,19 +85,19 @@ __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T
   const int cblocks = p.Cpad / 64;
   const int b = blockIdx.y / cblocks, ch0 = (blockIdx.y - b * cblocks) * 64;
   const int TC = p.T * p.C;
-  const float* xb = p.x + (long long)b * p.sB;
+  const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (long long)b * p.sB;
   const int pl = threadIdx.x & 31, cl0 = threadIdx.x >> 5;         // lane = pixel (coalesced 128-byte rows), warp = channel
   float v[PT][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = ch0 + cl0 + 8 * k;
     const int t = ch / p.C, c = ch - t * p.C;
-    const float* xc = xb + (long long)t * p.sT + (long long)c * p.sC;
-    const bool pm = c == 4 || c == 10 || c == 16 || c == 22;       // metnet3.py:362,370
+    const TIn* xc = xb + (long long)t * p.sT + (long long)c * p.sC;
+    const bool pm = !p.prestd && (c == 4 || c == 10 || c == 16 || c == 22);       // metnet3.py:362,370
 #pragma unroll
     for (int u = 0; u < PT; ++u) {
       const int px = px0 + u * 32 + pl;
-      v[u][k] = (ch < TC && px < HW) ? __ldg(xc + px) : 0.f;
+      v[u][k] = (ch < TC && px < HW) ? ld_in(xc + px) : 0.f;
     }
     if (pm && ch < TC) {
 #pragma unroll
@@ -143,7 +148,11 @@ __global__ void time_embed_kernel(const TimeParams p) {
     const float tv = p.ts[(long long)b * p.ts_sB + 6 * p.ts_sT + (long long)(1 + which) * p.ts_sF];   // time index 6 (Q2)
     const int k = (int)tv;                            // .int() truncation (metnet3.py:392)
     const float* e = which == 0 ? p.emb_m : (which == 1 ? p.emb_d : p.emb_h);
-    v = e[k * p.te + col];
+    const int rows = which == 0 ? 13 : (which == 1 ? 32 : 25);      // nn.Embedding(12+1 | 31+1 | 24+1) (metnet3.py:262-266)
+    // nn.Embedding raises IndexError on an out-of-range row; a kernel cannot: the lookup is skipped, the field is poisoned
+    // with NaN (visible in its predictions, evaluation_vit.py:256) and the sticky device flag is raised (vg_device_error)
+    if (!(tv > -1.0f && tv < (float)rows)) { v = __int_as_float(0x7fc00000); if (p.err) atomicOr(p.err, VG_DEVERR_TIMESTAMP); }
+    else v = e[k * p.te + col];
   }
   p.temb[i] = v;
 }
@@ -668,26 +677,28 @@ __global__ void __launch_bounds__(256) focal_r_bwd_kernel(const float* __restric
 // ================================================================================================
 static inline unsigned nblk(long long total, int per) { return (unsigned)((total + per - 1) / per); }
 
-int prepare_run(int dtype, const float* x, const long long* xs, int B, int T, int C, int H, int W, int pad_top, int pad_left,
-                int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st) {
+int prepare_run(int dtype, const void* x, int x_bf16, int prestd, const long long* xs, int B, int T, int C, int H, int W, int pad_top,
+                int pad_left, int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st) {
   if (Cpad % 64 || Cpad < T * C) return set_error("prepare: Cpad=%d must be a multiple of 64 and >= T*C=%d", Cpad, T * C);
   PrepParams p;
   p.x = x; p.sB = xs[0]; p.sT = xs[1]; p.sC = xs[2]; p.sH = xs[3]; p.sW = xs[4];
   p.B = B; p.T = T; p.C = C; p.H = H; p.W = W; p.pad_top = pad_top; p.pad_left = pad_left; p.Cpad = Cpad;
-  p.mean = mean; p.stdv = stdv; p.inv_std_unused = 0.f; p.pg = make_pgeom(B, HP, WP); p.w_fast = (xs[4] == 1);
+  p.mean = mean; p.stdv = stdv; p.prestd = prestd; p.pg = make_pgeom(B, HP, WP); p.w_fast = (xs[4] == 1);
   const size_t esz = dtype == 0 ? 2 : 4;
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)p.pg.pixels() * Cpad * esz, st);
   if (e != cudaSuccess) return set_error("prepare memset: %s", cudaGetErrorString(e));
-  if (xs[4] == 1 && xs[3] == W) {                              // contiguous (H, W) planes
-    dim3 gridf((unsigned)((H * W + 127) / 128), (unsigned)(B * (Cpad / 64)));
-    if (dtype == 0) prepare_flat_kernel<bf16><<<gridf, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
-    else prepare_flat_kernel<float><<<gridf, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
-    return check_launch("prepare_flat_kernel");
-  }
+  const bool flat = xs[4] == 1 && xs[3] == W;                  // contiguous (H, W) planes
+  dim3 gridf((unsigned)((H * W + 127) / 128), (unsigned)(B * (Cpad / 64)));
   dim3 grid((W + 31) / 32, H, B * (Cpad / 64));
-  if (dtype == 0) prepare_kernel<bf16><<<grid, 256, 0, st>>>(p, reinterpret_cast<bf16*>(out));
-  else prepare_kernel<float><<<grid, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
-  return check_launch("prepare_kernel");
+#define VG_PREP(TO, TI)                                                                                             \
+  do {                                                                                                              \
+    if (flat) prepare_flat_kernel<TO, TI><<<gridf, 256, 0, st>>>(p, reinterpret_cast<TO*>(out));                    \
+    else prepare_kernel<TO, TI><<<grid, 256, 0, st>>>(p, reinterpret_cast<TO*>(out));                               \
+  } while (0)
+  if (dtype == 0) { if (x_bf16) VG_PREP(bf16, bf16); else VG_PREP(bf16, float); }
+  else { if (x_bf16) VG_PREP(float, bf16); else VG_PREP(float, float); }
+#undef VG_PREP
+  return check_launch(flat ? "prepare_flat_kernel" : "prepare_kernel");
 }
 
 int time_terms_run(const TimeParams& p, cudaStream_t st) {

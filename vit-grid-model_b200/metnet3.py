@@ -69,6 +69,17 @@ def _pack_conv3x3(w, dtype, c_keep=None, c_pad=None):
     return out.reshape(co, 9 * c_pad).contiguous()
 
 
+def _check_timestamps(ts):
+    """month / day / hour of time index 6 (metnet3.py:405) must be valid rows of nn.Embedding(13 | 32 | 25)
+    (metnet3.py:262-266); the reference raises IndexError from the lookup"""
+    if ts.dim() != 3 or ts.shape[1] < 7 or ts.shape[2] < 4:
+        raise ValueError("timestamps must be (B, >=7, 4) [year, month, day, hour]")
+    t = ts[:, 6, 1:4].to(torch.float32)
+    hi = torch.tensor([13.0, 32.0, 25.0])
+    if not bool(((t > -1.0) & (t < hi)).all()):
+        raise IndexError("timestamps[:, 6, 1:4] (month, day, hour) outside the embedding tables 13 / 32 / 25 (metnet3.py:392)")
+
+
 class MetNet3(nn.Module):
     def __init__(
         self,
@@ -157,17 +168,34 @@ class MetNet3(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def set_precision(self, precision: str):
-        """'bf16' (default): bf16 storage + tcgen05 kind::f16 for the 3x3-conv encoder/decoder, fp32 storage + kind::tf32
-        for the MaxViT block; 'bf16_all': bf16 everywhere; 'fp32': exact-fp32 SIMT path."""
-        self.compute_dtype = {"bf16": torch.bfloat16, "bf16_all": torch.bfloat16, "fp32": torch.float32}[precision]
-        self.vit.set_precision(precision)
-        self.precision = precision
+        """'bf16' (default): bf16 storage + tcgen05 kind::f16 for the 3x3-conv encoder/decoder; the MaxViT block keeps fp32
+        storage with 16-bit / tf32 tensor-core operands at 128 channels, and runs exact-fp32 GEMMs in wider networks (stacked
+        tf32 layers of a 512-channel, depth-4 backbone were measured outside the 1e-2 tolerance; 'bf16_tf32' selects them
+        anyway); 'bf16_all': bf16 everywhere; 'fp32': exact-fp32 SIMT path."""
+        self.compute_dtype = {"bf16": torch.bfloat16, "bf16_tf32": torch.bfloat16, "bf16_all": torch.bfloat16,
+                              "fp32": torch.float32}[precision]
+        vit_precision = precision
+        if precision == "bf16" and self.n_start_channels > 128:
+            vit_precision = "fp32"
+        elif precision == "bf16_tf32":
+            vit_precision = "bf16"
+        self.vit.set_precision(vit_precision)
+        self.precision = "bf16" if precision == "bf16_tf32" else precision
+        self.invalidate_packed()
         return self
+
+    def invalidate_packed(self):
+        """Drop the kernel-layout copies of the weights (re-derived on the next forward).  The caches are keyed on
+        (data_ptr, version) of every parameter, which in-place writes through ``.data`` -- broadcasts, EMA swaps, raw kernel
+        updates such as FlatAdamW -- do not change: call this after any such write."""
+        self._packed_key = None
+        self.vit._packed_key = None
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         # checkpoints saved from nn.DataParallel carry a 'module.' prefix (evaluation_vit.py:107-109)
         if state_dict and all(k.startswith("module.") for k in state_dict):
             state_dict = {k[len("module."):]: v for k, v in state_dict.items()}
+        self.invalidate_packed()
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def pad_values(self):
@@ -229,7 +257,7 @@ class MetNet3(nn.Module):
                        out_copy=out_copy, head=head)
         return None if head else t2
 
-    def _forward_chunk(self, x, b0, b1, terms, P, dtype, out):
+    def _forward_chunk(self, x, b0, b1, terms, P, dtype, out, packed=False):
         """fields of samples [b0,b1) of x -> out[b0:b1]"""
         temb, cond_all, tt_all, tres_all = terms
         L, C = self.end_lead_time, self.n_start_channels
@@ -243,7 +271,7 @@ class MetNet3(nn.Module):
         mixed = dtype != torch.float32            # bf16 activations: skip connections travel as separate fp32 copies
         # ---- stem, once per sample
         s0 = P["resnet1"][0]
-        xin = ops.prepare(x[b0:b1], pads, HP, WP, P["c_pad"], self.pm25_mean, self.pm25_std, dtype)
+        xin = ops.prepare(x[b0:b1], pads, HP, WP, P["c_pad"], self.pm25_mean, self.pm25_std, dtype, packed=packed)
         raw3 = ops.gemm(xin, s0["w1"], ntaps=9, tap_shift=ops.conv_tap_shifts(WP), out_f32=True)
         rawres = ops.gemm(xin, s0["wres"], out_f32=True)
         del xin
@@ -336,13 +364,35 @@ class MetNet3(nn.Module):
             raise ValueError("timestamps is required (metnet3.py:405)")
         if not x.is_cuda:
             raise _lib.VitGridError("vit_grid_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        _lib.raise_device_errors()                     # e.g. an out-of-range timestamp met by an earlier call's kernels
+        if not timestamps.is_cuda:                      # host timestamps are validated for free, like nn.Embedding would
+            _check_timestamps(timestamps)
+        with torch.cuda.device(x.device):               # kernels launch on x's device and its current stream
+            return self._forward_impl(x, timestamps)
+
+    def forward_packed(self, x_packed, timestamps):
+        """inference on a batch packed by ``pipeline.pack_host`` (bf16, PM2.5 channels standardised before the rounding):
+        the same predictions, bit for bit, as ``forward`` on the fp32 tensor in the default 'bf16' precision"""
+        _lib.require_device()
+        if self._unsupported:
+            raise NotImplementedError(self._unsupported)
+        if self.training or self.compute_dtype != torch.bfloat16 or type(self) is not MetNet3:
+            raise NotImplementedError("packed bf16 batches feed the bf16 inference path of MetNet3 only")
+        if not x_packed.is_cuda or x_packed.dtype != torch.bfloat16:
+            raise _lib.VitGridError("forward_packed takes a CUDA bf16 tensor produced by pipeline.pack_host")
+        _lib.raise_device_errors()
+        with torch.cuda.device(x_packed.device):
+            return self._forward_impl(x_packed, timestamps, packed=True)
+
+    def _forward_impl(self, x, timestamps, packed=False):
         B, T, Cv, H, W = x.shape
         assert (T, Cv, H, W) == (self.window_size, self.n_variables, self.input_height, self.input_width)
         pl, pr, pt, pb = self.pad_values()
         if 0 in (pr, pb):
             raise ValueError("the reference's unpad (metnet3.py:337) needs non-zero right/bottom pads")
         dtype = self.compute_dtype
-        x = x.float()
+        if not packed:
+            x = x.float()
         ts = timestamps.to(device=x.device, dtype=torch.float32)
         if self.training:
             return self._forward_train(x, ts)
@@ -355,7 +405,7 @@ class MetNet3(nn.Module):
         out = torch.empty(B, L, H, W, dtype=torch.float32, device=x.device)
         step = max(1, self.max_fields[dtype] // L)
         for b0 in range(0, B, step):
-            self._forward_chunk(x, b0, min(B, b0 + step), terms, P, dtype, out)
+            self._forward_chunk(x, b0, min(B, b0 + step), terms, P, dtype, out, packed=packed)
         return out
 
 

@@ -56,14 +56,19 @@ def pg_to_nchw(buf, N, H, W):
     return v.permute(0, 3, 1, 2).contiguous()
 
 
-def prepare(x, cfg_pads, HP, WP, Cpad, mean, std, dtype):
+def prepare(x, cfg_pads, HP, WP, Cpad, mean, std, dtype, packed=False):
+    """packed=True: x is a bf16 batch packed on the host (pipeline.pack_host), PM2.5 channels already standardised"""
     B, T, C, H, W = x.shape
-    assert x.dtype == torch.float32 and x.is_cuda
+    assert x.is_cuda and x.dtype == (torch.bfloat16 if packed else torch.float32)
     out = torch.empty(pg_pixels(B, HP, WP), Cpad, dtype=dtype, device=x.device)
     strides = (ctypes.c_longlong * 5)(*x.stride())
     pl, _, pt, _ = cfg_pads
-    _lib.call("vg_prepare_fwd", DT_CODE[dtype], x.data_ptr(), strides, B, T, C, H, W, pt, pl, HP, WP, Cpad,
-              float(mean), float(std), out.data_ptr(), _st())
+    if packed:
+        _lib.call("vg_prepare_packed_fwd", DT_CODE[dtype], x.data_ptr(), strides, B, T, C, H, W, pt, pl, HP, WP, Cpad,
+                  out.data_ptr(), _st())
+    else:
+        _lib.call("vg_prepare_fwd", DT_CODE[dtype], x.data_ptr(), strides, B, T, C, H, W, pt, pl, HP, WP, Cpad,
+                  float(mean), float(std), out.data_ptr(), _st())
     return out
 
 
@@ -134,6 +139,8 @@ def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy
                   float(hs), float(hm), H, W, pt, pl, _p(ho), scratch.data_ptr(), scratch.numel(), _st())
         return out
     keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
+    _lib.TRACE_TAG = ("film" if film is not None else "plain") + ("+res" if res is not None else "") + \
+        ("+copy" if out_copy is not None else "") + ("+head" if head is not None else "")
     _lib.call("vg_conv3x3_ln_fwd", DT_CODE[dtype], x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
               ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP,
               _p(hw), float(hb), float(hs), float(hm), H, W, pt, pl, _p(ho), sp, sn, _st())

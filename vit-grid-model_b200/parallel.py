@@ -16,19 +16,18 @@ class DataParallel(nn.Module):
         super().__init__()
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("DataParallel needs an initialised torch.distributed process group (one process per GPU)")
-        self.module = module
+        self.module = module                            # state_dict keys carry the 'module.' prefix of the reference's nn.DataParallel checkpoints (evaluation_vit.py:107-109)
         self.process_group = process_group
         if broadcast:                                   # replicas start from rank 0's weights and buffers
-            for t in list(module.parameters()) + list(module.buffers()):
-                dist.broadcast(t.data, src=0, group=process_group)
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, src=0, group=process_group)
+            if hasattr(module, "invalidate_packed"):    # kernel-layout weight copies made before wrapping are stale now
+                module.invalidate_packed()
         module._grad_sync = GradSync(process_group)
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
-
-    def state_dict(self, *args, **kwargs):
-        """keys carry the 'module.' prefix like the reference's nn.DataParallel checkpoints (evaluation_vit.py:107-109)"""
-        return super().state_dict(*args, **kwargs)
 
 
 def shard_batch(B: int, rank: int, world: int):

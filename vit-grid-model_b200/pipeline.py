@@ -10,11 +10,32 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
+
+PM25_CHANNELS = (4, 10, 16, 22)                         # metnet3.py:362
+
+
+def pack_host(x: torch.Tensor, pm25_mean: float, pm25_std: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Data-loader side of the streaming path: (B,T,C,H,W) fp32 host tensor -> pinned bf16 host tensor holding exactly the
+    values the device `prepare` kernel derives from it in the default precision -- the PM2.5 channels standardised in
+    fp32 ((x - mean) / std, metnet3.py:369-373), then everything rounded to bf16 (round-to-nearest-even).  Feeding this to
+    ``HostPipeline`` halves the host->device bytes of a batch (422 instead of 844 MB at B=64) and leaves the predictions
+    bit-identical (tests/test_metnet3_gpu.py::test_packed_host_batches_bit_identical)."""
+    assert x.dtype == torch.float32 and not x.is_cuda and x.dim() == 5
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16).pin_memory()
+    out.copy_(x)
+    idx = [c for c in PM25_CHANNELS if c < x.shape[2]]
+    pm = (x[:, :, idx] - torch.tensor(pm25_mean, dtype=torch.float32)) / torch.tensor(pm25_std, dtype=torch.float32)
+    out[:, :, idx] = pm.to(torch.bfloat16)
+    return out
+
 
 class HostPipeline:
     """pipe = HostPipeline(model);  for y_host in pipe.run(batches): ...   where `batches` yields
     (x_host, timestamps_host[, out_host]) with pinned host tensors; `y_host` is a pinned (B, L, H, W) fp32 tensor that is
-    valid when it is yielded (the copy has completed)."""
+    valid when it is yielded (the copy has completed).  `x_host` is the reference's fp32 tensor or a bf16 batch from
+    ``pack_host`` (half the host->device bytes, same predictions)."""
 
     def __init__(self, model, depth: int = 2):
         self.model = model
@@ -59,7 +80,10 @@ class HostPipeline:
             except StopIteration:
                 nxt = None
             compute.wait_event(s["ready"])
-            y = self.model(s["x"], timestamps=s["ts"])
+            if s["x"].dtype == torch.bfloat16:
+                y = self.model.forward_packed(s["x"], s["ts"])
+            else:
+                y = self.model(s["x"], timestamps=s["ts"])
             s["free"].record(compute)
             done = torch.cuda.Event()
             done.record(compute)
@@ -75,8 +99,10 @@ class HostPipeline:
             while len(pending) > 1:                    # hand back results whose copy has certainly been issued one step ago
                 o, e = pending.pop(0)
                 e.synchronize()
+                _lib.raise_device_errors()             # e.g. an out-of-range timestamp: the reference raises IndexError
                 yield o
             k += 1
         for o, e in pending:
             e.synchronize()
+            _lib.raise_device_errors()
             yield o

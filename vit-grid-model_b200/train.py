@@ -53,6 +53,41 @@ class GradBuffer:
     def zero_(self):
         self.flat.zero_()
 
+    def views_of(self, flat):
+        """the per-parameter views of another flat tensor with this buffer's layout"""
+        return {n: flat[v.storage_offset():v.storage_offset() + v.numel()].view(v.shape) for n, v in self.views.items()}
+
+    def snapshot(self):
+        """copy of the flat buffer (one kernel) + its per-parameter views; remembered as `last_snapshot`"""
+        self.last_snapshot = self.flat.clone()
+        return self.views_of(self.last_snapshot)
+
+    def flat_of(self, params):
+        """If every ``p.grad`` of `params` ({name: parameter}) is a view, at this buffer's offsets, of ONE flat fp32 tensor,
+        return that tensor (autograd accumulates later backward passes into the first snapshot in place, so it then holds
+        the summed gradient); otherwise None."""
+        base = None
+        for n, v in self.views.items():
+            g = params[n].grad
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != v.shape:
+                return None
+            start = g.data_ptr() - 4 * v.storage_offset()
+            if base is None:
+                base = start
+            elif start != base:
+                return None
+        snap = getattr(self, "last_snapshot", None)
+        for cand in (snap, self.flat):
+            if cand is not None and cand.data_ptr() == base:
+                return cand
+        # p.grad lives in an older snapshot (gradient accumulation over several backward passes): rebuild the flat view
+        g0 = params[next(iter(self.views))].grad
+        st = g0.untyped_storage()
+        off = (base - st.data_ptr()) // 4
+        if off < 0 or (off + self.flat.numel()) * 4 > st.nbytes():
+            return None
+        return torch.empty(0, dtype=torch.float32, device=g0.device).set_(st, off, (self.flat.numel(),))
+
     def __getitem__(self, name):
         return self.views[name]
 
@@ -438,8 +473,11 @@ def metnet3_train_backward(model, S, dpred, G: GradBuffer, sync: GradSync | None
 
 class MetNet3TrainFn(torch.autograd.Function):
     """autograd node of the whole network: forward = train-mode forward on libvitgrid kernels, backward = hand-written
-    backward; parameter gradients come back as views of the model's flat GradBuffer (already all-reduced when the model
-    is wrapped in `DataParallel`)."""
+    backward.  The backward kernels accumulate into the model's flat GradBuffer (all-reduced in place when the model is wrapped
+    in `DataParallel`); what autograd receives are views of a SNAPSHOT of that buffer (one device copy of 13 MB), so that
+    several applications of the model inside one graph -- two forwards summed into one loss, micro-batches sharing one
+    backward -- accumulate correctly in ``p.grad`` instead of overwriting each other through the shared buffer.  The
+    snapshot keeps GradBuffer's layout: ``FlatAdamW`` consumes ``p.grad`` in place when it is still such a view."""
 
     @staticmethod
     def forward(ctx, model, x, ts, *params):
@@ -450,8 +488,12 @@ class MetNet3TrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpred):
         model = ctx.model
+        if ctx.S is None:
+            raise RuntimeError("MetNet3 backward ran twice through the same forward: the saved activations are released after "
+                               "the first backward (retain_graph is not supported); call the model again")
         G = model.grad_buffer()
         G.zero_()
         metnet3_train_backward(model, ctx.S, dpred.float(), G, model._grad_sync)
         ctx.S = None
-        return (None, None, None, *[G[n] for n in G.names])
+        snap = G.snapshot()
+        return (None, None, None, *[snap[n] for n in G.names])
