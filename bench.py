@@ -298,7 +298,10 @@ def run_other_config(args, dev, rank, world):
 
     model = MetNet3(**cfg.metnet3_kwargs())
     model.load_state_dict(synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), strict=True)
-    model = model.to(dev).eval().set_precision("bf16")
+    model = model.to(dev).eval()                               # the constructor's default precision for this width
+    if args.config == 3:
+        model.set_precision("bf16")
+    precision = model.precision
     x, ts, target = synth.make_inputs(cfg, B, seed=1234 + rank)
     x_host, ts_host = x.pin_memory(), ts.pin_memory()
     x, ts, target = x.to(dev), ts.to(dev), target.to(dev)
@@ -327,6 +330,23 @@ def run_other_config(args, dev, rank, world):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     fields = world * B * L * args.steps
     value = fields / (ms * 1e-3)
+    opt_in = None
+    if precision == "fp32":
+        # the reduced-precision mode of a wide network is opt-in: it misses the 1e-2 tolerance at this depth
+        model.set_precision("bf16")
+        with torch.no_grad():
+            for _ in range(W):
+                model(x, timestamps=ts)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                model(x, timestamps=ts)
+            e1.record()
+            barrier()
+        ms16 = max_over_ranks(e0.elapsed_time(e1))
+        opt_in = {"precision": "bf16 (opt-in; 3.6e-2 vs the oracle at this depth: outside the 1e-2 tolerance)", "value": fields / (ms16 * 1e-3),
+                  "ms_per_step": ms16 / args.steps, "model_tflops_reference_graph": fields / (ms16 * 1e-3) / world * gf_ref / 1e3}
+        model.set_precision(precision)
     train = None
     if not args.no_train:
         try:
@@ -359,8 +379,8 @@ def run_other_config(args, dev, rank, world):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
+            "data": "synthetic", "reduced_precision_opt_in": opt_in,
             "config": {"workload": workload, "batch_per_gpu": B, "fields_per_step": world * B * L,
                        "input_shape": [B, cfg.T, cfg.C, cfg.H, cfg.W], "gflop_per_field_reference_graph": gf_ref,
                        "l2": "activations of one step exceed the 126 MB L2", "parallelism": f"batch-sharded x{world}"},

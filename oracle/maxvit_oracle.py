@@ -134,7 +134,7 @@ def maxvit_forward(x: torch.Tensor, cond: torch.Tensor, sd, *, prefix: str = "",
         seq = attention(seq, cond, sd, f"{prefix}layers.{li}.1.", heads=heads, window=window, num_reg=num_reg,
                         prob_mask=pm, out_mask=om) + seq
         flat = torch.empty_like(flat)
-        flat[:, bidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D)
+        flat[:, bidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D).to(flat.dtype)
         # grid attention: registers = mean over windows of block-attention register outputs (:326-327)
         reg = seq[:, :num_reg].reshape(N, nwin, num_reg, D).mean(dim=1)
         tok = flat[:, gidx].reshape(N * nwin, window * window, D)
@@ -144,6 +144,6 @@ def maxvit_forward(x: torch.Tensor, cond: torch.Tensor, sd, *, prefix: str = "",
                         prob_mask=pm, out_mask=om) + seq
         regs_out = seq[:, :num_reg]
         flat = torch.empty_like(flat)
-        flat[:, gidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D)
+        flat[:, gidx] = seq[:, num_reg:].reshape(N, nwin * window * window, D).to(flat.dtype)
         x = flat.permute(0, 2, 1).reshape(N, D, H, W)
     return (x, regs_out) if return_registers else x

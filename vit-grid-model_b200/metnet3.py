@@ -158,6 +158,9 @@ class MetNet3(nn.Module):
         else:
             self._unsupported = None
         self.compute_dtype, self.precision = torch.bfloat16, "bf16"
+        if n_start_channels > 128:
+            self.compute_dtype, self.precision = torch.float32, "fp32"
+            self.vit.set_precision("fp32")
         self.max_fields = {torch.bfloat16: 768, torch.float32: 48}
         self._packed, self._packed_key = None, None
         self._capture = None          # debugging: set to a dict to collect stage outputs (NCHW copies)
@@ -168,19 +171,14 @@ class MetNet3(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def set_precision(self, precision: str):
-        """'bf16' (default): bf16 storage + tcgen05 kind::f16 for the 3x3-conv encoder/decoder; the MaxViT block keeps fp32
-        storage with 16-bit / tf32 tensor-core operands at 128 channels, and runs exact-fp32 GEMMs in wider networks (stacked
-        tf32 layers of a 512-channel, depth-4 backbone were measured outside the 1e-2 tolerance; 'bf16_tf32' selects them
-        anyway); 'bf16_all': bf16 everywhere; 'fp32': exact-fp32 SIMT path."""
-        self.compute_dtype = {"bf16": torch.bfloat16, "bf16_tf32": torch.bfloat16, "bf16_all": torch.bfloat16,
-                              "fp32": torch.float32}[precision]
-        vit_precision = precision
-        if precision == "bf16" and self.n_start_channels > 128:
-            vit_precision = "fp32"
-        elif precision == "bf16_tf32":
-            vit_precision = "bf16"
-        self.vit.set_precision(vit_precision)
-        self.precision = "bf16" if precision == "bf16_tf32" else precision
+        """'bf16': bf16 storage + tcgen05 kind::f16 for the 3x3-conv encoder/decoder, fp32 storage + 16-bit / tf32 tensor-core
+        operands for the MaxViT block; 'bf16_all': bf16 everywhere; 'fp32': exact-fp32 SIMT path.
+        Default: 'bf16' at 128 channels.  Wider networks default to 'fp32': on BASELINE configs[4] (512 channels, depth 4) the
+        bf16 activations of the encoder were measured at 3.4e-2 against the oracle whatever the MaxViT precision -- outside
+        the 1e-2 tolerance -- so the reduced-precision modes there are opt-in (tests/test_parity_r2_gpu.py)."""
+        self.compute_dtype = {"bf16": torch.bfloat16, "bf16_all": torch.bfloat16, "fp32": torch.float32}[precision]
+        self.vit.set_precision(precision)
+        self.precision = precision
         self.invalidate_packed()
         return self
 
