@@ -560,10 +560,12 @@ def main():
             attn_traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("attn_fused_dram_bytes_per_launch")
         except Exception:
             pass
-        kernels.append({"kernel": "attn_fused_kernel (window / grid attention in one kernel: tcgen05 kind::f16 QKV projection on fp16 operands and PV, kind::tf32 QK^T and out-projection; X, P, O operands in TMEM)",
+        kernels.append({"kernel": "attn_fused2_kernel (window / grid attention in one kernel, in place on the residual stream: partition = TMA tensor maps, "
+                                  "residual add = TMA reduce-store; tcgen05 kind::f16 QKV projection, QK^T and PV on fp16 / bf16 operands, kind::tf32 out-projection; "
+                                  "X, P, O operands in TMEM; two compute groups on alternate heads, three MMA issuers)",
                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         "traffic": attn_traffic, "launches_per_step": len(attn_ms) // args.steps, "avg_launch_ms": avg_ms,
-                        "peak_source": peak_src + "; 29 % of this kernel's FLOPs (QK^T, out-projection) run as kind::tf32 (half the bf16 rate)",
+                        "peak_source": peak_src + "; 21 % of this kernel's FLOPs (the out-projection) run as kind::tf32 (half the bf16 rate)",
                         "share_of_step": sum(attn_ms) / ms_total,
                         "algorithmic_gflop_per_field_per_launch": ATTN_FLOPS_PER_FIELD / 1e9})
     kernels.sort(key=lambda k: -k["share_of_step"])

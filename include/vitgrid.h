@@ -181,6 +181,19 @@ VG_API int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, 
                       const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win, int R,
                       int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt, int drop_thresh, void* stream);
 
+/* Second-generation fused attention (maxvit.py:170-219 + 298-340), IN PLACE on the fp32 residual stream: xio += to_out(attn(xio)).
+ * The window / grid partition (maxvit.py:298 / :322) is the TMA tensor map itself -- block: boxes (32 ch, 7, 7) of the view
+ * (C, Wl, N*Hl); grid: boxes (32 ch, 1, 7, 1, 7) of the view (C, Y, 7, X, 7N) -- the token rows of the next tile are prefetched
+ * by the TMA warp, and the result returns through the same maps with cp.reduce.async.bulk.tensor (.add), which performs the
+ * residual add.  QKV projection, QK^T and PV run as tcgen05 kind::f16 (fp16 / bf16 operands), the out-projection as
+ * kind::tf32 on the O_h accumulator read in place from TMEM; two compute groups of 8 warps alternate heads.  Same operand
+ * formats (wqkv_h, wout_h, head_tab), dropout hash and constraints as vg_attn_fused_fwd, plus: heads even.
+ * A caller that needs the input afterwards (training) copies it first and passes the copy. */
+VG_API int vg_attn_fused2_fwd(float* xio, const float* reg_in, int reg_per_field, float* reg_out, const float* film,
+                       const void* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win,
+                       int R, int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt,
+                       int drop_thresh, void* stream);
+
 /* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */
 VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);
 

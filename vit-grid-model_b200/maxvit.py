@@ -192,8 +192,9 @@ class MaxViT(nn.Module):
         N, H, W, C = x.shape
         w, R = self.vit_window_size, self.num_register_tokens
         if self.fused_attention and self.tf32 and C == 128 and self.dim_head == 32 and w == 7 and R == 4 and self.heads >= 4:
+            # x is a temporary of forward_cl (MBConv output / the previous attention's result): updated in place
             return ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
-                                  self.heads, self.dim_head)
+                                  self.heads, self.dim_head, inplace=True)
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
         qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32)
         del tokens

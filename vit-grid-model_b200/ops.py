@@ -8,7 +8,10 @@ import torch
 
 from . import _lib
 
+import os
+
 DT_CODE = {torch.bfloat16: 0, torch.float32: 1}
+_ATTN_V1 = os.environ.get("VG_ATTN_V1", "0") == "1"
 
 
 def _p(t):
@@ -267,20 +270,30 @@ def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     return torch.cat([tab.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
 
 
-def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5, drop=(0, 0, 0)):
+def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5, drop=(0, 0, 0),
+               inplace=False):
     """whole attention layer (+ residual) in one kernel; x CL (N,Hl,Wl,128) fp32.
-    drop = (seed, salt, T): training dropout with probability T/256 on the probabilities and the to_out output"""
+    drop = (seed, salt, T): training dropout with probability T/256 on the probabilities and the to_out output.
+    The kernel works in place on the residual stream (its TMA reduce-store performs the residual add): inplace=True lets it
+    overwrite x (inference: x is a temporary), otherwise x is copied first (training keeps the input for backward).
+    VG_ATTN_V1=1 selects the first-generation kernel (A/B comparisons)."""
     N, Hl, Wl, C = x.shape
-    assert x.dtype == torch.float32
+    assert x.dtype == torch.float32 and x.is_contiguous()
     nwin = (Hl // win) * (Wl // win)
-    x_out = torch.empty_like(x)
     reg_out = torch.empty(N * nwin, R, C, dtype=torch.float32, device=x.device) if want_reg_out else None
     if wqkv_h.dtype != torch.float16:                       # the kernel's QKV operand format (the modules pack it once)
         wqkv_h = wqkv_h.half()
-    _lib.call("vg_attn_fused_fwd", x.data_ptr(), x_out.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out),
-              film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
+    if _ATTN_V1 or heads % 2:
+        x_out = torch.empty_like(x)
+        _lib.call("vg_attn_fused_fwd", x.data_ptr(), x_out.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out),
+                  film.data_ptr(), wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
+                  int(drop[0]), int(drop[1]), int(drop[2]), _st())
+        return x_out, reg_out
+    xio = x if inplace else x.clone()
+    _lib.call("vg_attn_fused2_fwd", xio.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out), film.data_ptr(),
+              wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
               int(drop[0]), int(drop[1]), int(drop[2]), _st())
-    return x_out, reg_out
+    return xio, reg_out
 
 
 def reg_mean(reg_out, N, nwin):
