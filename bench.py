@@ -551,7 +551,7 @@ def main():
                                                        "frac": CONV_FLOPS_PER_FIELD * B * L / (sum(v) / len(v) * 1e-3) / 1e12 / peak_tf,
                                                        "traffic": (traffic_all.get("conv_variants") or {}).get(k.strip()[5:-1])}
                                      for k, v in per.items() if k.startswith("  conv[")}})
-    attn_ms = per.get("vg_attn_fused_fwd", [])
+    attn_ms = (per.get("vg_attn_fused2_fwd") or per.get("vg_attn_fused_fwd", []))
     if attn_ms and args.precision == "bf16":
         avg_ms = sum(attn_ms) / len(attn_ms)
         achieved = ATTN_FLOPS_PER_FIELD * B * L / (avg_ms * 1e-3) / 1e12

@@ -161,6 +161,34 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void pair_bar(int grp, int lg) { asm volatile("bar.sync %0, 64;" ::"r"(2 + 4 * grp + lg) : "memory"); }
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(10 + grp) : "memory"); }
 
+// mbarrier operations on precomputed 32-bit shared addresses (the generic-pointer helpers of vg_common.cuh re-derive the
+// aligned dynamic-shared-memory base -- eight uniform-datapath instructions -- at every call site of the hot loop)
+__device__ __forceinline__ bool mbar_try_a(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity, int tag) {
+  if (mbar_try_a(a, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_a(a, parity)) {
+    if (((++spins) & 0x3ff) == 0 && (clock64() - t0) > 1000000000LL) {
+      printf("vitgrid: mbarrier wait timeout tag %d parity %u (block %d thread %d)\n", tag, parity, (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void sts64f(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ float2 lds64f(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Up to three barriers polled by three different lanes at once, then the warp re-converges: a try_wait issued by all 32 lanes
 // of a warp on one barrier was measured at ~190 cycles even when the phase is long complete, and a role that polls three
 // barriers back to back pays it three times.  (__syncwarp orders the waiting lanes' acquire before the other lanes' accesses.)
@@ -206,7 +234,9 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
   uint64_t* wq_full = bars + 0;   uint64_t* wq_free = bars + 2;       // [2] each
   uint64_t* wo_full = bars + 4;   uint64_t* wo_free = bars + 6;       // [2] each
   uint64_t* tab_full = bars + 8;  uint64_t* tab_free = bars + 10;     // [2] each (per group)
-  uint64_t* qkv_done = bars + 12;                                      // [2] per group
+  uint64_t* qkv_done = bars + 12;                                      // [2] per group: "stage ready" = 3 arrivals per head: the head's table has
+                                                                       // landed (TMA), QKV(j) has retired, PV(j-2) has retired (this group's V bytes
+                                                                       // are free) -- one poll at the start of staging instead of three
   uint64_t* qk_ready = bars + 14;                                      // [2] per group
   uint64_t* s_done = bars + 16;                                        // [2] per group
   uint64_t* p_ready = bars + 18;                                       // [2] per group
@@ -226,7 +256,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(wq_full + i, 1); mbar_init(wq_free + i, 1); mbar_init(wo_full + i, 1); mbar_init(wo_free + i, 1);
       mbar_init(tab_full + i, 1); mbar_init(tab_free + i, 8);
-      mbar_init(qkv_done + i, 1); mbar_init(qk_ready + i, 8); mbar_init(s_done + i, 1); mbar_init(p_ready + i, 8);
+      mbar_init(qkv_done + i, 3); mbar_init(qk_ready + i, 8); mbar_init(s_done + i, 1); mbar_init(p_ready + i, 8);
       mbar_init(pv_done + i, 1);
     }
     mbar_init(qkv_free, 8); mbar_init(s_free, 8);
@@ -286,8 +316,8 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       auto load_tab = [&](int j, int h) {
         const uint32_t b = (uint32_t)(j & 1);
         mbar_wait_tag(tab_free + b, (uint32_t)(((j >> 1) & 1) ^ 1), 304);
-        mbar_arrive_expect_tx(tab_full + b, TAB_FLOATS * 4);
-        bulk_g2s(smem + TAB_OFF + b * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, tab_full + b);
+        mbar_arrive_expect_tx(qkv_done + b, TAB_FLOATS * 4);
+        bulk_g2s(smem + TAB_OFF + b * TAB_FLOATS * 4, p.head_tab + (long long)h * TAB_FLOATS, TAB_FLOATS * 4, qkv_done + b);
       };
       if (total > 0) load_raw(0);
       for (int j = 0; j < 2 && j < total; ++j) { load_wq(j, j % heads); load_tab(j, j % heads); }
@@ -344,8 +374,10 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     for (int j = 0; j < total; ++j) {
       long long* dm = (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) ? p.dbg + (2 * 128 + j) * 8 : nullptr;
       const uint32_t b = (uint32_t)(j & 1);
-      mbar_wait_tag(qk_ready + b, (uint32_t)((j >> 1) & 1), 314);
+      // s_free(j-1) first (the other group took S(j-1) long ago); the operands of head j arrive over a hardware named
+      // barrier: an mbarrier poll by a whole warp costs ~190 cycles, and this hand-over is in front of every softmax
       if (j > 0) mbar_wait_tag(s_free, (uint32_t)((j - 1) & 1), 315);
+      asm volatile("bar.sync %0, 288;" ::"r"(12 + (int)b) : "memory");
       tc_fence_after();
       if (dm) dm[7] = clock64();
       if (elect_one()) {
@@ -363,11 +395,13 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     constexpr uint32_t id_out = umma_idesc_tf32(128, 128);
     const uint32_t sWO = smem_u32(smem + WO_OFF), sVT = smem_u32(smem + VT_OFF);
     int h = 0, tl = 0;
+    if (lane == 0) { mbar_arrive(qkv_done + 0); mbar_arrive(qkv_done + 1); }      // heads 0 and 1 have no PV(j-2) to wait for
     for (int k = 0; k < total; ++k) {
       long long* dm = (p.dbg && blockIdx.x == 0 && k < 128 && lane == 0) ? p.dbg + (2 * 128 + k) * 8 : nullptr;
       const uint32_t b = (uint32_t)(k & 1);
-      wait3(lane, wo_full + b, (uint32_t)((k >> 1) & 1), (h == 0 && tl > 0) ? out_free : nullptr, (uint32_t)((tl - 1) & 1),
-            p_ready + b, (uint32_t)((k >> 1) & 1), 316);
+      mbar_wait_tag(wo_full + b, (uint32_t)((k >> 1) & 1), 316);
+      if (h == 0 && tl > 0) mbar_wait_tag(out_free, (uint32_t)((tl - 1) & 1), 317);
+      asm volatile("bar.sync %0, 288;" ::"r"(14 + (int)b) : "memory");      // P(k) stored by the 8 warps of group b
       tc_fence_after();
       if (dm) dm[3] = clock64();
       if (elect_one()) {
@@ -377,6 +411,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
 #pragma unroll
         for (int st = 0; st < 8; ++st) mma_ts_f16(tmem + T_O, tmem + T_P + 8 * st, dv + st * (2048 >> 4), id_pv, st ? 1u : 0u);
         tc_commit(pv_done + b);
+        if (k + 2 < total) tc_commit(qkv_done + b);          // staging(k+2) may overwrite this group's V bytes
       }
       __syncwarp();
       // a TMEM A operand is not ordered behind the MMA that writes it: wait for PV(k) to retire before out(k)
@@ -406,7 +441,9 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     const bool is_reg = i < REG;
     const int ti = (i >= REG && i < SEQ) ? i - REG : 0;
     const int ai = ti / WIN, bi = ti - ai * WIN;
-    float* red = reinterpret_cast<float*>(smem + RED_OFF) + grp * 512;       // [128 rows][2 threads] x (max, sum)
+    const uint32_t red = s_base + RED_OFF + grp * 2048 + t * 16;             // this row: [2 threads] x (max, sum)
+    const uint32_t a_stage = smem_u32(qkv_done + grp), a_qkv_free = smem_u32(qkv_free), a_s_done = smem_u32(s_done + grp);
+    const uint32_t a_s_free = smem_u32(s_free), a_tab_free = smem_u32(tab_free + grp), a_pv_other = smem_u32(pv_done + (grp ^ 1));
     float* lnred = reinterpret_cast<float*>(smem + RED_OFF) + 1024;          // [128][2] sums | [128][2] square sums
     const uint32_t b_off = is_reg ? (uint32_t)TAB_T169 * 4u : (uint32_t)(bi * TAB_SB + (ai + 6) * TAB_SR) * 4u;
     const uint32_t b_step = is_reg ? 0u : (uint32_t)TAB_SR * 4u;
@@ -556,8 +593,8 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       long long* dg = (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0 && (warp == 2 || warp == 10)) ? p.dbg + (grp * 128 + j) * 8 : nullptr;
       if (dg) dg[0] = clock64();
       // ---------------- staging: q^ | K" (fp16) and V^T (bf16) of head j ----------------
-      // table of this head; PV(j-2) has read this group's V bytes; QKV(j) has retired
-      wait3(lane, tab_full + grp, u & 1, u > 0 ? pv_done + grp : nullptr, (u - 1) & 1, qkv_done + grp, u & 1, 341);
+      // one barrier: the table of this head has landed, PV(j-2) has read this group's V bytes, QKV(j) has retired
+      mbar_wait_a(a_stage, u & 1, 341);
       tc_fence_after();
       if (dg) dg[1] = clock64();
       {
@@ -567,7 +604,13 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(qkv_free);                            // QKV(j+1) may overwrite the accumulator
+        if (lane == 0) mbar_arrive_a(a_qkv_free);                        // QKV(j+1) may overwrite the accumulator
+        // V (bf16), MN-major: key row t holds its 32 head dims contiguously (64 bytes, chunks grp*4 .. grp*4+3 of the 128-byte
+        // row): two 16-byte stores per thread instead of 16 transposing 2-byte stores
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          sts128w(VT + sw128b(t, grp * 4 + ch * 2 + c), pk_bf16(vv[8 * c], vv[8 * c + 1]), pk_bf16(vv[8 * c + 2], vv[8 * c + 3]),
+                  pk_bf16(vv[8 * c + 4], vv[8 * c + 5]), pk_bf16(vv[8 * c + 6], vv[8 * c + 7]));
         float2* a2 = reinterpret_cast<float2*>(a);
         float2 n2a = make_float2(0.f, 0.f), n2b = make_float2(0.f, 0.f);
 #pragma unroll
@@ -598,20 +641,14 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
                     pk_f16(a[8 * c + 4], a[8 * c + 5]), pk_f16(a[8 * c + 6], a[8 * c + 7]));
           }
         }
-        // V (bf16), MN-major: key row t holds its 32 head dims contiguously (64 bytes, chunks grp*4 .. grp*4+3 of the 128-byte
-        // row): two 16-byte stores per thread instead of 16 transposing 2-byte stores
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          sts128w(VT + sw128b(t, grp * 4 + ch * 2 + c), pk_bf16(vv[8 * c], vv[8 * c + 1]), pk_bf16(vv[8 * c + 2], vv[8 * c + 3]),
-                  pk_bf16(vv[8 * c + 4], vv[8 * c + 5]), pk_bf16(vv[8 * c + 6], vv[8 * c + 7]));
       }
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qk_ready + grp);
+      asm volatile("bar.arrive %0, 288;" ::"r"(12 + grp) : "memory");      // q^ | K" staged: the S issuer (warp 19) syncs on this barrier
       if (dg) dg[2] = clock64();
+      if (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2] = clock64();
 
       // ---------------- softmax of head j ----------------
-      wait3(lane, s_done + grp, u & 1, nullptr, 0, nullptr, 0, 344);
+      mbar_wait_a(a_s_done, u & 1, 344);
       tc_fence_after();
       if (dg) dg[3] = clock64();
       {
@@ -621,7 +658,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);                              // S(j+1) may overwrite the accumulator
+        if (lane == 0) mbar_arrive_a(a_s_free);                          // S(j+1) may overwrite the accumulator
         const uint32_t brow = tab + b_off;
         float m = -INFINITY;
         if (ch == 0) {
@@ -651,7 +688,10 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
           for (int jj = 0; jj < 21; ++jj) m = fmaxf(m, sc[jj]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(tab_free + grp);                      // last read of this head's tables
+        if (lane == 0) mbar_arrive_a(a_tab_free);                        // last read of this head's tables
+        // the P buffer is single: PV(j-1) (the other group's head) must have retired before this head's P is stored.  Polled
+        // here, where the thread has independent work in flight; a completed poll costs ~190 cycles at the hand-over otherwise
+        const bool p_free = j > 0 ? mbar_try_a(a_pv_other, (uint32_t)(((j - 1) >> 1) & 1)) : true;
         if (dg) dg[4] = clock64();
         const float2 nm = make_float2(-m, -m);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
@@ -676,12 +716,12 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         }
         acc0 = fadd2b(acc0, acc1);
         const float s_own = acc0.x + acc0.y;
-        *reinterpret_cast<float2*>(red + t * 4 + ch * 2) = make_float2(m, s_own);
+        sts64f(red + ch * 8, m, s_own);
         pair_bar(grp, lg);                                               // partner's (max, sum) is visible
-        const float2 oth = *reinterpret_cast<const float2*>(red + t * 4 + (ch ^ 1) * 2);
+        const float2 oth = lds64f(red + (ch ^ 1) * 8);
         const float mrow = fmaxf(m, oth.x);
         const float f_own = ex2f(m - mrow), f_oth = ex2f(oth.x - mrow);
-        const float inv_sum = f_own / fmaf(s_own, f_own, oth.y * f_oth);
+        const float inv_sum = f_own * rcpf(fmaf(s_own, f_own, oth.y * f_oth));
         if (DROP && p.drop.thresh) {                                     // nn.Dropout on the probabilities (maxvit.py:146, 209)
           const float ks = inv_sum * p.drop.scale;
           const uint32_t rid = drop_row(wdx, i);
@@ -699,7 +739,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         // P (bf16 pairs, one 32-bit TMEM column per two keys): own 32 keys -> columns [half*32 + ch*16, +16); the same keys of
         // the other window are zero.  The P buffer is single: PV(j-1) (the other group's head) must have retired.
         if (dg) dg[5] = clock64();
-        wait3(lane, j > 0 ? pv_done + (grp ^ 1) : nullptr, (uint32_t)(((j - 1) >> 1) & 1), nullptr, 0, nullptr, 0, 345);
+        if (!p_free) mbar_wait_a(a_pv_other, (uint32_t)(((j - 1) >> 1) & 1), 345);
         tc_fence_after();
         if (dg) dg[6] = clock64();
         uint32_t pk[16];
@@ -709,9 +749,9 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         tm_wait_st();
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready + grp);
+      asm volatile("bar.arrive %0, 288;" ::"r"(14 + grp) : "memory");      // P(j) is in TMEM: the back-end issuer (warp 18) syncs on this barrier
       if (dg) dg[7] = clock64();
+      if (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2 + 1] = clock64();
 
       // ---------------- tile boundary work after this group's last head of the tile ----------------
       if (h == heads - 2 + grp) {
