@@ -223,7 +223,9 @@ __device__ __forceinline__ WinPos win_pos(const Fused2Params& p, long long tile,
 
 }  // namespace
 
-template <bool DROP>
+// DROP: training instantiation with the dropout code; DBG: clock-stamp instrumentation (tools/run_attn_fused2.py) -- both
+// compiled out of the production instantiation, whose cold paths share an instruction cache with five hot role loops
+template <bool DROP, bool DBG>
 __global__ void __launch_bounds__(fb::THREADS, 1)
 attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_constant__ CUtensorMap mapWo,
                    const __grid_constant__ CUtensorMap mapX, const Fused2Params p) {
@@ -361,7 +363,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     if (total > 0) issue_qkv(0, 0, 0, nullptr);
     int hq = 1 % heads, tlq = heads == 1 ? 1 : 0;            // (head, tile) of j + 1
     for (int j = 0; j + 1 < total; ++j) {
-      long long* dm = (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) ? p.dbg + (2 * 128 + j) * 8 : nullptr;
+      long long* dm = (DBG && p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) ? p.dbg + (2 * 128 + j) * 8 : nullptr;
       if (dm) dm[0] = clock64();
       issue_qkv(j + 1, hq, tlq, dm);
       if (dm) dm[1] = clock64();
@@ -372,7 +374,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     constexpr uint32_t id_s = umma_idesc_f16(128, 128);
     const uint32_t sQK = smem_u32(smem + QK_OFF);
     for (int j = 0; j < total; ++j) {
-      long long* dm = (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) ? p.dbg + (2 * 128 + j) * 8 : nullptr;
+      long long* dm = (DBG && p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) ? p.dbg + (2 * 128 + j) * 8 : nullptr;
       const uint32_t b = (uint32_t)(j & 1);
       // s_free(j-1) first (the other group took S(j-1) long ago); the operands of head j arrive over a hardware named
       // barrier: an mbarrier poll by a whole warp costs ~190 cycles, and this hand-over is in front of every softmax
@@ -397,7 +399,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     int h = 0, tl = 0;
     if (lane == 0) { mbar_arrive(qkv_done + 0); mbar_arrive(qkv_done + 1); }      // heads 0 and 1 have no PV(j-2) to wait for
     for (int k = 0; k < total; ++k) {
-      long long* dm = (p.dbg && blockIdx.x == 0 && k < 128 && lane == 0) ? p.dbg + (2 * 128 + k) * 8 : nullptr;
+      long long* dm = (DBG && p.dbg && blockIdx.x == 0 && k < 128 && lane == 0) ? p.dbg + (2 * 128 + k) * 8 : nullptr;
       const uint32_t b = (uint32_t)(k & 1);
       mbar_wait_tag(wo_full + b, (uint32_t)((k >> 1) & 1), 316);
       if (h == 0 && tl > 0) mbar_wait_tag(out_free, (uint32_t)((tl - 1) & 1), 317);
@@ -590,7 +592,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     for (int j = grp; j < total; j += 2) {
       const uint32_t u = (uint32_t)(j >> 1);                  // sequence number inside this group
 
-      long long* dg = (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0 && (warp == 2 || warp == 10)) ? p.dbg + (grp * 128 + j) * 8 : nullptr;
+      long long* dg = (DBG && p.dbg && blockIdx.x == 0 && j < 128 && lane == 0 && (warp == 2 || warp == 10)) ? p.dbg + (grp * 128 + j) * 8 : nullptr;
       if (dg) dg[0] = clock64();
       // ---------------- staging: q^ | K" (fp16) and V^T (bf16) of head j ----------------
       // one barrier: the table of this head has landed, PV(j-2) has read this group's V bytes, QKV(j) has retired
@@ -645,7 +647,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       fence_proxy_async_smem();
       asm volatile("bar.arrive %0, 288;" ::"r"(12 + grp) : "memory");      // q^ | K" staged: the S issuer (warp 19) syncs on this barrier
       if (dg) dg[2] = clock64();
-      if (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2] = clock64();
+      if (DBG && p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2] = clock64();
 
       // ---------------- softmax of head j ----------------
       mbar_wait_a(a_s_done, u & 1, 344);
@@ -751,7 +753,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       tc_fence_before();
       asm volatile("bar.arrive %0, 288;" ::"r"(14 + grp) : "memory");      // P(j) is in TMEM: the back-end issuer (warp 18) syncs on this barrier
       if (dg) dg[7] = clock64();
-      if (p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2 + 1] = clock64();
+      if (DBG && p.dbg && blockIdx.x == 0 && j < 128 && lane == 0) p.dbg[3 * 128 * 8 + ((warp - 2) * 128 + j) * 2 + 1] = clock64();
 
       // ---------------- tile boundary work after this group's last head of the tile ----------------
       if (h == heads - 2 + grp) {
@@ -855,16 +857,18 @@ int attn_fused2_run(float* xio, const float* reg_in, int reg_per_field, float* r
   static bool attr[64] = {};
   if (dev < 0 || dev >= 64) return set_error("attn_fused2: device ordinal %d out of range", dev);
   if (!attr[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fused2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("attn_fused2 smem attr: %s", cudaGetErrorString(e));
     attr[dev] = true;
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (p.n_windows + 1) / 2;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  if (drop_thresh) attn_fused2_kernel<true><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
-  else attn_fused2_kernel<false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  if (drop_thresh) attn_fused2_kernel<true, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  else if (p.dbg) attn_fused2_kernel<false, true><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  else attn_fused2_kernel<false, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
   return check_launch("attn_fused2_kernel");
 }
 

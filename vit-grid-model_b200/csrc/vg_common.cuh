@@ -102,6 +102,22 @@ __device__ __forceinline__ void st8(float* p, const float* v) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// 256-bit global stores (sm_100: STG.E.ENL2.256).  A row-per-thread epilogue store touches 32 different 128-byte lines per warp
+// instruction whatever its width; 32 bytes per thread halve the number of store instructions (and LSU wavefronts) per row.
+// p must be 32-byte aligned.
+__device__ __forceinline__ void st8_256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st16_256(bf16* p, const float* v) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); u[i] = *reinterpret_cast<uint32_t*>(&h); }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ void st16_256(float* p, const float* v) { st8_256(p, v); st8_256(p + 8, v + 8); }
+
 // erf by Abramowitz & Stegun 7.1.26 (|error| < 6.1e-7 in fp32 arithmetic, checked against double over [-6, 6]): five FMAs and
 // two MUFU ops instead of libdevice erff's two polynomial branches -- the exact-erf GELU (nn.GELU(), maxvit.py:45,48) of
 // the 1x1 expand epilogue and the depthwise kernel costs as many issue slots as the convolution arithmetic around it

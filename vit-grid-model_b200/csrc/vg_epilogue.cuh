@@ -340,11 +340,11 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
     if (TRAIN && ep.relu_mask) ep.relu_mask[row * 4 + ch] = mbits;
     if (o) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st8(o + ch * 32 + j, v + j);
+      for (int j = 0; j < 32; j += 16) st16_256(o + ch * 32 + j, v + j);
     }
     if (o2) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st8(o2 + ch * 32 + j, v + j);
+      for (int j = 0; j < 32; j += 8) st8_256(o2 + ch * 32 + j, v + j);
     }
   }
   if (ep.head_w && valid) {
