@@ -147,10 +147,11 @@ VG_API int vg_attn_partition_debug(int N, int Hl, int Wl, int win, int R, int gr
 
 /* maxvit.py:298-308 / 322-332 + 176-187 -- partition (mode 0 block, 1 grid) folded into addressing, register
  * tokens prepended (reg: fp32 [R][C] shared or [N][R][C] per field), LayerNorm (no affine), FiLM (film: fp32
- * (N,2C) = gamma|beta)  ->  tokens [(N*nwin*S)][C]. */
+ * (N,2C) = gamma|beta)  ->  tokens [(N*nwin*S)][C] in x's dtype, or in bf16 from an fp32 x when tokens_bf16 != 0 (the
+ * mixed-precision training backward re-materialises the tokens in 16-bit storage). */
 VG_API int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, int N,
                        int Hl, int Wl, int C, int win, int R, int grid_mode, float ln_eps, void* tokens,
-                       void* stream);
+                       int tokens_bf16, void* stream);
 
 /* maxvit.py:195-215 -- per (window, head): q,k RMSNorm (F.normalize * sqrt(d) * gamma), QK^T + rel-pos bias
  * (table (2w-1)^2+1 x heads, fp32), softmax, PV.  qkv [(Nw*S)][3*heads*dh] -> out [(Nw*S)][heads*dh]. */
@@ -343,20 +344,23 @@ VG_API int vg_se_scale_oop(const float* x, const float* gate, float* out, int N,
 VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
               long long work_elems, void* stream);
-/* attention backward (fp32): gradient at the out-projection output (inverse of the scatter + register rows) */
+/* attention backward: gradient at the out-projection output (inverse of the scatter + register rows); dproj fp32, or bf16
+ * when dproj_bf16 != 0 */
 VG_API int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
-                           int R, int grid_mode, float* dproj, long long drop_seed, int drop_salt, int drop_thresh, void* stream);
+                           int R, int grid_mode, void* dproj, int dproj_bf16, long long drop_seed, int drop_salt, int drop_thresh,
+                           void* stream);
 /* test hook: the dropout masks the kernels use, as bytes (1 = kept): prob_mask [n_windows][heads][64][64] (query slot,
  * key slot), out_mask [n_windows][64][C] */
 VG_API int vg_dropout_mask_debug(long long drop_seed, int drop_salt, int drop_thresh, long long n_windows, int heads, int C,
                           void* prob_mask, void* out_mask, void* stream);
-/* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated.  use_tf32 = 1 / 2: tensor-core
- * kernel (1: tf32 mma; 2: bf16 mma + ldmatrix; fp32 accumulate), which can also re-materialise the forward output att = softmax(.) V [rows][inner]
+/* per-(field, head) core backward: dqkv written; dq_gamma, dk_gamma, dbias_table accumulated.  use_tf32 = 1 / 2 / 3: tensor-core
+ * kernel (1: tf32 mma; 2: bf16 mma + ldmatrix on fp32 tensors; 3: the same kernel with qkv, datt, dqkv and att_out as bf16
+ * tensors; fp32 accumulate), which can also re-materialise the forward output att = softmax(.) V [rows][inner]
  * (att_out, or NULL) for the to_out weight gradient when the forward pass was the fused kernel; 0: exact-fp32 SIMT kernel.
- * drop_thresh > 0 (bf16 kernel only): the forward pass applied dropout to the probabilities with these parameters. */
-VG_API int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
-                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, long long drop_seed,
+ * drop_thresh > 0 (bf16 kernels only): the forward pass applied dropout to the probabilities with these parameters. */
+VG_API int vg_attn_core_bwd(const void* qkv, const void* datt, const float* q_gamma, const float* k_gamma,
+                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, void* dqkv,
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, void* att_out, long long drop_seed,
                      int drop_salt, int drop_thresh, void* stream);
 /* LayerNorm + FiLM backward with the inverse partition; dx_in written (= dx + dx_out), dreg_in and dfilm accumulated */
 VG_API int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,

@@ -73,10 +73,13 @@ def attention(x: torch.Tensor, cond: torch.Tensor, sd, p: str, *, heads: int, wi
     to_out output (:151); both already contain the 1/(1-p) scale."""
     Nw, S, D = x.shape
     N = cond.shape[0]
-    x = F.layer_norm(x, (D,))                                         # no affine when cond_dim is set (:137)
-    gamma, beta = film(cond, sd, p)
-    rep = Nw // N
-    x = x * gamma.repeat_interleave(rep, 0)[:, None, :] + beta.repeat_interleave(rep, 0)[:, None, :]
+    if (p + "film.0.weight") in sd:
+        x = F.layer_norm(x, (D,))                                     # no affine when cond_dim is set (:137)
+        gamma, beta = film(cond, sd, p)
+        rep = Nw // N
+        x = x * gamma.repeat_interleave(rep, 0)[:, None, :] + beta.repeat_interleave(rep, 0)[:, None, :]
+    else:                                                             # cond_dim=None: LayerNorm with affine, no FiLM (:128-137)
+        x = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"])
     qkv = F.linear(x, sd[p + "to_qkv.weight"])
     inner = qkv.shape[-1] // 3
     dh = inner // heads
@@ -123,8 +126,12 @@ def maxvit_forward(x: torch.Tensor, cond: torch.Tensor, sd, *, prefix: str = "",
     gidx = grid_pixel_index(H, W, window).reshape(-1)
     regs_out = None
     for li in range(depth):
-        mb = f"{prefix}layers.{li}.0." + ("" if li == 0 else "fn.")
-        x = mbconv(x, sd, mb, residual=(li != 0), training=training)
+        # MBConvResidual (key level ".fn.") wraps every layer that is not the first of its stage (maxvit.py:99-100, 270);
+        # with a tuple depth the first layer of a stage also changes the width
+        residual = (f"{prefix}layers.{li}.0.fn.0.weight") in sd
+        mb = f"{prefix}layers.{li}.0." + ("fn." if residual else "")
+        x = mbconv(x, sd, mb, residual=residual, training=training)
+        D = x.shape[1]
         flat = x.reshape(N, D, H * W).permute(0, 2, 1)                        # (N, HW, D)
         # block attention on (registers ++ window tokens); residual covers registers too (:310)
         tok = flat[:, bidx].reshape(N * nwin, window * window, D)

@@ -134,6 +134,79 @@ def maxvit_spec(dim: int, depth: int, cond_dim: int, heads: int, dim_head: int, 
     return spec
 
 
+def maxvit_stage_dims(dim: int, depth) -> list:
+    """(dim_in, dim_out, first_of_stage) of every layer, as maxvit.py:240-262 builds them.  int depth: one stage at constant
+    width.  Tuple depth (d0, d1, ...): widths dim, 2 dim, 4 dim, ...; ``zip(dim_pairs, depth)`` pairs stage k = (2^k dim ->
+    2^(k+1) dim) with depth d_k and silently drops the last entry (quirk Q9), so len(depth) - 1 stages exist."""
+    if isinstance(depth, int):
+        return [(dim, dim, i == 0) for i in range(depth)]
+    dims = [(2 ** i) * dim for i in range(len(depth))]
+    pairs = list(zip(dims[:-1], dims[1:])) if len(depth) > 1 else [(dim, dim)]
+    out = []
+    for (d_in, d_out), n in zip(pairs, depth):
+        for i in range(n):
+            out.append((d_in if i == 0 else d_out, d_out, i == 0))
+    return out
+
+
+def maxvit_multistage_spec(dim: int, depth, cond_dim: int, heads: int, dim_head: int, window: int, expansion: float,
+                           shrink: float, num_reg: int) -> "OrderedDict[str, tuple]":
+    """name -> (shape, kind) of a MaxViT built with a tuple ``depth`` (maxvit.py:240-287)"""
+    spec: "OrderedDict[str, tuple]" = OrderedDict()
+    inner = heads * dim_head
+    for li, (d_in, d, first) in enumerate(maxvit_stage_dims(dim, depth)):
+        hidden = int(expansion * d)
+        se = int(hidden * shrink)
+        mb = f"layers.{li}.0." + ("" if (first or d_in != d) else "fn.")
+        spec[mb + "0.weight"] = ((hidden, d_in, 1, 1), "w")
+        spec[mb + "0.bias"] = ((hidden,), "b")
+        for bn, ch in (("1", hidden), ("4", hidden), ("8", d)):
+            spec[mb + bn + ".weight"] = ((ch,), "pos")
+            spec[mb + bn + ".bias"] = ((ch,), "b")
+            spec[mb + bn + ".running_mean"] = ((ch,), "b")
+            spec[mb + bn + ".running_var"] = ((ch,), "pos")
+            spec[mb + bn + ".num_batches_tracked"] = ((), "count")
+        spec[mb + "3.weight"] = ((hidden, 1, 3, 3), "w")
+        spec[mb + "3.bias"] = ((hidden,), "b")
+        spec[mb + "6.gate.1.weight"] = ((se, hidden), "w")
+        spec[mb + "6.gate.3.weight"] = ((hidden, se), "w")
+        spec[mb + "7.weight"] = ((d, hidden, 1, 1), "w")
+        spec[mb + "7.bias"] = ((d,), "b")
+        for ai in (1, 2):
+            at = f"layers.{li}.{ai}."
+            spec[at + "film.0.weight"] = ((2 * d, cond_dim), "w1")
+            spec[at + "film.0.bias"] = ((2 * d,), "b")
+            spec[at + "film.2.weight"] = ((2 * d, 2 * d), "w")
+            spec[at + "film.2.bias"] = ((2 * d,), "film_b")
+            spec[at + "to_qkv.weight"] = ((3 * inner, d), "w")
+            spec[at + "q_norm.gamma"] = ((heads, 1, dim_head), "pos")
+            spec[at + "k_norm.gamma"] = ((heads, 1, dim_head), "pos")
+            spec[at + "to_out.0.weight"] = ((d, inner), "w")
+            spec[at + "rel_pos_bias.weight"] = (((2 * window - 1) ** 2 + 1, heads), "w1")
+        spec[f"register_tokens.{li}"] = ((num_reg, d), "w1")
+    return spec
+
+
+def attention_spec(dim: int, cond_dim, heads: int, dim_head: int, window: int) -> "OrderedDict[str, tuple]":
+    """stand-alone Attention (maxvit.py:106-168); cond_dim None: LayerNorm carries an affine and there is no FiLM MLP"""
+    inner = heads * dim_head
+    spec: "OrderedDict[str, tuple]" = OrderedDict()
+    if cond_dim is None:
+        spec["norm.weight"] = ((dim,), "pos")
+        spec["norm.bias"] = ((dim,), "b")
+    else:
+        spec["film.0.weight"] = ((2 * dim, cond_dim), "w1")
+        spec["film.0.bias"] = ((2 * dim,), "b")
+        spec["film.2.weight"] = ((2 * dim, 2 * dim), "w")
+        spec["film.2.bias"] = ((2 * dim,), "film_b")
+    spec["to_qkv.weight"] = ((3 * inner, dim), "w")
+    spec["q_norm.gamma"] = ((heads, 1, dim_head), "pos")
+    spec["k_norm.gamma"] = ((heads, 1, dim_head), "pos")
+    spec["to_out.0.weight"] = ((dim, inner), "w")
+    spec["rel_pos_bias.weight"] = (((2 * window - 1) ** 2 + 1, heads), "w1")
+    return spec
+
+
 def metnet3_spec(cfg: GridConfig) -> "OrderedDict[str, tuple]":
     """name -> (shape, kind) of every persistent tensor of the reference MetNet3."""
     d = cfg.dim

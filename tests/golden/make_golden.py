@@ -87,6 +87,41 @@ def maxvit_fixture():
                                  x=x, cond=cond, y=y))
 
 
+def maxvit_multistage_fixture():
+    """tuple depth (maxvit.py:240-262): depth (2, 1) from width 64 builds ONE stage 64 -> 128 of two layers (quirk Q9)"""
+    dim, depth, heads, dh, w, r, N, H, W = 64, (2, 1), 4, 32, 7, 4, 2, 14, 21
+    m = ref_maxvit.MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w,
+                          num_register_tokens=r).eval()
+    sd = synth.make_state_dict(synth.maxvit_multistage_spec(dim, depth, 2, heads, dh, w, 4, 0.25, r), seed=6)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, dim, H, W, generator=g)
+    cond = torch.randn(N, 2, generator=g)
+    with torch.no_grad():
+        y = m(x, cond)
+    assert y.shape == (N, 2 * dim, H, W)
+    save("maxvit_multistage.pt", dict(dim=dim, depth=depth, heads=heads, dim_head=dh, window=w, num_reg=r, seed=6,
+                                      x=x, cond=cond, y=y, keys=list(m.state_dict().keys())))
+
+
+def attention_standalone_fixture():
+    """stand-alone Attention.forward (maxvit.py:170-219) at a kernel-sized width, with FiLM conditioning and with
+    cond_dim=None (LayerNorm affine, no FiLM: maxvit.py:128-137)"""
+    dim, heads, dh, w, r, N, nwin = 128, 4, 32, 7, 4, 2, 3
+    out = dict(dim=dim, heads=heads, dim_head=dh, window=w, num_reg=r)
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(N * nwin, r + w * w, dim, generator=g)
+    cond = torch.randn(N, 2, generator=g)
+    for name, cd in (("film", 2), ("nocond", None)):
+        att = ref_maxvit.Attention(dim=dim, cond_dim=cd, heads=heads, dim_head=dh, dropout=0.1, window_size=w, num_registers=r).eval()
+        sd = synth.make_state_dict(synth.attention_spec(dim, cd, heads, dh, w), seed=8)
+        att.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out[name] = att(x, cond)          # cond is required positionally even without FiLM (maxvit.py:172,177)
+    out.update(x=x, cond=cond, seed=8)
+    save("attention_standalone.pt", out)
+
+
 def metnet3_fixture(name, cfg, B, wseed, iseed):
     m = ref_metnet3.MetNet3(**cfg.metnet3_kwargs()).eval()
     sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=wseed)
@@ -145,6 +180,12 @@ def metnet3_train_fixture(name, cfg, B, wseed, iseed):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":      # the fixtures added in round 2 only
+        maxvit_multistage_fixture()
+        attention_standalone_fixture()
+        sys.exit(0)
+    maxvit_multistage_fixture()
+    attention_standalone_fixture()
     index_fixtures()
     attention_fixture()
     maxvit_fixture()

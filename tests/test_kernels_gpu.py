@@ -448,3 +448,63 @@ def test_focal_r_forward_backward():
         loss.backward()
         assert abs(loss.item() - focal_r(p.double(), t.double(), mse=mse).item()) / focal_r(p, t, mse=mse).item() < 1e-4
         assert rel_err(pd.grad, focal_r_grad(p, t, mse=mse)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ API corners (round 2)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_multistage_maxvit_golden_from_reference(golden, precision, tol):
+    """MaxViT(depth=(2, 1)) from width 64: ONE stage 64 -> 128 of two layers (the reference's zip() drops the last depth entry,
+    maxvit.py:240-262); the first MBConv widens the map and has no residual"""
+    from vit_grid_model_b200 import MaxViT
+    f = golden("maxvit_multistage.pt")
+    m = MaxViT(dim=f["dim"], depth=f["depth"], cond_dim=2, heads=f["heads"], dim_head=f["dim_head"], vit_window_size=f["window"],
+               num_register_tokens=f["num_reg"])
+    assert list(m.state_dict().keys()) == f["keys"]
+    sd = synth.make_state_dict(synth.maxvit_multistage_spec(f["dim"], f["depth"], 2, f["heads"], f["dim_head"], f["window"], 4, 0.25,
+                                                            f["num_reg"]), seed=f["seed"])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision(precision)
+    with torch.no_grad():
+        y = m(f["x"].cuda(), f["cond"].cuda())
+    assert y.shape == f["y"].shape and rel_err(y, f["y"]) < tol
+
+
+@pytest.mark.parametrize("variant,cond_dim", [("film", 2), ("nocond", None)])
+def test_standalone_attention_golden_from_reference(golden, variant, cond_dim):
+    """Attention.forward(x, cond) called on its own (maxvit.py:170-219), with FiLM and with cond_dim=None"""
+    from vit_grid_model_b200 import Attention
+    f = golden("attention_standalone.pt")
+    a = Attention(dim=f["dim"], cond_dim=cond_dim, heads=f["heads"], dim_head=f["dim_head"], dropout=0.1, window_size=f["window"],
+                  num_registers=f["num_reg"])
+    a.load_state_dict(synth.make_state_dict(synth.attention_spec(f["dim"], cond_dim, f["heads"], f["dim_head"], f["window"]), seed=f["seed"]),
+                      strict=True)
+    a = a.cuda().eval()
+    y = a(f["x"].cuda(), f["cond"].cuda())
+    assert y.shape == f[variant].shape and rel_err(y, f[variant]) < 1e-4
+
+
+def test_maxvit_module_trains_standalone():
+    """MaxViT.forward in train() mode is differentiable (x, cond, parameters) like the reference module under autograd"""
+    from vit_grid_model_b200 import MaxViT
+    dim, depth, heads, dh, w, R, N, H, W = 128, 1, 32, 32, 7, 4, 2, 14, 21
+    sd = synth.make_state_dict(synth.maxvit_spec(dim, depth, 2, heads, dh, w, 4, 0.25, R), seed=5)
+    for v in sd.values():
+        if v.is_floating_point() and v.dim() > 0:
+            v.requires_grad_(True)
+    x, cond, dy = rnd(N, dim, H, W, seed=1).requires_grad_(True), rnd(N, 2, seed=2).requires_grad_(True), rnd(N, dim, H, W, seed=3)
+    ref = mo.maxvit_forward(x, cond, {k: v for k, v in sd.items()}, depth=depth, heads=heads, window=w, num_reg=R, training=True)
+    ref.backward(dy)
+    m = MaxViT(dim=dim, depth=depth, cond_dim=2, heads=heads, dim_head=dh, vit_window_size=w, num_register_tokens=R, dropout=0.0)
+    m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    m = m.cuda().train().set_precision("fp32")
+    xc, cc = x.detach().cuda().requires_grad_(True), cond.detach().cuda().requires_grad_(True)
+    y = m(xc, cc)
+    y.backward(dy.cuda())
+    assert rel_err(y, ref) < 1e-4
+    assert rel_err(xc.grad, x.grad) < 1e-3 and rel_err(cc.grad, cond.grad) < 1e-3
+    for k, p in m.named_parameters():
+        if "running_" in k or sd[k].grad is None:
+            continue
+        if k.endswith((".0.0.bias", ".0.3.bias", ".0.7.bias")):
+            continue                                            # conv bias in front of a batch-statistic BatchNorm: zero gradient
+        assert rel_err(p.grad, sd[k].grad) < 2e-3, k

@@ -100,3 +100,24 @@ def test_sample_chunking_is_exact():
     # and the scramble really couples samples: chunking the INPUT (timestamps included) changes the answer
     y3 = torch.cat([metnet3_forward(x[b:b + 1], ts[b:b + 1], sd, cfg) for b in range(5)])
     assert (y3 - y).abs().max() > 1e-4
+
+
+def test_multistage_maxvit_matches_reference(golden):
+    """tuple depth (maxvit.py:240-262, quirk Q9): golden from the real reference"""
+    f = golden("maxvit_multistage.pt")
+    spec = synth.maxvit_multistage_spec(f["dim"], f["depth"], 2, f["heads"], f["dim_head"], f["window"], 4, 0.25, f["num_reg"])
+    assert list(spec.keys()) == [k for k in f["keys"]] or set(spec.keys()) == set(f["keys"])
+    sd = synth.make_state_dict(spec, seed=f["seed"])
+    n_layers = len(synth.maxvit_stage_dims(f["dim"], f["depth"]))
+    assert n_layers == 2                                  # depth (2, 1): the trailing entry is dropped by zip()
+    y = maxvit_forward(f["x"], f["cond"], sd, depth=n_layers, heads=f["heads"], window=f["window"], num_reg=f["num_reg"])
+    assert y.shape == f["y"].shape == (2, 128, 14, 21)
+    torch.testing.assert_close(y, f["y"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("variant,cond_dim", [("film", 2), ("nocond", None)])
+def test_standalone_attention_matches_reference(golden, variant, cond_dim):
+    f = golden("attention_standalone.pt")
+    sd = synth.make_state_dict(synth.attention_spec(f["dim"], cond_dim, f["heads"], f["dim_head"], f["window"]), seed=f["seed"])
+    y = attention(f["x"], f["cond"], sd, "", heads=f["heads"], window=f["window"], num_reg=f["num_reg"])
+    torch.testing.assert_close(y, f[variant], rtol=1e-4, atol=1e-4)

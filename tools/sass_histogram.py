@@ -1,7 +1,8 @@
 """Per-kernel SASS opcode histogram of the built library (evidence for the tcgen05 / TMA claims):
     python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt
 Counts, per kernel of vit-grid-model_b200/libvitgrid.so, the tensor-core and TMA mnemonics B200_PROFILING.md names
-(UTCHMMA / UTCQMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA load / store, UBLKCP = bulk copy,
+(UTCHMMA / UTCQMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG / UTMAREDG = TMA load / store / reduce-store,
+UBLKCP = bulk copy,
 HMMA = legacy mma.sync) and the ten most frequent opcodes."""
 import collections
 import os
@@ -11,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vit-grid-model_b200", "libvitgrid.so")
-KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "HMMA", "SYNCS", "MUFU", "LDGSTS")
+KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "HMMA", "SYNCS", "MUFU", "LDGSTS")
 
 
 def main():
@@ -26,7 +27,7 @@ def main():
         if m and cur is not None:
             cur[m.group(1)] += 1
             full = m.group(1) + m.group(2)
-            if m.group(1) in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTCQMMA"):
+            if m.group(1) in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCQMMA"):
                 cur["~" + full] += 1
     total = collections.Counter()
     demangle = subprocess.run(["cu++filt"] + list(per), capture_output=True, text=True).stdout.splitlines() if per else []
@@ -36,7 +37,7 @@ def main():
         for k, v in cnt.items():
             if k in KEY:
                 total[k] += v
-        if not any(k in cnt for k in ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "HMMA", "LDTM")) and "-v" not in sys.argv:
+        if not any(k in cnt for k in ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "HMMA", "LDTM")) and "-v" not in sys.argv:
             continue
         n = sum(v for k, v in cnt.items() if not k.startswith("~"))
         short = re.sub(r"\(.*", "", pretty)[:110]

@@ -261,10 +261,10 @@ int vg_attn_partition_debug(int N, int Hl, int Wl, int win, int R, int grid_mode
 }
 
 int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, int N, int Hl,
-                       int Wl, int C, int win, int R, int grid_mode, float ln_eps, void* tokens, void* stream) {
+                       int Wl, int C, int win, int R, int grid_mode, float ln_eps, void* tokens, int tokens_bf16, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
-  return attn_gather_run(dtype, x, reg, reg_per_field, film, g, ln_eps, tokens, (cudaStream_t)stream);
+  return attn_gather_run(dtype, x, reg, reg_per_field, film, g, ln_eps, tokens, tokens_bf16, (cudaStream_t)stream);
 }
 
 int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma, const float* bias_table,
@@ -483,10 +483,11 @@ int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float*
 }
 
 int vg_attn_out_bwd_gather(const float* dx_out, const float* dreg, float reg_scale, int N, int Hl, int Wl, int C, int win,
-                           int R, int grid_mode, float* dproj, long long drop_seed, int drop_salt, int drop_thresh, void* stream) {
+                           int R, int grid_mode, void* dproj, int dproj_bf16, long long drop_seed, int drop_salt, int drop_thresh,
+                           void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
-  return attn_out_bwd_gather_run(dx_out, dreg, reg_scale, g, dproj, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh,
+  return attn_out_bwd_gather_run(dx_out, dreg, reg_scale, g, dproj, dproj_bf16, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh,
                                  (cudaStream_t)stream);
 }
 
@@ -497,14 +498,14 @@ int vg_dropout_mask_debug(long long drop_seed, int drop_salt, int drop_thresh, l
                                 (cudaStream_t)stream);
 }
 
-int vg_attn_core_bwd(const float* qkv, const float* datt, const float* q_gamma, const float* k_gamma,
-                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, float* dqkv,
-                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, float* att_out, long long drop_seed,
+int vg_attn_core_bwd(const void* qkv, const void* datt, const float* q_gamma, const float* k_gamma,
+                     const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, void* dqkv,
+                     float* dq_gamma, float* dk_gamma, float* dbias_table, int use_tf32, void* att_out, long long drop_seed,
                      int drop_salt, int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
-  return attn_core_bwd_run(qkv, datt, q_gamma, k_gamma, bias_table, g, heads, dh, dqkv, dq_gamma, dk_gamma, dbias_table,
-                           use_tf32, att_out, (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh, (cudaStream_t)stream);
+  return attn_core_bwd_run(reinterpret_cast<const float*>(qkv), reinterpret_cast<const float*>(datt), q_gamma, k_gamma, bias_table, g, heads, dh, reinterpret_cast<float*>(dqkv), dq_gamma, dk_gamma, dbias_table,
+                           use_tf32, reinterpret_cast<float*>(att_out), (unsigned)drop_seed, (unsigned)drop_salt, drop_thresh, (cudaStream_t)stream);
 }
 
 int vg_attn_gather_bwd(const float* x, const float* reg, int reg_per_field, const float* film, const float* dtok,

@@ -26,10 +26,10 @@ __global__ void attn_partition_debug_kernel(const AttnGeom g, long long* __restr
   out[r] = tok < g.R ? -1 : (long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R);
 }
 
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ x, const float* __restrict__ reg, int reg_per_field,
                                                           const float* __restrict__ film, const AttnGeom g, float eps,
-                                                          T* __restrict__ tokens, long long rows) {
+                                                          TO* __restrict__ tokens, long long rows) {
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -59,12 +59,12 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
   for (int i = 0; i < 4 * nv; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
   const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);             // nn.LayerNorm, no affine (maxvit.py:137)
   const float* gam = film + (long long)n * 2 * C;                        // [gamma | beta], used raw (maxvit.py:187)
-  T* dst = tokens + r * C;
+  TO* dst = tokens + r * C;
   for (int i = 0; i < nv; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = i * 128 + lane * 4 + j;
-      Act<T>::st(dst + c, v[4 * i + j] * rstd * gam[c] + gam[C + c]);
+      Act<TO>::st(dst + c, v[4 * i + j] * rstd * gam[c] + gam[C + c]);
     }
 }
 
@@ -147,13 +147,15 @@ __global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qk
   }
 }
 
+// out_bf16: fp32 residual stream in, bf16 tokens out (the mixed-precision training backward re-materialises tokens in 16 bits)
 int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
-                    float eps, void* tokens, cudaStream_t st) {
+                    float eps, void* tokens, int out_bf16, cudaStream_t st) {
   if (g.C % 128 || g.C > 512) return set_error("attn_gather: C=%d must be a multiple of 128 (<=512)", g.C);
   const long long rows = (long long)g.N * g.nwin() * g.S();
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (dtype == 0) attn_gather_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<bf16*>(tokens), rows);
-  else attn_gather_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<float*>(tokens), rows);
+  if (dtype == 0) attn_gather_kernel<bf16, bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<bf16*>(tokens), rows);
+  else if (out_bf16) attn_gather_kernel<float, bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<bf16*>(tokens), rows);
+  else attn_gather_kernel<float, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reg, reg_per_field, film, g, eps, reinterpret_cast<float*>(tokens), rows);
   return check_launch("attn_gather_kernel");
 }
 

@@ -310,7 +310,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
       }
       if (TRAIN && xo) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) st8(xo + ch * 32 + j, xh + j);
+        for (int j = 0; j < 32; j += 16) st16_256(xo + ch * 32 + j, xh + j);
       }
       if (rf || r || rtma) {
 #pragma unroll
@@ -334,7 +334,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
       if (TRAIN && xo) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) st8(xo + ch * 32 + j, v + j);
+        for (int j = 0; j < 32; j += 16) st16_256(xo + ch * 32 + j, v + j);
       }
     }
     if (TRAIN && ep.relu_mask) ep.relu_mask[row * 4 + ch] = mbits;

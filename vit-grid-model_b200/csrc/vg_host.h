@@ -95,7 +95,7 @@ int focal_r_bwd_run(const float* pred, const float* tgt, long long n, float beta
 // attention (vg_attn.cu); AttnGeom / attn_token_pixel live in vg_common.cuh
 int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st);
 int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
-                    float eps, void* tokens, cudaStream_t st);
+                    float eps, void* tokens, int out_bf16, cudaStream_t st);
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
                   const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st);
 
@@ -160,8 +160,8 @@ int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long 
 int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
                const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,
                long long work_elems, cudaStream_t st);
-int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, float* dproj, unsigned seed,
-                            unsigned salt, int drop_thresh, cudaStream_t st);
+int attn_out_bwd_gather_run(const float* dx_out, const float* dreg, float reg_scale, const AttnGeom& g, void* dproj, int out_bf16,
+                            unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
 int dropout_mask_debug_run(unsigned seed, unsigned salt, int drop_thresh, long long n_windows, int heads, int C, unsigned char* prob_mask,
                            unsigned char* out_mask, cudaStream_t st);
 int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,

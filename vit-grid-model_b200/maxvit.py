@@ -72,25 +72,61 @@ def rel_pos_indices(window_size: int, num_registers: int) -> torch.Tensor:
 
 
 class Attention(nn.Module):
-    """parameter holder for one window/grid attention (maxvit.py:106-168)"""
+    """One window / grid attention (maxvit.py:106-219).  Inside ``MaxViT`` it is a parameter holder -- the partition, the
+    register tokens and the residual are fused around it (``MaxViT.forward_cl``).  Called on its own it has the reference's
+    ``forward(x, cond)``: x (Nw, num_registers + window_size^2, dim) token sequences -> to_out(attention(x)) without the
+    residual; ``cond_dim=None`` gives the un-conditioned variant (LayerNorm with affine, no FiLM, maxvit.py:128-137)."""
 
     def __init__(self, dim, cond_dim=None, heads=32, dim_head=32, dropout=0., window_size=8, num_registers=1):
         super().__init__()
         assert num_registers > 0
         assert (dim % dim_head) == 0, 'dimension should be divisible by dimension per head'
-        if cond_dim is None:
-            raise NotImplementedError("vit_grid_model_b200.Attention requires cond_dim (FiLM conditioning), as MaxViT always passes it")
         inner = dim_head * heads
         self.dim, self.heads, self.dim_head = dim, heads, dim_head
         self.window_size, self.num_registers, self.dropout_p = window_size, num_registers, dropout
-        self.film = nn.Sequential(nn.Linear(cond_dim, dim * 2), nn.SiLU(), nn.Linear(dim * 2, dim * 2), nn.Identity())
-        self.norm = nn.LayerNorm(dim, elementwise_affine=False)
+        self.has_cond = cond_dim is not None
+        self.film = None
+        if self.has_cond:
+            self.film = nn.Sequential(nn.Linear(cond_dim, dim * 2), nn.SiLU(), nn.Linear(dim * 2, dim * 2), nn.Identity())
+        self.norm = nn.LayerNorm(dim, elementwise_affine=not self.has_cond)
         self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
         self.q_norm = RMSNorm(dim_head, heads=heads)
         self.k_norm = RMSNorm(dim_head, heads=heads)
         self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), nn.Dropout(dropout))
         self.rel_pos_bias = nn.Embedding((2 * window_size - 1) ** 2 + 1, heads)
         self.register_buffer('rel_pos_indices', rel_pos_indices(window_size, num_registers), persistent=False)
+
+    @torch.no_grad()
+    def forward(self, x, cond=None):
+        """reference signature (maxvit.py:170): x (Nw, S, dim), cond (b, cond_dim) with Nw a multiple of b (window sequences
+        field-major, as ``MaxViT`` packs them).  Inference only (eval mode, or dropout 0): the training path of the package is
+        ``MetNet3`` / ``MaxViT`` in train() mode."""
+        _lib.require_device()
+        if not x.is_cuda:
+            raise _lib.VitGridError("vit_grid_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError("stand-alone Attention.forward is the inference path; train through MaxViT / MetNet3")
+        Nw, S, D = x.shape
+        w, R = self.window_size, self.num_registers
+        assert S == R + w * w and D == self.dim
+        if D % 128 or D > 512:
+            raise NotImplementedError("the attention kernels are built for dim = 128, 256, 384, 512")
+        x = x.float().contiguous()
+        if self.has_cond:
+            assert cond is not None and Nw % cond.shape[0] == 0
+            f = self.film
+            gb = ops.cond_mlp(cond.float().contiguous(), f[0].weight.float().contiguous(), f[0].bias.float().contiguous(),
+                              f[2].weight.float().contiguous(), f[2].bias.float().contiguous())
+            film = gb.repeat_interleave(Nw // cond.shape[0], dim=0).contiguous()          # one FiLM row per window
+        else:                                                    # LayerNorm affine == FiLM with (weight, bias) for every window
+            film = torch.cat([self.norm.weight, self.norm.bias]).float().expand(Nw, 2 * D).contiguous()
+        # every window sequence as a one-window "field": the gather kernel's block partition of a (w x w) map is the identity
+        tokens = ops.attn_gather(x[:, R:].reshape(Nw, w, w, D).contiguous(), x[:, :R].contiguous(), film, w, R, False,
+                                 eps=self.norm.eps)
+        qkv = ops.gemm(tokens, self.to_qkv.weight.float().contiguous())
+        att = ops.attn_core(qkv, self.q_norm.gamma.float().reshape(-1).contiguous(), self.k_norm.gamma.float().reshape(-1).contiguous(),
+                            self.rel_pos_bias.weight.float().contiguous(), Nw, w, w, w, R, self.heads, self.dim_head)
+        return ops.gemm(att, self.to_out[0].weight.float().contiguous()).view(Nw, S, D)
 
 
 def _fold_bn(conv_bias, bn: nn.BatchNorm2d):
@@ -106,23 +142,28 @@ class MaxViT(nn.Module):
         super().__init__()
         depth = (depth,) if isinstance(depth, int) else tuple(depth)
         assert num_register_tokens > 0
-        if len(depth) != 1:
-            # the reference builds len(depth)-1 stages of doubling width for tuples (maxvit.py:246-262); MetNet3
-            # only ever passes an int
-            raise NotImplementedError("vit_grid_model_b200.MaxViT supports a single stage (int depth)")
         self.cond_dim = cond_dim
         self.dim, self.heads, self.dim_head = dim, heads, dim_head
         self.vit_window_size = vit_window_size
         self.num_register_tokens = num_register_tokens
         self.layers = nn.ModuleList([])
         self.register_tokens = nn.ParameterList([])
-        for stage_ind in range(depth[0]):
-            conv = MBConv(dim, dim, downsample=(stage_ind == 0), expansion_rate=mbconv_expansion_rate,
-                          shrinkage_rate=mbconv_shrinkage_rate)
-            kw = dict(dim=dim, cond_dim=cond_dim, heads=heads, dim_head=dim_head, dropout=dropout,
-                      window_size=vit_window_size, num_registers=num_register_tokens)
-            self.layers.append(nn.ModuleList([conv, Attention(**kw), Attention(**kw)]))
-            self.register_tokens.append(nn.Parameter(torch.randn(num_register_tokens, dim)))
+        # Stage widths dim, 2 dim, 4 dim, ...: stage k maps width 2^k dim -> 2^(k+1) dim in its first layer.  The reference
+        # pairs the (in, out) widths with `depth` through zip(), which drops the LAST depth entry: a tuple of n entries builds
+        # n - 1 stages (maxvit.py:240-251, quirk Q9); an int builds one stage of constant width.
+        widths = [dim * 2 ** i for i in range(len(depth))]
+        stages = list(zip(widths[:-1], widths[1:])) if len(depth) > 1 else [(dim, dim)]
+        for (w_in, w_out), n_layers in zip(stages, depth):
+            for k in range(n_layers):
+                conv = MBConv(w_in if k == 0 else w_out, w_out, downsample=(k == 0), expansion_rate=mbconv_expansion_rate,
+                              shrinkage_rate=mbconv_shrinkage_rate)
+                kw = dict(dim=w_out, cond_dim=cond_dim, heads=heads, dim_head=dim_head, dropout=dropout,
+                          window_size=vit_window_size, num_registers=num_register_tokens)
+                self.layers.append(nn.ModuleList([conv, Attention(**kw), Attention(**kw)]))
+                self.register_tokens.append(nn.Parameter(torch.randn(num_register_tokens, w_out)))
+        self.dim_out = stages[-1][1] if len(self.layers) else dim
+        if cond_dim is None:
+            raise NotImplementedError("MaxViT needs cond_dim: the reference's forward asserts cond.shape == (b, cond_dim) (maxvit.py:290)")
         self.set_precision("bf16")
         self.fused_attention = True      # one-kernel attention (tf32 mode, dim 128, dim_head 32, <=64 tokens/window)
         self._packed = None
@@ -172,6 +213,12 @@ class MaxViT(nn.Module):
                     q_gamma=att.q_norm.gamma.float().reshape(-1).contiguous(),
                     k_gamma=att.k_norm.gamma.float().reshape(-1).contiguous(),
                     w_out=att.to_out[0].weight.to(dtype).contiguous(),
+                    # transposed / 16-bit copies for the backward GEMMs (packed once per weight version, not once per step)
+                    w_out_t=att.to_out[0].weight.to(dtype).t().contiguous(),
+                    w_qkv_t=att.to_qkv.weight.to(dtype).t().contiguous(),
+                    w_qkv_bf16=att.to_qkv.weight.to(torch.bfloat16).contiguous(),
+                    w_out_t_bf16=att.to_out[0].weight.to(torch.bfloat16).t().contiguous(),
+                    w_qkv_t_bf16=att.to_qkv.weight.to(torch.bfloat16).t().contiguous(),
                     bias_table=att.rel_pos_bias.weight.float().contiguous())
                 inner, dh, hd = att.heads * att.dim_head, att.dim_head, att.heads
                 wq = att.to_qkv.weight.float()
@@ -224,13 +271,14 @@ class MaxViT(nn.Module):
                 # the squeeze-excite scale rides on per-field projection weights (256 KB per field) instead of a
                 # read-modify-write pass over the hidden activations
                 wn = ops.se_fold_weights(P["w_proj"], gate)
-                y = ops.gemm(h2.view(N * H * W, hidden), wn, rows_per_batch=H * W, b_rows_per_batch=C, scale=P["s_proj"],
+                y = ops.gemm(h2.view(N * H * W, hidden), wn, rows_per_batch=H * W, b_rows_per_batch=P["w_proj"].shape[0], scale=P["s_proj"],
                              shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
             else:
                 ops.se_scale_(h2, gate)
                 y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],
                              res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
             del h2
+            C = y.shape[1]                                       # the first layer of a stage of a tuple-depth MaxViT widens the map
             x = y.view(N, H, W, C)
             cap = self._capture
             if cap is not None:
@@ -246,11 +294,27 @@ class MaxViT(nn.Module):
             x, _ = self._attention(x, film, fg, reg, True, False)
         return x
 
+    def next_dropout_seed(self) -> int:
+        """32-bit seed of this step's dropout masks (see MetNet3.next_dropout_seed)"""
+        if getattr(self, "_dropout_state", None) is None:
+            self._dropout_state = torch.initial_seed() & 0x7FFFFFFF
+        self._dropout_state = (self._dropout_state * 1103515245 + 12345) & 0x7FFFFFFF
+        return self._dropout_state
+
     def forward(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
-        """reference signature (maxvit.py:289): x (N,dim,H,W) -> (N,dim,H,W), same dtype as x"""
+        """reference signature (maxvit.py:289): x (N,dim,H,W) -> (N,dim_out,H,W), same dtype as x.  In train() mode the module
+        runs the training kernels (batch-statistic BatchNorm, dropout) and is differentiable with respect to x, cond and its
+        parameters (train.MaxViTTrainFn), like the reference module under autograd."""
         assert cond.shape == (x.shape[0], self.cond_dim)
         if not x.is_cuda:
             raise _lib.VitGridError("vit_grid_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
-        x_cl = x.permute(0, 2, 3, 1).to(self.compute_dtype).contiguous()
-        y = self.forward_cl(x_cl, cond)
-        return y.permute(0, 3, 1, 2).to(x.dtype).contiguous()
+        with torch.cuda.device(x.device):
+            x_cl = x.permute(0, 2, 3, 1).to(self.compute_dtype).contiguous()
+            if self.training:
+                from .train import MaxViTTrainFn
+                if self.compute_dtype != torch.float32:
+                    raise NotImplementedError("MaxViT training supports set_precision('bf16') (mixed) and 'fp32'")
+                y = MaxViTTrainFn.apply(self, x_cl, cond.float().contiguous(), *self.parameters())
+            else:
+                y = self.forward_cl(x_cl, cond)
+            return y.permute(0, 3, 1, 2).to(x.dtype).contiguous()

@@ -212,14 +212,15 @@ def se_scale_(x, gate):
     return x
 
 
-def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None):
+def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None, out_bf16=False):
+    """out_bf16: bf16 tokens from an fp32 residual stream (16-bit attention backward chain of the training step)"""
     N, Hl, Wl, C = x.shape
     S = R + win * win
     rows = N * (Hl // win) * (Wl // win) * S
     if out is None:
-        out = torch.empty(rows, C, dtype=x.dtype, device=x.device)
+        out = torch.empty(rows, C, dtype=torch.bfloat16 if out_bf16 else x.dtype, device=x.device)
     _lib.call("vg_attn_gather_fwd", DT_CODE[x.dtype], x.data_ptr(), reg.data_ptr(), int(reg.dim() == 3), film.data_ptr(),
-              N, Hl, Wl, C, win, R, int(grid_mode), float(eps), out.data_ptr(), _st())
+              N, Hl, Wl, C, win, R, int(grid_mode), float(eps), out.data_ptr(), int(out.dtype == torch.bfloat16 and x.dtype != torch.bfloat16), _st())
     return out
 
 

@@ -244,12 +244,12 @@ def dropout_masks(drop, n_windows, heads, C):
     return pm, om
 
 
-def attn_out_bwd_gather(dx_out, dreg, reg_scale, win, R, grid_mode, drop=(0, 0, 0)):
+def attn_out_bwd_gather(dx_out, dreg, reg_scale, win, R, grid_mode, drop=(0, 0, 0), out_bf16=False):
     N, Hl, Wl, C = dx_out.shape
     rows = N * (Hl // win) * (Wl // win) * (R + win * win)
-    dproj = torch.empty(rows, C, dtype=torch.float32, device=dx_out.device)
+    dproj = torch.empty(rows, C, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dx_out.device)
     _lib.call("vg_attn_out_bwd_gather", dx_out.data_ptr(), _p(dreg), float(reg_scale), N, Hl, Wl, C, win, R, int(grid_mode),
-              dproj.data_ptr(), int(drop[0]), int(drop[1]), int(drop[2]), _st())
+              dproj.data_ptr(), int(out_bf16), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return dproj
 
 
@@ -257,9 +257,13 @@ def attn_core_bwd(qkv, datt, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, he
                   tf32=False, want_att=False, drop=(0, 0, 0)):
     """-> dqkv (, att = softmax(.) V re-materialised by the tensor-core kernel when want_att)"""
     dqkv = torch.empty_like(qkv)
-    att = torch.empty(qkv.shape[0], heads * dh, dtype=torch.float32, device=qkv.device) if want_att else None
-    # tensor-core variants: 2 = bf16 mma + ldmatrix (default), 1 = tf32 mma (VG_ATTN_BWD=tf32); 0 = exact-fp32 SIMT
+    att = torch.empty(qkv.shape[0], heads * dh, dtype=qkv.dtype, device=qkv.device) if want_att else None
+    # tensor-core variants: 2 = bf16 mma + ldmatrix (default), 1 = tf32 mma (VG_ATTN_BWD=tf32); 0 = exact-fp32 SIMT;
+    # 3 = the bf16 kernel on bf16 tensors (qkv, datt -> dqkv, att), selected by the dtype of qkv
     mode = 0 if not tf32 else (1 if os.environ.get("VG_ATTN_BWD", "bf16") == "tf32" else 2)
+    if qkv.dtype == torch.bfloat16:
+        assert datt.dtype == torch.bfloat16
+        mode = 3
     _lib.call("vg_attn_core_bwd", qkv.data_ptr(), datt.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
               bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, dqkv.data_ptr(), dq_gamma.data_ptr(), dk_gamma.data_ptr(),
               dbias_table.data_ptr(), mode, _p(att), int(drop[0]), int(drop[1]), int(drop[2]), _st())

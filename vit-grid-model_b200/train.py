@@ -169,30 +169,33 @@ def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out, drop=
 
 
 def _attention_train_bwd(vit, sv, P, att_mod, pre, G, cond, dcond, dx_out, dreg_res, reg_scale, dreg_in):
-    """-> dx_in.  dreg_in: accumulation target for the register-token input gradient ((R,C) param grad or (N,R,C))."""
+    """-> dx_in.  dreg_in: accumulation target for the register-token input gradient ((R,C) param grad or (N,R,C)).
+    Mixed precision (forward = the fused kernel): tokens, qkv, dproj, datt, dqkv and att -- everything between the fp32 residual
+    stream and the fp32 gradients -- are re-materialised and kept in bf16 (kind::f16 GEMMs, half the HBM bytes)."""
     x = sv["x"]
     N, H, W, C = x.shape
     w, R = vit.vit_window_size, vit.num_register_tokens
     tf32 = vit.tf32
     gm = sv["grid_mode"]
     recompute = "qkv" not in sv
+    lo = recompute and tf32                       # 16-bit backward chain
     if recompute:
-        tokens = ops.attn_gather(x, sv["reg_in"], sv["film"], w, R, gm)
-        qkv = ops.gemm(tokens, P["w_qkv"], tf32=tf32)
+        tokens = ops.attn_gather(x, sv["reg_in"], sv["film"], w, R, gm, out_bf16=lo)
+        qkv = ops.gemm(tokens, P["w_qkv_bf16"] if lo else P["w_qkv"], tf32=tf32 and not lo)
     else:
         tokens, qkv = sv["tokens"], sv["qkv"]
     drop = sv["drop"]
-    dproj = ot.attn_out_bwd_gather(dx_out, dreg_res, reg_scale, w, R, gm, drop=drop)
-    datt = ops.gemm(dproj, att_mod.to_out[0].weight.detach().t().contiguous(), tf32=tf32)
+    dproj = ot.attn_out_bwd_gather(dx_out, dreg_res, reg_scale, w, R, gm, drop=drop, out_bf16=lo)
+    datt = ops.gemm(dproj, P["w_out_t_bf16"] if lo else P["w_out_t"], tf32=tf32 and not lo)
     res = ot.attn_core_bwd(qkv, datt, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head,
                            G[pre + "q_norm.gamma"], G[pre + "k_norm.gamma"], G[pre + "rel_pos_bias.weight"], tf32=tf32,
                            want_att=recompute, drop=drop)
     dqkv, att = res if recompute else (res, sv["att"])
     del datt, qkv
-    ot.wgrad(dproj, att, G[pre + "to_out.0.weight"], tf32=tf32)
+    ot.wgrad(dproj, att, G[pre + "to_out.0.weight"], tf32=tf32 and not lo)
     del dproj, att
-    ot.wgrad(dqkv, tokens, G[pre + "to_qkv.weight"], tf32=tf32)
-    dtok = ops.gemm(dqkv, att_mod.to_qkv.weight.detach().t().contiguous(), tf32=tf32)
+    ot.wgrad(dqkv, tokens, G[pre + "to_qkv.weight"], tf32=tf32 and not lo)
+    dtok = ops.gemm(dqkv, P["w_qkv_t_bf16"] if lo else P["w_qkv_t"], tf32=tf32 and not lo, out_f32=True)
     del dqkv, tokens
     dfilm = torch.zeros(N, 2 * C, dtype=torch.float32, device=x.device)
     dx_in = ot.attn_gather_bwd(x, sv["reg_in"], sv["film"], dtok, dx_out, dreg_res, reg_scale, dreg_in, dfilm, w, R, gm)
@@ -290,6 +293,29 @@ def maxvit_train_backward(vit, saved, cond, dcond, dx, G, prefix):
                       tf32=tf32).view(N, H, W, C)
         del dh0, dh1
     return dx
+
+
+class MaxViTTrainFn(torch.autograd.Function):
+    """autograd node of a stand-alone ``MaxViT`` in train() mode (maxvit.py:289-341 under autograd): x CL (N,H,W,C) fp32,
+    cond (N,cond_dim) -> y CL; backward returns the gradients of x, cond and every parameter."""
+
+    @staticmethod
+    def forward(ctx, vit, x, cond, *params):
+        y, saved = maxvit_train_forward(vit, x, cond, seed=vit.next_dropout_seed())
+        ctx.vit, ctx.saved, ctx.cond = vit, saved, cond
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        vit = ctx.vit
+        if ctx.saved is None:
+            raise RuntimeError("MaxViT backward ran twice through the same forward (retain_graph is not supported)")
+        named = list(vit.named_parameters())
+        G = {n: torch.zeros(p.shape, dtype=torch.float32, device=p.device) for n, p in named}
+        dcond = torch.zeros_like(ctx.cond)
+        dx = maxvit_train_backward(vit, ctx.saved, ctx.cond, dcond, dy.float().contiguous(), G, "")
+        ctx.saved = None
+        return (None, dx, dcond, *[G[n] for n, _ in named])
 
 
 # ------------------------------------------------------------------------------------------------ MetNet3
