@@ -36,6 +36,9 @@ extern "C" {
 
 #define VG_DTYPE_BF16 0
 #define VG_DTYPE_FP32 1
+/* fp16 storage: vg_gemm_fwd operands (dtype 3, plain store epilogue; out_f32 = 3 stores fp16) and vg_dw3x3_fwd -- the hidden
+ * tensor of the MBConv block in mixed-precision inference (10-bit mantissa = what a tf32 MMA keeps of an fp32 operand) */
+#define VG_DTYPE_FP16 3
 
 VG_API int vg_version(void);
 VG_API const char* vg_last_error(void);
@@ -339,7 +342,9 @@ VG_API int vg_field_parts(long long HW);
 VG_API int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW, int C, void* stream);
 /* squeeze-excite scale folded into per-field weights of the following 1x1 projection: out[n][co][c] = W[co][c]*gate[n][c]
  * (fp32; consumed by vg_gemm_fwd with rows_per_batch = H*W, b_rows_per_batch = Cout) */
-VG_API int vg_se_fold_weights(const float* W, const float* gate, float* out, int N, int Cout, int C, void* stream);
+/* per-field projection weights out[n][co][c] = W[co][c] * gate[n][c] (the squeeze-excite scale folded into the 1x1 projection,
+ * maxvit.py:38-48,95); out fp32, or fp16 when out_f16 != 0 (inference keeps the MBConv hidden tensor in fp16) */
+VG_API int vg_se_fold_weights(const float* W, const float* gate, void* out, int out_f16, int N, int Cout, int C, void* stream);
 VG_API int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream);
 VG_API int vg_se_bwd(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
               const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,

@@ -468,8 +468,8 @@ int vg_field_dot(const float* a, const float* b, float* out, int N, long long HW
   return field_dot_run(a, b, out, N, HW, C, (cudaStream_t)stream);
 }
 
-int vg_se_fold_weights(const float* W, const float* gate, float* out, int N, int Cout, int C, void* stream) {
-  return se_fold_run(W, gate, out, N, Cout, C, (cudaStream_t)stream);
+int vg_se_fold_weights(const float* W, const float* gate, void* out, int out_f16, int N, int Cout, int C, void* stream) {
+  return se_fold_run(W, gate, out, out_f16, N, Cout, C, (cudaStream_t)stream);
 }
 
 int vg_se_scale_oop(const float* x, const float* gate, float* out, int N, long long HW, int C, void* stream) {

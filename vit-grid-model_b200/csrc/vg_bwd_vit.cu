@@ -214,6 +214,21 @@ template <> struct Ld4<bf16> {
   }
 };
 
+template <> struct Ld4<__half> {
+  static __device__ __forceinline__ float4 ld(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(__half* p, float4 v) {
+    uint2 u;
+    *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(128, 3) dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w9,
                                                            const float* __restrict__ scale, const float* __restrict__ shift, int act,
@@ -356,7 +371,8 @@ __global__ void __launch_bounds__(256) se_gate_train_kernel(const float* __restr
 
 // squeeze-excite scale folded into the per-field weights of the 1x1 projection that follows (maxvit.py:47 + :95):
 //   Wn[n][co][c] = W[co][c] * gate[n][c]    -- 256 KB per field instead of a read-modify-write pass over the activations
-__global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ W, const float* __restrict__ gate, float* __restrict__ out,
+template <typename TO>
+__global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ W, const float* __restrict__ gate, TO* __restrict__ out,
                                                       int Cout, int C, long long total4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
@@ -366,7 +382,14 @@ __global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ 
   const int co = (int)(r % Cout);
   const long long n = r / Cout;
   const float4 w = *reinterpret_cast<const float4*>(W + (long long)co * C + c), g = *reinterpret_cast<const float4*>(gate + n * C + c);
-  *reinterpret_cast<float4*>(out + e) = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+  if constexpr (sizeof(TO) == 4) {
+    *reinterpret_cast<float4*>(out + e) = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+  } else {                                                    // fp16 per-field weights (the hidden tensor of the MBConv is fp16)
+    uint2 u;
+    *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(w.x * g.x, w.y * g.y);
+    *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(w.z * g.z, w.w * g.w);
+    *reinterpret_cast<uint2*>(out + e) = u;
+  }
 }
 
 // out[n][p][c] = x[n][p][c] * gate[n][c]   (out of place: training keeps the pre-gate activations)
@@ -1383,6 +1406,7 @@ int dwconv_march_run(int dtype, const void* in, const float* w9, const float* sc
   const int spb = 128 / (C / 4);
   const int sblocks = (strips + spb - 1) / spb;
   if (dtype == 0) dwconv_march_kernel<bf16><<<N * sblocks, 128, 0, st>>>(reinterpret_cast<const bf16*>(in), w9, scale, shift, act, reinterpret_cast<bf16*>(out), psum, H, W, C, strips);
+  else if (dtype == 3) dwconv_march_kernel<__half><<<N * sblocks, 128, 0, st>>>(reinterpret_cast<const __half*>(in), w9, scale, shift, act, reinterpret_cast<__half*>(out), psum, H, W, C, strips);
   else dwconv_march_kernel<float><<<N * sblocks, 128, 0, st>>>(reinterpret_cast<const float*>(in), w9, scale, shift, act, reinterpret_cast<float*>(out), psum, H, W, C, strips);
   return check_launch("dwconv_march_kernel");
 }
@@ -1427,10 +1451,11 @@ int field_dot_run(const float* a, const float* b, float* out, int N, long long H
   return check_launch("field_dot_kernel");
 }
 
-int se_fold_run(const float* W, const float* gate, float* out, int N, int Cout, int C, cudaStream_t st) {
+int se_fold_run(const float* W, const float* gate, void* out, int out_f16, int N, int Cout, int C, cudaStream_t st) {
   if (C % 4) return set_error("se_fold: C %% 4 != 0");
   const long long total4 = (long long)N * Cout * C / 4;
-  se_fold_kernel<<<nblk(total4, 256), 256, 0, st>>>(W, gate, out, Cout, C, total4);
+  if (out_f16) se_fold_kernel<__half><<<nblk(total4, 256), 256, 0, st>>>(W, gate, reinterpret_cast<__half*>(out), Cout, C, total4);
+  else se_fold_kernel<float><<<nblk(total4, 256), 256, 0, st>>>(W, gate, reinterpret_cast<float*>(out), Cout, C, total4);
   return check_launch("se_fold_kernel");
 }
 

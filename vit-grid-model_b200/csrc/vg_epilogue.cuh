@@ -19,7 +19,7 @@ enum EpiKind : int {
 struct EpiParams {
   void* out;
   long long ldo;
-  int out_f32;               // output element type: 0 = activation dtype T, 1 = fp32, 2 = bf16
+  int out_f32;               // output element type: 0 = activation dtype T, 1 = fp32, 2 = bf16, 3 = fp16 (coalesced store epilogue)
   int n_total;               // total number of GEMM columns
   const float* bias;         // [n_total] (EPI_CONVT: [C])
   const float* col_scale;    // folded BatchNorm: y = acc*scale + shift (bias already folded into shift)
@@ -161,7 +161,12 @@ __device__ __forceinline__ void epi_store_coalesced(const EpiParams& ep, long lo
         const long long off = row * ep.ldo + c0 + cq;
         const bool f32out = ep.out_f32 == 1 || (ep.out_f32 == 0 && sizeof(T) == 4);
         if (f32out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = make_float4(o[0], o[1], o[2], o[3]);
-        else {
+        else if (ep.out_f32 == 3) {
+          uint2 u;
+          *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(o[0], o[1]);
+          *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(o[2], o[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + off) = u;
+        } else {
           uint2 u;
           *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(o[0], o[1]);
           *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(o[2], o[3]);

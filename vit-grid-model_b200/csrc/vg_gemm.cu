@@ -21,6 +21,7 @@ struct GemmShape {
   int tiles_per_batch;      // m-tiles per batch (== num_m_tiles when not batched)
   long long rows_per_batch; // A / output rows per batch (== M when not batched)
   int b_rows_per_batch;     // B row offset per batch (per-field weights)
+  int f16;                  // 16-bit operands are fp16, not bf16 (kind::f16 with the fp16 operand format)
 };
 
 constexpr int BM = 256, BN = 128, BK = 64, STAGES = 4;        // tile = 256 rows (two M=128 MMAs sharing one B stage) x 128 cols
@@ -108,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     {                                                        // ===== MMA issuer: the warp runs converged, an elected lane issues (see elect_one) =====
-      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
+      const uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : (gs.f16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN));
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -789,12 +790,15 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st) {
+  // dtype 3: fp16 operands -- the bf16 pipeline (2-byte elements, same tensor maps) with the fp16 instruction descriptor
+  const bool f16 = dtype == 3;
+  if (f16) { dtype = 0; if (kind != EPI_STORE) return set_error("gemm: fp16 operands are built for the plain store epilogue"); }
   const int bke = dtype == 2 ? 32 : 64;
   if (dtype != 1 && Ca % bke) return set_error("gemm: channels (%d) must be a multiple of %d", Ca, bke);   // SIMT path: any Ca
   if (ntaps < 1 || ntaps > 9) return set_error("gemm: bad tap count %d", ntaps);
   if (M <= 0) return 0;
   GemmShape gs;
-  gs.M = M;
+  gs.M = M; gs.f16 = f16 ? 1 : 0;
   gs.cblocks = dtype == 1 ? 1 : Ca / bke;                    // the SIMT kernel only uses k_blocks / cblocks = ntaps
   gs.k_blocks = gs.cblocks * ntaps;
   for (int i = 0; i < 9; ++i) gs.tap_shift[i] = i < ntaps ? tap_shift[i] : 0;

@@ -155,7 +155,7 @@ int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const 
                       float* gate, float* mean, float* hid, cudaStream_t st);
 int field_parts(long long HW);
 int field_dot_run(const float* a, const float* b, float* out, int N, long long HW, int C, cudaStream_t st);
-int se_fold_run(const float* W, const float* gate, float* out, int N, int Cout, int C, cudaStream_t st);
+int se_fold_run(const float* W, const float* gate, void* out, int out_f16, int N, int Cout, int C, cudaStream_t st);
 int se_scale_oop_run(const float* x, const float* gate, float* out, int N, long long HW, int C, cudaStream_t st);
 int se_bwd_run(const float* dh4, const float* h3, const float* gate, const float* mean, const float* hid, const float* W1,
                const float* W2, int N, long long HW, int C, int se, float* dW1, float* dW2, float* dmean, float* work,

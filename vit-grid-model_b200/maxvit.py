@@ -262,7 +262,13 @@ class MaxViT(nn.Module):
         cond = cond.float().contiguous()
         nwin = (H // w) * (W // w)
         for P in self.packed(x.dtype):
-            h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1, tf32=self.tf32)
+            # mixed precision: the hidden tensor (4x the channels, written and read twice) is stored in fp16 -- the 10-bit mantissa a
+            # tf32 MMA keeps of an fp32 operand anyway -- and the projection runs as kind::f16; exact-fp32 / bf16_all keep their dtype
+            n_hid = P["w_exp"].shape[0]
+            marching = n_hid % 4 == 0 and 128 % (n_hid // 4) == 0          # the fp16 depthwise kernel (hidden <= 512 channels)
+            hid_dtype = torch.float16 if (self.tf32 and x.dtype == torch.float32 and marching) else None
+            h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1, tf32=self.tf32,
+                         out_dtype=hid_dtype)
             hidden = h.shape[1]
             h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
             del h
@@ -270,9 +276,9 @@ class MaxViT(nn.Module):
             if x.dtype == torch.float32:
                 # the squeeze-excite scale rides on per-field projection weights (256 KB per field) instead of a
                 # read-modify-write pass over the hidden activations
-                wn = ops.se_fold_weights(P["w_proj"], gate)
+                wn = ops.se_fold_weights(P["w_proj"], gate, dtype=h2.dtype)
                 y = ops.gemm(h2.view(N * H * W, hidden), wn, rows_per_batch=H * W, b_rows_per_batch=P["w_proj"].shape[0], scale=P["s_proj"],
-                             shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32)
+                             shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32, out_f32=True)
             else:
                 ops.se_scale_(h2, gate)
                 y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],

@@ -10,7 +10,7 @@ from . import _lib
 
 import os
 
-DT_CODE = {torch.bfloat16: 0, torch.float32: 1}
+DT_CODE = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 3}
 _ATTN_V1 = os.environ.get("VG_ATTN_V1", "0") == "1"
 
 
@@ -23,9 +23,11 @@ def _st():
 
 
 def _gemm_code(dtype, tf32):
-    """0 = bf16 tcgen05, 1 = fp32 SIMT, 2 = fp32 storage + tf32 tcgen05"""
+    """0 = bf16 tcgen05, 1 = fp32 SIMT, 2 = fp32 storage + tf32 tcgen05, 3 = fp16 tcgen05"""
     if dtype == torch.bfloat16:
         return 0
+    if dtype == torch.float16:
+        return 3
     return 2 if tf32 else 1
 
 
@@ -102,21 +104,34 @@ def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
 
 
 def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per_batch=0, bias=None, scale=None,
-         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None, tf32=False):
+         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None, tf32=False, out_dtype=None):
+    """out_dtype=torch.float16: fp16 output from any operand type (the MBConv hidden tensor)"""
     dtype = A.dtype
     rowsA, Ca = A.shape
     M = rowsA if M is None else M
     Ntot = n_out if n_out is not None else (b_rows_per_batch if rows_per_batch else Wt.shape[0])
     if out is None:
-        out = torch.empty(M, Ntot, dtype=torch.float32 if out_f32 else dtype, device=A.device)
+        out = torch.empty(M, Ntot, dtype=out_dtype or (torch.float32 if out_f32 else dtype), device=A.device)
     shifts = (ctypes.c_int * ntaps)(*tap_shift)
     keep, sp, sn = _scratch(dtype, M * Ntot, A.device, tf32)
     _lib.TRACE_TAG = f"M={M} K={ntaps}x{Ca} N={Ntot} {'tf32' if tf32 else str(dtype)[6:]}"
     res_f32 = int(res is not None and res.dtype == torch.float32)
     _lib.call("vg_gemm_fwd", _gemm_code(dtype, tf32), A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
               rows_per_batch, b_rows_per_batch, _p(bias), _p(scale), _p(shift), act, _p(res),
-              res.shape[1] if res is not None else 0, res_f32, out.data_ptr(), out.shape[1], int(out_f32), sp, sn, _st())
+              res.shape[1] if res is not None else 0, res_f32, out.data_ptr(), out.shape[1], _out_code(dtype, out.dtype, out_f32),
+              sp, sn, _st())
     return out
+
+
+def _out_code(in_dtype, out_dtype, out_f32):
+    """EpiParams.out_f32: 0 = the operand dtype, 1 = fp32, 2 = bf16, 3 = fp16"""
+    if out_dtype == torch.float16:
+        return 3
+    if out_dtype == torch.float32 and in_dtype != torch.float32:
+        return 1
+    if out_dtype == torch.bfloat16 and in_dtype != torch.bfloat16:
+        return 2
+    return int(out_f32)
 
 
 def conv_tap_shifts(WP):
@@ -197,12 +212,12 @@ def se_gate(psum, HW, W1, W2):
     return gate
 
 
-def se_fold_weights(W, gate):
-    """(Cout, C) fp32 projection weights x (N, C) gates -> per-field weights (N*Cout, C)"""
+def se_fold_weights(W, gate, dtype=torch.float32):
+    """(Cout, C) fp32 projection weights x (N, C) gates -> per-field weights (N*Cout, C) in fp32 or fp16"""
     Cout, C = W.shape
     N = gate.shape[0]
-    out = torch.empty(N * Cout, C, dtype=torch.float32, device=W.device)
-    _lib.call("vg_se_fold_weights", W.data_ptr(), gate.data_ptr(), out.data_ptr(), N, Cout, C, _st())
+    out = torch.empty(N * Cout, C, dtype=dtype, device=W.device)
+    _lib.call("vg_se_fold_weights", W.data_ptr(), gate.data_ptr(), out.data_ptr(), int(dtype == torch.float16), N, Cout, C, _st())
     return out
 
 
