@@ -331,7 +331,7 @@ def run_other_config(args, dev, rank, world):
     fields = world * B * L * args.steps
     value = fields / (ms * 1e-3)
     opt_in = None
-    if precision == "fp32":
+    if precision != "bf16":
         # the reduced-precision mode of a wide network is opt-in: it misses the 1e-2 tolerance at this depth
         model.set_precision("bf16")
         with torch.no_grad():

@@ -113,20 +113,35 @@ def test_config3_geometry_512_vs_cpu_oracle(precision, tol):
 @pytest.mark.slow
 def test_config4_full_depth_default_precision_vs_cpu_oracle():
     """BASELINE configs[4]: 512 channels, 32 heads x dim_head 64, MaxViT depth 4, 82 x 67 domain, one sample (12 fields).
-    The DEFAULT precision of a wide network must meet the north-star tolerance against the CPU oracle.  Measured on B200
-    (tools/config5_parity.py): bf16 convolutions + tf32 MaxViT 3.6e-2, bf16 convolutions + exact-fp32 MaxViT 3.4e-2 (the
-    encoder's bf16 activations, amplified by four layers of un-scaled +-32*gamma^2 logits, not the tf32 projections), exact
-    fp32 2.1e-5 -- so wide networks default to the exact-fp32 mode and the reduced-precision modes are opt-in."""
+    The DEFAULT precision of a wide network must meet the north-star 1e-2 against the CPU oracle.  Measured on B200
+    (tools/config5_parity.py): bf16 3.6e-2, tf32 everywhere 1.4e-2, tf32 + exact-fp32 QKV projection 1.07e-2, tf32 convolutions +
+    exact-fp32 MaxViT 4.3e-3, exact fp32 2.1e-5 -- four stacked MaxViT layers with un-scaled +-32 gamma^2 logits amplify the
+    operand rounding of every projection of the block.  Wide networks therefore default to 'tf32_conv'; the faster
+    reduced-precision modes are opt-in there.  The exact-fp32 mode is held to the fp32 tolerance on the same case."""
     cfg = synth.GridConfig(dim=512, heads=32, dim_head=64, vit_depth=4)
     m = build(cfg, 0, None)
-    assert m.precision == "fp32"
+    assert m.precision == "tf32_conv"
     x, ts, _ = synth.make_inputs(cfg, 1, seed=3)
     with torch.no_grad():
         y = m(x.cuda(), timestamps=ts.cuda()).cpu()
         ref = metnet3_forward(x, ts, synth.make_state_dict(synth.metnet3_spec(cfg), seed=0), cfg)
+        y32 = m.set_precision("fp32")(x.cuda(), timestamps=ts.cuda()).cpu()
     e = rel_err(y, ref)
-    assert e < 1e-4, e                                     # the fp32 tolerance of north_star
+    assert e < 7e-3, e                                     # north_star bf16-mode tolerance 1e-2, with margin
+    assert rel_err(y32, ref) < 1e-4
     assert build(synth.CFG_12HR, 0, None).precision == "bf16"
+
+
+@pytest.mark.parametrize("name", ["metnet3_small128.pt", "metnet3_12hr_b1.pt", "metnet3_wide256.pt", "metnet3_wide512.pt"])
+def test_tf32_mode_golden_from_reference(golden, name):
+    """set_precision('tf32'): fp32 storage, every contraction on tcgen05 kind::tf32 -- 3e-3 on the goldens (bf16 mode: 7e-3)"""
+    f = golden(name)
+    cfg = synth.GridConfig(**f["cfg"])
+    m = build(cfg, f["weight_seed"], "tf32")
+    x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
+    with torch.no_grad():
+        y = m(x.cuda(), timestamps=ts.cuda())
+    assert rel_err(y, f["y"]) < 6e-3
 
 
 # ------------------------------------------------------------------------------------------ callers either side

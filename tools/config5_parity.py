@@ -16,8 +16,21 @@ print(f"oracle: {time.perf_counter() - t0:.1f} s", flush=True)
 m = MetNet3(**cfg.metnet3_kwargs())
 m.load_state_dict(sd, strict=True)
 m = m.cuda().eval()
-for mode in ("bf16", "bf16_tf32", "fp32", "bf16_all"):
-    m.set_precision(mode)
+for mode in ("tf32", "tf32+qkv_exact", "tf32conv+fp32vit", "fp32"):
+    m.vit.qkv_exact = mode == "tf32+qkv_exact"
+    if mode == "tf32+qkv_exact":
+        m.set_precision("tf32")
+        with torch.no_grad():
+            y = m(x.cuda(), timestamps=ts.cuda()); torch.cuda.synchronize(); t0 = time.perf_counter()
+            y = m(x.cuda(), timestamps=ts.cuda()); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(f"{mode:10s} rel err vs oracle {((y.cpu() - ref).abs().max() / ref.abs().max()).item():.3e}   {dt * 1e3:.1f} ms / 12 fields", flush=True)
+        continue
+    if mode == "tf32conv+fp32vit":
+        m.set_precision("tf32"); m.vit.set_precision("fp32")
+    elif mode == "fp32conv+tf32vit":
+        m.set_precision("fp32"); m.vit.set_precision("bf16")
+    else:
+        m.set_precision(mode)
     with torch.no_grad():
         y = m(x.cuda(), timestamps=ts.cuda())
         torch.cuda.synchronize(); t0 = time.perf_counter()

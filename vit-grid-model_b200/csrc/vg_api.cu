@@ -93,6 +93,11 @@ int vg_prepare_packed_fwd(int dtype, const void* x_bf16, const long long* xstrid
                      (cudaStream_t)stream);
 }
 
+int vg_standardise_channel(float* x, const long long* xstride, int B, int T, int C, int H, int W, int channel, float pm_mean,
+                           float pm_std, void* stream) {
+  return standardise_channel_run(x, xstride, B, T, C, H, W, channel, pm_mean, pm_std, (cudaStream_t)stream);
+}
+
 int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long long ts_sF, int B, int L, int le, int te,
                       const float* emb_lead, const float* emb_month, const float* emb_day, const float* emb_hour,
                       const float* w3, const float* w1, int c_in, int c_data, int Cout, float* temb, float* cond,

@@ -66,6 +66,7 @@ struct StemParams {
 int prepare_run(int dtype, const void* x, int x_bf16, int prestd, const long long* xs, int B, int T, int C, int H, int W, int pad_top,
                 int pad_left, int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st);
 int time_terms_run(const TimeParams& p, cudaStream_t st);
+int standardise_channel_run(float* x, const long long* xs, int B, int T, int C, int H, int W, int ch, float mean, float stdv, cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st);

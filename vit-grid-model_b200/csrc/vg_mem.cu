@@ -123,6 +123,22 @@ __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T
   }
 }
 
+// MetNet3_with_stn_imgs (metnet3.py:701): x[:, :, ch] = (x[:, :, ch] - mean) / std, written back into the CALLER's tensor
+// (the reference normalises the view before its clone).  x (B,T,C,H,W) fp32 with arbitrary element strides.
+__global__ void __launch_bounds__(256) standardise_channel_kernel(float* __restrict__ x, long long sB, long long sT, long long sC, long long sH,
+                                                                  long long sW, int B, int T, int H, int W, int ch, float mean, float stdv) {
+  const long long total = (long long)B * T * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    float* p = x + b * sB + t * sT + ch * sC + h * sH + w * sW;
+    *p = (*p - mean) / stdv;
+  }
+}
+
 // ================================================================================================
 // time terms.  Field n = b*L + l.  temb[n] = [lead_emb(l+1) | scrambled model-time embedding] (metnet3.py:389-402,
 // quirk Q1: the three (N,te) embeddings are concatenated on dim 0 and re-viewed as (N,3te)); cond[n] = lead_emb.
@@ -699,6 +715,15 @@ int prepare_run(int dtype, const void* x, int x_bf16, int prestd, const long lon
   else { if (x_bf16) VG_PREP(float, bf16); else VG_PREP(float, float); }
 #undef VG_PREP
   return check_launch(flat ? "prepare_flat_kernel" : "prepare_kernel");
+}
+
+int standardise_channel_run(float* x, const long long* xs, int B, int T, int C, int H, int W, int ch, float mean, float stdv, cudaStream_t st) {
+  if (ch < 0 || ch >= C) return set_error("standardise_channel: channel %d outside [0, %d)", ch, C);
+  const long long total = (long long)B * T * H * W;
+  if (total <= 0) return 0;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  standardise_channel_kernel<<<grid, 256, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xs[4], B, T, H, W, ch, mean, stdv);
+  return check_launch("standardise_channel_kernel");
 }
 
 int time_terms_run(const TimeParams& p, cudaStream_t st) {

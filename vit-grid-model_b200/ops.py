@@ -77,6 +77,15 @@ def prepare(x, cfg_pads, HP, WP, Cpad, mean, std, dtype, packed=False):
     return out
 
 
+def standardise_channel_(x, channel, mean, std):
+    """x[:, :, channel] = (x[:, :, channel] - mean) / std in place (metnet3.py:701); x (B,T,C,H,W) fp32, any strides"""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+    B, T, C, H, W = x.shape
+    strides = (ctypes.c_longlong * 5)(*x.stride())
+    _lib.call("vg_standardise_channel", x.data_ptr(), strides, B, T, C, H, W, int(channel), float(mean), float(std), _st())
+    return x
+
+
 def time_terms(ts, B, L, emb_lead, emb_m, emb_d, emb_h, w3, w1, c_data, Cout):
     le, te = emb_lead.shape[1], emb_m.shape[1]
     N = B * L
@@ -139,10 +148,12 @@ def conv_tap_shifts(WP):
     return tuple((ky - 1) * P + (kx - 1) for ky in range(3) for kx in range(3))
 
 
-def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy=None, head=None):
-    """head = (w[C], b, std, mean, H, W, pads, out (N,H,W) fp32) fuses the 1x1 head / unpad / de-normalisation"""
+def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy=None, head=None, tf32=False):
+    """head = (w[C], b, std, mean, H, W, pads, out (N,H,W) fp32) fuses the 1x1 head / unpad / de-normalisation.
+    tf32 (fp32 storage only): the contraction runs on tcgen05 kind::tf32 instead of the exact-fp32 SIMT kernel"""
     dtype = x.dtype
     C = x.shape[1]
+    code = 2 if (tf32 and dtype == torch.float32) else DT_CODE[dtype]
     res_f32 = int(res is not None and res.dtype == torch.float32 and dtype != torch.float32)
     if head is None:
         hw, hb, hs, hm, H, W, pt, pl, ho = None, 0.0, 1.0, 0.0, 0, 0, 0, 0, None
@@ -152,14 +163,14 @@ def conv3x3_ln(x, Wt, bias, ln_g, ln_b, eps, film, res, out, N, HP, WP, out_copy
     if C != 128:
         # other widths (256 / 384 / 512): plain shifted-row GEMM into an fp32 scratch + row-wise LN / FiLM / ReLU / residual
         scratch = torch.empty(x.shape[0] * C * (2 if dtype == torch.float32 else 1), dtype=torch.float32, device=x.device)
-        _lib.call("vg_conv3x3_ln_wide_fwd", DT_CODE[dtype], x.data_ptr(), C, Wt.data_ptr(), bias.data_ptr(), ln_g.data_ptr(),
+        _lib.call("vg_conv3x3_ln_wide_fwd", code, x.data_ptr(), C, Wt.data_ptr(), bias.data_ptr(), ln_g.data_ptr(),
                   ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP, _p(hw), float(hb),
                   float(hs), float(hm), H, W, pt, pl, _p(ho), scratch.data_ptr(), scratch.numel(), _st())
         return out
-    keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device)
+    keep, sp, sn = _scratch(dtype, x.shape[0] * 128, x.device, tf32)
     _lib.TRACE_TAG = ("film" if film is not None else "plain") + ("+res" if res is not None else "") + \
         ("+copy" if out_copy is not None else "") + ("+head" if head is not None else "")
-    _lib.call("vg_conv3x3_ln_fwd", DT_CODE[dtype], x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
+    _lib.call("vg_conv3x3_ln_fwd", code, x.data_ptr(), x.shape[1], Wt.data_ptr(), bias.data_ptr(),
               ln_g.data_ptr(), ln_b.data_ptr(), float(eps), _p(film), _p(res), res_f32, _p(out), _p(out_copy), N, HP, WP,
               _p(hw), float(hb), float(hs), float(hm), H, W, pt, pl, _p(ho), sp, sn, _st())
     return out
