@@ -184,6 +184,10 @@ struct EpiCtx {
   const float* bias;
   const float* ln_g;
   const float* ln_b;
+  // the tcgen05 kernels stage bias / ln_g / ln_b (and gb) in shared memory: read them with ld.shared.  Through a generic
+  // pointer every one of these warp-uniform 16-byte reads (128 per row) is an LD.E.128 that costs 2.4 LSU wavefronts instead
+  // of one broadcast -- 55 M of the kernel's wavefronts with the LSU data pipe at 80 % (ncu, round 2)
+  bool params_smem = false;
   // FiLM folded into the LayerNorm affine, staged per tile by the epilogue warpgroup (tcgen05 kernel only):
   // gb[f][0..127] = g*(scale+1), gb[f][128..255] = b*(scale+1)+shift for the fields n_first+f, f in {0,1}
   const float* gb;
@@ -199,6 +203,15 @@ struct EpiCtx {
   long long res_row0 = 0;          // row of lane 0 in this tile
   long long res_next_row0 = -1;    // row of lane 0 in the CTA's next tile, -1 = none
 };
+
+__device__ __forceinline__ float4 ldp4(const EpiCtx& cx, const float* p) {
+  if (cx.params_smem) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+  }
+  return *reinterpret_cast<const float4*>(p);
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -225,10 +238,10 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     ld.load(ch, v);
-    if (ch == 0) x0 = v[0] + cx.bias[0];
+    if (ch == 0) x0 = v[0] + ldp4(cx, cx.bias).x;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(cx.bias + ch * 32 + j);
+      const float4 b4 = ldp4(cx, cx.bias + ch * 32 + j);
       const float d0 = v[j] + b4.x - x0, d1 = v[j + 1] + b4.y - x0, d2 = v[j + 2] + b4.z - x0, d3 = v[j + 3] + b4.w - x0;
       s1 += (d0 + d1) + (d2 + d3);
       s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
@@ -295,9 +308,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const int c = ch * 32 + j;
-        const float4 b4 = *reinterpret_cast<const float4*>(cx.bias + c);
-        const float4 g4 = *reinterpret_cast<const float4*>(pg_ + c);
-        const float4 e4 = *reinterpret_cast<const float4*>(pb_ + c);
+        const float4 b4 = ldp4(cx, cx.bias + c), g4 = ldp4(cx, pg_ + c), e4 = ldp4(cx, pb_ + c);
         float y0 = fmaf((v[j] + b4.x - mean) * rstd, g4.x, e4.x), y1 = fmaf((v[j + 1] + b4.y - mean) * rstd, g4.y, e4.y);
         float y2 = fmaf((v[j + 2] + b4.z - mean) * rstd, g4.z, e4.z), y3 = fmaf((v[j + 3] + b4.w - mean) * rstd, g4.w, e4.w);
         if (film) {

@@ -140,7 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int lg = warp & 3;                                 // TMEM lane group this warp may access
     const int e = (warp - 4) >> 2;                           // row half of the tile
     EpiCtx cx;
-    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0; cx.params_smem = true;
     float* sgb = sparam + 384 + e * 512;                     // this warpgroup's staging buffer
     const int wt = (warp & 3) * 32 + lane;                   // thread index inside the warpgroup
     int it = 0;
@@ -336,7 +336,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int lg = warp & 3;
     const int e = (warp - 4) >> 2;
     EpiCtx cx;
-    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0; cx.params_smem = true;
     if (hs.res_tma) {
       cx.res_map = &mapR; cx.res_buf = sres + (warp - 4) * 8192; cx.res_bar = res_full + (warp - 4) * 2;
       if (lane == 0 && (int)blockIdx.x < hs.num_tiles) {     // chunks 0 and 1 of the first tile
@@ -532,7 +532,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int lg = warp & 3;
     const int e = (warp - 4) >> 2;
     EpiCtx cx;
-    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0;
+    cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0; cx.params_smem = true;
     const long long tile_stride = (long long)npairs_grid * 2 * BM;
     if (hs.res_tma) {
       cx.res_map = &mapR; cx.res_buf = sres + (warp - 4) * 8192; cx.res_bar = res_full + (warp - 4) * 2;
