@@ -569,9 +569,33 @@ def main():
                         "share_of_step": sum(attn_ms) / ms_total,
                         "algorithmic_gflop_per_field_per_launch": ATTN_FLOPS_PER_FIELD / 1e9})
     kernels.sort(key=lambda k: -k["share_of_step"])
+    # HBM-bound kernels of the step against the measured copy bandwidth: algorithmic bytes (the tensors each kernel must read
+    # and write once, in their storage types) / launch time.  The two GELU kernels are issue-bound, not bandwidth-bound; they are
+    # listed with the same yardstick so that nothing hides.
+    peak_bw = peaks.get("hbm_gbs", 6560.0)
+    F, PXB, PXN, LOWP = B * L, B * 85 * 71 + 71, B * L * 85 * 71 + 71, B * L * 42 * 35
+    bw_spec = [
+        ("vg_prepare_fwd", None, "prepare (PM2.5 standardise, pad, NCHW fp32 -> channels-last bf16)", x_host.numel() * 4 + PXB * 640 * 2),
+        ("vg_stem_finish_fwd", None, "stem finish (+time terms, ChanLN, FiLM, ReLU per lead time; bf16 + fp32 skip out)", PXB * 128 * 4 * 2 + PXN * 128 * (2 + 4)),
+        ("vg_pool2_fwd", None, "2x2 max-pool bf16 -> fp32", PXN * 128 * 2 + LOWP * 128 * 4),
+        ("vg_gemm_fwd", "K=1x128 N=512", "MBConv expand 1x1 + BN + GELU (tf32 MMA, fp16 out; GELU issue-bound)", LOWP * 128 * 4 + LOWP * 512 * 2),
+        ("vg_dw3x3_fwd", None, "MBConv depthwise 3x3 + BN + GELU (fp16 in / out; GELU + stencil issue-bound)", LOWP * 512 * 2 * 2),
+        ("vg_gemm_fwd", "K=1x512 N=128", "MBConv project 1x1 + BN (fp16 operands, SE gate folded into per-field weights)", LOWP * 512 * 2 + LOWP * 128 * 4),
+        ("vg_convT2_fwd", None, "ConvTranspose 2x2 as GEMM + depth-to-space (bf16 + fp32 skip out)", LOWP * 128 * 4 + PXN * 128 * (2 + 4)),
+    ]
+    bandwidth = []
+    if args.precision == "bf16":
+        for entry, tagpat, label, nbytes in bw_spec:
+            ms_list = [a.elapsed_time(b) for name, tag, a, b in trace if name == entry and (tagpat is None or tagpat in tag)]
+            if ms_list:
+                avg = sum(ms_list) / len(ms_list)
+                gbs = nbytes / (avg * 1e-3) / 1e9
+                bandwidth.append({"kernel": label, "entry": entry, "avg_launch_ms": avg, "algorithmic_bytes": nbytes, "achieved_gbs": gbs,
+                                  "peak_gbs": peak_bw, "frac": gbs / peak_bw, "share_of_step": sum(ms_list) / ms_total})
     if kernels:
         roofline = dict(kernels[0])                           # the dominant kernel of the step
         roofline["other_kernels"] = kernels[1:]
+        roofline["bandwidth_kernels"] = bandwidth
 
     if rank == 0:
         if args.trace:
