@@ -166,14 +166,17 @@ VG_API int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int re
  * (table (2w-1)^2+1 x heads, fp32), softmax, PV.  qkv [(Nw*S)][3*heads*dh] -> out [(Nw*S)][heads*dh]. */
 VG_API int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out,
-                     void* stream);
+                     long long drop_seed, int drop_salt, int drop_thresh, void* stream);
 
 /* maxvit.py:218-219 + 310/334 + 312-319/336-340 -- to_out projection, residual add and inverse partition:
  * window tokens are scattered back to CL x_out (N,Hl,Wl,C) = proj + x_in; register-token rows go to reg_out
  * (fp32 [Nw][R][C] = proj + reg_in) when reg_out != NULL (block attention) and are dropped otherwise. */
 VG_API int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, const void* x_in, const float* reg_in,
                     int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
-                    int grid_mode, float* scratch, long long scratch_elems, void* stream);
+                    int grid_mode, long long drop_seed, int drop_salt, int drop_thresh, float* scratch, long long scratch_elems,
+                    void* stream);
+/* (both: drop_thresh T in [1,255] = the training dropout of vg_attn_fused_fwd -- same hash, same masks -- on the
+ * probabilities / on the to_out output before the residual; 0 = none) */
 
 /* maxvit.py:170-219 + 298-340 in ONE kernel (fp32 residual stream, tcgen05 kind::f16 QKV projection on fp16 operands, kind::tf32 QK^T / out-projection, bf16 PV):
  * gather + register tokens + LayerNorm + FiLM -> per head {QKV, QK-RMSNorm, QK^T + rel-pos bias, softmax, PV,

@@ -122,8 +122,12 @@ def test_train_with_default_dropout_and_unsupported_modes():
     with torch.no_grad():
         y_eval = m(x.cuda(), timestamps=ts.cuda())               # eval mode: no dropout, running statistics
     assert torch.isfinite(y_eval).all()
-    m.train().set_precision("fp32")
-    with pytest.raises(NotImplementedError):                     # dropout is built into the mixed-precision path only
+    m.train().set_precision("fp32")                              # the exact-fp32 path applies the same counter-based masks
+    loss32 = focal_r_loss(m(x.cuda(), timestamps=ts.cuda()), target.cuda())
+    loss32.backward()
+    assert torch.isfinite(loss32) and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    m.set_precision("bf16_all")
+    with pytest.raises(NotImplementedError):
         m(x.cuda(), timestamps=ts.cuda())
 
 

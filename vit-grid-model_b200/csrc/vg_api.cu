@@ -273,21 +273,27 @@ int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int reg_per_f
 }
 
 int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma, const float* bias_table,
-                     int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out, void* stream) {
+                     int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out, long long drop_seed, int drop_salt,
+                     int drop_thresh, void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, 0, win, R, 0)) return 1;
-  return attn_core_run(dtype, qkv, q_gamma, k_gamma, bias_table, g, heads, dh, out, (cudaStream_t)stream);
+  return attn_core_run(dtype, qkv, q_gamma, k_gamma, bias_table, g, heads, dh, out, (unsigned)drop_seed, (unsigned)drop_salt,
+                       drop_thresh, (cudaStream_t)stream);
 }
 
 int vg_attn_out_fwd(int dtype, const void* attn, int inner, const void* Wt, const void* x_in, const float* reg_in,
                     int reg_per_field, float* reg_out, void* x_out, int N, int Hl, int Wl, int C, int win, int R,
-                    int grid_mode, float* scratch, long long scratch_elems, void* stream) {
+                    int grid_mode, long long drop_seed, int drop_salt, int drop_thresh, float* scratch, long long scratch_elems,
+                    void* stream) {
   AttnGeom g;
   if (make_attn_geom(g, N, Hl, Wl, C, win, R, grid_mode)) return 1;
   EpiParams ep = epi_zero();
   ep.out = x_out; ep.n_total = C; ep.S = g.S(); ep.R = R; ep.nwin = g.nwin(); ep.grid_mode = grid_mode; ep.win = win;
   ep.X = g.X; ep.Y = g.Y; ep.Hl = Hl; ep.Wl = Wl; ep.x_in = x_in; ep.reg_in = reg_in;
   ep.reg_in_per_field = reg_per_field; ep.reg_out = reg_out;
+  if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_out: dropout threshold %d outside [0, 255]", drop_thresh);
+  ep.drop_seed = (unsigned)drop_seed; ep.drop_salt = (unsigned)drop_salt; ep.drop_thresh = drop_thresh;
+  ep.drop_scale = 256.0f / (256.0f - (float)drop_thresh);
   const long long M = (long long)N * g.nwin() * g.S();
   const int shift0 = 0;
   return gemm_run(dtype, EPI_ATTN_OUT, attn, M, inner, Wt, C, 1, &shift0, M, 0, 0, ep, scratch, scratch_elems,

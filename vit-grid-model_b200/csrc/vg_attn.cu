@@ -9,6 +9,7 @@
 // NCHW/NHWC form.
 #include "vg_common.cuh"
 #include "vg_host.h"
+#include "vg_rng.cuh"
 
 namespace vg {
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qkv, const float* __restrict__ qgamma,
                                                         const float* __restrict__ kgamma, const float* __restrict__ bias_table,
-                                                        const AttnGeom g, int heads, T* __restrict__ out, long long pairs) {
+                                                        const AttnGeom g, int heads, T* __restrict__ out, long long pairs, const DropCfg drop) {
   extern __shared__ float sm[];
   const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,7 +122,11 @@ __global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qk
     for (int d = 0; d < DH; ++d) { q[d] *= inv * qgamma[hd * DH + d]; o[d] = 0.f; }
     const int ti = i - g.R, ai = ti / g.win, bi = ti - ai * g.win;
     float m = -INFINITY, l = 0.f;
+    uint32_t hsh = 0u;
     for (int j = 0; j < S; ++j) {
+      // nn.Dropout on the probabilities (maxvit.py:146): the same counter-based mask as the fused kernels (vg_rng.cuh)
+      if (drop.thresh && (j & 3) == 0) hsh = drop_hash(drop.seed, drop_row(wdx, i), drop_group_prob(drop.salt, hd, j >> 2));
+      const float mk = !drop.thresh ? 1.0f : ((int)((hsh >> (8 * (j & 3))) & 255u) >= drop.thresh ? drop.scale : 0.f);
       float sc = 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) sc = fmaf(q[d], sk[j * (DH + 1) + d], sc);
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qk
       const float corr = __expf(m - mn), p = __expf(sc - mn);
       l = l * corr + p;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = fmaf(p, sv[j * (DH + 1) + d], o[d] * corr);
+      for (int d = 0; d < DH; ++d) o[d] = fmaf(p * mk, sv[j * (DH + 1) + d], o[d] * corr);      // the normaliser l stays un-dropped
       m = mn;
     }
     const float il = 1.0f / l;
@@ -166,7 +171,7 @@ int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st)
 }
 
 template <typename T, int DH>
-static int core_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, cudaStream_t st) {
+static int core_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, const DropCfg& drop, cudaStream_t st) {
   const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   const size_t smem = 4 * (size_t)(2 * S * (DH + 1) + nb) * sizeof(float);
   static size_t attr_bytes = 48 * 1024;                     // the size depends on the window geometry: raise the limit when it grows
@@ -176,17 +181,20 @@ static int core_launch(const void* qkv, const float* qg, const float* kg, const 
     attr_bytes = smem;
   }
   const long long pairs = (long long)g.N * g.nwin() * heads;
-  attn_core_kernel<T, DH><<<(unsigned)((pairs + 3) / 4), 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), pairs);
+  attn_core_kernel<T, DH><<<(unsigned)((pairs + 3) / 4), 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), pairs, drop);
   return check_launch("attn_core_kernel");
 }
 
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
-                  const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st) {
+                  const AttnGeom& g, int heads, int dh, void* out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
   if (g.S() > 128) return set_error("attn_core: sequence %d too long", g.S());
-  if (dh == 32) return dtype == 0 ? core_launch<bf16, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                                  : core_launch<float, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
-  if (dh == 64) return dtype == 0 ? core_launch<bf16, 64>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                                  : core_launch<float, 64>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
+  if (drop_thresh < 0 || drop_thresh > 255 || (drop_thresh && g.S() > 64)) return set_error("attn_core: bad dropout threshold %d (or sequence > 64)", drop_thresh);
+  DropCfg drop;
+  drop.seed = seed; drop.salt = salt; drop.thresh = drop_thresh; drop.scale = 256.0f / (256.0f - (float)drop_thresh);
+  if (dh == 32) return dtype == 0 ? core_launch<bf16, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st)
+                                  : core_launch<float, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st);
+  if (dh == 64) return dtype == 0 ? core_launch<bf16, 64>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st)
+                                  : core_launch<float, 64>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st);
   return set_error("attn_core: dim_head %d not supported (32 or 64)", dh);
 }
 

@@ -504,7 +504,7 @@ struct AttnCoreBwdParams {
   int heads;
 };
 
-__global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdParams p) {
+__global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdParams p, const DropCfg drop) {
   constexpr int DH = 32, LD = DH + 1, SM = 64;
   extern __shared__ float sm[];
   const AttnGeom g = p.g;
@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdPar
   float* inq = dbias + nb;            // [SM] 1/|q|
   float* ink = inq + SM;
   float* gred = ink + SM;             // [8][2][DH]
+  float* MK = gred + 8 * 2 * DH;      // [SM][SM+1] dropout mask * scale of the probabilities (allocated when dropout is on)
   const int n = blockIdx.x / p.heads, hd = blockIdx.x - n * p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = p.heads * DH;
@@ -570,12 +571,22 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdPar
       const float inv = 1.0f / warp_sum(e0 + e1);
       P[i * (SM + 1) + lane] = e0 * inv;
       P[i * (SM + 1) + lane + 32] = e1 * inv;
+      if (drop.thresh) {                                     // the forward pass's mask on the probabilities (maxvit.py:146)
+        const uint32_t rid = drop_row((long long)n * nwin + wi, i);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = lane + 32 * t;
+          const uint32_t hsh = drop_hash(drop.seed, rid, drop_group_prob(drop.salt, hd, j >> 2));
+          MK[i * (SM + 1) + j] = (int)((hsh >> (8 * (j & 3))) & 255u) >= drop.thresh ? drop.scale : 0.f;
+        }
+      }
     }
     __syncthreads();
-    // ---- dV[j][d] = sum_i P[i][j] dO[i][d]: warp per j, lane = d
+    // ---- dV[j][d] = sum_i P'[i][j] dO[i][d] (P' = P * mask): warp per j, lane = d
     for (int j = warp; j < S; j += 8) {
       float a = 0.f;
-      for (int i = 0; i < S; ++i) a = fmaf(P[i * (SM + 1) + j], dO[i * LD + lane], a);
+      if (drop.thresh) { for (int i = 0; i < S; ++i) a = fmaf(P[i * (SM + 1) + j] * MK[i * (SM + 1) + j], dO[i * LD + lane], a); }
+      else for (int i = 0; i < S; ++i) a = fmaf(P[i * (SM + 1) + j], dO[i * LD + lane], a);
       p.dqkv[(row0 + j) * 3 * inner + 2 * inner + hd * DH + lane] = a;
     }
     __syncthreads();
@@ -590,6 +601,7 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const AttnCoreBwdPar
         if (j < S) {
 #pragma unroll
           for (int d = 0; d < DH; ++d) a = fmaf(dO[i * LD + d], vv[j * LD + d], a);
+          if (drop.thresh) a *= MK[i * (SM + 1) + j];         // d(att)/dP passes through the mask
         }
         dp[t] = a; pr[t] = j < S ? P[i * (SM + 1) + j] : 0.f;
       }
@@ -1532,7 +1544,7 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
                       int use_tf32, float* att_out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
   if (dh != 32) return set_error("attn_core_bwd: dim_head must be 32 (got %d)", dh);
   if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_core_bwd: dropout threshold %d outside [0, 255]", drop_thresh);
-  if (drop_thresh && use_tf32 != 2 && use_tf32 != 3) return set_error("attn_core_bwd: dropout is only built into the bf16 tensor-core kernel (modes 2, 3)");
+  if (drop_thresh && use_tf32 == 1) return set_error("attn_core_bwd: dropout is built into the bf16 tensor-core kernels (modes 2, 3) and the exact-fp32 kernel (mode 0)");
   if (g.S() > 64) return set_error("attn_core_bwd: sequence %d > 64", g.S());
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   if (use_tf32 == 2 || use_tf32 == 3) {
@@ -1568,7 +1580,7 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
     return check_launch("attn_core_bwd_mma_kernel");
   }
   if (att_out) return set_error("attn_core_bwd: att_out is only produced by the tf32 kernel");
-  const size_t smem = (size_t)(8 * 64 * 33 + 64 * 65 + 2 * nb + 128 + 8 * 2 * 32) * sizeof(float);
+  const size_t smem = (size_t)(8 * 64 * 33 + 64 * 65 + 2 * nb + 128 + 8 * 2 * 32 + (drop_thresh ? 64 * 65 : 0)) * sizeof(float);
   static size_t attr = 0;                        // depends on the window size: raise the limit when it grows
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1578,7 +1590,7 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   AttnCoreBwdParams p;
   p.qkv = qkv; p.datt = datt; p.qgamma = qgamma; p.kgamma = kgamma; p.bias_table = bias_table; p.dqkv = dqkv;
   p.dqgamma = dqgamma; p.dkgamma = dkgamma; p.dbias_table = dbias_table; p.g = g; p.heads = heads;
-  attn_core_bwd_kernel<<<g.N * heads, 256, smem, st>>>(p);
+  attn_core_bwd_kernel<<<g.N * heads, 256, smem, st>>>(p, make_drop(seed, salt, drop_thresh));
   return check_launch("attn_core_bwd_kernel");
 }
 

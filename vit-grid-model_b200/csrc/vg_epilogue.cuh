@@ -5,6 +5,7 @@
 // stores are predicated on row validity.
 #pragma once
 #include "vg_common.cuh"
+#include "vg_rng.cuh"
 
 namespace vg {
 
@@ -51,6 +52,7 @@ struct EpiParams {
   const float* reg_in;       // register-token residual: [R][C] (shared) or [N][R][C] (per field)
   int reg_in_per_field;
   float* reg_out;            // [Nw][R][C] register-token outputs (block attention) or null
+  unsigned drop_seed, drop_salt; int drop_thresh; float drop_scale;   // nn.Dropout after to_out (maxvit.py:151); thresh 0 = off
 };
 
 // store 8 consecutive outputs at element offset `off` of ep.out in the selected output type
@@ -398,6 +400,15 @@ __device__ __forceinline__ void epi_attn_out(const EpiParams& ep, long long row,
     ld.load(ch, v);
     const int c0 = n0 + ch * 32;
     if (c0 >= C) continue;
+    if (ep.drop_thresh && ok) {                              // nn.Dropout after to_out, before the residual (maxvit.py:151, 310)
+      const uint32_t rid = drop_row(wdx, tok);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const uint32_t hsh = drop_hash(ep.drop_seed, rid, drop_group_out(ep.drop_salt, (c0 + j) >> 2));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[j + k] *= (int)((hsh >> (8 * k)) & 255u) >= ep.drop_thresh ? ep.drop_scale : 0.f;
+      }
+    }
     if (dst) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) { float t[8]; ld8(rsrc + c0 + j, t);

@@ -98,7 +98,7 @@ int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st)
 int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
                     float eps, void* tokens, int out_bf16, cudaStream_t st);
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
-                  const AttnGeom& g, int heads, int dh, void* out, cudaStream_t st);
+                  const AttnGeom& g, int heads, int dh, void* out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
 
 int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_per_field, float* reg_out,
                    const float* film, const void* wqkv_h, const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps,

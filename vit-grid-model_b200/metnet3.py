@@ -345,9 +345,8 @@ class MetNet3(nn.Module):
             raise NotImplementedError("the training kernels are built for n_start_channels=128; wider networks run inference only")
         if self.precision == "bf16_all":
             raise NotImplementedError("training supports set_precision('bf16') (mixed) and 'fp32'")
-        if self.dropout > 0 and self.precision != "bf16":
-            raise NotImplementedError("attention dropout (maxvit.py:146,151) is built into the mixed-precision ('bf16') path only; "
-                                      "construct with dropout=0.0 to train in fp32")
+        if self.precision not in ("bf16", "fp32"):
+            raise NotImplementedError("training supports set_precision('bf16') (mixed) and 'fp32'")
         return MetNet3TrainFn.apply(self, x, ts, *self.parameters())
 
     def next_dropout_seed(self) -> int:

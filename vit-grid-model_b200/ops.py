@@ -250,15 +250,15 @@ def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None, out_bf16=Fa
     return out
 
 
-def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None):
+def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None, drop=(0, 0, 0)):
     if out is None:
         out = torch.empty(qkv.shape[0], heads * dh, dtype=qkv.dtype, device=qkv.device)
     _lib.call("vg_attn_core_fwd", DT_CODE[qkv.dtype], qkv.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
-              bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, out.data_ptr(), _st())
+              bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, out.data_ptr(), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return out
 
 
-def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False):
+def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False, drop=(0, 0, 0)):
     N, Hl, Wl, C = x_in.shape
     nwin = (Hl // win) * (Wl // win)
     if x_out is None:
@@ -267,7 +267,7 @@ def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None
     keep, sp, sn = _scratch(attn.dtype, attn.shape[0] * C, attn.device, tf32)
     _lib.call("vg_attn_out_fwd", _gemm_code(attn.dtype, tf32), attn.data_ptr(), attn.shape[1], Wt.data_ptr(), x_in.data_ptr(),
               reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out), x_out.data_ptr(), N, Hl, Wl, C, win, R,
-              int(grid_mode), sp, sn, _st())
+              int(grid_mode), int(drop[0]), int(drop[1]), int(drop[2]), sp, sn, _st())
     return x_out, reg_out
 
 

@@ -159,12 +159,12 @@ def _attention_train_fwd(vit, x, film, P, reg_in, grid_mode, want_reg_out, drop=
         x_out, reg_out = ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
                                         vit.heads, vit.dim_head, drop=drop)
         return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, grid_mode=grid_mode, drop=drop)
-    if drop[2]:
-        raise NotImplementedError("attention dropout is built into the fused (mixed-precision) attention path only")
+    if drop[2] and vit.tf32:
+        raise NotImplementedError("attention dropout on the un-fused tf32 path (shapes the fused kernel does not cover) is not built")
     tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
     qkv = ops.gemm(tokens, P["w_qkv"], tf32=vit.tf32)
-    att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head)
-    x_out, reg_out = ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=vit.tf32)
+    att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, vit.heads, vit.dim_head, drop=drop)
+    x_out, reg_out = ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=vit.tf32, drop=drop)
     return x_out, reg_out, dict(x=x, film=film, reg_in=reg_in, tokens=tokens, qkv=qkv, att=att, grid_mode=grid_mode, drop=drop)
 
 
