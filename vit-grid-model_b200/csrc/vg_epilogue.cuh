@@ -98,6 +98,35 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, long long row, bo
   }
 }
 
+// plain fp32 row store (+ optional fp32 residual) of a 128-column accumulator row, 256-bit global accesses: the epilogue of the
+// convolution's data gradient in the halo kernel
+__device__ __forceinline__ void ld8_256(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+template <class Loader>
+__device__ __forceinline__ void epi_store_f32_rows(const EpiParams& ep, long long row, bool ok, Loader& ld) {
+  float v[32];
+  float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo;
+  const float* r = ep.res ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float rr[32];
+    if (ok && r) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) ld8_256(r + ch * 32 + j, rr + j);
+    }
+    ld.load(ch, v);
+    if (!ok) continue;
+    if (r) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += rr[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) st8_256(o + ch * 32 + j, v + j);
+  }
+}
+
 // EPI_STORE for the tcgen05 kernel: same math as epi_store, but the 32x32 block a warp reads from TMEM (one row per
 // thread) is transposed through a padded shared-memory tile so that every global access is a run of four full
 // 128-byte row segments per warp instruction instead of 32 scattered 16-byte pieces (the row-per-thread stores made

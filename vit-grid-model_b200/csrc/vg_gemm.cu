@@ -228,6 +228,7 @@ struct HaloShape {
   int HR;               // halo rows loaded per tile (multiple of 16)
   int use_base_offset;
   int res_tma;          // the fp32 residual arrives through mapR (else: per-thread global loads)
+  int flip;             // data gradient: tap t of the weights is applied with the input shift of tap 8 - t (the negated shift)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int row) {
@@ -235,7 +236,9 @@ __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int
   return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <bool TRAIN>
+// MODE 0: conv + ChanLN / FiLM / ReLU / residual epilogue; 1: the same, saving xhat / rstd / mask for backward; 2: plain fp32 store
+// (+ fp32 residual) -- the DATA GRADIENT of the convolution runs through the same halo pipeline with the tap order flipped
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapR, const HaloShape hs, const EpiParams ep) {
@@ -264,8 +267,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
-    sparam[i] = ep.bias[i]; sparam[128 + i] = ep.ln_g[i]; sparam[256 + i] = ep.ln_b[i];
+  if (MODE != 2) {
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
+      sparam[i] = ep.bias[i]; sparam[128 + i] = ep.ln_g[i]; sparam[256 + i] = ep.ln_b[i];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -287,7 +292,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty + stage, phase ^ 1);
             mbar_arrive_expect_tx(full + stage, B_BYTES);
-            tma_load_2d(sB + stage * B_BYTES, &mapB, full + stage, tap * 128 + cb * 64, 0);
+            tma_load_2d(sB + stage * B_BYTES, &mapB, full + stage, (hs.flip ? 8 - tap : tap) * 128 + cb * 64, 0);
             if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -355,13 +360,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (hs.res_tma) {
         cx.res_g0 = it * 4; cx.res_row0 = row - lane;
         cx.res_next_row0 = (t + (int)gridDim.x < hs.num_tiles) ? cx.res_row0 + (long long)gridDim.x * BM : -1;
-      } else {
+      } else if (MODE != 2) {
         epi_conv_ln_prefetch<bf16>(ep, row, ok);
       }
       mbar_wait(tfull + as, aphase);
       tc_fence_after();
       TmemLoader ld{tmem_base + as * 256 + e * 128 + ((uint32_t)(lg * 32) << 16)};
-      run_epilogue<TRAIN ? EPI_CONV_LN_TRAIN : EPI_CONV_LN, bf16>(ep, cx, row, ok, 0, ld);
+      if constexpr (MODE == 2) epi_store_f32_rows(ep, row, ok && row < hs.M, ld);
+      else run_epilogue<MODE == 1 ? EPI_CONV_LN_TRAIN : EPI_CONV_LN, bf16>(ep, cx, row, ok, 0, ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
@@ -710,8 +716,15 @@ static int launch_simt_epi(const float* scratch, int Ntot, const GemmShape& gs, 
 }
 
 // bf16 3x3 conv (Cin = Cout = 128) over a PG buffer with halo reuse; returns -1 when the shape does not fit
+int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const EpiParams& ep, int mode_k, int flip, cudaStream_t st);
+
 int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, int train, cudaStream_t st) {
-  const int P = pg.P;
+  return conv_halo_run_mp(x, Wt, pg.pixels(), pg.P, ep, train ? 1 : 0, 0, st);
+}
+
+// mode 0 / 1: forward (+ training outputs); 2: plain fp32 store (+ fp32 residual); flip: data gradient (negated tap shifts)
+int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const EpiParams& ep, int mode_k, int flip, cudaStream_t st) {
+  const int train = mode_k == 1;
   const int HR = ((BM + 2 * (P + 1)) + 15) / 16 * 16;
   if (HR > HALO_MAX_ROWS) return -1;
   static int mode = -1;
@@ -723,13 +736,13 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   CUtensorMap ma, mb, mr;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
-  const bool res_tma = res_tma_mode && ep.res && ep.res_f32 && ep.ldres == 128 && (reinterpret_cast<uintptr_t>(ep.res) & 15) == 0;
+  const bool res_tma = mode_k != 2 && res_tma_mode && ep.res && ep.res_f32 && ep.ldres == 128 && (reinterpret_cast<uintptr_t>(ep.res) & 15) == 0;
   if (res_tma) {
-    int rc = make_map_2d(&mr, true, ep.res, 128, pg.pixels(), 32);
+    int rc = make_map_2d(&mr, true, ep.res, 128, M, 32);
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[2] = {128, (cuuint64_t)pg.pixels()};
+    cuuint64_t dims[2] = {128, (cuuint64_t)M};
     cuuint64_t strides[1] = {256};
     cuuint32_t box[2] = {64u, (cuuint32_t)(HR / 2)};
     cuuint32_t estr[2] = {1u, 1u};
@@ -741,11 +754,13 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   int rc = make_map_2d(&mb, false, Wt, 9 * 128, 128, BN);
   if (rc) return rc;
   HaloShape hs;
-  hs.M = pg.pixels(); hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset; hs.res_tma = res_tma ? 1 : 0;
+  hs.M = M; hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset; hs.res_tma = res_tma ? 1 : 0;
+  hs.flip = flip;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -755,7 +770,7 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
   // default: on B200 it measures 1.28 ms against 1.18 ms -- the single-CTA kernel already runs at 0.81 of the sustained
   // (power-capped) bf16 peak, so halving the weight-tile traffic buys nothing (profiles/r01_summary.md).
   const char* pe = getenv("VG_CONV_PAIR");
-  const bool pair_mode = pe && pe[0] == '1';
+  const bool pair_mode = pe && pe[0] == '1' && mode_k != 2;
   if (pair_mode && num_sms() >= 2) {
     CUtensorMap mb2;
     rc = make_map_2d(&mb2, false, Wt, 9 * 128, 128, 64);     // half of the output channels per CTA
@@ -780,8 +795,9 @@ int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParam
     if (le != cudaSuccess) return set_error("conv_halo2 launch: %s", cudaGetErrorString(le));
     return check_launch("conv_halo2_kernel");
   }
-  if (train) conv_halo_kernel<true><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
-  else conv_halo_kernel<false><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
+  if (mode_k == 2) conv_halo_kernel<2><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
+  else if (train) conv_halo_kernel<1><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
+  else conv_halo_kernel<0><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
   return check_launch("conv_halo_kernel");
 }
 
@@ -812,6 +828,19 @@ int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const 
   const int Ktot = Ca * ntaps;
   if ((kind == EPI_CONV_LN || kind == EPI_CONV_LN_TRAIN) && Ntot != BN) return set_error("gemm: conv+LN epilogue needs exactly %d output channels (got %d)", BN, Ntot);
 
+  // The data gradient of a 128 -> 128 3x3 convolution (bf16 operands, fp32 output, optional fp32 residual, tap shifts = the
+  // negated -- or plain -- shifts of a row pitch P) runs through the halo-reuse kernel: 1.7x the generic shifted-row GEMM
+  if (dtype == 0 && !f16 && kind == EPI_STORE && ntaps == 9 && Ca == 128 && Ntot == 128 && !batched && rowsA == M && ep.out_f32 == 1 &&
+      !ep.col_scale && !ep.bias && ep.act == 0 && (!ep.res || (ep.res_f32 && ep.ldres == 128)) && ep.ldo == 128) {
+    const int P = tap_shift[3] - tap_shift[0];                 // (ky) step of the shift pattern, signed
+    const int sgn = P < 0 ? -1 : 1, aP = P < 0 ? -P : P;
+    bool pattern = aP > 2;
+    for (int t = 0; t < 9 && pattern; ++t) pattern = tap_shift[t] == sgn * ((t / 3 - 1) * aP + (t % 3 - 1));
+    if (pattern) {
+      const int rc = conv_halo_run_mp(A, B, M, aP, ep, 2, sgn < 0 ? 1 : 0, st);
+      if (rc >= 0) return rc;
+    }
+  }
   if (dtype == 0 || dtype == 2) {
     CUtensorMap ma, mb;
     int rc = make_map_2d(&ma, dtype == 2, A, Ca, rowsA, BM);       // one 256-row box per K block
