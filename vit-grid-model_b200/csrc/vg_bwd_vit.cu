@@ -1538,7 +1538,12 @@ int dropout_mask_debug_run(unsigned seed, unsigned salt, int drop_thresh, long l
   return check_launch("dropout_mask_debug_kernel");
 }
 
-// use_tf32: 0 exact-fp32 SIMT, 1 tf32 mma.sync, 2 bf16 mma.sync on fp32 tensors, 3 bf16 mma.sync on bf16 tensors (qkv, datt, dqkv, att_out)
+int attn_core_bwd_tc_run(const void* qkv, const void* datt, const float* qgamma, const float* kgamma, const float* bias_table,
+                         const AttnGeom& g, int heads, void* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
+                         void* att_out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st);
+
+// use_tf32: 0 exact-fp32 SIMT, 1 tf32 mma.sync, 2 bf16 mma.sync on fp32 tensors, 3 bf16 tensors (qkv, datt, dqkv, att_out): the
+// tcgen05 kernel (vg_attn_bwd_tc.cu); VG_ATTN_BWD_TC=0 or a shape outside it selects the bf16 mma.sync kernel
 int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, const float* kgamma, const float* bias_table,
                       const AttnGeom& g, int heads, int dh, float* dqkv, float* dqgamma, float* dkgamma, float* dbias_table,
                       int use_tf32, float* att_out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
@@ -1547,6 +1552,14 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   if (drop_thresh && use_tf32 == 1) return set_error("attn_core_bwd: dropout is built into the bf16 tensor-core kernels (modes 2, 3) and the exact-fp32 kernel (mode 0)");
   if (g.S() > 64) return set_error("attn_core_bwd: sequence %d > 64", g.S());
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
+  if (use_tf32 == 3) {
+    const char* e = getenv("VG_ATTN_BWD_TC");                // read per call so one process can compare the two kernels
+    if (!(e && e[0] == '0')) {
+      const int rc = attn_core_bwd_tc_run(qkv, datt, qgamma, kgamma, bias_table, g, heads, dqkv, dqgamma, dkgamma, dbias_table, att_out,
+                                          seed, salt, drop_thresh, st);
+      if (rc >= 0) return rc;
+    }
+  }
   if (use_tf32 == 2 || use_tf32 == 3) {
     // mode 3: two cp.async stages of [q | k | v | dO] rows instead of the static V / dO tiles
     const size_t smem3 = (size_t)cbh::BYTES + (size_t)(2 * nb + 6 * cbh::DH) * sizeof(float) +
