@@ -117,6 +117,13 @@ __device__ __forceinline__ void st16_256(bf16* p, const float* v) {
                "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
 }
 __device__ __forceinline__ void st16_256(float* p, const float* v) { st8_256(p, v); st8_256(p + 8, v + 8); }
+__device__ __forceinline__ void st16_256(__half* p, const float* v) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); u[i] = *reinterpret_cast<uint32_t*>(&h); }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
 
 // erf by Abramowitz & Stegun 7.1.26 (|error| < 6.1e-7 in fp32 arithmetic, checked against double over [-6, 6]): five FMAs and
 // two MUFU ops instead of libdevice erff's two polynomial branches -- the exact-erf GELU (nn.GELU(), maxvit.py:45,48) of

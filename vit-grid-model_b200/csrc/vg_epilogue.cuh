@@ -127,6 +127,30 @@ __device__ __forceinline__ void epi_store_f32_rows(const EpiParams& ep, long lon
   }
 }
 
+// EPI_STORE with a 16-bit output and nothing else to do (no scale / bias / activation / residual): every thread converts its row's 32
+// accumulator columns and writes them as two 256-bit stores (64 contiguous bytes).  The transposing epilogue below needs 8 + 8
+// shared-memory instructions and 8 stores per 32 columns for the same 64 sectors; with one epilogue warp pair per scheduler that
+// instruction count, not HBM, bounded the QKV re-materialisation GEMM of the training step (0.88 ms for 1.9 GB of output)
+template <typename T>
+__device__ __forceinline__ bool epi_store_rows16_ok(const EpiParams& ep) {
+  const bool out16 = ep.out_f32 == 2 || ep.out_f32 == 3 || (ep.out_f32 == 0 && sizeof(T) == 2);
+  return out16 && !ep.res && !ep.col_scale && !ep.bias && ep.act == 0 && (ep.n_total & 31) == 0 && (ep.ldo & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0;
+}
+template <class Loader>
+__device__ __forceinline__ void epi_store_rows16(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+  float v[32];
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    const int c0 = n0 + ch * 32;
+    ld.load(ch, v);
+    if (c0 >= ep.n_total || !ok) continue;
+    const long long off = row * ep.ldo + c0;
+    if (ep.out_f32 == 3) { __half* o = reinterpret_cast<__half*>(ep.out) + off; st16_256(o, v); st16_256(o + 16, v + 16); }
+    else { bf16* o = reinterpret_cast<bf16*>(ep.out) + off; st16_256(o, v); st16_256(o + 16, v + 16); }
+  }
+}
+
 // EPI_STORE for the tcgen05 kernel: same math as epi_store, but the 32x32 block a warp reads from TMEM (one row per
 // thread) is transposed through a padded shared-memory tile so that every global access is a run of four full
 // 128-byte row segments per warp instruction instead of 32 scattered 16-byte pieces (the row-per-thread stores made

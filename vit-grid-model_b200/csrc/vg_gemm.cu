@@ -181,8 +181,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (nv2 < nv) nv = nv2;
         const int nvalid = nv < 0 ? 0 : (nv > 32 ? 32 : (int)nv);
         float* stg = sparam + (warp - 4) * (32 * 36);
-        if (TF32) epi_store_coalesced<float>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
-        else epi_store_coalesced<bf16>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+        if (TF32) {
+          if (epi_store_rows16_ok<float>(ep)) epi_store_rows16(ep, row, ok, n_tile * BN, ld);
+          else epi_store_coalesced<float>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+        } else {
+          if (epi_store_rows16_ok<bf16>(ep)) epi_store_rows16(ep, row, ok, n_tile * BN, ld);
+          else epi_store_coalesced<bf16>(ep, row - lane, nvalid, n_tile * BN, ld, stg, lane);
+        }
       } else if constexpr (KIND == EPI_CONVT) {
         float* stg = sparam + (warp - 4) * (32 * 36);
         if (TF32) epi_convt_coalesced<float>(ep, row, ok, n_tile * BN, ld, stg, lane);
