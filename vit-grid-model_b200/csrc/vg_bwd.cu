@@ -32,11 +32,14 @@ struct ConvLnBwdParams {
   PGeom pg;
 };
 
+// Half a warp per pixel (lane = 8 channels), two pixels per half-warp in flight: the kernel is a stream of 1 KB rows with two
+// 16-lane reductions each, and with one row per warp-iteration the loads of a row waited out the full DRAM latency behind the
+// shuffles of the previous one (3.1 TB/s); four rows per warp-iteration are issued before the first is used.
 template <typename T, typename TO>
-__global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams p) {
-  constexpr int C = 128, PPW = 64;
+__global__ void __launch_bounds__(256, 3) conv_ln_bwd_kernel(const ConvLnBwdParams p) {
+  constexpr int C = 128, PPW = 64, U = 2;
   __shared__ float sacc[3][C];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, sub = lane >> 4, c0 = hl * 8;
   const long long q_block = (long long)blockIdx.x * (8 * PPW);
   for (int i = threadIdx.x; i < 3 * C; i += 256) (&sacc[0][0])[i] = 0.f;
   int nf0, hh, ww;
@@ -45,58 +48,66 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
   __syncthreads();
   const T* xh = reinterpret_cast<const T*>(p.xhat);
   TO* dc = reinterpret_cast<TO*>(p.dconv);
-  float A[4] = {0.f, 0.f, 0.f, 0.f}, B[4] = {0.f, 0.f, 0.f, 0.f}, D[4] = {0.f, 0.f, 0.f, 0.f};
-  float gs[4] = {0.f, 0.f, 0.f, 0.f};
+  float A[8], B[8], D[8], gs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) A[i] = B[i] = D[i] = gs[i] = 0.f;
   int n_cur = -1;
   auto flush = [&]() {
     if (n_cur < 0) return;
-    if (n_cur == nf0) {
+    float* dA = n_cur == nf0 ? &sacc[0][c0] : p.sumA + (long long)n_cur * C + c0;
+    float* dB = n_cur == nf0 ? &sacc[1][c0] : p.sumB + (long long)n_cur * C + c0;
+    float* dD = n_cur == nf0 ? &sacc[2][c0] : p.sumD + (long long)n_cur * C + c0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { atomicAdd(&sacc[0][c0 + i], A[i]); atomicAdd(&sacc[1][c0 + i], B[i]); atomicAdd(&sacc[2][c0 + i], D[i]); }
-    } else {
+    for (int i = 0; i < 8; ++i) { atomicAdd(dA + i, A[i]); atomicAdd(dB + i, B[i]); atomicAdd(dD + i, D[i]); A[i] = B[i] = D[i] = 0.f; }
+  };
+  const long long q0 = q_block + warp * PPW;
+  const long long npix = p.pg.pixels();
+  const bool small = npix < (1ll << 31);
+  for (int k = 0; k < PPW; k += 2 * U) {
+    long long q[U]; int n[U], h[U], w[U]; bool valid[U], inr[U];
+    float dy[U][8], x[U][8], rstd[U]; unsigned bits[U];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        atomicAdd(p.sumA + (long long)n_cur * C + c0 + i, A[i]); atomicAdd(p.sumB + (long long)n_cur * C + c0 + i, B[i]);
-        atomicAdd(p.sumD + (long long)n_cur * C + c0 + i, D[i]);
+    for (int u = 0; u < U; ++u) {
+      q[u] = q0 + k + 2 * u + sub;
+      inr[u] = q[u] < npix;
+      valid[u] = inr[u] && (small ? p.pg.decode32((unsigned)q[u], n[u], h[u], w[u]) : p.pg.decode(q[u], n[u], h[u], w[u]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dy[u][i] = x[u][i] = 0.f;
+      rstd[u] = 0.f; bits[u] = 0u;
+      if (valid[u]) {
+        ld8(p.dY + q[u] * C + c0, dy[u]);
+        ld8(xh + q[u] * C + c0, x[u]);
+        bits[u] = p.mask[q[u] * 4 + (hl >> 2)] >> ((hl & 3) * 8);
+        rstd[u] = p.rstd[q[u]];
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) A[i] = B[i] = D[i] = 0.f;
-  };
-  const long long q0 = q_block + warp * PPW;
-  for (int k = 0; k < PPW; ++k) {
-    const long long q = q0 + k;
-    if (q >= p.pg.pixels()) break;
-    int n, h, w;
-    const bool valid = p.pg.decode(q, n, h, w);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      if (n != n_cur) {
+    for (int u = 0; u < U; ++u) {
+      if (valid[u] && n[u] != n_cur) {
         flush();
-        n_cur = n;
+        n_cur = n[u];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gs[i] = p.ln_g[c0 + i] * (p.film ? p.film[(long long)n * 2 * C + c0 + i] + 1.0f : 1.0f);
+        for (int i = 0; i < 8; ++i) gs[i] = p.ln_g[c0 + i] * (p.film ? p.film[(long long)n_cur * 2 * C + c0 + i] + 1.0f : 1.0f);
       }
-      const float4 dy = *reinterpret_cast<const float4*>(p.dY + q * C + c0);
-      float x[4];
+      float dx[8], o[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = Act<T>::ld(xh + q * C + c0 + i);
-      const unsigned bits = p.mask[q * 4 + (lane >> 3)] >> ((lane & 7) * 4);
-      const float rstd = p.rstd[q];
-      float dz[4] = {(bits & 1u) ? dy.x : 0.f, (bits & 2u) ? dy.y : 0.f, (bits & 4u) ? dy.z : 0.f, (bits & 8u) ? dy.w : 0.f};
-      float dx[4], s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const float dz = ((bits[u] >> i) & 1u) ? dy[u][i] : 0.f;
+        dx[i] = dz * gs[i]; s1 += dx[i]; s2 = fmaf(dx[i], x[u][i], s2);
+        A[i] = fmaf(dz, x[u][i], A[i]); B[i] += dz;
+      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { dx[i] = dz[i] * gs[i]; s1 += dx[i]; s2 += dx[i] * x[i]; A[i] += dz[i] * x[i]; B[i] += dz[i]; }
-      s1 = warp_sum(s1) * (1.0f / C);
-      s2 = rstd >= p.rstd_clamp ? 0.f : warp_sum(s2) * (1.0f / C);     // var.clamp(min=eps): no gradient through a clamped variance
+      for (int o2 = 8; o2 >= 1; o2 >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o2); s2 += __shfl_xor_sync(0xffffffffu, s2, o2); }
+      s1 *= (1.0f / C);
+      s2 = rstd[u] >= p.rstd_clamp ? 0.f : s2 * (1.0f / C);        // var.clamp(min=eps): no gradient through a clamped variance
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { o[i] = rstd * (dx[i] - s1 - x[i] * s2); D[i] += o[i]; }
-      if (p.border) {
-        const bool r0 = h == 0, rl = h == p.pg.HP - 1, k0 = w == 0, kl = w == p.pg.WP - 1;
+      for (int i = 0; i < 8; ++i) { o[i] = valid[u] ? rstd[u] * (dx[i] - s1 - x[u][i] * s2) : 0.f; D[i] += o[i]; }
+      if (p.border && valid[u]) {
+        const bool r0 = h[u] == 0, rl = h[u] == p.pg.HP - 1, k0 = w[u] == 0, kl = w[u] == p.pg.WP - 1;
         if (r0 | rl | k0 | kl) {
-          float* bb = p.border + (long long)n * 8 * C + c0;
+          float* bb = p.border + (long long)n[u] * 8 * C + c0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 8; ++i) {
             if (r0) atomicAdd(bb + 0 * C + i, o[i]);
             if (rl) atomicAdd(bb + 1 * C + i, o[i]);
             if (k0) atomicAdd(bb + 2 * C + i, o[i]);
@@ -108,9 +119,8 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
           }
         }
       }
+      if (inr[u]) st8(dc + q[u] * C + c0, o);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Act<TO>::st(dc + q * C + c0 + i, o[i]);
   }
   flush();
   __syncthreads();
@@ -124,20 +134,27 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
 
 // parameter gradients of one Block from the per-field sums (one thread per channel):
 //   dg += sum_n A (s+1);  db += sum_n B (s+1);  dbias += sum_n D;  dfilm[n] = (A g + B b | B)
-__global__ void conv_ln_param_grads_kernel(const float* __restrict__ sumA, const float* __restrict__ sumB, const float* __restrict__ sumD,
+__global__ void __launch_bounds__(256) conv_ln_param_grads_kernel(const float* __restrict__ sumA, const float* __restrict__ sumB, const float* __restrict__ sumD,
                                            int N, const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ film,
                                            float* __restrict__ dg, float* __restrict__ db, float* __restrict__ dbias, float* __restrict__ dfilm) {
   constexpr int C = 128;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[3][8][32];
+  const int l = threadIdx.x & 31, slice = threadIdx.x >> 5, c = blockIdx.x * 32 + l;     // 32 channels x 8 slices of the fields
   float ag = 0.f, ab = 0.f, ad = 0.f;
-  for (int n = 0; n < N; ++n) {
+  for (int n = slice; n < N; n += 8) {
     const float A = sumA[n * C + c], B = sumB[n * C + c];
     const float s1 = film ? film[(long long)n * 2 * C + c] + 1.0f : 1.0f;
     ag += A * s1; ab += B * s1; ad += sumD[n * C + c];
     if (dfilm) { dfilm[(long long)n * 2 * C + c] = A * g[c] + B * b[c]; dfilm[(long long)n * 2 * C + C + c] = B; }
   }
-  dg[c] += ag; db[c] += ab; dbias[c] += ad;
+  red[0][slice][l] = ag; red[1][slice][l] = ab; red[2][slice][l] = ad;
+  __syncthreads();
+  if (slice == 0) {
+    ag = ab = ad = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ag += red[0][k][l]; ab += red[1][k][l]; ad += red[2][k][l]; }
+    dg[c] += ag; db[c] += ab; dbias[c] += ad;
+  }
 }
 
 // ================================================================================================
@@ -318,18 +335,26 @@ __device__ __forceinline__ float valid_sum(const float* border, const float* sum
   return v;
 }
 
-// grid: one thread per (co, ct, tap10) -- tap 9 = the 1x1 res_conv
-__global__ void time_w_bwd_kernel(const TimeBwdParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.Cout * p.ntc * 10) return;
-  const int tap = i % 10, ct = (i / 10) % p.ntc, co = i / (10 * p.ntc);
-  float acc = 0.f;
-  for (int n = 0; n < p.N; ++n) {
-    const float v = tap == 9 ? p.tres_sum[(long long)n * p.Cout + co] : valid_sum(p.border, p.sumD, n, co, p.Cout, tap / 3, tap % 3);
-    acc += p.temb[n * p.ntc + ct] * v;
+// grid: one block per (co, tap10) -- tap 9 = the 1x1 res_conv; the per-field factor is computed once into shared memory, then a
+// thread per time channel sums over the fields (a thread per (co, ct, tap) looping over N was 480 us of dependent L2 round trips)
+__global__ void __launch_bounds__(128) time_w_bwd_kernel(const TimeBwdParams p) {
+  extern __shared__ float sv[];                            // [N]
+  const int tap = blockIdx.x % 10, co = blockIdx.x / 10;
+  for (int n = threadIdx.x; n < p.N; n += 128)
+    sv[n] = tap == 9 ? p.tres_sum[(long long)n * p.Cout + co] : valid_sum(p.border, p.sumD, n, co, p.Cout, tap / 3, tap % 3);
+  __syncthreads();
+  for (int ct = threadIdx.x; ct < p.ntc; ct += 128) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0;
+    for (; n + 3 < p.N; n += 4) {
+      a0 = fmaf(p.temb[n * p.ntc + ct], sv[n], a0); a1 = fmaf(p.temb[(n + 1) * p.ntc + ct], sv[n + 1], a1);
+      a2 = fmaf(p.temb[(n + 2) * p.ntc + ct], sv[n + 2], a2); a3 = fmaf(p.temb[(n + 3) * p.ntc + ct], sv[n + 3], a3);
+    }
+    for (; n < p.N; ++n) a0 = fmaf(p.temb[n * p.ntc + ct], sv[n], a0);
+    const float acc = (a0 + a1) + (a2 + a3);
+    if (tap == 9) p.dw1[(long long)co * p.c_in + p.c_data + ct] += acc;
+    else p.dw3[((long long)co * p.c_in + p.c_data + ct) * 9 + tap] += acc;
   }
-  if (tap == 9) p.dw1[(long long)co * p.c_in + p.c_data + ct] += acc;
-  else p.dw3[((long long)co * p.c_in + p.c_data + ct) * 9 + tap] += acc;
 }
 // one block per field n: dtemb[n][ct]; thread 0.. also adds db1 (res_conv bias) = sum_n tres_sum
 __global__ void __launch_bounds__(128) time_emb_bwd_kernel(const TimeBwdParams p) {
@@ -420,19 +445,23 @@ __global__ void __launch_bounds__(256) cond_mlp_bwd_kernel(const float* __restri
 }
 
 // dW[o][i] += sum_n G[n][o] * X[n][i];  db[o] += sum_n G[n][o]   (tiny reductions over the fields)
-__global__ void outer_sum_kernel(const float* __restrict__ G, const float* __restrict__ X, int N, int O, int I,
-                                 float* __restrict__ dW, float* __restrict__ db) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per output element, lanes stride the fields: with a thread per output the loop over N was a chain of N dependent L2
+// round trips (68 us per launch for 4 MB of traffic).
+__global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict__ G, const float* __restrict__ X, int N, int O, int I,
+                                                        float* __restrict__ dW, float* __restrict__ db) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (t < O * I) {
     const int o = t / I, i = t - o * I;
     float a = 0.f;
-    for (int n = 0; n < N; ++n) a += G[(long long)n * O + o] * X[(long long)n * I + i];
-    dW[t] += a;
+    for (int n = lane; n < N; n += 32) a = fmaf(G[(long long)n * O + o], X[(long long)n * I + i], a);
+    a = warp_sum(a);
+    if (lane == 0) dW[t] += a;
   }
   if (db && t < O) {
     float a = 0.f;
-    for (int n = 0; n < N; ++n) a += G[(long long)n * O + t];
-    db[t] += a;
+    for (int n = lane; n < N; n += 32) a += G[(long long)n * O + t];
+    a = warp_sum(a);
+    if (lane == 0) db[t] += a;
   }
 }
 
@@ -474,7 +503,7 @@ int conv_ln_bwd_run(int xdtype, int odtype, const float* dY, const void* xhat, c
 
 int conv_ln_param_grads_run(const float* sumA, const float* sumB, const float* sumD, int N, const float* g, const float* b,
                             const float* film, float* dg, float* db, float* dbias, float* dfilm, cudaStream_t st) {
-  conv_ln_param_grads_kernel<<<1, 128, 0, st>>>(sumA, sumB, sumD, N, g, b, film, dg, db, dbias, dfilm);
+  conv_ln_param_grads_kernel<<<4, 256, 0, st>>>(sumA, sumB, sumD, N, g, b, film, dg, db, dbias, dfilm);
   return check_launch("conv_ln_param_grads_kernel");
 }
 
@@ -530,7 +559,7 @@ int time_terms_bwd_run(const float* border, const float* sumD, const float* tres
   TimeBwdParams p;
   p.border = border; p.sumD = sumD; p.tres_sum = tres_sum; p.temb = temb; p.w3 = w3; p.w1 = w1;
   p.dw3 = dw3; p.dw1 = dw1; p.dtemb = dtemb; p.db1 = db1; p.N = N; p.ntc = ntc; p.c_in = c_in; p.c_data = c_data; p.Cout = Cout;
-  time_w_bwd_kernel<<<nblk((long long)Cout * ntc * 10, 128), 128, 0, st>>>(p);
+  time_w_bwd_kernel<<<Cout * 10, 128, (size_t)N * sizeof(float), st>>>(p);
   int rc = check_launch("time_w_bwd_kernel");
   if (rc) return rc;
   time_emb_bwd_kernel<<<N, 128, 0, st>>>(p);
@@ -553,16 +582,16 @@ int cond_mlp_bwd_run(const float* cond, int N, int cd, int pre_relu, const float
   cond_mlp_bwd_kernel<<<N, 256, (cd + hid + od) * sizeof(float), st>>>(cond, cd, pre_relu, W0, b0, hid, W1, od, dout, xin, dpre, hact, dcond);
   int rc = check_launch("cond_mlp_bwd_kernel");
   if (rc) return rc;
-  outer_sum_kernel<<<nblk((long long)hid * cd > hid ? (long long)hid * cd : hid, 128), 128, 0, st>>>(dpre, xin, N, hid, cd, dW0, db0);
+  outer_sum_kernel<<<nblk((long long)hid * cd > hid ? (long long)hid * cd : hid, 8), 256, 0, st>>>(dpre, xin, N, hid, cd, dW0, db0);
   rc = check_launch("outer_sum_kernel");
   if (rc || !W1) return rc;
-  outer_sum_kernel<<<nblk((long long)od * hid, 128), 128, 0, st>>>(dout, hact, N, od, hid, dW1, db1);
+  outer_sum_kernel<<<nblk((long long)od * hid, 8), 256, 0, st>>>(dout, hact, N, od, hid, dW1, db1);
   return check_launch("outer_sum_kernel");
 }
 
 int outer_sum_run(const float* G, const float* X, int N, int O, int I, float* dW, float* db, cudaStream_t st) {
   const long long t = (long long)O * I > O ? (long long)O * I : O;
-  outer_sum_kernel<<<nblk(t, 128), 128, 0, st>>>(G, X, N, O, I, dW, db);
+  outer_sum_kernel<<<nblk(t, 8), 256, 0, st>>>(G, X, N, O, I, dW, db);
   return check_launch("outer_sum_kernel");
 }
 

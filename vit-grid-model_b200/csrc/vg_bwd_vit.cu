@@ -33,16 +33,42 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
   }
 }
 
+// Sum of the per-block partials part[p][2][C] over p for channel c, by the 8 slices (threadIdx.x >> 5) of a 256-thread block that
+// covers 32 channels: the single-thread loop over ~1000-2000 partials was a chain of dependent L2 round trips (170 us per
+// launch for a kernel that moves 4 MB).  Returns the totals to every thread of the channel.
+__device__ __forceinline__ void sum_parts2(const float* __restrict__ part, int nparts, int C, int c, double& s1, double& s2) {
+  __shared__ double red[2][8][32];
+  const int slice = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    int p = slice;
+    for (; p + 24 < nparts; p += 32) {
+      const float a0 = part[((long long)p * 2) * C + c], b0 = part[((long long)p * 2 + 1) * C + c];
+      const float a1 = part[((long long)(p + 8) * 2) * C + c], b1 = part[((long long)(p + 8) * 2 + 1) * C + c];
+      const float a2 = part[((long long)(p + 16) * 2) * C + c], b2 = part[((long long)(p + 16) * 2 + 1) * C + c];
+      const float a3 = part[((long long)(p + 24) * 2) * C + c], b3 = part[((long long)(p + 24) * 2 + 1) * C + c];
+      a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+    }
+    for (; p < nparts; p += 8) { a += part[((long long)p * 2) * C + c]; b += part[((long long)p * 2 + 1) * C + c]; }
+  }
+  red[0][slice][l] = a; red[1][slice][l] = b;
+  __syncthreads();
+  s1 = 0.0; s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1 += red[0][k][l]; s2 += red[1][k][l]; }
+}
+
 // BatchNorm2d training statistics (maxvit.py:89,92,96): biased variance for normalisation, unbiased for the running
 // estimate, momentum update of the running buffers, and the folded per-channel affine  y = raw*scale + shift.
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ run_mean,
                                    float* __restrict__ run_var, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);       // 256 threads: 32 channels x 8 slices of the partials
   double s = 0.0, s2 = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += part[((long long)p * 2) * C + c]; s2 += part[((long long)p * 2 + 1) * C + c]; }
+  sum_parts2(part, nparts, C, c, s, s2);
+  if (c >= C || threadIdx.x >= 32) return;
   const double m = s / (double)M;
   double var = s2 / (double)M - m * m;
   if (var < 0.0) var = 0.0;
@@ -138,10 +164,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p,
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);       // 256 threads: 32 channels x 8 slices of the partials
   double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < nparts; ++p) { s1 += part[((long long)p * 2) * C + c]; s2 += part[((long long)p * 2 + 1) * C + c]; }
+  sum_parts2(part, nparts, C, c, s1, s2);
+  if (c >= C || threadIdx.x >= 32) return;
   dbeta[c] += (float)s1; dgamma[c] += (float)s2;
   k1[c] = (float)(s1 / (double)M); k2[c] = (float)(s2 / (double)M);
 }
@@ -164,13 +190,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p, 
   *reinterpret_cast<float4*>(draw + r * p.C + c) = o;
 }
 
-// out[j] (+)= sum_p part[p][j]
+// out[j] (+)= sum_p part[p][j]: 32 outputs x 8 slices of the partials per block
 __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int nparts, long long n, float beta, float* __restrict__ out) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + j];
-  out[j] = (beta != 0.f ? beta * out[j] : 0.f) + s;
+  __shared__ float red[8][32];
+  const int l = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long j = (long long)blockIdx.x * 32 + l;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < n) {
+    int p = slice;
+    for (; p + 8 < nparts; p += 16) { s0 += part[(long long)p * n + j]; s1 += part[(long long)(p + 8) * n + j]; }
+    if (p < nparts) s0 += part[(long long)p * n + j];
+  }
+  red[slice][l] = s0 + s1;
+  __syncthreads();
+  if (slice == 0 && j < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][l];
+    out[j] = (beta != 0.f ? beta * out[j] : 0.f) + s;
+  }
 }
 
 // column sums of X fp32 [M][C] accumulated into out[C] (bias gradients)
@@ -438,16 +476,27 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ d
   }
   __syncthreads();
   for (int j = threadIdx.x; j < se; j += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < C; ++c) a += W2[(long long)c * se + j] * sp[c];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;         // four chains: the loads of a single one waited for each other
+    int c = 0;
+    for (; c + 3 < C; c += 4) {
+      a0 = fmaf(W2[(long long)c * se + j], sp[c], a0); a1 = fmaf(W2[(long long)(c + 1) * se + j], sp[c + 1], a1);
+      a2 = fmaf(W2[(long long)(c + 2) * se + j], sp[c + 2], a2); a3 = fmaf(W2[(long long)(c + 3) * se + j], sp[c + 3], a3);
+    }
+    for (; c < C; ++c) a0 = fmaf(W2[(long long)c * se + j], sp[c], a0);
+    float a = (a0 + a1) + (a2 + a3);
     if (hid[(long long)n * se + j] <= 0.f) a = 0.f;
     sd[j] = a; dhid[(long long)n * se + j] = a;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int j = 0; j < se; ++j) a += W1[(long long)j * C + c] * sd[j];
-    dmean[(long long)n * C + c] = a * inv_count;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 3 < se; j += 4) {
+      a0 = fmaf(W1[(long long)j * C + c], sd[j], a0); a1 = fmaf(W1[(long long)(j + 1) * C + c], sd[j + 1], a1);
+      a2 = fmaf(W1[(long long)(j + 2) * C + c], sd[j + 2], a2); a3 = fmaf(W1[(long long)(j + 3) * C + c], sd[j + 3], a3);
+    }
+    for (; j < se; ++j) a0 = fmaf(W1[(long long)j * C + c], sd[j], a0);
+    dmean[(long long)n * C + c] = ((a0 + a1) + (a2 + a3)) * inv_count;
   }
 }
 
@@ -1374,7 +1423,7 @@ int bn_stats_run(const float* X, long long M, int C, const float* gamma, const f
   colstats_kernel<<<nparts, 256, 0, st>>>(X, M, C, work);
   int rc = check_launch("colstats_kernel");
   if (rc) return rc;
-  bn_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(work, nparts, M, C, gamma, beta, eps, momentum, run_mean, run_var, mean, rstd, scale, shift);
+  bn_finalize_kernel<<<nblk(C, 32), 256, 0, st>>>(work, nparts, M, C, gamma, beta, eps, momentum, run_mean, run_var, mean, rstd, scale, shift);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -1399,7 +1448,7 @@ int bn_bwd_run(const float* dOut, const float* raw, const float* scale, const fl
   bn_bwd_reduce_kernel<<<nparts, 256, 0, st>>>(p, work);
   int rc = check_launch("bn_bwd_reduce_kernel");
   if (rc) return rc;
-  bn_bwd_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(work, nparts, M, C, dgamma, dbeta, k1, k2);
+  bn_bwd_finalize_kernel<<<nblk(C, 32), 256, 0, st>>>(work, nparts, M, C, dgamma, dbeta, k1, k2);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   bn_bwd_apply_kernel<<<nblk(M * (C / 4), 256), 256, 0, st>>>(p, k1, k2, draw);
@@ -1436,14 +1485,14 @@ int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, fl
   int rc = check_launch("dw_wgrad_kernel");
   if (rc) return rc;
   float* tot = work + nparts * 10 * C;
-  partial_sum_kernel<<<nblk(10LL * C, 256), 256, 0, st>>>(work, (int)nparts, 10LL * C, 0.f, tot);
+  partial_sum_kernel<<<nblk(10LL * C, 32), 256, 0, st>>>(work, (int)nparts, 10LL * C, 0.f, tot);
   rc = check_launch("partial_sum_kernel");
   if (rc) return rc;
   // dw9 [9][C] += tot[0..9), dbias[C] += tot[9]
-  partial_sum_kernel<<<nblk(9LL * C, 256), 256, 0, st>>>(tot, 1, 9LL * C, 1.f, dw9);
+  partial_sum_kernel<<<nblk(9LL * C, 32), 256, 0, st>>>(tot, 1, 9LL * C, 1.f, dw9);
   rc = check_launch("partial_sum_kernel");
   if (rc) return rc;
-  partial_sum_kernel<<<nblk(C, 256), 256, 0, st>>>(tot + 9LL * C, 1, C, 1.f, dbias);
+  partial_sum_kernel<<<nblk(C, 32), 256, 0, st>>>(tot + 9LL * C, 1, C, 1.f, dbias);
   return check_launch("partial_sum_kernel");
 }
 

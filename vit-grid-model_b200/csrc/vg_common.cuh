@@ -40,6 +40,15 @@ struct PGeom {
     h = r - 1; w = col - 1;
     return (col >= 1) && (r >= 1) && (n < N) && (qq >= 0);
   }
+  // the same for 0 <= qq < 2^31 (32-bit divisions: the 64-bit ones are ~400-cycle software routines)
+  __host__ __device__ bool decode32(unsigned qq, int& n, int& h, int& w) const {
+    const unsigned row = qq / (unsigned)P;
+    const int col = (int)(qq - row * (unsigned)P);
+    n = (int)(row / (unsigned)R);
+    const int r = (int)(row - (unsigned)n * (unsigned)R);
+    h = r - 1; w = col - 1;
+    return (col >= 1) && (r >= 1) && (n < N);
+  }
 };
 inline PGeom make_pgeom(int N, int HP, int WP) { PGeom g; g.HP = HP; g.WP = WP; g.P = WP + 1; g.R = HP + 1; g.N = N; return g; }
 
