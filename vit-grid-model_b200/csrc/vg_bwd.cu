@@ -32,16 +32,33 @@ struct ConvLnBwdParams {
   PGeom pg;
 };
 
-// Half a warp per pixel (lane = 8 channels), two pixels per half-warp in flight: the kernel is a stream of 1 KB rows with two
-// 16-lane reductions each, and with one row per warp-iteration the loads of a row waited out the full DRAM latency behind the
-// shuffles of the previous one (3.1 TB/s); four rows per warp-iteration are issued before the first is used.
+// Half a warp per pixel (lane = 8 channels).  The kernel is a stream of ~1 KB rows with two 16-lane reductions each; what bounds it
+// is how many bytes a warp keeps in flight.  Every warp owns a three-stage ring in shared memory; one lane fills a stage with
+// the rows of four consecutive pixels (dY 2 KB + xhat 1 KB + mask + rstd: four bulk copies, cp.async.bulk -> mbarrier) two
+// iterations ahead of the arithmetic, so ~6 KB per warp are always on their way from HBM without costing registers
+// (loads issued from registers one iteration at a time reached 3.4 TB/s).
+namespace lnb {
+constexpr int C = 128, PPW = 64, G = 4, NST = 3;
+template <typename T> __host__ __device__ constexpr int stage_bytes() { return ((G * C * 4 + G * C * (int)sizeof(T) + G * 16 + G * 4) + 127) / 128 * 128; }
+}  // namespace lnb
+
+__device__ __forceinline__ void bulk_g2s_b(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <typename T, typename TO>
-__global__ void __launch_bounds__(256, 3) conv_ln_bwd_kernel(const ConvLnBwdParams p) {
-  constexpr int C = 128, PPW = 64, U = 2;
+__global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams p) {
+  using namespace lnb;
+  constexpr int XB = C * (int)sizeof(T), SB = stage_bytes<T>();
+  extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ float sacc[3][C];
+  __shared__ uint64_t bars[8][NST];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, sub = lane >> 4, c0 = hl * 8;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ring_raw) + 127) & ~uintptr_t(127)) + (size_t)warp * NST * SB;
   const long long q_block = (long long)blockIdx.x * (8 * PPW);
   for (int i = threadIdx.x; i < 3 * C; i += 256) (&sacc[0][0])[i] = 0.f;
+  if (lane == 0) { for (int s = 0; s < NST; ++s) mbar_init(&bars[warp][s], 1); fence_mbar_init(); }
   int nf0, hh, ww;
   p.pg.decode(q_block, nf0, hh, ww);
   if (nf0 >= p.pg.N) nf0 = p.pg.N - 1;
@@ -63,49 +80,74 @@ __global__ void __launch_bounds__(256, 3) conv_ln_bwd_kernel(const ConvLnBwdPara
   const long long q0 = q_block + warp * PPW;
   const long long npix = p.pg.pixels();
   const bool small = npix < (1ll << 31);
-  for (int k = 0; k < PPW; k += 2 * U) {
-    long long q[U]; int n[U], h[U], w[U]; bool valid[U], inr[U];
-    float dy[U][8], x[U][8], rstd[U]; unsigned bits[U];
+  auto issue = [&](int it) {                               // lane 0: the rows of pixels q0 + it*G .. +G-1 -> stage it % NST
+    const long long q = q0 + (long long)it * G;
+    if (it >= PPW / G || q >= npix) return;
+    const uint32_t rows = (uint32_t)(npix - q < G ? npix - q : G);
+    uint8_t* st = ring + (it % NST) * SB;
+    uint64_t* bar = &bars[warp][it % NST];
+    mbar_arrive_expect_tx(bar, rows * (C * 4 + XB + 16 + 4));
+    bulk_g2s_b(st, p.dY + q * C, rows * C * 4, bar);
+    bulk_g2s_b(st + G * C * 4, xh + q * C, rows * XB, bar);
+    bulk_g2s_b(st + G * C * 4 + G * XB, p.mask + q * 4, rows * 16, bar);
+    bulk_g2s_b(st + G * C * 4 + G * XB + G * 16, p.rstd + q, rows * 4, bar);
+  };
+  // (rows * 4 bytes of rstd are a multiple of 16 only for rows == 4: a shorter tail is read from global memory below)
+  if (lane == 0) { issue(0); issue(1); }
+  for (int it = 0; it < PPW / G; ++it) {
+    const long long qb = q0 + (long long)it * G;
+    if (qb >= npix) break;
+    __syncwarp();                                          // every lane is done with the stage that iteration it+2 refills
+    if (lane == 0) issue(it + 2);
+    const bool full = npix - qb >= G;
+    uint8_t* st = ring + (it % NST) * SB;
+    if (full) mbar_wait(&bars[warp][it % NST], (uint32_t)((it / NST) & 1));
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      q[u] = q0 + k + 2 * u + sub;
-      inr[u] = q[u] < npix;
-      valid[u] = inr[u] && (small ? p.pg.decode32((unsigned)q[u], n[u], h[u], w[u]) : p.pg.decode(q[u], n[u], h[u], w[u]));
+    for (int u = 0; u < G / 2; ++u) {
+      const int pi = 2 * u + sub;                          // pixel of this half-warp inside the group of four
+      const long long q = qb + pi;
+      const bool inr = q < npix;
+      int n = 0, h = 0, w = 0;
+      const bool valid = inr && (small ? p.pg.decode32((unsigned)q, n, h, w) : p.pg.decode(q, n, h, w));
+      float dy[8], x[8], rstd = 0.f; unsigned bits = 0u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dy[u][i] = x[u][i] = 0.f;
-      rstd[u] = 0.f; bits[u] = 0u;
-      if (valid[u]) {
-        ld8(p.dY + q[u] * C + c0, dy[u]);
-        ld8(xh + q[u] * C + c0, x[u]);
-        bits[u] = p.mask[q[u] * 4 + (hl >> 2)] >> ((hl & 3) * 8);
-        rstd[u] = p.rstd[q[u]];
+      for (int i = 0; i < 8; ++i) dy[i] = x[i] = 0.f;
+      if (valid) {
+        if (full) {
+          ld8(reinterpret_cast<const float*>(st) + pi * C + c0, dy);
+          ld8(reinterpret_cast<const T*>(st + G * C * 4) + pi * C + c0, x);
+          bits = reinterpret_cast<const unsigned*>(st + G * C * 4 + G * XB)[pi * 4 + (hl >> 2)] >> ((hl & 3) * 8);
+          rstd = reinterpret_cast<const float*>(st + G * C * 4 + G * XB + G * 16)[pi];
+        } else {                                           // the last, partial group of the tensor: straight from global memory
+          ld8(p.dY + q * C + c0, dy);
+          ld8(xh + q * C + c0, x);
+          bits = p.mask[q * 4 + (hl >> 2)] >> ((hl & 3) * 8);
+          rstd = p.rstd[q];
+        }
       }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (valid[u] && n[u] != n_cur) {
+      if (valid && n != n_cur) {
         flush();
-        n_cur = n[u];
+        n_cur = n;
 #pragma unroll
         for (int i = 0; i < 8; ++i) gs[i] = p.ln_g[c0 + i] * (p.film ? p.film[(long long)n_cur * 2 * C + c0 + i] + 1.0f : 1.0f);
       }
       float dx[8], o[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float dz = ((bits[u] >> i) & 1u) ? dy[u][i] : 0.f;
-        dx[i] = dz * gs[i]; s1 += dx[i]; s2 = fmaf(dx[i], x[u][i], s2);
-        A[i] = fmaf(dz, x[u][i], A[i]); B[i] += dz;
+        const float dz = ((bits >> i) & 1u) ? dy[i] : 0.f;
+        dx[i] = dz * gs[i]; s1 += dx[i]; s2 = fmaf(dx[i], x[i], s2);
+        A[i] = fmaf(dz, x[i], A[i]); B[i] += dz;
       }
 #pragma unroll
       for (int o2 = 8; o2 >= 1; o2 >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o2); s2 += __shfl_xor_sync(0xffffffffu, s2, o2); }
       s1 *= (1.0f / C);
-      s2 = rstd[u] >= p.rstd_clamp ? 0.f : s2 * (1.0f / C);        // var.clamp(min=eps): no gradient through a clamped variance
+      s2 = rstd >= p.rstd_clamp ? 0.f : s2 * (1.0f / C);           // var.clamp(min=eps): no gradient through a clamped variance
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { o[i] = valid[u] ? rstd[u] * (dx[i] - s1 - x[u][i] * s2) : 0.f; D[i] += o[i]; }
-      if (p.border && valid[u]) {
-        const bool r0 = h[u] == 0, rl = h[u] == p.pg.HP - 1, k0 = w[u] == 0, kl = w[u] == p.pg.WP - 1;
+      for (int i = 0; i < 8; ++i) { o[i] = valid ? rstd * (dx[i] - s1 - x[i] * s2) : 0.f; D[i] += o[i]; }
+      if (p.border && valid) {
+        const bool r0 = h == 0, rl = h == p.pg.HP - 1, k0 = w == 0, kl = w == p.pg.WP - 1;
         if (r0 | rl | k0 | kl) {
-          float* bb = p.border + (long long)n[u] * 8 * C + c0;
+          float* bb = p.border + (long long)n * 8 * C + c0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (r0) atomicAdd(bb + 0 * C + i, o[i]);
@@ -119,7 +161,7 @@ __global__ void __launch_bounds__(256, 3) conv_ln_bwd_kernel(const ConvLnBwdPara
           }
         }
       }
-      if (inr[u]) st8(dc + q[u] * C + c0, o);
+      if (inr) st8(dc + q * C + c0, o);
     }
   }
   flush();
@@ -494,9 +536,21 @@ int conv_ln_bwd_run(int xdtype, int odtype, const float* dY, const void* xhat, c
   p.sumA = sumA; p.sumB = sumB; p.sumD = sumD; p.border = border; p.rstd_clamp = 1.0f / sqrtf(eps) * (1.0f - 1e-6f);
   p.pg = make_pgeom(N, HP, WP);
   const unsigned g = nblk(p.pg.pixels(), 512);
-  if (xdtype == 0 && odtype == 0) conv_ln_bwd_kernel<bf16, bf16><<<g, 256, 0, st>>>(p);
-  else if (xdtype == 0 && odtype == 1) conv_ln_bwd_kernel<bf16, float><<<g, 256, 0, st>>>(p);
-  else if (xdtype == 1 && odtype == 1) conv_ln_bwd_kernel<float, float><<<g, 256, 0, st>>>(p);
+  // the bulk copies need 16-byte aligned rows (torch allocations are; views at odd offsets are not)
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(rstd)) & 15)
+    return set_error("conv_ln_bwd: dY / xhat / mask / rstd must be 16-byte aligned");
+  const size_t sm16 = 8 * lnb::NST * lnb::stage_bytes<bf16>() + 128, sm32 = 8 * lnb::NST * lnb::stage_bytes<float>() + 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_ln_bwd_kernel<bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_bwd_kernel<bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_bwd_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32);
+    if (e != cudaSuccess) return set_error("conv_ln_bwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  if (xdtype == 0 && odtype == 0) conv_ln_bwd_kernel<bf16, bf16><<<g, 256, sm16, st>>>(p);
+  else if (xdtype == 0 && odtype == 1) conv_ln_bwd_kernel<bf16, float><<<g, 256, sm16, st>>>(p);
+  else if (xdtype == 1 && odtype == 1) conv_ln_bwd_kernel<float, float><<<g, 256, sm32, st>>>(p);
   else return set_error("conv_ln_bwd: unsupported dtype combination (%d, %d)", xdtype, odtype);
   return check_launch("conv_ln_bwd_kernel");
 }
