@@ -84,6 +84,7 @@ __device__ __forceinline__ float4 lds128f(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ float2 lds64f(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ float lds32f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts64f(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
@@ -247,7 +248,8 @@ attn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid
     const float rs = sqrtf((float)DH);
     float* sbx = reinterpret_cast<float*>(smem + BX_OFF);
     const uint32_t a_gam = sb + GAM_OFF, a_inv = sb + INV_OFF, a_bx = sb + BX_OFF + (uint32_t)(i * BX_LD + cq * 16) * 4u;
-    const uint32_t a_max = sb + MAX_OFF + (uint32_t)t * 16u, a_sum = sb + SUM_OFF + (uint32_t)t * 32u;
+    // exchange arrays are [column quarter][row]: a warp's stores and loads touch consecutive words (the [row][quarter] layout cost 8-way conflicts)
+    const uint32_t a_max = sb + MAX_OFF + (uint32_t)t * 4u, a_sum = sb + SUM_OFF + (uint32_t)t * 8u;
     constexpr float LOG2E = 1.4426950408889634f;
     float* gpart = gred;                                     // [16][32]
     float* wpart = gred + 512;                               // [16]
@@ -270,44 +272,47 @@ attn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid
       mbar_wait_tag(raw_full + st, (Tn >> 1) & 1, 404);
       if (p.dbg && blockIdx.x == 0 && lane == 0 && Tn >= 1 && Tn <= 64) p.dbg[((Tn - 1) * 16 + warp) * 8 + 6] = clock64();
       const bool valid = i < S && (2 * tt_n + half) < nwin;
-      // TMA SWIZZLE_64B rows: 16-byte chunk c of row i sits at chunk c ^ ((i >> 1) & 3) (a warp's row reads are conflict free)
-      // raw matrix staged by this warp: the two normalising roles (q, k) go to the warps with the light epilogues (dV, att)
-      const int mi = cq == 0 ? 0 : (cq == 3 ? 1 : cq + 1);   // cq 0 -> q, 1 -> v, 2 -> dO, 3 -> k
-      const uint32_t src = sb + RAW_OFF + st * RAW_STAGE + half * 16384 + mi * 4096 + i * 64;
-      const int sx = (i >> 1) & 3;
-      uint4 w[4];
+      const int sx = (i >> 1) & 3;                           // TMA SWIZZLE_64B rows: 16-byte chunk c of row i sits at chunk c ^ ((i >> 1) & 3)
+      auto stage_matrix = [&](int mi) {                      // mi: 0 q, 1 k, 2 v, 3 dO
+        const uint32_t src = sb + RAW_OFF + st * RAW_STAGE + half * 16384 + mi * 4096 + i * 64;
+        uint4 w[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) w[c] = valid ? lds128u(src + ((c ^ sx) << 4)) : make_uint4(0u, 0u, 0u, 0u);
-      if (mi < 2) {                                          // q or k: unit vector (maxvit.py:30); k also takes the whole scale (maxvit.py:197)
-        float ss = 0.f;                                      // (the row stays packed: 16 registers instead of 32 floats)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float2 a = unbf(w[c].x), b = unbf(w[c].y), cc = unbf(w[c].z), d = unbf(w[c].w);
-          ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss); ss = fmaf(b.x, b.x, ss); ss = fmaf(b.y, b.y, ss);
-          ss = fmaf(cc.x, cc.x, ss); ss = fmaf(cc.y, cc.y, ss); ss = fmaf(d.x, d.x, ss); ss = fmaf(d.y, d.y, ss);
-        }
-        const float inv = rsqrtf(fmaxf(ss, 1e-24f));           // 1 / max(|x|, 1e-12)  (F.normalize eps, maxvit.py:30)
-        if (mi == 0) {
+        for (int c = 0; c < 4; ++c) w[c] = valid ? lds128u(src + ((c ^ sx) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+        if (mi < 2) {                                        // q or k: unit vector (maxvit.py:30); k also takes the whole scale (maxvit.py:197)
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // (the row stays packed: 16 registers instead of 32 floats)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float2 a = unbf(w[c].x), b = unbf(w[c].y), cc = unbf(w[c].z), d = unbf(w[c].w);
-            w[c].x = pkbf(a.x * inv, a.y * inv); w[c].y = pkbf(b.x * inv, b.y * inv);
-            w[c].z = pkbf(cc.x * inv, cc.y * inv); w[c].w = pkbf(d.x * inv, d.y * inv);
+            s0 = fmaf(a.x, a.x, s0); s1 = fmaf(a.y, a.y, s1); s2 = fmaf(b.x, b.x, s2); s3 = fmaf(b.y, b.y, s3);
+            s0 = fmaf(cc.x, cc.x, s0); s1 = fmaf(cc.y, cc.y, s1); s2 = fmaf(d.x, d.x, s2); s3 = fmaf(d.y, d.y, s3);
           }
-        } else {
+          const float inv = rsqrtf(fmaxf((s0 + s1) + (s2 + s3), 1e-24f));     // 1 / max(|x|, 1e-12)  (F.normalize eps, maxvit.py:30)
+          if (mi == 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 g0 = lds128f(a_gam + 32 * c), g1 = lds128f(a_gam + 32 * c + 16);
-            const float2 a = unbf(w[c].x), b = unbf(w[c].y), cc = unbf(w[c].z), d = unbf(w[c].w);
-            w[c].x = pkbf(a.x * inv * g0.x, a.y * inv * g0.y); w[c].y = pkbf(b.x * inv * g0.z, b.y * inv * g0.w);
-            w[c].z = pkbf(cc.x * inv * g1.x, cc.y * inv * g1.y); w[c].w = pkbf(d.x * inv * g1.z, d.y * inv * g1.w);
+            for (int c = 0; c < 4; ++c) {
+              const float2 a = unbf(w[c].x), b = unbf(w[c].y), cc = unbf(w[c].z), d = unbf(w[c].w);
+              w[c].x = pkbf(a.x * inv, a.y * inv); w[c].y = pkbf(b.x * inv, b.y * inv);
+              w[c].z = pkbf(cc.x * inv, cc.y * inv); w[c].w = pkbf(d.x * inv, d.y * inv);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 g0 = lds128f(a_gam + 32 * c), g1 = lds128f(a_gam + 32 * c + 16);
+              const float2 a = unbf(w[c].x), b = unbf(w[c].y), cc = unbf(w[c].z), d = unbf(w[c].w);
+              w[c].x = pkbf(a.x * inv * g0.x, a.y * inv * g0.y); w[c].y = pkbf(b.x * inv * g0.z, b.y * inv * g0.w);
+              w[c].z = pkbf(cc.x * inv * g1.x, cc.y * inv * g1.y); w[c].w = pkbf(d.x * inv * g1.z, d.y * inv * g1.w);
+            }
           }
+          sts32f(a_inv + (buf * 256 + mi * 128 + t) * 4, inv);
         }
-        sts32f(a_inv + (buf * 256 + mi * 128 + t) * 4, inv);
-      }
-      const uint32_t dst = sb + ((mi < 2) ? QK_OFF : VD_OFF) + buf * 16384;
+        const uint32_t dst = sb + ((mi < 2) ? QK_OFF : VD_OFF) + buf * 16384;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sts128u(dst + sw128(t, (mi & 1) * 4 + c), w[c]);
+        for (int c = 0; c < 4; ++c) sts128u(dst + sw128(t, (mi & 1) * 4 + c), w[c]);
+      };
+      // roles by epilogue weight: the dK^ warps (cq 2, the longest epilogue) stage nothing, the att warps (cq 3, the shortest) stage k and dO
+      if (cq == 0) stage_matrix(0);
+      else if (cq == 1) stage_matrix(2);
+      else if (cq == 3) { stage_matrix(1); stage_matrix(3); }
       if (p.dbg && blockIdx.x == 0 && lane == 0 && Tn >= 1 && Tn <= 64) p.dbg[((Tn - 1) * 16 + warp) * 8 + 7] = clock64();
       fence_proxy_async_smem();
       tc_fence_before();
@@ -366,11 +371,10 @@ attn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid
           }
 #pragma unroll
           for (int e = 0; e < 16; ++e) m = fmaxf(m, s[e]);
-          sts32f(a_max + cq * 4, m);
+          sts32f(a_max + cq * 512, m);
           bar_sync(1 + lg, 128);
           {
-            const float4 mm = lds128f(a_max);
-            m = fmaxf(fmaxf(mm.x, mm.y), fmaxf(mm.z, mm.w));
+            m = fmaxf(fmaxf(lds32f(a_max), lds32f(a_max + 512)), fmaxf(lds32f(a_max + 1024), lds32f(a_max + 1536)));
           }
           float se = 0.f, sed = 0.f;
           // dropout on the probabilities (maxvit.py:146): one hash = the mask bytes of 4 keys; a per-byte compare turns them
@@ -390,11 +394,11 @@ attn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid
             s[e] = ex;
             se += ex; sed = fmaf(ex, dp[e], sed);
           }
-          sts64f(a_sum + cq * 8, se, sed);
+          sts64f(a_sum + cq * 1024, se, sed);
           bar_sync(1 + lg, 128);
           {
-            const float4 a = lds128f(a_sum), b = lds128f(a_sum + 16);
-            se = (a.x + a.z) + (b.x + b.z); sed = (a.y + a.w) + (b.y + b.w);
+            const float2 e0 = lds64f(a_sum), e1 = lds64f(a_sum + 1024), e2 = lds64f(a_sum + 2048), e3 = lds64f(a_sum + 3072);
+            se = (e0.x + e1.x) + (e2.x + e3.x); sed = (e0.y + e1.y) + (e2.y + e3.y);
           }
           const float inv = row_ok ? __frcp_rn(se) : 0.f;
           const float delta = sed * inv;
