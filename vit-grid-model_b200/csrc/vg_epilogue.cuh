@@ -257,7 +257,19 @@ struct EpiCtx {
   uint32_t res_g0 = 0;             // running chunk index of this tile's chunk 0
   long long res_row0 = 0;          // row of lane 0 in this tile
   long long res_next_row0 = -1;    // row of lane 0 in the CTA's next tile, -1 = none
+  // fp32 copy of the output (out2) through the SAME buffers: after the residual is added, the finished [32 rows][32 columns]
+  // block goes back into the chunk's buffer and leaves as one TMA tensor store; the refill of the buffer waits for the store
+  // to have read it.  16 of a row's 24 epilogue store instructions disappear from the LSU, which bounded these launches.
+  const CUtensorMap* out2_map = nullptr;
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldp4(const EpiCtx& cx, const float* p) {
   if (cx.params_smem) {
@@ -315,6 +327,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
   float* o2 = ep.out2 ? ep.out2 + row * ep.ldo : nullptr;
   const T* r = (ep.res && !ep.res_f32 && valid) ? reinterpret_cast<const T*>(ep.res) + row * ep.ldres : nullptr;
   const bool rtma = cx.res_map != nullptr;
+  const bool o2tma = rtma && cx.out2_map != nullptr && ep.out2 != nullptr;      // warp-uniform
   const int lane_ = threadIdx.x & 31;
   const float* rf = (ep.res && ep.res_f32 && valid && !rtma) ? reinterpret_cast<const float*>(ep.res) + row * ep.ldres : nullptr;
   float head = 0.f;
@@ -347,7 +360,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
         rr[4 * j] = q4.x; rr[4 * j + 1] = q4.y; rr[4 * j + 2] = q4.z; rr[4 * j + 3] = q4.w;
       }
       __syncwarp();
-      if (lane_ == 0) {                                      // refill the buffer with chunk g + 2
+      if (lane_ == 0 && !o2tma) {                            // refill the buffer with chunk g + 2
         const long long r0 = ch < 2 ? cx.res_row0 : cx.res_next_row0;
         if (r0 >= 0) {
           fence_proxy_async_smem();
@@ -356,7 +369,7 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
         }
       }
     }
-    if (!in_buf) continue;
+    if (in_buf) {
     unsigned mbits = 0u;
     float xh[TRAIN ? 32 : 1];
     if (valid) {
@@ -413,9 +426,34 @@ __device__ __forceinline__ void epi_conv_ln(const EpiParams& ep, const EpiCtx& c
 #pragma unroll
       for (int j = 0; j < 32; j += 16) st16_256(o + ch * 32 + j, v + j);
     }
-    if (o2) {
+    if (o2 && !o2tma) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) st8_256(o2 + ch * 32 + j, v + j);
+    }
+    }                                                        // in_buf
+    if (o2tma) {
+      const uint32_t g = cx.res_g0 + ch;
+      uint8_t* buf = cx.res_buf + (g & 1) * 4096;
+      if (in_buf) {
+        uint8_t* p = buf + lane_ * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(p + ((j ^ (lane_ & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_ == 0) {
+        tma_store_2d(cx.out2_map, buf, ch * 32, (int)cx.res_row0);      // rows beyond the tensor are clipped by the map
+        bulk_commit_group();
+        const long long r0 = ch < 2 ? cx.res_row0 : cx.res_next_row0;
+        bulk_wait_read_all();                                           // the store has read the buffer: it may be refilled
+        if (r0 >= 0) {
+          uint64_t* bar = cx.res_bar + (g & 1);
+          mbar_arrive_expect_tx(bar, 4096);
+          tma_load_2d(buf, cx.res_map, bar, ((ch + 2) & 3) * 32, (int)r0);
+        }
+      }
+      __syncwarp();
     }
   }
   if (ep.head_w && valid) {

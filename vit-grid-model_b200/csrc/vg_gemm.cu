@@ -234,6 +234,7 @@ struct HaloShape {
   int use_base_offset;
   int res_tma;          // the fp32 residual arrives through mapR (else: per-thread global loads)
   int flip;             // data gradient: tap t of the weights is applied with the input shift of tap 8 - t (the negated shift)
+  int out2_tma;         // the fp32 copy of the output leaves through mapO (TMA tensor stores from the residual buffers)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int row) {
@@ -246,7 +247,7 @@ __device__ __forceinline__ uint64_t umma_desc_k128_shift(uint32_t tile_addr, int
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapR, const HaloShape hs, const EpiParams ep) {
+                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const HaloShape hs, const EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + 2 * HALO_A_BYTES;
@@ -349,6 +350,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     cx.bias = sparam; cx.ln_g = sparam + 128; cx.ln_b = sparam + 256; cx.gb = nullptr; cx.n_first = 0; cx.params_smem = true;
     if (hs.res_tma) {
       cx.res_map = &mapR; cx.res_buf = sres + (warp - 4) * 8192; cx.res_bar = res_full + (warp - 4) * 2;
+      if (hs.out2_tma) cx.out2_map = &mapO;
       if (lane == 0 && (int)blockIdx.x < hs.num_tiles) {     // chunks 0 and 1 of the first tile
         const int r0 = (int)((long long)blockIdx.x * BM + e * 128 + lg * 32);
         for (int c = 0; c < 2; ++c) {
@@ -377,6 +379,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
     }
+    if (hs.out2_tma && lane == 0) bulk_wait_all();           // outstanding tensor stores have been performed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -761,6 +764,16 @@ int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const Ep
   HaloShape hs;
   hs.M = M; hs.num_tiles = (int)((hs.M + BM - 1) / BM); hs.P = P; hs.HR = HR; hs.use_base_offset = g_halo_base_offset; hs.res_tma = res_tma ? 1 : 0;
   hs.flip = flip;
+  // fp32 copy through TMA stores (needs the residual buffers: residual launches only); VG_CONV_OUT2_TMA=0 restores the per-thread stores
+  const char* o2e = getenv("VG_CONV_OUT2_TMA");             // read per call so one process can compare the two
+  const int o2_mode = (o2e && o2e[0] == '0') ? 0 : 1;
+  CUtensorMap mo = ma;
+  hs.out2_tma = 0;
+  if (o2_mode && res_tma && ep.out2 && ep.ldo == 128 && (reinterpret_cast<uintptr_t>(ep.out2) & 15) == 0) {
+    int rc2 = make_map_2d(&mo, true, ep.out2, 128, M, 32);
+    if (rc2) return rc2;
+    hs.out2_tma = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
@@ -800,9 +813,9 @@ int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const Ep
     if (le != cudaSuccess) return set_error("conv_halo2 launch: %s", cudaGetErrorString(le));
     return check_launch("conv_halo2_kernel");
   }
-  if (mode_k == 2) conv_halo_kernel<2><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
-  else if (train) conv_halo_kernel<1><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
-  else conv_halo_kernel<0><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, hs, ep);
+  if (mode_k == 2) conv_halo_kernel<2><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, mo, hs, ep);
+  else if (train) conv_halo_kernel<1><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, mo, hs, ep);
+  else conv_halo_kernel<0><<<grid, TC_THREADS, HALO_SMEM_BYTES, st>>>(ma, mb, mr, mo, hs, ep);
   return check_launch("conv_halo_kernel");
 }
 
