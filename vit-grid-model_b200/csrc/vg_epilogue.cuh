@@ -138,10 +138,10 @@ __device__ __forceinline__ bool epi_store_rows16_ok(const EpiParams& ep) {
          (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0;
 }
 template <class Loader>
-__device__ __forceinline__ void epi_store_rows16(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld) {
+__device__ __forceinline__ void epi_store_rows16(const EpiParams& ep, long long row, bool ok, int n0, Loader& ld, int ch_begin = 0, int ch_end = 4) {
   float v[32];
 #pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = n0 + ch * 32;
     ld.load(ch, v);
     if (c0 >= ep.n_total || !ok) continue;
@@ -158,12 +158,12 @@ __device__ __forceinline__ void epi_store_rows16(const EpiParams& ep, long long 
 // this warp's 32 (rows are consecutive), stg = this warp's [32][36] float tile.
 template <typename T, class Loader>
 __device__ __forceinline__ void epi_store_coalesced(const EpiParams& ep, long long row0, int nvalid, int n0, Loader& ld,
-                                                    float* stg, int lane) {
+                                                    float* stg, int lane, int ch_begin = 0, int ch_end = 4) {
   constexpr int LDS_ = 36;                                 // row stride of the tile: 16-byte aligned, conflict-free for 128-bit access
   float v[32];
   const int rr = lane >> 3, cq = (lane & 7) * 4;
 #pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = n0 + ch * 32;
     // this lane's four output columns are the same for every row of the transposed phase: fetch their parameters once
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
