@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
   };
   const long long q0 = q_block + warp * PPW;
   const long long npix = p.pg.pixels();
-  const bool small = npix < (1ll << 31);
   auto issue = [&](int it) {                               // lane 0: the rows of pixels q0 + it*G .. +G-1 -> stage it % NST
     const long long q = q0 + (long long)it * G;
     if (it >= PPW / G || q >= npix) return;
@@ -94,6 +93,18 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
   };
   // (rows * 4 bytes of rstd are a multiple of 16 only for rows == 4: a shorter tail is read from global memory below)
   if (lane == 0) { issue(0); issue(1); }
+  // This half-warp visits pixels q0 + sub, +2, +4, ...: its PG coordinates advance incrementally (the two 32-bit divisions of a
+  // decode per pixel were a third of the kernel's instructions, which ncu showed to be what bounds it: 61 % issue utilisation)
+  long long q = q0 + sub;
+  int col, rr_, n;
+  {
+    const long long row = q / p.pg.P;
+    col = (int)(q - row * p.pg.P);
+    n = (int)(row / p.pg.R);
+    rr_ = (int)(row - (long long)n * p.pg.R);
+  }
+  TO* dcp = dc + q * C + c0;
+  const int Pp = p.pg.P, Rr = p.pg.R, Nn = p.pg.N, HPm = p.pg.HP - 1, WPm = p.pg.WP - 1;
   for (int it = 0; it < PPW / G; ++it) {
     const long long qb = q0 + (long long)it * G;
     if (qb >= npix) break;
@@ -105,10 +116,9 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
 #pragma unroll
     for (int u = 0; u < G / 2; ++u) {
       const int pi = 2 * u + sub;                          // pixel of this half-warp inside the group of four
-      const long long q = qb + pi;
       const bool inr = q < npix;
-      int n = 0, h = 0, w = 0;
-      const bool valid = inr && (small ? p.pg.decode32((unsigned)q, n, h, w) : p.pg.decode(q, n, h, w));
+      const bool valid = inr && col >= 1 && rr_ >= 1 && n < Nn;
+      const int h = rr_ - 1, w = col - 1;
       float dy[8], x[8], rstd = 0.f; unsigned bits = 0u;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dy[i] = x[i] = 0.f;
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
       float dx[8], o[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float dz = ((bits >> i) & 1u) ? dy[i] : 0.f;
+        const float dz = (bits & (1u << i)) ? dy[i] : 0.f;
         dx[i] = dz * gs[i]; s1 += dx[i]; s2 = fmaf(dx[i], x[i], s2);
         A[i] = fmaf(dz, x[i], A[i]); B[i] += dz;
       }
@@ -142,10 +152,11 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
       for (int o2 = 8; o2 >= 1; o2 >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o2); s2 += __shfl_xor_sync(0xffffffffu, s2, o2); }
       s1 *= (1.0f / C);
       s2 = rstd >= p.rstd_clamp ? 0.f : s2 * (1.0f / C);           // var.clamp(min=eps): no gradient through a clamped variance
+      const float rv = valid ? rstd : 0.f;                         // pad positions: zeros
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { o[i] = valid ? rstd * (dx[i] - s1 - x[i] * s2) : 0.f; D[i] += o[i]; }
+      for (int i = 0; i < 8; ++i) { o[i] = rv * (dx[i] - s1 - x[i] * s2); D[i] += o[i]; }
       if (p.border && valid) {
-        const bool r0 = h == 0, rl = h == p.pg.HP - 1, k0 = w == 0, kl = w == p.pg.WP - 1;
+        const bool r0 = h == 0, rl = h == HPm, k0 = w == 0, kl = w == WPm;
         if (r0 | rl | k0 | kl) {
           float* bb = p.border + (long long)n * 8 * C + c0;
 #pragma unroll
@@ -161,7 +172,10 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
           }
         }
       }
-      if (inr) st8(dc + q * C + c0, o);
+      if (inr) st8(dcp, o);
+      // next pixel of this half-warp: q + 2
+      q += 2; dcp += 2 * C; col += 2;
+      if (col >= Pp) { col -= Pp; if (++rr_ == Rr) { rr_ = 0; ++n; } }
     }
   }
   flush();
