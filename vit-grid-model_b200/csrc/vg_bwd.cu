@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
   const long long npix = p.pg.pixels();
   auto issue = [&](int it) {                               // lane 0: the rows of pixels q0 + it*G .. +G-1 -> stage it % NST
     const long long q = q0 + (long long)it * G;
-    if (it >= PPW / G || q >= npix) return;
-    const uint32_t rows = (uint32_t)(npix - q < G ? npix - q : G);
+    if (it >= PPW / G || npix - q < G) return;             // (the last, partial group of the tensor is read straight from global memory:
+    const uint32_t rows = G;                               //  bulk copies move multiples of 16 bytes, 4 bytes of rstd per pixel)
     uint8_t* st = ring + (it % NST) * SB;
     uint64_t* bar = &bars[warp][it % NST];
     mbar_arrive_expect_tx(bar, rows * (C * 4 + XB + 16 + 4));
@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(256) conv_ln_bwd_kernel(const ConvLnBwdParams 
     bulk_g2s_b(st + G * C * 4 + G * XB, p.mask + q * 4, rows * 16, bar);
     bulk_g2s_b(st + G * C * 4 + G * XB + G * 16, p.rstd + q, rows * 4, bar);
   };
-  // (rows * 4 bytes of rstd are a multiple of 16 only for rows == 4: a shorter tail is read from global memory below)
   if (lane == 0) { issue(0); issue(1); }
   // This half-warp visits pixels q0 + sub, +2, +4, ...: its PG coordinates advance incrementally (the two 32-bit divisions of a
   // decode per pixel were a third of the kernel's instructions, which ncu showed to be what bounds it: 61 % issue utilisation)
