@@ -175,8 +175,11 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   pp = f2_fma(pp, t, make_float2(-0.284496736f, -0.284496736f));
   pp = f2_fma(pp, t, make_float2(0.254829592f, 0.254829592f));
   pp = f2_mul(pp, t);
-  const float2 nz2 = f2_mul(az, make_float2(-az.x, -az.y));                 // -z^2
-  const float2 e = make_float2(__expf(nz2.x), __expf(nz2.y));
+  // e^{-z^2} = 2^{x^2 (-log2(e) / 2)}: the exp2 argument straight from x on the packed pipe (no scalar scaling multiply per element)
+  const float2 ea = f2_mul(f2_mul(x, x), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(ea.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(ea.y));
   const float2 one_m = f2_fma(make_float2(-pp.x, -pp.y), e, make_float2(1.0f, 1.0f));     // erf(|z|)
   const float2 er = make_float2(copysignf(one_m.x, z.x), copysignf(one_m.y, z.y));
   const float2 hx = f2_mul(x, make_float2(0.5f, 0.5f));
