@@ -1378,16 +1378,24 @@ __global__ void __launch_bounds__(256) attn_gather_bwd_kernel(const AttnGatherBw
     for (int i = 0; i < 4; ++i) { atomicAdd(p.dfilm + (long long)n_cur * 2 * C + c0 + i, ag[i]); atomicAdd(p.dfilm + (long long)n_cur * 2 * C + C + c0 + i, ab[i]); ag[i] = ab[i] = 0.f; }
   };
   const long long r0 = ((long long)blockIdx.x * 8 + warp) * RPW;
+  // (window, token) of the warp's first row by division, then incrementally: four 64- / 32-bit divisions per row were most of the
+  // kernel's instructions
+  long long wdx0 = r0 / S;
+  int tok = (int)(r0 - wdx0 * S);
+  int n = (int)(wdx0 / nwin), wi = (int)(wdx0 - (long long)n * nwin);
+  int wx = wi / g.Y, wy = wi - wx * g.Y;                    // window coordinates (attn_token_pixel: wi = x*Y + y)
+  int ta = tok >= g.R ? (tok - g.R) / g.win : 0, tb = tok >= g.R ? (tok - g.R) - ta * g.win : 0;   // token row / column inside the window
   for (int k = 0; k < RPW; ++k) {
     const long long r = r0 + k;
     if (r >= rows) break;
-    const long long wdx = r / S;
-    const int tok = (int)(r - wdx * S);
-    const int n = (int)(wdx / nwin), wi = (int)(wdx - (long long)n * nwin);
     if (n != n_cur) { flush(); n_cur = n; }
     const float* src; long long pix = -1;
     if (tok < g.R) src = p.reg + (p.reg_per_field ? (long long)n * g.R * C : 0) + (long long)tok * C;
-    else { pix = (long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R); src = p.x + pix * C; }
+    else {
+      const int ph = g.grid_mode ? ta * g.X + wx : wx * g.win + ta, pw = g.grid_mode ? tb * g.Y + wy : wy * g.win + tb;      // == attn_token_pixel(g, wi, tok - R)
+      pix = (long long)n * g.Hl * g.Wl + (long long)ph * g.Wl + pw;
+      src = p.x + pix * C;
+    }
     const float4 xv = *reinterpret_cast<const float4*>(src + c0);
     float v[4] = {xv.x, xv.y, xv.z, xv.w};
     const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / C);
@@ -1416,6 +1424,13 @@ __global__ void __launch_bounds__(256) attn_gather_bwd_kernel(const AttnGatherBw
     } else {
       const float4 ro = *reinterpret_cast<const float4*>(p.dx_out + pix * C + c0);
       *reinterpret_cast<float4*>(p.dx_in + pix * C + c0) = make_float4(dx[0] + ro.x, dx[1] + ro.y, dx[2] + ro.z, dx[3] + ro.w);
+    }
+    // next row
+    if (tok >= g.R) { if (++tb == g.win) { tb = 0; ++ta; } }
+    if (++tok == S) {
+      tok = 0; ta = 0; tb = 0;
+      if (++wy == g.Y) { wy = 0; ++wx; }
+      if (++wi == nwin) { wi = 0; wx = 0; wy = 0; ++n; }
     }
   }
   flush();
