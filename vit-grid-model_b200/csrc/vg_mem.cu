@@ -78,30 +78,55 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p, T* __r
 // every 32-column tile, and each thread has its eight loads in flight before the transposing store.
 template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T* __restrict__ out) {
+  // (round 2: ncu showed this kernel instruction-bound -- 76 % issue utilisation, 32 instructions per element, two thirds of them
+  //  integer: a channel -> (t, c) division per thread and channel, a pixel -> (h, w) division per thread and tile, predicates and
+  //  64-bit address arithmetic around every load.  The channel offsets and the output rows of the block's 64 channels / 128 pixels
+  //  are now computed once into shared memory, and interior blocks load without predicates.)
   constexpr int PT = 4;                                            // 32-pixel tiles per block: 32 loads in flight per thread
   __shared__ float tile[PT][64][33];
+  __shared__ long long s_off[64];                                  // element offset of channel ch0 + i inside the sample, -1 = padding channel
+  __shared__ long long s_row[PT * 32];                             // output row (PG pixel index) of pixel px0 + i, -1 = outside the field
+  __shared__ int s_pm[64];
   const int HW = p.H * p.W;
   const int px0 = blockIdx.x * 32 * PT;
   const int cblocks = p.Cpad / 64;
   const int b = blockIdx.y / cblocks, ch0 = (blockIdx.y - b * cblocks) * 64;
   const int TC = p.T * p.C;
-  const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (long long)b * p.sB;
+  if (threadIdx.x < 64) {
+    const int ch = ch0 + threadIdx.x;
+    const int t = ch / p.C, c = ch - t * p.C;
+    s_off[threadIdx.x] = ch < TC ? (long long)t * p.sT + (long long)c * p.sC : -1;
+    s_pm[threadIdx.x] = (!p.prestd && ch < TC && (c == 4 || c == 10 || c == 16 || c == 22)) ? 1 : 0;       // metnet3.py:362,370
+  } else if (threadIdx.x < 64 + PT * 32) {
+    const int i = threadIdx.x - 64, px = px0 + i;
+    long long q = -1;
+    if (px < HW) { const int h = px / p.W, w = px - h * p.W; q = p.pg.q(b, h + p.pad_top, w + p.pad_left); }
+    s_row[i] = q;
+  }
+  __syncthreads();
+  const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (long long)b * p.sB + px0;
   const int pl = threadIdx.x & 31, cl0 = threadIdx.x >> 5;         // lane = pixel (coalesced 128-byte rows), warp = channel
+  const bool interior = px0 + 32 * PT <= HW;                       // block-uniform
   float v[PT][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int ch = ch0 + cl0 + 8 * k;
-    const int t = ch / p.C, c = ch - t * p.C;
-    const TIn* xc = xb + (long long)t * p.sT + (long long)c * p.sC;
-    const bool pm = !p.prestd && (c == 4 || c == 10 || c == 16 || c == 22);       // metnet3.py:362,370
+    const long long off = s_off[cl0 + 8 * k];                      // warp-uniform
+    if (off >= 0) {
+      const TIn* xc = xb + off + pl;
+      if (interior) {
 #pragma unroll
-    for (int u = 0; u < PT; ++u) {
-      const int px = px0 + u * 32 + pl;
-      v[u][k] = (ch < TC && px < HW) ? ld_in(xc + px) : 0.f;
-    }
-    if (pm && ch < TC) {
+        for (int u = 0; u < PT; ++u) v[u][k] = ld_in(xc + u * 32);
+      } else {
 #pragma unroll
-      for (int u = 0; u < PT; ++u) if (px0 + u * 32 + pl < HW) v[u][k] = (v[u][k] - p.mean) / p.stdv;
+        for (int u = 0; u < PT; ++u) v[u][k] = (px0 + u * 32 + pl < HW) ? ld_in(xc + u * 32) : 0.f;
+      }
+      if (s_pm[cl0 + 8 * k]) {
+#pragma unroll
+        for (int u = 0; u < PT; ++u) v[u][k] = (v[u][k] - p.mean) / p.stdv;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < PT; ++u) v[u][k] = 0.f;
     }
   }
 #pragma unroll
@@ -112,13 +137,12 @@ __global__ void __launch_bounds__(256) prepare_flat_kernel(const PrepParams p, T
   const int wl = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
 #pragma unroll
   for (int u = 0; u < PT; ++u) {
-    const int px = px0 + u * 32 + wl;
-    if (px < HW) {
-      const int h = px / p.W, w = px - h * p.W;
+    const long long q = s_row[u * 32 + wl];
+    if (q >= 0) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = tile[u][c8 + j][wl];
-      st8(out + p.pg.q(b, h + p.pad_top, w + p.pad_left) * p.Cpad + ch0 + c8, o);
+      st8(out + q * p.Cpad + ch0 + c8, o);
     }
   }
 }
