@@ -256,7 +256,7 @@ __global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_
 // One warp per output flat pixel q (C = 128: 4 channels per lane).  Pads are written as zeros.
 // ================================================================================================
 
-template <typename T>
+template <typename T, bool TRAIN>
 __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T* __restrict__ h1, float* __restrict__ res) {
   // One block per (sample b, PG row r): the L fields of a sample share raw3 / rawres, so each pixel's two rows are loaded
   // ONCE and finished for all L lead times (L2 reads / L); the per-lead constants of the row (FiLM scale / shift, the
@@ -274,16 +274,30 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
   const bool pad_row = r < 1;
   if (!pad_row) {
     const int ry = h == 0 ? 0 : (h == p.pgN.HP - 1 ? 2 : 1);
+    // (round 2: the LayerNorm affine is folded into the FiLM rows here -- y = xhat G + B with G = g (scale + 1), B = b (scale + 1) + shift --
+    //  two instructions per element less in a loop that ncu showed instruction-bound at 28 instructions per element)
     for (int i = threadIdx.x; i < L * LS / 4; i += 256) {
       const int l = i / (LS / 4), k = (i - l * (LS / 4)) * 4, n = b * L + l;
-      const float* src = k < 2 * C ? p.film + (long long)n * 2 * C + k
-                       : (k < 3 * C ? p.tres + (long long)n * C + (k - 2 * C) : p.tt + ((long long)n * 9 + ry * 3) * C + (k - 3 * C));
-      *reinterpret_cast<float4*>(s_lead + l * LS + k) = *reinterpret_cast<const float4*>(src);
+      float4 v4;
+      if (k < 2 * C) {
+        const int c = k < C ? k : k - C;
+        const float4 sc = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + c);
+        if (k < C) {
+          const float4 g = *reinterpret_cast<const float4*>(p.ln_g + c);
+          v4 = make_float4(g.x * (sc.x + 1.0f), g.y * (sc.y + 1.0f), g.z * (sc.z + 1.0f), g.w * (sc.w + 1.0f));
+        } else {
+          const float4 be = *reinterpret_cast<const float4*>(p.ln_b + c), sh = *reinterpret_cast<const float4*>(p.film + (long long)n * 2 * C + C + c);
+          v4 = make_float4(fmaf(be.x, sc.x + 1.0f, sh.x), fmaf(be.y, sc.y + 1.0f, sh.y), fmaf(be.z, sc.z + 1.0f, sh.z), fmaf(be.w, sc.w + 1.0f, sh.w));
+        }
+      } else {
+        const float* src = k < 3 * C ? p.tres + (long long)n * C + (k - 2 * C) : p.tt + ((long long)n * 9 + ry * 3) * C + (k - 3 * C);
+        v4 = *reinterpret_cast<const float4*>(src);
+      }
+      *reinterpret_cast<float4*>(s_lead + l * LS + k) = v4;
     }
   }
   __syncthreads();
   const float4 bb = *reinterpret_cast<const float4*>(p.bias3 + c0), rb = *reinterpret_cast<const float4*>(p.bias1 + c0);
-  const float4 g4 = *reinterpret_cast<const float4*>(p.ln_g + c0), b4 = *reinterpret_cast<const float4*>(p.ln_b + c0);
   const long long qb_row = ((long long)b * R + r) * P;       // this row in the B-image geometry (same R, P)
   for (int col = warp; col < P; col += 8) {
     const bool pad = pad_row || col < 1;
@@ -324,20 +338,18 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
 #pragma unroll
       for (int i = 0; i < 4; ++i) { v[i] -= mean; ss += v[i] * v[i]; }
       const float rstd = rsqrtf(fmaxf(warp_sum(ss) * (1.0f / C), p.eps));
-      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float sc[4] = {f0.x, f0.y, f0.z, f0.w}, t[4] = {f1.x, f1.y, f1.z, f1.w};
+      const float sc[4] = {f0.x, f0.y, f0.z, f0.w}, t[4] = {f1.x, f1.y, f1.z, f1.w};       // folded affine: G, B
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         xh[i] = v[i] * rstd;
-        float zz = xh[i] * g[i] + be[i];
-        zz = zz * (sc[i] + 1.0f) + t[i];
-        if (zz > 0.f) nib |= 1u << i;
+        const float zz = fmaf(xh[i], sc[i], t[i]);
+        if (TRAIN && zz > 0.f) nib |= 1u << i;
         y[i] = fmaxf(zz, 0.f);
       }
       rr[0] = ra.x + rt.x; rr[1] = ra.y + rt.y; rr[2] = ra.z + rt.z; rr[3] = ra.w + rt.w;
       Ld4<T>::st(h1 + q * C + c0, make_float4(y[0], y[1], y[2], y[3]));
       *reinterpret_cast<float4*>(res + q * C + c0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-      if (xhat) {                                     // training: what the backward pass needs
+      if (TRAIN && xhat) {                            // training: what the backward pass needs
         Ld4<T>::st(xhat + q * C + c0, make_float4(xh[0], xh[1], xh[2], xh[3]));
         unsigned wbits = nib << ((lane & 7) * 4);
         wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
@@ -771,13 +783,16 @@ int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaSt
   if (smem > 200 * 1024) return set_error("stem_finish: %d lead times need %zu bytes of shared memory", p.L, smem);
   static size_t attr[2] = {48 * 1024, 48 * 1024};
   if (smem > attr[dtype == 0 ? 0 : 1]) {
-    cudaError_t e = dtype == 0 ? cudaFuncSetAttribute(stem_finish_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                               : cudaFuncSetAttribute(stem_finish_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(stem_finish_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("stem_finish smem attr: %s", cudaGetErrorString(e));
     attr[dtype == 0 ? 0 : 1] = smem;
   }
-  if (dtype == 0) stem_finish_kernel<bf16><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res);
-  else stem_finish_kernel<float><<<g, 256, smem, st>>>(p, reinterpret_cast<float*>(h1), res);
+  const bool train = p.xhat != nullptr;
+  if (dtype == 0) { if (train) stem_finish_kernel<bf16, true><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res); else stem_finish_kernel<bf16, false><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res); }
+  else { if (train) stem_finish_kernel<float, true><<<g, 256, smem, st>>>(p, reinterpret_cast<float*>(h1), res); else stem_finish_kernel<float, false><<<g, 256, smem, st>>>(p, reinterpret_cast<float*>(h1), res); }
   return check_launch("stem_finish_kernel");
 }
 
