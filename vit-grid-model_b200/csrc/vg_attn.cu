@@ -50,9 +50,16 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
     }
   } else {
     const T* src = x + ((long long)n * g.Hl * g.Wl + attn_token_pixel(g, wi, tok - g.R)) * C;
-    for (int i = 0; i < nv; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[4 * i + j] = Act<T>::ld(src + i * 128 + lane * 4 + j);
+    for (int i = 0; i < nv; ++i) {                                       // one 16- / 8-byte load per lane and 128 channels
+      if constexpr (sizeof(T) == 4) {
+        const float4 f = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(src + i * 128 + lane * 4);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b2.x; v[4 * i + 3] = b2.y;
+      }
+    }
   }
   for (int i = 0; i < 4 * nv; ++i) s += v[i];
   const float mean = warp_sum(s) / (float)C;
@@ -61,12 +68,20 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
   const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);             // nn.LayerNorm, no affine (maxvit.py:137)
   const float* gam = film + (long long)n * 2 * C;                        // [gamma | beta], used raw (maxvit.py:187)
   TO* dst = tokens + r * C;
-  for (int i = 0; i < nv; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = i * 128 + lane * 4 + j;
-      Act<TO>::st(dst + c, v[4 * i + j] * rstd * gam[c] + gam[C + c]);
+  for (int i = 0; i < nv; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 ga = *reinterpret_cast<const float4*>(gam + c), be = *reinterpret_cast<const float4*>(gam + C + c);
+    const float o0 = v[4 * i] * rstd * ga.x + be.x, o1 = v[4 * i + 1] * rstd * ga.y + be.y;
+    const float o2 = v[4 * i + 2] * rstd * ga.z + be.z, o3 = v[4 * i + 3] * rstd * ga.w + be.w;
+    if constexpr (sizeof(TO) == 4) {
+      *reinterpret_cast<float4*>(dst + c) = make_float4(o0, o1, o2, o3);
+    } else {
+      uint2 u;
+      *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(o0, o1);
+      *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(o2, o3);
+      *reinterpret_cast<uint2*>(dst + c) = u;
     }
+  }
 }
 
 // One warp per (window, head).  K-hat and V staged in shared memory as fp32, each lane owns query rows

@@ -521,11 +521,31 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ h, cons
   const long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= total) return;
   const int lane = threadIdx.x & 31;
-  const int x = (int)(i % W); long long t = i / W;
-  const int y = (int)(t % H); const int n = (int)(t / H);
+  int x, y, n;
+  if (total < (1ll << 31)) {                                 // 32-bit divisions (the 64-bit ones are software routines)
+    const unsigned iu = (unsigned)i, t = iu / (unsigned)W;
+    x = (int)(iu - t * (unsigned)W); n = (int)(t / (unsigned)H); y = (int)(t - (unsigned)n * (unsigned)H);
+  } else {
+    x = (int)(i % W); const long long t = i / W;
+    y = (int)(t % H); n = (int)(t / H);
+  }
   const T* p = h + pg.q(n, y + pad_top, x + pad_left) * C;
   float a = 0.f;
-  for (int c = lane; c < C; c += 32) a += Act<T>::ld(p + c) * w[c];
+  if ((C & 127) == 0) {                                      // four channels per lane and 128-channel block: one vector load each
+    for (int c = lane * 4; c < C; c += 128) {
+      float v[4];
+      if constexpr (sizeof(T) == 4) { const float4 f = *reinterpret_cast<const float4*>(p + c); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+      else {
+        const uint2 u = *reinterpret_cast<const uint2*>(p + c);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+      }
+      const float4 w4 = *reinterpret_cast<const float4*>(w + c);
+      a = fmaf(v[0], w4.x, a); a = fmaf(v[1], w4.y, a); a = fmaf(v[2], w4.z, a); a = fmaf(v[3], w4.w, a);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) a += Act<T>::ld(p + c) * w[c];
+  }
   a = warp_sum(a);
   if (lane == 0) out[i] = (a + bias) * stdv + mean;
 }
