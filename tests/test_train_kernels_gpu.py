@@ -242,7 +242,7 @@ def _attn_core_autograd(qkv, datt, qg, kg, bt, nw, S, win, R, heads, dh, pmask=N
     return x.grad.permute(1, 3, 0, 2, 4).reshape(nw * S, 3 * inner), out.detach(), qg_.grad.reshape(-1), kg_.grad.reshape(-1), bt_.grad
 
 
-@pytest.mark.parametrize("Hl,Wl,N,T", [(14, 21, 3, 0), (21, 35, 2, 0), (21, 35, 2, 64), (7, 7, 5, 26)])
+@pytest.mark.parametrize("Hl,Wl,N,T", [(14, 21, 3, 0), (21, 35, 2, 0), (21, 35, 2, 64), (7, 7, 5, 26), (14, 14, 12, 26)])
 def test_attn_core_bwd_tcgen05(Hl, Wl, N, T, monkeypatch):
     """The tcgen05 attention-core backward (csrc/vg_attn_bwd_tc.cu: bf16 tensors, two windows per M=128 tile) against fp32 autograd
     of the same bf16 inputs and against the mma.sync kernel it replaces; even and odd window counts (an odd count leaves the
@@ -279,8 +279,11 @@ def test_attn_core_bwd_tcgen05(Hl, Wl, N, T, monkeypatch):
         e_new, e_old = l2(got, rf), l2(old, rf)
         assert e_new < 1.2e-2 and e_new < 1.15 * e_old + 1e-4, (nm, e_new, e_old)
         assert rel_err(got, rf) < 3e-2, (nm, rel_err(got, rf), rel_err(old, rf))
-    # the kernel is deterministic in everything but the order of its global atomics
+    # the kernel is deterministic in everything but the order of its global atomics: repeated launches must give the same bits (a
+    # hand-over race -- e.g. the item flush reusing the P' / dS blocks before the last product has retired -- shows up here)
     monkeypatch.setenv("VG_ATTN_BWD_TC", "1")
-    dqg, dkg, dbt = torch.zeros_like(qg), torch.zeros_like(kg), torch.zeros_like(bt)
-    dqkv2, att2 = OT().attn_core_bwd(qkv, datt, qg, kg, bt, N, Hl, Wl, win, R, heads, dh, dqg, dkg, dbt, tf32=True, want_att=True, drop=drop)
-    assert torch.equal(dqkv2, out["1"][0]) and torch.equal(att2, out["1"][1])
+    for _ in range(12):
+        dqg, dkg, dbt = torch.zeros_like(qg), torch.zeros_like(kg), torch.zeros_like(bt)
+        dqkv2, att2 = OT().attn_core_bwd(qkv, datt, qg, kg, bt, N, Hl, Wl, win, R, heads, dh, dqg, dkg, dbt, tf32=True, want_att=True, drop=drop)
+        assert torch.equal(dqkv2, out["1"][0]) and torch.equal(att2, out["1"][1])
+        assert rel_err(dbt, out["1"][4]) < 1e-4 and rel_err(dqg, out["1"][2]) < 1e-4

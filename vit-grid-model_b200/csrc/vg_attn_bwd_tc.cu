@@ -511,6 +511,9 @@ attn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid
         }
       }
       // ---------------- item flush: bias and gamma gradients, no shared-memory atomics (fp32 ones are CAS loops) ----------------
+      // The staging below overwrites the P' / dS blocks: EVERY output product of the last tile must have retired, not only the one
+      // this warp's epilogue waited for (att is committed last; commits complete in issue order).
+      mbar_wait_tag(out_done + 3, (T - 1) & 1, 407);
       {
         float db[16];
         tmld16(lane_addr + T_DB + cq * 16, db);
