@@ -422,6 +422,34 @@ def test_conv3x3_ln_fp32_skip_copy_and_fused_head():
     assert rel_err(pred, ref_head) < 2e-3
 
 
+def test_conv3x3_ln_copy_tma_store_matches_thread_stores_and_is_repeatable(monkeypatch):
+    """The fp32 copy of the conv output leaves through TMA tensor stores from the residual chunk buffers (csrc/vg_epilogue.cuh);
+    VG_CONV_OUT2_TMA=0 keeps the per-thread stores.  Both paths must give the same bits, launch after launch, on a buffer
+    large enough for many tiles per CTA (a buffer-reuse race between the store, the refill and the next chunk would show)."""
+    o = ops()
+    N, H, W, C, dtype = 40, 84, 70, 128, torch.bfloat16
+    g_ = torch.Generator(device="cuda").manual_seed(5)
+    xp = o.pg_from_nchw(torch.randn(N, C, H, W, device="cuda", generator=g_), dtype)
+    wt = (torch.randn(C, 9 * C, device="cuda", generator=g_) / math.sqrt(9 * C)).to(dtype)
+    b, g, be = (torch.randn(C, device="cuda", generator=g_) * 0.1 for _ in range(3))
+    g = g + 1.0
+    rp = torch.randn(xp.shape[0], C, device="cuda", generator=g_)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("VG_CONV_OUT2_TMA", mode)
+        for rep in range(6):
+            out = torch.empty_like(xp)
+            copy = torch.full((xp.shape[0], C), float("nan"), dtype=torch.float32, device="cuda")
+            o.conv3x3_ln(xp, wt, b, g, be, 1e-5, None, rp, out, N, H, W, out_copy=copy)
+            torch.cuda.synchronize()
+            if mode + "o" not in outs:
+                outs[mode + "o"], outs[mode + "c"] = out, copy
+            else:
+                assert torch.equal(out, outs[mode + "o"]) and torch.equal(copy, outs[mode + "c"]), (mode, rep)
+    assert torch.isfinite(outs["1c"]).all()
+    assert torch.equal(outs["0o"], outs["1o"]) and torch.equal(outs["0c"], outs["1c"])
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_head(dtype):
     o = ops()

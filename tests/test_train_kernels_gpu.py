@@ -287,3 +287,55 @@ def test_attn_core_bwd_tcgen05(Hl, Wl, N, T, monkeypatch):
         dqkv2, att2 = OT().attn_core_bwd(qkv, datt, qg, kg, bt, N, Hl, Wl, win, R, heads, dh, dqg, dkg, dbt, tf32=True, want_att=True, drop=drop)
         assert torch.equal(dqkv2, out["1"][0]) and torch.equal(att2, out["1"][1])
         assert rel_err(dbt, out["1"][4]) < 1e-4 and rel_err(dqg, out["1"][2]) < 1e-4
+
+
+def test_repeatable_launches_of_the_pipelined_kernels():
+    """Kernels with producer / consumer hand-overs through shared memory must give the same bits launch after launch:
+    the LayerNorm backward (per-warp bulk-copy ring), the store-epilogue GEMM with sixteen epilogue warps (16-bit plain store and
+    BN + GELU fp16 output) and the conv data gradient through the halo kernel."""
+    o, ot = O(), OT()
+    g_ = torch.Generator(device="cuda").manual_seed(11)
+    # LN backward on a PG buffer whose pixel count is not a multiple of four (the last group is read without the ring)
+    N, HP, WP, C = 7, 29, 23, 128
+    npix = o.pg_pixels(N, HP, WP)
+    dY = torch.randn(npix, C, device="cuda", generator=g_)
+    xhat = torch.randn(npix, C, device="cuda", generator=g_).to(torch.bfloat16)
+    rstd = torch.rand(npix, device="cuda", generator=g_) + 0.5
+    mask = torch.randint(0, 2 ** 31 - 1, (npix, 4), device="cuda", generator=g_, dtype=torch.int32)
+    ln_g = torch.randn(C, device="cuda", generator=g_)
+    film = torch.randn(N, 2 * C, device="cuda", generator=g_) * 0.1
+    ref = None
+    for _ in range(6):
+        dconv, sums, _b = ot.conv_ln_bwd(dY, (xhat, rstd, mask), ln_g, film, 1e-5, N, HP, WP, torch.bfloat16)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (dconv, sums)
+        else:
+            assert torch.equal(dconv, ref[0])
+            assert rel_err(sums, ref[1]) < 1e-5                      # float atomics: order-dependent in the last bits only
+    # GEMMs
+    M, K = 20000, 128
+    A = torch.randn(M, K, device="cuda", generator=g_)
+    for (Nn, kw, dt) in ((3072, dict(), torch.bfloat16), (512, dict(scale=torch.rand(512, device="cuda") + 0.5, shift=torch.randn(512, device="cuda"), act=1, tf32=True, out_dtype=torch.float16), torch.float32)):
+        Wm = (torch.randn(Nn, K, device="cuda", generator=g_) / math.sqrt(K)).to(dt)
+        first = None
+        for _ in range(6):
+            out = o.gemm(A.to(dt), Wm, **kw)
+            torch.cuda.synchronize()
+            first = out if first is None else first
+            assert torch.equal(out, first)
+        refm = A.to(dt).float() @ Wm.float().t()
+        if "act" in kw:
+            refm = F.gelu(refm * kw["scale"] + kw["shift"])
+        assert rel_err(first, refm) < 1.5e-2
+    # conv data gradient (halo kernel, flipped taps)
+    Nf, H, W = 5, 28, 21
+    dconv = o.pg_from_nchw(torch.randn(Nf, C, H, W, device="cuda", generator=g_), torch.bfloat16)
+    Wd = (torch.randn(C, 9 * C, device="cuda", generator=g_) / 34).to(torch.bfloat16)
+    res = torch.randn(dconv.shape[0], C, device="cuda", generator=g_)
+    first = None
+    for _ in range(6):
+        dx = o.gemm(dconv, Wd, ntaps=9, tap_shift=tuple(-s for s in o.conv_tap_shifts(W)), res=res, out_f32=True)
+        torch.cuda.synchronize()
+        first = dx if first is None else first
+        assert torch.equal(dx, first)
