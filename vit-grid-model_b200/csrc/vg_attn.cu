@@ -189,7 +189,8 @@ template <typename T, int DH>
 static int core_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, const DropCfg& drop, cudaStream_t st) {
   const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   const size_t smem = 4 * (size_t)(2 * S * (DH + 1) + nb) * sizeof(float);
-  static size_t attr_bytes = 48 * 1024;                     // the size depends on the window geometry: raise the limit when it grows
+  static PerDeviceSize attr_pd;                             // the size depends on the window geometry: raise the limit when it grows
+  size_t& attr_bytes = attr_pd.cur();
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("attn_core smem attr: %s", cudaGetErrorString(e));

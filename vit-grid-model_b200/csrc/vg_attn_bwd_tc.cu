@@ -629,14 +629,17 @@ int attn_core_bwd_tc_run(const void* qkv, const void* datt, const float* qgamma,
   if (rc) return rc;
   rc = rows_map(&md, datt, (long long)heads * ab::DH, rows, S);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ab::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("attn_core_bwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  static PerDeviceSize sms_pd;
+  size_t& sms_c = sms_pd.cur();
+  int sms = (int)sms_c;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; sms_c = (size_t)sms; }
   AttnBwdTcParams p;
   p.qgamma = qgamma; p.kgamma = kgamma; p.bias_table = bias_table; p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.att_out = reinterpret_cast<bf16*>(att_out); p.dqgamma = dqgamma; p.dkgamma = dkgamma; p.dbias_table = dbias_table;

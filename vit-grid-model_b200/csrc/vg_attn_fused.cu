@@ -771,7 +771,8 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
   p.drop.seed = seed; p.drop.salt = salt; p.drop.thresh = drop_thresh; p.drop.scale = 256.0f / (256.0f - (float)drop_thresh);
   p.dbg = nullptr;
   if (const char* e = getenv("VG_ATTN_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES);

@@ -585,7 +585,8 @@ int conv_ln_bwd_run(int xdtype, int odtype, const float* dY, const void* xhat, c
   if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(rstd)) & 15)
     return set_error("conv_ln_bwd: dY / xhat / mask / rstd must be 16-byte aligned");
   const size_t sm16 = 8 * lnb::NST * lnb::stage_bytes<bf16>() + 128, sm32 = 8 * lnb::NST * lnb::stage_bytes<float>() + 128;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_ln_bwd_kernel<bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_bwd_kernel<bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);

@@ -1639,7 +1639,8 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
     // mode 3: two cp.async stages of [q | k | v | dO] rows instead of the static V / dO tiles
     const size_t smem3 = (size_t)cbh::BYTES + (size_t)(2 * nb + 6 * cbh::DH) * sizeof(float) +
                          (use_tf32 == 3 ? (size_t)(2 * 4 - 2) * cbh::SM * cbh::LDQ * 2 : 0);
-    static size_t attr3 = 0;                        // depends on the window size: raise the limit when it grows
+    static PerDeviceSize attr3_pd;                  // depends on the window size: raise the limit when it grows
+    size_t& attr3 = attr3_pd.cur();
     if (smem3 > attr3) {
       cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_bwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
@@ -1655,7 +1656,8 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   }
   if (use_tf32) {
     const size_t smem2 = (size_t)(cb::SLOT_FLOATS + 2 * nb + 2 * cb::DH) * sizeof(float);
-    static size_t attr2 = 0;                        // depends on the window size: raise the limit when it grows
+    static PerDeviceSize attr2_pd;                  // depends on the window size: raise the limit when it grows
+    size_t& attr2 = attr2_pd.cur();
     if (smem2 > attr2) {
       cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
       if (e != cudaSuccess) return set_error("attn_core_bwd_mma smem attr: %s", cudaGetErrorString(e));
@@ -1669,7 +1671,8 @@ int attn_core_bwd_run(const float* qkv, const float* datt, const float* qgamma, 
   }
   if (att_out) return set_error("attn_core_bwd: att_out is only produced by the tf32 kernel");
   const size_t smem = (size_t)(8 * 64 * 33 + 64 * 65 + 2 * nb + 128 + 8 * 2 * 32 + (drop_thresh ? 64 * 65 : 0)) * sizeof(float);
-  static size_t attr = 0;                        // depends on the window size: raise the limit when it grows
+  static PerDeviceSize attr_pd;                  // depends on the window size: raise the limit when it grows
+  size_t& attr = attr_pd.cur();
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("attn_core_bwd smem attr: %s", cudaGetErrorString(e));

@@ -701,19 +701,21 @@ static int make_map_2d(CUtensorMap* m, bool f32, const void* ptr, long long inne
   return 0;
 }
 
-static int g_num_sms = 0;
 static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int n_sms[64] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  int& n = n_sms[dev & 63];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_num_sms;
+  return n;
 }
 
 template <int KIND, int TF32>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& gs, const EpiParams& ep, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr_set = attr_pd.cur();
   constexpr int SMEM = KIND == EPI_STORE ? TC_SMEM_BYTES_STORE16 : (KIND == EPI_CONVT ? TC_SMEM_BYTES_STORE : TC_SMEM_BYTES);
   constexpr int THREADS = KIND == EPI_STORE ? TC_THREADS_STORE : TC_THREADS;
   if (!attr_set) {
@@ -785,7 +787,8 @@ int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const Ep
     if (rc2) return rc2;
     hs.out2_tma = 1;
   }
-  static bool attr_set = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr_set = attr_pd.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES);
@@ -804,7 +807,8 @@ int conv_halo_run_mp(const void* x, const void* Wt, long long M, int P, const Ep
     CUtensorMap mb2;
     rc = make_map_2d(&mb2, false, Wt, 9 * 128, 128, 64);     // half of the output channels per CTA
     if (rc) return rc;
-    static bool attr2 = false;
+    static PerDeviceFlag attr2_pd;
+    bool& attr2 = attr2_pd.cur();
     if (!attr2) {
       cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO2_SMEM_BYTES);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO2_SMEM_BYTES);

@@ -9,6 +9,11 @@ namespace vg {
 
 struct EpiParams;
 
+// cudaFuncSetAttribute and the SM count belong to a DEVICE: "already done" caches are kept per device ordinal, so a process that
+// drives several GPUs (the reference wraps its model in nn.DataParallel) configures every one of them.
+struct PerDeviceFlag { bool done[64] = {}; bool& cur() { int d = 0; cudaGetDevice(&d); return done[d & 63]; } };
+struct PerDeviceSize { size_t v[64] = {}; size_t& cur() { int d = 0; cudaGetDevice(&d); return v[d & 63]; } };
+
 // printf-style: records the message for vg_last_error() and returns a non-zero error code
 int set_error(const char* fmt, ...);
 // cudaGetLastError() after a launch; 0 when clean

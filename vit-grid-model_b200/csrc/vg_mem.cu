@@ -801,14 +801,15 @@ int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaSt
   const unsigned g = (unsigned)(p.pgB.N * p.pgB.R);          // one block per (sample, PG row)
   const size_t smem = (size_t)p.L * 6 * 128 * sizeof(float);
   if (smem > 200 * 1024) return set_error("stem_finish: %d lead times need %zu bytes of shared memory", p.L, smem);
-  static size_t attr[2] = {48 * 1024, 48 * 1024};
-  if (smem > attr[dtype == 0 ? 0 : 1]) {
+  static PerDeviceSize attr_pd;
+  size_t& attr_cur = attr_pd.cur();
+  if (smem > attr_cur) {
     cudaError_t e = cudaFuncSetAttribute(stem_finish_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_finish_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("stem_finish smem attr: %s", cudaGetErrorString(e));
-    attr[dtype == 0 ? 0 : 1] = smem;
+    attr_cur = smem;
   }
   const bool train = p.xhat != nullptr;
   if (dtype == 0) { if (train) stem_finish_kernel<bf16, true><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res); else stem_finish_kernel<bf16, false><<<g, 256, smem, st>>>(p, reinterpret_cast<bf16*>(h1), res); }

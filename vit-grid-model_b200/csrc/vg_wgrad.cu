@@ -340,12 +340,13 @@ int wgrad_run(int dtype, const void* dY, const void* A, long long rowsA, long lo
     rc = make_rows_map(&ma, dtype == 2, A, Ca, rowsA, kt);
     if (rc) return rc;
     const int smem = ws.stages * (1 + ws.acc_per_cta) * wg::TILE_BYTES + 1024 + 256;
-    static int attr_done[2] = {0, 0};
-    if (attr_done[dtype == 2] < smem) {
+    static PerDeviceSize attr_pd[2];
+    size_t& attr_cur = attr_pd[dtype == 2].cur();
+    if (attr_cur < (size_t)smem) {
       cudaError_t e = dtype == 2 ? cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
                                  : cudaFuncSetAttribute(wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return set_error("wgrad smem attr: %s", cudaGetErrorString(e));
-      attr_done[dtype == 2] = 227 * 1024;
+      attr_cur = 227 * 1024;
     }
     const int grid = ws.n_tiles * ws.groups * ws.ksplit;
     if (dtype == 2) wgrad_tc_kernel<1><<<grid, wg::THREADS, smem, st>>>(my, ma, ws, work);
