@@ -165,3 +165,28 @@ def test_host_pipeline_matches_direct_calls():
     assert len(got) == len(direct)
     for a, b in zip(got, direct):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_model_on_second_device_while_first_is_current():
+    """One process driving two GPUs (the reference wraps its model in nn.DataParallel): a model on cuda:1 called while
+    cuda:0 is the current device gives the cuda:0 bits, and a training step runs there (device guards in every public
+    entry point, per-device function attributes; tools/two_devices_one_process.py is the same check as a script)."""
+    from vit_grid_model_b200 import MetNet3, focal_r_loss
+    cfg = synth.CFG_SMALL128
+    sd = synth.make_state_dict(synth.metnet3_spec(cfg), seed=0)
+    x, ts, target = synth.make_inputs(cfg, 2, seed=1)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = MetNet3(**cfg.metnet3_kwargs())
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev).eval()
+        torch.cuda.set_device(0)
+        with torch.no_grad():
+            outs.append(m(x.to(dev), timestamps=ts.to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
+    m = m.train()
+    loss = focal_r_loss(m(x.to("cuda:1"), timestamps=ts.to("cuda:1")), target.to("cuda:1"))
+    loss.backward()
+    torch.cuda.synchronize("cuda:1")
+    assert torch.isfinite(loss).item() and all(torch.isfinite(p.grad).all().item() for p in m.parameters() if p.grad is not None)

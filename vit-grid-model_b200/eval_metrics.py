@@ -61,11 +61,12 @@ class EvalMetrics:
         need = _lib.load().vg_eval_metrics_workspace(B, L, P)
         if self._work is None or self._work.numel() < need:
             self._work = torch.empty(need, dtype=torch.float64, device=preds.device)
-        _lib.call("vg_eval_metrics", preds.data_ptr(), truth.data_ptr(), truth_classes.data_ptr(),
-                  int(truth_classes.dtype == torch.int64), last_obs.data_ptr(), sim_21h.data_ptr(), sim_avg.data_ptr(), B, L, P,
-                  self.bounds[0], self.bounds[1], self.bounds[2], int(clamp_preds), self.counts.data_ptr(), self.sums.data_ptr(),
-                  self.glob.data_ptr(), self.nonzero.data_ptr(), self.loss_sum.data_ptr(), self._work.data_ptr(),
-                  self._work.numel(), torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.device(preds.device):              # launch on the tensors' device, whatever the current one is
+            _lib.call("vg_eval_metrics", preds.data_ptr(), truth.data_ptr(), truth_classes.data_ptr(),
+                      int(truth_classes.dtype == torch.int64), last_obs.data_ptr(), sim_21h.data_ptr(), sim_avg.data_ptr(), B, L, P,
+                      self.bounds[0], self.bounds[1], self.bounds[2], int(clamp_preds), self.counts.data_ptr(), self.sums.data_ptr(),
+                      self.glob.data_ptr(), self.nonzero.data_ptr(), self.loss_sum.data_ptr(), self._work.data_ptr(),
+                      self._work.numel(), torch.cuda.current_stream().cuda_stream)
         self.entries += B * L * P
         self.steps += 1
 

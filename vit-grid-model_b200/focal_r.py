@@ -17,13 +17,15 @@ class _FocalR(torch.autograd.Function):
         pred_c, target_c = pred.float().contiguous(), target.float().contiguous()
         ctx.save_for_backward(pred_c, target_c)
         ctx.cfg = (beta, gamma, mse)
-        return ops.focal_r_forward(pred_c, target_c, beta, gamma, mse)
+        with torch.cuda.device(pred_c.device):             # kernels launch on the tensors' device, whatever the current one is
+            return ops.focal_r_forward(pred_c, target_c, beta, gamma, mse)
 
     @staticmethod
     def backward(ctx, grad_out):
         pred, target = ctx.saved_tensors
         beta, gamma, mse = ctx.cfg
-        g = ops.focal_r_backward(pred, target, 1.0, beta, gamma, mse)
+        with torch.cuda.device(pred.device):
+            g = ops.focal_r_backward(pred, target, 1.0, beta, gamma, mse)
         return g * grad_out, None, None, None, None
 
 

@@ -74,8 +74,9 @@ class FlatAdamW:
         (loss-scale removal / averaging over accumulated micro-batches) at no extra pass"""
         g = self._grad_flat()
         self.step_count += 1
-        ot.adamw_step(self.flat, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.weight_decay, self.step_count, gscale=grad_scale)
+        with torch.cuda.device(self.flat.device):
+            ot.adamw_step(self.flat, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                          self.weight_decay, self.step_count, gscale=grad_scale)
         self.model.invalidate_packed()                    # kernel-layout weight copies are re-derived on the next forward
 
     # ------------------------------------------------------------------ checkpoint / resume

@@ -313,7 +313,8 @@ class MaxViTTrainFn(torch.autograd.Function):
         named = list(vit.named_parameters())
         G = {n: torch.zeros(p.shape, dtype=torch.float32, device=p.device) for n, p in named}
         dcond = torch.zeros_like(ctx.cond)
-        dx = maxvit_train_backward(vit, ctx.saved, ctx.cond, dcond, dy.float().contiguous(), G, "")
+        with torch.cuda.device(dy.device):
+            dx = maxvit_train_backward(vit, ctx.saved, ctx.cond, dcond, dy.float().contiguous(), G, "")
         ctx.saved = None
         return (None, dx, dcond, *[G[n] for n, _ in named])
 
@@ -519,7 +520,8 @@ class MetNet3TrainFn(torch.autograd.Function):
                                "the first backward (retain_graph is not supported); call the model again")
         G = model.grad_buffer()
         G.zero_()
-        metnet3_train_backward(model, ctx.S, dpred.float(), G, model._grad_sync)
+        with torch.cuda.device(dpred.device):
+            metnet3_train_backward(model, ctx.S, dpred.float(), G, model._grad_sync)
         ctx.S = None
         snap = G.snapshot()
         return (None, None, None, *[snap[n] for n in G.names])
