@@ -67,6 +67,15 @@ VG_API int vg_prepare_fwd(int dtype, const float* x, const long long* xstride, i
 VG_API int vg_standardise_channel(float* x, const long long* xstride, int B, int T, int C, int H, int W, int channel,
                            float pm_mean, float pm_std, void* stream);
 
+/* Operand split for fp32-accurate products on the tf32 tensor cores ("3xTF32"): x = hi + lo with hi = x truncated to tf32's 10
+ * mantissa bits.  in: fp32 [rows][K]; out: fp32 [rows][3K].  pattern 0 (left operand): [hi | hi | lo]; pattern 1 (right operand,
+ * [N][K] weights): [hi | lo | hi] -- so that ONE tf32 GEMM over K' = 3K computes hi*hi + hi*lo + lo*hi with every epilogue of
+ * vg_gemm_fwd intact (the dropped lo*lo term is ~2^-22 of the product; measured 3e-6 .. 3e-5 of the largest output for K = 128 ..
+ * 2048, which is the truncating fp32 accumulation of the tensor core over 3K/8 instructions; plain tf32 measures 8e-4).  Used by the "tf32_conv" precision for the projections of
+ * the MaxViT block (nn.Conv2d 1x1 / nn.Linear in maxvit.py:88-96, 139, 150), where exact fp32 is required but the SIMT GEMM is
+ * 10x slower than the tensor cores. */
+VG_API int vg_split3_tf32(const float* in, long long rows, int K, float* out, int pattern, void* stream);
+
 /* Same as vg_prepare_fwd for a batch PACKED on the host (HostPipeline.pack_host: the data-loader side of
  * evaluation_vit.py:236-249): x is bf16 (B,T,C,H,W) whose PM2.5 channels were standardised in fp32 BEFORE the rounding
  * to bf16 -- exactly the values vg_prepare_fwd(VG_DTYPE_BF16) produces from the fp32 tensor, so the predictions are
@@ -83,6 +92,12 @@ VG_API int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, 
                       int te, const float* emb_lead, const float* emb_month, const float* emb_day,
                       const float* emb_hour, const float* w3, const float* w1, int c_in, int c_data, int Cout,
                       float* temb, float* cond, float* tt, float* tres, void* stream);
+
+/* One nn.Linear over a few rows with wide weights: out (N,od) = act(W (od,in_dim) . relu?(in (N,in_dim)) + b), fp32; act 0 none,
+ * 1 ReLU, 2 SiLU, 3 sigmoid.  The two layers of the FiLM MLP (maxvit.py:130-135) at BASELINE configs[4]'s widths (12 fields,
+ * 512 -> 2048 -> 1024) are two calls of this instead of one vg_cond_mlp_fwd: a warp per weight row instead of a block per field. */
+VG_API int vg_dense_rows_fwd(const float* in, int N, int in_dim, int pre_relu, const float* W, const float* b, int od, int act,
+                             float* out, void* stream);
 
 /* metnet3.py:140-143 (pre_relu=1, W1=NULL) and maxvit.py:130-135 (Linear->SiLU->Linear): per-field
  * conditioning vectors, fp32.  out (N,hid) if W1 is NULL else (N,od). */

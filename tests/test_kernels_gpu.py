@@ -536,3 +536,55 @@ def test_maxvit_module_trains_standalone():
         if k.endswith((".0.0.bias", ".0.3.bias", ".0.7.bias")):
             continue                                            # conv bias in front of a batch-statistic BatchNorm: zero gradient
         assert rel_err(p.grad, sd[k].grad) < 2e-3, k
+
+
+# ---- fp32-accurate projections on the tf32 tensor cores (the MaxViT side of precision 'tf32_conv') --------------------------
+def test_split3_tf32_layout_is_bit_exact():
+    """vg_split3_tf32: hi = the operand with the 13 low mantissa bits cleared, lo = x - hi (exact in fp32), laid out [hi|hi|lo] for
+    the left operand and [hi|lo|hi] for the weights"""
+    x = rnd(37, 64, seed=3).cuda()
+    hi = (x.view(torch.int32) & -8192).view(torch.float32)
+    lo = x - hi
+    assert torch.equal(ops().split3_tf32(x, 0), torch.cat([hi, hi, lo], 1))
+    assert torch.equal(ops().split3_tf32(x, 1), torch.cat([hi, lo, hi], 1))
+
+
+@pytest.mark.parametrize("M,K,N", [(777, 128, 384), (2120, 512, 1536), (300, 2048, 512)])
+def test_gemm_3xtf32_is_fp32_accurate(M, K, N):
+    """one tf32 GEMM over the split operands against a float64 product.  Tolerance: 1.5 * (3K/8) * 2^-24 + 1e-6 of the largest
+    output -- the truncating fp32 accumulation of the tensor core over 3K/8 instructions is what is left once the operand rounding
+    is gone (measured 3e-6 at K=128, 8e-6 at 512, 3e-5 at 2048; plain tf32 8e-4; the SIMT kernel 1e-6) -- and at least 20x closer
+    than plain tf32, with the fused epilogue (BN scale/shift + GELU + residual) intact"""
+    A, W = rnd(M, K, seed=1).cuda(), (rnd(N, K, seed=2) / math.sqrt(K)).cuda()
+    ref = A.double() @ W.double().t()
+    scale = ref.abs().max().item()
+    err_x3 = (ops().gemm(A, W, x3=True).double() - ref).abs().max().item() / scale
+    err_simt = (ops().gemm(A, W).double() - ref).abs().max().item() / scale
+    err_tf32 = (ops().gemm(A, W, tf32=True).double() - ref).abs().max().item() / scale
+    tol = 1.5 * (3 * K / 8) * 2.0 ** -24 + 1e-6
+    assert err_simt < 3e-6 and err_x3 < tol, (err_x3, err_simt, tol)
+    assert err_tf32 > 20 * err_x3, (err_tf32, err_x3)
+    s, t, r = (1 + 0.1 * rnd(N, seed=4)).cuda(), rnd(N, seed=5).cuda(), rnd(M, N, seed=6).cuda()
+    got = ops().gemm(A, W, scale=s, shift=t, act=1, res=r, x3=True)
+    want = F.gelu(ref * s.double() + t.double()) + r.double()
+    assert (got.double() - want).abs().max().item() / want.abs().max().item() < 2 * tol
+
+
+@pytest.mark.parametrize("N,cd,hid,od", [(12, 2, 1024, 1024), (12, 512, 2048, 1024), (5, 67, 1024, 256), (1, 512, 1024, 1024)])
+def test_cond_mlp_wide_rows_path(N, cd, hid, od):
+    """few fields x wide FiLM layers (configs[4]) go through two vg_dense_rows_fwd passes: same numbers as Linear -> SiLU -> Linear"""
+    c = rnd(N, cd, seed=1).cuda()
+    W0, b0 = (rnd(hid, cd, seed=2) / math.sqrt(cd)).cuda(), rnd(hid, seed=3).cuda()
+    W1, b1 = (rnd(od, hid, seed=4) / math.sqrt(hid)).cuda(), rnd(od, seed=5).cuda()
+    want = F.linear(F.silu(F.linear(c.double(), W0.double(), b0.double())), W1.double(), b1.double())
+    assert rel_err(ops().cond_mlp(c, W0, b0, W1, b1), want) < 1e-5
+
+
+def test_se_gate_wide_rows_path():
+    """squeeze-excite gate at configs[4]'s widths (12 fields, 2048 channels, 512 hidden): mean -> Linear -> ReLU -> Linear -> sigmoid"""
+    N, parts, C, se, HW = 12, 13, 2048, 512, 1590
+    psum = rnd(N, parts, C, seed=1, scale=30.0).cuda()
+    W1, W2 = (rnd(se, C, seed=2) / math.sqrt(C)).cuda(), (rnd(C, se, seed=3) / math.sqrt(se)).cuda()
+    mean = psum.double().sum(1) / HW
+    want = torch.sigmoid(F.linear(F.relu(F.linear(mean, W1.double())), W2.double()))
+    assert rel_err(ops().se_gate(psum, HW, W1, W2), want) < 1e-5

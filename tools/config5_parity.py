@@ -16,7 +16,7 @@ print(f"oracle: {time.perf_counter() - t0:.1f} s", flush=True)
 m = MetNet3(**cfg.metnet3_kwargs())
 m.load_state_dict(sd, strict=True)
 m = m.cuda().eval()
-for mode in ("tf32", "tf32+qkv_exact", "tf32conv+fp32vit", "fp32"):
+for mode in ("tf32", "tf32+qkv_exact", "tf32conv+fp32vit", "tf32_conv", "fp32"):
     m.vit.qkv_exact = mode == "tf32+qkv_exact"
     if mode == "tf32+qkv_exact":
         m.set_precision("tf32")

@@ -98,6 +98,10 @@ int vg_standardise_channel(float* x, const long long* xstride, int B, int T, int
   return standardise_channel_run(x, xstride, B, T, C, H, W, channel, pm_mean, pm_std, (cudaStream_t)stream);
 }
 
+int vg_split3_tf32(const float* in, long long rows, int K, float* out, int pattern, void* stream) {
+  return split3_tf32_run(in, rows, K, out, pattern, (cudaStream_t)stream);
+}
+
 int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long long ts_sF, int B, int L, int le, int te,
                       const float* emb_lead, const float* emb_month, const float* emb_day, const float* emb_hour,
                       const float* w3, const float* w1, int c_in, int c_data, int Cout, float* temb, float* cond,
@@ -110,6 +114,11 @@ int vg_time_terms_fwd(const float* ts, long long ts_sB, long long ts_sT, long lo
   p.temb = temb; p.cond = cond; p.tt = tt; p.tres = tres;
   p.err = device_error_ptr();
   return time_terms_run(p, (cudaStream_t)stream);
+}
+
+int vg_dense_rows_fwd(const float* in, int N, int in_dim, int pre_relu, const float* W, const float* b, int od, int act,
+                      float* out, void* stream) {
+  return dense_rows_run(in, N, in_dim, pre_relu, W, b, od, act, out, (cudaStream_t)stream);
 }
 
 int vg_cond_mlp_fwd(const float* cond, int N, int cond_dim, int pre_relu, const float* W0, const float* b0, int hid,

@@ -418,6 +418,17 @@ __global__ void __launch_bounds__(256) se_gate_train_kernel(const float* __restr
   }
 }
 
+__global__ void __launch_bounds__(256) field_mean_kernel(const float* __restrict__ psum, int nparts, float inv_count, int C,
+                                                         long long total, float* __restrict__ mean) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / C;
+  const int c = (int)(i - n * C);
+  float s = 0.f;
+  for (int h = 0; h < nparts; ++h) s += psum[(n * nparts + h) * C + c];
+  mean[i] = s * inv_count;
+}
+
 // squeeze-excite scale folded into the per-field weights of the 1x1 projection that follows (maxvit.py:47 + :95):
 //   Wn[n][co][c] = W[co][c] * gate[n][c]    -- 256 KB per field instead of a read-modify-write pass over the activations
 template <typename TO>
@@ -1524,6 +1535,13 @@ int dw_wgrad_run(const float* X, const float* dY, int N, int H, int W, int C, fl
 
 int se_gate_train_run(const float* psum, int N, int nparts, long long HW, const float* W1, const float* W2, int C, int se,
                       float* gate, float* mean, float* hid, cudaStream_t st) {
+  if (N <= 32 && C >= 1024 && C % 4 == 0 && se % 4 == 0 && mean && hid) {      // few fields, wide layers: a warp per weight row (vg_mem.cu)
+    field_mean_kernel<<<nblk((long long)N * C, 256), 256, 0, st>>>(psum, nparts, 1.0f / (float)HW, C, (long long)N * C, mean);
+    int rc = check_launch("field_mean_kernel");
+    if (rc == 0) rc = dense_rows_run(mean, N, C, 0, W1, nullptr, se, 1, hid, st);
+    if (rc == 0) rc = dense_rows_run(hid, N, se, 0, W2, nullptr, C, 3, gate, st);
+    return rc;
+  }
   se_gate_train_kernel<<<N, 256, (C + se) * sizeof(float), st>>>(psum, nparts, 1.0f / (float)HW, W1, W2, C, se, gate, mean, hid);
   return check_launch("se_gate_train_kernel");
 }

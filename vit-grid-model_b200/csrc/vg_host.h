@@ -25,6 +25,7 @@ int* device_error_ptr();
 enum { VG_DEVERR_TIMESTAMP = 1 };
 
 int conv_halo_run(const void* x, const void* Wt, const PGeom& pg, const EpiParams& ep, int train, cudaStream_t st);
+int split3_tf32_run(const float* in, long long rows, int K, float* out, int pattern, cudaStream_t st);
 int gemm_run(int dtype, int kind, const void* A, long long rowsA, int Ca, const void* B, int Ntot, int ntaps,
              const int* tap_shift, long long M, long long rows_per_batch, int b_rows_per_batch,
              const EpiParams& ep, float* scratch, long long scratch_elems, cudaStream_t st);
@@ -72,6 +73,8 @@ int prepare_run(int dtype, const void* x, int x_bf16, int prestd, const long lon
                 int pad_left, int HP, int WP, int Cpad, float mean, float stdv, void* out, cudaStream_t st);
 int time_terms_run(const TimeParams& p, cudaStream_t st);
 int standardise_channel_run(float* x, const long long* xs, int B, int T, int C, int H, int W, int ch, float mean, float stdv, cudaStream_t st);
+int dense_rows_run(const float* in, int N, int cd, int pre_relu, const float* W, const float* b, int od, int act, float* out,
+                   cudaStream_t st);
 int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0, const float* b0, int hid,
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st);
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st);

@@ -250,6 +250,56 @@ __global__ void cond_mlp_kernel(const float* __restrict__ cond, int cd, int pre_
   }
 }
 
+// One dense layer over a FEW rows (fields) with wide weights (configs[4]: 12 fields through 512 -> 2048 -> 1024 FiLM layers and the
+// 2048 -> 512 -> 2048 squeeze-excite): the weights are the traffic, so a warp owns one output row of W, reads it once with
+// coalesced 16-byte loads and dots it with NF fields' inputs at a time (the inputs stay in L1).  grid (od / 8, fields / NF).
+// act: 0 none, 1 ReLU, 2 SiLU, 3 sigmoid.  (The block-per-field kernels above walk each W row with one thread or one rolled
+// loop: 0.4 ms / 1.0 ms per call at these widths, a chain of dependent L2 round trips.)
+template <int NF>
+__global__ void __launch_bounds__(256) dense_rows_kernel(const float* __restrict__ in, int N, int cd, int pre_relu,
+                                                         const float* __restrict__ W, const float* __restrict__ b, int od, int act,
+                                                         float* __restrict__ out, int vec) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp, n0 = blockIdx.y * NF;
+  if (o >= od) return;
+  float acc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+  const float4* w4 = reinterpret_cast<const float4*>(W + (long long)o * cd);
+  const float4* x4 = reinterpret_cast<const float4*>(in + (long long)n0 * cd);
+  const int q = vec ? cd >> 2 : 0;
+  if (!vec) {                                                  // narrow / odd input widths (the 2-wide condition of maxvit.py:130)
+    for (int j = lane; j < cd; j += 32) {
+      const float w = W[(long long)o * cd + j];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        if (n0 + f < N) { const float x = in[(long long)(n0 + f) * cd + j]; acc[f] = fmaf(w, pre_relu ? fmaxf(x, 0.f) : x, acc[f]); }
+      }
+    }
+  }
+#pragma unroll 4
+  for (int j = lane; j < q; j += 32) {
+    const float4 w = __ldg(w4 + j);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      if (n0 + f < N) {
+        float4 x = __ldg(x4 + (long long)f * q + j);
+        if (pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        acc[f] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[f]))));
+      }
+    }
+  }
+  const float bo = b ? b[o] : 0.f;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    float a = warp_sum(acc[f]) + bo;
+    if (act == 1) a = fmaxf(a, 0.f);
+    else if (act == 2) a = a / (1.0f + expf(-a));
+    else if (act == 3) a = 1.0f / (1.0f + expf(-a));
+    if (lane == 0 && n0 + f < N) out[(long long)(n0 + f) * od + o] = a;
+  }
+}
+
 // ================================================================================================
 // stem finish: per field n = b*L + l and frame pixel: v = raw3[b] + bias + tt[n][case]; ChanLayerNorm; FiLM
 // (scale+1, shift); ReLU -> h1[n].  Also the per-field residual  res[n] = rawres[b] + res_bias + tres[n].
@@ -374,6 +424,34 @@ __global__ void __launch_bounds__(256) stem_finish_kernel(const StemParams p, T*
       }
     }
   }
+}
+
+// ================================================================================================
+// 3xTF32 operand split (see vg_split3_tf32 in include/vitgrid.h): one float4 of the input -> three float4s of the output row
+// ================================================================================================
+__global__ void __launch_bounds__(256) split3_tf32_kernel(const float* __restrict__ in, long long rows, int K, float* __restrict__ out, int pattern) {
+  const int k4 = K >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * k4) return;
+  const long long r = i / k4;
+  const int c = (int)(i - r * k4) * 4;
+  const float4 x = *reinterpret_cast<const float4*>(in + r * K + c);
+  float4 hi, lo;
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;      // exact in fp32
+  float* o = out + r * 3 * K + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + K) = pattern ? lo : hi;
+  *reinterpret_cast<float4*>(o + 2 * K) = pattern ? hi : lo;
+}
+
+int split3_tf32_run(const float* in, long long rows, int K, float* out, int pattern, cudaStream_t st) {
+  if (K % 4) return set_error("split3_tf32: K %% 4 != 0");
+  if (rows <= 0) return 0;
+  const long long total = rows * (K / 4);
+  split3_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, rows, K, out, pattern);
+  return check_launch("split3_tf32_kernel");
 }
 
 // ================================================================================================
@@ -795,6 +873,15 @@ int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0
                  const float* W1, const float* b1, int od, float* out, cudaStream_t st) {
   cond_mlp_kernel<<<N, 256, (cd + hid) * sizeof(float), st>>>(cond, cd, pre_relu, W0, b0, hid, W1, b1, od, out);
   return check_launch("cond_mlp_kernel");
+}
+
+int dense_rows_run(const float* in, int N, int cd, int pre_relu, const float* W, const float* b, int od, int act, float* out,
+                   cudaStream_t st) {
+  const int vec = cd % 4 == 0 && (((uintptr_t)in | (uintptr_t)W) & 15) == 0;
+  if (N <= 0 || od <= 0) return 0;
+  constexpr int NF = 4;
+  dense_rows_kernel<NF><<<dim3(nblk(od, 8), nblk(N, NF)), 256, 0, st>>>(in, N, cd, pre_relu, W, b, od, act, out, vec);
+  return check_launch("dense_rows_kernel");
 }
 
 int stem_finish_run(int dtype, const StemParams& p, void* h1, float* res, cudaStream_t st) {

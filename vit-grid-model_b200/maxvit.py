@@ -175,13 +175,18 @@ class MaxViT(nn.Module):
         """'bf16'     : fp32 storage, projections on tcgen05 kind::tf32 (the MaxViT block dominates the rounding error
                         of the network, see DESIGN.md, so it keeps 10-bit mantissas; the 3x3 convs around it are bf16)
            'bf16_all' : bf16 storage and kind::f16 MMA everywhere (faster, ~2x the error)
-           'fp32'     : fp32 storage, exact-fp32 SIMT GEMMs"""
+           'fp32'     : fp32 storage, exact-fp32 SIMT GEMMs
+           'fp32_x3'  : fp32 storage, projections on the tensor cores by the 3xTF32 operand split (the MaxViT side of MetNet3's
+                        'tf32_conv' mode: 3e-6 .. 3e-5 of the largest output per GEMM, bounded by the truncating fp32 accumulation
+                        of the tensor core over 3K/8 instructions -- plain tf32 is 8e-4, the SIMT kernel 1e-6 -- and 9x faster
+                        than the SIMT GEMM at 512 channels)"""
         self.compute_dtype, self.tf32 = {"bf16": (torch.float32, True), "bf16_all": (torch.bfloat16, False),
-                                         "fp32": (torch.float32, False)}[precision]
+                                         "fp32": (torch.float32, False), "fp32_x3": (torch.float32, False)}[precision]
+        self.fp32_x3 = precision == "fp32_x3"
         return self
 
     def _pack_key(self, dtype):
-        return (dtype, tuple((p.data_ptr(), p._version) for p in self.parameters()),
+        return (dtype, self.fp32_x3, tuple((p.data_ptr(), p._version) for p in self.parameters()),
                 tuple((b.data_ptr(), b._version) for b in self.buffers()))
 
     @torch.no_grad()
@@ -229,6 +234,10 @@ class MaxViT(nn.Module):
                 if att.window_size == 7 and dh == 32:
                     P[name]["head_tab"] = ops.pack_head_tables(P[name]["bias_table"], P[name]["q_gamma"], P[name]["k_gamma"])
             P["reg"] = self.register_tokens[li].float().contiguous()
+            if self.fp32_x3 and dtype == torch.float32:              # 3xTF32 right operands [hi | lo | hi], split once per weight version
+                P["w_exp_x3"] = ops.split3_tf32(P["w_exp"], 1)
+                for name in ("block", "grid"):
+                    P[name]["w_qkv_x3"], P[name]["w_out_x3"] = ops.split3_tf32(P[name]["w_qkv"], 1), ops.split3_tf32(P[name]["w_out"], 1)
             layers.append(P)
         self._packed, self._packed_key = layers, key
         return layers
@@ -245,11 +254,12 @@ class MaxViT(nn.Module):
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
         # qkv_exact: the QKV projection alone in exact fp32 -- its rounding error is multiplied by the un-scaled logits
         # (+-32 gamma_q gamma_k, maxvit.py:26-30,203) before the softmax; every other contraction of the block stays tf32
-        qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32 and not getattr(self, "qkv_exact", False))
+        qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32 and not getattr(self, "qkv_exact", False), x3=self.fp32_x3, Wt_x3=P.get("w_qkv_x3"))
         del tokens
         att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head)
         del qkv
-        return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=self.tf32)
+        return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=self.tf32, x3=self.fp32_x3,
+                            Wt_x3=P.get("w_out_x3"))
 
     def forward_cl(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
         """channels-last entry used by MetNet3: x (N,H,W,dim) in the compute dtype, cond (N,cond_dim) fp32"""
@@ -270,7 +280,7 @@ class MaxViT(nn.Module):
             marching = n_hid % 4 == 0 and 128 % (n_hid // 4) == 0          # the fp16 depthwise kernel (hidden <= 512 channels)
             hid_dtype = torch.float16 if (self.tf32 and x.dtype == torch.float32 and marching) else None
             h = ops.gemm(x.view(N * H * W, C), P["w_exp"], scale=P["s_exp"], shift=P["t_exp"], act=1, tf32=self.tf32,
-                         out_dtype=hid_dtype)
+                         out_dtype=hid_dtype, x3=self.fp32_x3, Wt_x3=P.get("w_exp_x3"))
             hidden = h.shape[1]
             h2, psum = ops.dw3x3_bnact(h.view(N, H, W, hidden), P["w_dw"], P["s_dw"], P["t_dw"])
             del h
@@ -280,7 +290,7 @@ class MaxViT(nn.Module):
                 # read-modify-write pass over the hidden activations
                 wn = ops.se_fold_weights(P["w_proj"], gate, dtype=h2.dtype)
                 y = ops.gemm(h2.view(N * H * W, hidden), wn, rows_per_batch=H * W, b_rows_per_batch=P["w_proj"].shape[0], scale=P["s_proj"],
-                             shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32, out_f32=True)
+                             shift=P["t_proj"], res=x.view(N * H * W, C) if P["residual"] else None, tf32=self.tf32, out_f32=True, x3=self.fp32_x3)
             else:
                 ops.se_scale_(h2, gate)
                 y = ops.gemm(h2.view(N * H * W, hidden), P["w_proj"], scale=P["s_proj"], shift=P["t_proj"],

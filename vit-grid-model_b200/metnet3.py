@@ -160,7 +160,7 @@ class MetNet3(nn.Module):
         self.compute_dtype, self.precision, self.conv_tf32 = torch.bfloat16, "bf16", False
         if n_start_channels > 128:
             self.compute_dtype, self.precision, self.conv_tf32 = torch.float32, "tf32_conv", True
-            self.vit.set_precision("fp32")
+            self.vit.set_precision("fp32_x3")
         self.max_fields = {torch.bfloat16: 768, torch.float32: 48}
         self._packed, self._packed_key = None, None
         self._capture = None          # debugging: set to a dict to collect stage outputs (NCHW copies)
@@ -175,7 +175,8 @@ class MetNet3(nn.Module):
                         operands for the MaxViT block (default at 128 channels);
            'bf16_all' : bf16 everywhere;
            'tf32'     : fp32 storage, every contraction on tcgen05 kind::tf32;
-           'tf32_conv': fp32 storage, tf32 convolutions, exact-fp32 MaxViT block (default above 128 channels);
+           'tf32_conv': fp32 storage, tf32 convolutions, near-fp32 MaxViT block (its projections as 3xTF32 split products on the
+                        tensor cores, ~1e-5 per GEMM; attention core exact fp32; default above 128 channels);
            'fp32'     : exact-fp32 SIMT path.
         Wide networks default to 'tf32_conv': on BASELINE configs[4] (512 channels, 32 x 64 heads, depth 4, random weights) the
         modes measure 3.6e-2 (bf16), 1.4e-2 (tf32), 4.3e-3 (tf32_conv) and 2e-5 (fp32) against the oracle -- four stacked MaxViT
@@ -184,7 +185,7 @@ class MetNet3(nn.Module):
         self.compute_dtype = {"bf16": torch.bfloat16, "bf16_all": torch.bfloat16, "fp32": torch.float32, "tf32": torch.float32,
                               "tf32_conv": torch.float32}[precision]
         self.conv_tf32 = precision in ("tf32", "tf32_conv")
-        self.vit.set_precision({"tf32": "bf16", "tf32_conv": "fp32"}.get(precision, precision))
+        self.vit.set_precision({"tf32": "bf16", "tf32_conv": "fp32_x3"}.get(precision, precision))
         self.precision = precision
         self.invalidate_packed()
         return self
@@ -311,7 +312,7 @@ class MetNet3(nn.Module):
             cap["vit"] = low.permute(0, 3, 1, 2).float()
         # ---- decoder
         up = [b for b in bufs if b is not h][0]       # pads of every PG buffer are already zero (written by conv/stem)
-        ops.convT2(low, P["w_up_vit"], P["b_up"], up, tf32=self.vit.tf32, out_copy=skips[0] if mixed else None)
+        ops.convT2(low, P["w_up_vit"], P["b_up"], up, tf32=self.vit.tf32 or self.conv_tf32, out_copy=skips[0] if mixed else None)
         del low
         h, hs = up, (skips[0] if mixed else up)
         if cap is not None:

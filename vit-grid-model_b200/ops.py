@@ -107,14 +107,34 @@ def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
     hid = W0.shape[0]
     od = W1.shape[0] if W1 is not None else hid
     out = torch.empty(N, od, dtype=torch.float32, device=cond.device)
+    if W1 is not None and N <= 32 and hid >= 1024:      # few fields, wide layers (configs[4])
+        h = torch.empty(N, hid, dtype=torch.float32, device=cond.device)
+        _lib.call("vg_dense_rows_fwd", cond.data_ptr(), N, cd, int(pre_relu), W0.data_ptr(), _p(b0), hid, 2, h.data_ptr(), _st())
+        _lib.call("vg_dense_rows_fwd", h.data_ptr(), N, hid, 0, W1.data_ptr(), _p(b1), od, 0, out.data_ptr(), _st())
+        return out
     _lib.call("vg_cond_mlp_fwd", cond.data_ptr(), N, cd, int(pre_relu), W0.data_ptr(), _p(b0), hid, _p(W1), _p(b1), od,
               out.data_ptr(), _st())
     return out
 
 
+def split3_tf32(x, pattern):
+    """fp32 [rows][K] -> fp32 [rows][3K]: (hi | hi | lo) for the left operand (pattern 0), (hi | lo | hi) for the [N][K] weights
+    (pattern 1), hi = x truncated to tf32; one tf32 GEMM over 3K then computes hi*hi + hi*lo + lo*hi (include/vitgrid.h)"""
+    rows, K = x.shape
+    out = torch.empty(rows, 3 * K, dtype=torch.float32, device=x.device)
+    _lib.call("vg_split3_tf32", x.data_ptr(), rows, K, out.data_ptr(), int(pattern), _st())
+    return out
+
+
 def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per_batch=0, bias=None, scale=None,
-         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None, tf32=False, out_dtype=None):
-    """out_dtype=torch.float16: fp16 output from any operand type (the MBConv hidden tensor)"""
+         shift=None, act=0, res=None, out=None, out_f32=False, n_out=None, tf32=False, out_dtype=None, x3=False, Wt_x3=None):
+    """out_dtype=torch.float16: fp16 output from any operand type (the MBConv hidden tensor).
+    x3 (fp32 operands, no tf32): near-fp32 product (~1e-5, see include/vitgrid.h) on the tensor cores by the 3xTF32 operand split
+    instead of the SIMT kernel; Wt_x3: the weights already split (split3_tf32(Wt, 1), cached by the caller)"""
+    if x3 and not tf32 and A.dtype == torch.float32 and ntaps == 1 and A.is_contiguous() and Wt.is_contiguous() and A.shape[1] % 32 == 0:
+        return gemm(split3_tf32(A, 0), Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), M=M, rows_per_batch=rows_per_batch, b_rows_per_batch=b_rows_per_batch,
+                    bias=bias, scale=scale, shift=shift, act=act, res=res, out=out, out_f32=out_f32, n_out=n_out, tf32=True,
+                    out_dtype=out_dtype)
     dtype = A.dtype
     rowsA, Ca = A.shape
     M = rowsA if M is None else M
@@ -218,8 +238,12 @@ def se_gate(psum, HW, W1, W2):
     """psum: (N, nparts, C) partial channel sums over the HW pixels of each field"""
     N, nparts, C = psum.shape
     gate = torch.empty(N, C, dtype=torch.float32, device=psum.device)
+    mean = hid = None
+    if N <= 32 and C >= 1024:      # few fields, wide layers: the library runs the two layers as vg_dense_rows_fwd passes over (mean, hid)
+        mean = torch.empty(N, C, dtype=torch.float32, device=psum.device)
+        hid = torch.empty(N, W1.shape[0], dtype=torch.float32, device=psum.device)
     _lib.call("vg_se_gate_train_fwd", psum.data_ptr(), N, nparts, HW, W1.data_ptr(), W2.data_ptr(), C, W1.shape[0],
-              gate.data_ptr(), None, None, _st())
+              gate.data_ptr(), _p(mean), _p(hid), _st())
     return gate
 
 
@@ -258,7 +282,10 @@ def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, o
     return out
 
 
-def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False, drop=(0, 0, 0)):
+def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False, drop=(0, 0, 0), x3=False, Wt_x3=None):
+    if x3 and not tf32 and attn.dtype == torch.float32 and attn.shape[1] % 32 == 0:      # 3xTF32 (see gemm)
+        return attn_out(split3_tf32(attn, 0), Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=x_out,
+                        tf32=True, drop=drop)
     N, Hl, Wl, C = x_in.shape
     nwin = (Hl // win) * (Wl // win)
     if x_out is None:
