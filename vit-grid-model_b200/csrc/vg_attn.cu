@@ -84,87 +84,130 @@ __global__ void __launch_bounds__(256) attn_gather_kernel(const T* __restrict__ 
   }
 }
 
-// One warp per (window, head).  K-hat and V staged in shared memory as fp32, each lane owns query rows
-// lane and lane+32; single pass over the keys with an online softmax.
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4f(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// One block per (window, head), one query row per thread (ceil(S / 32) warps).  K-hat and V are staged in shared memory as fp32
+// rows of DH floats (pad rows up to a multiple of 4 are zeros): DH/4 lanes stage one row with 16-byte loads and stores, the
+// row norm by shuffles.  Every lane of a warp then reads the same key, so the reads are 16-byte broadcasts.  Keys go four at a
+// time through the online softmax: four scores (each four partial sums -- a single 64-long FMA chain was the latency bound of
+// the first version of this kernel, which also kept one (K, V) copy per warp: 113 KB per block, 8 warps per SM), one rescale
+// of the output row per four keys.  BASELINE configs[4] (32 heads x 64, 360 windows): 0.93 -> see profiles/r02_summary.md.
 template <typename T, int DH>
-__global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qkv, const float* __restrict__ qgamma,
+__global__ void __launch_bounds__(128, DH == 64 ? 3 : 5) attn_core_kernel(const T* __restrict__ qkv, const float* __restrict__ qgamma,
                                                         const float* __restrict__ kgamma, const float* __restrict__ bias_table,
-                                                        const AttnGeom g, int heads, T* __restrict__ out, long long pairs, const DropCfg drop) {
-  extern __shared__ float sm[];
-  const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sk = sm + warp * (2 * S * (DH + 1) + nb);
-  float* sv = sk + S * (DH + 1);
-  float* sbias = sv + S * (DH + 1);
-  const long long pair = (long long)blockIdx.x * 4 + warp;
-  if (pair >= pairs) return;
+                                                        const AttnGeom g, int heads, T* __restrict__ out, const DropCfg drop) {
+  extern __shared__ __align__(16) float sm[];
+  const int S = g.S(), Sp = (S + 3) & ~3, nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
+  const int lane = threadIdx.x & 31;
+  float* sk = sm;
+  float* sv = sk + Sp * DH;
+  float* sbias = sv + Sp * DH;
+  const long long pair = blockIdx.x;
   const long long wdx = pair / heads;
   const int hd = (int)(pair - wdx * heads);
   const int inner = heads * DH;
   const T* base = qkv + wdx * S * 3 * inner + hd * DH;
   const float rs = sqrtf((float)DH);
 
-  for (int i = lane; i < nb; i += 32) sbias[i] = bias_table[i * heads + hd];
-  // K-hat, V -> smem (row j handled by lane j, j+32)
-  for (int j = lane; j < S; j += 32) {
-    const T* kp = base + (long long)j * 3 * inner + inner;
-    const T* vp = kp + inner;
-    float kk[DH], nrm = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[i] = bias_table[i * heads + hd];
+  {
+    constexpr int LPR = DH / 4, RPP = 32 / LPR;              // lanes per row, rows per warp pass
+    const int sub = lane / LPR, ch = lane - sub * LPR;
+    const float4 kg = *reinterpret_cast<const float4*>(kgamma + hd * DH + ch * 4);
+    // all the loads of a batch of UNR passes are issued before the first norm: one global round trip per batch, not per pass
+    constexpr int UNR = 7;
+    const int step = (blockDim.x >> 5) * RPP;
+    for (int jb = (threadIdx.x >> 5) * RPP; jb < Sp; jb += step * UNR) {
+      float4 k[UNR], v[UNR];
 #pragma unroll
-    for (int d = 0; d < DH; d += 8) ld8(kp + d, kk + d);
+      for (int t = 0; t < UNR; ++t) {
+        const int j = jb + t * step + sub;
+        k[t] = make_float4(0.f, 0.f, 0.f, 0.f); v[t] = k[t];
+        if (j < S) { const T* kp = base + (long long)j * 3 * inner + inner + ch * 4; k[t] = ld4f(kp); v[t] = ld4f(kp + inner); }
+      }
 #pragma unroll
-    for (int d = 0; d < DH; ++d) nrm += kk[d] * kk[d];
-    const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);                  // F.normalize eps (maxvit.py:30)
+      for (int t = 0; t < UNR; ++t) {
+        if (jb + t * step < Sp) {                                // warp-uniform; then j < Sp too (Sp is a multiple of 4, RPP divides 4)
+          const int j = jb + t * step + sub;
+          float nrm = k[t].x * k[t].x + k[t].y * k[t].y + k[t].z * k[t].z + k[t].w * k[t].w;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) sk[j * (DH + 1) + d] = kk[d] * inv * kgamma[hd * DH + d];
-#pragma unroll
-    for (int d = 0; d < DH; d += 8) ld8(vp + d, kk + d);
-#pragma unroll
-    for (int d = 0; d < DH; ++d) sv[j * (DH + 1) + d] = kk[d];
+          for (int o = LPR / 2; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+          const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);      // F.normalize eps (maxvit.py:30)
+          *reinterpret_cast<float4*>(sk + j * DH + ch * 4) = make_float4(k[t].x * inv * kg.x, k[t].y * inv * kg.y, k[t].z * inv * kg.z, k[t].w * inv * kg.w);
+          *reinterpret_cast<float4*>(sv + j * DH + ch * 4) = v[t];
+        }
+      }
+    }
   }
-  __syncwarp();
+  __syncthreads();
 
+  const int i = threadIdx.x;
+  if (i >= S) return;
   const int W2 = 2 * g.win - 1;
-  for (int i = lane; i < S; i += 32) {
-    float q[DH], o[DH], nrm = 0.f;
-    const T* qp = base + (long long)i * 3 * inner;
+  float q[DH], o[DH], nrm = 0.f;
+  const T* qp = base + (long long)i * 3 * inner;
 #pragma unroll
-    for (int d = 0; d < DH; d += 8) ld8(qp + d, q + d);
+  for (int d = 0; d < DH; d += 8) ld8(qp + d, q + d);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) nrm += q[d] * q[d];
-    const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);
+  for (int d = 0; d < DH; ++d) nrm += q[d] * q[d];
+  const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) { q[d] *= inv * qgamma[hd * DH + d]; o[d] = 0.f; }
-    const int ti = i - g.R, ai = ti / g.win, bi = ti - ai * g.win;
-    float m = -INFINITY, l = 0.f;
-    uint32_t hsh = 0u;
-    for (int j = 0; j < S; ++j) {
-      // nn.Dropout on the probabilities (maxvit.py:146): the same counter-based mask as the fused kernels (vg_rng.cuh)
-      if (drop.thresh && (j & 3) == 0) hsh = drop_hash(drop.seed, drop_row(wdx, i), drop_group_prob(drop.salt, hd, j >> 2));
-      const float mk = !drop.thresh ? 1.0f : ((int)((hsh >> (8 * (j & 3))) & 255u) >= drop.thresh ? drop.scale : 0.f);
-      float sc = 0.f;
+  for (int d = 0; d < DH; ++d) { q[d] *= inv * qgamma[hd * DH + d]; o[d] = 0.f; }
+  const int ti = i - g.R, ai = ti / g.win, bi = ti - ai * g.win;
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < Sp; j0 += 4) {
+    // nn.Dropout on the probabilities (maxvit.py:146): the same counter-based mask as the fused kernels (vg_rng.cuh)
+    const uint32_t hsh = drop.thresh ? drop_hash(drop.seed, drop_row(wdx, i), drop_group_prob(drop.salt, hd, j0 >> 2)) : 0u;
+    float sc[4];
 #pragma unroll
-      for (int d = 0; d < DH; ++d) sc = fmaf(q[d], sk[j * (DH + 1) + d], sc);
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const float4* kr = reinterpret_cast<const float4*>(sk + j * DH);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        const float4 k = kr[c];
+        s0 = fmaf(q[4 * c], k.x, s0); s1 = fmaf(q[4 * c + 1], k.y, s1); s2 = fmaf(q[4 * c + 2], k.z, s2); s3 = fmaf(q[4 * c + 3], k.w, s3);
+      }
       int bidx = nb - 1;                                                 // register row/col -> shared last entry
-      if (i >= g.R && j >= g.R) {
+      if (i >= g.R && j >= g.R && j < S) {
         const int tj = j - g.R, aj = tj / g.win, bj = tj - aj * g.win;
         bidx = (ai - aj + g.win - 1) * W2 + (bi - bj + g.win - 1);
       }
-      sc += sbias[bidx];
-      const float mn = fmaxf(m, sc);
-      const float corr = __expf(m - mn), p = __expf(sc - mn);
-      l = l * corr + p;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = fmaf(p * mk, sv[j * (DH + 1) + d], o[d] * corr);      // the normaliser l stays un-dropped
-      m = mn;
+      sc[u] = j < S ? (s0 + s1) + (s2 + s3) + sbias[bidx] : -INFINITY;
     }
-    const float il = 1.0f / l;
+    const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));    // the first key of a group is always valid: finite
+    const float corr = __expf(m - mn);
+    float pm[4], ps = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] *= il;
-    T* op = out + (wdx * S + i) * inner + hd * DH;
+    for (int u = 0; u < 4; ++u) {
+      const float p = __expf(sc[u] - mn);
+      ps += p;                                                             // the normaliser l stays un-dropped
+      pm[u] = !drop.thresh ? p : ((int)((hsh >> (8 * u)) & 255u) >= drop.thresh ? p * drop.scale : 0.f);
+    }
+    l = l * corr + ps;
+    m = mn;
+    const float4* v0 = reinterpret_cast<const float4*>(sv + j0 * DH);
 #pragma unroll
-    for (int d = 0; d < DH; d += 8) st8(op + d, o + d);
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 a = v0[c], b = v0[c + DH / 4], cc = v0[c + 2 * (DH / 4)], dd = v0[c + 3 * (DH / 4)];
+      o[4 * c]     = fmaf(pm[0], a.x, fmaf(pm[1], b.x, fmaf(pm[2], cc.x, fmaf(pm[3], dd.x, o[4 * c] * corr))));
+      o[4 * c + 1] = fmaf(pm[0], a.y, fmaf(pm[1], b.y, fmaf(pm[2], cc.y, fmaf(pm[3], dd.y, o[4 * c + 1] * corr))));
+      o[4 * c + 2] = fmaf(pm[0], a.z, fmaf(pm[1], b.z, fmaf(pm[2], cc.z, fmaf(pm[3], dd.z, o[4 * c + 2] * corr))));
+      o[4 * c + 3] = fmaf(pm[0], a.w, fmaf(pm[1], b.w, fmaf(pm[2], cc.w, fmaf(pm[3], dd.w, o[4 * c + 3] * corr))));
+    }
   }
+  const float il = 1.0f / l;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) o[d] *= il;
+  T* op = out + (wdx * S + i) * inner + hd * DH;
+#pragma unroll
+  for (int d = 0; d < DH; d += 8) st8(op + d, o + d);
 }
 
 // out_bf16: fp32 residual stream in, bf16 tokens out (the mixed-precision training backward re-materialises tokens in 16 bits)
@@ -187,17 +230,18 @@ int attn_partition_debug_run(const AttnGeom& g, long long* out, cudaStream_t st)
 
 template <typename T, int DH>
 static int core_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, const DropCfg& drop, cudaStream_t st) {
-  const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
-  const size_t smem = 4 * (size_t)(2 * S * (DH + 1) + nb) * sizeof(float);
+  const int S = g.S(), Sp = (S + 3) & ~3, nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
+  const size_t smem = (size_t)(2 * Sp * DH + nb) * sizeof(float);
   static PerDeviceSize attr_pd;                             // the size depends on the window geometry: raise the limit when it grows
   size_t& attr_bytes = attr_pd.cur();
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_kernel<T, DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error("attn_core smem attr: %s", cudaGetErrorString(e));
     attr_bytes = smem;
   }
   const long long pairs = (long long)g.N * g.nwin() * heads;
-  attn_core_kernel<T, DH><<<(unsigned)((pairs + 3) / 4), 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), pairs, drop);
+  attn_core_kernel<T, DH><<<(unsigned)pairs, 32 * ((S + 31) / 32), smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), drop);
   return check_launch("attn_core_kernel");
 }
 
