@@ -588,3 +588,22 @@ def test_se_gate_wide_rows_path():
     mean = psum.double().sum(1) / HW
     want = torch.sigmoid(F.linear(F.relu(F.linear(mean, W1.double())), W2.double()))
     assert rel_err(ops().se_gate(psum, HW, W1, W2), want) < 1e-5
+
+
+@pytest.mark.parametrize("dh,heads", [(64, 8), (32, 4)])
+@pytest.mark.parametrize("N,H,W,w,R", [(2, 14, 21, 7, 4), (1, 16, 24, 8, 0), (3, 7, 7, 7, 4)])
+def test_attn_core_tensor_core_variants_match_exact_fp32(dh, heads, N, H, W, w, R):
+    """the mma.sync core (3xTF32 split products for fp32 tensors = precision 'tf32_conv'; single tf32 products for bf16 tensors) against
+    the exact-fp32 SIMT core on the same qkv: 2e-5 (split) and 1e-2 (bf16 storage) of the largest output"""
+    o = ops()
+    S, nwin = w * w + R, (H // w) * (W // w)
+    qkv = rnd(N * nwin * S, 3 * heads * dh, seed=1).cuda()
+    qg, kg = (1 + 0.2 * rnd(heads * dh, seed=2)).cuda(), (1 + 0.2 * rnd(heads * dh, seed=3)).cuda()
+    bt = rnd((2 * w - 1) ** 2 + 1, heads, seed=4).cuda()
+    exact = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh)
+    split = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, x3=True)
+    assert rel_err(split, exact) < 2e-5
+    q16 = qkv.bfloat16()
+    exact16 = o.attn_core(q16.float(), qg, kg, bt, N, H, W, w, R, heads, dh)
+    assert rel_err(o.attn_core(q16, qg, kg, bt, N, H, W, w, R, heads, dh), exact16) < 1e-2
+    assert rel_err(o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, tf32=True), exact) < 1e-2      # fp32 storage, single tf32 products

@@ -210,6 +210,180 @@ __global__ void __launch_bounds__(128, DH == 64 ? 3 : 5) attn_core_kernel(const 
   for (int d = 0; d < DH; d += 8) st8(op + d, o + d);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same core on the tensor cores for the shapes of the un-fused path (S <= 64, no dropout): mma.sync m16n8k8 tf32, one block
+// of four warps per (window, head), 16 query rows per warp.  SPLIT: every product as three tf32 products of the operands' hi / lo
+// halves (hi*hi + hi*lo + lo*hi: fp32-grade, 24 accumulation steps per score) -- the 'tf32_conv' precision of wide networks; without
+// SPLIT one tf32 product (10-bit operands, for bf16 storage).  K-hat and V sit in shared memory as fp32 rows of DH + 4 floats:
+// the B-fragment reads (key g, dim t) and (key 2t, dim g) both touch 32 different banks.  The accumulator fragment of S holds keys
+// (2t, 2t+1) of every 8-key tile where the A fragment of the next product wants (t, t+4): instead of moving P between lanes the
+// contraction index of P.V is permuted -- the V fragment is read at keys (8k + 2t, 8k + 2t + 1).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u; }
+
+template <typename T, int DH, bool SPLIT>
+__global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ qgamma,
+                                                            const float* __restrict__ kgamma, const float* __restrict__ bias_table,
+                                                            const AttnGeom g, int heads, T* __restrict__ out) {
+  constexpr int LD = DH + 4, KT = DH / 8;
+  extern __shared__ __align__(16) float sm[];
+  float* sk = sm;
+  float* sv = sk + 64 * LD;
+  float* sbias = sv + 64 * LD;
+  int* skey = reinterpret_cast<int*>(sbias + (((2 * g.win - 1) * (2 * g.win - 1) + 1 + 3) & ~3));     // [64]: key -> (aj << 8 | bj), -1 = register token
+  const int S = g.S(), nb = (2 * g.win - 1) * (2 * g.win - 1) + 1, W2 = 2 * g.win - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pair = blockIdx.x;
+  const long long wdx = pair / heads;
+  const int hd = (int)(pair - wdx * heads);
+  const int inner = heads * DH;
+  const T* base = qkv + wdx * S * 3 * inner + hd * DH;
+  const float rs = sqrtf((float)DH);
+
+  for (int i = threadIdx.x; i < nb; i += 128) sbias[i] = bias_table[i * heads + hd];
+  if (threadIdx.x < 64) {
+    const int tj = (int)threadIdx.x - g.R, aj = tj / g.win;
+    skey[threadIdx.x] = tj < 0 ? -1 : ((aj << 8) | (tj - aj * g.win));
+  }
+  {
+    constexpr int LPR = DH / 4, RPP = 32 / LPR, UNR = 64 / (4 * RPP);      // the block stages 64 rows in UNR passes of 4 * RPP rows
+    const int sub = lane / LPR, ch = lane - sub * LPR;
+    const float4 kg = *reinterpret_cast<const float4*>(kgamma + hd * DH + ch * 4);
+    float4 k[UNR], v[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      const int j = (t * 4 + warp) * RPP + sub;
+      k[t] = make_float4(0.f, 0.f, 0.f, 0.f); v[t] = k[t];
+      if (j < S) { const T* kp = base + (long long)j * 3 * inner + inner + ch * 4; k[t] = ld4f(kp); v[t] = ld4f(kp + inner); }
+    }
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      const int j = (t * 4 + warp) * RPP + sub;
+      float nrm = k[t].x * k[t].x + k[t].y * k[t].y + k[t].z * k[t].z + k[t].w * k[t].w;
+#pragma unroll
+      for (int o = LPR / 2; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+      const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);        // F.normalize eps (maxvit.py:30); pad rows stay zero
+      *reinterpret_cast<float4*>(sk + j * LD + ch * 4) = make_float4(k[t].x * inv * kg.x, k[t].y * inv * kg.y, k[t].z * inv * kg.z, k[t].w * inv * kg.w);
+      *reinterpret_cast<float4*>(sv + j * LD + ch * 4) = v[t];
+    }
+  }
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (r0 >= S) return;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int i0 = r0 + gq, i1 = i0 + 8;
+
+  // Q-hat fragments: this thread holds dims t4 + 4m of rows i0 and i1 (the four lanes of a quad cover a row)
+  uint32_t qh[2][2 * KT], ql[SPLIT ? 2 : 1][SPLIT ? 2 * KT : 1];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = r ? i1 : i0;
+    float q[2 * KT], nrm = 0.f;
+    const T* qp = base + (long long)i * 3 * inner;
+#pragma unroll
+    for (int m = 0; m < 2 * KT; ++m) { q[m] = i < S ? (float)qp[t4 + 4 * m] : 0.f; nrm = fmaf(q[m], q[m], nrm); }
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
+    const float inv = rs / fmaxf(sqrtf(nrm), 1e-12f);
+#pragma unroll
+    for (int m = 0; m < 2 * KT; ++m) {
+      const float x = q[m] * inv * qgamma[hd * DH + t4 + 4 * m];
+      qh[r][m] = tf32_hi(x);
+      if (SPLIT) ql[r][m] = tf32_lo(x, qh[r][m]);
+    }
+  }
+
+  float sacc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+    const float* kr = sk + (8 * nt + gq) * LD + t4;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const float k0 = kr[8 * kt], k1 = kr[8 * kt + 4];
+      const uint32_t b0 = tf32_hi(k0), b1 = tf32_hi(k1);
+      if (SPLIT) {
+        const uint32_t c0 = tf32_lo(k0, b0), c1 = tf32_lo(k1, b1);
+        mma_tf32(sacc[nt], ql[0][2 * kt], ql[1][2 * kt], ql[0][2 * kt + 1], ql[1][2 * kt + 1], b0, b1);
+        mma_tf32(sacc[nt], qh[0][2 * kt], qh[1][2 * kt], qh[0][2 * kt + 1], qh[1][2 * kt + 1], c0, c1);
+      }
+      mma_tf32(sacc[nt], qh[0][2 * kt], qh[1][2 * kt], qh[0][2 * kt + 1], qh[1][2 * kt + 1], b0, b1);
+    }
+  }
+
+  // bias, mask of the pad keys, softmax over the row (16 keys per thread and row, the quad holds the row)
+  const int ti0 = i0 - g.R, ai0 = ti0 / g.win, bi0 = ti0 - ai0 * g.win;
+  const int ti1 = i1 - g.R, ai1 = ti1 / g.win, bi1 = ti1 - ai1 * g.win;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = 8 * nt + 2 * t4 + e;
+      const int kj = skey[j];
+      const int aj = kj >> 8, bj = kj & 255;
+      const int x0 = (ti0 < 0 || kj < 0 || i0 >= S) ? nb - 1 : (ai0 - aj + g.win - 1) * W2 + (bi0 - bj + g.win - 1);
+      const int x1 = (ti1 < 0 || kj < 0 || i1 >= S) ? nb - 1 : (ai1 - aj + g.win - 1) * W2 + (bi1 - bj + g.win - 1);
+      sacc[nt][e] = j < S ? sacc[nt][e] + sbias[x0] : -INFINITY;
+      sacc[nt][2 + e] = j < S ? sacc[nt][2 + e] + sbias[x1] : -INFINITY;
+      m0 = fmaxf(m0, sacc[nt][e]); m1 = fmaxf(m1, sacc[nt][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sacc[nt][e] = __expf(sacc[nt][e] - m0); l0 += sacc[nt][e];
+      sacc[nt][2 + e] = __expf(sacc[nt][2 + e] - m1); l1 += sacc[nt][2 + e];
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float il0 = 1.0f / l0, il1 = 1.0f / l1;
+
+  // P (normalised) as the A operand: key tile ks, fragment columns (t, t+4) = keys (8ks + 2t, 8ks + 2t + 1)
+  uint32_t ph[8][4], pl[SPLIT ? 8 : 1][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float p0 = sacc[ks][0] * il0, p1 = sacc[ks][2] * il1, p2 = sacc[ks][1] * il0, p3 = sacc[ks][3] * il1;
+    ph[ks][0] = tf32_hi(p0); ph[ks][1] = tf32_hi(p1); ph[ks][2] = tf32_hi(p2); ph[ks][3] = tf32_hi(p3);
+    if (SPLIT) { pl[ks][0] = tf32_lo(p0, ph[ks][0]); pl[ks][1] = tf32_lo(p1, ph[ks][1]); pl[ks][2] = tf32_lo(p2, ph[ks][2]); pl[ks][3] = tf32_lo(p3, ph[ks][3]); }
+  }
+  T* op0 = out + (wdx * S + i0) * inner + hd * DH + 2 * t4;
+  T* op1 = out + (wdx * S + i1) * inner + hd * DH + 2 * t4;
+#pragma unroll
+  for (int nd = 0; nd < KT; ++nd) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* vr = sv + (2 * t4) * LD + 8 * nd + gq;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const float v0 = vr[8 * ks * LD], v1 = vr[8 * ks * LD + LD];
+      const uint32_t b0 = tf32_hi(v0), b1 = tf32_hi(v1);
+      if (SPLIT) {
+        const uint32_t c0 = tf32_lo(v0, b0), c1 = tf32_lo(v1, b1);
+        mma_tf32(o, pl[ks][0], pl[ks][1], pl[ks][2], pl[ks][3], b0, b1);
+        mma_tf32(o, ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], c0, c1);
+      }
+      mma_tf32(o, ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], b0, b1);
+    }
+    if constexpr (sizeof(T) == 4) {
+      if (i0 < S) *reinterpret_cast<float2*>(op0 + 8 * nd) = make_float2(o[0], o[1]);
+      if (i1 < S) *reinterpret_cast<float2*>(op1 + 8 * nd) = make_float2(o[2], o[3]);
+    } else {
+      if (i0 < S) *reinterpret_cast<__nv_bfloat162*>(op0 + 8 * nd) = __floats2bfloat162_rn(o[0], o[1]);
+      if (i1 < S) *reinterpret_cast<__nv_bfloat162*>(op1 + 8 * nd) = __floats2bfloat162_rn(o[2], o[3]);
+    }
+  }
+}
+
 // out_bf16: fp32 residual stream in, bf16 tokens out (the mixed-precision training backward re-materialises tokens in 16 bits)
 int attn_gather_run(int dtype, const void* x, const float* reg, int reg_per_field, const float* film, const AttnGeom& g,
                     float eps, void* tokens, int out_bf16, cudaStream_t st) {
@@ -245,12 +419,41 @@ static int core_launch(const void* qkv, const float* qg, const float* kg, const 
   return check_launch("attn_core_kernel");
 }
 
+template <typename T, int DH, bool SPLIT>
+static int core_mma_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, cudaStream_t st) {
+  const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
+  const size_t smem = (size_t)(2 * 64 * (DH + 4) + ((nb + 3) & ~3) + 64) * sizeof(float);
+  static PerDeviceSize attr_pd;
+  size_t& attr_bytes = attr_pd.cur();
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_mma_kernel<T, DH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_mma_kernel<T, DH, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_error("attn_core (mma) smem attr: %s", cudaGetErrorString(e));
+    attr_bytes = smem;
+  }
+  const long long pairs = (long long)g.N * g.nwin() * heads;
+  attn_core_mma_kernel<T, DH, SPLIT><<<(unsigned)pairs, 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out));
+  return check_launch("attn_core_mma_kernel");
+}
+
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
                   const AttnGeom& g, int heads, int dh, void* out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
   if (g.S() > 128) return set_error("attn_core: sequence %d too long", g.S());
   if (drop_thresh < 0 || drop_thresh > 255 || (drop_thresh && g.S() > 64)) return set_error("attn_core: bad dropout threshold %d (or sequence > 64)", drop_thresh);
   DropCfg drop;
   drop.seed = seed; drop.salt = salt; drop.thresh = drop_thresh; drop.scale = 256.0f / (256.0f - (float)drop_thresh);
+  // dtype 2 = fp32 storage with 3xTF32 tensor-core products (the 'tf32_conv' precision of wide networks); dtype 4 = fp32 storage and
+  // bf16 storage (0) take single tf32 products (the mixed-precision modes).  Shapes outside the mma kernel (S > 64, attention dropout) and exact fp32 (dtype 1) run the SIMT kernel.
+  static const bool mma_off = getenv("VG_ATTN_CORE_MMA") && atoi(getenv("VG_ATTN_CORE_MMA")) == 0;
+  if (dtype != 1 && !mma_off && drop_thresh == 0 && g.S() <= 64 && g.win <= 64) {
+    if (dh == 64) return dtype == 0 ? core_mma_launch<bf16, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
+                       : dtype == 4 ? core_mma_launch<float, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
+                                    : core_mma_launch<float, 64, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
+    if (dh == 32) return dtype == 0 ? core_mma_launch<bf16, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
+                       : dtype == 4 ? core_mma_launch<float, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
+                                    : core_mma_launch<float, 32, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
+  }
+  if (dtype == 2 || dtype == 4) dtype = 1;
   if (dh == 32) return dtype == 0 ? core_launch<bf16, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st)
                                   : core_launch<float, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st);
   if (dh == 64) return dtype == 0 ? core_launch<bf16, 64>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st)

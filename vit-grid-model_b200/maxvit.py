@@ -256,7 +256,7 @@ class MaxViT(nn.Module):
         # (+-32 gamma_q gamma_k, maxvit.py:26-30,203) before the softmax; every other contraction of the block stays tf32
         qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32 and not getattr(self, "qkv_exact", False), x3=self.fp32_x3, Wt_x3=P.get("w_qkv_x3"))
         del tokens
-        att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head)
+        att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head, x3=self.fp32_x3, tf32=self.tf32)
         del qkv
         return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=self.tf32, x3=self.fp32_x3,
                             Wt_x3=P.get("w_out_x3"))

@@ -107,7 +107,7 @@ def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
     hid = W0.shape[0]
     od = W1.shape[0] if W1 is not None else hid
     out = torch.empty(N, od, dtype=torch.float32, device=cond.device)
-    if W1 is not None and N <= 32 and hid >= 1024:      # few fields, wide layers (configs[4])
+    if W1 is not None and N <= 1024 and hid >= 1024:    # wide layers (configs[4])
         h = torch.empty(N, hid, dtype=torch.float32, device=cond.device)
         _lib.call("vg_dense_rows_fwd", cond.data_ptr(), N, cd, int(pre_relu), W0.data_ptr(), _p(b0), hid, 2, h.data_ptr(), _st())
         _lib.call("vg_dense_rows_fwd", h.data_ptr(), N, hid, 0, W1.data_ptr(), _p(b1), od, 0, out.data_ptr(), _st())
@@ -239,7 +239,7 @@ def se_gate(psum, HW, W1, W2):
     N, nparts, C = psum.shape
     gate = torch.empty(N, C, dtype=torch.float32, device=psum.device)
     mean = hid = None
-    if N <= 32 and C >= 1024:      # few fields, wide layers: the library runs the two layers as vg_dense_rows_fwd passes over (mean, hid)
+    if N <= 1024 and C >= 1024:    # wide layers: the library runs the two layers as vg_dense_rows_fwd passes over (mean, hid)
         mean = torch.empty(N, C, dtype=torch.float32, device=psum.device)
         hid = torch.empty(N, W1.shape[0], dtype=torch.float32, device=psum.device)
     _lib.call("vg_se_gate_train_fwd", psum.data_ptr(), N, nparts, HW, W1.data_ptr(), W2.data_ptr(), C, W1.shape[0],
@@ -274,10 +274,15 @@ def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None, out_bf16=Fa
     return out
 
 
-def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None, drop=(0, 0, 0)):
+def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None, drop=(0, 0, 0), x3=False, tf32=False):
+    """fp32 tensors: x3 = QK^T and PV as 3xTF32 split products on the tensor cores (dtype code 2), tf32 = single tf32 products (code 4),
+    neither = exact-fp32 FMAs"""
     if out is None:
         out = torch.empty(qkv.shape[0], heads * dh, dtype=qkv.dtype, device=qkv.device)
-    _lib.call("vg_attn_core_fwd", DT_CODE[qkv.dtype], qkv.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
+    code = DT_CODE[qkv.dtype]
+    if qkv.dtype == torch.float32 and (x3 or tf32):
+        code = 4 if tf32 else 2
+    _lib.call("vg_attn_core_fwd", code, qkv.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
               bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, out.data_ptr(), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return out
 
