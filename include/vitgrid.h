@@ -181,7 +181,7 @@ VG_API int vg_attn_gather_fwd(int dtype, const void* x, const float* reg, int re
  * (table (2w-1)^2+1 x heads, fp32), softmax, PV.  qkv [(Nw*S)][3*heads*dh] -> out [(Nw*S)][heads*dh].
  * dtype 0: bf16 tensors (tf32 mma products, fp32 softmax); 1: fp32 tensors, exact-fp32 FMAs; 2: fp32 tensors, QK^T and PV as 3xTF32
  * split products on the tensor cores (mma.sync; fp32-grade: 24 accumulation steps per score); 4: fp32 tensors, single tf32 products (the
- * mixed-precision modes).  Dropout and S > 64 run the SIMT kernel. */
+ * mixed-precision modes); 6: as 2, with out [(Nw*S)][3*heads*dh] written as the split operand [hi | hi | lo] of vg_split3_tf32 (pattern 0).  Dropout and S > 64 run the SIMT kernel. */
 VG_API int vg_attn_core_fwd(int dtype, const void* qkv, const float* q_gamma, const float* k_gamma,
                      const float* bias_table, int N, int Hl, int Wl, int win, int R, int heads, int dh, void* out,
                      long long drop_seed, int drop_salt, int drop_thresh, void* stream);

@@ -607,3 +607,15 @@ def test_attn_core_tensor_core_variants_match_exact_fp32(dh, heads, N, H, W, w, 
     exact16 = o.attn_core(q16.float(), qg, kg, bt, N, H, W, w, R, heads, dh)
     assert rel_err(o.attn_core(q16, qg, kg, bt, N, H, W, w, R, heads, dh), exact16) < 1e-2
     assert rel_err(o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, tf32=True), exact) < 1e-2      # fp32 storage, single tf32 products
+
+
+def test_attn_core_split_output_is_the_split_of_the_plain_output():
+    """dtype code 6: the core writes its rows as [hi | hi | lo] -- bit for bit what vg_split3_tf32 makes of the plain (code 2) output"""
+    o = ops()
+    N, H, W, w, R, heads, dh = 2, 14, 21, 7, 4, 8, 64
+    qkv = rnd(N * 6 * (w * w + R), 3 * heads * dh, seed=1).cuda()
+    qg, kg = (1 + 0.2 * rnd(heads * dh, seed=2)).cuda(), (1 + 0.2 * rnd(heads * dh, seed=3)).cuda()
+    bt = rnd((2 * w - 1) ** 2 + 1, heads, seed=4).cuda()
+    plain = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, x3=True)
+    split = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, x3=True, split_out=True)
+    assert torch.equal(split, o.split3_tf32(plain, 0))

@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __flo
 template <typename T, int DH, bool SPLIT>
 __global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ qgamma,
                                                             const float* __restrict__ kgamma, const float* __restrict__ bias_table,
-                                                            const AttnGeom g, int heads, T* __restrict__ out) {
+                                                            const AttnGeom g, int heads, T* __restrict__ out, int out_split) {
   constexpr int LD = DH + 4, KT = DH / 8;
   extern __shared__ __align__(16) float sm[];
   float* sk = sm;
@@ -357,8 +357,10 @@ __global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict_
     ph[ks][0] = tf32_hi(p0); ph[ks][1] = tf32_hi(p1); ph[ks][2] = tf32_hi(p2); ph[ks][3] = tf32_hi(p3);
     if (SPLIT) { pl[ks][0] = tf32_lo(p0, ph[ks][0]); pl[ks][1] = tf32_lo(p1, ph[ks][1]); pl[ks][2] = tf32_lo(p2, ph[ks][2]); pl[ks][3] = tf32_lo(p3, ph[ks][3]); }
   }
-  T* op0 = out + (wdx * S + i0) * inner + hd * DH + 2 * t4;
-  T* op1 = out + (wdx * S + i1) * inner + hd * DH + 2 * t4;
+  // out_split (fp32): the row is written as the left operand of a 3xTF32 GEMM, [hi | hi | lo] (vg_split3_tf32 pattern 0), 3 * inner long
+  const int ldo = out_split ? 3 * inner : inner;
+  T* op0 = out + (wdx * S + i0) * ldo + hd * DH + 2 * t4;
+  T* op1 = out + (wdx * S + i1) * ldo + hd * DH + 2 * t4;
 #pragma unroll
   for (int nd = 0; nd < KT; ++nd) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -375,8 +377,24 @@ __global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict_
       mma_tf32(o, ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], b0, b1);
     }
     if constexpr (sizeof(T) == 4) {
-      if (i0 < S) *reinterpret_cast<float2*>(op0 + 8 * nd) = make_float2(o[0], o[1]);
-      if (i1 < S) *reinterpret_cast<float2*>(op1 + 8 * nd) = make_float2(o[2], o[3]);
+      if (out_split) {
+        float h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __uint_as_float(__float_as_uint(o[e]) & 0xffffe000u);
+        if (i0 < S) {
+          *reinterpret_cast<float2*>(op0 + 8 * nd) = make_float2(h[0], h[1]);
+          *reinterpret_cast<float2*>(op0 + inner + 8 * nd) = make_float2(h[0], h[1]);
+          *reinterpret_cast<float2*>(op0 + 2 * inner + 8 * nd) = make_float2(o[0] - h[0], o[1] - h[1]);
+        }
+        if (i1 < S) {
+          *reinterpret_cast<float2*>(op1 + 8 * nd) = make_float2(h[2], h[3]);
+          *reinterpret_cast<float2*>(op1 + inner + 8 * nd) = make_float2(h[2], h[3]);
+          *reinterpret_cast<float2*>(op1 + 2 * inner + 8 * nd) = make_float2(o[2] - h[2], o[3] - h[3]);
+        }
+      } else {
+        if (i0 < S) *reinterpret_cast<float2*>(op0 + 8 * nd) = make_float2(o[0], o[1]);
+        if (i1 < S) *reinterpret_cast<float2*>(op1 + 8 * nd) = make_float2(o[2], o[3]);
+      }
     } else {
       if (i0 < S) *reinterpret_cast<__nv_bfloat162*>(op0 + 8 * nd) = __floats2bfloat162_rn(o[0], o[1]);
       if (i1 < S) *reinterpret_cast<__nv_bfloat162*>(op1 + 8 * nd) = __floats2bfloat162_rn(o[2], o[3]);
@@ -420,7 +438,7 @@ static int core_launch(const void* qkv, const float* qg, const float* kg, const 
 }
 
 template <typename T, int DH, bool SPLIT>
-static int core_mma_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, cudaStream_t st) {
+static int core_mma_launch(const void* qkv, const float* qg, const float* kg, const float* bt, const AttnGeom& g, int heads, void* out, int out_split, cudaStream_t st) {
   const int nb = (2 * g.win - 1) * (2 * g.win - 1) + 1;
   const size_t smem = (size_t)(2 * 64 * (DH + 4) + ((nb + 3) & ~3) + 64) * sizeof(float);
   static PerDeviceSize attr_pd;
@@ -432,7 +450,7 @@ static int core_mma_launch(const void* qkv, const float* qg, const float* kg, co
     attr_bytes = smem;
   }
   const long long pairs = (long long)g.N * g.nwin() * heads;
-  attn_core_mma_kernel<T, DH, SPLIT><<<(unsigned)pairs, 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out));
+  attn_core_mma_kernel<T, DH, SPLIT><<<(unsigned)pairs, 128, smem, st>>>(reinterpret_cast<const T*>(qkv), qg, kg, bt, g, heads, reinterpret_cast<T*>(out), out_split);
   return check_launch("attn_core_mma_kernel");
 }
 
@@ -445,13 +463,16 @@ int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* 
   // dtype 2 = fp32 storage with 3xTF32 tensor-core products (the 'tf32_conv' precision of wide networks); dtype 4 = fp32 storage and
   // bf16 storage (0) take single tf32 products (the mixed-precision modes).  Shapes outside the mma kernel (S > 64, attention dropout) and exact fp32 (dtype 1) run the SIMT kernel.
   static const bool mma_off = getenv("VG_ATTN_CORE_MMA") && atoi(getenv("VG_ATTN_CORE_MMA")) == 0;
+  const int out_split = dtype == 6;                        // dtype 6 = 2 with the output rows as the split operand [hi | hi | lo]
+  if (out_split) dtype = 2;
+  if (out_split && (mma_off || drop_thresh || g.S() > 64 || (dh != 32 && dh != 64))) return set_error("attn_core: the split output (dtype 6) needs the tensor-core kernel (S <= 64, dim_head 32 / 64, no dropout)");
   if (dtype != 1 && !mma_off && drop_thresh == 0 && g.S() <= 64 && g.win <= 64) {
-    if (dh == 64) return dtype == 0 ? core_mma_launch<bf16, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                       : dtype == 4 ? core_mma_launch<float, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                                    : core_mma_launch<float, 64, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
-    if (dh == 32) return dtype == 0 ? core_mma_launch<bf16, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                       : dtype == 4 ? core_mma_launch<float, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, st)
-                                    : core_mma_launch<float, 32, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, st);
+    if (dh == 64) return dtype == 0 ? core_mma_launch<bf16, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, 0, st)
+                       : dtype == 4 ? core_mma_launch<float, 64, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, out_split, st)
+                                    : core_mma_launch<float, 64, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, out_split, st);
+    if (dh == 32) return dtype == 0 ? core_mma_launch<bf16, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, 0, st)
+                       : dtype == 4 ? core_mma_launch<float, 32, false>(qkv, qgamma, kgamma, bias_table, g, heads, out, out_split, st)
+                                    : core_mma_launch<float, 32, true>(qkv, qgamma, kgamma, bias_table, g, heads, out, out_split, st);
   }
   if (dtype == 2 || dtype == 4) dtype = 1;
   if (dh == 32) return dtype == 0 ? core_launch<bf16, 32>(qkv, qgamma, kgamma, bias_table, g, heads, out, drop, st)

@@ -256,10 +256,12 @@ class MaxViT(nn.Module):
         # (+-32 gamma_q gamma_k, maxvit.py:26-30,203) before the softmax; every other contraction of the block stays tf32
         qkv = ops.gemm(tokens, P["w_qkv"], tf32=self.tf32 and not getattr(self, "qkv_exact", False), x3=self.fp32_x3, Wt_x3=P.get("w_qkv_x3"))
         del tokens
-        att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head, x3=self.fp32_x3, tf32=self.tf32)
+        split = self.fp32_x3 and qkv.dtype == torch.float32 and w * w + R <= 64 and self.dim_head in (32, 64)
+        att = ops.attn_core(qkv, P["q_gamma"], P["k_gamma"], P["bias_table"], N, H, W, w, R, self.heads, self.dim_head, x3=self.fp32_x3, tf32=self.tf32,
+                            split_out=split)
         del qkv
         return ops.attn_out(att, P["w_out"], x, reg_in, w, R, grid_mode, want_reg_out, tf32=self.tf32, x3=self.fp32_x3,
-                            Wt_x3=P.get("w_out_x3"))
+                            Wt_x3=P.get("w_out_x3"), attn_is_split=split)
 
     def forward_cl(self, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
         """channels-last entry used by MetNet3: x (N,H,W,dim) in the compute dtype, cond (N,cond_dim) fp32"""

@@ -274,20 +274,28 @@ def attn_gather(x, reg, film, win, R, grid_mode, eps=1e-5, out=None, out_bf16=Fa
     return out
 
 
-def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None, drop=(0, 0, 0), x3=False, tf32=False):
+def attn_core(qkv, q_gamma, k_gamma, bias_table, N, Hl, Wl, win, R, heads, dh, out=None, drop=(0, 0, 0), x3=False, tf32=False, split_out=False):
     """fp32 tensors: x3 = QK^T and PV as 3xTF32 split products on the tensor cores (dtype code 2), tf32 = single tf32 products (code 4),
-    neither = exact-fp32 FMAs"""
+    neither = exact-fp32 FMAs.  split_out (with x3, S <= 64): the output rows are written as [hi | hi | lo] (3 * heads * dh long), the left
+    operand of the 3xTF32 out-projection, instead of a split3_tf32 pass over them (code 6)"""
+    if split_out:
+        assert x3 and qkv.dtype == torch.float32 and out is None and win * win + R <= 64 and not drop[2]
+        out = torch.empty(qkv.shape[0], 3 * heads * dh, dtype=qkv.dtype, device=qkv.device)
     if out is None:
         out = torch.empty(qkv.shape[0], heads * dh, dtype=qkv.dtype, device=qkv.device)
     code = DT_CODE[qkv.dtype]
     if qkv.dtype == torch.float32 and (x3 or tf32):
-        code = 4 if tf32 else 2
+        code = 4 if tf32 else (6 if split_out else 2)
     _lib.call("vg_attn_core_fwd", code, qkv.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(),
               bias_table.data_ptr(), N, Hl, Wl, win, R, heads, dh, out.data_ptr(), int(drop[0]), int(drop[1]), int(drop[2]), _st())
     return out
 
 
-def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False, drop=(0, 0, 0), x3=False, Wt_x3=None):
+def attn_out(attn, Wt, x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=None, tf32=False, drop=(0, 0, 0), x3=False, Wt_x3=None,
+             attn_is_split=False):
+    if attn_is_split:                                                                   # attn_core(split_out=True) wrote [hi | hi | lo] rows
+        return attn_out(attn, Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=x_out,
+                        tf32=True, drop=drop)
     if x3 and not tf32 and attn.dtype == torch.float32 and attn.shape[1] % 32 == 0:      # 3xTF32 (see gemm)
         return attn_out(split3_tf32(attn, 0), Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), x_in, reg_in, win, R, grid_mode, want_reg_out, x_out=x_out,
                         tf32=True, drop=drop)
