@@ -298,14 +298,17 @@ __global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict_
     }
   }
 
+  // consecutive MMAs go to different accumulators (the asm statements keep their order: a key-tile-outer loop would issue 3 * KT
+  // dependent MMAs back to back)
   float sacc[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-    const float* kr = sk + (8 * nt + gq) * LD + t4;
+  for (int nt = 0; nt < 8; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      const float k0 = kr[8 * kt], k1 = kr[8 * kt + 4];
+  for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float* kr = sk + (8 * nt + gq) * LD + t4 + 8 * kt;
+      const float k0 = kr[0], k1 = kr[4];
       const uint32_t b0 = tf32_hi(k0), b1 = tf32_hi(k1);
       if (SPLIT) {
         const uint32_t c0 = tf32_lo(k0, b0), c1 = tf32_lo(k1, b1);
@@ -361,21 +364,27 @@ __global__ void __launch_bounds__(128) attn_core_mma_kernel(const T* __restrict_
   const int ldo = out_split ? 3 * inner : inner;
   T* op0 = out + (wdx * S + i0) * ldo + hd * DH + 2 * t4;
   T* op1 = out + (wdx * S + i1) * ldo + hd * DH + 2 * t4;
+  float oacc[KT][4];
 #pragma unroll
-  for (int nd = 0; nd < KT; ++nd) {
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* vr = sv + (2 * t4) * LD + 8 * nd + gq;
+  for (int nd = 0; nd < KT; ++nd) oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const float v0 = vr[8 * ks * LD], v1 = vr[8 * ks * LD + LD];
+  for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+    for (int nd = 0; nd < KT; ++nd) {
+      const float* vr = sv + (8 * ks + 2 * t4) * LD + 8 * nd + gq;
+      const float v0 = vr[0], v1 = vr[LD];
       const uint32_t b0 = tf32_hi(v0), b1 = tf32_hi(v1);
       if (SPLIT) {
         const uint32_t c0 = tf32_lo(v0, b0), c1 = tf32_lo(v1, b1);
-        mma_tf32(o, pl[ks][0], pl[ks][1], pl[ks][2], pl[ks][3], b0, b1);
-        mma_tf32(o, ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], c0, c1);
+        mma_tf32(oacc[nd], pl[ks][0], pl[ks][1], pl[ks][2], pl[ks][3], b0, b1);
+        mma_tf32(oacc[nd], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], c0, c1);
       }
-      mma_tf32(o, ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], b0, b1);
+      mma_tf32(oacc[nd], ph[ks][0], ph[ks][1], ph[ks][2], ph[ks][3], b0, b1);
     }
+  }
+#pragma unroll
+  for (int nd = 0; nd < KT; ++nd) {
+    const float* o = oacc[nd];
     if constexpr (sizeof(T) == 4) {
       if (out_split) {
         float h[4];
