@@ -186,8 +186,10 @@ class MaxViT(nn.Module):
         return self
 
     def _pack_key(self, dtype):
-        return (dtype, self.fp32_x3, tuple((p.data_ptr(), p._version) for p in self.parameters()),
-                tuple((b.data_ptr(), b._version) for b in self.buffers()))
+        # train() mode never reads the folded eval-BatchNorm constants (the only users of the buffers): keyed on the parameters
+        # alone there, or the running-statistics update of every forward would force a second full pack in the backward pass
+        return (dtype, self.fp32_x3, self.training, tuple((p.data_ptr(), p._version) for p in self.parameters()),
+                () if self.training else tuple((b.data_ptr(), b._version) for b in self.buffers()))
 
     @torch.no_grad()
     def packed(self, dtype):
@@ -199,13 +201,13 @@ class MaxViT(nn.Module):
             seq = conv.fn if isinstance(conv, MBConvResidual) else conv
             P = {"residual": isinstance(conv, MBConvResidual)}
             P["w_exp"] = seq[0].weight.flatten(1).to(dtype).contiguous()                     # (hidden, dim)
-            P["s_exp"], P["t_exp"] = _fold_bn(seq[0].bias, seq[1])
+            P["s_exp"], P["t_exp"] = (None, None) if self.training else _fold_bn(seq[0].bias, seq[1])
             P["w_dw"] = seq[3].weight.float().reshape(seq[3].weight.shape[0], 9).t().contiguous()   # [9][hidden]
-            P["s_dw"], P["t_dw"] = _fold_bn(seq[3].bias, seq[4])
+            P["s_dw"], P["t_dw"] = (None, None) if self.training else _fold_bn(seq[3].bias, seq[4])
             P["se_w1"] = seq[6].gate[1].weight.float().contiguous()
             P["se_w2"] = seq[6].gate[3].weight.float().contiguous()
             P["w_proj"] = seq[7].weight.flatten(1).to(dtype).contiguous()                    # (dim, hidden)
-            P["s_proj"], P["t_proj"] = _fold_bn(seq[7].bias, seq[8])
+            P["s_proj"], P["t_proj"] = (None, None) if self.training else _fold_bn(seq[7].bias, seq[8])
             # training (batch-statistic BatchNorm: nothing is folded)
             P["b_exp"], P["b_dw"], P["b_proj"] = (seq[i].bias.float().contiguous() for i in (0, 3, 7))
             P["w_dw_flip"] = P["w_dw"].flip(0).contiguous()                                  # dgrad = correlation with flipped taps
