@@ -136,7 +136,9 @@ class GradSync:
 def _pack_dgrad3x3(w, dtype):
     """(Cout,Cin,3,3) -> [Cin][9*Cout] with K index tap*Cout + co (dX = conv^T: negated tap shifts)"""
     co, ci = w.shape[:2]
-    return w.permute(1, 2, 3, 0).reshape(ci, 9 * co).to(dtype).contiguous()
+    out = torch.empty(ci, 3, 3, co, dtype=dtype, device=w.device)
+    out.copy_(w.permute(1, 2, 3, 0))                             # permutation and conversion in one pass
+    return out.view(ci, 9 * co)
 
 
 def _unpack_wgrad3x3(dWt, co, ci_pad, ci):
