@@ -132,12 +132,15 @@ def test_config4_full_depth_default_precision_vs_cpu_oracle():
     assert build(synth.CFG_12HR, 0, None).precision == "bf16"
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32_conv"])
 @pytest.mark.parametrize("name", ["metnet3_small128.pt", "metnet3_12hr_b1.pt", "metnet3_wide256.pt", "metnet3_wide512.pt"])
-def test_tf32_mode_golden_from_reference(golden, name):
-    """set_precision('tf32'): fp32 storage, every contraction on tcgen05 kind::tf32 -- 3e-3 on the goldens (bf16 mode: 7e-3)"""
+def test_tf32_mode_golden_from_reference(golden, name, precision):
+    """set_precision('tf32'): fp32 storage, every contraction on tcgen05 kind::tf32 -- 3e-3 on the goldens (bf16 mode: 7e-3);
+    'tf32_conv': tf32 convolutions, the MaxViT block in fp32 with 3xTF32 split projections and attention core (the default of wide
+    networks, here also on the 128-channel goldens)"""
     f = golden(name)
     cfg = synth.GridConfig(**f["cfg"])
-    m = build(cfg, f["weight_seed"], "tf32")
+    m = build(cfg, f["weight_seed"], precision)
     x, ts, _ = synth.make_inputs(cfg, f["B"], seed=f["input_seed"])
     with torch.no_grad():
         y = m(x.cuda(), timestamps=ts.cuda())
