@@ -330,6 +330,50 @@ def run_other_config(args, dev, rank, world):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     fields = world * B * L * args.steps
     value = fields / (ms * 1e-3)
+    # per-entry-point CUDA events on two extra steps outside the timed region: breakdown + roofline of the dominant entry
+    breakdown, roof = None, None
+    if rank == 0:
+        import re
+        _lib.TRACE = []
+        with torch.no_grad():
+            for _ in range(2):
+                model(x, timestamps=ts)
+        torch.cuda.synchronize()
+        trace, _lib.TRACE = _lib.TRACE, None
+        per = {}
+        for name, tag, a, b in trace:
+            per.setdefault(f"{name}[{tag}]" if name == "vg_gemm_fwd" else name, []).append(a.elapsed_time(b))
+        tot = sum(sum(v) for v in per.values())
+        top = sorted(per.items(), key=lambda kv: -sum(kv[1]))
+        breakdown = [{"entry": k, "launches_per_step": len(v) // 2, "ms_per_step": sum(v) / 2, "share": sum(v) / tot} for k, v in top[:8]]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        name, v = top[0]
+        avg = sum(v) / len(v)
+        mt = re.search(r"M=(\d+) K=(\d+)x(\d+) N=(\d+) (\S+)( 3xTF32)?", name)
+        if mt:                                                  # a GEMM: 2 M K N; a 3xTF32 product executes three times its algorithmic FLOPs
+            Mg, taps, Kg, Ng = (int(mt.group(i)) for i in (1, 2, 3, 4))
+            split, tf32 = mt.group(6) is not None, mt.group(5) == "tf32"
+            algo = 2.0 * Mg * taps * Kg * Ng / (3 if split else 1)
+            pk = peak_tf / 2 if tf32 else peak_tf
+            roof = {"kernel": f"gemm_tc_kernel via {name}", "bound": "tensor", "achieved": algo / (avg * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                    "frac": algo / (avg * 1e-3) / 1e12 / pk, "executed_tflops": algo * (3 if split else 1) / (avg * 1e-3) / 1e12,
+                    "avg_launch_ms": avg, "launches_per_step": len(v) // 2, "share_of_step": sum(v) / tot, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" + (" / 2 (kind::tf32 runs at half the bf16 rate)" if tf32 else "")
+                                   + ("; achieved counts the fp32 product's FLOPs, the 3xTF32 split executes three times as many" if split else "")}
+        elif name.startswith("vg_conv3x3_ln"):
+            C = cfg.dim
+            algo = 2.0 * min(B * L, model.max_fields[model.compute_dtype]) * (cfg.H + (14 - cfg.H) % 14) * (cfg.W + (14 - cfg.W) % 14) * 9 * C * C
+            tf32 = model.conv_tf32
+            pk = peak_tf / 2 if tf32 else peak_tf
+            roof = {"kernel": name, "bound": "tensor", "achieved": algo / (avg * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                    "frac": algo / (avg * 1e-3) / 1e12 / pk, "avg_launch_ms": avg, "launches_per_step": len(v) // 2, "share_of_step": sum(v) / tot,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" + (" / 2 (kind::tf32)" if tf32 else ""),
+                    "note": "algorithmic FLOPs of the padded frame (multiple of 14 in both directions) of the fields one launch covers"}
     opt_in = None
     if precision != "bf16":
         # the reduced-precision mode of a wide network is opt-in: it misses the 1e-2 tolerance at this depth
@@ -387,7 +431,7 @@ def run_other_config(args, dev, rank, world):
             "clocks": clk.summary(),
             "e2e": {"value": fields / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": x_host.numel() * 4 + ts_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "roofline": roof, "breakdown": breakdown,
             "model_tflops_reference_graph": value / world * gf_ref / 1e3,
             "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "train": train,

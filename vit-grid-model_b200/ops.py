@@ -117,6 +117,9 @@ def cond_mlp(cond, W0, b0, W1=None, b1=None, pre_relu=False):
     return out
 
 
+_X3_TAG = ""      # trace tag suffix of the GEMM issued by gemm(x3=True)
+
+
 def split3_tf32(x, pattern):
     """fp32 [rows][K] -> fp32 [rows][3K]: (hi | hi | lo) for the left operand (pattern 0), (hi | lo | hi) for the [N][K] weights
     (pattern 1), hi = x truncated to tf32; one tf32 GEMM over 3K then computes hi*hi + hi*lo + lo*hi (include/vitgrid.h)"""
@@ -132,9 +135,14 @@ def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per
     x3 (fp32 operands, no tf32): near-fp32 product (~1e-5, see include/vitgrid.h) on the tensor cores by the 3xTF32 operand split
     instead of the SIMT kernel; Wt_x3: the weights already split (split3_tf32(Wt, 1), cached by the caller)"""
     if x3 and not tf32 and A.dtype == torch.float32 and ntaps == 1 and A.is_contiguous() and Wt.is_contiguous() and A.shape[1] % 32 == 0:
-        return gemm(split3_tf32(A, 0), Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), M=M, rows_per_batch=rows_per_batch, b_rows_per_batch=b_rows_per_batch,
-                    bias=bias, scale=scale, shift=shift, act=act, res=res, out=out, out_f32=out_f32, n_out=n_out, tf32=True,
-                    out_dtype=out_dtype)
+        global _X3_TAG
+        _X3_TAG = " 3xTF32"
+        try:
+            return gemm(split3_tf32(A, 0), Wt_x3 if Wt_x3 is not None else split3_tf32(Wt, 1), M=M, rows_per_batch=rows_per_batch, b_rows_per_batch=b_rows_per_batch,
+                        bias=bias, scale=scale, shift=shift, act=act, res=res, out=out, out_f32=out_f32, n_out=n_out, tf32=True,
+                        out_dtype=out_dtype)
+        finally:
+            _X3_TAG = ""
     dtype = A.dtype
     rowsA, Ca = A.shape
     M = rowsA if M is None else M
@@ -143,7 +151,7 @@ def gemm(A, Wt, *, ntaps=1, tap_shift=(0,), M=None, rows_per_batch=0, b_rows_per
         out = torch.empty(M, Ntot, dtype=out_dtype or (torch.float32 if out_f32 else dtype), device=A.device)
     shifts = (ctypes.c_int * ntaps)(*tap_shift)
     keep, sp, sn = _scratch(dtype, M * Ntot, A.device, tf32)
-    _lib.TRACE_TAG = f"M={M} K={ntaps}x{Ca} N={Ntot} {'tf32' if tf32 else str(dtype)[6:]}"
+    _lib.TRACE_TAG = f"M={M} K={ntaps}x{Ca} N={Ntot} {'tf32' if tf32 else str(dtype)[6:]}{_X3_TAG}"
     res_f32 = int(res is not None and res.dtype == torch.float32)
     _lib.call("vg_gemm_fwd", _gemm_code(dtype, tf32), A.data_ptr(), rowsA, Ca, Wt.data_ptr(), Ntot, ntaps, shifts, M,
               rows_per_batch, b_rows_per_batch, _p(bias), _p(scale), _p(shift), act, _p(res),
