@@ -219,11 +219,14 @@ VG_API int vg_attn_fused_fwd(const float* x, float* x_out, const float* reg_in, 
  * residual add.  QKV projection, QK^T and PV run as tcgen05 kind::f16 (fp16 / bf16 operands), the out-projection as
  * kind::tf32 on the O_h accumulator read in place from TMEM; two compute groups of 8 warps alternate heads.  Same operand
  * formats (wqkv_h, wout_h, head_tab), dropout hash and constraints as vg_attn_fused_fwd, plus: heads even.
- * A caller that needs the input afterwards (training) copies it first and passes the copy. */
+ * A caller that needs the input afterwards (training) copies it first and passes the copy.
+ * logit_bound: 0, or a bound of |logit + bias| * log2(e) over all heads that the caller derived from the weights (q-hat and k-hat are
+ * unit vectors, maxvit.py:26-30: |logit| <= dh * max|gamma_q * gamma_k|); at most 115 lets the kernel skip the running maximum of the
+ * softmax (2^-115 is a normal fp32 number, 53 * 2^115 is finite), the result is the same softmax. */
 VG_API int vg_attn_fused2_fwd(float* xio, const float* reg_in, int reg_per_field, float* reg_out, const float* film,
                        const void* wqkv_h, const float* wout_h, const float* head_tab, int N, int Hl, int Wl, int C, int win,
                        int R, int grid_mode, int heads, int dh, float ln_eps, long long drop_seed, int drop_salt,
-                       int drop_thresh, void* stream);
+                       int drop_thresh, float logit_bound, void* stream);
 
 /* maxvit.py:326 -- mean of the register tokens over windows: (N,nwin,R*C) -> (N,R*C), fp32 */
 VG_API int vg_reg_mean_fwd(const float* in, float* out, int N, int nwin, int RC, void* stream);

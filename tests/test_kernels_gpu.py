@@ -293,6 +293,13 @@ def test_attention_fused(grid_mode, N, H, W):
                                   w, R, grid_mode, True, heads, dh)
     assert rel_err(x_out.reshape(N, H * W, C), ref_x) < 4e-3
     assert rel_err(reg_out, ref[:, :R]) < 4e-3
+    # the same softmax without the running maximum (the caller's logit bound proves exp2 stays inside fp32)
+    bound = o.attn_logit_bound(sd["rel_pos_bias.weight"].cuda(), sd["q_norm.gamma"].cuda(), sd["k_norm.gamma"].cuda(), dh)
+    assert 0 < bound <= 115
+    x_nm, reg_nm = o.attn_fused(x.cuda(), reg.cuda(), film, wqkv_h.contiguous().cuda(), wout_h.cuda(), head_tab,
+                                w, R, grid_mode, True, heads, dh, logit_bound=bound)
+    assert rel_err(x_nm.reshape(N, H * W, C), ref_x) < 4e-3 and rel_err(reg_nm, ref[:, :R]) < 4e-3
+    assert rel_err(x_nm, x_out) < 1e-3
 
 
 @pytest.mark.parametrize("grid_mode", [False, True])
@@ -312,7 +319,7 @@ def test_attention_fused_is_deterministic(grid_mode, drop):
     tab = o.pack_head_tables(rnd(170, heads, seed=16).cuda(), qg, kg)
     ref = None
     for _ in range(6):
-        y, r = o.attn_fused(x, reg, film, wqkv, wout, tab, w, R, grid_mode, True, heads, dh, drop=drop)
+        y, r = o.attn_fused(x, reg, film, wqkv, wout, tab, w, R, grid_mode, True, heads, dh, drop=drop, logit_bound=0.0 if drop[2] else 110.0)
         torch.cuda.synchronize()
         if ref is None:
             ref = (y.clone(), r.clone())

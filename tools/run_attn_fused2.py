@@ -17,18 +17,19 @@ wout = (torch.randn(heads, C, dh, generator=g) / 32).cuda()
 qg, kg = torch.ones(heads * dh).cuda(), torch.ones(heads * dh).cuda()
 bias = torch.randn(170, heads, generator=g).cuda()
 tab = ops.pack_head_tables(bias, qg, kg)
+lb = ops.attn_logit_bound(bias, qg, kg, dh) if os.environ.get("NOMAX", "0") == "1" else 0.0      # NOMAX=1: softmax without the running maximum
 best = 1e9
 for _ in range(iters):
     xin = x.clone()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    y, r = ops.attn_fused(xin, reg, film, wqkv, wout, tab, w, R, grid, True, heads, dh, inplace=True)
+    y, r = ops.attn_fused(xin, reg, film, wqkv, wout, tab, w, R, grid, True, heads, dh, inplace=True, logit_bound=lb)
     e1.record()
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 gf = 2.0125 * N
-print(f"{'v1' if ops._ATTN_V1 else 'v2'} {'grid' if grid else 'block'} N={N} windows={N*30} best ms={best:.3f}  {gf / best:.1f} TFLOP/s algorithmic  finite={torch.isfinite(y).all().item()}")
+print(f"logit_bound={lb:.1f} {'v1' if ops._ATTN_V1 else 'v2'} {'grid' if grid else 'block'} N={N} windows={N*30} best ms={best:.3f}  {gf / best:.1f} TFLOP/s algorithmic  finite={torch.isfinite(y).all().item()}")
 
 if not ops._ATTN_V1:
     dbg = torch.zeros(3 * 128 * 8 + 16 * 128 * 2, dtype=torch.int64, device="cuda")

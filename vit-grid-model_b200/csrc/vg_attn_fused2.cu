@@ -225,7 +225,10 @@ __device__ __forceinline__ WinPos win_pos(const Fused2Params& p, long long tile,
 
 // DROP: training instantiation with the dropout code; DBG: clock-stamp instrumentation (tools/run_attn_fused2.py) -- both
 // compiled out of the production instantiation, whose cold paths share an instruction cache with five hot role loops
-template <bool DROP, bool DBG>
+// NOMAX: the caller proved |logit + bias| <= 115 in the exp2 domain (unit q-hat / k-hat: |logit| <= log2e * dh * max|gamma_q gamma_k|), so
+// neither exp2 (>= 2^-115, a normal number) nor the row sum of 53 of them (< 2^121) can leave the fp32 range and the softmax skips the
+// running maximum: 32 FMNMX + 16 packed subtractions per thread and head, and two exp2 of the pair exchange
+template <bool DROP, bool DBG, bool NOMAX>
 __global__ void __launch_bounds__(fb::THREADS, 1)
 attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_constant__ CUtensorMap mapWo,
                    const __grid_constant__ CUtensorMap mapX, const Fused2Params p) {
@@ -662,7 +665,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive_a(a_s_free);                          // S(j+1) may overwrite the accumulator
         const uint32_t brow = tab + b_off;
-        float m = -INFINITY;
+        float m = NOMAX ? 0.f : -INFINITY;
         if (ch == 0) {
           // keys 0..3 are register tokens, keys 4..31 are window rows aj = 0..3
           const float t169 = tabf[TAB_T169];
@@ -675,8 +678,10 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
             float* q = sc + 4 + aj * 7;
             q[0] += b0.x; q[1] += b0.y; q[2] += b0.z; q[3] += b0.w; q[4] += b1.x; q[5] += b1.y; q[6] += b1.z;
           }
+          if (!NOMAX) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) m = fmaxf(m, sc[jj]);
+            for (int jj = 0; jj < 32; ++jj) m = fmaxf(m, sc[jj]);
+          }
         } else {
           // keys 32..52 are window rows aj = 4..6; keys 53..63 are padding
 #pragma unroll
@@ -686,8 +691,10 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
             float* q = sc + (aj - 4) * 7;
             q[0] += b0.x; q[1] += b0.y; q[2] += b0.z; q[3] += b0.w; q[4] += b1.x; q[5] += b1.y; q[6] += b1.z;
           }
+          if (!NOMAX) {
 #pragma unroll
-          for (int jj = 0; jj < 21; ++jj) m = fmaxf(m, sc[jj]);
+            for (int jj = 0; jj < 21; ++jj) m = fmaxf(m, sc[jj]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_a(a_tab_free);                        // last read of this head's tables
@@ -700,18 +707,18 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         if (ch == 0) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            sc2[k] = fadd2b(sc2[k], nm);
+            if (!NOMAX) sc2[k] = fadd2b(sc2[k], nm);
             sc2[k].x = ex2f(sc2[k].x); sc2[k].y = ex2f(sc2[k].y);
             if (k & 1) acc1 = fadd2b(acc1, sc2[k]); else acc0 = fadd2b(acc0, sc2[k]);
           }
         } else {
 #pragma unroll
           for (int k = 0; k < 10; ++k) {
-            sc2[k] = fadd2b(sc2[k], nm);
+            if (!NOMAX) sc2[k] = fadd2b(sc2[k], nm);
             sc2[k].x = ex2f(sc2[k].x); sc2[k].y = ex2f(sc2[k].y);
             if (k & 1) acc1 = fadd2b(acc1, sc2[k]); else acc0 = fadd2b(acc0, sc2[k]);
           }
-          sc[20] = ex2f(sc[20] - m); sc[21] = 0.f;
+          sc[20] = ex2f(NOMAX ? sc[20] : sc[20] - m); sc[21] = 0.f;
           acc0 = fadd2b(acc0, sc2[10]);
 #pragma unroll
           for (int k = 11; k < 16; ++k) sc2[k] = make_float2(0.f, 0.f);
@@ -721,9 +728,14 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         sts64f(red + ch * 8, m, s_own);
         pair_bar(grp, lg);                                               // partner's (max, sum) is visible
         const float2 oth = lds64f(red + (ch ^ 1) * 8);
-        const float mrow = fmaxf(m, oth.x);
-        const float f_own = ex2f(m - mrow), f_oth = ex2f(oth.x - mrow);
-        const float inv_sum = f_own * rcpf(fmaf(s_own, f_own, oth.y * f_oth));
+        float inv_sum;
+        if (NOMAX) {
+          inv_sum = rcpf(s_own + oth.y);
+        } else {
+          const float mrow = fmaxf(m, oth.x);
+          const float f_own = ex2f(m - mrow), f_oth = ex2f(oth.x - mrow);
+          inv_sum = f_own * rcpf(fmaf(s_own, f_own, oth.y * f_oth));
+        }
         if (DROP && p.drop.thresh) {                                     // nn.Dropout on the probabilities (maxvit.py:146, 209)
           const float ks = inv_sum * p.drop.scale;
           const uint32_t rid = drop_row(wdx, i);
@@ -834,7 +846,7 @@ int attn_partition_map(CUtensorMap* m, const float* x, const AttnGeom& g) {
 // wqkv_h: fp16 [heads*96][128]; wout_h: fp32 [heads*128][32]; xio: residual stream, updated in place
 int attn_fused2_run(float* xio, const float* reg_in, int reg_per_field, float* reg_out, const float* film, const void* wqkv_h,
                     const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps, unsigned seed,
-                    unsigned salt, int drop_thresh, cudaStream_t st) {
+                    unsigned salt, int drop_thresh, float logit_bound, cudaStream_t st) {
   if (drop_thresh < 0 || drop_thresh > 255) return set_error("attn_fused2: dropout threshold %d outside [0, 255]", drop_thresh);
   if (g.C != fb::C || dh != fb::DH) return set_error("attn_fused2: needs C=128, dim_head=32 (got C=%d, dh=%d)", g.C, dh);
   if (heads < 2 || (heads & 1)) return set_error("attn_fused2: the two compute groups alternate heads: heads must be even (got %d)", heads);
@@ -857,18 +869,23 @@ int attn_fused2_run(float* xio, const float* reg_in, int reg_per_field, float* r
   static bool attr[64] = {};
   if (dev < 0 || dev >= 64) return set_error("attn_fused2: device ordinal %d out of range", dev);
   if (!attr[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fused2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused2_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("attn_fused2 smem attr: %s", cudaGetErrorString(e));
     attr[dev] = true;
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (p.n_windows + 1) / 2;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  if (drop_thresh) attn_fused2_kernel<true, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
-  else if (p.dbg) attn_fused2_kernel<false, true><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
-  else attn_fused2_kernel<false, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  // logit_bound: the caller's bound of |logit + bias| in the exp2 domain (0 = none given); VG_ATTN2_NOMAX=0 keeps the running maximum
+  static const bool nomax_off = getenv("VG_ATTN2_NOMAX") && atoi(getenv("VG_ATTN2_NOMAX")) == 0;
+  const bool nomax = !nomax_off && logit_bound > 0.f && logit_bound <= 115.f;
+  if (drop_thresh) attn_fused2_kernel<true, false, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  else if (p.dbg) attn_fused2_kernel<false, true, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  else if (nomax) attn_fused2_kernel<false, false, true><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
+  else attn_fused2_kernel<false, false, false><<<grid, fb::THREADS, fb::SMEM_BYTES, st>>>(mq, mo, mx, p);
   return check_launch("attn_fused2_kernel");
 }
 

@@ -115,7 +115,7 @@ int attn_fused_run(const float* x, float* x_out, const float* reg_in, int reg_pe
 // second-generation fused attention (vg_attn_fused2.cu): in place on the residual stream, partition through TMA tensor maps
 int attn_fused2_run(float* xio, const float* reg_in, int reg_per_field, float* reg_out, const float* film, const void* wqkv_h,
                     const float* wout_h, const float* head_tab, const AttnGeom& g, int heads, int dh, float ln_eps, unsigned seed,
-                    unsigned salt, int drop_thresh, cudaStream_t st);
+                    unsigned salt, int drop_thresh, float logit_bound, cudaStream_t st);
 int attn_partition_map(CUtensorMap* m, const float* x, const AttnGeom& g);
 
 // ---- training (vg_wgrad.cu, vg_bwd.cu, vg_bwd_vit.cu)

@@ -235,6 +235,10 @@ class MaxViT(nn.Module):
                 P[name]["wout_h"] = att.to_out[0].weight.float().reshape(-1, hd, dh).permute(1, 0, 2).contiguous()
                 if att.window_size == 7 and dh == 32:
                     P[name]["head_tab"] = ops.pack_head_tables(P[name]["bias_table"], P[name]["q_gamma"], P[name]["k_gamma"])
+                    # inference packs once per weight version: one host read for the logit bound that lets the fused kernel skip the
+                    # running maximum of its softmax (train() mode re-packs every step and keeps the maximum)
+                    P[name]["logit_bound"] = 0.0 if self.training else ops.attn_logit_bound(P[name]["bias_table"], P[name]["q_gamma"],
+                                                                                            P[name]["k_gamma"], dh)
             P["reg"] = self.register_tokens[li].float().contiguous()
             if self.fp32_x3 and dtype == torch.float32:              # 3xTF32 right operands [hi | lo | hi], split once per weight version
                 P["w_exp_x3"] = ops.split3_tf32(P["w_exp"], 1)
@@ -252,7 +256,7 @@ class MaxViT(nn.Module):
         if self.fused_attention and self.tf32 and C == 128 and self.dim_head == 32 and w == 7 and R == 4 and self.heads >= 4:
             # x is a temporary of forward_cl (MBConv output / the previous attention's result): updated in place
             return ops.attn_fused(x, reg_in, film, P["wqkv_h"], P["wout_h"], P["head_tab"], w, R, grid_mode, want_reg_out,
-                                  self.heads, self.dim_head, inplace=True)
+                                  self.heads, self.dim_head, inplace=True, logit_bound=P.get("logit_bound", 0.0))
         tokens = ops.attn_gather(x, reg_in, film, w, R, grid_mode)
         # qkv_exact: the QKV projection alone in exact fp32 -- its rounding error is multiplied by the un-scaled logits
         # (+-32 gamma_q gamma_k, maxvit.py:26-30,203) before the softmax; every other contraction of the block stays tf32

@@ -345,8 +345,15 @@ def pack_head_tables(bias_table, q_gamma, k_gamma, win=7):
     return torch.cat([tab.reshape(heads, -1), t_last, qg * kg * qg.shape[1], torch.zeros_like(kg)], dim=1).contiguous()
 
 
+def attn_logit_bound(bias_table, q_gamma, k_gamma, dh):
+    """bound of |logit + bias| in the exp2 domain for vg_attn_fused2_fwd: q-hat and k-hat are unit vectors times sqrt(dh) * gamma
+    (maxvit.py:26-30), so |logit| <= dh * max|gamma_q gamma_k|; 2 % slack for the fp16 operands.  One host sync: call at pack time."""
+    g = (q_gamma.float().reshape(-1, dh) * k_gamma.float().reshape(-1, dh)).abs().max()
+    return float(1.02 * 1.4426950408889634 * (dh * g + bias_table.float().abs().max()).item())
+
+
 def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, want_reg_out, heads, dh, eps=1e-5, drop=(0, 0, 0),
-               inplace=False):
+               inplace=False, logit_bound=0.0):
     """whole attention layer (+ residual) in one kernel; x CL (N,Hl,Wl,128) fp32.
     drop = (seed, salt, T): training dropout with probability T/256 on the probabilities and the to_out output.
     The kernel works in place on the residual stream (its TMA reduce-store performs the residual add): inplace=True lets it
@@ -367,7 +374,7 @@ def attn_fused(x, reg_in, film, wqkv_h, wout_h, head_tab, win, R, grid_mode, wan
     xio = x if inplace else x.clone()
     _lib.call("vg_attn_fused2_fwd", xio.data_ptr(), reg_in.data_ptr(), int(reg_in.dim() == 3), _p(reg_out), film.data_ptr(),
               wqkv_h.data_ptr(), wout_h.data_ptr(), head_tab.data_ptr(), N, Hl, Wl, C, win, R, int(grid_mode), heads, dh, float(eps),
-              int(drop[0]), int(drop[1]), int(drop[2]), _st())
+              int(drop[0]), int(drop[1]), int(drop[2]), float(logit_bound), _st())
     return xio, reg_out
 
 
