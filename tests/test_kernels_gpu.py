@@ -626,3 +626,18 @@ def test_attn_core_split_output_is_the_split_of_the_plain_output():
     plain = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, x3=True)
     split = o.attn_core(qkv, qg, kg, bt, N, H, W, w, R, heads, dh, x3=True, split_out=True)
     assert torch.equal(split, o.split3_tf32(plain, 0))
+
+
+def test_new_entry_points_reject_bad_arguments():
+    """error behaviour of the C ABI: bad codes come back as VitGridError with vg_last_error()'s text, nothing is launched"""
+    from vit_grid_model_b200 import _lib
+    o = ops()
+    x = rnd(8, 64, seed=1).cuda()
+    with pytest.raises(_lib.VitGridError, match="pattern"):
+        o.split3_tf32(x, 2)
+    out = torch.empty(8, 4, device="cuda")
+    with pytest.raises(_lib.VitGridError, match="activation"):
+        _lib.call("vg_dense_rows_fwd", x.data_ptr(), 8, 64, 0, x.data_ptr(), None, 4, 7, out.data_ptr(), None)
+    qkv = rnd(53, 3 * 64, seed=2).cuda()
+    with pytest.raises(_lib.VitGridError, match="dtype code"):
+        _lib.call("vg_attn_core_fwd", 3, qkv.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 7, 7, 7, 4, 1, 64, out.data_ptr(), 0, 0, 0, None)

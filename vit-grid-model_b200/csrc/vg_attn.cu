@@ -466,6 +466,7 @@ static int core_mma_launch(const void* qkv, const float* qg, const float* kg, co
 int attn_core_run(int dtype, const void* qkv, const float* qgamma, const float* kgamma, const float* bias_table,
                   const AttnGeom& g, int heads, int dh, void* out, unsigned seed, unsigned salt, int drop_thresh, cudaStream_t st) {
   if (g.S() > 128) return set_error("attn_core: sequence %d too long", g.S());
+  if (dtype != 0 && dtype != 1 && dtype != 2 && dtype != 4 && dtype != 6) return set_error("attn_core: dtype code %d (0 bf16, 1 fp32, 2 / 6 fp32 3xTF32, 4 fp32 tf32)", dtype);
   if (drop_thresh < 0 || drop_thresh > 255 || (drop_thresh && g.S() > 64)) return set_error("attn_core: bad dropout threshold %d (or sequence > 64)", drop_thresh);
   DropCfg drop;
   drop.seed = seed; drop.salt = salt; drop.thresh = drop_thresh; drop.scale = 256.0f / (256.0f - (float)drop_thresh);

@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(256) split3_tf32_kernel(const float* __restric
 }
 
 int split3_tf32_run(const float* in, long long rows, int K, float* out, int pattern, cudaStream_t st) {
-  if (K % 4) return set_error("split3_tf32: K %% 4 != 0");
+  if (K % 4 || (((uintptr_t)in | (uintptr_t)out) & 15)) return set_error("split3_tf32: K = %d must be a multiple of 4 and both pointers 16-byte aligned", K);
+  if (pattern != 0 && pattern != 1) return set_error("split3_tf32: pattern %d (0 = [hi|hi|lo], 1 = [hi|lo|hi])", pattern);
   if (rows <= 0) return 0;
   const long long total = rows * (K / 4);
   split3_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, rows, K, out, pattern);
@@ -877,6 +878,7 @@ int cond_mlp_run(const float* cond, int N, int cd, int pre_relu, const float* W0
 
 int dense_rows_run(const float* in, int N, int cd, int pre_relu, const float* W, const float* b, int od, int act, float* out,
                    cudaStream_t st) {
+  if (act < 0 || act > 3) return set_error("dense_rows: activation code %d (0 none, 1 ReLU, 2 SiLU, 3 sigmoid)", act);
   const int vec = cd % 4 == 0 && (((uintptr_t)in | (uintptr_t)W) & 15) == 0;
   if (N <= 0 || od <= 0) return 0;
   constexpr int NF = 4;
