@@ -737,13 +737,17 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
           inv_sum = f_own * rcpf(fmaf(s_own, f_own, oth.y * f_oth));
         }
         if (DROP && p.drop.thresh) {                                     // nn.Dropout on the probabilities (maxvit.py:146, 209)
+          // one hash -> four mask bytes -> per-byte compare (0xFF where kept) -> PRMT sign-replicate -> AND: the backward kernel's form
           const float ks = inv_sum * p.drop.scale;
-          const uint32_t rid = drop_row(wdx, i);
+          const float2 ks2 = make_float2(ks, ks);
+          const uint32_t rid = drop_row(wdx, i), th4 = (uint32_t)p.drop.thresh * 0x01010101u;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) sc2[k] = fmul2b(sc2[k], ks2);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const uint32_t hsh = drop_hash(p.drop.seed, rid, drop_group_prob(p.drop.salt, h, ch * 8 + c));
+            const uint32_t keep = __vcmpgeu4(drop_hash(p.drop.seed, rid, drop_group_prob(p.drop.salt, h, ch * 8 + c)), th4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sc[4 * c + k] *= (int)((hsh >> (8 * k)) & 255u) >= p.drop.thresh ? ks : 0.f;
+            for (int k = 0; k < 4; ++k) sc[4 * c + k] = __uint_as_float(__float_as_uint(sc[4 * c + k]) & __byte_perm(keep, 0u, 0x8888u + 0x1111u * k));
           }
         } else {
           const float2 is2 = make_float2(inv_sum, inv_sum);
