@@ -87,3 +87,29 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_attention_logit_bound_dominates_the_logits():
+    """ops.attn_logit_bound (host logic behind vg_attn_fused2_fwd's logit_bound): for random weights and inputs the bound must
+    dominate |q.k + bias| * log2(e) of maxvit.py:26-30,203 -- it is what allows the fused kernel to drop the softmax's running
+    maximum -- and the 3xTF32 operand split must reproduce its input exactly (hi + lo == x, hi has 13 zero low bits)."""
+    import math
+    import torch.nn.functional as F
+    from vit_grid_model_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    heads, dh, S, w = 4, 32, 53, 7
+    for trial in range(5):
+        qg = 0.5 + torch.rand(heads, dh, generator=g) * (1 + trial)
+        kg = 0.5 + torch.rand(heads, dh, generator=g)
+        table = torch.randn((2 * w - 1) ** 2 + 1, heads, generator=g) * (1 + trial)
+        q = torch.randn(3, heads, S, dh, generator=g) * 10 ** (trial - 2)
+        k = torch.randn(3, heads, S, dh, generator=g)
+        qn = F.normalize(q, dim=-1) * math.sqrt(dh) * qg[None, :, None, :]
+        kn = F.normalize(k, dim=-1) * math.sqrt(dh) * kg[None, :, None, :]
+        sim = qn @ kn.transpose(-1, -2)
+        worst = (sim.abs().max() + table.abs().max()).item() * 1.4426950408889634
+        bound = ops.attn_logit_bound(table, qg.reshape(-1), kg.reshape(-1), dh)
+        assert worst <= bound, (trial, worst, bound)
+    x = torch.randn(1000, generator=g) * torch.logspace(-20, 20, 1000)
+    hi = (x.view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(hi + (x - hi), x) and ((x - hi).abs() <= x.abs() * 2.0 ** -10).all()
