@@ -182,6 +182,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity, int tag
 }
 __device__ __forceinline__ void mbar_arrive_a(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
 __device__ __forceinline__ void sts64f(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ float lds32f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float2 lds64f(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -449,20 +455,23 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     const uint32_t red = s_base + RED_OFF + grp * 2048 + t * 16;             // this row: [2 threads] x (max, sum)
     const uint32_t a_stage = smem_u32(qkv_done + grp), a_qkv_free = smem_u32(qkv_free), a_s_done = smem_u32(s_done + grp);
     const uint32_t a_s_free = smem_u32(s_free), a_tab_free = smem_u32(tab_free + grp), a_pv_other = smem_u32(pv_done + (grp ^ 1));
-    float* lnred = reinterpret_cast<float*>(smem + RED_OFF) + 1024;          // [128][2] sums | [128][2] square sums
+    const uint32_t lnred = s_base + RED_OFF + 4096;                          // float [128][2] sums | [128][2] square sums
+    // barriers of the tile-boundary work by 32-bit shared address: generic pointers in this role made the compiler rebuild the 64-bit
+    // shared-window address (S2R SR_SWINHI, S2UR SR_CgaCtaId, 64-bit adds) in every head iteration
+    const uint32_t a_x_ready = smem_u32(x_ready), a_x_free = smem_u32(x_free), a_raw_full = smem_u32(raw_full), a_raw_consumed = smem_u32(raw_consumed);
+    const uint32_t a_epi_done = smem_u32(epi_done), a_tile_done = smem_u32(tile_done), a_out_free = smem_u32(out_free);
     const uint32_t b_off = is_reg ? (uint32_t)TAB_T169 * 4u : (uint32_t)(bi * TAB_SB + (ai + 6) * TAB_SR) * 4u;
     const uint32_t b_step = is_reg ? 0u : (uint32_t)TAB_SR * 4u;
     const uint32_t QK = s_base + QK_OFF + grp * 16384;
     const uint32_t VT = s_base + VT_OFF;
     const uint32_t tab = s_base + TAB_OFF + grp * TAB_FLOATS * 4;
-    const float* tabf = reinterpret_cast<const float*>(smem + TAB_OFF) + grp * TAB_FLOATS;
 
     // ---------------- tile prologue (group 0): LN + FiLM of the prefetched rows -> X tile (fp16, TMEM) ----------------
     auto build_x = [&](int tl) {
       const long long tile = blockIdx.x + (long long)tl * gridDim.x;
       const WinPos w = win_pos(p, tile, half);
-      if (tl > 0) mbar_wait_tag(x_free, (uint32_t)((tl - 1) & 1), 321);      // every QKV projection of the previous tile has retired
-      mbar_wait_tag(raw_full, (uint32_t)(tl & 1), 322);
+      if (tl > 0) mbar_wait_a(a_x_free, (uint32_t)((tl - 1) & 1), 321);      // every QKV projection of the previous tile has retired
+      mbar_wait_a(a_raw_full, (uint32_t)(tl & 1), 322);
       tc_fence_after();
       const bool valid = w.valid && i < SEQ;
       float4 v[16];
@@ -482,18 +491,20 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       }
 #pragma unroll
       for (int c = 0; c < 16; ++c) sm += (v[c].x + v[c].y) + (v[c].z + v[c].w);
-      lnred[t * 2 + ch] = sm;
+      sts32f(lnred + (t * 2 + ch) * 4, sm);
       pair_bar(grp, lg);
-      const float mean = (lnred[t * 2] + lnred[t * 2 + 1]) * (1.0f / C);
+      const float2 sm2 = lds64f(lnred + t * 8);
+      const float mean = (sm2.x + sm2.y) * (1.0f / C);
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
         ss += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
       }
-      lnred[256 + t * 2 + ch] = ss;
+      sts32f(lnred + (256 + t * 2 + ch) * 4, ss);
       pair_bar(grp, lg);
-      const float rstd = rsqrtf((lnred[256 + t * 2] + lnred[256 + t * 2 + 1]) * (1.0f / C) + p.ln_eps);
+      const float2 ss2 = lds64f(lnred + (256 + t * 2) * 4);
+      const float rstd = rsqrtf((ss2.x + ss2.y) * (1.0f / C) + p.ln_eps);
       const uint32_t film = s_base + FILM_OFF + half * 1024 + ch * 256;       // gamma at +0, beta at +512
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -513,17 +524,17 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
       tm_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(x_ready); mbar_arrive(raw_consumed); }
+      if (lane == 0) { mbar_arrive_a(a_x_ready); mbar_arrive_a(a_raw_consumed); }
     };
 
     // ---------------- tile epilogue (group 1): Out -> the staging planes -> TMA reduce-add through the partition map ----------------
     auto epilogue = [&](int tl) {
       const long long tile = blockIdx.x + (long long)tl * gridDim.x;
       const WinPos w = win_pos(p, tile, half);
-      mbar_wait_tag(tile_done, (uint32_t)(tl & 1), 331);
+      mbar_wait_a(a_tile_done, (uint32_t)(tl & 1), 331);
       // the staging buffer holds the NEXT tile's prefetched rows until group 0 has built its X tile
       const int last_build = (tl + 1 < my_tiles) ? tl + 1 : tl;
-      mbar_wait_tag(raw_consumed, (uint32_t)(last_build & 1), 332);
+      mbar_wait_a(a_raw_consumed, (uint32_t)(last_build & 1), 332);
       tc_fence_after();
       const bool valid = w.valid && i < SEQ;
 #pragma unroll 1
@@ -534,7 +545,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         if (q == 1) {                                          // Out is in registers: the next tile's out-projections may start
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(out_free);
+          if (lane == 0) mbar_arrive_a(a_out_free);
         }
         if (DROP && p.drop.thresh) {                           // nn.Dropout after to_out (maxvit.py:151)
           const uint32_t rid = drop_row(w.wdx, i);
@@ -575,7 +586,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         }
         bulk_commit();
         bulk_wait_read0();                                     // the staging planes may be overwritten (next prefetch)
-        mbar_arrive(epi_done);
+        mbar_arrive_a(a_epi_done);
       }
     };
 
@@ -668,7 +679,7 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
         float m = NOMAX ? 0.f : -INFINITY;
         if (ch == 0) {
           // keys 0..3 are register tokens, keys 4..31 are window rows aj = 0..3
-          const float t169 = tabf[TAB_T169];
+          const float t169 = lds32f(tab + TAB_T169 * 4);                  // (a generic load here made the compiler rebuild the 64-bit smem pointer per head)
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) sc[jj] += t169;
 #pragma unroll
