@@ -448,18 +448,22 @@ attn_fused2_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_const
     const int t = lg * 32 + lane;                            // tile row == TMEM lane
     const int half = t >> 6, i = t & 63;                     // window within the tile, token slot
     const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
-    const uint32_t s_base = smem_u32(smem);
+    // the aligned base as a 32-bit shared address computed from the raw array's shared address (a compile-time constant): derived
+    // from the generic pointer it made every barrier address below depend on the 64-bit shared-window chain (S2R SR_SWINHI, S2UR
+    // SR_CgaCtaId, two 64-bit adds), which the compiler rebuilt in every head iteration rather than keep ten addresses in registers
+    const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_bar = s_base + BAR_OFF;
     const bool is_reg = i < REG;
     const int ti = (i >= REG && i < SEQ) ? i - REG : 0;
     const int ai = ti / WIN, bi = ti - ai * WIN;
     const uint32_t red = s_base + RED_OFF + grp * 2048 + t * 16;             // this row: [2 threads] x (max, sum)
-    const uint32_t a_stage = smem_u32(qkv_done + grp), a_qkv_free = smem_u32(qkv_free), a_s_done = smem_u32(s_done + grp);
-    const uint32_t a_s_free = smem_u32(s_free), a_tab_free = smem_u32(tab_free + grp), a_pv_other = smem_u32(pv_done + (grp ^ 1));
+    const uint32_t a_stage = s_bar + 8 * (12 + grp), a_qkv_free = s_bar + 8 * 22, a_s_done = s_bar + 8 * (16 + grp);
+    const uint32_t a_s_free = s_bar + 8 * 23, a_tab_free = s_bar + 8 * (10 + grp), a_pv_other = s_bar + 8 * (20 + (grp ^ 1));
     const uint32_t lnred = s_base + RED_OFF + 4096;                          // float [128][2] sums | [128][2] square sums
     // barriers of the tile-boundary work by 32-bit shared address: generic pointers in this role made the compiler rebuild the 64-bit
     // shared-window address (S2R SR_SWINHI, S2UR SR_CgaCtaId, 64-bit adds) in every head iteration
-    const uint32_t a_x_ready = smem_u32(x_ready), a_x_free = smem_u32(x_free), a_raw_full = smem_u32(raw_full), a_raw_consumed = smem_u32(raw_consumed);
-    const uint32_t a_epi_done = smem_u32(epi_done), a_tile_done = smem_u32(tile_done), a_out_free = smem_u32(out_free);
+    const uint32_t a_x_ready = s_bar + 8 * 24, a_x_free = s_bar + 8 * 25, a_raw_full = s_bar + 8 * 26, a_raw_consumed = s_bar + 8 * 27;
+    const uint32_t a_epi_done = s_bar + 8 * 28, a_tile_done = s_bar + 8 * 29, a_out_free = s_bar + 8 * 30;
     const uint32_t b_off = is_reg ? (uint32_t)TAB_T169 * 4u : (uint32_t)(bi * TAB_SB + (ai + 6) * TAB_SR) * 4u;
     const uint32_t b_step = is_reg ? 0u : (uint32_t)TAB_SR * 4u;
     const uint32_t QK = s_base + QK_OFF + grp * 16384;
