@@ -115,7 +115,8 @@ def test_config4_full_depth_default_precision_vs_cpu_oracle():
     """BASELINE configs[4]: 512 channels, 32 heads x dim_head 64, MaxViT depth 4, 82 x 67 domain, one sample (12 fields).
     The DEFAULT precision of a wide network must meet the north-star 1e-2 against the CPU oracle.  Measured on B200
     (tools/config5_parity.py): bf16 3.6e-2, tf32 everywhere 1.4e-2, tf32 + exact-fp32 QKV projection 1.07e-2, tf32 convolutions +
-    exact-fp32 MaxViT 4.3e-3, exact fp32 2.1e-5 -- four stacked MaxViT layers with un-scaled +-32 gamma^2 logits amplify the
+    exact-fp32 SIMT MaxViT 4.3e-3, tf32 convolutions + 3xTF32 MaxViT projections and attention core (the default, 'tf32_conv') 4.4e-3,
+    exact fp32 2.2e-5 -- four stacked MaxViT layers with un-scaled +-32 gamma^2 logits amplify the
     operand rounding of every projection of the block.  Wide networks therefore default to 'tf32_conv'; the faster
     reduced-precision modes are opt-in there.  The exact-fp32 mode is held to the fp32 tolerance on the same case."""
     cfg = synth.GridConfig(dim=512, heads=32, dim_head=64, vit_depth=4)
